@@ -1,0 +1,168 @@
+"""Oracle evaluation of a likelihood *spec* (the un-collapsed chain, stage by stage, FP64 NumPy).
+
+TEST INFRASTRUCTURE — the checker, never the product (see oracle/core.py header).
+
+The spec (plain dicts / ndarrays; schema in DESIGN.md "likelihood spec") describes what the reference pipeline of
+SURVEY.md section 3.1 computes for one point:
+
+    tables(theta)                                (emulator predict | Kaiser | damped BAO -> FFTLog)
+ -> P = sum_terms coef(theta, x) * colvec * table        (tracer combine, reference full_shape.py:545-550, :628-634; bao.py:527-529, :905)
+ -> flat = W . P + offset                         (reference window.py:459-473)
+ -> d = concat(flat) - data;  logL = -1/2 d^T P d (reference likelihoods/base.py:658-664, :13-17)
+ -> analytic marginalisation over linear x        (reference likelihoods/base.py:129-200, :314-413)
+ -> + prior(theta)                                (reference parameter.py:1889-1897, :1994-2017)
+"""
+import numpy as np
+
+from . import core
+
+
+def _coef(term, X, names, xvalues):
+    """Per-point scalar coefficient of a term: scale * prod theta^pow * (solved value)."""
+    c = np.full(X.shape[0], float(term.get('scale', 1.)))
+    for name, power in term.get('factors', []):
+        c = c * X[:, names.index(name)]**power
+    if term.get('solved') is not None:
+        c = c * xvalues[term['solved']]
+    return c
+
+
+def theory_tables(theory, X, names):
+    """-> dict table name -> [N, nin]."""
+    kind = theory['kind']
+    cols = [names.index(p) for p in theory['params']]
+    Xe = X[:, cols]
+    if kind == 'taylor':
+        mono = core.taylor_monomials(Xe, theory['center'], theory['powers'])
+        return {name: mono @ deriv.reshape(deriv.shape[0], -1) for name, deriv in theory['tables'].items()}
+    if kind == 'mlp':
+        y = core.mlp_predict(Xe, theory['mlp'])
+        return {name: y[:, sl] for name, sl in theory['tables'].items()}
+    if kind == 'kaiser':
+        tpl = theory['template']
+        mu, wmu = core.legendre_weights(theory['ells'], theory['nmu'])
+        k = np.asarray(theory['k'], dtype='f8')
+        out = {name: np.empty((X.shape[0], len(theory['ells']) * k.size)) for name in ['pk_dd', 'pk_dt', 'pk_tt', 'pk11_l0']}
+        for ip in range(X.shape[0]):
+            p = dict(zip(theory['params'], Xe[ip]))
+            p = {**theory.get('defaults', {}), **p}
+            qpar, qper = core.ap_qpar_qper(tpl['apmode'], p, tpl.get('eta', 1. / 3.))
+            pk_t = tpl['pk_dd_fid'] * core.shapefit_factor(tpl['k'], p.get('dm', 0.), p.get('dn', 0.), tpl['a'], tpl['kp'])
+            f = tpl['f_fid'] * p.get('df', 1.)
+            tabs = core.kaiser_tables(k, mu, wmu, tpl['k'], pk_t, f, qpar, qper, p.get('sigmapar', 0.), p.get('sigmaper', 0.))
+            for name in ['pk_dd', 'pk_dt', 'pk_tt']:
+                out[name][ip] = tabs[name].ravel()
+            out['pk11_l0'][ip] = np.tile(tabs['pk_dd'][list(theory['ells']).index(0)], len(theory['ells'])) if 0 in theory['ells'] else 0.
+        return out
+    if kind == 'bao_xi':
+        tpl = theory['template']
+        mu, wmu = core.legendre_weights(theory['ells'], theory['nmu'])
+        p2c = core.PowerToCorr(theory['s'], theory['ells'], interp_order=1)
+        out = {'corr': np.empty((X.shape[0], len(theory['ells']) * len(theory['s'])))}
+        for ip in range(X.shape[0]):
+            p = dict(zip(theory['params'], Xe[ip]))
+            p = {**theory.get('defaults', {}), **p}
+            qpar, qper = core.ap_qpar_qper(tpl['apmode'], p, tpl.get('eta', 1. / 3.))
+            power = core.bao_damped_power(p2c.kin, mu, wmu, tpl['k'], tpl['pk_dd_fid'], tpl['pknow_dd_fid'], tpl['f_fid'] * p.get('df', 1.),
+                                          qpar, qper, b1=p.get('b1', 1.), dbeta=p.get('dbeta', 1.), sigmas=p.get('sigmas', 0.),
+                                          sigmapar=p.get('sigmapar', 9.), sigmaper=p.get('sigmaper', 6.), mode=theory.get('mode', ''),
+                                          smoothing_radius=theory.get('smoothing_radius', 15.))
+            out['corr'][ip] = p2c(power).ravel()
+        return out
+    if kind == 'bao_pk':
+        tpl = theory['template']
+        mu, wmu = core.legendre_weights(theory['ells'], theory['nmu'])
+        k = np.asarray(theory['k'], dtype='f8')
+        out = {'power': np.empty((X.shape[0], len(theory['ells']) * k.size))}
+        for ip in range(X.shape[0]):
+            p = dict(zip(theory['params'], Xe[ip]))
+            p = {**theory.get('defaults', {}), **p}
+            qpar, qper = core.ap_qpar_qper(tpl['apmode'], p, tpl.get('eta', 1. / 3.))
+            out['power'][ip] = core.bao_damped_power(k, mu, wmu, tpl['k'], tpl['pk_dd_fid'], tpl['pknow_dd_fid'], tpl['f_fid'] * p.get('df', 1.),
+                                                     qpar, qper, b1=p.get('b1', 1.), dbeta=p.get('dbeta', 1.), sigmas=p.get('sigmas', 0.),
+                                                     sigmapar=p.get('sigmapar', 9.), sigmaper=p.get('sigmaper', 6.), mode=theory.get('mode', ''),
+                                                     smoothing_radius=theory.get('smoothing_radius', 15.)).ravel()
+        return out
+    raise ValueError('unknown theory kind {}'.format(kind))
+
+
+def observable_flat(obs, X, names, xvalues, tables=None, only_solved=None):
+    """flat theory [N, nobs] of one observable.  ``only_solved``: return d flat / d x_name instead (Jacobian row)."""
+    if tables is None:
+        tables = theory_tables(obs['theory'], X, names)
+    P = np.zeros((X.shape[0], obs['nin']), dtype='f8')
+    for term in obs['terms']:
+        if only_solved is not None:
+            if term.get('solved') != only_solved: continue
+            c = _coef(term, X, names, {only_solved: 1.})
+        else:
+            c = _coef(term, X, names, xvalues)
+        vec = tables[term['table']] if term.get('table') is not None else 1.
+        if term.get('colvec') is not None:
+            vec = vec * term['colvec']
+        P = P + c[:, None] * vec
+    flat = P @ obs['wmatrix'].T if obs.get('wmatrix') is not None else P
+    if only_solved is None and obs.get('offset') is not None:
+        flat = flat + obs['offset']
+    return flat
+
+
+def _precision_blocks(spec):
+    """-> list of (slice over the joint data vector, precision block) -- one entry when the precision is joint."""
+    sizes = [len(obs['data']) for obs in spec['observables']]
+    prec = spec['precision']
+    if isinstance(prec, (list, tuple)):
+        out, start = [], 0
+        for size, pb in zip(sizes, prec):
+            out.append((slice(start, start + size), np.asarray(pb, dtype='f8')))
+            start += size
+        return out
+    return [(slice(0, sum(sizes)), np.asarray(prec, dtype='f8'))]
+
+
+def evaluate(spec, X, return_theory=False):
+    """X [N, d] -> dict(logposterior, loglikelihood, logprior, x_solved [N, ns], flattheory [N, n])."""
+    X = np.atleast_2d(np.asarray(X, dtype='f8'))
+    names = list(spec['params'])
+    solved = spec.get('solved', [])
+    x0 = {s['name']: float(s.get('value', 0.)) for s in solved}
+    N = X.shape[0]
+    flats, jacs = [], []
+    for obs in spec['observables']:
+        tables = theory_tables(obs['theory'], X, names)
+        flat = observable_flat(obs, X, names, x0, tables=tables)
+        if obs.get('transform') == 'cubic':
+            flat = core.cubic_transform(flat, obs['data'])
+        flats.append(flat)
+        if solved:
+            snames = {t.get('solved') for t in obs['terms']}
+            jacs.append(np.stack([observable_flat(obs, X, names, x0, tables=tables, only_solved=s['name']) if s['name'] in snames
+                                  else np.zeros_like(flat) for s in solved], axis=1))  # [N, ns, nobs]
+    flattheory = np.concatenate(flats, axis=-1)
+    flatdata = np.concatenate([obs['data'] for obs in spec['observables']])
+    flatdiff = flattheory - flatdata
+    blocks = _precision_blocks(spec)
+    logprior = core.logprior(X, names, spec.get('priors', {}))
+    out = {}
+    if not solved:
+        loglike = np.zeros(N)
+        for sl, P in blocks:
+            loglike += -0.5 * core.chi2(flatdiff[:, sl], P)
+        out['x_solved'] = np.zeros((N, 0))
+    else:
+        J = np.concatenate(jacs, axis=-1)  # [N, ns, n]
+        loglike, xs = np.empty(N), np.empty((N, len(solved)))
+        lp_solved = np.empty(N)
+        priors = [s.get('prior') for s in solved]
+        marg = [bool(s.get('marg', True)) for s in solved]
+        xx0 = [x0[s['name']] for s in solved]
+        for ip in range(N):
+            res = core.solve_marginalised([flatdiff[ip, sl] for sl, P in blocks], [J[ip][:, sl] for sl, P in blocks], [P for sl, P in blocks],
+                                          xx0, priors, marg)
+            loglike[ip], xs[ip], lp_solved[ip] = res['loglikelihood'], res['x'], res['logprior_solved']
+        logprior = logprior + lp_solved
+        out['x_solved'] = xs
+    out.update(loglikelihood=loglike, logprior=logprior, logposterior=loglike + logprior)
+    if return_theory:
+        out['flattheory'] = flattheory
+    return out
