@@ -1,0 +1,11 @@
+"""desilike_b200: B200-native (sm_100a CUDA) batched full-shape likelihood path of cosmodesi/desilike.
+
+Scope: ONE hot path -- N parameter points through emulated / Kaiser / BAO theory -> window matrix -> Gaussian chi2 with
+analytic marginalisation -> prior -- behind desilike's calling conventions.  See DESIGN.md / INTEGRATION.md.
+"""
+from ._capi import DesilikeB200Error, load as load_library
+from .plan import Plan, launch_count, measure_fp64_peak
+from .lowering import Lowered, LoweringError
+
+__all__ = ['Plan', 'Lowered', 'LoweringError', 'DesilikeB200Error', 'load_library', 'launch_count', 'measure_fp64_peak']
+__version__ = '0.1.0'

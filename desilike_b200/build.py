@@ -1,0 +1,43 @@
+"""Build libdesilike_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo snapshot)."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(ROOT, 'csrc')
+LIBDIR = os.path.join(ROOT, 'lib')
+LIBPATH = os.path.join(LIBDIR, 'libdesilike_b200.so')
+SOURCES = ['plan.cu', 'contract.cu', 'features.cu', 'theory_kernels.cu', 'solve.cu', 'peaks.cu', 'sampler.cu']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC', '-shared',
+              '-cudart', 'static']
+
+
+def sources():
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def needs_build():
+    if not os.path.exists(LIBPATH):
+        return True
+    mtime = os.path.getmtime(LIBPATH)
+    deps = sources() + [os.path.join(CSRC, 'common.h'), os.path.join(ROOT, '..', 'include', 'desilike_b200.h')]
+    return any(os.path.getmtime(d) > mtime for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source into ``desilike_b200/lib/libdesilike_b200.so``.  nvcc cross-compiles without a GPU."""
+    if not force and not needs_build():
+        return LIBPATH
+    os.makedirs(LIBDIR, exist_ok=True)
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIBPATH] + sources()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed:\n{}\n{}'.format(' '.join(cmd), res.stderr))
+    if verbose:
+        print(res.stderr)
+    return LIBPATH
+
+
+if __name__ == '__main__':
+    import sys
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

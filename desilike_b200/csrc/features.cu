@@ -1,0 +1,92 @@
+// Feature generators: theta[N, d] -> per-point feature rows F[Npad, fstride] (one padded segment per generator) and
+// per-point bias-monomial coefficients C[Npad, cstride].  Rows >= N and the padding columns are written as zeros so the
+// contraction kernel can consume full tiles without masking.
+#include "common.h"
+
+namespace dlb {
+
+namespace {
+
+__device__ __forceinline__ double ipow(double x, int n) {
+  double r = 1.;
+  for (int i = 0; i < n; ++i) r *= x;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Taylor monomials  m_t = prod_j (theta_j - center_j)^powers[t, j]
+//   layout fixed by the reference's fit (reference desilike/emulators/__init__.py:471-507: center, powers[T, d];
+//   1/alpha! is already folded into the stored derivatives); predict restated in oracle/core.py:taylor_monomials.
+//   idata = powers [T, nparams];  ddata = center [nparams];  nfeat = 2 + T: features = (1, 0, m_0 .. m_{T-1}).
+//   One thread per (point, term): coalesced stores.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void taylor_features_kernel(const DevGen g, const double* __restrict__ params, int d, long long N, long long npad,
+                                       double* __restrict__ F, int fstride) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long p = idx / g.fpad;
+  const int t = (int)(idx - p * g.fpad);
+  if (p >= npad) return;
+  double m = 0.;
+  if (p < N && t == 0) m = 1.;  // every segment starts with the constant pair (1, 0)
+  if (p < N && t >= 2 && t < g.nfeat) {
+    m = 1.;
+    const int* pw = g.idata + (size_t)(t - 2) * g.nparams;
+    for (int j = 0; j < g.nparams; ++j) {
+      const int e = pw[j];
+      if (e) {
+        const double x = (g.pidx[j] >= 0 ? params[p * d + g.pidx[j]] : g.pdef[j]) - g.ddata[j];
+        m *= ipow(x, e);
+      }
+    }
+  }
+  F[p * fstride + g.foff + t] = m;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// bias-monomial coefficients  c = scale * prod_f theta[idx_f]^pow_f   (tracer combine, reference full_shape.py:545-550)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void coef_kernel(const DevCoef* __restrict__ coefs, int ncoef, const double* __restrict__ params, int d, long long N,
+                            long long npad, double* __restrict__ C, int cstride) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long p = idx / cstride;
+  const int j = (int)(idx - p * cstride);
+  if (p >= npad) return;
+  double c = 0.;
+  if (p < N && j < ncoef) {
+    const DevCoef cf = coefs[j];
+    c = cf.scale;
+    for (int f = 0; f < cf.nf; ++f) {
+      const double x = params[p * d + cf.idx[f]];
+      const int e = cf.pow[f];
+      c *= e >= 0 ? ipow(x, e) : 1. / ipow(x, -e);
+    }
+  }
+  C[p * cstride + j] = c;
+}
+
+}  // namespace
+
+int launch_features(const DevGen& g, const double* params, int d, long long N, long long npad, double* F, int fstride, cudaStream_t stream) {
+  const int threads = 256;
+  if (g.kind == DLB_GEN_TAYLOR) {
+    const long long total = npad * g.fpad;
+    taylor_features_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(g, params, d, N, npad, F, fstride);
+    g_launches++;
+    DLB_CUDA(cudaGetLastError());
+    return DLB_OK;
+  }
+  set_error("feature generator kind " + std::to_string(g.kind) + " not implemented");
+  return DLB_ERR_UNSUPPORTED;
+}
+
+int launch_coefs(const DevCoef* coefs, int ncoef, const double* params, int d, long long N, long long npad, double* C, int cstride,
+                 cudaStream_t stream) {
+  const int threads = 256;
+  const long long total = npad * cstride;
+  coef_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(coefs, ncoef, params, d, N, npad, C, cstride);
+  g_launches++;
+  DLB_CUDA(cudaGetLastError());
+  return DLB_OK;
+}
+
+}  // namespace dlb

@@ -1,0 +1,178 @@
+// Final per-point stage: sum the Gram partials of the contraction kernel over column blocks, add the prior, and -- when
+// the likelihood has analytically solved linear parameters -- assemble and solve the normal equations.
+//
+// Restates, per point, reference desilike/likelihoods/base.py:129-200 (FastFisher.__call__: g, H, prior terms, solve) and
+// :314-413 (BaseLikelihood._solve: logprior of the solved values, 1/2 dx^T H_L dx + g_L . dx, -1/2 log det(-H[marg, marg])),
+// plus the prior of the sampled parameters (reference desilike/parameter.py:1889-1897, :1994-2017).
+// With M = -H_posterior = J~ J~^T + diag(1/scale^2) (SPD), M dx = g, and the '.marg' parameters ordered first, the
+// marginalisation log-determinant is 2 sum_{j < nmarg} log L_jj of the Cholesky factor M = L L^T.
+// One warp per point: the matrix lives in shared memory, columns are eliminated cooperatively (warp-level batched Cholesky).
+#include "common.h"
+#include <math_constants.h>
+
+namespace dlb {
+
+namespace {
+
+__device__ __forceinline__ double prior_logpdf(int kind, double x, double lo, double hi, double loc, double scale, bool* inside) {
+  const bool isin = (lo <= x) && (x <= hi);
+  if (!isin) { *inside = false; return -CUDART_INF; }
+  if (kind == 2) { const double t = (x - loc) / scale; return -0.5 * t * t; }
+  return 0.;
+}
+
+__global__ void finish_nosolve_kernel(const SolveParams p) {
+  const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pt >= p.N) return;
+  double chi2 = 0.;
+  for (int b = 0; b < p.nblocks; ++b) {
+    const SolveBlock blk = p.blocks[b];
+    for (int cb = 0; cb < blk.ncb; ++cb) chi2 += p.partial[(blk.poff + (long long)cb * blk.npart) * p.npad + pt];
+  }
+  double lp = 0.;
+  bool inside = true;
+  for (int j = 0; j < p.d; ++j)
+    lp += prior_logpdf(p.prior_kind[j], p.params[pt * p.d + j], p.prior_lo[j], p.prior_hi[j], p.prior_loc[j], p.prior_scale[j], &inside);
+  int st = 0;
+  double ll = -0.5 * chi2;
+  if (!inside) st |= DLB_PT_OUT_OF_PRIOR;
+  if (!isfinite(chi2)) { st |= DLB_PT_NONFINITE; ll = CUDART_NAN; }
+  if (p.loglike) p.loglike[pt] = ll;
+  if (p.logprior) p.logprior[pt] = lp;
+  if (p.logpost) p.logpost[pt] = inside ? ll + lp : -CUDART_INF;
+  if (p.status) p.status[pt] = st;
+}
+
+constexpr int SOLVE_WARPS = 4;
+
+__global__ void __launch_bounds__(SOLVE_WARPS * 32) finish_solve_kernel(const SolveParams p) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ns = p.ns, ld = ns + 1;
+  double* M = sm + (size_t)warp * (ns * ld + 4 * ns);
+  double* g = M + ns * ld;
+  double* gL = g + ns;
+  double* dx = gL + ns;
+  double* y = dx + ns;
+  const long long pt = (long long)blockIdx.x * SOLVE_WARPS + warp;
+  if (pt >= p.N) return;
+
+  for (int i = lane; i < ns * ns; i += 32) M[(i / ns) * ld + (i % ns)] = p.M0[i];
+  for (int i = lane; i < ns; i += 32) { gL[i] = 0.; }
+  __syncwarp();
+  double chi2 = 0.;
+  for (int b = 0; b < p.nblocks; ++b) {
+    const SolveBlock blk = p.blocks[b];
+    for (int e = lane; e < blk.npart; e += 32) {
+      double v = 0.;
+      for (int cb = 0; cb < blk.ncb; ++cb) v += p.partial[(blk.poff + (long long)cb * blk.npart + e) * p.npad + pt];
+      const EntryMap m = blk.map[e];
+      if (m.kind == 0) chi2 += v;
+      else if (m.kind == 1) gL[m.i] -= v;
+      else { M[m.i * ld + m.j] += v; if (m.i != m.j) M[m.j * ld + m.i] += v; }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) chi2 += __shfl_xor_sync(0xffffffffu, chi2, o);
+  for (int i = lane; i < ns; i += 32) g[i] = p.g0[i] + gL[i];
+  __syncwarp();
+
+  // ---- Cholesky M = L L^T (lower, in place) ----
+  bool spd = true;
+  double logdet = 0.;
+  for (int j = 0; j < ns; ++j) {
+    const double djj = M[j * ld + j];
+    if (!(djj > 0.) || !isfinite(djj)) { spd = false; break; }
+    const double l = sqrt(djj);
+    if (j < p.nmarg) logdet += 2. * log(l);
+    const double inv = 1. / l;
+    for (int i = j + 1 + lane; i < ns; i += 32) M[i * ld + j] *= inv;
+    __syncwarp();
+    if (lane == 0) M[j * ld + j] = l;
+    for (int i = j + 1 + lane; i < ns; i += 32) {
+      const double lij = M[i * ld + j];
+      for (int k = j + 1; k <= i; ++k) M[i * ld + k] -= lij * M[k * ld + j];
+    }
+    __syncwarp();
+  }
+  double lp = 0.;
+  bool inside = true;
+  for (int j = lane; j < p.d; j += 32) {
+    bool in_j = true;
+    lp += prior_logpdf(p.prior_kind[j], p.params[pt * p.d + j], p.prior_lo[j], p.prior_hi[j], p.prior_loc[j], p.prior_scale[j], &in_j);
+    inside = inside && in_j;
+  }
+  double quad = 0.;
+  if (spd) {
+    // forward L y = g
+    for (int i = lane; i < ns; i += 32) y[i] = g[i];
+    __syncwarp();
+    for (int j = 0; j < ns; ++j) {
+      const double yj = y[j] / M[j * ld + j];
+      __syncwarp();
+      if (lane == 0) y[j] = yj;
+      for (int i = j + 1 + lane; i < ns; i += 32) y[i] -= M[i * ld + j] * yj;
+      __syncwarp();
+    }
+    // backward L^T dx = y
+    for (int j = ns - 1; j >= 0; --j) {
+      const double xj = y[j] / M[j * ld + j];
+      __syncwarp();
+      if (lane == 0) { dx[j] = xj; y[j] = xj; }
+      for (int i = lane; i < j; i += 32) y[i] -= M[j * ld + i] * xj;
+      __syncwarp();
+    }
+    for (int i = lane; i < ns; i += 32) {
+      const double di = dx[i];
+      const double xi = p.x0[i] + di;
+      // 1/2 dx^T H_L dx + g_L . dx  with  H_L = -(M - diag(prec))  and  dx^T M dx = g . dx
+      quad += 0.5 * (-g[i] * di + p.xprec[i] * di * di) + gL[i] * di;
+      bool in_i = true;
+      lp += prior_logpdf(p.xkind[i], xi, p.xlo[i], p.xhi[i], p.xloc[i], p.xkind[i] == 2 ? rsqrt(p.xprec[i]) : 1., &in_i);
+      // NB: the reference adds -inf to logprior when a solved value leaves its limits, but does not veto the point
+      if (p.xsolved) p.xsolved[pt * ns + i] = xi;
+    }
+  } else if (p.xsolved) {
+    for (int i = lane; i < ns; i += 32) p.xsolved[pt * ns + i] = CUDART_NAN;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lp += __shfl_xor_sync(0xffffffffu, lp, o);
+    quad += __shfl_xor_sync(0xffffffffu, quad, o);
+    inside = __shfl_xor_sync(0xffffffffu, (int)inside, o) && inside;
+  }
+  if (lane == 0) {
+    int st = 0;
+    double ll = -0.5 * chi2 + quad - 0.5 * logdet;
+    if (!inside) st |= DLB_PT_OUT_OF_PRIOR;
+    if (!spd) { st |= DLB_PT_NOT_SPD; ll = CUDART_NAN; }
+    if (!isfinite(chi2)) { st |= DLB_PT_NONFINITE; ll = CUDART_NAN; }
+    if (p.loglike) p.loglike[pt] = ll;
+    if (p.logprior) p.logprior[pt] = lp;
+    if (p.logpost) p.logpost[pt] = inside ? ll + lp : -CUDART_INF;
+    if (p.status) p.status[pt] = st;
+  }
+}
+
+}  // namespace
+
+int launch_solve(const SolveParams& p, cudaStream_t stream) {
+  if (p.ns == 0) {
+    const int threads = 256;
+    finish_nosolve_kernel<<<(unsigned)((p.N + threads - 1) / threads), threads, 0, stream>>>(p);
+  } else {
+    const size_t smem = (size_t)SOLVE_WARPS * (p.ns * (p.ns + 1) + 4 * p.ns) * sizeof(double);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      DLB_CUDA(cudaFuncSetAttribute(finish_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    finish_solve_kernel<<<(unsigned)((p.N + SOLVE_WARPS - 1) / SOLVE_WARPS), SOLVE_WARPS * 32, smem, stream>>>(p);
+  }
+  g_launches++;
+  DLB_CUDA(cudaGetLastError());
+  return DLB_OK;
+}
+
+}  // namespace dlb

@@ -1,0 +1,277 @@
+"""Plan-time lowering: likelihood spec -> flat constant tables of ``dlb_plan_desc`` (include/desilike_b200.h).
+
+All parameter-independent linear algebra of the chain is folded here, once, in FP64 on the host:
+
+  * the precision matrix P (dense / block-diagonal / diagonal; built by the reference at
+    desilike/likelihoods/base.py:605-631) is factorised P = L^T L and L is multiplied into
+  * the window matrix W (reference desilike/observables/galaxy_clustering/window.py:459-468), the constant shot-noise /
+    offset vectors (window.py:445-457), the bias-combine column weights (reference full_shape.py:545-550, :628-634) and
+  * the emulator's linear output map (Taylor ``derivatives`` [T, ny], reference desilike/emulators/__init__.py:471-507;
+    last MLP layer + inverse y-operations, reference desilike/emulators/conversion.py:18-33,76-84),
+
+so that per point the GPU only evaluates features f(theta), bias monomials c(theta) and the contraction
+``r = sum_t c_t f_t . M_t - r0`` (chi2 = |r|^2), plus the whitened Jacobian rows of the solved parameters.
+Nothing here runs per point.
+
+Likelihood spec (plain dicts / ndarrays; the same structure the oracle evaluates un-collapsed):
+  spec = dict(params=[names], priors={name: dict(dist, limits, loc, scale) | None},
+              solved=[dict(name, value, prior, marg)], observables=[obs, ...],
+              precision=[P_b per observable] | P joint [n, n] | diag [n])
+  obs  = dict(theory=dict(kind='taylor'|'mlp'|'kaiser'|'bao_xi'|'bao_pk', params=[...], ...constants...),
+              terms=[dict(scale, factors=[(param, pow)], solved=name|None, table=name|None, colvec=[nin]|None)],
+              nin=int, wmatrix=[nobs, nin]|None, offset=[nobs]|None, data=[nobs], transform=None)
+"""
+import ctypes
+
+import numpy as np
+
+from . import _capi
+from ._capi import f64, i32, as_ptr
+
+
+class LoweringError(ValueError):
+    pass
+
+
+def _prior_tables(names, priors):
+    n = len(names)
+    kind, lo, hi = np.zeros(n, dtype=np.int32), np.full(n, -np.inf), np.full(n, np.inf)
+    loc, scale = np.zeros(n), np.ones(n)
+    for i, name in enumerate(names):
+        prior = priors.get(name) if priors else None
+        if prior is None: continue
+        dist = prior.get('dist', 'uniform')
+        limits = prior.get('limits', (-np.inf, np.inf))
+        lo[i] = -np.inf if limits[0] is None else limits[0]
+        hi[i] = np.inf if limits[1] is None else limits[1]
+        if dist == 'uniform': kind[i] = 1
+        elif dist == 'norm':
+            kind[i] = 2; loc[i] = prior.get('loc', 0.); scale[i] = prior.get('scale', 1.)
+        else:
+            raise LoweringError('prior distribution {!r} of {} is not on the CUDA path (uniform / norm only, as the reference fast paths '
+                                'parameter.py:2005-2009)'.format(dist, name))
+    return kind, lo, hi, loc, scale
+
+
+def _whitening(precision):
+    """P = L^T L  ->  L (upper triangular for dense P, diagonal for 1-D P)."""
+    precision = np.asarray(precision, dtype=np.float64)
+    if precision.ndim == 1:
+        return np.diag(np.sqrt(precision))
+    return np.linalg.cholesky(precision).T
+
+
+class _Generator(object):
+    """Host description of one feature generator + where each theory table lives in its feature segment."""
+
+    def __init__(self, theory, names):
+        self.kind_name = theory['kind']
+        self.params = list(theory['params'])
+        defaults = theory.get('defaults', {})
+        self.param_idx = i32([names.index(p) if p in names else -1 for p in self.params])
+        self.tables = {}  # name -> (foff, K, D [K, nin] or None for identity)
+        self.keep = []
+        if self.kind_name == 'taylor':
+            self.kind = _capi.GEN_TAYLOR
+            center, powers = f64(theory['center']), i32(theory['powers'])
+            T = powers.shape[0]
+            self.param_default = f64([defaults.get(p, center[j]) for j, p in enumerate(self.params)])
+            self.idata, self.ddata, self.nfeat = powers.ravel(), center, T + 2
+            for name, deriv in theory['tables'].items():
+                self.tables[name] = (2, T, f64(deriv).reshape(T, -1))
+        elif self.kind_name == 'mlp':
+            from .mlp import lower_mlp
+            lower_mlp(self, theory, defaults)
+        elif self.kind_name in ('kaiser', 'bao_xi', 'bao_pk'):
+            from .theory_lowering import lower_theory
+            lower_theory(self, theory, defaults)
+        else:
+            raise LoweringError('unknown theory kind {!r}'.format(self.kind_name))
+
+    def desc(self):
+        g = _capi.GeneratorDesc()
+        g.kind, g.nparams, g.nfeat = self.kind, len(self.params), int(self.nfeat)
+        self.param_idx, self.param_default = i32(self.param_idx), f64(self.param_default)
+        self.idata, self.ddata = i32(self.idata), f64(self.ddata)
+        g.param_idx, g.param_default = as_ptr(self.param_idx, ctypes.c_int32), as_ptr(self.param_default)
+        g.ni, g.idata = int(self.idata.size), as_ptr(self.idata, ctypes.c_int32)
+        g.nd, g.ddata = int(self.ddata.size), as_ptr(self.ddata)
+        return g
+
+
+class Lowered(object):
+    """Flat arrays + ctypes descriptor (keeps every buffer alive until the plan has been created)."""
+
+    def __init__(self, spec, with_plain=True):
+        self.spec = spec
+        names = self.names = list(spec['params'])
+        self.d = len(names)
+        self.prior = _prior_tables(names, spec.get('priors', {}))
+        # ---- solved parameters: '.marg' first (so log det(-H[marg, marg]) is a leading-block Cholesky product) ----
+        solved = list(spec.get('solved', []))
+        order = [i for i, s in enumerate(solved) if s.get('marg', True)] + [i for i, s in enumerate(solved) if not s.get('marg', True)]
+        self.solved_order = np.array(order, dtype=int)          # plan index -> spec index
+        self.solved_names = [solved[i]['name'] for i in order]
+        self.ns, self.nmarg = len(solved), sum(1 for s in solved if s.get('marg', True))
+        sindex = {name: i for i, name in enumerate(self.solved_names)}
+        self.x0 = f64([solved[i].get('value', 0.) for i in order])
+        skind, slo, shi, sloc, sscale = _prior_tables(self.solved_names, {s['name']: s.get('prior') for s in solved})
+        sscale = np.where(skind == 2, sscale, np.inf)
+        self.xprior = (skind, sloc, sscale, slo, shi)
+        # ---- generators (one per distinct theory object) ----
+        self.gens, gen_of = [], {}
+        for obs in spec['observables']:
+            key = id(obs['theory'])
+            if key not in gen_of:
+                gen_of[key] = len(self.gens)
+                self.gens.append(_Generator(obs['theory'], names))
+        # ---- coefficients ----
+        self.coef_keys = {}
+
+        def coef_index(factors):
+            key = tuple(sorted((names.index(n), int(p)) for n, p in factors))
+            if not key: return -1
+            if len(key) > _capi.DLB_COEF_MAXF: raise LoweringError('too many factors in a bias monomial')
+            if key not in self.coef_keys: self.coef_keys[key] = len(self.coef_keys)
+            return self.coef_keys[key]
+
+        # ---- blocks ----
+        prec = spec['precision']
+        observables = spec['observables']
+        if isinstance(prec, (list, tuple)):
+            groups = [([obs], np.asarray(p, dtype=np.float64)) for obs, p in zip(observables, prec)]
+        else:
+            groups = [(list(observables), np.asarray(prec, dtype=np.float64))]
+        self.blocks = []
+        for group, P in groups:
+            ncols = sum(len(o['data']) for o in group)
+            if P.shape[0] != ncols: raise LoweringError('precision size {} != data size {}'.format(P.shape, ncols))
+            L = _whitening(P)
+            terms = {}   # (slot, coef, gen, foff, K) -> plain matrix [K, ncols]
+            slot_of, const_rows = {}, {}
+            const_plain = np.zeros(ncols)
+            data = np.concatenate([f64(o['data']) for o in group])
+            c0 = 0
+            for obs in group:
+                if obs.get('transform') is not None:
+                    raise LoweringError('observable transform {!r} is not on the CUDA path yet'.format(obs['transform']))
+                n_o, nin = len(obs['data']), int(obs['nin'])
+                W = f64(obs['wmatrix']) if obs.get('wmatrix') is not None else None
+                if W is None and nin != n_o: raise LoweringError('wmatrix=None requires nin == len(data)')
+                gi = gen_of[id(obs['theory'])]
+                gen = self.gens[gi]
+                if obs.get('offset') is not None: const_plain[c0:c0 + n_o] += f64(obs['offset'])
+
+                def add(slot, coef, foff, K, mat_o):
+                    key = (slot, coef, gi, foff, K)
+                    if key not in terms: terms[key] = np.zeros((K, ncols))
+                    terms[key][:, c0:c0 + n_o] += mat_o
+
+                for term in obs['terms']:
+                    scale = float(term.get('scale', 1.))
+                    factors = list(term.get('factors', []))
+                    colvec = f64(term['colvec']) if term.get('colvec') is not None else None
+                    sname = term.get('solved')
+                    if term.get('table') is not None:
+                        foff, K, D = gen.tables[term['table']]
+                        if D is None:   # identity features: the table itself is the feature sub-segment
+                            cv = np.ones(nin) if colvec is None else colvec
+                            mat = scale * (cv[:, None] * (W.T if W is not None else np.eye(nin)))
+                        else:
+                            Dc = D if colvec is None else D * colvec
+                            mat = scale * (Dc @ W.T if W is not None else Dc)
+                        theta_dep = True
+                    else:
+                        cv = np.ones(nin) if colvec is None else colvec
+                        vec = scale * (W @ cv if W is not None else cv)
+                        foff, K, mat = 0, 1, vec[None, :]
+                        theta_dep = bool(factors)
+                    if sname is None:
+                        if theta_dep: add(0, coef_index(factors), foff, K, mat)
+                        else: const_plain[c0:c0 + n_o] += mat[0]
+                        continue
+                    si = sindex[sname]
+                    if theta_dep:
+                        if si not in slot_of: slot_of[si] = 1 + len(slot_of)
+                        add(slot_of[si], coef_index(factors), foff, K, mat)
+                        if self.x0[si] != 0.: add(0, coef_index(factors), foff, K, self.x0[si] * mat)
+                    else:
+                        if si in slot_of: raise LoweringError('solved parameter {} mixes constant and theta-dependent templates'.format(sname))
+                        row = const_rows.setdefault(si, np.zeros(ncols))
+                        row[c0:c0 + n_o] += mat[0]
+                        if self.x0[si] != 0.: const_plain[c0:c0 + n_o] += self.x0[si] * mat[0]
+                c0 += n_o
+            for si in const_rows:
+                if si in slot_of: raise LoweringError('solved parameter {} mixes constant and theta-dependent templates'.format(self.solved_names[si]))
+            nslots = 1 + len(slot_of)
+            if nslots > 8: raise LoweringError('more than 7 theta-dependent solved templates per block are not supported')
+            blk = dict(ncols=ncols, nslots=nslots)
+            keys = sorted(terms.keys())
+            blk['terms'] = keys
+            blk['plain'] = [terms[k] for k in keys]
+            blk['white'] = [terms[k] @ L.T for k in keys]
+            blk['r0_white'] = L @ (data - const_plain)
+            blk['t0_plain'] = const_plain
+            inv = sorted(slot_of.items(), key=lambda kv: kv[1])
+            blk['slot_solved'] = i32([si for si, _ in inv])
+            blk['const_solved'] = i32(sorted(const_rows.keys()))
+            blk['gconst_white'] = f64([L @ const_rows[si] for si in sorted(const_rows.keys())]).reshape(len(const_rows), ncols)
+            self.blocks.append(blk)
+        self.ntheory = sum(b['ncols'] for b in self.blocks)
+        self.with_plain = with_plain
+        self._build_desc()
+
+    def _build_desc(self):
+        keep = self._keep = []
+        desc = _capi.PlanDesc()
+        desc.abi_version, desc.d = _capi.DLB_ABI_VERSION, self.d
+        kind, lo, hi, loc, scale = [np.ascontiguousarray(a) for a in self.prior]
+        keep += [kind, lo, hi, loc, scale]
+        desc.prior_kind, desc.prior_lo, desc.prior_hi = as_ptr(kind, ctypes.c_int32), as_ptr(lo), as_ptr(hi)
+        desc.prior_loc, desc.prior_scale = as_ptr(loc), as_ptr(scale)
+        gens = (_capi.GeneratorDesc * len(self.gens))(*[g.desc() for g in self.gens])
+        desc.ngen, desc.gens = len(self.gens), gens
+        ncoef = len(self.coef_keys)
+        coefs = (_capi.CoefDesc * max(ncoef, 1))()
+        for key, j in self.coef_keys.items():
+            coefs[j].scale, coefs[j].nf = 1., len(key)
+            for f, (idx, power) in enumerate(key):
+                coefs[j].idx[f], coefs[j].pow[f] = idx, power
+        desc.ncoef, desc.coefs = ncoef, coefs
+        blocks = (_capi.BlockDesc * len(self.blocks))()
+        for b, blk in zip(blocks, self.blocks):
+            nt = len(blk['terms'])
+            terms = (_capi.TermDesc * nt)()
+            moff = 0
+            for t, key, mat in zip(terms, blk['terms'], blk['white']):
+                t.slot, t.coef, t.gen, t.foff, t.K = key
+                t.moff = moff
+                moff += mat.size
+            white = f64(np.concatenate([m.ravel() for m in blk['white']]))
+            plain = f64(np.concatenate([m.ravel() for m in blk['plain']])) if self.with_plain else None
+            r0, t0 = f64(blk['r0_white']), f64(blk['t0_plain'])
+            ss, cs, gc = i32(blk['slot_solved']), i32(blk['const_solved']), f64(blk['gconst_white'])
+            keep += [terms, white, plain, r0, t0, ss, cs, gc]
+            b.ncols, b.nslots, b.nterms, b.terms = blk['ncols'], blk['nslots'], nt, terms
+            b.matrices_white, b.matrices_plain = as_ptr(white), as_ptr(plain)
+            b.r0_white, b.t0_plain = as_ptr(r0), as_ptr(t0)
+            b.slot_solved, b.nconst, b.const_solved, b.gconst_white = as_ptr(ss, ctypes.c_int32), len(cs), as_ptr(cs, ctypes.c_int32), as_ptr(gc)
+        desc.nblocks, desc.blocks = len(self.blocks), blocks
+        skind, sloc, sscale, slo, shi = [np.ascontiguousarray(a) for a in self.xprior]
+        keep += [gens, coefs, blocks, skind, sloc, sscale, slo, shi, self.x0]
+        desc.ns, desc.nmarg = self.ns, self.nmarg
+        desc.x0, desc.xprior_kind = as_ptr(self.x0), as_ptr(skind, ctypes.c_int32)
+        desc.xprior_loc, desc.xprior_scale, desc.xprior_lo, desc.xprior_hi = as_ptr(sloc), as_ptr(sscale), as_ptr(slo), as_ptr(shi)
+        self.desc = desc
+
+    def flops_per_point(self):
+        """Algorithmic FLOPs per evaluation of the folded chain (2 per multiply-add), by stage; DESIGN.md section 'roofline'."""
+        contract = 0
+        gram = 0
+        for blk in self.blocks:
+            for (slot, coef, gen, foff, K) in blk['terms']:
+                contract += 2 * K * blk['ncols']
+            R, nc = blk['nslots'], len(blk['const_solved'])
+            gram += 2 * blk['ncols'] * (R * (R + 1) // 2 + R * nc)
+        solve = self.ns**3 // 3 + 2 * self.ns**2
+        return dict(contract=contract, gram=gram, solve=solve, total=contract + gram + solve)

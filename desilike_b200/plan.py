@@ -1,0 +1,125 @@
+"""Plan handle: owns the device constants of one likelihood and evaluates batches through the C-ABI."""
+import ctypes
+
+import numpy as np
+
+from . import _capi
+from .lowering import Lowered
+
+
+def _is_torch_cuda(x):
+    return hasattr(x, 'is_cuda') and x.is_cuda
+
+
+class Plan(object):
+    """
+    Device-resident, immutable evaluation plan of a likelihood spec.
+
+    ``plan.eval(X)`` replaces ``vmap(likelihood)(params)`` of the reference (desilike/base.py:232-273 driving
+    likelihoods/base.py:242-245,314-413) for a batch ``X[N, d]`` (columns ordered as ``plan.params``).
+    NumPy input -> host buffers (staged by the library, NumPy outputs); CUDA torch tensor input -> used in place on the
+    current torch stream, torch outputs, no host round trip.
+    """
+
+    def __init__(self, spec, device=None, with_theory=True):
+        self._lib = _capi.load()
+        if self._lib.dlb_device_count() <= 0:
+            raise _capi.DesilikeB200Error('no CUDA device visible: desilike_b200 has no CPU fallback')
+        if device is not None:
+            import torch
+            torch.cuda.set_device(device)
+        self.lowered = Lowered(spec, with_plain=with_theory)
+        self.params = list(self.lowered.names)
+        self.d, self.ns, self.ntheory = self.lowered.d, self.lowered.ns, self.lowered.ntheory
+        self.solved_names = [s['name'] for s in spec.get('solved', [])]
+        handle = ctypes.c_void_p()
+        _capi.check(self._lib.dlb_plan_create(ctypes.byref(self.lowered.desc), ctypes.byref(handle)))
+        self._handle = handle
+        # plan order -> spec order of the solved parameters
+        self._unperm = np.argsort(self.lowered.solved_order) if self.ns else np.zeros(0, dtype=int)
+
+    def close(self):
+        if getattr(self, '_handle', None):
+            self._lib.dlb_plan_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
+
+    # ---- evaluation --------------------------------------------------------------------------------------------------
+    def eval(self, X, return_solved=True, return_status=True, out=None):
+        """-> dict(logposterior, loglikelihood, logprior[, x_solved (spec order), status])."""
+        if _is_torch_cuda(X):
+            return self._eval_torch(X, return_solved, return_status, out)
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim != 2 or X.shape[1] != self.d:
+            raise ValueError('expected params of shape (N, {:d}), got {}'.format(self.d, X.shape))
+        N = X.shape[0]
+        res = dict(logposterior=np.empty(N), loglikelihood=np.empty(N), logprior=np.empty(N))
+        xs = np.empty((N, self.ns)) if (return_solved and self.ns) else None
+        st = np.empty(N, dtype=np.int32) if return_status else None
+        _capi.check(self._lib.dlb_eval_batch(self._handle, X.ctypes.data, N, res['logposterior'].ctypes.data, res['loglikelihood'].ctypes.data,
+                                             res['logprior'].ctypes.data, xs.ctypes.data if xs is not None else None,
+                                             st.ctypes.data if st is not None else None, None))
+        if xs is not None: res['x_solved'] = xs[:, self._unperm]
+        if st is not None: res['status'] = st
+        return res
+
+    def _eval_torch(self, X, return_solved, return_status, out):
+        import torch
+        if X.dtype != torch.float64 or not X.is_contiguous() or X.dim() != 2 or X.shape[1] != self.d:
+            raise ValueError('expected a contiguous float64 CUDA tensor of shape (N, {:d})'.format(self.d))
+        N = X.shape[0]
+        if out is None:
+            out = dict(logposterior=torch.empty(N, dtype=torch.float64, device=X.device), loglikelihood=torch.empty(N, dtype=torch.float64, device=X.device),
+                       logprior=torch.empty(N, dtype=torch.float64, device=X.device))
+            if return_solved and self.ns: out['x_solved_plan_order'] = torch.empty((N, self.ns), dtype=torch.float64, device=X.device)
+            if return_status: out['status'] = torch.empty(N, dtype=torch.int32, device=X.device)
+        stream = torch.cuda.current_stream(X.device).cuda_stream
+        ptr = lambda key: out[key].data_ptr() if key in out else None
+        _capi.check(self._lib.dlb_eval_batch(self._handle, X.data_ptr(), N, ptr('logposterior'), ptr('loglikelihood'), ptr('logprior'),
+                                             ptr('x_solved_plan_order'), ptr('status'), ctypes.c_void_p(stream)))
+        if 'x_solved_plan_order' in out:
+            out['x_solved'] = out['x_solved_plan_order'][:, torch.as_tensor(self._unperm, device=X.device)]
+        return out
+
+    def theory(self, X):
+        """Flat theory vectors [N, n] at the solved parameters' defaults (reference ``likelihood.flattheory``)."""
+        if _is_torch_cuda(X):
+            import torch
+            out = torch.empty((X.shape[0], self.ntheory), dtype=torch.float64, device=X.device)
+            stream = torch.cuda.current_stream(X.device).cuda_stream
+            _capi.check(self._lib.dlb_theory_batch(self._handle, X.data_ptr(), X.shape[0], out.data_ptr(), ctypes.c_void_p(stream)))
+            return out
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        out = np.empty((X.shape[0], self.ntheory))
+        _capi.check(self._lib.dlb_theory_batch(self._handle, X.ctypes.data, X.shape[0], out.ctypes.data, None))
+        return out
+
+    def features(self, gen, X):
+        """Per-point features of generator ``gen`` [N, nfeat] (parity entry for the theory kernels)."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        nfeat = int(self.lowered.gens[gen].nfeat)
+        out = np.empty((X.shape[0], nfeat))
+        _capi.check(self._lib.dlb_features_batch(self._handle, gen, X.ctypes.data, X.shape[0], out.ctypes.data, None))
+        return out
+
+    # ---- instrumentation ---------------------------------------------------------------------------------------------
+    def set_timing(self, enabled=True):
+        _capi.check(self._lib.dlb_set_timing(self._handle, int(enabled)))
+
+    def last_kernel_ms(self):
+        a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        _capi.check(self._lib.dlb_last_kernel_ms(self._handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return dict(features=a.value, contract=b.value, solve=c.value)
+
+
+def launch_count():
+    return int(_capi.load().dlb_launch_count())
+
+
+def measure_fp64_peak(kind='dmma'):
+    val = ctypes.c_double()
+    _capi.check(_capi.load().dlb_measure_fp64_peak(0 if kind == 'dmma' else 1, ctypes.byref(val)))
+    return val.value

@@ -1,0 +1,163 @@
+/*
+ * desilike_b200 -- C ABI of the B200-native batched full-shape likelihood path.
+ *
+ * The reference (cosmodesi/desilike) is pure Python and has no FFI; this header is what a `backend='cuda'` branch of
+ *   desilike.base.vmap                      (reference desilike/base.py:232-383)
+ * would bind through ctypes.  One call evaluates N parameter points through
+ *   emulator predict / Kaiser / damped-BAO+FFTLog   (reference emulators/__init__.py:408-409,471-507; theories/galaxy_clustering/
+ *                                                    full_shape.py:488-500,545-550,628-634; bao.py:117-151; base.py:127-136)
+ *   -> window matrix apply                          (reference observables/galaxy_clustering/window.py:459-473, :717-728)
+ *   -> Gaussian chi2                                (reference likelihoods/base.py:13-17, :658-664)
+ *   -> analytic marginalisation of linear params    (reference likelihoods/base.py:129-200, :314-413)
+ *   -> prior                                        (reference parameter.py:1889-1897, :1994-2017)
+ *
+ * Plain pointers and sizes only; no torch / Python types.  All matrices are row-major FP64, index tables int32.
+ * Buffers passed to the *_batch calls may live in host memory (pageable or pinned) or in device memory
+ * (detected with cudaPointerGetAttributes); device buffers are used in place, host buffers are staged.
+ *
+ * Ownership: the caller owns every buffer it passes; dlb_plan_create copies what it needs to the device, the plan owns
+ * those copies and its workspace.  A plan is immutable after creation; calls on the SAME plan are serialised
+ * internally (one workspace per plan); different plans are independent.  One plan lives on one device (the current
+ * CUDA device at creation).
+ *
+ * Errors: every entry point returns 0 on success, a negative dlb_status otherwise; dlb_last_error() gives the message
+ * (thread-local).  Per-point problems never fail the call: they are reported in the `status` bitmask
+ * and mapped by the host layer onto the reference's `errors='raise'|'return'|'nan'` conventions (reference base.py:193-258).
+ * There is NO CPU fallback: without a usable CUDA device every compute entry point fails with DLB_ERR_CUDA.
+ */
+#ifndef DESILIKE_B200_H
+#define DESILIKE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLB_ABI_VERSION 1
+
+typedef enum {
+  DLB_OK = 0,
+  DLB_ERR_ARG = -1,      /* bad shape / NULL pointer / inconsistent descriptor */
+  DLB_ERR_CUDA = -2,     /* CUDA runtime error (no device, launch failure, out of memory) */
+  DLB_ERR_UNSUPPORTED = -3
+} dlb_status;
+
+/* per-point status bits (int32 per point) */
+#define DLB_PT_NONFINITE 1   /* theory / chi2 not finite                      -> logposterior = NaN          */
+#define DLB_PT_OUT_OF_PRIOR 2/* a sampled parameter is outside its limits     -> logposterior = -inf         */
+#define DLB_PT_NOT_SPD 4     /* -Hessian of the solved parameters not SPD     -> logposterior = NaN          */
+
+/* ---- feature generators: theta -> per-point feature segment -------------------------------------------------------
+ * Every generator's segment starts with the constant pair (1.0, 0.0) -- feature 0 lets theta-dependent scalars multiply
+ * constant vectors (shot-noise / broadband terms) -- followed by the kind-specific features.                            */
+typedef enum {
+  DLB_GEN_TAYLOR = 1,  /* monomials prod_j (theta_j - c_j)^p_tj   (reference emulators/__init__.py:471-507)               */
+  DLB_GEN_MLP = 2,     /* last hidden layer of an MLP emulator (+1) (reference emulators/conversion.py:18-33)              */
+  DLB_GEN_KAISER = 3,  /* Kaiser pt tables dd/dt/tt/pk11 on (ell, k) (reference full_shape.py:488-500, power_template.py:747-761) */
+  DLB_GEN_BAO = 4      /* damped BAO P_ell(k) [-> FFTLog -> xi_ell(s)] (reference bao.py:117-151, base.py:127-136)          */
+} dlb_gen_kind;
+
+typedef struct {
+  int32_t kind;            /* dlb_gen_kind */
+  int32_t nparams;         /* number of input columns this generator reads */
+  const int32_t* param_idx;/* [nparams] column index into the batch `params` (>= 0), or -1: use param_default */
+  const double* param_default; /* [nparams] */
+  int32_t nfeat;           /* features written per point (before padding) */
+  /* kind-specific integer / double payloads (layouts documented next to each kernel in csrc/features.cu) */
+  int32_t ni; const int32_t* idata;
+  int64_t nd; const double* ddata;
+} dlb_generator_desc;
+
+/* ---- per-point scalar coefficients: c = scale * prod_f theta[idx_f]^pow_f  (bias monomials, reference full_shape.py:545-550) */
+#define DLB_COEF_MAXF 4
+typedef struct {
+  double scale;
+  int32_t nf;
+  int32_t idx[DLB_COEF_MAXF];
+  int32_t pow[DLB_COEF_MAXF];
+} dlb_coef_desc;
+
+/* ---- contraction terms: slot[s] += coef * features[foff : foff + K] . M[K, ncols] --------------------------------- */
+typedef struct {
+  int32_t slot;       /* 0: (whitened) residual / theory; s >= 1: theta-dependent Jacobian row of a solved parameter */
+  int32_t coef;       /* index into the coefficient table, -1 for 1.0 */
+  int32_t gen;        /* generator whose feature segment is contracted */
+  int32_t foff;       /* offset inside that segment */
+  int32_t K;          /* contraction length */
+  int64_t moff;       /* offset (doubles) of M[K, ncols] (row-major) in `matrices` */
+} dlb_term_desc;
+
+/* ---- output blocks: independent groups of data-vector columns (one per tracer when the precision is block-diagonal) */
+typedef struct {
+  int32_t ncols;            /* n_b */
+  int32_t nslots;           /* 1 + number of theta-dependent Jacobian rows */
+  int32_t nterms;
+  const dlb_term_desc* terms;
+  const double* matrices_white;  /* whitened (L . W . ...) term matrices, for dlb_eval_batch   */
+  const double* matrices_plain;  /* un-whitened (W . ...) term matrices, for dlb_theory_batch  (may be NULL) */
+  const double* r0_white;        /* [ncols] constant subtracted from slot 0:  L (data - offset - const part)  */
+  const double* t0_plain;        /* [ncols] constant ADDED to slot 0 in theory mode (offset + const part)      */
+  const int32_t* slot_solved;    /* [nslots - 1] solved-parameter index of slots 1.. */
+  int32_t nconst;                /* constant (theta-independent) whitened Jacobian rows */
+  const int32_t* const_solved;   /* [nconst] solved-parameter index */
+  const double* gconst_white;    /* [nconst, ncols] */
+} dlb_block_desc;
+
+typedef struct {
+  int32_t abi_version;      /* DLB_ABI_VERSION */
+  int32_t d;                /* number of columns of the batch `params` */
+  /* prior over the d input columns (reference parameter.py:1994-2017): kind 0 none, 1 uniform, 2 normal */
+  const int32_t* prior_kind; const double* prior_lo; const double* prior_hi; const double* prior_loc; const double* prior_scale;
+  int32_t ngen; const dlb_generator_desc* gens;
+  int32_t ncoef; const dlb_coef_desc* coefs;
+  int32_t nblocks; const dlb_block_desc* blocks;
+  /* solved (analytically marginalised / profiled) linear parameters, reference likelihoods/base.py:314-413.
+   * Ordered with the `nmarg` '.marg' parameters FIRST, then the '.best' ones. */
+  int32_t ns; int32_t nmarg;
+  const double* x0;          /* [ns] value at which d0 and J are evaluated (the parameter defaults) */
+  const int32_t* xprior_kind;/* [ns] 0 none (improper), 1 uniform (limits only), 2 normal */
+  const double* xprior_loc; const double* xprior_scale; const double* xprior_lo; const double* xprior_hi; /* [ns] */
+} dlb_plan_desc;
+
+typedef struct dlb_plan dlb_plan;
+
+/* Library / device ----------------------------------------------------------------------------------------------- */
+int dlb_abi_version(void);
+const char* dlb_last_error(void);
+int dlb_device_count(void);
+
+/* Plan -------------------------------------------------------------------------------------------------------------- */
+int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out);
+void dlb_plan_destroy(dlb_plan* plan);
+int dlb_plan_ntheory(const dlb_plan* plan);      /* total data-vector length n */
+int dlb_plan_nsolved(const dlb_plan* plan);
+
+/* Batched evaluation (replaces the per-point loop of reference base.py:239-273 + likelihoods/base.py:242-245,314-413).
+ * params [N, d].  Outputs (each may be NULL): logposterior/loglikelihood/logprior [N], x_solved [N, ns] (in the plan's solved
+ * order), status [N].  `stream` is a cudaStream_t (NULL = default stream); the call returns after the work is
+ * ENQUEUED when every buffer is device memory, and after completion when any buffer is host memory. */
+int dlb_eval_batch(dlb_plan* plan, const double* params, int64_t N,
+                   double* logposterior, double* loglikelihood, double* logprior,
+                   double* x_solved, int32_t* status, void* stream);
+
+/* Theory vectors (parity / debug entry; reference `likelihood.flattheory`, likelihoods/base.py:662-664): theory [N, n],
+ * evaluated at the solved parameters' defaults x0. */
+int dlb_theory_batch(dlb_plan* plan, const double* params, int64_t N, double* theory, void* stream);
+
+/* Per-point features of one generator [N, nfeat] (parity / debug entry for the theory kernels, e.g. Kaiser tables). */
+int dlb_features_batch(dlb_plan* plan, int32_t gen, const double* params, int64_t N, double* features, void* stream);
+
+/* Instrumentation ----------------------------------------------------------------------------------------------- */
+int64_t dlb_launch_count(void);                  /* kernels launched by this library since load (all plans) */
+/* Achieved FP64 rate (TFLOP/s) of a register-resident DMMA.8x8x4 loop (kind 0) or DFMA loop (kind 1) on the current
+ * device: the denominator of the FP64 roofline (MEASURED_PEAKS.json has no FP64 entry). */
+int dlb_measure_fp64_peak(int32_t kind, double* tflops);
+/* Time (ms, CUDA events on `stream`) of the last dlb_eval_batch's contraction kernel launches; for bench.py's roofline. */
+int dlb_last_kernel_ms(const dlb_plan* plan, double* features_ms, double* contract_ms, double* solve_ms);
+int dlb_set_timing(dlb_plan* plan, int32_t enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DESILIKE_B200_H */

@@ -1,0 +1,108 @@
+"""Parity of the CUDA path (through the C-ABI) against the oracle on the same seeded inputs.  Run with ``-m gpu``.
+
+Tolerances (BASELINE.json north_star): relative 1e-10 on theory vectors in FP64; |delta chi2| < 1e-4, i.e.
+|delta logL| < 5e-5 -- the FP64 path is held to a much tighter 1e-8 * max(1, |logL|) here.
+"""
+import numpy as np
+import pytest
+
+from oracle import configs, pipeline
+
+pytestmark = pytest.mark.gpu
+
+THEORY_RTOL = 1e-10
+
+
+def check(spec, N, seed, solved=False):
+    import desilike_b200
+    plan = desilike_b200.Plan(spec)
+    X = configs.sample_points(spec, N, seed=seed)
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    got = plan.eval(X)
+    theory = plan.theory(X)
+    scale = np.max(np.abs(ref['flattheory']), axis=0)
+    assert np.max(np.abs(theory - ref['flattheory']) / scale) < THEORY_RTOL
+    for key in ['loglikelihood', 'logprior', 'logposterior']:
+        tol = 1e-8 * np.maximum(1., np.abs(ref[key]))
+        assert np.all(np.abs(got[key] - ref[key]) <= tol), (key, np.max(np.abs(got[key] - ref[key])))
+    assert np.max(np.abs(got['loglikelihood'] - ref['loglikelihood'])) < 5e-5  # |delta chi2| < 1e-4
+    if solved:
+        sc = np.maximum(1., np.abs(ref['x_solved']))
+        assert np.max(np.abs(got['x_solved'] - ref['x_solved']) / sc) < 1e-7
+    assert np.all(got['status'] == 0)
+    plan.close()
+    return got, ref
+
+
+def test_c2_small(gpu_required):
+    check(configs.config_c2(nkin=50, nbins=12, order=2), 300, seed=21)
+
+
+def test_c2_full_shape(gpu_required):
+    """BASELINE configs[1] shapes: T = 70, 3 x [3, 350] tables, W [108, 1050], n = 108."""
+    check(configs.config_c2(), 1000, seed=22)
+
+
+def test_c5_two_tracers_solved(gpu_required):
+    check(configs.config_c5(ntracers=2, nkin=40, nbins=10, order=2, solved=True), 200, seed=23, solved=True)
+
+
+def test_c5_dense_precision(gpu_required):
+    check(configs.config_c5(ntracers=2, nkin=40, nbins=10, order=2, solved=True, dense=True), 130, seed=24, solved=True)
+
+
+def test_c5_five_tracers(gpu_required):
+    check(configs.config_c5(ntracers=5, nkin=60, nbins=40, order=3, coefficients='random'), 257, seed=25)
+
+
+def test_ragged_and_edge_batches(gpu_required):
+    """N = 1, N not a multiple of the point tile, out-of-prior points (-inf), device-resident torch tensors."""
+    import torch
+    import desilike_b200
+    spec = configs.config_c2(nkin=50, nbins=12, order=2)
+    plan = desilike_b200.Plan(spec)
+    for N in [1, 127, 129]:
+        X = configs.sample_points(spec, N, seed=N)
+        ref = pipeline.evaluate(spec, X)
+        got = plan.eval(X)
+        assert np.allclose(got['logposterior'], ref['logposterior'], rtol=1e-9, atol=1e-8)
+    X = configs.sample_points(spec, 64, seed=5)
+    X[3, 0] = 1.5   # qpar outside uniform[0.8, 1.2]
+    X[7, 4] = -1.   # b1 outside [0, 10]
+    ref = pipeline.evaluate(spec, X)
+    got = plan.eval(X)
+    assert np.isneginf(got['logposterior'][[3, 7]]).all() and np.isneginf(ref['logposterior'][[3, 7]]).all()
+    assert (got['status'][[3, 7]] & 2).all()
+    mask = np.isfinite(ref['logposterior'])
+    assert np.allclose(got['logposterior'][mask], ref['logposterior'][mask], rtol=1e-9, atol=1e-8)
+    Xd = torch.as_tensor(X, device='cuda')
+    outd = plan.eval(Xd)
+    torch.cuda.synchronize()
+    assert np.array_equal(outd['logposterior'].cpu().numpy(), got['logposterior'])
+    plan.close()
+
+
+def test_full_size_properties(gpu_required):
+    """At BASELINE's full batch size (65 536 points): chunk-independence and permutation equivariance (size-independent checks)."""
+    import desilike_b200
+    spec = configs.config_c2(coefficients='random')
+    plan = desilike_b200.Plan(spec)
+    N = 65536
+    X = configs.sample_points(spec, N, seed=31)
+    full = plan.eval(X)['logposterior']
+    perm = np.random.default_rng(0).permutation(N)
+    assert np.array_equal(plan.eval(X[perm])['logposterior'], full[perm])
+    parts = np.concatenate([plan.eval(X[i:i + 10007])['logposterior'] for i in range(0, N, 10007)])
+    assert np.array_equal(parts, full)
+    sub = np.random.default_rng(1).choice(N, 256, replace=False)
+    ref = pipeline.evaluate(spec, X[sub])['logposterior']
+    assert np.allclose(full[sub], ref, rtol=1e-9, atol=1e-8)
+    plan.close()
+
+
+def test_fp64_peak_measurement(gpu_required):
+    import desilike_b200
+    dmma = desilike_b200.measure_fp64_peak('dmma')
+    dfma = desilike_b200.measure_fp64_peak('dfma')
+    print('FP64 peak TFLOP/s: DMMA {:.2f} DFMA {:.2f}'.format(dmma, dfma))
+    assert dmma > 1. and dfma > 1.
