@@ -4,8 +4,8 @@ Scope: ONE hot path -- N parameter points through emulated / Kaiser / BAO theory
 analytic marginalisation -> prior -- behind desilike's calling conventions.  See DESIGN.md / INTEGRATION.md.
 """
 from ._capi import DesilikeB200Error, load as load_library
-from .plan import Plan, launch_count, measure_fp64_peak
+from .plan import Plan, launch_count, measure_fp64_peak, pinned_empty
 from .lowering import Lowered, LoweringError
 
-__all__ = ['Plan', 'Lowered', 'LoweringError', 'DesilikeB200Error', 'load_library', 'launch_count', 'measure_fp64_peak']
+__all__ = ['Plan', 'Lowered', 'LoweringError', 'DesilikeB200Error', 'load_library', 'launch_count', 'measure_fp64_peak', 'pinned_empty']
 __version__ = '0.1.0'

@@ -56,9 +56,13 @@ class Plan(object):
         if X.ndim != 2 or X.shape[1] != self.d:
             raise ValueError('expected params of shape (N, {:d}), got {}'.format(self.d, X.shape))
         N = X.shape[0]
-        res = dict(logposterior=np.empty(N), loglikelihood=np.empty(N), logprior=np.empty(N))
-        xs = np.empty((N, self.ns)) if (return_solved and self.ns) else None
-        st = np.empty(N, dtype=np.int32) if return_status else None
+        if out is not None:   # caller-provided (e.g. pinned) host buffers
+            res = {key: out[key] for key in ['logposterior', 'loglikelihood', 'logprior']}
+            xs, st = out.get('x_solved_plan_order'), out.get('status')
+        else:
+            res = dict(logposterior=np.empty(N), loglikelihood=np.empty(N), logprior=np.empty(N))
+            xs = np.empty((N, self.ns)) if (return_solved and self.ns) else None
+            st = np.empty(N, dtype=np.int32) if return_status else None
         _capi.check(self._lib.dlb_eval_batch(self._handle, X.ctypes.data, N, res['logposterior'].ctypes.data, res['loglikelihood'].ctypes.data,
                                              res['logprior'].ctypes.data, xs.ctypes.data if xs is not None else None,
                                              st.ctypes.data if st is not None else None, None))
@@ -71,6 +75,7 @@ class Plan(object):
         if X.dtype != torch.float64 or not X.is_contiguous() or X.dim() != 2 or X.shape[1] != self.d:
             raise ValueError('expected a contiguous float64 CUDA tensor of shape (N, {:d})'.format(self.d))
         N = X.shape[0]
+        own = out is None
         if out is None:
             out = dict(logposterior=torch.empty(N, dtype=torch.float64, device=X.device), loglikelihood=torch.empty(N, dtype=torch.float64, device=X.device),
                        logprior=torch.empty(N, dtype=torch.float64, device=X.device))
@@ -80,7 +85,7 @@ class Plan(object):
         ptr = lambda key: out[key].data_ptr() if key in out else None
         _capi.check(self._lib.dlb_eval_batch(self._handle, X.data_ptr(), N, ptr('logposterior'), ptr('loglikelihood'), ptr('logprior'),
                                              ptr('x_solved_plan_order'), ptr('status'), ctypes.c_void_p(stream)))
-        if 'x_solved_plan_order' in out:
+        if own and 'x_solved_plan_order' in out:
             out['x_solved'] = out['x_solved_plan_order'][:, torch.as_tensor(self._unperm, device=X.device)]
         return out
 
@@ -113,6 +118,13 @@ class Plan(object):
         a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
         _capi.check(self._lib.dlb_last_kernel_ms(self._handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return dict(features=a.value, contract=b.value, solve=c.value)
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """Page-locked host array (through torch's caching host allocator) for the host-buffer entry points."""
+    import torch
+    tdtype = {np.dtype('f8'): torch.float64, np.dtype('i4'): torch.int32}[np.dtype(dtype)]
+    return torch.empty(shape, dtype=tdtype, pin_memory=True).numpy()
 
 
 def launch_count():

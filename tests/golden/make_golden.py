@@ -1,0 +1,51 @@
+"""Generate tests/golden/*.npz: outputs of the reference's OWN NumPy code path (under stub third-party modules) on
+seeded inputs.  Runs only in the build container (needs /root/reference); the fixtures are committed and travel.
+
+    python tests/golden/make_golden.py
+
+Each fixture stores the config name + kwargs (the spec is rebuilt from its seed by oracle/configs.py), the points X and the
+reference's logposterior / loglikelihood / logprior / flattheory.  See oracle/ref_harness.py for how the reference is run.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import configs, ref_harness  # noqa: E402
+
+CASES = {
+    'c1_kaiser_shapefit': dict(config='config_c1', kwargs={}, eftlike=False, mode=None, n=64, seed=101),
+    'kaiser_window': dict(config='config_kaiser_window', kwargs=dict(eftlike=False, solved=False), eftlike=False, mode=None, n=48, seed=102),
+    'eftlike_sampled': dict(config='config_kaiser_window', kwargs=dict(eftlike=True, solved=False), eftlike=True, mode=None, n=48, seed=103),
+    'eftlike_marg': dict(config='config_kaiser_window', kwargs=dict(eftlike=True, solved=True), eftlike=True, mode='.marg', n=48, seed=104),
+    'eftlike_best': dict(config='config_kaiser_window', kwargs=dict(eftlike=True, solved=True), eftlike=True, mode='.best', n=48, seed=105),
+    'kaiser_window_cubic': dict(config='config_kaiser_window', kwargs=dict(eftlike=False, solved=False, transform='cubic'), eftlike=False, mode=None, n=32, seed=106),
+}
+
+
+def build_spec(case):
+    spec = getattr(configs, case['config'])(**case['kwargs'])
+    if case['mode'] == '.best':
+        for s in spec['solved']: s['marg'] = False
+    return spec
+
+
+def main():
+    for name, case in CASES.items():
+        spec = build_spec(case)
+        like = ref_harness.reference_kaiser_likelihood(spec, eftlike=case['eftlike'], solved_mode=case['mode'])
+        if spec['solved']: ref_harness.install_jacfwd_stub()
+        X = configs.sample_points(spec, case['n'], seed=case['seed'])
+        if not spec['solved']:
+            X[1, 0] = 1.3   # out of prior -> -inf
+        ref = ref_harness.run_vmap(like, spec, X)
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), case=json.dumps(case), X=X, **ref)
+        print(name, X.shape, ref['logposterior'][:3])
+
+
+if __name__ == '__main__':
+    main()

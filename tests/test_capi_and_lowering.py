@@ -1,0 +1,103 @@
+"""Host logic on CPU: the C-ABI library loads and exports every symbol of include/desilike_b200.h; the plan-time folding
+(desilike_b200/lowering.py) reproduces the oracle through a NumPy emulation of the kernels (tests/lowered_numpy.py)."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+from oracle import configs, pipeline  # noqa: E402
+import lowered_numpy  # noqa: E402
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    import desilike_b200
+    from desilike_b200 import _capi, build
+    build.build()
+    header = open(os.path.join(ROOT, 'include', 'desilike_b200.h')).read()
+    declared = set(re.findall(r'\b(dlb_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_capi.SYMBOLS), declared ^ set(_capi.SYMBOLS)
+    lib = ctypes.CDLL(build.LIBPATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib = desilike_b200.load_library()
+    assert lib.dlb_abi_version() == _capi.DLB_ABI_VERSION
+    assert lib.dlb_launch_count() == 0
+
+
+def test_struct_layouts_match_header():
+    import ctypes
+    from desilike_b200 import _capi
+    assert ctypes.sizeof(_capi.CoefDesc) == 8 + 4 + 4 * 4 + 4 * 4 + 4
+    assert ctypes.sizeof(_capi.TermDesc) == 32
+    assert _capi.PlanDesc.abi_version.offset == 0 and _capi.PlanDesc.prior_kind.offset == 8
+
+
+def test_no_gpu_means_loud_failure():
+    import desilike_b200
+    if desilike_b200.load_library().dlb_device_count() > 0:
+        pytest.skip('GPU present')
+    with pytest.raises(desilike_b200.DesilikeB200Error):
+        desilike_b200.Plan(configs.config_c2(nkin=20, nbins=6, order=1))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'desilike_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith('.py'):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), fn
+
+
+CASES = {
+    'c2': lambda: configs.config_c2(nkin=50, nbins=12, order=2),
+    'c2_random': lambda: configs.config_c2(nkin=30, nbins=8, order=3, coefficients='random'),
+    'c5_solved': lambda: configs.config_c5(ntracers=2, nkin=40, nbins=10, order=2, solved=True),
+    'c5_dense': lambda: configs.config_c5(ntracers=2, nkin=40, nbins=10, order=2, solved=True, dense=True),
+    'c5_three': lambda: configs.config_c5(ntracers=3, nkin=30, nbins=8, order=2),
+}
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_lowering_reproduces_oracle(name):
+    from desilike_b200.lowering import Lowered
+    spec = CASES[name]()
+    low = Lowered(spec)
+    X = configs.sample_points(spec, 24, seed=3)
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    got = lowered_numpy.evaluate(low, X)
+    theory = lowered_numpy.evaluate(low, X, white=False)
+    assert np.max(np.abs(theory / ref['flattheory'] - 1)) < 1e-12
+    for key in ['logposterior', 'loglikelihood', 'logprior']:
+        assert np.allclose(got[key], ref[key], rtol=1e-10, atol=1e-8), key
+    if spec['solved']:
+        assert np.allclose(got['x_solved'], ref['x_solved'], rtol=1e-7, atol=1e-7)
+
+
+def test_marg_parameters_are_ordered_first():
+    from desilike_b200.lowering import Lowered
+    spec = configs.config_c5(ntracers=2, nkin=20, nbins=6, order=1, solved=True)
+    for i, s in enumerate(spec['solved']): s['marg'] = bool(i % 2)
+    low = Lowered(spec)
+    assert low.nmarg == sum(s['marg'] for s in spec['solved'])
+    flags = [spec['solved'][i]['marg'] for i in low.solved_order]
+    assert flags == sorted(flags, reverse=True)
+    X = configs.sample_points(spec, 6, seed=1)
+    ref = pipeline.evaluate(spec, X)
+    got = lowered_numpy.evaluate(low, X)
+    assert np.allclose(got['logposterior'], ref['logposterior'], rtol=1e-10, atol=1e-8)
+    assert np.allclose(got['x_solved'], ref['x_solved'], rtol=1e-7, atol=1e-7)
+
+
+def test_unsupported_features_fail_loudly():
+    from desilike_b200.lowering import Lowered, LoweringError
+    spec = configs.config_kaiser_window(transform='cubic', nkin=20, nbins=6)
+    spec['observables'][0]['theory'] = configs.config_c2(nkin=20, nbins=6, order=1)['observables'][0]['theory']
+    with pytest.raises(LoweringError):
+        Lowered(spec)
