@@ -67,9 +67,10 @@ struct ContractParams {
   int npart;                             // partial sums per (point, column block)
   double* partial; long long npad;       // [(poff + cb * npart + e) * npad + p]
   long long poff;
-  double* theory; int ntheory; int coloff; int ncols;  // theory mode: out [N, ntheory], this block's first column and width
-  long long nvalid;                      // valid rows (N)
-  int mode;                              // 0 eval (Gram partials), 1 theory
+  double* out; long long ostride; int ocol0; int ncols;  // output mode: out[row * ostride + ocol0 + col] for col < ncols, row < out_rows
+  long long out_rows;
+  int act;                               // output mode: activation applied to (slot 0 + r0): 0 none, 1 silu, 2 relu, 3 tanh
+  int mode;                              // 0 eval (Gram partials), 1 output (theory vectors / MLP layer)
   int nstages;
 };
 
@@ -86,11 +87,14 @@ struct DevGen {
   double pdef[MAXP];
   const int* idata; int ni;
   const double* ddata; long long nd;
+  int aux[8];             // kind-specific layout offsets computed at plan time
 };
 
 struct DevCoef { double scale; int nf; int idx[DLB_COEF_MAXF]; int pow[DLB_COEF_MAXF]; };
 
 int launch_features(const DevGen& g, const double* params, int d, long long N, long long npad, double* F, int fstride, cudaStream_t stream);
+int launch_theory_features(const DevGen& g, const double* params, int d, long long N, long long npad, double* F, int fstride, cudaStream_t stream);  // csrc/theory_kernels.cu
+int launch_mlp_input(const DevGen& g, const double* params, int d, long long N, long long npad, double* F, int fstride, cudaStream_t stream);
 int launch_coefs(const DevCoef* coefs, int ncoef, const double* params, int d, long long N, long long npad, double* C, int cstride, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -170,7 +170,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const __grid_cons
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int col = cb * BN + colw + nt * 8 + e;
-          if (row < p.nvalid && col < p.ncols) p.theory[row * p.ntheory + p.coloff + col] = acc[0][mt][nt][e] + r0[colw + nt * 8 + e];
+          if (row < p.out_rows && col < p.ncols) {
+            double v = acc[0][mt][nt][e] + r0[colw + nt * 8 + e];
+            if (p.act == 1) v = v / (1. + exp(-v));        // silu  (reference emulators/conversion.py:27)
+            else if (p.act == 2) v = fmax(v, 0.);          // relu  (:29)
+            else if (p.act == 3) v = tanh(v);              // tanh  (:31)
+            p.out[row * p.ostride + p.ocol0 + col] = v;
+          }
         }
     }
     return;

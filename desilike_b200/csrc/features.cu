@@ -43,6 +43,27 @@ __global__ void taylor_features_kernel(const DevGen g, const double* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// MLP input stage: the x-operation '(v - lo) / (hi - lo)' (reference emulators/conversion.py:76-77) as v * a + b, written
+// into the generator's xs sub-segment (g.aux[0]); also sets the constant pair (1, 0).  ddata = [a (d), b (d), ...].
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void mlp_input_kernel(const DevGen g, const double* __restrict__ params, int d, long long N, long long npad,
+                                 double* __restrict__ F, int fstride) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = g.nparams + 2;
+  const long long p = idx / w;
+  const int j = (int)(idx - p * w);
+  if (p >= npad) return;
+  double* row = F + p * fstride + g.foff;
+  if (j >= g.nparams) { row[j - g.nparams] = (j == g.nparams && p < N) ? 1. : 0.; return; }
+  double v = 0.;
+  if (p < N) {
+    const double x = g.pidx[j] >= 0 ? params[p * d + g.pidx[j]] : g.pdef[j];
+    v = x * g.ddata[j] + g.ddata[g.nparams + j];
+  }
+  row[g.aux[0] + j] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // bias-monomial coefficients  c = scale * prod_f theta[idx_f]^pow_f   (tracer combine, reference full_shape.py:545-550)
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void coef_kernel(const DevCoef* __restrict__ coefs, int ncoef, const double* __restrict__ params, int d, long long N,
@@ -75,8 +96,16 @@ int launch_features(const DevGen& g, const double* params, int d, long long N, l
     DLB_CUDA(cudaGetLastError());
     return DLB_OK;
   }
-  set_error("feature generator kind " + std::to_string(g.kind) + " not implemented");
-  return DLB_ERR_UNSUPPORTED;
+  return launch_theory_features(g, params, d, N, npad, F, fstride, stream);
+}
+
+int launch_mlp_input(const DevGen& g, const double* params, int d, long long N, long long npad, double* F, int fstride, cudaStream_t stream) {
+  const int threads = 256;
+  const long long total = npad * (g.nparams + 2);
+  mlp_input_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(g, params, d, N, npad, F, fstride);
+  g_launches++;
+  DLB_CUDA(cudaGetLastError());
+  return DLB_OK;
 }
 
 int launch_coefs(const DevCoef* coefs, int ncoef, const double* params, int d, long long N, long long npad, double* C, int cstride,

@@ -22,6 +22,8 @@ struct Block {
   EntryMap* d_map = nullptr;
 };
 
+struct MlpLayers { int act = 0; std::vector<Block> layers; };
+
 }  // namespace dlb
 
 struct dlb_plan {
@@ -29,6 +31,7 @@ struct dlb_plan {
   int d = 0, ngen = 0, ncoef = 0, cstride = 1, fstride = 4, ns = 0, nmarg = 0, ntheory = 0;
   std::vector<dlb::DevGen> gens;
   std::vector<dlb::Block> blocks;
+  std::vector<dlb::MlpLayers> mlps;   // one per generator (empty unless kind == MLP)
   dlb::DevCoef* d_coefs = nullptr;
   int* d_prior_kind = nullptr;
   double *d_prior_lo = nullptr, *d_prior_hi = nullptr, *d_prior_loc = nullptr, *d_prior_scale = nullptr;
@@ -74,35 +77,33 @@ static Variant choose_variant(int nslots) {
   return Variant{8, 1, 4};
 }
 
-static int build_block(dlb_plan* plan, const dlb_plan_desc* desc, const dlb_block_desc& bd, Block& blk) {
-  DLB_REQUIRE(bd.ncols > 0 && bd.nslots >= 1 && bd.nslots <= 8, "block: ncols > 0 and 1 <= nslots <= 8 required");
-  DLB_REQUIRE(bd.nterms > 0 && bd.terms && bd.matrices_white && bd.r0_white, "block: terms / matrices_white / r0_white required");
-  blk.ncols = bd.ncols; blk.nslots = bd.nslots; blk.nconst = bd.nconst;
-  blk.var = choose_variant(bd.nslots);
+struct TermSpec { int slot, coef, fcol, K; const double* white; const double* plain; };  // matrices [K, ncols] row-major
+
+// Chunk the terms, pre-tile their matrices into the contraction kernel's shared-memory image and upload everything.
+static int build_block_core(dlb_plan* plan, int ncols, int nslots, const std::vector<TermSpec>& terms, const double* r0_white,
+                            const double* t0_plain, int nconst, const double* gconst_white, Block& blk) {
+  blk.ncols = ncols; blk.nslots = nslots; blk.nconst = nconst;
+  blk.var = choose_variant(nslots);
   const int BN = variant_bn(blk.var);
-  blk.ncb = (bd.ncols + BN - 1) / BN;
+  blk.ncb = (ncols + BN - 1) / BN;
   std::vector<Chunk> chunks;
-  struct Src { long long moff; int k0; int K; };
+  struct Src { int term; int k0; };
   std::vector<Src> srcs;
-  for (int t = 0; t < bd.nterms; ++t) {
-    const dlb_term_desc& td = bd.terms[t];
-    DLB_REQUIRE(td.slot >= 0 && td.slot < bd.nslots, "term slot out of range");
-    DLB_REQUIRE(td.coef >= -1 && td.coef < desc->ncoef, "term coef out of range");
-    DLB_REQUIRE(td.gen >= 0 && td.gen < desc->ngen, "term generator out of range");
-    DLB_REQUIRE(td.K > 0 && td.foff >= 0 && (td.foff % 2) == 0 && td.foff + td.K <= plan->gens[td.gen].nfeat, "term feature range invalid (foff must be even)");
+  for (size_t t = 0; t < terms.size(); ++t) {
+    const TermSpec& td = terms[t];
     const int Kpad = (td.K + 3) & ~3;
     const int nch = (Kpad + KC - 1) / KC;
     int kc = (Kpad + nch - 1) / nch;
     kc = (kc + 3) & ~3;
     for (int k0 = 0; k0 < Kpad; k0 += kc) {
       Chunk ch;
-      ch.slot = td.slot; ch.coef = td.coef; ch.fcol = plan->gens[td.gen].foff + td.foff + k0; ch.kc = std::min(kc, Kpad - k0);
+      ch.slot = td.slot; ch.coef = td.coef; ch.fcol = td.fcol + k0; ch.kc = std::min(kc, Kpad - k0);
       chunks.push_back(ch);
-      srcs.push_back(Src{td.moff, k0, td.K});
+      srcs.push_back(Src{(int)t, k0});
     }
   }
   blk.nchunks = (int)chunks.size();
-  blk.npart = bd.nslots * (bd.nslots + 1) / 2 + bd.nslots * bd.nconst;
+  blk.npart = nslots * (nslots + 1) / 2 + nslots * nconst;
   blk.nstages = 0;
   for (int s = 4; s >= 2; --s)
     if (contract_smem_bytes(blk.var, s, blk.nchunks, blk.npart) <= 227 * 1024) { blk.nstages = s; break; }
@@ -112,34 +113,56 @@ static int build_block(dlb_plan* plan, const dlb_plan_desc* desc, const dlb_bloc
   const size_t tile = (size_t)BN * KC;
   std::vector<double> tiles((size_t)blk.ncb * blk.nchunks * tile);
   for (int pass = 0; pass < 2; ++pass) {
-    const double* mats = pass == 0 ? bd.matrices_white : bd.matrices_plain;
-    if (!mats) continue;
+    bool any = false;
+    for (const TermSpec& td : terms) any = any || (pass == 0 ? td.white : td.plain) != nullptr;
+    if (!any) continue;
     std::fill(tiles.begin(), tiles.end(), 0.);
     for (int cb = 0; cb < blk.ncb; ++cb)
       for (int c = 0; c < blk.nchunks; ++c) {
         double* dst = tiles.data() + ((size_t)cb * blk.nchunks + c) * tile;
-        const Src& s = srcs[c];
+        const TermSpec& td = terms[srcs[c].term];
+        const double* mat = pass == 0 ? td.white : td.plain;
+        if (!mat) continue;
         for (int n = 0; n < BN; ++n) {
           const int col = cb * BN + n;
-          if (col >= bd.ncols) break;
+          if (col >= ncols) break;
           for (int k = 0; k < chunks[c].kc; ++k) {
-            const int kk = s.k0 + k;
-            if (kk < s.K) dst[(size_t)n * KC + k] = mats[s.moff + (long long)kk * bd.ncols + col];
+            const int kk = srcs[c].k0 + k;
+            if (kk < td.K) dst[(size_t)n * KC + k] = mat[(long long)kk * ncols + col];
           }
         }
       }
     DLB_TRY(upload(plan, tiles.data(), tiles.size(), pass == 0 ? &blk.d_tiles_white : &blk.d_tiles_plain));
   }
   std::vector<double> pad((size_t)blk.ncb * BN, 0.);
-  std::copy(bd.r0_white, bd.r0_white + bd.ncols, pad.begin());
-  DLB_TRY(upload(plan, pad.data(), pad.size(), &blk.d_r0_white));
-  if (bd.t0_plain) {
-    std::copy(bd.t0_plain, bd.t0_plain + bd.ncols, pad.begin());
+  if (r0_white) {
+    std::copy(r0_white, r0_white + ncols, pad.begin());
+    DLB_TRY(upload(plan, pad.data(), pad.size(), &blk.d_r0_white));
+  }
+  if (t0_plain) {
+    std::copy(t0_plain, t0_plain + ncols, pad.begin());
     DLB_TRY(upload(plan, pad.data(), pad.size(), &blk.d_t0_plain));
   }
-  std::vector<double> gpad((size_t)std::max(bd.nconst, 1) * blk.ncb * BN, 0.);
-  for (int i = 0; i < bd.nconst; ++i) std::copy(bd.gconst_white + (size_t)i * bd.ncols, bd.gconst_white + (size_t)(i + 1) * bd.ncols, gpad.begin() + (size_t)i * blk.ncb * BN);
+  std::vector<double> gpad((size_t)std::max(nconst, 1) * blk.ncb * BN, 0.);
+  for (int i = 0; i < nconst; ++i) std::copy(gconst_white + (size_t)i * ncols, gconst_white + (size_t)(i + 1) * ncols, gpad.begin() + (size_t)i * blk.ncb * BN);
   DLB_TRY(upload(plan, gpad.data(), gpad.size(), &blk.d_gconst));
+  return DLB_OK;
+}
+
+static int build_block(dlb_plan* plan, const dlb_plan_desc* desc, const dlb_block_desc& bd, Block& blk) {
+  DLB_REQUIRE(bd.ncols > 0 && bd.nslots >= 1 && bd.nslots <= 8, "block: ncols > 0 and 1 <= nslots <= 8 required");
+  DLB_REQUIRE(bd.nterms > 0 && bd.terms && bd.matrices_white && bd.r0_white, "block: terms / matrices_white / r0_white required");
+  std::vector<TermSpec> terms;
+  for (int t = 0; t < bd.nterms; ++t) {
+    const dlb_term_desc& td = bd.terms[t];
+    DLB_REQUIRE(td.slot >= 0 && td.slot < bd.nslots, "term slot out of range");
+    DLB_REQUIRE(td.coef >= -1 && td.coef < desc->ncoef, "term coef out of range");
+    DLB_REQUIRE(td.gen >= 0 && td.gen < desc->ngen, "term generator out of range");
+    DLB_REQUIRE(td.K > 0 && td.foff >= 0 && (td.foff % 2) == 0 && td.foff + td.K <= plan->gens[td.gen].nfeat, "term feature range invalid (foff must be even)");
+    terms.push_back(TermSpec{td.slot, td.coef, plan->gens[td.gen].foff + td.foff, td.K, bd.matrices_white + td.moff,
+                             bd.matrices_plain ? bd.matrices_plain + td.moff : nullptr});
+  }
+  DLB_TRY(build_block_core(plan, bd.ncols, bd.nslots, terms, bd.r0_white, bd.t0_plain, bd.nconst, bd.gconst_white, blk));
   // entry map of the Gram partials (order fixed by contract_kernel's epilogue)
   std::vector<EntryMap> map(blk.npart);
   const int R = bd.nslots;
@@ -158,6 +181,47 @@ static int build_block(dlb_plan* plan, const dlb_plan_desc* desc, const dlb_bloc
   for (const EntryMap& m : map)
     DLB_REQUIRE(m.kind == 0 || (m.i >= 0 && m.i < desc->ns && (m.kind == 1 || (m.j >= 0 && m.j < desc->ns))), "solved-parameter index out of range");
   DLB_TRY(upload(plan, map.data(), map.size(), &blk.d_map));
+  return DLB_OK;
+}
+
+// MLP generator (reference emulators/conversion.py:18-33): x-operation (affine min-max scale) -> hidden layers
+// v <- act(v W_l + b_l), each one an output-mode launch of the DMMA contraction kernel writing the next feature segment.
+// The last linear layer and the inverse y-operations are affine in the last hidden activations and are folded into
+// the term matrices by the host (desilike_b200/mlp.py).
+//   idata = [nhidden, act, d, H_1 .. H_nhidden];  ddata = [a (d), b (d), then per hidden layer W [Hin, Hout] row-major, bias [Hout]]
+static int build_mlp(dlb_plan* plan, const dlb_generator_desc& gd, DevGen& g, MlpLayers& mlp) {
+  DLB_REQUIRE(gd.ni >= 3 && gd.idata, "mlp generator: idata = [nhidden, act, d, H_1..]");
+  const int nh = gd.idata[0], act = gd.idata[1], d = gd.idata[2];
+  DLB_REQUIRE(nh >= 0 && gd.ni == 3 + nh && d == gd.nparams && act >= 0 && act <= 3, "mlp generator: inconsistent idata");
+  std::vector<int> width(nh + 1);
+  width[0] = d;
+  long long need = 2LL * d;
+  for (int l = 0; l < nh; ++l) { width[l + 1] = gd.idata[3 + l]; DLB_REQUIRE(width[l + 1] > 0, "mlp: layer width"); need += (long long)width[l] * width[l + 1] + width[l + 1]; }
+  DLB_REQUIRE(gd.nd == need, "mlp generator: ddata size mismatch");
+  DLB_REQUIRE(gd.nfeat == 2 + width[nh], "mlp generator: nfeat must be 2 + last hidden width");
+  auto pad4 = [](int n) { return (n + 3) & ~3; };
+  // segment layout: [1, 0, h_last | xs | h_1 .. h_{nh-1}]  (visible features first)
+  std::vector<int> off(nh + 1);
+  int cur = pad4(2 + width[nh]);
+  if (nh == 0) off[0] = 2;
+  else {
+    off[nh] = 2;
+    off[0] = cur; cur += pad4(width[0]);
+    for (int l = 1; l < nh; ++l) { off[l] = cur; cur += pad4(width[l]); }
+  }
+  g.fpad = cur;
+  g.aux[0] = off[0];
+  mlp.act = act;
+  const double* w = gd.ddata + 2 * d;
+  for (int l = 0; l < nh; ++l) {
+    Block blk;
+    std::vector<TermSpec> terms{TermSpec{0, -1, g.foff + off[l], width[l], nullptr, w}};
+    const double* bias = w + (size_t)width[l] * width[l + 1];
+    DLB_TRY(build_block_core(plan, width[l + 1], 1, terms, nullptr, bias, 0, nullptr, blk));
+    blk.coloff = g.foff + off[l + 1];
+    mlp.layers.push_back(blk);
+    w = bias + width[l + 1];
+  }
   return DLB_OK;
 }
 
@@ -183,9 +247,24 @@ static int run_front(dlb_plan* plan, const double* d_params, long long N, long l
     int rc = launch_coefs(plan->d_coefs, plan->ncoef, d_params, plan->d, N, npad, plan->w_C, plan->cstride, stream);
     if (rc) return rc;
   }
-  for (const DevGen& g : plan->gens) {
-    int rc = launch_features(g, d_params, plan->d, N, npad, plan->w_F, plan->fstride, stream);
-    if (rc) return rc;
+  for (size_t ig = 0; ig < plan->gens.size(); ++ig) {
+    const DevGen& g = plan->gens[ig];
+    if (g.kind == DLB_GEN_MLP) {
+      DLB_TRY(launch_mlp_input(g, d_params, plan->d, N, npad, plan->w_F, plan->fstride, stream));
+      for (const Block& blk : plan->mlps[ig].layers) {
+        ContractParams cp;
+        std::memset(&cp, 0, sizeof(cp));
+        cp.F = plan->w_F; cp.fstride = plan->fstride; cp.C = plan->w_C; cp.cstride = plan->cstride;
+        cp.chunks = blk.d_chunks; cp.nchunks = blk.nchunks; cp.tiles = blk.d_tiles_plain; cp.r0 = blk.d_t0_plain;
+        cp.gconst = blk.d_gconst; cp.nslots = 1; cp.npad = npad;
+        cp.out = plan->w_F; cp.ostride = plan->fstride; cp.ocol0 = blk.coloff; cp.ncols = blk.ncols; cp.out_rows = npad;
+        cp.act = plan->mlps[ig].act; cp.mode = 1; cp.nstages = blk.nstages;
+        const int BM = variant_bm(blk.var);
+        DLB_TRY(launch_contract(blk.var, cp, (int)((npad + BM - 1) / BM), blk.ncb, stream));
+      }
+      continue;
+    }
+    DLB_TRY(launch_features(g, d_params, plan->d, N, npad, plan->w_F, plan->fstride, stream));
   }
   return DLB_OK;
 }
@@ -199,8 +278,8 @@ static int run_contract(dlb_plan* plan, long long N, long long npad, int mode, d
     cp.r0 = mode == 0 ? blk.d_r0_white : blk.d_t0_plain;
     cp.gconst = blk.d_gconst; cp.nconst = blk.nconst; cp.nslots = blk.nslots; cp.npart = blk.npart;
     cp.partial = plan->w_partial; cp.npad = npad; cp.poff = blk.poff;
-    cp.theory = d_theory; cp.ntheory = plan->ntheory; cp.coloff = blk.coloff; cp.ncols = blk.ncols;
-    cp.nvalid = N; cp.mode = mode; cp.nstages = blk.nstages;
+    cp.out = d_theory; cp.ostride = plan->ntheory; cp.ocol0 = blk.coloff; cp.ncols = blk.ncols;
+    cp.out_rows = N; cp.act = 0; cp.mode = mode; cp.nstages = blk.nstages;
     if (mode == 1 && (!cp.tiles || !cp.r0)) { set_error("plan was built without un-whitened matrices: theory_batch unavailable"); return DLB_ERR_ARG; }
     const int BM = variant_bm(blk.var);
     int rc = launch_contract(blk.var, cp, (int)((N + BM - 1) / BM), blk.ncb, stream);
@@ -271,6 +350,14 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
     DLB_TRY(upload(plan, gd.ddata, (size_t)gd.nd, &dd));
     g.idata = di; g.ni = gd.ni; g.ddata = dd; g.nd = gd.nd;
     if (gd.kind == DLB_GEN_TAYLOR) DLB_REQUIRE(gd.nfeat > 2 && gd.ni == (gd.nfeat - 2) * gd.nparams && gd.nd == gd.nparams, "taylor generator: nfeat = 2 + T, idata = powers[T, d], ddata = center[d]");
+    plan->mlps.emplace_back();
+    if (gd.kind == DLB_GEN_MLP) DLB_TRY(build_mlp(plan, gd, g, plan->mlps.back()));
+    if (gd.kind == DLB_GEN_KAISER || gd.kind == DLB_GEN_BAO) {
+      DLB_REQUIRE(gd.ni >= 8, "theory generator: idata header missing");
+      g.fpad = std::max(g.fpad, (gd.idata[7] + 3) & ~3);   // idata[7] = total segment length incl. scratch
+      g.aux[1] = gd.idata[3];                              // nt (template knots), needed on the host for shared-memory sizing
+      g.aux[2] = gd.idata[0]; g.aux[3] = gd.idata[1]; g.aux[4] = gd.idata[5];
+    }
     foff += g.fpad;
     plan->gens.push_back(g);
   }

@@ -70,7 +70,7 @@ class _Generator(object):
         defaults = theory.get('defaults', {})
         self.param_idx = i32([names.index(p) if p in names else -1 for p in self.params])
         self.tables = {}  # name -> (foff, K, D [K, nin] or None for identity)
-        self.keep = []
+        self._names = names
         if self.kind_name == 'taylor':
             self.kind = _capi.GEN_TAYLOR
             center, powers = f64(theory['center']), i32(theory['powers'])
@@ -92,6 +92,7 @@ class _Generator(object):
         g = _capi.GeneratorDesc()
         g.kind, g.nparams, g.nfeat = self.kind, len(self.params), int(self.nfeat)
         self.param_idx, self.param_default = i32(self.param_idx), f64(self.param_default)
+        assert len(self.param_idx) == len(self.params) == len(self.param_default)
         self.idata, self.ddata = i32(self.idata), f64(self.ddata)
         g.param_idx, g.param_default = as_ptr(self.param_idx, ctypes.c_int32), as_ptr(self.param_default)
         g.ni, g.idata = int(self.idata.size), as_ptr(self.idata, ctypes.c_int32)

@@ -1,0 +1,48 @@
+"""Lowering of an MLP emulator engine (reference desilike/emulators/conversion.py:18-33,76-104; predict in cosmoprimo,
+restated in oracle/core.py:mlp_predict) onto the CUDA path.
+
+x-operation (min-max scale) -> affine ``v * a + b``; hidden layers run on the GPU (DMMA GEMM + activation epilogue);
+the LAST dense layer and the inverse y-operations (PCA ``v @ eigvecs + mean``, min-max un-scaling) are affine in the last
+hidden activations, so they are folded into each table's linear map ``table = [1, 0, h] . [c; 0; A]``.
+"""
+import numpy as np
+
+from . import _capi
+from ._capi import f64
+
+ACTIVATIONS = {'identity': 0, 'silu': 1, 'relu': 2, 'tanh': 3}
+
+
+def lower_mlp(gen, theory, defaults):
+    mlp = theory['mlp']
+    gen.kind = _capi.GEN_MLP
+    d = len(gen.params)
+    act = mlp.get('activation', 'silu')
+    if act not in ACTIVATIONS:
+        raise ValueError('activation {!r} is not on the CUDA path (supported: {})'.format(act, sorted(ACTIVATIONS)))
+    if mlp.get('xlimits') is not None:
+        lim = f64(mlp['xlimits'])
+        a = 1. / (lim[:, 1] - lim[:, 0])
+        b = -lim[:, 0] * a
+    else:
+        a, b = np.ones(d), np.zeros(d)
+    layers = [(f64(k), f64(bb)) for k, bb in mlp['layers']]
+    hidden, (W_out, b_out) = layers[:-1], layers[-1]
+    widths = [k.shape[1] for k, _ in hidden]
+    gen.param_default = f64([defaults.get(p, 0.) for p in gen.params])
+    gen.idata = np.array([len(hidden), ACTIVATIONS[act], d] + widths, dtype=np.int32)
+    gen.ddata = np.concatenate([a, b] + [np.concatenate([k.ravel(), bb]) for k, bb in hidden]) if True else None
+    H = widths[-1] if widths else d
+    gen.nfeat = 2 + H
+    # fold last layer + inverse y-operations:  y = h . A + c
+    A, c = W_out, b_out
+    if mlp.get('pca') is not None:
+        eigvecs, mean = f64(mlp['pca'][0]), f64(mlp['pca'][1])
+        A, c = A @ eigvecs, c @ eigvecs + mean
+    if mlp.get('ylimits') is not None:
+        lim = f64(mlp['ylimits'])
+        scale = lim[:, 1] - lim[:, 0]
+        A, c = A * scale, c * scale + lim[:, 0]
+    for name, sl in theory['tables'].items():
+        D = np.concatenate([c[sl][None, :], np.zeros((1, c[sl].size)), A[:, sl]], axis=0)
+        gen.tables[name] = (0, H + 2, D)

@@ -1,0 +1,121 @@
+"""GPU parity of the theory generators (Kaiser + ShapeFit + AP, MLP) and of the CUDA path against the committed golden
+fixtures, i.e. against outputs of the reference's OWN code (tests/golden/make_golden.py).  Run with ``-m gpu``."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import configs, pipeline
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIXTURES = sorted(f for f in glob.glob(os.path.join(HERE, 'golden', '*.npz')) if 'cubic' not in f)
+
+
+def test_kaiser_tables_match_oracle(gpu_required):
+    """Feature-level parity: pk_dd / pk_dt / pk_tt tables, relative 1e-10 (FP64)."""
+    import desilike_b200
+    spec = configs.config_kaiser_window(eftlike=True, solved=True)
+    plan = desilike_b200.Plan(spec)
+    X = configs.sample_points(spec, 77, seed=3)
+    feats = plan.features(0, X)
+    gen = plan.lowered.gens[0]
+    tabs = pipeline.theory_tables(spec['observables'][0]['theory'], X, spec['params'])
+    assert np.all(feats[:, 0] == 1.) and np.all(feats[:, 1] == 0.)
+    for name in ['pk_dd', 'pk_dt', 'pk_tt', 'pk11_l0']:
+        foff, K, _ = gen.tables[name]
+        got, ref = feats[:, foff:foff + K], tabs[name]
+        assert np.max(np.abs(got - ref) / np.max(np.abs(ref), axis=0)) < 1e-10, name
+    plan.close()
+
+
+@pytest.mark.parametrize('fn', FIXTURES, ids=[os.path.basename(f)[:-4] for f in FIXTURES])
+def test_cuda_matches_reference_fixture(gpu_required, fn):
+    """CUDA path vs the reference's own outputs (Kaiser + ShapeFit, window, EFT-like terms, .marg / .best)."""
+    import desilike_b200
+    data = np.load(fn)
+    case = json.loads(str(data['case']))
+    spec = getattr(configs, case['config'])(**case['kwargs'])
+    if case['mode'] == '.best':
+        for s in spec['solved']: s['marg'] = False
+    plan = desilike_b200.Plan(spec)
+    X = data['X']
+    got = plan.eval(X)
+    theory = plan.theory(X)
+    scale = np.max(np.abs(data['flattheory']), axis=0)
+    assert np.max(np.abs(theory - data['flattheory']) / scale) < 1e-10
+    for key in ['logposterior', 'loglikelihood', 'logprior']:
+        ref = data[key]
+        finite = np.isfinite(ref)
+        if key == 'logposterior':
+            assert np.array_equal(np.isneginf(ref), np.isneginf(got[key]))
+        if key == 'logprior':
+            finite &= np.isfinite(got[key])
+        assert np.allclose(got[key][finite], ref[finite], rtol=1e-9, atol=1e-7), (key, np.max(np.abs(got[key][finite] - ref[finite])))
+    plan.close()
+
+
+def test_c1_full_batch(gpu_required):
+    """BASELINE configs[0]: Kaiser + ShapeFit -> chi2, 1024 points."""
+    import desilike_b200
+    spec = configs.config_c1()
+    plan = desilike_b200.Plan(spec)
+    X = configs.sample_points(spec, 1024, seed=8)
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    got = plan.eval(X)
+    assert np.max(np.abs(plan.theory(X) - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-10
+    assert np.allclose(got['logposterior'], ref['logposterior'], rtol=1e-9, atol=1e-6)
+    assert np.max(np.abs(got['loglikelihood'] - ref['loglikelihood']) / np.maximum(1., np.abs(ref['loglikelihood']))) < 1e-9
+    plan.close()
+
+
+def test_kaiser_with_damping_and_apmodes(gpu_required):
+    import desilike_b200
+    for apmode, pnames in [('qisoqap', ['qiso', 'qap']), ('qiso', ['qiso']), ('qap', ['qap'])]:
+        spec = configs.config_c1()
+        th = spec['observables'][0]['theory']
+        th['template'] = dict(th['template'], apmode=apmode)
+        th['params'] = pnames + ['dm', 'df', 'sigmapar', 'sigmaper']
+        th['defaults'] = dict(th['defaults'], qiso=1., qap=1.)
+        spec['params'] = pnames + ['dm', 'df', 'sigmapar', 'sigmaper', 'b1', 'sn0']
+        spec['priors'] = {}
+        rng = np.random.default_rng(4)
+        X = np.column_stack([rng.uniform(0.95, 1.05, 50) for _ in pnames] + [rng.uniform(-0.05, 0.05, 50), rng.uniform(0.9, 1.1, 50),
+                            rng.uniform(0., 5., 50), rng.uniform(0., 5., 50), rng.uniform(1.5, 2.5, 50), rng.normal(0., 0.1, 50)])
+        plan = desilike_b200.Plan(spec)
+        ref = pipeline.evaluate(spec, X, return_theory=True)
+        assert np.max(np.abs(plan.theory(X) - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-10, apmode
+        assert np.allclose(plan.eval(X)['logposterior'], ref['logposterior'], rtol=1e-9, atol=1e-6)
+        plan.close()
+
+
+def test_mlp_emulated_marginalised(gpu_required):
+    """C4-like: MLP pt emulator -> EFT-like combine -> window -> chi2 with 7 marginalised terms per tracer."""
+    import desilike_b200
+    spec = configs.config_c4(ntracers=2, nkin=40, nbins=10, hidden=(16, 16))
+    plan = desilike_b200.Plan(spec)
+    X = configs.sample_points(spec, 150, seed=14)
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    got = plan.eval(X)
+    assert np.max(np.abs(plan.theory(X) - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-10
+    assert np.max(np.abs(got['logposterior'] - ref['logposterior']) / np.maximum(1., np.abs(ref['logposterior']))) < 1e-8
+    assert np.max(np.abs(got['x_solved'] - ref['x_solved']) / np.maximum(1., np.abs(ref['x_solved']))) < 1e-7
+    plan.close()
+
+
+def test_mlp_full_width(gpu_required):
+    """Reference-like MLP width (3 x 64, SiLU) at BASELINE C4 table sizes for one tracer; tanh / relu variants."""
+    import desilike_b200
+    for act in ['silu', 'tanh', 'relu']:
+        spec = configs.config_c4(ntracers=1, nkin=350, nbins=36, hidden=(64, 64, 64))
+        spec['observables'][0]['theory']['mlp']['activation'] = act
+        from oracle.pipeline import observable_flat
+        plan = desilike_b200.Plan(spec)
+        X = configs.sample_points(spec, 200, seed=15)
+        ref = pipeline.evaluate(spec, X, return_theory=True)
+        got = plan.eval(X)
+        assert np.max(np.abs(plan.theory(X) - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-10, act
+        assert np.max(np.abs(got['logposterior'] - ref['logposterior']) / np.maximum(1., np.abs(ref['logposterior']))) < 1e-8, act
+        plan.close()
