@@ -357,6 +357,7 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
       g.fpad = std::max(g.fpad, (gd.idata[7] + 3) & ~3);   // idata[7] = total segment length incl. scratch
       g.aux[1] = gd.idata[3];                              // nt (template knots), needed on the host for shared-memory sizing
       g.aux[2] = gd.idata[0]; g.aux[3] = gd.idata[1]; g.aux[4] = gd.idata[5];
+      if (gd.kind == DLB_GEN_BAO) { DLB_REQUIRE(gd.ni >= 16, "bao generator: idata header"); g.aux[5] = gd.idata[14]; }
     }
     foff += g.fpad;
     plan->gens.push_back(g);

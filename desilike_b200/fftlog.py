@@ -1,0 +1,61 @@
+"""Plan-time constants of the FFTLog P_ell(k) -> xi_ell(s) transform evaluated by csrc/theory_kernels.cu:fftlog_kernel.
+
+What the reference computes: ``BaseTheoryCorrelationFunctionFromPowerSpectrumMultipoles`` (desilike/theories/galaxy_clustering/
+base.py:46-136) builds ``cosmoprimo.PowerToCorrelation(k=logspace(-4, 3, 2048), ell, q=0, lowring=True)`` (:76-77) and in
+``get_corr`` (:127-136) resamples P_ell from ``kin`` onto that grid (linear in log10 k, high-k extrapolation with Gaussian
+damping), transforms, and linearly interpolates onto the requested ``s``.  cosmoprimo is absent; the algorithm
+(Hamilton 2000: power-law bias q' = 1.5 + q, low-ringing shift, zero padding to the next power of two >= 2 N) is restated
+here for the constants and validated against the defining integral through the oracle tests.
+"""
+import numpy as np
+from scipy.special import loggamma
+
+
+def kernel_u(ell, z):
+    """Mellin transform of sqrt(2 / pi) j_ell: 2^(z - 3/2) Gamma((ell + z) / 2) / Gamma((3 + ell - z) / 2)."""
+    z = np.asarray(z, dtype=np.complex128)
+    return np.exp(np.log(2.) * (z - 1.5) + loggamma(0.5 * (ell + z)) - loggamma(0.5 * (3. + ell - z)))
+
+
+def fftlog_constants(kin, ells, s_out, ng=2048, kmin=1e-4, kmax=1e3, q=0., minfolds=2):
+    """-> dict of arrays consumed by the kernel (layout documented in csrc/theory_kernels.cu)."""
+    kin = np.asarray(kin, dtype=np.float64)
+    s_out = np.asarray(s_out, dtype=np.float64)
+    k = np.logspace(np.log10(kmin), np.log10(kmax), ng)
+    qq = 1.5 + q
+    delta = np.log(k[-1] / k[0]) / (ng - 1)
+    npad_size = 2**((ng * minfolds - 1).bit_length())
+    npad = npad_size - ng
+    pad_in_left, pad_out_left = npad // 2, npad - npad // 2
+    # resampling kin -> k (reference base.py:62-74, :127-133)
+    mask = k > kin[-1]
+    jmap = np.full(ng, -1, dtype=np.int32)
+    wgt, lh, dh = np.zeros(ng), np.zeros(ng), np.ones(ng)
+    lk_mid, lkin = np.log10(k[~mask]), np.log10(kin)
+    j = np.clip(np.searchsorted(lkin, lk_mid, side='right') - 1, 0, kin.size - 2)
+    jmap[~mask] = j
+    wgt[~mask] = (lk_mid - lkin[j]) / (lkin[j + 1] - lkin[j])
+    lh[mask] = np.log10(k[mask] / kin[-1])
+    dh[mask] = np.exp(-(k[mask] / kin[-1] - 1.)**2 / (2. * (10.)**2))
+    slope_inv = 1. / np.log10(kin[-1] / kin[-2])
+    pre = k**(3. - qq) / (2. * np.pi)**1.5
+    m = np.arange(0, npad_size // 2 + 1)
+    u, post, outj, outw, s_grids = [], [], [], [], []
+    for ell in ells:
+        lnxy = delta / np.pi * np.angle(kernel_u(ell, qq + 1j * np.pi / delta))
+        s = np.exp(lnxy - delta) / k[::-1]
+        uu = kernel_u(ell, qq + 2j * np.pi / npad_size / delta * m) * np.exp(-2j * np.pi * lnxy / npad_size / delta * m)
+        uu[-1] = uu[-1].real
+        u.append(np.stack([uu.real, uu.imag], axis=-1))
+        post.append(s**(-qq) * (-1.)**(ell // 2))
+        if s_out.min() < s[0] or s_out.max() > s[-1]:
+            raise ValueError('requested s outside the FFTLog output grid')
+        jj = np.clip(np.searchsorted(s, s_out, side='right') - 1, 0, ng - 2)
+        outj.append(jj.astype(np.int32))
+        outw.append((s_out - s[jj]) / (s[jj + 1] - s[jj]))
+        s_grids.append(s)
+    tw = np.exp(-2j * np.pi * np.arange(npad_size // 2) / npad_size)
+    ddata = np.concatenate([wgt, lh, dh, pre, np.array(u).ravel(), np.array(post).ravel(), [slope_inv, 0.],
+                            np.stack([tw.real, tw.imag], axis=-1).ravel(), np.array(outw).ravel()])
+    idata = np.concatenate([jmap, np.array(outj).ravel()]).astype(np.int32)
+    return dict(ddata=ddata, idata=idata, ng=ng, npad_size=npad_size, pad_in_left=pad_in_left, pad_out_left=pad_out_left, k=k, s=np.array(s_grids))

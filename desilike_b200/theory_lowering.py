@@ -68,4 +68,54 @@ def lower_theory(gen, theory, defaults, names=None):
         for t, name in enumerate(['pk_dd', 'pk_dt', 'pk_tt', 'pk11_l0']):
             gen.tables[name] = (2 + t * ntab, nin, None)
         return
+    if kind in ('bao_pk', 'bao_xi'):
+        from .spline import second_derivatives
+        from .fftlog import fftlog_constants
+        gen.kind = _capi.GEN_BAO
+        xi = kind == 'bao_xi'
+        nmu = int(theory.get('nmu', 10))
+        mu, wmu = legendre_weights(ells, nmu)
+        k_t = f64(tpl['k'])
+        nell, nt = len(ells), k_t.size
+        if xi:
+            s_out = f64(theory['s'])
+            interp_order = int(theory.get('interp_order', 1))
+            if interp_order != 1:
+                raise ValueError('interp_order=3 of the P -> xi resampling is not on the CUDA path (reference default is 1)')
+            k = np.geomspace(1e-4, 0.6, int(300. / interp_order + 0.5)) if theory.get('kin') is None else f64(theory['kin'])  # reference base.py:67
+        else:
+            k = f64(theory['k'])
+        nk = k.size
+        consts = spline_constants(np.log10(k_t))
+        pk_t, pknow_t = f64(tpl['pk_dd_fid']), f64(tpl['pknow_dd_fid'])
+        M_pk, M_now = second_derivatives(consts, nt, pk_t), second_derivatives(consts, nt, pknow_t)
+        from .spline import evaluate
+        pknow_k = evaluate(consts, nt, pknow_t, M_now, np.log10(k))
+        slots = [(q0, 1.), (q1, 1.), ('b1', 1.), ('dbeta', 1.), ('sigmas', 0.), ('sigmapar', 9.), ('sigmaper', 6.), ('df', 1.)]
+        gen.param_idx, gen.param_default, gen.params = _slots(gen, slots, defaults, names)
+        flags = (1 if theory.get('mode', '') == 'reciso' else 0) | (2 if xi else 0)
+        head = [float(tpl.get('eta', 1. / 3.)), float(tpl['f_fid']), float(theory.get('smoothing_radius', 15.)), 0.]
+        ddata = [head, k, mu, wmu.ravel(), pknow_k, pk_t, M_pk, pknow_t, M_now, consts]
+        nin = nell * nk
+        if xi:
+            ns = s_out.size
+            nvis = 2 + nell * ns
+            poff = (nvis + 3) & ~3
+            total = poff + nin
+            fc = fftlog_constants(k, ells, s_out)
+            off_d = sum(np.size(a) for a in ddata)
+            off_d += off_d % 2    # keep the complex tables 16-byte aligned
+            ddata = ddata + [np.zeros(off_d - sum(np.size(a) for a in ddata)), fc['ddata']]
+            header = [nk, nell, nmu, nt, APMODES[apmode], flags, 0, total, ns, nk, off_d, 16, poff, fc['ng'], fc['npad_size'], fc['pad_in_left']]
+            gen.idata = np.concatenate([np.array(header, dtype=np.int32), fc['idata']])
+            gen.nfeat = nvis
+            gen.tables['corr'] = (2, nell * ns, None)
+        else:
+            total = 2 + nin
+            header = [nk, nell, nmu, nt, APMODES[apmode], flags, 0, total, 0, nk, 0, 16, 2, 0, 0, 0]
+            gen.idata = np.array(header, dtype=np.int32)
+            gen.nfeat = total
+            gen.tables['power'] = (2, nin, None)
+        gen.ddata = np.concatenate([np.ravel(a) for a in ddata])
+        return
     raise ValueError('theory kind {!r} not lowered yet'.format(kind))

@@ -87,3 +87,98 @@ def evaluate(low, X, feature_fn=None, white=True):
                 lp[ip] += (-0.5 * (x[i] - sloc[i])**2 * xprec[i] if skind[i] == 2 else 0.) if isin else -np.inf
             xs[ip] = x
     return dict(loglikelihood=ll, logprior=lp, logposterior=ll + lp, x_solved=xs[:, np.argsort(low.solved_order)] if ns else xs)
+
+
+def theory_features(ig, gen, Xe):
+    """NumPy mirror of csrc/theory_kernels.cu for the direct theory generators, driven ONLY by the lowered payloads
+    (idata / ddata) -- checks the plan-time constants (spline pivots, FFTLog tables) against the oracle on CPU."""
+    from desilike_b200 import spline
+    idata, dd = np.asarray(gen.idata), np.asarray(gen.ddata)
+    nk, nell, nmu, nt, apmode, flags = idata[:6]
+    N = Xe.shape[0]
+
+    def ap(q0, q1, eta):
+        if apmode == 0: return q0, q1
+        if apmode == 1: return q0, q0
+        if apmode == 2: return q0**(1 - eta), q0**(-eta)
+        return q0 * q1**(1 - eta), q0 * q1**(-eta)
+
+    if gen.kind_name == 'kaiser':
+        ntab = idata[6]
+        eta, f_fid = dd[0], dd[2]
+        o = 4
+        k = dd[o:o + nk]; o += nk
+        mu = dd[o:o + nmu]; o += nmu
+        wmu = dd[o:o + nell * nmu].reshape(nell, nmu); o += nell * nmu
+        pk_fid, Tt, Lt = dd[o:o + nt], dd[o + nt:o + 2 * nt], dd[o + 2 * nt:o + 3 * nt]; o += 3 * nt
+        consts = dd[o:o + 5 * nt + 4]
+        out = np.zeros((N, gen.nfeat)); out[:, 0] = 1.
+        ell0 = idata[5] >> 8
+        for ip in range(N):
+            q0, q1, dm, dn, df, spar, sper, _ = Xe[ip]
+            qpar, qper = ap(q0, q1, eta)
+            y = pk_fid * np.exp(dm * Tt + dn * Lt)
+            M = spline.second_derivatives(consts, nt, y)
+            qap, jac = qpar / qper, 1. / (qpar * qper**2)
+            fap = np.sqrt(1. + mu**2 * (1. / qap**2 - 1.))
+            kap, muap = k[:, None] / qper * fap, np.broadcast_to(mu / qap / fap, (nk, nmu))
+            p = jac * spline.evaluate(consts, nt, y, M, np.log10(kap)) * np.exp(-0.5 * kap**2 * (spar**2 * muap**2 + sper**2 * (1 - muap**2)))
+            f = f_fid * df
+            tabs = [p @ wmu.T, (f * muap**2 * p) @ wmu.T, (f**2 * muap**4 * p) @ wmu.T]
+            for t, tab in enumerate(tabs): out[ip, 2 + t * ntab:2 + t * ntab + nell * nk] = tab.T.ravel()
+            out[ip, 2 + 3 * ntab:2 + 3 * ntab + nell * nk] = np.tile(tabs[0][:, ell0], nell) if ell0 >= 0 else 0.
+        return out
+    # BAO (+ FFTLog)
+    eta, f_fid, rs = dd[0], dd[1], dd[2]
+    o = 4
+    k = dd[o:o + nk]; o += nk
+    mu = dd[o:o + nmu]; o += nmu
+    wmu = dd[o:o + nell * nmu].reshape(nell, nmu); o += nell * nmu
+    pknow_k = dd[o:o + nk]; o += nk
+    pk_t, M_pk, pknow_t, M_now = (dd[o + i * nt:o + (i + 1) * nt] for i in range(4)); o += 4 * nt
+    consts = dd[o:o + 5 * nt + 4]
+    power = np.zeros((N, nell, nk))
+    for ip in range(N):
+        q0, q1, b1, dbeta, sigmas, spar, sper, df = Xe[ip]
+        qpar, qper = ap(q0, q1, eta)
+        f = dbeta * f_fid * df
+        qap = qpar / qper
+        fap = np.sqrt(1. + mu**2 * (1. / qap**2 - 1.))
+        kap, muap = k[:, None] / qper * fap, np.broadcast_to(mu / qap / fap, (nk, nmu))
+        lk = np.log10(kap)
+        pkwap = spline.evaluate(consts, nt, pk_t, M_pk, lk) - spline.evaluate(consts, nt, pknow_t, M_now, lk)
+        sk = np.exp(-0.5 * (k[:, None] * rs)**2) if flags & 1 else 0.
+        Cap = (b1 + f * muap**2 * (1 - sk))**2 * np.exp(-0.5 * kap**2 * (spar**2 * muap**2 + sper**2 * (1 - muap**2)))
+        B = (b1 + f * mu**2 * (1 - sk))**2 / (1. + 0.5 * (sigmas * k[:, None] * mu)**2)**2
+        power[ip] = ((B * pknow_k[:, None] + Cap * pkwap) @ wmu.T).T
+    if not flags & 2:
+        out = np.zeros((N, gen.nfeat)); out[:, 0] = 1.
+        out[:, 2:] = power.reshape(N, -1)
+        return out
+    ns, off_d, off_i, Ng, Np, padl = idata[8], idata[10], idata[11], idata[13], idata[14], idata[15]
+    fd, fi = dd[off_d:], idata[off_i:]
+    wgt, lh, dh, pre = (fd[i * Ng:(i + 1) * Ng] for i in range(4)); o = 4 * Ng
+    nu = Np // 2 + 1
+    u = fd[o:o + nell * nu * 2].reshape(nell, nu, 2); o += nell * nu * 2
+    u = u[..., 0] + 1j * u[..., 1]
+    post = fd[o:o + nell * Ng].reshape(nell, Ng); o += nell * Ng
+    slope_inv = fd[o]; o += 2 + Np
+    outw = fd[o:o + nell * ns].reshape(nell, ns)
+    jmap, outj = fi[:Ng], fi[Ng:Ng + nell * ns].reshape(nell, ns)
+    out = np.zeros((N, gen.nfeat)); out[:, 0] = 1.
+    padout = Np - Ng - padl
+    for ip in range(N):
+        for ell in range(nell):
+            pin = power[ip, ell]
+            slope = (pin[-1] - pin[-2]) * slope_inv
+            jj = np.maximum(jmap, 0)
+            v = np.where(jmap >= 0, pin[jj] + wgt * (pin[np.minimum(jj + 1, nk - 1)] - pin[jj]), (pin[-1] + slope * lh) * dh) * pre
+            x = np.zeros(Np); x[padl:padl + Ng] = v
+            X = np.fft.fft(x)
+            m = np.arange(Np)
+            fac = np.where(m <= Np // 2, u[ell][np.minimum(m, Np // 2)], np.conj(u[ell][np.minimum(Np - m, Np // 2)]))
+            g = np.fft.fft(X * fac).real / Np
+            xi = g[padout:padout + Ng] * post[ell]
+            j = outj[ell]
+            out[ip, 2 + ell * ns:2 + (ell + 1) * ns] = xi[j] + outw[ell] * (xi[j + 1] - xi[j])
+    return out

@@ -119,3 +119,64 @@ def test_mlp_full_width(gpu_required):
         assert np.max(np.abs(plan.theory(X) - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-10, act
         assert np.max(np.abs(got['logposterior'] - ref['logposterior']) / np.maximum(1., np.abs(ref['logposterior']))) < 1e-8, act
         plan.close()
+
+
+def test_c3_bao_fftlog(gpu_required):
+    """BASELINE configs[2]: damped-BAO P(k) -> FFTLog -> xi_ell(s) (+ marginalised broadband) -> chi2."""
+    import desilike_b200
+    spec = configs.config_c3()
+    plan = desilike_b200.Plan(spec)
+    X = configs.sample_points(spec, 96, seed=33)
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    got = plan.eval(X)
+    theory = plan.theory(X)
+    assert np.max(np.abs(theory - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-10
+    assert np.max(np.abs(got['logposterior'] - ref['logposterior']) / np.maximum(1., np.abs(ref['logposterior']))) < 1e-8
+    assert np.max(np.abs(got['loglikelihood'] - ref['loglikelihood'])) < 5e-5
+    assert np.max(np.abs(got['x_solved'] - ref['x_solved'])) < 1e-9
+    plan.close()
+
+
+def test_c3_fixed_broadband_and_reciso(gpu_required):
+    import desilike_b200
+    spec = configs.config_c3(broadband_solved=False)
+    spec['observables'][0]['theory']['mode'] = 'reciso'
+    plan = desilike_b200.Plan(spec)
+    X = configs.sample_points(spec, 40, seed=34)
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    assert np.max(np.abs(plan.theory(X) - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-10
+    assert np.allclose(plan.eval(X)['logposterior'], ref['logposterior'], rtol=1e-8, atol=1e-6)
+    plan.close()
+
+
+def test_bao_power_spectrum(gpu_required):
+    """Damped BAO P_ell(k) observable (reference bao.py:117-151) with a power-law broadband (bao.py:527-529)."""
+    import desilike_b200
+    rng = np.random.default_rng(5)
+    k = np.arange(0.02, 0.3, 0.005)
+    ells = (0, 2)
+    tpl = configs.bao_template()
+    theory = dict(kind='bao_pk', k=k, ells=ells, nmu=10, template=tpl, mode='', params=['qpar', 'qper', 'b1', 'dbeta', 'sigmas', 'sigmapar', 'sigmaper'],
+                  defaults=dict(qpar=1., qper=1., df=1.))
+    terms = [dict(scale=1., factors=[], table='power')]
+    solved = []
+    kp = 2. * np.pi / 100.
+    for ill, ell in enumerate(ells):
+        for power in (-1, 0, 1):
+            cv = np.zeros((len(ells), k.size)); cv[ill] = (k / kp)**power
+            name = 'al{:d}_{:d}'.format(ell, power)
+            terms.append(dict(scale=1., factors=[], solved=name, table=None, colvec=cv.ravel()))
+            solved.append(dict(name=name, value=0., prior=dict(dist='norm', loc=0., scale=1e4), marg=True))
+    obs = dict(name='pk', theory=theory, terms=terms, nin=len(ells) * k.size, wmatrix=None, offset=None)
+    spec = dict(params=list(theory['params']), observables=[obs], solved=solved)
+    fid = np.array([[1., 1., 2., 1., 4., 6., 4.]])
+    obs['data'] = pipeline.observable_flat(obs, fid, spec['params'], {s['name']: 0. for s in solved})[0]
+    spec['precision'] = [1. / (0.05 * np.abs(obs['data']) + 20.)**2]   # diagonal precision
+    spec['priors'] = configs.default_priors(spec['params'])
+    plan = desilike_b200.Plan(spec)
+    X = configs.sample_points(spec, 64, seed=35)
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    got = plan.eval(X)
+    assert np.max(np.abs(plan.theory(X) - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-10
+    assert np.max(np.abs(got['logposterior'] - ref['logposterior']) / np.maximum(1., np.abs(ref['logposterior']))) < 1e-8
+    plan.close()
