@@ -7,5 +7,18 @@ from ._capi import DesilikeB200Error, load as load_library
 from .plan import Plan, launch_count, measure_fp64_peak, pinned_empty
 from .lowering import Lowered, LoweringError
 
-__all__ = ['Plan', 'Lowered', 'LoweringError', 'DesilikeB200Error', 'load_library', 'launch_count', 'measure_fp64_peak', 'pinned_empty']
+from .parameter import Parameter, ParameterCollection, Samples
+from .theories import (ShapeFitPowerSpectrumTemplate, BAOPowerSpectrumTemplate, KaiserTracerPowerSpectrumMultipoles,
+                       EFTLikeKaiserTracerPowerSpectrumMultipoles, DampedBAOWigglesTracerPowerSpectrumMultipoles,
+                       DampedBAOWigglesTracerCorrelationFunctionMultipoles)
+from .emulators import Emulator, EmulatedCalculator
+from .observables import TracerPowerSpectrumMultipolesObservable, TracerCorrelationFunctionMultipolesObservable
+from .likelihoods import ObservablesGaussianLikelihood, SumLikelihood, PipelineError
+from .base import vmap, status_to_errors
+
+__all__ = ['Parameter', 'ParameterCollection', 'Samples', 'ShapeFitPowerSpectrumTemplate', 'BAOPowerSpectrumTemplate',
+           'KaiserTracerPowerSpectrumMultipoles', 'EFTLikeKaiserTracerPowerSpectrumMultipoles', 'DampedBAOWigglesTracerPowerSpectrumMultipoles',
+           'DampedBAOWigglesTracerCorrelationFunctionMultipoles', 'Emulator', 'EmulatedCalculator', 'TracerPowerSpectrumMultipolesObservable',
+           'TracerCorrelationFunctionMultipolesObservable', 'ObservablesGaussianLikelihood', 'SumLikelihood', 'PipelineError', 'vmap', 'status_to_errors',
+           'Plan', 'Lowered', 'LoweringError', 'DesilikeB200Error', 'load_library', 'launch_count', 'measure_fp64_peak', 'pinned_empty']
 __version__ = '0.1.0'

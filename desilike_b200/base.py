@@ -1,0 +1,89 @@
+"""Batched entry point: ``vmap`` with the reference's calling / return conventions (desilike/base.py:131-258, :232-383).
+
+``vmap(likelihood, backend='cuda', errors='raise'|'return'|'nan', return_derived=False)`` returns ``wrapper(params)``
+with ``params`` a dict name -> array (all of equal shape, rank >= 1).  The result is shaped ``params.shape`` (+ result
+shape); with ``return_derived=True`` it is the tuple ``(logposterior, derived)`` where ``derived`` holds
+``loglikelihood``, ``logprior`` and every analytically solved parameter (reference likelihoods/base.py:342-352,363-369).
+``errors='return'`` -> ``(results, errs)`` with ``errs = {flat_index: (exception, traceback_str)}`` and failed slots filled
+with a copy of the first good result; ``errors='nan'`` fills them with NaN (reference base.py:193-226).
+"""
+import numpy as np
+
+from . import _capi
+from .parameter import Samples
+from .likelihoods import PipelineError
+
+
+class PointError(ArithmeticError):
+    """Per-point failure reported by the CUDA path (status bitmask of include/desilike_b200.h)."""
+
+
+def status_to_errors(status):
+    """Per-point status bitmask -> {flat_index: (exception, traceback_str)}.  Non-finite theory is NOT an exception in the
+    reference either (NaN propagates and samplers map it to -inf, samplers/base.py:187-191); a non-SPD normal matrix
+    corresponds to the reference's LinAlgError in ``jnp.linalg.solve``."""
+    errs = {}
+    for idx in np.flatnonzero(np.asarray(status).ravel() & _capi.PT_NOT_SPD):
+        errs[int(idx)] = (PointError('normal equations of the solved parameters are not positive definite'), '')
+    return errs
+
+
+def _check_params(params, known=None):
+    """reference desilike/base.py:131-159."""
+    params = dict(params)
+    cshapes, names = [], list(params.keys())
+    for name in names:
+        array = params[name]
+        if array is None: continue
+        arr = np.asarray(array, dtype='f8')
+        if not arr.shape:
+            raise ValueError('input array {}: {} must be of rank >= 1 for lmap'.format(name, array))
+        cshapes.append(arr.shape)
+        params[name] = arr.ravel()
+    if cshapes and not all(cshape == cshapes[0] for cshape in cshapes):
+        raise ValueError('input shapes are different: {}'.format(dict(zip(names, cshapes))))
+    return params, cshapes[0]
+
+
+def vmap(calculate, backend='cuda', errors='raise', return_derived=False, mpicomm=None, **kwargs):
+    """Batched evaluation of a desilike_b200 likelihood.  ``backend`` must be 'cuda' (there is no CPU fallback);
+    ``mpicomm`` may be a ``desilike_b200.distributed.Communicator`` to shard the batch over GPUs."""
+    errors = str(errors)
+    if backend != 'cuda':
+        raise ValueError("desilike_b200.vmap only provides backend='cuda' (the reference's None / 'jax' / 'mpi' backends live in desilike itself)")
+    if errors not in ('raise', 'return', 'nan'): raise ValueError("errors must be one of 'raise', 'return', 'nan'")
+    likelihood = calculate
+
+    def wrapper(params, **kw):
+        rd = kw.pop('return_derived', return_derived)
+        params, shape = _check_params(params)
+        X = likelihood._points(params)
+        if mpicomm is not None:
+            res = mpicomm.eval_sharded(likelihood.plan, X)
+        else:
+            res = likelihood.plan.eval(X)
+        errs = status_to_errors(res['status'])
+        if errs and errors == 'raise':
+            raise errs[min(errs)][0]
+        out = {key: np.array(res[key]) for key in ['logposterior', 'loglikelihood', 'logprior']}
+        xs = np.array(res['x_solved']) if 'x_solved' in res else None
+        if errs:
+            good = [i for i in range(X.shape[0]) if i not in errs]
+            for key in out:
+                fill = np.nan if (errors == 'nan' or not good) else out[key][good[0]]
+                out[key][list(errs)] = fill
+            if xs is not None:
+                xs[list(errs)] = np.nan if (errors == 'nan' or not good) else xs[good[0]]
+        results = out['logposterior'].reshape(shape)
+        if rd:
+            derived = Samples(loglikelihood=out['loglikelihood'].reshape(shape), logprior=out['logprior'].reshape(shape))
+            for i, name in enumerate(likelihood.plan.solved_names):
+                derived[name] = xs[:, i].reshape(shape)
+            results = (results, derived)
+        if errors == 'return':
+            return results, errs
+        return results
+
+    wrapper.__wrapped__vmap__ = calculate
+    wrapper.__wrapped__errors__ = errors
+    return wrapper

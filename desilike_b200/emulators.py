@@ -1,0 +1,244 @@
+"""Emulator files on the batched path: reader / writer of the reference's emulator ``.npy`` state and the
+``EmulatedCalculator`` that plugs an emulated perturbation-theory calculator into a tracer theory.
+
+Reference API kept (desilike/emulators/__init__.py): ``Emulator.save(fn)`` = ``np.save(fn, state, allow_pickle=True)`` (:240-248),
+``EmulatedCalculator.load(fn)`` (:411-415), ``emulator.to_calculator()`` (:150-208).  State keys written by desilike itself
+(:210-216): varied_params, in_calculator_state, calculator__class__, is_calculator_sequence, yaml_data, all_params; keys
+of the (absent, third-party) cosmoprimo base class as evidenced by desilike/emulators/conversion.py:48-54,102-104 and the
+back-compat shim :218-235: engines {name: {name: 'taylor'|'mlp', params, xshape, yshape, xoperations, yoperations,
+center/derivatives/powers | model_operations/model_yoperations}}, xoperations, yoperations, defaults, fixed.
+Operations are {expression, inverse, locals} strings (conversion.py:24-33,76-84); they are NOT eval'ed here: a whitelist of
+the expressions the reference itself emits is pattern-matched and lowered to the CUDA MLP generator; anything else raises.
+The schema beyond those call sites is third-party, so compatibility is best effort and round-trip tested with this writer.
+
+Fitting (Taylor finite differences / MLP training) is a 'next' row of SURVEY.md section 8(f) and not part of this module.
+"""
+import os
+import re
+
+import numpy as np
+
+from .parameter import Parameter, ParameterCollection
+from .theories import BaseCalculator
+
+_DENSE = '(v[..., None, :] @ kernel)[..., 0, :] + bias'
+_ACTS = {'v / (1 + jnp.exp(-v))': 'silu', 'jnp.maximum(v, 0.)': 'relu', 'jnp.tanh(v)': 'tanh'}
+_ACT_EXPR = {v: k for k, v in _ACTS.items()}
+_MINMAX = '(v - limits[..., 0]) / (limits[..., 1] - limits[..., 0])'
+_MINMAX_INV = 'v * (limits[..., 1] - limits[..., 0]) + limits[..., 0]'
+_PCA = 'v @ eigvecs + mean'
+
+
+def _norm(expr):
+    expr = re.sub(r'\s+', ' ', str(expr).strip())
+    while expr.startswith('(') and expr.endswith(')') and _balanced(expr[1:-1]): expr = expr[1:-1].strip()
+    return expr
+
+
+def _balanced(s):
+    depth = 0
+    for c in s:
+        depth += (c == '(') - (c == ')')
+        if depth < 0: return False
+    return depth == 0
+
+
+def _op(expression, inverse=None, locals=None):
+    return {'expression': expression, 'inverse': inverse, 'locals': dict(locals or {})}
+
+
+def _op_fields(op):
+    get = lambda *keys: next((op[k] for k in keys if k in op), None)
+    return get('expression', '_expression', 'direct'), get('inverse', '_inverse'), get('locals', '_locals') or {}
+
+
+class Emulator(object):
+    """Container of an emulator state (no fitting): ``Emulator.load(fn)``, ``.save(fn)``, ``.to_calculator()``."""
+
+    def __init__(self, state):
+        self.state = state
+        for key in ['engines', 'fixed']:
+            if key not in state: raise ValueError('emulator state has no {!r} entry'.format(key))
+
+    @classmethod
+    def load(cls, filename):
+        state = np.load(filename, allow_pickle=True)[()]
+        return cls(state)
+
+    def save(self, filename, yaml=False):
+        dirname = os.path.dirname(str(filename))
+        if dirname: os.makedirs(dirname, exist_ok=True)
+        np.save(filename, self.state, allow_pickle=True)
+
+    def to_calculator(self):
+        return EmulatedCalculator(self)
+
+    # ---- writers ----------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _base_state(params, defaults, fixed, names, calculator_class, all_params):
+        all_params = all_params or [Parameter(p, value=defaults.get(p, 0.)) for p in params]
+        return {'engines': {}, 'xoperations': [], 'yoperations': [], 'defaults': dict(defaults), 'fixed': dict(fixed, names=list(names)),
+                'varied_params': list(params), 'in_calculator_state': list(names), 'calculator__class__': tuple(calculator_class),
+                'is_calculator_sequence': False, 'yaml_data': {'class': calculator_class[1], 'info': {}, 'params': {}},
+                'all_params': {'data': [dict(basename=p.basename, namespace=p.namespace, value=p.value, fixed=p.fixed, prior=p.prior, ref=p.ref, derived=p.derived)
+                                        for p in all_params]}}
+
+    @classmethod
+    def from_taylor(cls, params, center, powers, tables, fixed, defaults=None, all_params=None,
+                    calculator_class=('desilike.theories.galaxy_clustering.full_shape', 'KaiserPowerSpectrumMultipoles')):
+        """``tables``: {name: derivatives [T, *yshape]} in the layout of the reference's fit (emulators/__init__.py:471-507)."""
+        defaults = dict(zip(params, np.asarray(center, dtype='f8'))) if defaults is None else defaults
+        state = cls._base_state(params, defaults, fixed, list(tables), calculator_class, all_params)
+        for name, deriv in tables.items():
+            deriv = np.asarray(deriv, dtype='f8')
+            state['engines'][name] = {'name': 'taylor', 'params': list(params), 'xshape': (len(params),), 'yshape': tuple(deriv.shape[1:]),
+                                      'xoperations': [], 'yoperations': [], 'center': np.asarray(center, dtype='f8'),
+                                      'derivatives': deriv, 'powers': np.asarray(powers, dtype='i4')}
+        return cls(state)
+
+    @classmethod
+    def from_mlp(cls, params, mlp, tables, yshapes, fixed, defaults=None, all_params=None,
+                 calculator_class=('desilike.theories.galaxy_clustering.full_shape', 'KaiserPowerSpectrumMultipoles')):
+        """``mlp``: dict(xlimits, layers [(kernel, bias)], activation, ylimits, pca); ``tables``: {name: slice into the network output}."""
+        defaults = defaults or {p: 0. for p in params}
+        state = cls._base_state(params, defaults, fixed, list(tables), calculator_class, all_params)
+        xops = [_op(_MINMAX, locals={'limits': np.asarray(mlp['xlimits'])})] if mlp.get('xlimits') is not None else []
+        hidden, (W, b) = mlp['layers'][:-1], mlp['layers'][-1]
+        act = _ACT_EXPR[mlp.get('activation', 'silu')]
+        for name, sl in tables.items():
+            ops = []
+            for kernel, bias in hidden:
+                ops += [_op(_DENSE, locals={'kernel': np.asarray(kernel), 'bias': np.asarray(bias)}), _op(act)]
+            if mlp.get('pca') is not None:
+                raise NotImplementedError('writer: per-table PCA')
+            ops.append(_op(_DENSE, locals={'kernel': np.asarray(W)[:, sl], 'bias': np.asarray(b)[sl]}))
+            yops = [_op('(' + _MINMAX + ')', inverse=_MINMAX_INV, locals={'limits': np.asarray(mlp['ylimits'])[sl]})] if mlp.get('ylimits') is not None else []
+            state['engines'][name] = {'name': 'mlp', 'params': list(params), 'xshape': (len(params),), 'yshape': tuple(yshapes[name]),
+                                      'xoperations': xops, 'yoperations': yops, 'model_operations': ops, 'model_yoperations': []}
+        return cls(state)
+
+
+def _parse_mlp_engine(engine):
+    """-> dict(xlimits, layers, activation, ylimits, pca) of ONE engine, by pattern-matching its operation strings."""
+    out = dict(xlimits=None, ylimits=None, pca=None, activation='identity', layers=[])
+    for op in engine.get('xoperations', []):
+        expr, inv, loc = _op_fields(op)
+        if _norm(expr) != _norm(_MINMAX): raise ValueError('x-operation {!r} is not on the CUDA path'.format(expr))
+        out['xlimits'] = np.asarray(loc['limits'], dtype='f8')
+    acts = set()
+    for op in engine['model_operations']:
+        expr, inv, loc = _op_fields(op)
+        e = _norm(expr)
+        if e == _norm(_DENSE):
+            out['layers'].append((np.asarray(loc['kernel'], dtype='f8'), np.asarray(loc['bias'], dtype='f8')))
+        elif e in {_norm(k): v for k, v in _ACTS.items()}:
+            acts.add({_norm(k): v for k, v in _ACTS.items()}[e])
+        else:
+            raise ValueError('model operation {!r} is not on the CUDA path (dense / silu / relu / tanh only)'.format(expr))
+    if len(acts) > 1: raise ValueError('mixed activations are not on the CUDA path')
+    if acts: out['activation'] = acts.pop()
+    if engine.get('model_yoperations'): raise ValueError('model_yoperations are not on the CUDA path')
+    ny = out['layers'][-1][0].shape[1]
+    for op in engine.get('yoperations', []):   # inverse operations are applied in reverse order at predict time
+        expr, inv, loc = _op_fields(op)
+        if _norm(inv) == _norm(_MINMAX_INV):
+            out['ylimits'] = np.asarray(loc['limits'], dtype='f8').reshape(ny, 2)
+        elif _norm(inv) == _norm(_PCA):
+            out['pca'] = (np.asarray(loc['eigvecs'], dtype='f8'), np.asarray(loc['mean'], dtype='f8'))
+        else:
+            raise ValueError('y-operation with inverse {!r} is not on the CUDA path (min-max scaling / PCA only)'.format(inv))
+    if len(engine.get('yoperations', [])) > 1: raise ValueError('chained y-operations are not on the CUDA path')
+    return out
+
+
+def _merge_mlps(nets):
+    """Merge per-table networks into ONE network whose output is the concatenation of theirs: shared hidden stacks are kept
+    once, different ones are stacked block-diagonally (exact: the extra entries are zeros)."""
+    names = list(nets)
+    first = nets[names[0]]
+    same_hidden = all(len(n['layers']) == len(first['layers']) and all(np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+                      for a, b in zip(n['layers'][:-1], first['layers'][:-1])) for n in nets.values())
+    for n in nets.values():
+        if n['activation'] != first['activation'] or (n['xlimits'] is None) != (first['xlimits'] is None) or \
+           (n['xlimits'] is not None and not np.array_equal(n['xlimits'], first['xlimits'])) or n['pca'] is not None:
+            raise ValueError('engines with different x-operations / activations (or PCA) cannot be merged on the CUDA path')
+    sizes = [n['layers'][-1][0].shape[1] for n in nets.values()]
+    tables, start = {}, 0
+    for name, size in zip(names, sizes):
+        tables[name] = slice(start, start + size); start += size
+    if same_hidden:
+        layers = list(first['layers'][:-1])
+        layers.append((np.concatenate([n['layers'][-1][0] for n in nets.values()], axis=1), np.concatenate([n['layers'][-1][1] for n in nets.values()])))
+    else:
+        import scipy.linalg
+        nl = len(first['layers'])
+        if any(len(n['layers']) != nl for n in nets.values()): raise ValueError('engines with different depths cannot be merged')
+        layers = [(np.concatenate([n['layers'][0][0] for n in nets.values()], axis=1), np.concatenate([n['layers'][0][1] for n in nets.values()]))]
+        for il in range(1, nl):
+            layers.append((scipy.linalg.block_diag(*[n['layers'][il][0] for n in nets.values()]), np.concatenate([n['layers'][il][1] for n in nets.values()])))
+        if nl == 1: layers = [(np.concatenate([n['layers'][0][0] for n in nets.values()], axis=1), np.concatenate([n['layers'][0][1] for n in nets.values()]))]
+    ylimits = None
+    if any(n['ylimits'] is not None for n in nets.values()):
+        ylimits = np.concatenate([n['ylimits'] if n['ylimits'] is not None else np.stack([np.zeros(s), np.ones(s)], axis=-1) for n, s in zip(nets.values(), sizes)])
+    return dict(xlimits=first['xlimits'], layers=layers, activation=first['activation'], ylimits=ylimits, pca=None), tables
+
+
+class EmulatedCalculator(BaseCalculator):
+    """Emulated perturbation-theory calculator (reference emulators/__init__.py:394-418): pass it as ``pt=`` to a tracer theory."""
+
+    def __init__(self, emulator):
+        self.emulator = emulator
+        state = emulator.state
+        self.fixed = state['fixed']
+        self.k, self.ells = np.asarray(self.fixed['k'], dtype='f8'), tuple(self.fixed['ells'])
+        self.varied_params_names = list(state.get('varied_params', []))
+        params = []
+        for ps in state.get('all_params', {}).get('data', []):
+            params.append(Parameter(ps['basename'], value=ps.get('value', 0.), fixed=ps.get('fixed', False), prior=ps.get('prior'), ref=ps.get('ref'),
+                                    derived=ps.get('derived', False), namespace=ps.get('namespace', '')))
+        self.params = ParameterCollection(params)
+
+    @classmethod
+    def load(cls, filename):
+        return Emulator.load(filename).to_calculator()
+
+    def save(self, filename):
+        return self.emulator.save(filename)
+
+    def theory_spec(self, tracer_theory=None):
+        state = self.emulator.state
+        engines = state['engines']
+        if tracer_theory is not None:
+            if len(tracer_theory.k) != len(self.k) or not np.allclose(tracer_theory.k, self.k) or tuple(tracer_theory.ells) != self.ells:
+                raise ValueError('the emulator was built on a different (k, ells) grid than the one requested by the window / observable')
+        kinds = {e['name'] for e in engines.values()}
+        if len(kinds) != 1: raise ValueError('mixed emulator engines are not on the CUDA path')
+        kind = kinds.pop()
+        nk, nell = len(self.k), len(self.ells)
+        names = list(engines)
+        first = engines[names[0]]
+        params = list(first['params'])
+        defaults = dict(state.get('defaults', {}))
+        if kind == 'taylor':
+            for e in engines.values():
+                if list(e['params']) != params or not np.array_equal(e['center'], first['center']) or not np.array_equal(e['powers'], first['powers']):
+                    raise ValueError('Taylor engines with different expansion points / term lists are not on the CUDA path')
+                if e.get('xoperations') or e.get('yoperations'): raise ValueError('operations are not supported for the Taylor engine (reference emulators/__init__.py:435-436)')
+            T = np.asarray(first['powers']).shape[0]
+            tables = {name: np.asarray(e['derivatives'], dtype='f8').reshape(T, -1) for name, e in engines.items()}
+            src = tables.get('pk11', tables.get('pk_dd'))
+            if src is not None and 0 in self.ells:
+                i0 = self.ells.index(0)
+                tables['pk11_l0'] = np.tile(src.reshape(T, nell, nk)[:, i0], (1, nell))
+            return dict(kind='taylor', params=params, center=np.asarray(first['center'], dtype='f8'), powers=np.asarray(first['powers'], dtype='i4'),
+                        tables=tables, defaults=defaults)
+        if kind == 'mlp':
+            nets = {name: _parse_mlp_engine(e) for name, e in engines.items()}
+            mlp, tables = _merge_mlps(nets)
+            src = 'pk11' if 'pk11' in tables else 'pk_dd' if 'pk_dd' in tables else None
+            if src is not None and 0 in self.ells:
+                i0 = self.ells.index(0)
+                base = np.arange(tables[src].start, tables[src].stop).reshape(nell, nk)[i0]
+                tables['pk11_l0'] = np.tile(base, nell)
+            return dict(kind='mlp', params=params, mlp=mlp, tables=tables, defaults=defaults)
+        raise ValueError('emulator engine {!r} is not on the CUDA path'.format(kind))

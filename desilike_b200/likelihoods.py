@@ -1,0 +1,213 @@
+"""Host-side mirror of the reference's Gaussian likelihood on the batched path.
+
+  ObservablesGaussianLikelihood   reference likelihoods/base.py:506-664 (covariance -> precision :605-631, Hartlap :623-629,
+                                  Percival :633-656, chi2 :658-660), result = loglikelihood + logprior (:242-245, :413)
+  SumLikelihood                   reference likelihoods/base.py:715-732
+Calling ``likelihood(**params)`` evaluates ONE point through the same CUDA path as a batch of one; ``vmap(likelihood)`` is the
+batched entry (desilike_b200/base.py).
+"""
+import numpy as np
+
+from .parameter import ParameterCollection, Samples
+from .plan import Plan
+
+
+class PipelineError(Exception):
+    """reference desilike/base.py (unknown parameter name etc.)."""
+
+
+class BaseLikelihood(object):
+    solved_default = '.marg'   # reference likelihoods/base.py:207
+
+    def __init__(self):
+        self._plan, self._spec = None, None
+        self.loglikelihood = self.logprior = None
+        self.flattheory = self.flatdiff = None
+
+    # ---- parameters ----
+    @property
+    def all_params(self):
+        params = ParameterCollection()
+        for obs in self.observables: params = params + obs.theory.all_params
+        return params
+
+    @property
+    def varied_params(self):
+        return ParameterCollection([p for p in self.all_params if p.varied and not p.solved])
+
+    @property
+    def solved_params(self):
+        return ParameterCollection([p for p in self.all_params if p.solved])
+
+    # ---- spec / plan ----
+    def _invalidate(self):
+        if self._plan is not None: self._plan.close()
+        self._plan, self._spec = None, None
+
+    def build_spec(self):
+        all_params = self.all_params
+        varied = [p.name for p in all_params if p.varied and not p.solved]
+        solved = [p for p in all_params if p.solved]
+        for p in solved:
+            if p.derived.startswith('.prec'):
+                raise NotImplementedError("'.prec' pre-marginalisation (reference likelihoods/base.py:280-309) is a plan-time 'next' row; use '.marg' / '.best'")
+        solved_names = [p.name for p in solved]
+        fixed = {p.name: p.value for p in all_params if not p.varied}
+        spec = dict(params=varied, priors={p.name: p.prior for p in all_params if p.name in varied}, observables=[], precision=None,
+                    solved=[dict(name=p.name, value=p.value, prior=p.prior, marg=p.derived.replace('.auto', self.solved_default).startswith('.marg')) for p in solved])
+        for obs in self.observables:
+            ospec = obs.observable_spec()
+            theory = obs.theory.theory_spec()
+            theory['params'] = [n for n in theory['params'] if n in varied]
+            theory['defaults'] = dict(theory.get('defaults', {}))
+            terms = []
+            for term in obs.theory.terms():
+                term = dict(term)
+                scale, factors, sname = float(term.get('scale', 1.)), [], term.get('solved')
+                for name, power in term.get('factors', []):
+                    if name in solved_names:
+                        if power != 1 or sname is not None: raise ValueError('solved parameter {} must enter linearly'.format(name))
+                        sname = name
+                    elif name in fixed:
+                        scale *= fixed[name]**power
+                    else:
+                        factors.append((name, power))
+                if scale == 0.: continue
+                terms.append(dict(term, scale=scale, factors=factors, solved=sname))
+            ospec.update(theory=theory, terms=terms)
+            spec['observables'].append(ospec)
+        return spec
+
+    def _finalize_spec(self, spec):
+        return spec
+
+    @property
+    def plan(self):
+        if self._plan is None:
+            self._spec = self._finalize_spec(self.build_spec())
+            self._plan = Plan(self._spec)
+        return self._plan
+
+    @property
+    def spec(self):
+        self.plan
+        return self._spec
+
+    # ---- evaluation ----
+    def _points(self, params, shape=None):
+        plan = self.plan
+        known = set(self.all_params.names())
+        for name in params:
+            if name not in known: raise PipelineError('input parameter {} is not one of parameters: {}'.format(name, sorted(known)))
+        defaults = {p.name: p.value for p in self.all_params}
+        cols = []
+        n = None
+        for name in plan.params:
+            col = np.asarray(params[name], dtype='f8').ravel() if name in params else None
+            if col is not None: n = col.size
+            cols.append(col)
+        n = n or 1
+        return np.column_stack([col if col is not None else np.full(n, defaults[name]) for col, name in zip(cols, plan.params)])
+
+    def __call__(self, *args, return_derived=False, **kwargs):
+        params = args[0] if (len(args) == 1 and not kwargs) else kwargs
+        if args and kwargs: raise PipelineError('could not interpret input args = {}, kwargs = {}'.format(args, kwargs))
+        X = self._points({k: [v] for k, v in params.items()})
+        res = self.plan.eval(X)
+        self.loglikelihood, self.logprior = float(res['loglikelihood'][0]), float(res['logprior'][0])
+        self.flattheory = self.plan.theory(X)[0]
+        self.flatdiff = self.flattheory - self.flatdata
+        if return_derived:
+            derived = Samples(loglikelihood=res['loglikelihood'][0], logprior=res['logprior'][0])
+            for i, name in enumerate(self.plan.solved_names): derived[name] = res['x_solved'][0, i]
+            return float(res['logposterior'][0]), derived
+        return float(res['logposterior'][0])
+
+
+class ObservablesGaussianLikelihood(BaseLikelihood):
+
+    def __init__(self, observables, covariance=None, scale_covariance=1., correct_covariance='hartlap-percival2014', precision=None, name=None):
+        super().__init__()
+        if not isinstance(observables, (list, tuple)): observables = [observables]
+        self.observables, self.name = list(observables), name
+        self.nobs = None
+        if isinstance(correct_covariance, dict):
+            self.nobs = correct_covariance.get('nobs')
+            correct_covariance = correct_covariance['correction']
+        self.correct_covariance = correct_covariance
+        sizes = [obs.size for obs in self.observables]
+        n = sum(sizes)
+        self._groups = None
+        if covariance is None and precision is None:
+            if not all(obs.covariance is not None for obs in self.observables):
+                raise ValueError('Observables must have their own covariance if global covariance or precision matrix not provided')
+            self._groups = [[i] for i in range(len(self.observables))]
+            self.covariance = [np.atleast_2d(obs.covariance) * scale_covariance for obs in self.observables]
+            self.precision = [np.linalg.inv(c) for c in self.covariance]
+        elif precision is not None:
+            self.covariance = None
+            self.precision = np.array(precision, dtype='f8') / scale_covariance
+            if self.precision.shape[0] != n:
+                raise ValueError('based on provided observables, precision expected to be of size {:d}, but found {}'.format(n, self.precision.shape))
+        else:
+            self.covariance = np.atleast_2d(np.array(covariance, dtype='f8')) * scale_covariance
+            if self.covariance.shape != (n, n):
+                raise ValueError('based on provided observables, covariance expected to be a matrix of shape ({0:d}, {0:d}), but found {1}'.format(n, self.covariance.shape))
+            self.precision = np.linalg.inv(self.covariance)
+        if self.nobs is not None and 'hartlap' in self.correct_covariance:   # reference likelihoods/base.py:623-629
+            self.hartlap2007_factor = (self.nobs - n - 2.) / (self.nobs - 1.)
+            self.precision = [p * self.hartlap2007_factor for p in self.precision] if isinstance(self.precision, list) else self.precision * self.hartlap2007_factor
+
+    def _finalize_spec(self, spec):
+        precision = self.precision
+        if self.nobs is not None and 'percival' in self.correct_covariance:   # reference likelihoods/base.py:633-656
+            nbins = sum(obs.size for obs in self.observables)
+            A = 2. / (self.nobs - nbins - 1.) / (self.nobs - nbins - 4.)
+            B = (self.nobs - nbins - 2.) / (self.nobs - nbins - 1.) / (self.nobs - nbins - 4.)
+            nparams = len(spec['params']) + len(spec['solved'])
+            self.percival2014_factor = (1 + B * (nbins - nparams)) / (1 + A + B * (nparams + 1))
+            precision = [p / self.percival2014_factor for p in precision] if isinstance(precision, list) else precision / self.percival2014_factor
+        spec['precision'] = precision
+        # synthetic data generated from the theory at given parameters (reference power_spectrum.py:95-97)
+        pending = [obs for obs in self.observables if obs.flatdata is None]
+        for obs, ospec in zip(self.observables, spec['observables']):
+            ospec['data'] = obs.flatdata if obs.flatdata is not None else np.zeros(obs.size)
+        if pending:
+            tmp = Plan(spec)
+            defaults = {p.name: p.value for p in self.all_params}
+            start = 0
+            for obs, ospec in zip(self.observables, spec['observables']):
+                if obs.flatdata is None:
+                    vals = dict(defaults); vals.update(obs._data_params or {})
+                    X = np.array([[vals[name] for name in tmp.params]])
+                    obs.flatdata = tmp.theory(X)[0, start:start + obs.size].copy()
+                    ospec['data'] = obs.flatdata
+                start += obs.size
+            tmp.close()
+        self.flatdata = np.concatenate([obs.flatdata for obs in self.observables])
+        return spec
+
+
+class SumLikelihood(BaseLikelihood):
+    """Sum of independent Gaussian likelihoods (reference likelihoods/base.py:715-732): one plan, one block per member."""
+
+    def __init__(self, likelihoods):
+        super().__init__()
+        self.likelihoods = list(likelihoods)
+        self.observables = [obs for like in self.likelihoods for obs in like.observables]
+
+    def _finalize_spec(self, spec):
+        precisions, offset = [], 0
+        for like in self.likelihoods:
+            nobs = len(like.observables)
+            sub = dict(spec, observables=spec['observables'][offset:offset + nobs])
+            sub = like._finalize_spec(sub)
+            if not isinstance(sub['precision'], list):
+                if nobs > 1: raise NotImplementedError('SumLikelihood members with a joint precision over several observables')
+                precisions.append(sub['precision'])
+            else:
+                precisions += list(sub['precision'])
+            offset += nobs
+        spec['precision'] = precisions
+        self.flatdata = np.concatenate([obs.flatdata for obs in self.observables])
+        return spec

@@ -1,0 +1,169 @@
+"""Host-side mirrors of the reference's two-point observables and window on the batched path (declarative: constants only).
+
+  TracerPowerSpectrumMultipolesObservable            reference observables/galaxy_clustering/power_spectrum.py:22-121, :400-404
+  TracerCorrelationFunctionMultipolesObservable       reference observables/galaxy_clustering/correlation_function.py:380-381
+  window handling (ndarray ``wmatrix`` branch, ``kin`` / ``kinrebin`` / ``kinlim`` rebinning, shot noise in / out, k-mask)
+                                                     reference observables/galaxy_clustering/window.py:207-473
+File-based inputs (pypower / pycorr / lsstypes containers) are out of scope: arrays only.
+"""
+import numpy as np
+
+
+def matrix_lininterp(xin, xout):
+    """Matrix for linear interpolation (reference desilike/utils.py:646-657)."""
+    toret = np.zeros((len(xin), len(xout)), dtype='f8')
+    for iout, xo in enumerate(xout):
+        iin = np.searchsorted(xin, xo, side='right') - 1
+        if 0 <= iin < len(xin) - 1:
+            frac = (xo - xin[iin]) / (xin[iin + 1] - xin[iin])
+            toret[iin, iout] = 1. - frac
+            toret[iin + 1, iout] = frac
+        elif np.isclose(xo, xin[-1]):
+            toret[iin, iout] = 1.
+    return toret
+
+
+def _block_diag(mats):
+    import scipy.linalg
+    return scipy.linalg.block_diag(*mats)
+
+
+class BaseTwoPointObservable(object):
+    _default_step = 0.01
+
+    def _set_binning(self, x, xlim, ells, step_default):
+        """(reference window.py:218-292, simplified to arrays): -> list of per-multipole coordinates."""
+        if ells is None: ells = list(xlim) if xlim is not None else (0, 2, 4)
+        ells = tuple(ells)
+        if x is not None:
+            if np.ndim(x[0]) == 0: x = [x] * len(ells)
+            x = [np.array(xx, dtype='f8') for xx in x]
+            if len(x) != len(ells): raise ValueError("provide as many k's as ells")
+        masklim = None
+        if xlim is not None:
+            xlim = dict(xlim)
+            if x is not None:
+                newx, newells, masklim = [], [], {}
+                for ill, ell in enumerate(ells):
+                    xx = x[ill]
+                    masklim[ell] = np.zeros(len(xx), dtype='?')
+                    if ell not in xlim: continue
+                    lo, hi, *step = xlim[ell]
+                    mask = (xx >= lo) & (xx <= hi)
+                    masklim[ell] = mask
+                    if mask.any():
+                        newx.append(xx[mask]); newells.append(ell)
+                x, ells = newx, tuple(newells)
+            else:
+                if list(ells) != list(xlim): raise ValueError('incompatible ells = {} and lim = {}'.format(ells, list(xlim)))
+                x = []
+                for ell in ells:
+                    lo, hi, *step = xlim[ell]
+                    step = step[0] if step else step_default
+                    edges = np.arange(lo, hi + step / 2., step=step)
+                    x.append((edges[:-1] + edges[1:]) / 2.)
+        if x is None:
+            x = [np.arange(0.01, 0.2 + step_default / 2., step_default)] * len(ells)
+        return x, ells, masklim
+
+
+class TracerPowerSpectrumMultipolesObservable(BaseTwoPointObservable):
+
+    def __init__(self, data=None, covariance=None, klim=None, k=None, ells=None, wmatrix=None, kin=None, kinrebin=1, kinlim=None, ellsin=None,
+                 theory=None, shotnoise=None, wshotnoise=None, transform=None, name='spectrum2poles'):
+        from .theories import KaiserTracerPowerSpectrumMultipoles
+        self.name, self.transform = name, transform
+        if transform not in (None, 'cubic'): raise ValueError('transform must be one of [None, "cubic"]')
+        self.k, self.ells, masklim = self._set_binning(k, klim, ells, self._default_step)
+        if theory is None: raise ValueError('provide a theory (the reference default needs a cosmoprimo fiducial)')
+        self.theory = theory
+        self.matrix_full, self.kmask, self.offset = None, None, None
+        if wmatrix is None:   # reference window.py:296-303
+            self.ellsin = tuple(self.ells)
+            self.kin = np.unique(np.concatenate(self.k, axis=0))
+            if not all(kk.shape == self.kin.shape and np.allclose(kk, self.kin) for kk in self.k):
+                kmask = [np.searchsorted(self.kin, kk, side='left') for kk in self.k]
+                self.kmask = np.concatenate([self.kin.size * i + km for i, km in enumerate(kmask)], axis=0)
+        elif isinstance(wmatrix, np.ndarray):   # reference window.py:309-323
+            self.ellsin = tuple(ellsin or self.ells)
+            matrix_full = np.array(wmatrix, dtype='f8')
+            ksize = sum(len(kk) for kk in self.k)
+            if matrix_full.shape[0] != ksize:
+                raise ValueError('output "wmatrix" size is {:d}, but got {:d} output "k"'.format(matrix_full.shape[0], ksize))
+            kin = np.asarray(kin, dtype='f8').flatten()
+            self.kin = kin.copy()
+            if kinrebin is not None and kinrebin != 1: self.kin = self.kin[::kinrebin]
+            if kinlim is not None: self.kin = self.kin[(self.kin >= kinlim[0]) & (self.kin <= kinlim[-1])]
+            rebin = _block_diag([matrix_lininterp(self.kin, kin) for ell in self.ellsin])
+            self.matrix_full = matrix_full.dot(rebin.T)
+        else:
+            raise ValueError('only ndarray window matrices are supported on this path (file readers of pypower / lsstypes are out of scope)')
+        self.theory.set_k(self.kin, self.ellsin)
+        # shot noise in / out (reference window.py:445-457)
+        shotnoise = 0. if shotnoise is None else float(shotnoise)
+        self.shotnoisein = np.array([shotnoise * (ell == 0) for ell in self.ellsin])
+        base = np.concatenate([np.full_like(kk, (ell == 0), dtype='f8') for ell, kk in zip(self.ells, self.k)])
+        self.shotnoiseout = shotnoise * base
+        if wshotnoise is not None:
+            self.shotnoisein[...] = 0.
+            self.shotnoiseout = shotnoise * (base - np.concatenate(wshotnoise, axis=0) if not np.ndim(wshotnoise[0]) == 0 else base - np.asarray(wshotnoise))
+        self.covariance = None if covariance is None else np.array(covariance, dtype='f8')
+        self._data_params = dict(data) if isinstance(data, dict) else None
+        self.flatdata = None
+        if data is not None and self._data_params is None:
+            flatdata = np.ravel(np.asarray(data, dtype='f8'))
+            if masklim is not None:
+                sizes = [len(m) for m in masklim.values()]
+                if flatdata.size == sum(sizes):
+                    chunks = np.split(flatdata, np.cumsum(sizes)[:-1])
+                    flatdata = np.concatenate([chunks[list(masklim).index(ell)][masklim[ell]] for ell in self.ells])
+            self.flatdata = flatdata
+
+    @property
+    def size(self):
+        return sum(len(kk) for kk in self.k)
+
+    def observable_spec(self):
+        """Window + constants of this observable as the ``obs`` part of a likelihood spec (everything folded to W, offset)."""
+        nin = self.theory.nin
+        nkin = len(self.kin)
+        W = self.matrix_full
+        offset = np.zeros(self.size)
+        noise_in = np.repeat(self.shotnoisein, nkin)
+        if W is not None:
+            offset = W.dot(noise_in)
+        else:
+            offset = noise_in[self.kmask] if self.kmask is not None else noise_in.copy()
+            if self.kmask is not None:
+                W = np.eye(nin)[self.kmask]
+        if self.offset is not None: offset = offset + self.offset
+        offset = offset - self.shotnoiseout
+        return dict(name=self.name, nin=nin, wmatrix=W, offset=offset, transform=self.transform)
+
+
+class TracerCorrelationFunctionMultipolesObservable(BaseTwoPointObservable):
+    _default_step = 5.
+
+    def __init__(self, data=None, covariance=None, slim=None, s=None, ells=None, theory=None, transform=None, name='correlation2poles'):
+        self.name, self.transform = name, None
+        self.s, self.ells, masklim = self._set_binning(s, slim, ells, self._default_step)
+        if theory is None: raise ValueError('provide a theory')
+        self.theory = theory
+        self.sin = np.unique(np.concatenate(self.s, axis=0))
+        self.smask = None
+        if not all(ss.shape == self.sin.shape and np.allclose(ss, self.sin) for ss in self.s):
+            smask = [np.searchsorted(self.sin, ss, side='left') for ss in self.s]
+            self.smask = np.concatenate([self.sin.size * i + sm for i, sm in enumerate(smask)], axis=0)
+        self.theory.set_k(self.sin, self.ells)
+        self.covariance = None if covariance is None else np.array(covariance, dtype='f8')
+        self._data_params = dict(data) if isinstance(data, dict) else None
+        self.flatdata = None if (data is None or self._data_params is not None) else np.ravel(np.asarray(data, dtype='f8'))
+
+    @property
+    def size(self):
+        return sum(len(ss) for ss in self.s)
+
+    def observable_spec(self):
+        nin = self.theory.nin
+        W = np.eye(nin)[self.smask] if self.smask is not None else None
+        return dict(name=self.name, nin=nin, wmatrix=W, offset=None, transform=None)

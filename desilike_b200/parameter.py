@@ -1,0 +1,119 @@
+"""Minimal parameter containers mirroring the part of desilike/parameter.py the batched path needs:
+name / value / fixed / prior / derived ('.marg', '.best', '.auto', '.prec' mark analytically solved parameters,
+reference parameter.py:659,864-866) and name-based selection.  Not a re-implementation of the reference's 3000-line
+module: containers only, no expression evaluation, no Samples algebra."""
+import fnmatch
+
+import numpy as np
+
+
+class Parameter(object):
+
+    def __init__(self, basename, value=None, fixed=False, prior=None, ref=None, derived=False, namespace='', latex=None, delta=None):
+        self.basename, self.namespace = str(basename), str(namespace or '')
+        self.prior = dict(prior) if prior is not None else None
+        if self.prior is not None and 'dist' not in self.prior:
+            self.prior['dist'] = 'uniform'
+        self.ref = dict(ref) if ref is not None else None
+        if value is None:   # reference default: centre of the ref (else prior) distribution
+            value = 0.
+            for dist in (self.ref, self.prior):
+                if dist is not None:
+                    if 'limits' in dist and dist.get('dist', 'uniform') == 'uniform' and np.all(np.isfinite(dist['limits'])): value = float(np.mean(dist['limits']))
+                    elif 'loc' in dist: value = float(dist['loc'])
+                    break
+        self.value, self.fixed, self.derived, self.latex, self.delta = float(value), bool(fixed), derived, latex, delta
+
+    @property
+    def name(self):
+        return '{}.{}'.format(self.namespace, self.basename) if self.namespace else self.basename
+
+    @property
+    def solved(self):
+        """reference parameter.py:864-866."""
+        return isinstance(self.derived, str) and self.derived.startswith('.') and not self.fixed
+
+    @property
+    def varied(self):
+        return not self.fixed and (self.derived is False or self.solved)
+
+    def update(self, **kwargs):
+        for key, val in kwargs.items():
+            if key == 'prior' and val is not None:
+                val = dict(val)
+                val.setdefault('dist', 'uniform')
+            if not hasattr(self, key) and key not in ('name',):
+                raise AttributeError('unknown parameter attribute {}'.format(key))
+            setattr(self, key, val if key != 'value' else float(val))
+        return self
+
+    def clone(self, **kwargs):
+        new = Parameter(self.basename, value=self.value, fixed=self.fixed, prior=self.prior, ref=self.ref, derived=self.derived,
+                        namespace=self.namespace, latex=self.latex, delta=self.delta)
+        return new.update(**kwargs)
+
+    def __repr__(self):
+        return 'Parameter({}, value={}, {})'.format(self.name, self.value, 'solved' if self.solved else 'varied' if self.varied else 'fixed')
+
+
+class ParameterCollection(object):
+
+    def __init__(self, params=()):
+        self.data = []
+        for p in params: self.set(p)
+
+    def set(self, param):
+        for i, p in enumerate(self.data):
+            if p.name == param.name:
+                self.data[i] = param
+                return
+        self.data.append(param)
+
+    def __iter__(self):
+        return iter(self.data)
+
+    def __len__(self):
+        return len(self.data)
+
+    def __contains__(self, name):
+        name = getattr(name, 'name', name)
+        return any(p.name == name for p in self.data)
+
+    def __getitem__(self, name):
+        if isinstance(name, int): return self.data[name]
+        for p in self.data:
+            if p.name == name: return p
+        for p in self.data:   # basename lookup when unambiguous
+            if p.basename == name: return p
+        raise KeyError(name)
+
+    def names(self, **kwargs):
+        return [p.name for p in self.select(**kwargs)]
+
+    def select(self, varied=None, fixed=None, solved=None, basename=None, name=None):
+        out = []
+        patterns = [basename] if isinstance(basename, str) else basename
+        npatterns = [name] if isinstance(name, str) else name
+        for p in self.data:
+            if varied is not None and p.varied != varied: continue
+            if fixed is not None and p.fixed != fixed: continue
+            if solved is not None and p.solved != solved: continue
+            if patterns is not None and not any(fnmatch.fnmatch(p.basename, pat) for pat in patterns): continue
+            if npatterns is not None and not any(fnmatch.fnmatch(p.name, pat) for pat in npatterns): continue
+            out.append(p)
+        return ParameterCollection(out)
+
+    def __add__(self, other):
+        new = ParameterCollection(self.data)
+        for p in other: new.set(p)
+        return new
+
+    def __repr__(self):
+        return 'ParameterCollection({})'.format(self.names())
+
+
+class Samples(dict):
+    """Derived outputs of a batched call: name -> array shaped like the input batch (stand-in for desilike's Samples)."""
+
+    def __getitem__(self, name):
+        return dict.__getitem__(self, getattr(name, 'name', name))

@@ -1,0 +1,269 @@
+"""Host-side mirrors of the reference's theory calculators on the batched path.  They are *declarative*: they hold the
+constants and the parameter collection (names, defaults and priors copied from the reference's YAML) and describe
+themselves as the ``theory`` / ``terms`` parts of a likelihood spec; all per-point arithmetic happens in the CUDA kernels.
+
+Mirrored (same class names, argument meaning, parameter names):
+  ShapeFitPowerSpectrumTemplate, BAOPowerSpectrumTemplate          reference theories/galaxy_clustering/power_template.py:69-172, :340-376, :690-761
+  KaiserTracerPowerSpectrumMultipoles, EFTLikeKaiserTracer...       reference theories/galaxy_clustering/full_shape.py:144-207, :466-550, :577-640
+  DampedBAOWigglesTracerPowerSpectrumMultipoles / ...CorrelationFunctionMultipoles   reference theories/galaxy_clustering/bao.py:96-151, :424-541, :805-924
+
+The fiducial linear power spectrum comes from cosmoprimo/CLASS in the reference (power_template.py:49-66); here the
+caller provides it (callable or tabulated) -- it is a constant of the path, not part of its arithmetic.
+"""
+import re
+
+import numpy as np
+
+from .parameter import Parameter, ParameterCollection
+
+_Q = dict(prior=dict(limits=[0.8, 1.2]), ref=dict(limits=[0.99, 1.01]), value=1., delta=0.008)
+_AP_PARAMS = {'qparqper': ['qpar', 'qper'], 'qiso': ['qiso'], 'qap': ['qap'], 'qisoqap': ['qiso', 'qap']}
+
+
+class BaseCalculator(object):
+    """Common parameter plumbing (subset of reference desilike/base.py:1119-1322)."""
+
+    @property
+    def all_params(self):
+        return self.params
+
+    @property
+    def varied_params(self):
+        return self.all_params.select(varied=True)
+
+
+def _tabulate(fun, k):
+    if callable(fun): return np.asarray(fun(k), dtype='f8')
+    fun = np.asarray(fun, dtype='f8')
+    if fun.shape != np.shape(k): raise ValueError('tabulated fiducial spectrum must match the template k-grid')
+    return fun
+
+
+class BasePowerSpectrumTemplate(BaseCalculator):
+
+    def __init__(self, pk_dd_fid, f_fid, pknow_dd_fid=None, k=None, z=1., apmode='qparqper', eta=1. / 3., only_now=False, rs_drag=None):
+        self.pk_dd_fid, self.pknow_dd_fid, self.f_fid = pk_dd_fid, pknow_dd_fid, float(f_fid)
+        self.k = None if k is None else np.asarray(k, dtype='f8')
+        self.z, self.apmode, self.eta, self.only_now, self.rs_drag_fid = z, apmode, float(eta), bool(only_now), rs_drag
+        if apmode not in _AP_PARAMS: raise ValueError('unknown apmode {}'.format(apmode))
+        self.params = ParameterCollection([Parameter(name, **_Q) for name in _AP_PARAMS[apmode]])
+
+    def template_spec(self, k):
+        """Constants on the template grid ``k`` (chosen by the PT theory, reference full_shape.py:29)."""
+        if self.k is not None: k = self.k
+        spec = dict(k=k, pk_dd_fid=_tabulate(self.pk_dd_fid, k), f_fid=self.f_fid, apmode=self.apmode, eta=self.eta, only_now=self.only_now)
+        spec['pknow_dd_fid'] = _tabulate(self.pknow_dd_fid, k) if self.pknow_dd_fid is not None else spec['pk_dd_fid']
+        return spec
+
+
+class ShapeFitPowerSpectrumTemplate(BasePowerSpectrumTemplate):
+    """pk_dd = pk_dd_fid * exp(dm / a * tanh(a ln(k / kp)) + dn ln(k / kp)),  f = f_fid * df  (reference power_template.py:747-761)."""
+
+    def __init__(self, *args, kp=0.03, a=0.6, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.kp, self.a = float(kp), float(a)
+        for p in [Parameter('dm', value=0., prior=dict(limits=[-3., 3.]), ref=dict(limits=[-0.01, 0.01]), delta=0.01),
+                  Parameter('dn', value=0., fixed=True, prior=dict(limits=[-0.5, 0.5])),
+                  Parameter('df', value=1., prior=dict(limits=[0., 2.]), ref=dict(limits=[0.95, 1.05]), delta=0.02)]:
+            self.params.set(p)
+
+    def template_spec(self, k):
+        return dict(super().template_spec(k), kind='shapefit', a=self.a, kp=self.kp)
+
+
+class BAOPowerSpectrumTemplate(BasePowerSpectrumTemplate):
+    """Fixed linear template, f = f_fid * df (reference power_template.py:372-376)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.params.set(Parameter('df', value=1., fixed=True, prior=dict(limits=[0., 2.])))
+
+    def template_spec(self, k):
+        return dict(super().template_spec(k), kind='bao')
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class BaseTracerPowerSpectrumMultipoles(BaseCalculator):
+    _klim = (1e-3, 1., 500)   # reference full_shape.py:19
+    is_correlation = False
+
+    def __init__(self, template=None, pt=None, k=None, ells=(0, 2, 4), mu=8, shotnoise=1e4, tracer=None):
+        self.template, self.pt = template, pt
+        self.k = np.linspace(0.01, 0.2, 101) if k is None else np.asarray(k, dtype='f8')   # reference base.py:16-19
+        self.ells, self.mu, self.nd, self.tracer = tuple(ells), int(mu), 1. / float(shotnoise), tracer
+        self.params = ParameterCollection()
+
+    def _ns(self, name):
+        return '{}.{}'.format(self.tracer, name) if self.tracer else name
+
+    def set_k(self, k, ells):
+        """Called by the window (reference window.py:443: ``theory.init.update(k=kin, ells=ellsin)``)."""
+        self.k, self.ells = np.asarray(k, dtype='f8'), tuple(ells)
+
+    @property
+    def all_params(self):
+        base = self.pt.all_params if self.pt is not None else (self.template.params + self._pt_params())
+        return base + self.params
+
+    def _pt_params(self):
+        return ParameterCollection()
+
+    @property
+    def nin(self):
+        return len(self.ells) * len(self.k)
+
+
+class KaiserTracerPowerSpectrumMultipoles(BaseTracerPowerSpectrumMultipoles):
+    """P_ell = b1^2 pk_dd + 2 b1 pk_dt + pk_tt + delta_{ell 0} sn0 / nd  (reference full_shape.py:545-550; tables :488-500)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.params = ParameterCollection([
+            Parameter('b1', prior=dict(limits=[0., 4.]), ref=dict(limits=[1., 2.]), namespace=self.tracer),
+            Parameter('sn0', prior=dict(dist='norm', loc=0., scale=1000.), ref=dict(dist='norm', loc=0., scale=0.1), namespace=self.tracer)])
+
+    def _pt_params(self):
+        return ParameterCollection([Parameter('sigmapar', value=0., fixed=True, prior=dict(limits=[0., 10.])),
+                                    Parameter('sigmaper', value=0., fixed=True, prior=dict(limits=[0., 10.]))])
+
+    def theory_spec(self):
+        if self.pt is not None:
+            return self.pt.theory_spec(self)
+        k_t = np.geomspace(min(self._klim[0], self.k[0] / 2), max(self._klim[1], self.k[-1] * 2), self._klim[2])  # reference full_shape.py:29
+        names = self.all_params.names()
+        params = [n for n in names if n.split('.')[-1] in ('qpar', 'qper', 'qiso', 'qap', 'dm', 'dn', 'df', 'sigmapar', 'sigmaper')]
+        return dict(kind='kaiser', k=self.k, ells=self.ells, nmu=self.mu, template=self.template.template_spec(k_t), params=params,
+                    defaults={p.basename: p.value for p in self.all_params})
+
+    def terms(self):
+        nk = len(self.k)
+        e0 = np.concatenate([np.full(nk, float(ell == 0)) for ell in self.ells])
+        b1, sn0 = self._ns('b1'), self._ns('sn0')
+        return [dict(scale=1., factors=[(b1, 2)], table='pk_dd'), dict(scale=2., factors=[(b1, 1)], table='pk_dt'),
+                dict(scale=1., factors=[], table='pk_tt'), dict(scale=1. / self.nd, factors=[(sn0, 1)], table=None, colvec=e0)]
+
+
+class EFTLikeKaiserTracerPowerSpectrumMultipoles(KaiserTracerPowerSpectrumMultipoles):
+    """Kaiser + EFT-like counter terms ct{ell}_{pow} * (k / kp)^pow * pk11_{ell=0} and stochastic terms sn{ell}_{pow} * (k / kp)^pow / nd
+    (reference full_shape.py:577-640), exactly marginalisable (set ``derived='.marg'``)."""
+    kp = 1.
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        b1, sn0 = self.params['b1'], self.params['sn0']
+        params = [b1]   # order of the reference YAML (full_shape.yaml:112-152): b1, ct*, sn0, sn*_2
+        for ell in (0, 2, 4):
+            params.append(Parameter('ct{:d}_2'.format(ell), value=0., prior=dict(dist='norm', loc=0., scale=100.), namespace=self.tracer))
+        params.append(sn0)
+        for ell in (0, 2, 4):
+            params.append(Parameter('sn{:d}_2'.format(ell), value=0., prior=dict(dist='norm', loc=0., scale=1000.), namespace=self.tracer))
+        self.params = ParameterCollection(params)
+
+    def terms(self):
+        terms = super().terms()
+        nk = len(self.k)
+        for p in self.params:
+            match = re.match(r'(ct|sn)(\d+)_(-?\d+)$', p.basename)
+            if not match: continue
+            base, ell, power = match.group(1), int(match.group(2)), int(match.group(3))
+            if ell not in self.ells: continue
+            colvec = np.zeros((len(self.ells), nk))
+            colvec[self.ells.index(ell)] = (self.k / self.kp)**power
+            if base == 'ct':
+                terms.append(dict(scale=1., factors=[(p.name, 1)], table='pk11_l0', colvec=colvec.ravel()))
+            else:
+                terms.append(dict(scale=1. / self.nd, factors=[(p.name, 1)], table=None, colvec=colvec.ravel()))
+        # reference behaviour: 'sn0' is added by KaiserTracer.calculate (full_shape.py:549) AND by the stochastic matrix (:634)
+        terms[3] = dict(terms[3], scale=2. / self.nd)
+        return terms
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class _BaseBAOTracer(BaseCalculator):
+
+    def __init__(self, template, ells=(0, 2), mu=10, mode='', smoothing_radius=15., tracer=None):
+        self.template, self.ells, self.mu, self.mode, self.smoothing_radius, self.tracer = template, tuple(ells), int(mu), str(mode), float(smoothing_radius), tracer
+        if self.mode not in ('', 'recsym', 'reciso'): raise ValueError('Reconstruction mode {} must be one of ["", "recsym", "reciso"]'.format(mode))
+        self.params = ParameterCollection([
+            Parameter('b1', prior=dict(limits=[0.2, 4.]), ref=dict(limits=[1.5, 2.5])), Parameter('dbeta', value=1., prior=dict(limits=[0.7, 1.3]), ref=dict(limits=[0.8, 1.2])),
+            Parameter('sigmas', value=0., prior=dict(limits=[0., 10.]), ref=dict(limits=[0., 1.])),
+            Parameter('sigmapar', value=9., fixed=True, prior=dict(limits=[0.1, 10.])), Parameter('sigmaper', value=6., fixed=True, prior=dict(limits=[0.1, 10.]))])
+
+    @property
+    def all_params(self):
+        return self.template.params + self.params
+
+    def _theory_common(self):
+        k_t = np.geomspace(1e-4, 1., 2000) if self.template.k is None else self.template.k   # reference bao.py:67,79
+        names = self.all_params.names()
+        params = [n for n in names if n.split('.')[-1] in ('qpar', 'qper', 'qiso', 'qap', 'df', 'b1', 'dbeta', 'sigmas', 'sigmapar', 'sigmaper')]
+        return dict(ells=self.ells, nmu=self.mu, template=self.template.template_spec(k_t), mode=self.mode, smoothing_radius=self.smoothing_radius,
+                    params=params, defaults={p.basename: p.value for p in self.all_params})
+
+    def _broadband_terms(self, x, pivot, powers):
+        terms = []
+        for ill, ell in enumerate(self.ells):
+            for power in powers:
+                name = 'al{:d}_{:d}'.format(ell, power)
+                if name not in self.params: continue
+                colvec = np.zeros((len(self.ells), len(x)))
+                colvec[ill] = (x / pivot)**power
+                terms.append(dict(scale=1., factors=[(self.params[name].name, 1)], table=None, colvec=colvec.ravel()))
+        return terms
+
+
+class DampedBAOWigglesTracerPowerSpectrumMultipoles(_BaseBAOTracer):
+    """Damped BAO P_ell(k) (Beutler 2017 / Chen 2023 'standard' model, reference bao.py:117-134) + power-law broadband
+    al{ell}_{pow} (k / kp)^pow, pow in [-3, 1] (reference bao.py:467-476, :527-534)."""
+    is_correlation = False
+
+    def __init__(self, template, k=None, kp=None, **kwargs):
+        super().__init__(template, **kwargs)
+        self.k = np.linspace(0.01, 0.2, 101) if k is None else np.asarray(k, dtype='f8')
+        if kp is None:
+            if template.rs_drag_fid is None: raise ValueError('provide kp or the template rs_drag (kp defaults to 2 pi / rs_drag, reference bao.py:493)')
+            kp = 2. * np.pi / template.rs_drag_fid
+        self.kp = float(kp)
+        for ell in self.ells:
+            for power in range(-3, 2):
+                self.params.set(Parameter('al{:d}_{:d}'.format(ell, power), value=0., ref=dict(limits=[-1e2, 1e2]), delta=0.005))
+
+    def set_k(self, k, ells):
+        self.k, self.ells = np.asarray(k, dtype='f8'), tuple(ells)
+
+    @property
+    def nin(self):
+        return len(self.ells) * len(self.k)
+
+    def theory_spec(self):
+        return dict(self._theory_common(), kind='bao_pk', k=self.k)
+
+    def terms(self):
+        return [dict(scale=1., factors=[], table='power')] + self._broadband_terms(self.k, self.kp, range(-3, 2))
+
+
+class DampedBAOWigglesTracerCorrelationFunctionMultipoles(_BaseBAOTracer):
+    """xi_ell(s) from the damped BAO P_ell(k) through FFTLog (reference base.py:46-136) + power-law broadband
+    al{ell}_{pow} (s / sp)^pow, pow in [-2, 2], sp = 2 pi / 0.02 (reference bao.py:849-853, :867, :905)."""
+    is_correlation = True
+
+    def __init__(self, template, s=None, sp=None, **kwargs):
+        super().__init__(template, **kwargs)
+        self.s = np.linspace(20., 200., 101) if s is None else np.asarray(s, dtype='f8')
+        self.sp = 2. * np.pi / 0.02 if sp is None else float(sp)
+        for ell in self.ells:
+            for power in range(-2, 3):
+                self.params.set(Parameter('al{:d}_{:d}'.format(ell, power), value=0., ref=dict(limits=[-1e-3, 1e-3]), delta=0.005))
+
+    def set_k(self, s, ells):
+        self.s, self.ells = np.asarray(s, dtype='f8'), tuple(ells)
+
+    @property
+    def nin(self):
+        return len(self.ells) * len(self.s)
+
+    def theory_spec(self):
+        return dict(self._theory_common(), kind='bao_xi', s=self.s)
+
+    def terms(self):
+        return [dict(scale=1., factors=[], table='corr')] + self._broadband_terms(self.s, self.sp, range(-2, 3))

@@ -47,5 +47,25 @@ def main():
         print(name, X.shape, ref['logposterior'][:3])
 
 
+def bao_theory():
+    """Theory-level fixture: the reference's damped-BAO P_ell(k) class and its P -> xi class (get_corr wiring; the FFTLog
+    call itself is routed to oracle/fftlog.py by the cosmoprimo stub) on seeded points."""
+    ref_harness.setup()
+    from desilike.theories.galaxy_clustering import (BAOPowerSpectrumTemplate, DampedBAOWigglesTracerPowerSpectrumMultipoles,
+                                                     DampedBAOWigglesTracerCorrelationFunctionMultipoles)
+    k, s, ells = np.arange(0.02, 0.3, 0.005), np.arange(20., 152., 4.), (0, 2)
+    pk = DampedBAOWigglesTracerPowerSpectrumMultipoles(template=BAOPowerSpectrumTemplate(z=1.), k=k, ells=ells)
+    xi = DampedBAOWigglesTracerCorrelationFunctionMultipoles(template=BAOPowerSpectrumTemplate(z=1.), s=s, ells=ells)
+    names = ['qpar', 'qper', 'b1', 'dbeta', 'sigmas', 'sigmapar', 'sigmaper']
+    spec = dict(params=names)
+    X = configs.sample_points(spec, 12, seed=107)
+    power = np.array([pk(**dict(zip(names, x))) for x in X])
+    corr = np.array([xi(**dict(zip(names, x))) for x in X])
+    np.savez_compressed(os.path.join(HERE, 'bao_theory.npz'), case=json.dumps(dict(kind='bao_theory')), X=X, k=k, s=s, power=power, corr=corr,
+                        k_template_pk=np.array(pk.template.k), k_template_xi=np.array(xi.template.k))
+    print('bao_theory', power.shape, corr.shape)
+
+
 if __name__ == '__main__':
+    bao_theory()
     main()

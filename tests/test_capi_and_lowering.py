@@ -101,3 +101,54 @@ def test_unsupported_features_fail_loudly():
     spec['observables'][0]['theory'] = configs.config_c2(nkin=20, nbins=6, order=1)['observables'][0]['theory']
     with pytest.raises(LoweringError):
         Lowered(spec)
+
+
+THEORY_CASES = {
+    'c1_kaiser': lambda: configs.config_c1(),
+    'kaiser_window_eft_marg': lambda: configs.config_kaiser_window(eftlike=True, solved=True),
+    'c3_bao_fftlog': lambda: configs.config_c3(),
+    'c4_mlp': lambda: configs.config_c4(ntracers=2, nkin=40, nbins=10, hidden=(16, 16)),
+}
+
+
+def _mlp_features(ig, gen, Xe):
+    nh, act, d = gen.idata[:3]
+    widths, dd = list(gen.idata[3:]), gen.ddata
+    v = Xe * dd[:d] + dd[d:2 * d]
+    off, win = 2 * d, d
+    for h in widths:
+        W = dd[off:off + win * h].reshape(win, h); off += win * h
+        b = dd[off:off + h]; off += h
+        v = v @ W + b
+        v = {1: lambda t: t / (1 + np.exp(-t)), 2: lambda t: np.maximum(t, 0.), 3: np.tanh, 0: lambda t: t}[int(act)](v)
+        win = h
+    return np.concatenate([np.ones((len(v), 1)), np.zeros((len(v), 1)), v], axis=-1)
+
+
+@pytest.mark.parametrize('name', list(THEORY_CASES))
+def test_theory_payloads_reproduce_oracle(name):
+    """Plan-time constants of the theory kernels (spline pivots, FFTLog tables, MLP folding) evaluated by a NumPy mirror of
+    the kernels reproduce the oracle."""
+    from desilike_b200.lowering import Lowered
+    spec = THEORY_CASES[name]()
+    low = Lowered(spec)
+    X = configs.sample_points(spec, 5, seed=3)
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    fn = _mlp_features if name == 'c4_mlp' else lowered_numpy.theory_features
+    got = lowered_numpy.evaluate(low, X, feature_fn=fn)
+    theory = lowered_numpy.evaluate(low, X, feature_fn=fn, white=False)
+    assert np.max(np.abs(theory - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-11
+    assert np.allclose(got['logposterior'], ref['logposterior'], rtol=1e-9, atol=1e-7)
+
+
+def test_spline_constants_match_scipy():
+    from scipy import interpolate
+    from desilike_b200 import spline
+    from oracle import synthetic
+    for x in [np.log10(np.geomspace(1e-3, 1., 500)), np.sort(np.random.default_rng(0).uniform(-3, 0, 40))]:
+        y = synthetic.pk_fid(10**x)
+        c = spline.spline_constants(x)
+        M = spline.second_derivatives(c, x.size, y)
+        xq = np.random.default_rng(1).uniform(x[0] - 0.05, x[-1] + 0.05, 1000)
+        ref = interpolate.interp1d(x, y, kind='cubic', fill_value='extrapolate')(xq)
+        assert np.max(np.abs(spline.evaluate(c, x.size, y, M, xq) / ref - 1)) < 1e-11

@@ -1,0 +1,130 @@
+"""The reference-facing host API evaluated through the C-ABI on the GPU; these read like the reference's own tests
+(likelihoods/tests/test_galaxy_clustering.py:6-16, observables/tests/test_galaxy_clustering.py:128-174, tests/test_base.py:246-294).
+Run with ``-m gpu``."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import desilike_b200 as dl
+from oracle import configs, pipeline, synthetic
+from test_host_api import make_kaiser_likelihood
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def kaiser_likelihood(**kwargs):
+    template = dl.ShapeFitPowerSpectrumTemplate(pk_dd_fid=synthetic.pk_fid, pknow_dd_fid=synthetic.pknow_fid, f_fid=synthetic.F_FID)
+    theory = dl.KaiserTracerPowerSpectrumMultipoles(template=template)
+    observable = dl.TracerPowerSpectrumMultipolesObservable(data={}, klim={0: [0.02, 0.2, 0.005], 2: [0.02, 0.2, 0.005], 4: [0.02, 0.2, 0.005]},
+                                                            theory=theory, covariance=np.eye(108), **kwargs)
+    return dl.ObservablesGaussianLikelihood(observables=[observable])
+
+
+def test_likelihood_is_zero_at_data_generating_parameters(gpu_required):
+    """reference likelihoods/tests/test_galaxy_clustering.py:6-16: data = theory at default params, identity covariance."""
+    like = kaiser_likelihood()
+    assert like.varied_params.names() == ['qpar', 'qper', 'dm', 'df', 'b1', 'sn0']
+    assert abs(like()) < 1e-12
+    assert like.flatdiff.shape == (108,) and np.max(np.abs(like.flatdiff)) < 1e-9 * np.max(np.abs(like.flattheory))
+    assert like(b1=2.) < -1.
+    assert np.allclose(like.flatdiff, like.flattheory - like.flatdata)
+    assert abs(like.loglikelihood + like.logprior - like(b1=2.)) < 1e-9
+
+
+def test_vmap_conventions(gpu_required):
+    """reference base.py:162-226: result shaped params.shape; errors='return' -> (results, errs); return_derived -> tuple."""
+    like = kaiser_likelihood()
+    rng = np.random.default_rng(0)
+    params = {'b1': rng.uniform(1., 2., (3, 4)), 'qpar': rng.uniform(0.95, 1.05, (3, 4))}
+    res = dl.vmap(like, backend='cuda')(params)
+    assert res.shape == (3, 4)
+    single = np.array([[like(b1=params['b1'][i, j], qpar=params['qpar'][i, j]) for j in range(4)] for i in range(3)])
+    assert np.allclose(res, single, rtol=1e-12, atol=1e-9)
+    (res2, derived), errs = dl.vmap(like, backend='cuda', errors='return', return_derived=True)(params)
+    assert errs == {} and np.array_equal(res2, res)
+    assert derived['loglikelihood'].shape == (3, 4) and np.allclose(derived['loglikelihood'] + derived['logprior'], res)
+    with pytest.raises(ValueError):
+        dl.vmap(like)({'b1': 1.})
+    with pytest.raises(ValueError):
+        dl.vmap(like)({'b1': np.zeros(3), 'qpar': np.ones(4)})
+    with pytest.raises(dl.PipelineError):
+        dl.vmap(like)({'unknown': np.zeros(3)})
+    out = dl.vmap(like)({'b1': np.array([1.5, 5.])})   # b1 prior is uniform [0, 4]
+    assert np.isfinite(out[0]) and np.isneginf(out[1])
+
+
+@pytest.mark.parametrize('name', ['c1_kaiser_shapefit', 'kaiser_window', 'eftlike_sampled', 'eftlike_marg', 'eftlike_best'])
+def test_api_matches_reference_outputs(gpu_required, name):
+    """Mirror classes -> plan -> CUDA vs the reference's own outputs on the same inputs."""
+    data = np.load(os.path.join(HERE, 'golden', name + '.npz'))
+    case = json.loads(str(data['case']))
+    spec = getattr(configs, case['config'])(**case['kwargs'])
+    like = make_kaiser_likelihood(spec, eftlike=case['eftlike'], mode=case['mode'])
+    X = data['X']
+    params = {n: X[:, i] for i, n in enumerate(spec['params'])}
+    (res, derived), errs = dl.vmap(like, errors='return', return_derived=True)(params)
+    ref = data['logposterior']
+    finite = np.isfinite(ref)
+    assert errs == {} and np.array_equal(np.isneginf(ref), np.isneginf(res))
+    assert np.allclose(res[finite], ref[finite], rtol=1e-9, atol=1e-7)
+    assert np.allclose(derived['loglikelihood'][finite], data['loglikelihood'][finite], rtol=1e-9, atol=1e-7)
+    if spec['solved']:
+        orc = pipeline.evaluate(spec, X)
+        for i, s in enumerate(spec['solved']):
+            assert np.allclose(derived[s['name']], orc['x_solved'][:, i], rtol=1e-7, atol=1e-7)
+
+
+def test_marg_invariant_under_sum_and_sumlikelihood(gpu_required):
+    """(L + L)() == 2 L() - logprior (reference observables/tests/test_galaxy_clustering.py:174) for independent copies."""
+    spec = configs.config_kaiser_window(eftlike=False, solved=False)
+    like1, like2 = make_kaiser_likelihood(spec), make_kaiser_likelihood(spec)
+    both = dl.SumLikelihood([like1, like2])
+    vals = dict(b1=1.8, qpar=1.02, sn0=0.05)
+    total, single = both(**vals), like1(**vals)
+    assert abs(total - (2. * single - like1.logprior)) < 1e-8 * max(1., abs(total))
+
+
+def test_emulated_likelihood_from_file(gpu_required, tmp_path):
+    """Emulator file -> EmulatedCalculator.load -> tracer theory -> observable -> likelihood on the GPU == oracle of the spec."""
+    spec = configs.config_c2(nkin=30, nbins=8, order=2)
+    th = spec['observables'][0]['theory']
+    kin, ells = np.arange(1, 31) * (0.35 / 30), (0, 2, 4)
+    tables = {name: th['tables'][name].reshape(-1, 3, 30) for name in ['pk_dd', 'pk_dt', 'pk_tt']}
+    fn = str(tmp_path / 'emu.npy')
+    dl.Emulator.from_taylor(th['params'], th['center'], th['powers'], tables, fixed=dict(k=kin, ells=ells, z=1.)).save(fn)
+    theory = dl.KaiserTracerPowerSpectrumMultipoles(pt=dl.EmulatedCalculator.load(fn))
+    obs0 = spec['observables'][0]
+    kout = configs.klim_edges((0.02, 0.02 + 8 * 0.005, 0.005))[:8]
+    observable = dl.TracerPowerSpectrumMultipolesObservable(data=obs0['data'], wmatrix=obs0['wmatrix'], kin=kin, ellsin=ells, k=[kout] * 3, ells=ells,
+                                                            theory=theory, shotnoise=1e4)
+    like = dl.ObservablesGaussianLikelihood([observable], precision=spec['precision'][0])
+    for p in like.all_params:
+        if p.name in spec['params']: p.update(fixed=False, prior=spec['priors'][p.name])
+        else: p.update(fixed=True)
+    X = configs.sample_points(spec, 100, seed=1)
+    res = dl.vmap(like)({n: X[:, i] for i, n in enumerate(spec['params'])})
+    assert np.allclose(res, pipeline.evaluate(spec, X)['logposterior'], rtol=1e-9, atol=1e-7)
+
+
+def test_bao_correlation_function_likelihood(gpu_required):
+    """Damped BAO xi_ell(s) with analytically marginalised broadband through the mirror classes."""
+    template = dl.BAOPowerSpectrumTemplate(pk_dd_fid=synthetic.pk_fid, pknow_dd_fid=synthetic.pknow_fid, f_fid=synthetic.F_FID, rs_drag=synthetic.RS_DRAG)
+    theory = dl.DampedBAOWigglesTracerCorrelationFunctionMultipoles(template=template, ells=(0, 2))
+    for p in theory.params.select(basename='al*'):
+        p.update(derived='.marg' if p.basename.endswith(('_0', '_2')) else False, fixed=not p.basename.endswith(('_0', '_2')))
+    s = np.arange(20., 152., 4.)
+    observable = dl.TracerCorrelationFunctionMultipolesObservable(data={'b1': 2., 'sigmas': 3.}, s=[s, s], ells=(0, 2), theory=theory,
+                                                                  covariance=np.diag(np.full(66, 1e-8)))
+    like = dl.ObservablesGaussianLikelihood([observable])
+    assert like.solved_params.names() == ['al0_0', 'al0_2', 'al2_0', 'al2_2']
+    built = like.spec
+    rng = np.random.default_rng(2)
+    X = np.column_stack([rng.uniform(0.97, 1.03, 40), rng.uniform(0.97, 1.03, 40), rng.uniform(1.8, 2.2, 40), rng.uniform(0.9, 1.1, 40), rng.uniform(2., 4., 40)])
+    assert built['params'] == ['qpar', 'qper', 'b1', 'dbeta', 'sigmas']
+    (res, derived) = dl.vmap(like, return_derived=True)({n: X[:, i] for i, n in enumerate(built['params'])})
+    orc = pipeline.evaluate(built, X)
+    assert np.max(np.abs(res - orc['logposterior']) / np.maximum(1., np.abs(orc['logposterior']))) < 1e-7
+    assert np.allclose(derived['al0_0'], orc['x_solved'][:, 0], rtol=1e-6, atol=1e-9)

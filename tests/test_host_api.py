@@ -1,0 +1,151 @@
+"""Host-side mirror of the reference interface (CPU part): the mirror classes produce a likelihood spec whose oracle
+evaluation equals the outputs of the reference's own classes (golden fixtures); vmap argument validation; emulator file
+round trip.  The GPU part (same objects evaluated through the C-ABI) is tests/test_gpu_api.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import desilike_b200 as dl
+from oracle import configs, pipeline, synthetic
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def make_kaiser_likelihood(spec, eftlike=False, mode=None):
+    """Same construction as oracle/ref_harness.py:reference_kaiser_likelihood, with desilike_b200's mirror classes."""
+    obs0 = spec['observables'][0]
+    th = obs0['theory']
+    template = dl.ShapeFitPowerSpectrumTemplate(pk_dd_fid=synthetic.pk_fid, pknow_dd_fid=synthetic.pknow_fid, f_fid=synthetic.F_FID)
+    cls = dl.EFTLikeKaiserTracerPowerSpectrumMultipoles if eftlike else dl.KaiserTracerPowerSpectrumMultipoles
+    theory = cls(template=template, mu=th['nmu'])
+    nell = len(th['ells'])
+    if obs0.get('wmatrix') is not None:
+        kw = dict(wmatrix=np.asarray(obs0['wmatrix_raw']), kin=th['k'], ellsin=th['ells'], k=[obs0['kout']] * nell, ells=th['ells'], shotnoise=obs0.get('shotnoise'))
+    else:
+        kw = dict(k=[th['k']] * nell, ells=th['ells'])
+    observable = dl.TracerPowerSpectrumMultipolesObservable(data=np.asarray(obs0['data']), theory=theory, **kw)
+    likelihood = dl.ObservablesGaussianLikelihood(observables=[observable], precision=np.array(spec['precision'][0]))
+    for param in likelihood.all_params:
+        if param.name in spec['params']:
+            param.update(fixed=False, prior=spec['priors'].get(param.name))
+        elif any(s['name'] == param.name for s in spec.get('solved', [])):
+            s = [s for s in spec['solved'] if s['name'] == param.name][0]
+            param.update(fixed=False, value=s['value'], prior=s.get('prior'), derived=mode or '.marg')
+        else:
+            param.update(fixed=True)
+    return likelihood
+
+
+@pytest.mark.parametrize('name', ['c1_kaiser_shapefit', 'kaiser_window', 'eftlike_sampled', 'eftlike_marg', 'eftlike_best'])
+def test_mirror_classes_reproduce_reference_outputs(name):
+    data = np.load(os.path.join(HERE, 'golden', name + '.npz'))
+    case = json.loads(str(data['case']))
+    spec = getattr(configs, case['config'])(**case['kwargs'])
+    like = make_kaiser_likelihood(spec, eftlike=case['eftlike'], mode=case['mode'])
+    built = like._finalize_spec(like.build_spec())
+    assert built['params'] == spec['params']
+    assert [s['name'] for s in built['solved']] == [s['name'] for s in spec['solved']]
+    X = data['X']
+    got = pipeline.evaluate(built, X, return_theory=True)
+    assert np.max(np.abs(got['flattheory'] - data['flattheory']) / np.max(np.abs(data['flattheory']), axis=0)) < 1e-12
+    finite = np.isfinite(data['logposterior'])
+    assert np.allclose(got['logposterior'][finite], data['logposterior'][finite], rtol=1e-11, atol=2e-9)
+
+
+def test_reference_default_parameters():
+    """Names, defaults and priors follow the reference YAML (full_shape.yaml:43-83, power_template.yaml:279-338)."""
+    template = dl.ShapeFitPowerSpectrumTemplate(pk_dd_fid=synthetic.pk_fid, f_fid=0.8)
+    theory = dl.KaiserTracerPowerSpectrumMultipoles(template=template)
+    names = theory.all_params.names()
+    assert names == ['qpar', 'qper', 'dm', 'dn', 'df', 'sigmapar', 'sigmaper', 'b1', 'sn0']
+    assert theory.all_params['b1'].value == 1.5 and theory.all_params['dn'].fixed and theory.all_params['sigmapar'].fixed
+    assert theory.varied_params.names() == ['qpar', 'qper', 'dm', 'df', 'b1', 'sn0']
+    eft = dl.EFTLikeKaiserTracerPowerSpectrumMultipoles(template=template)
+    assert [p.basename for p in eft.params] == ['b1', 'ct0_2', 'ct2_2', 'ct4_2', 'sn0', 'sn0_2', 'sn2_2', 'sn4_2']
+    assert eft.params['ct0_2'].prior == dict(dist='norm', loc=0., scale=100.)
+
+
+def test_vmap_argument_validation():
+    """reference base.py:144-157: rank >= 1, equal shapes; :531-533 unknown parameter."""
+    from desilike_b200.base import _check_params
+    with pytest.raises(ValueError):
+        _check_params({'a': 1.})
+    with pytest.raises(ValueError):
+        _check_params({'a': np.zeros(3), 'b': np.zeros(4)})
+    params, shape = _check_params({'a': np.zeros((2, 3)), 'b': np.ones((2, 3))})
+    assert shape == (2, 3) and params['a'].shape == (6,)
+    with pytest.raises(ValueError):
+        dl.vmap(None, backend='jax')
+    spec = configs.config_c1()
+    like = make_kaiser_likelihood(spec)
+    like._plan = type('FakePlan', (), {'params': spec['params'], 'close': lambda self: None})()
+    with pytest.raises(dl.PipelineError):
+        like._points({'not_a_param': [1.]})
+    X = like._points({'b1': [2., 3.]})
+    assert X.shape == (2, 6) and np.array_equal(X[:, 4], [2., 3.]) and np.all(X[:, 0] == 1.)
+
+
+def test_emulator_file_round_trip(tmp_path):
+    """Emulator save -> load -> same state and same spec (reference emulators/tests/test_base.py:10-69)."""
+    spec = configs.config_c2(nkin=30, nbins=8, order=2)
+    th = spec['observables'][0]['theory']
+    kin, ells = np.arange(1, 31) * (0.35 / 30), (0, 2, 4)
+    tables = {name: th['tables'][name].reshape(-1, 3, 30) for name in ['pk_dd', 'pk_dt', 'pk_tt']}
+    emu = dl.Emulator.from_taylor(th['params'], th['center'], th['powers'], tables, fixed=dict(k=kin, ells=ells, z=1.))
+    fn = str(tmp_path / 'emu.npy')
+    emu.save(fn)
+    state = np.load(fn, allow_pickle=True)[()]
+    for key in ['engines', 'xoperations', 'yoperations', 'defaults', 'fixed', 'varied_params', 'in_calculator_state', 'calculator__class__',
+                'is_calculator_sequence', 'yaml_data', 'all_params']:
+        assert key in state, key
+    assert state['engines']['pk_dd']['name'] == 'taylor' and state['engines']['pk_dd']['yshape'] == (3, 30)
+    pt = dl.EmulatedCalculator.load(fn)
+    got = pt.theory_spec()
+    assert got['kind'] == 'taylor' and np.array_equal(got['powers'], th['powers'])
+    for name in ['pk_dd', 'pk_dt', 'pk_tt']:
+        assert np.array_equal(got['tables'][name], th['tables'][name])
+    assert np.array_equal(got['tables']['pk11_l0'], np.tile(th['tables']['pk_dd'][:, :30], (1, 3)))
+    # emulated pt inside a tracer theory: same oracle result as the original spec
+    theory = dl.KaiserTracerPowerSpectrumMultipoles(pt=pt)
+    obs0 = spec['observables'][0]
+    kout = configs.klim_edges((0.02, 0.02 + 8 * 0.005, 0.005))[:8]
+    observable = dl.TracerPowerSpectrumMultipolesObservable(data=obs0['data'], wmatrix=obs0['wmatrix'], kin=kin, ellsin=ells, k=[kout] * 3, ells=ells,
+                                                            theory=theory, shotnoise=1e4)
+    like = dl.ObservablesGaussianLikelihood([observable], precision=spec['precision'][0])
+    for p in like.all_params:
+        if p.name in spec['params']: p.update(fixed=False, prior=spec['priors'][p.name])
+        else: p.update(fixed=True)
+    built = like._finalize_spec(like.build_spec())
+    X = configs.sample_points(spec, 8, seed=1)
+    cols = [spec['params'].index(n) for n in built['params']]
+    assert np.allclose(pipeline.evaluate(built, X[:, cols])['logposterior'], pipeline.evaluate(spec, X)['logposterior'], rtol=1e-12, atol=1e-9)
+
+
+def test_mlp_emulator_file_round_trip(tmp_path):
+    rng = np.random.default_rng(3)
+    kin = np.arange(1, 21) * (0.35 / 20)
+    nin = 3 * 20
+    mlp = configs.mlp_engine(rng, 3 * nin, hidden=(8, 8), kin=kin)
+    tables = {'pk_dd': slice(0, nin), 'pk_dt': slice(nin, 2 * nin), 'pk_tt': slice(2 * nin, 3 * nin)}
+    emu = dl.Emulator.from_mlp(['qpar', 'qper', 'dm', 'df'], mlp, tables, {n: (3, 20) for n in tables}, fixed=dict(k=kin, ells=(0, 2, 4), z=1.))
+    fn = str(tmp_path / 'mlp.npy')
+    emu.save(fn)
+    got = dl.EmulatedCalculator.load(fn).theory_spec()
+    from oracle import core
+    X = rng.uniform(0.95, 1.05, (6, 4)); X[:, 2] -= 1.
+    y0, y1 = core.mlp_predict(X, mlp), core.mlp_predict(X, got['mlp'])
+    for name, sl in tables.items():
+        assert np.allclose(y1[:, got['tables'][name]], y0[:, sl], rtol=1e-13)
+    assert len(got['mlp']['layers']) == 3 and got['mlp']['layers'][0][0].shape == (4, 8)   # shared hidden stack kept once
+
+
+def test_unknown_operation_fails_loudly(tmp_path):
+    rng = np.random.default_rng(3)
+    kin = np.arange(1, 11) * 0.03
+    mlp = configs.mlp_engine(rng, 30, hidden=(4,), kin=kin)
+    emu = dl.Emulator.from_mlp(['qpar', 'qper', 'dm', 'df'], mlp, {'pk_dd': slice(0, 30)}, {'pk_dd': (3, 10)}, fixed=dict(k=kin, ells=(0, 2, 4), z=1.))
+    emu.state['engines']['pk_dd']['model_operations'][1]['expression'] = 'jnp.sin(v)'
+    with pytest.raises(ValueError):
+        emu.to_calculator().theory_spec()

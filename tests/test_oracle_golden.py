@@ -9,7 +9,7 @@ import pytest
 from oracle import configs, pipeline
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURES = sorted(glob.glob(os.path.join(HERE, 'golden', '*.npz')))
+FIXTURES = sorted(f for f in glob.glob(os.path.join(HERE, 'golden', '*.npz')) if 'bao_theory' not in f)
 
 
 def load_case(fn):
@@ -38,3 +38,22 @@ def test_oracle_matches_reference_fixture(fn):
         finite = np.isfinite(ref)
         assert np.array_equal(np.isneginf(ref), np.isneginf(got[key])), key
         assert np.allclose(got[key][finite], ref[finite], rtol=1e-11, atol=2e-9), (key, np.max(np.abs(got[key][finite] - ref[finite])))
+
+
+def test_bao_theory_fixture():
+    """Oracle damped-BAO P_ell(k) and P -> xi against the reference classes' outputs (tests/golden/make_golden.py:bao_theory)."""
+    from oracle import core, synthetic
+    data = np.load(os.path.join(HERE, 'golden', 'bao_theory.npz'))
+    X, k, s = data['X'], data['k'], data['s']
+    ells = (0, 2)
+    mu, wmu = core.legendre_weights(ells, 10)
+    for which, kt in [('power', data['k_template_pk']), ('corr', data['k_template_xi'])]:
+        pk_t, pknow_t = synthetic.pk_fid(kt), synthetic.pknow_fid(kt)
+        p2c = core.PowerToCorr(s, ells)
+        for x, ref in zip(X, data[which]):
+            kw = dict(b1=x[2], dbeta=x[3], sigmas=x[4], sigmapar=x[5], sigmaper=x[6])
+            if which == 'power':
+                got = core.bao_damped_power(k, mu, wmu, kt, pk_t, pknow_t, synthetic.F_FID, x[0], x[1], **kw)
+            else:
+                got = p2c(core.bao_damped_power(p2c.kin, mu, wmu, kt, pk_t, pknow_t, synthetic.F_FID, x[0], x[1], **kw))
+            assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref)), which
