@@ -11,7 +11,7 @@ from oracle import configs, pipeline
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURES = sorted(f for f in glob.glob(os.path.join(HERE, 'golden', '*.npz')) if 'cubic' not in f)
+FIXTURES = sorted(f for f in glob.glob(os.path.join(HERE, 'golden', '*.npz')) if 'cubic' not in f and 'bao_theory' not in f)
 
 
 def test_kaiser_tables_match_oracle(gpu_required):
@@ -180,3 +180,23 @@ def test_bao_power_spectrum(gpu_required):
     assert np.max(np.abs(plan.theory(X) - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-10
     assert np.max(np.abs(got['logposterior'] - ref['logposterior']) / np.maximum(1., np.abs(ref['logposterior']))) < 1e-8
     plan.close()
+
+
+def test_bao_kernels_match_reference_classes(gpu_required):
+    """GPU damped-BAO P_ell(k) and FFTLog xi_ell(s) vs the outputs of the reference's own classes (tests/golden/bao_theory.npz)."""
+    import desilike_b200
+    from oracle import synthetic
+    data = np.load(os.path.join(HERE, 'golden', 'bao_theory.npz'))
+    X, k, s, ells = data['X'], data['k'], data['s'], (0, 2)
+    names = ['qpar', 'qper', 'b1', 'dbeta', 'sigmas', 'sigmapar', 'sigmaper']
+    for which, kt in [('power', data['k_template_pk']), ('corr', data['k_template_xi'])]:
+        tpl = dict(kind='bao', k=kt, pk_dd_fid=synthetic.pk_fid(kt), pknow_dd_fid=synthetic.pknow_fid(kt), f_fid=synthetic.F_FID, apmode='qparqper', eta=1. / 3.)
+        theory = dict(ells=ells, nmu=10, template=tpl, mode='', params=names, defaults={})
+        theory.update(dict(kind='bao_pk', k=k) if which == 'power' else dict(kind='bao_xi', s=s))
+        n = 2 * (k.size if which == 'power' else s.size)
+        obs = dict(name='x', theory=theory, terms=[dict(scale=1., factors=[], table=which)], nin=n, wmatrix=None, offset=None, data=np.zeros(n))
+        spec = dict(params=names, priors={}, solved=[], observables=[obs], precision=[np.ones(n)])
+        plan = desilike_b200.Plan(spec)
+        got = plan.theory(X).reshape(data[which].shape)
+        assert np.max(np.abs(got - data[which])) <= 1e-10 * np.max(np.abs(data[which])), which
+        plan.close()
