@@ -6,6 +6,7 @@
 #include <vector>
 #include <atomic>
 #include <mutex>
+#include <algorithm>
 
 #include "../../include/desilike_b200.h"
 
@@ -41,46 +42,62 @@ extern std::atomic<long long> g_launches;
 // tiling constants of the contraction kernel (csrc/contract.cu)
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int KC = 36;        // k-chunk length == shared-memory row stride in doubles; 36 = 4 (mod 8) -> conflict-free 64-bit fragment loads
-constexpr int NCONSUMER_WARPS = 8;
-constexpr int NTHREADS = (NCONSUMER_WARPS + 1) * 32;  // + 1 TMA producer warp
-constexpr int ROW_ALIGN = 128;  // batch rows are padded to a multiple of the largest point tile
+constexpr int ROW_ALIGN = 384;  // batch rows are padded to a multiple of every variant's row unit (64, 48) and tile
 
-struct Variant { int R, MT, NT; };          // accumulator slots, m-tiles and n-tiles (of 8) per warp; warp grid is 4 (m) x 2 (n)
-inline int variant_bm(const Variant& v) { return 4 * v.MT * 8; }
-inline int variant_bn(const Variant& v) { return 2 * v.NT * 8; }
+struct Variant { int R, MT, NT, WM; };      // accumulator slots, m-tiles (of 8 rows) and n-tiles (of 8 columns) per warp; warp grid is WM (m) x 2 (n)
+inline int variant_unit(const Variant& v) { return 8 * v.WM; }          // rows per unit (one m-tile of every warp row)
+inline int variant_bm(const Variant& v) { return 8 * v.WM * v.MT; }
+inline int variant_bn(const Variant& v) { return 16 * v.NT; }
 
-struct Chunk {        // one k-chunk of one term (device table, one per output block)
+struct Chunk {        // one k-chunk of one term (device table, one per output block); read as one int4
   int slot;           // accumulator slot
-  int coef;           // coefficient column, -1 -> 1
-  int fcol;           // first feature column (absolute, in the per-point feature row)
+  int coef;           // coefficient index, -1 -> 1
+  int fcol;           // first feature column: absolute in the per-point feature row (streaming A) or relative to the
+                      // block's generator segment (resident A)
   int kc;             // chunk length (multiple of 4, <= KC)
 };
 
-struct ContractParams {
-  const double* F; int fstride;          // features [Npad, fstride]
-  const double* C; int cstride;          // coefficients [Npad, cstride]
-  const Chunk* chunks; int nchunks;
-  const double* tiles;                   // [ncb][nchunks][BN][KC] pre-tiled term matrices (n-major, zero padded)
-  const double* r0;                      // [ncb * BN] subtracted from (eval) / added to (theory) slot 0
-  const double* gconst; int nconst;      // [nconst][ncb * BN] constant whitened Jacobian rows
-  int nslots;                            // slots actually used (<= R)
-  int npart;                             // partial sums per (point, column block)
-  double* partial; long long npad;       // [(poff + cb * npart + e) * npad + p]
-  long long poff;
-  double* out; long long ostride; int ocol0; int ncols;  // output mode: out[row * ostride + ocol0 + col] for col < ncols, row < out_rows
-  long long out_rows;
-  int act;                               // output mode: activation applied to (slot 0 + r0): 0 none, 1 silu, 2 relu, 3 tanh
-  int mode;                              // 0 eval (Gram partials), 1 output (theory vectors / MLP layer)
-  int nstages;
+constexpr int MAXP = 16;  // max input parameters of one generator
+
+struct GenDev {       // Taylor generator constants for the in-kernel monomial evaluation (resident A)
+  int nparams, maxdeg;
+  int pidx[MAXP];
+  double center[MAXP], pdef[MAXP];
 };
 
-size_t contract_smem_bytes(const Variant& v, int nstages, int nchunks, int npart);
-int launch_contract(const Variant& v, const ContractParams& p, int ntiles, int ncb, cudaStream_t stream);
+struct BlockDev {     // one output block as seen by the contraction kernel (device table)
+  const Chunk* chunks;
+  const double* tiles;                 // [ncb][nchunks][BN][KC] pre-tiled term matrices (n-major, zero padded)
+  const double* epi;                   // [ncb][nconst + 1][BN] epilogue constants per column block: constant whitened Jacobian rows,
+                                       // then r0 (subtracted from slot 0 in eval mode / added in output mode)
+  const unsigned long long* paths;     // [ast] monomial factor lists of the block's Taylor generator (resident A), else NULL
+  long long poff;                      // first Gram-partial row of the block: partial[(poff + e) * npad + point]
+  int nchunks, ncb, nslots, nconst, npart, ncols, ocol0, gen;
+  int fill, fbase, acols;              // resident A: 0 = evaluate Taylor monomials, 1 = copy acols columns of F from column fbase
+};
+
+struct DevCoef { double scale; int nf; int idx[DLB_COEF_MAXF]; int pow[DLB_COEF_MAXF]; };
+
+struct ContractParams {
+  const BlockDev* blocks; int nblocks;
+  const GenDev* gens; int ngen;
+  const DevCoef* coefs; int ncoef;
+  const double* params; int d; long long N;
+  const double* F; int fstride;          // features [npad, fstride] (streaming A)
+  double* partial; long long npad;       // Gram partials, summed over column blocks
+  double* out; long long ostride; long long out_rows;  // output mode: out[row * ostride + ocol0 + col]
+  int act;                               // output mode: activation applied to (slot 0 + r0): 0 none, 1 silu, 2 relu, 3 tanh
+  int mode;                              // 0 eval (Gram partials), 1 output (theory vectors / MLP layer)
+  int nstages, resident, ast, dpad, npart_max;
+  long long U;                           // number of row units (variant_unit rows each) to process
+};
+
+size_t contract_smem_bytes(const Variant& v, int nstages, bool resident, int ast, int dpad, int ncoef, int npart_max, int ngen);
+int launch_contract(const Variant& v, const ContractParams& p, int nsm, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------------------------------
 // feature generators (csrc/features.cu)
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int MAXP = 16;  // max input parameters of one generator
 struct DevGen {
   int kind, nparams, nfeat, fpad, foff;
   int pidx[MAXP];
@@ -89,8 +106,6 @@ struct DevGen {
   const double* ddata; long long nd;
   int aux[8];             // kind-specific layout offsets computed at plan time
 };
-
-struct DevCoef { double scale; int nf; int idx[DLB_COEF_MAXF]; int pow[DLB_COEF_MAXF]; };
 
 int launch_features(const DevGen& g, const double* params, int d, long long N, long long npad, double* F, int fstride, cudaStream_t stream);
 int launch_theory_features(const DevGen& g, const double* params, int d, long long N, long long npad, double* F, int fstride, cudaStream_t stream);  // csrc/theory_kernels.cu

@@ -1,23 +1,37 @@
-// Fused contraction kernel (sm_100a): for a tile of parameter points and a block of data-vector columns
+// Persistent fused contraction kernel (sm_100a).  For every tile of parameter points and every output block (a group of
+// data-vector columns, one per tracer when the precision is block-diagonal)
 //
-//     slot[s][p, :] = sum_{terms t of slot s} coef_t[p] * F[p, fcol_t : fcol_t + K_t] . M_t[K_t, cols]
+//     slot[s][p, :] = sum_{terms t of slot s} coef_t[p] * A[p, fcol_t : fcol_t + K_t] . M_t[K_t, cols]
 //
 // followed, in registers, by the chi2 / normal-equation (Gram) reduction over the columns.  This one kernel replaces,
-// per point, the reference's   emulator tensordot -> tracer bias combine -> window matrix apply -> flatdiff -> d^T P d
-// and the J P d, J P J^T products of the analytic marginalisation
+// per point, the reference's   emulator predict (Taylor monomials + tensordot) -> tracer bias combine -> window matrix apply
+// -> flatdiff -> d^T P d   and the J P d, J P J^T products of the analytic marginalisation
 //   (reference emulators/__init__.py:471-507; full_shape.py:545-550,628-634; window.py:459-473; likelihoods/base.py:13-17,
 //    :165-174, :658-664): all constant matrices (Taylor derivatives / last MLP layer, window W, Cholesky factor L of the
 //    precision) are folded into M_t at plan time, so no theory vector ever touches HBM.
 //
 // Hardware mapping
+//   * one persistent CTA per SM; the batch is split into row units (WM * 8 rows) and every CTA owns a contiguous range of
+//     units (balanced to one unit, so there is no wave-quantisation tail); it walks its range in tiles of up to MT units
+//     and, per tile, over all blocks / column blocks / k-chunks.  One launch covers the whole likelihood.
 //   * FP64 tensor pipe: DMMA.8x8x4 (mma.sync.m8n8k4.f64) -- tcgen05 has no FP64 kind; every FP64 mma shape lowers to
-//     DMMA.8x8x4 on sm_100a (checked with cuobjdump).  8 consumer warps in a 4 (m) x 2 (n) grid, warp tile (MT*8) x (NT*8).
-//   * operands staged in shared memory by the TMA unit: 1-D bulk copies (cp.async.bulk -> UBLKCP) issued by a dedicated
-//     producer warp into an mbarrier ring (full/empty), 2-4 stages; the term matrices are pre-tiled at plan time into
-//     the exact shared-memory image (n-major rows of KC = 36 doubles: 36 = 4 mod 8 makes both 64-bit fragment loads
-//     bank-conflict free), so one bulk copy moves a whole B tile and one per point row moves the A tile.
-//   * per-point coefficient (bias monomial) applied to the A fragment in registers; the Gram epilogue is warp-shuffle
-//     reductions + shared-memory atomics, then one coalesced store of the partial sums.
+//     DMMA.8x8x4 on sm_100a (checked with cuobjdump).  One warp can issue a DMMA every 32 cycles while the pipe retires one
+//     per 16 cycles and scheduler (measured: dlb_measure_fp64_peak(100 + warps)), so 2 warps per scheduler have zero slack:
+//     the kernel runs 3-4 warps per scheduler (12-16 warps, all of them consumers) with a (MT*8) x (NT*8) tile each,
+//     warp grid WM (m) x 2 (n).
+//   * B operand (pre-tiled term matrices, L2 resident) streamed with 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) into an
+//     mbarrier full/empty ring; there is no dedicated producer warp: warp 0 re-arms the stage that was released one chunk
+//     earlier after finishing its own chunk (S - 1 chunks of prefetch).  Rows are KC = 36 doubles (36 = 4 mod 8 makes the
+//     64-bit fragment loads bank-conflict free).  The per-column-block epilogue constants (r0, constant Jacobian rows)
+//     travel through the same ring as one extra chunk.
+//   * A operand, RESIDENT mode (Taylor emulators): the warps evaluate the monomials prod_j (theta_j - c_j)^p_tj of their
+//     tile straight into shared memory (one warp per row, one lane per monomial) -- the feature matrix never exists in
+//     HBM -- and it stays resident for all terms and column blocks.  STREAMING mode (MLP / Kaiser / BAO features computed
+//     by their own kernels): A tiles are TMA-copied per chunk.
+//   * the parameter tile of the NEXT row tile is prefetched with cp.async while the current one computes; bias-monomial
+//     coefficients are evaluated per tile into shared memory and applied to the A fragment in registers.
+//   * the Gram epilogue is warp-shuffle reductions accumulated in a per-warp-column shared-memory copy (no atomics), summed
+//     over column blocks in the kernel and written once per (tile, block).
 #include "common.h"
 
 namespace dlb {
@@ -53,215 +67,399 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template <int R, int MT, int NT>
-__global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const __grid_constant__ ContractParams p) {
-  constexpr int BM = 4 * MT * 8, BN = 2 * NT * 8;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int S = p.nstages;
-  double* stage_base = reinterpret_cast<double*>(smem_raw);
-  constexpr int STAGE_DOUBLES = (BM + BN) * KC;
-  uint64_t* full = reinterpret_cast<uint64_t*>(stage_base + (size_t)S * STAGE_DOUBLES);
-  uint64_t* empty = full + S;
-  Chunk* schunks = reinterpret_cast<Chunk*>(empty + S);
-  double* red = reinterpret_cast<double*>(schunks + ((p.nchunks + 1) & ~1));
+__device__ __forceinline__ double ipow(double x, int n) {
+  double r = 1.;
+  for (int i = 0; i < n; ++i) r *= x;
+  return r;
+}
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cb = blockIdx.y;
-  const long long row0 = (long long)blockIdx.x * BM;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONSUMER_WARPS); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int c = threadIdx.x; c < p.nchunks; c += NTHREADS) schunks[c] = p.chunks[c];
-  if (p.mode == 0)
-    for (int i = threadIdx.x; i < BM * p.npart; i += NTHREADS) red[i] = 0.;
-  __syncthreads();
-
-  if (warp == NCONSUMER_WARPS) {
-    // ===== TMA producer warp =====
-    const double* tiles = p.tiles + (size_t)cb * p.nchunks * (BN * KC);
-    for (int c = 0; c < p.nchunks; ++c) {
-      const int s = c % S;
-      const uint32_t ph = (c / S) & 1;
-      mbar_wait(&empty[s], ph ^ 1);
-      const Chunk ch = schunks[c];
-      double* As = stage_base + (size_t)s * STAGE_DOUBLES;
-      double* Bs = As + BM * KC;
-      if (lane == 0) {
-        mbar_arrive_expect_tx(&full[s], (uint32_t)(BM * ch.kc * 8 + BN * KC * 8));
-        tma_bulk_g2s(Bs, tiles + (size_t)c * (BN * KC), BN * KC * 8, &full[s]);
-      }
-      __syncwarp();
-      const double* Fsrc = p.F + row0 * p.fstride + ch.fcol;
-      for (int r = lane; r < BM; r += 32) tma_bulk_g2s(As + r * KC, Fsrc + (size_t)r * p.fstride, ch.kc * 8, &full[s]);
-    }
-    return;
-  }
-
-  // ===== consumer warps =====
-  const int wm = warp >> 1, wn = warp & 1;
-  const int lr = lane >> 2, lc = lane & 3;
-  double acc[R][MT][NT][2];
-#pragma unroll
-  for (int s = 0; s < R; ++s)
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) acc[s][mt][nt][0] = acc[s][mt][nt][1] = 0.;
-
-  const double* Crow = p.C + (row0 + wm * (MT * 8) + lr) * p.cstride;
-  double beta_next[MT];
-  {
-    const int coef = schunks[0].coef;
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) beta_next[mt] = coef >= 0 ? __ldg(Crow + (size_t)mt * 8 * p.cstride + coef) : 1.;
-  }
-  for (int c = 0; c < p.nchunks; ++c) {
-    const int s = c % S;
-    const uint32_t ph = (c / S) & 1;
-    const Chunk ch = schunks[c];
-    double beta[MT];
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) beta[mt] = beta_next[mt];
-    if (c + 1 < p.nchunks) {  // prefetch the next chunk's coefficient while this chunk computes
-      const int coef = schunks[c + 1].coef;
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) beta_next[mt] = coef >= 0 ? __ldg(Crow + (size_t)mt * 8 * p.cstride + coef) : 1.;
-    }
-    mbar_wait(&full[s], ph);
-    const double* A = stage_base + (size_t)s * STAGE_DOUBLES + (wm * (MT * 8) + lr) * KC + lc;
-    const double* B = stage_base + (size_t)s * STAGE_DOUBLES + BM * KC + (wn * (NT * 8) + lr) * KC + lc;
-    const int nk4 = ch.kc >> 2;
-#pragma unroll
-    for (int slot = 0; slot < R; ++slot) {
-      if (ch.slot == slot) {
+// One k-chunk of DMMAs for MTC active m-tiles: acc[mt][nt] += (beta[mt] * A[mt-rows, k]) . B[k, nt-cols]
+template <int MT, int NT, int MTC>
+__device__ __forceinline__ void mma_chunk(double (&acc)[MT][NT][2], const double* __restrict__ A, int astride, const double* __restrict__ B,
+                                          const double (&beta)[MT], int nk4) {
 #pragma unroll 3
-        for (int k4 = 0; k4 < nk4; ++k4) {
-          double a[MT], b[NT];
+  for (int k4 = 0; k4 < nk4; ++k4) {
+    double a[MTC], b[NT];
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) a[mt] = A[mt * 8 * KC + k4 * 4] * beta[mt];
+    for (int mt = 0; mt < MTC; ++mt) a[mt] = A[mt * astride + k4 * 4] * beta[mt];
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt) b[nt] = B[nt * 8 * KC + k4 * 4];
+    for (int nt = 0; nt < NT; ++nt) b[nt] = B[nt * 8 * KC + k4 * 4];
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt)
+    for (int mt = 0; mt < MTC; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) dmma884(acc[slot][mt][nt][0], acc[slot][mt][nt][1], a[mt], b[nt]);
-        }
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
-  }
-
-  // ===== epilogue =====
-  const int colw = wn * (NT * 8) + 2 * lc;  // + nt * 8 + e
-  const double* r0 = p.r0 + (size_t)cb * BN;
-  if (p.mode == 1) {
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      const long long row = row0 + wm * (MT * 8) + mt * 8 + lr;
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int col = cb * BN + colw + nt * 8 + e;
-          if (row < p.out_rows && col < p.ncols) {
-            double v = acc[0][mt][nt][e] + r0[colw + nt * 8 + e];
-            if (p.act == 1) v = v / (1. + exp(-v));        // silu  (reference emulators/conversion.py:27)
-            else if (p.act == 2) v = fmax(v, 0.);          // relu  (:29)
-            else if (p.act == 3) v = tanh(v);              // tanh  (:31)
-            p.out[row * p.ostride + p.ocol0 + col] = v;
-          }
-        }
-    }
-    return;
-  }
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    const double2 rr = *reinterpret_cast<const double2*>(r0 + colw + nt * 8);
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) { acc[0][mt][nt][0] -= rr.x; acc[0][mt][nt][1] -= rr.y; }
-  }
-  const int Rb = p.nslots;
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt) {
-    double* redrow = red + (wm * (MT * 8) + mt * 8 + lr) * p.npart;
-#pragma unroll
-    for (int a = 0; a < R; ++a) {
-#pragma unroll
-      for (int b = a; b < R; ++b) {
-        if (b < Rb) {
-          double s = 0.;
-#pragma unroll
-          for (int nt = 0; nt < NT; ++nt) s += acc[a][mt][nt][0] * acc[b][mt][nt][0] + acc[a][mt][nt][1] * acc[b][mt][nt][1];
-          s += __shfl_xor_sync(0xffffffffu, s, 1);
-          s += __shfl_xor_sync(0xffffffffu, s, 2);
-          if (lc == 0) atomicAdd(redrow + (a * Rb - (a * (a - 1)) / 2 + (b - a)), s);
-        }
-      }
-    }
-    const int nS = (Rb * (Rb + 1)) / 2;
-    for (int i = 0; i < p.nconst; ++i) {
-      const double* g = p.gconst + ((size_t)i * gridDim.y + cb) * BN + colw;
-      double gv[NT][2];
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const double2 t = __ldg(reinterpret_cast<const double2*>(g + nt * 8));
-        gv[nt][0] = t.x; gv[nt][1] = t.y;
-      }
-#pragma unroll
-      for (int a = 0; a < R; ++a) {
-        if (a < Rb) {
-          double s = 0.;
-#pragma unroll
-          for (int nt = 0; nt < NT; ++nt) s += acc[a][mt][nt][0] * gv[nt][0] + acc[a][mt][nt][1] * gv[nt][1];
-          s += __shfl_xor_sync(0xffffffffu, s, 1);
-          s += __shfl_xor_sync(0xffffffffu, s, 2);
-          if (lc == 0) atomicAdd(redrow + nS + i * Rb + a, s);
-        }
-      }
-    }
-  }
-  asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMER_WARPS * 32) : "memory");
-  double* out = p.partial + (p.poff + (long long)cb * p.npart) * p.npad + row0;
-  for (int i = threadIdx.x; i < BM * p.npart; i += NCONSUMER_WARPS * 32) {
-    const int e = i / BM, r = i - e * BM;
-    out[(long long)e * p.npad + r] = red[r * p.npart + e];
+      for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
   }
 }
 
-template <int R, int MT, int NT>
-int launch_variant(const ContractParams& p, int ntiles, int ncb, size_t smem, cudaStream_t stream) {
+template <int MT, int NT>
+__device__ __forceinline__ void mma_chunk_dispatch(double (&acc)[MT][NT][2], const double* A, int astride, const double* B, const double (&beta)[MT],
+                                                   int nk4, int mtc) {
+  if (mtc == MT) { mma_chunk<MT, NT, MT>(acc, A, astride, B, beta, nk4); return; }
+  if constexpr (MT > 1) { if (mtc == 1) { mma_chunk<MT, NT, 1>(acc, A, astride, B, beta, nk4); return; } }
+  if constexpr (MT > 2) { if (mtc == 2) { mma_chunk<MT, NT, 2>(acc, A, astride, B, beta, nk4); return; } }
+  if constexpr (MT > 3) { if (mtc == 3) { mma_chunk<MT, NT, 3>(acc, A, astride, B, beta, nk4); return; } }
+}
+
+// Position in the CTA's chunk sequence (tile, block, column block, chunk); chunk == nchunks is the epilogue-constants chunk.
+struct Cursor {
+  long long u;
+  int b, cb, c, nchunks, ncb;
+  bool done;
+};
+
+template <int R, int MT, int NT, int WM, bool RESIDENT>
+__global__ void __launch_bounds__(WM * 64, 1) contract_kernel(const __grid_constant__ ContractParams p) {
+  constexpr int NW = 2 * WM, NTH = NW * 32, UNIT = WM * 8, BM = UNIT * MT, BN = 16 * NT;
+  constexpr int STAGE_DOUBLES = BN * KC + (RESIDENT ? 0 : BM * KC);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int S = p.nstages;
+  double* stage_base = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage_base + (size_t)S * STAGE_DOUBLES);
+  uint64_t* empty = full + S;
+  uint64_t* abar = empty + S;                                         // resident A tile copied from the feature matrix
+  double* A_s = reinterpret_cast<double*>(abar + 2);                  // [BM][ast]           (RESIDENT)
+  double* xs0 = A_s + (RESIDENT ? (size_t)BM * p.ast : 0);            // [2][BM][dpad]       parameter tiles (double buffered)
+  double* cs = xs0 + (size_t)2 * BM * p.dpad;                         // [ncoef][BM]         bias monomials
+  double* red = cs + (size_t)(p.ncoef > 0 ? p.ncoef : 1) * BM;        // [2][BM][npart_max]  Gram partials (per warp column)
+  GenDev* gens_s = reinterpret_cast<GenDev*>(red + (size_t)2 * BM * p.npart_max);   // [ngen]   (RESIDENT)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long U = p.U;
+  const long long u0 = U * blockIdx.x / gridDim.x, u1 = U * (blockIdx.x + 1) / gridDim.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+    mbar_init(abar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if constexpr (RESIDENT) {
+    for (int i = tid; i < p.ngen * (int)(sizeof(GenDev) / 4); i += NTH) reinterpret_cast<int*>(gens_s)[i] = reinterpret_cast<const int*>(p.gens)[i];
+  }
+  for (int i = tid; i < 2 * BM; i += NTH) xs0[(size_t)i * p.dpad + p.d] = 1.;   // constant-one column (absent monomial factors)
+  // parameter tile of the first row tile
+  {
+    const int h = UNIT * (int)min((long long)MT, u1 - u0);
+    for (int i = tid; i < h * p.d; i += NTH) {
+      const int r = i / p.d, j = i - r * p.d;
+      cp_async8(xs0 + (size_t)r * p.dpad + j, p.params + min(u0 * UNIT + r, p.N - 1) * p.d + j);
+    }
+  }
+  __syncthreads();
+
+  // ---- TMA refill state (used by warp 0 only; uniform across its lanes) ----
+  Cursor cur;
+  cur.u = u0; cur.b = 0; cur.cb = 0; cur.c = 0; cur.done = false;
+  cur.nchunks = p.blocks[0].nchunks; cur.ncb = p.blocks[0].ncb;
+  int rs = 0;
+  uint32_t rph = 0;
+  auto refill = [&]() {
+    if (cur.done) return;
+    mbar_wait(&empty[rs], rph ^ 1);
+    const BlockDev* blk = p.blocks + cur.b;
+    double* dst = stage_base + (size_t)rs * STAGE_DOUBLES;
+    if (cur.c == cur.nchunks) {   // epilogue constants of this column block: [nconst + 1][BN]
+      const int nrow = blk->nconst + 1;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full[rs], (uint32_t)(nrow * BN * 8));
+        tma_bulk_g2s(dst, blk->epi + (size_t)cur.cb * nrow * BN, nrow * BN * 8, &full[rs]);
+      }
+    } else {
+      const double* src = blk->tiles + ((size_t)cur.cb * cur.nchunks + cur.c) * (BN * KC);
+      if constexpr (RESIDENT) {
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full[rs], (uint32_t)(BN * KC * 8));
+          tma_bulk_g2s(dst, src, BN * KC * 8, &full[rs]);
+        }
+      } else {
+        const int4 ch = __ldg(reinterpret_cast<const int4*>(blk->chunks + cur.c));   // slot, coef, fcol, kc
+        const int h = UNIT * (int)min((long long)MT, u1 - cur.u);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full[rs], (uint32_t)(h * ch.w * 8 + BN * KC * 8));
+          tma_bulk_g2s(dst, src, BN * KC * 8, &full[rs]);
+        }
+        __syncwarp();
+        const double* Fsrc = p.F + cur.u * UNIT * p.fstride + ch.z;
+        for (int r = lane; r < h; r += 32) tma_bulk_g2s(dst + BN * KC + r * KC, Fsrc + (size_t)r * p.fstride, ch.w * 8, &full[rs]);
+      }
+    }
+    // advance
+    if (++cur.c > cur.nchunks) {
+      cur.c = 0;
+      if (++cur.cb == cur.ncb) {
+        cur.cb = 0;
+        if (++cur.b == p.nblocks) {
+          cur.b = 0;
+          cur.u += MT;
+          if (cur.u >= u1) cur.done = true;
+        }
+        cur.nchunks = p.blocks[cur.b].nchunks; cur.ncb = p.blocks[cur.b].ncb;
+      }
+    }
+    if (++rs == S) { rs = 0; rph ^= 1; }
+  };
+  if (warp == 0)
+    for (int i = 0; i < S - 1; ++i) refill();
+
+  const int wm = warp >> 1, wn = warp & 1;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int npm = p.npart_max;
+  int s = 0, xbuf = 0;
+  uint32_t ph = 0, aph = 0;
+  for (long long u = u0; u < u1; u += MT) {
+    const int mtc = (int)min((long long)MT, u1 - u);
+    const int h = UNIT * mtc;
+    const long long row0 = u * UNIT;
+    double* xs = xs0 + (size_t)xbuf * BM * p.dpad;
+    cp_async_wait_all();
+    __syncthreads();   // this tile's parameters have landed; previous tile completely finished (red flushed, cs / A_s free)
+    if (u + MT < u1) {  // prefetch the next tile's parameters (rows beyond N replicate the last point; their results are never read)
+      const int hn = UNIT * (int)min((long long)MT, u1 - u - MT);
+      double* xn = xs0 + (size_t)(xbuf ^ 1) * BM * p.dpad;
+      for (int i = tid; i < hn * p.d; i += NTH) {
+        const int r = i / p.d, j = i - r * p.d;
+        cp_async8(xn + (size_t)r * p.dpad + j, p.params + min(row0 + BM + r, p.N - 1) * p.d + j);
+      }
+    }
+    xbuf ^= 1;
+    // ---- bias monomials c = scale * prod_f theta[idx_f]^pow_f (tracer combine, reference full_shape.py:545-550) ----
+    for (int i = tid; i < p.ncoef * h; i += NTH) {
+      const int j = i / h, r = i - j * h;
+      const DevCoef* cf = p.coefs + j;
+      double c = cf->scale;
+      const int nf = cf->nf;
+      for (int f = 0; f < nf; ++f) {
+        const double x = xs[r * p.dpad + cf->idx[f]];
+        const int e = cf->pow[f];
+        c *= e >= 0 ? ipow(x, e) : 1. / ipow(x, -e);
+      }
+      cs[j * BM + r] = c;
+    }
+    for (int b = 0; b < p.nblocks; ++b) {
+      const BlockDev* blk = p.blocks + b;
+      const int nchunks = blk->nchunks, ncb = blk->ncb, npart = blk->npart, Rb = blk->nslots, nconst = blk->nconst;
+      const Chunk* chunks = blk->chunks;
+      if (b > 0) __syncthreads();   // flush of the previous block done; every warp finished reading A_s
+      if (RESIDENT && blk->fill == 1) {
+        // ---- resident A tile = this block's generator segment of the feature matrix (MLP activations, ...): one TMA row copy
+        //      per point, once per (tile, block) ----
+        const int acols = blk->acols;
+        if (tid == 0) mbar_arrive_expect_tx(abar, (uint32_t)(h * acols * 8));
+        __syncthreads();
+        const double* Fsrc = p.F + row0 * p.fstride + blk->fbase;
+        for (int r = tid; r < h; r += NTH) tma_bulk_g2s(A_s + (size_t)r * p.ast, Fsrc + (size_t)r * p.fstride, acols * 8, abar);
+        mbar_wait(abar, aph);
+        aph ^= 1;
+      } else if constexpr (RESIDENT) {
+        // ---- Taylor monomials of this block's emulator, straight into shared memory ----
+        //   m_t = prod_j (theta_j - center_j)^powers[t, j]  (layout: reference emulators/__init__.py:471-507).  paths[col] lists the
+        //   factors of column col as bytes (variable index + 1, 0 terminates); top byte 0xFF marks a structural zero column.
+        //   Every factor is read as xs[row][col_k] - c_k; absent factors point at the constant-one column with c_k = 0.
+        const GenDev* g = gens_s + blk->gen;
+        const int maxdeg = g->maxdeg;
+        for (int j0 = 0; j0 < p.ast; j0 += 32) {
+          const int j = j0 + lane;
+          const unsigned long long path = j < p.ast ? __ldg(blk->paths + j) : 0xFF00000000000000ull;
+          int col[7];
+          double ck[7];
+#pragma unroll
+          for (int k = 0; k < 7; ++k) {
+            const int v = (int)((path >> (8 * k)) & 0xFFull);
+            col[k] = p.d; ck[k] = 0.;
+            if (k < maxdeg && v) {
+              const int pc = g->pidx[v - 1];
+              if (pc >= 0) { col[k] = pc; ck[k] = g->center[v - 1]; }
+              else ck[k] = 1. - (g->pdef[v - 1] - g->center[v - 1]);
+            }
+          }
+          const bool zero = (path >> 56) != 0ull;
+          if (j < p.ast) {
+#pragma unroll 4
+            for (int r = warp; r < h; r += NW) {
+              const double* xr = xs + (size_t)r * p.dpad;
+              double m = xr[col[0]] - ck[0];
+#pragma unroll
+              for (int k = 1; k < 7; ++k)
+                if (k < maxdeg) m *= xr[col[k]] - ck[k];
+              A_s[(size_t)r * p.ast + j] = zero ? 0. : m;
+            }
+          }
+        }
+      }
+      if (p.mode == 0) {   // zero this warp's rows of its Gram copy
+        for (int mt = 0; mt < mtc; ++mt)
+          for (int i = lane; i < 8 * npart; i += 32) red[((size_t)wn * BM + mt * UNIT + wm * 8 + i / npart) * npm + (i % npart)] = 0.;
+      }
+      __syncthreads();
+
+      int4 ch_next = __ldg(reinterpret_cast<const int4*>(chunks));   // slot, coef, fcol, kc (prefetched one chunk ahead)
+      for (int cb = 0; cb < ncb; ++cb) {
+        double acc[R][MT][NT][2];
+#pragma unroll
+        for (int sl = 0; sl < R; ++sl)
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) acc[sl][mt][nt][0] = acc[sl][mt][nt][1] = 0.;
+
+        for (int c = 0; c < nchunks; ++c) {
+          const int4 ch = ch_next;
+          ch_next = __ldg(reinterpret_cast<const int4*>(chunks + (c + 1 < nchunks ? c + 1 : 0)));
+          double beta[MT];
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) beta[mt] = ch.y >= 0 ? cs[ch.y * BM + mt * UNIT + wm * 8 + lr] : 1.;
+          mbar_wait(&full[s], ph);
+          const double* Bp = stage_base + (size_t)s * STAGE_DOUBLES + (wn * (NT * 8) + lr) * KC + lc;
+          const double* Ap;
+          int astride;
+          if constexpr (RESIDENT) { Ap = A_s + (wm * 8 + lr) * p.ast + ch.z + lc; astride = UNIT * p.ast; }
+          else { Ap = stage_base + (size_t)s * STAGE_DOUBLES + BN * KC + (wm * 8 + lr) * KC + lc; astride = UNIT * KC; }
+          const int nk4 = ch.w >> 2;
+#pragma unroll
+          for (int sl = 0; sl < R; ++sl)
+            if (ch.x == sl) mma_chunk_dispatch<MT, NT>(acc[sl], Ap, astride, Bp, beta, nk4, mtc);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);
+          if (warp == 0) refill();
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+
+        // ===== epilogue: constants of this column block arrive as one more chunk: rows [0, nconst) = constant whitened
+        //       Jacobian rows, row nconst = r0 =====
+        mbar_wait(&full[s], ph);
+        const int colw = wn * (NT * 8) + 2 * lc;  // + nt * 8 + e
+        const double* epi = stage_base + (size_t)s * STAGE_DOUBLES;
+        const double* r0 = epi + (size_t)nconst * BN;
+        if (p.mode == 1) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            if (mt < mtc) {
+              const long long row = row0 + mt * UNIT + wm * 8 + lr;
+#pragma unroll
+              for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int col = cb * BN + colw + nt * 8 + e;
+                  if (row < p.out_rows && col < blk->ncols) {
+                    double v = acc[0][mt][nt][e] + r0[colw + nt * 8 + e];
+                    if (p.act == 1) v = v / (1. + exp(-v));        // silu  (reference emulators/conversion.py:27)
+                    else if (p.act == 2) v = fmax(v, 0.);          // relu  (:29)
+                    else if (p.act == 3) v = tanh(v);              // tanh  (:31)
+                    p.out[row * p.ostride + blk->ocol0 + col] = v;
+                  }
+                }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const double2 rr = *reinterpret_cast<const double2*>(r0 + colw + nt * 8);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) { acc[0][mt][nt][0] -= rr.x; acc[0][mt][nt][1] -= rr.y; }
+          }
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            if (mt < mtc) {
+              double* redrow = red + ((size_t)wn * BM + mt * UNIT + wm * 8 + lr) * npm;
+#pragma unroll
+              for (int a = 0; a < R; ++a) {
+#pragma unroll
+                for (int bb = a; bb < R; ++bb) {
+                  if (bb < Rb) {
+                    double sum = 0.;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) sum += acc[a][mt][nt][0] * acc[bb][mt][nt][0] + acc[a][mt][nt][1] * acc[bb][mt][nt][1];
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                    if (lc == 0) redrow[a * Rb - (a * (a - 1)) / 2 + (bb - a)] += sum;
+                  }
+                }
+              }
+              const int nS = (Rb * (Rb + 1)) / 2;
+              for (int i = 0; i < nconst; ++i) {
+                const double* g = epi + (size_t)i * BN + colw;
+                double gv[NT][2];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                  const double2 t = *reinterpret_cast<const double2*>(g + nt * 8);
+                  gv[nt][0] = t.x; gv[nt][1] = t.y;
+                }
+#pragma unroll
+                for (int a = 0; a < R; ++a) {
+                  if (a < Rb) {
+                    double sum = 0.;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) sum += acc[a][mt][nt][0] * gv[nt][0] + acc[a][mt][nt][1] * gv[nt][1];
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                    if (lc == 0) redrow[nS + i * Rb + a] += sum;
+                  }
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (warp == 0) refill();
+        if (++s == S) { s = 0; ph ^= 1; }
+      }  // cb
+
+      if (p.mode == 0) {
+        __syncthreads();   // every warp's contributions are in its Gram copy
+        double* out = p.partial + blk->poff * p.npad + row0;
+        for (int i = tid; i < h * npart; i += NTH) {
+          const int e = i / h, r = i - e * h;
+          out[(long long)e * p.npad + r] = red[(size_t)r * npm + e] + red[((size_t)BM + r) * npm + e];
+        }
+      }
+    }  // blocks
+  }    // tiles
+}
+
+template <int R, int MT, int NT, int WM, bool RESIDENT>
+int launch_variant(const ContractParams& p, int grid, size_t smem, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    DLB_CUDA(cudaFuncSetAttribute(contract_kernel<R, MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DLB_CUDA(cudaFuncSetAttribute(contract_kernel<R, MT, NT, WM, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  dim3 grid(ntiles, ncb);
-  contract_kernel<R, MT, NT><<<grid, NTHREADS, smem, stream>>>(p);
+  contract_kernel<R, MT, NT, WM, RESIDENT><<<grid, WM * 64, smem, stream>>>(p);
   g_launches++;
   DLB_CUDA(cudaGetLastError());
   return DLB_OK;
 }
 
-}  // namespace
-
-size_t contract_smem_bytes(const Variant& v, int nstages, int nchunks, int npart) {
-  const size_t stage = (size_t)(variant_bm(v) + variant_bn(v)) * KC * 8;
-  return nstages * stage + 2 * nstages * 8 + (size_t)((nchunks + 1) & ~1) * sizeof(Chunk) + (size_t)variant_bm(v) * npart * 8;
+template <int R, int MT, int NT, int WM>
+int launch_mode(const ContractParams& p, int grid, size_t smem, cudaStream_t stream) {
+  return p.resident ? launch_variant<R, MT, NT, WM, true>(p, grid, smem, stream) : launch_variant<R, MT, NT, WM, false>(p, grid, smem, stream);
 }
 
-int launch_contract(const Variant& v, const ContractParams& p, int ntiles, int ncb, cudaStream_t stream) {
-  const size_t smem = contract_smem_bytes(v, p.nstages, p.nchunks, p.mode == 0 ? p.npart : 0);
-  if (v.R == 1 && v.MT == 4 && v.NT == 7) return launch_variant<1, 4, 7>(p, ntiles, ncb, smem, stream);
-  if (v.R == 1 && v.MT == 2 && v.NT == 7) return launch_variant<1, 2, 7>(p, ntiles, ncb, smem, stream);
-  if (v.R == 4 && v.MT == 2 && v.NT == 4) return launch_variant<4, 2, 4>(p, ntiles, ncb, smem, stream);
-  if (v.R == 8 && v.MT == 1 && v.NT == 4) return launch_variant<8, 1, 4>(p, ntiles, ncb, smem, stream);
+}  // namespace
+
+size_t contract_smem_bytes(const Variant& v, int nstages, bool resident, int ast, int dpad, int ncoef, int npart_max, int ngen) {
+  const int BM = variant_bm(v), BN = variant_bn(v);
+  const size_t stage = (size_t)(BN * KC + (resident ? 0 : BM * KC)) * 8;
+  size_t bytes = nstages * stage + (size_t)(2 * nstages + 2) * 8;
+  if (resident) bytes += (size_t)BM * ast * 8 + (size_t)ngen * sizeof(GenDev);
+  bytes += (size_t)2 * BM * dpad * 8 + (size_t)std::max(ncoef, 1) * BM * 8 + (size_t)2 * BM * std::max(npart_max, 1) * 8;
+  return bytes;
+}
+
+int launch_contract(const Variant& v, const ContractParams& p, int nsm, cudaStream_t stream) {
+  const size_t smem = contract_smem_bytes(v, p.nstages, p.resident != 0, p.ast, p.dpad, p.ncoef, p.npart_max, p.ngen);
+  if (smem > 227 * 1024) { set_error("contraction kernel: shared-memory budget exceeded"); return DLB_ERR_UNSUPPORTED; }
+  const int grid = (int)std::min<long long>(nsm, std::max<long long>(p.U, 1));
+  if (v.R == 1 && v.MT == 2 && v.NT == 7 && v.WM == 8) return launch_mode<1, 2, 7, 8>(p, grid, smem, stream);
+  if (v.R == 4 && v.MT == 2 && v.NT == 4 && v.WM == 6) return launch_mode<4, 2, 4, 6>(p, grid, smem, stream);
+  if (v.R == 8 && v.MT == 1 && v.NT == 4 && v.WM == 6) return launch_mode<8, 1, 4, 6>(p, grid, smem, stream);
   set_error("no contraction kernel variant for requested tile shape");
   return DLB_ERR_UNSUPPORTED;
 }

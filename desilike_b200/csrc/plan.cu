@@ -15,20 +15,32 @@ void set_error(const std::string& msg) { g_error = msg; }
 
 struct Block {
   Variant var;
-  int ncols = 0, nslots = 1, nconst = 0, ncb = 0, nchunks = 0, npart = 0, nstages = 2, coloff = 0;
+  int ncols = 0, nslots = 1, nconst = 0, ncb = 0, nchunks = 0, npart = 0, coloff = 0, gen = -1, maxcol = 0;
+  int fill = 0, fbase = 0;   // resident A: 0 = Taylor monomials evaluated in the kernel, 1 = copied from the feature matrix at column fbase
   long long poff = 0;
   Chunk* d_chunks = nullptr;
-  double *d_tiles_white = nullptr, *d_tiles_plain = nullptr, *d_r0_white = nullptr, *d_t0_plain = nullptr, *d_gconst = nullptr;
+  double *d_tiles_white = nullptr, *d_tiles_plain = nullptr, *d_epi_white = nullptr, *d_epi_plain = nullptr;
   EntryMap* d_map = nullptr;
 };
 
-struct MlpLayers { int act = 0; std::vector<Block> layers; };
+// launch configuration of one persistent contraction launch (a list of blocks sharing one kernel variant)
+struct Launch {
+  Variant var;
+  int nblocks = 0, nstages = 2, resident = 0, ast = 0, npart_max = 1;
+  BlockDev *d_white = nullptr, *d_plain = nullptr;
+};
+
+struct MlpLayers { int act = 0; std::vector<Block> layers; std::vector<Launch> launches; };
 
 }  // namespace dlb
 
 struct dlb_plan {
   int device = 0;
-  int d = 0, ngen = 0, ncoef = 0, cstride = 1, fstride = 4, ns = 0, nmarg = 0, ntheory = 0;
+  int d = 0, ngen = 0, ncoef = 0, fstride = 4, ns = 0, nmarg = 0, ntheory = 0, nsm = 1, dpad = 1;
+  bool resident = false;               // Taylor monomials evaluated inside the contraction kernel (no feature matrix in HBM)
+  dlb::Launch launch;                  // the likelihood blocks
+  dlb::GenDev* d_gens = nullptr;
+  std::vector<unsigned long long*> d_paths;   // per generator (resident mode)
   std::vector<dlb::DevGen> gens;
   std::vector<dlb::Block> blocks;
   std::vector<dlb::MlpLayers> mlps;   // one per generator (empty unless kind == MLP)
@@ -42,7 +54,7 @@ struct dlb_plan {
   std::vector<void*> owned;
   // workspace
   long long cap = 0;
-  double *w_F = nullptr, *w_C = nullptr, *w_partial = nullptr, *w_params = nullptr, *w_out = nullptr, *w_theory = nullptr;
+  double *w_F = nullptr, *w_partial = nullptr, *w_params = nullptr, *w_out = nullptr, *w_theory = nullptr;
   int* w_status = nullptr;
   long long theory_cap = 0;
   std::mutex mutex;
@@ -72,23 +84,41 @@ static bool is_device_ptr(const void* ptr) {
 }
 
 static Variant choose_variant(int nslots) {
-  if (nslots <= 1) return Variant{1, 4, 7};
-  if (nslots <= 4) return Variant{4, 2, 4};
-  return Variant{8, 1, 4};
+  if (nslots <= 1) return Variant{1, 2, 7, 8};   // 16 warps, 128 x 112 tile
+  if (nslots <= 4) return Variant{4, 2, 4, 6};   // 12 warps,  96 x  64 tile
+  return Variant{8, 1, 4, 6};                    // 12 warps,  48 x  64 tile
 }
 
-struct TermSpec { int slot, coef, fcol, K; const double* white; const double* plain; };  // matrices [K, ncols] row-major
+static int round_ast(int n) {   // row stride of the resident A tile: = 4 (mod 8) keeps the 64-bit fragment loads bank-conflict free
+  int a = std::max(n, 4);
+  while ((a & 7) != 4) ++a;
+  return a;
+}
+
+// Extent (in feature columns) covered by the k-chunks of a term of length K (mirrors the chunking in build_block_core).
+static int chunk_extent(int K) {
+  const int Kpad = (K + 3) & ~3;
+  const int nch = (Kpad + KC - 1) / KC;
+  int kc = (Kpad + nch - 1) / nch;
+  kc = (kc + 3) & ~3;
+  return Kpad;   // chunks are [k0, min(k0 + kc, Kpad)): they never reach beyond Kpad
+  (void)kc;
+}
+
+// fcol: absolute first feature column of the term in the per-point feature row; frel: the same relative to its generator's segment
+struct TermSpec { int slot, coef, fcol, frel, K; const double* white; const double* plain; };  // matrices [K, ncols] row-major
 
 // Chunk the terms, pre-tile their matrices into the contraction kernel's shared-memory image and upload everything.
-static int build_block_core(dlb_plan* plan, int ncols, int nslots, const std::vector<TermSpec>& terms, const double* r0_white,
-                            const double* t0_plain, int nconst, const double* gconst_white, Block& blk) {
+static int build_block_core(dlb_plan* plan, const Variant& var, bool resident, int ncols, int nslots, const std::vector<TermSpec>& terms,
+                            const double* r0_white, const double* t0_plain, int nconst, const double* gconst_white, Block& blk) {
   blk.ncols = ncols; blk.nslots = nslots; blk.nconst = nconst;
-  blk.var = choose_variant(nslots);
+  blk.var = var;
   const int BN = variant_bn(blk.var);
   blk.ncb = (ncols + BN - 1) / BN;
   std::vector<Chunk> chunks;
   struct Src { int term; int k0; };
   std::vector<Src> srcs;
+  blk.maxcol = 0;
   for (size_t t = 0; t < terms.size(); ++t) {
     const TermSpec& td = terms[t];
     const int Kpad = (td.K + 3) & ~3;
@@ -97,17 +127,14 @@ static int build_block_core(dlb_plan* plan, int ncols, int nslots, const std::ve
     kc = (kc + 3) & ~3;
     for (int k0 = 0; k0 < Kpad; k0 += kc) {
       Chunk ch;
-      ch.slot = td.slot; ch.coef = td.coef; ch.fcol = td.fcol + k0; ch.kc = std::min(kc, Kpad - k0);
+      ch.slot = td.slot; ch.coef = td.coef; ch.fcol = (resident ? td.frel : td.fcol) + k0; ch.kc = std::min(kc, Kpad - k0);
       chunks.push_back(ch);
       srcs.push_back(Src{(int)t, k0});
+      blk.maxcol = std::max(blk.maxcol, td.frel + k0 + ch.kc);
     }
   }
   blk.nchunks = (int)chunks.size();
   blk.npart = nslots * (nslots + 1) / 2 + nslots * nconst;
-  blk.nstages = 0;
-  for (int s = 4; s >= 2; --s)
-    if (contract_smem_bytes(blk.var, s, blk.nchunks, blk.npart) <= 227 * 1024) { blk.nstages = s; break; }
-  DLB_REQUIRE(blk.nstages >= 2, "block needs too much shared memory (too many terms or constant rows)");
   DLB_TRY(upload(plan, chunks.data(), chunks.size(), &blk.d_chunks));
   // pre-tile: [ncb][nchunks][BN][KC], n-major rows, zero padded
   const size_t tile = (size_t)BN * KC;
@@ -134,35 +161,33 @@ static int build_block_core(dlb_plan* plan, int ncols, int nslots, const std::ve
       }
     DLB_TRY(upload(plan, tiles.data(), tiles.size(), pass == 0 ? &blk.d_tiles_white : &blk.d_tiles_plain));
   }
-  std::vector<double> pad((size_t)blk.ncb * BN, 0.);
-  if (r0_white) {
-    std::copy(r0_white, r0_white + ncols, pad.begin());
-    DLB_TRY(upload(plan, pad.data(), pad.size(), &blk.d_r0_white));
+  // epilogue constants per column block: [ncb][nconst + 1][BN] = constant whitened Jacobian rows, then r0 / t0 (zero padded)
+  DLB_REQUIRE(nconst + 1 <= KC, "too many constant solved templates in one block (max 35)");
+  for (int pass = 0; pass < 2; ++pass) {
+    const double* vec = pass == 0 ? r0_white : t0_plain;
+    if (!vec) continue;
+    std::vector<double> epi((size_t)blk.ncb * (nconst + 1) * BN, 0.);
+    for (int cb = 0; cb < blk.ncb; ++cb)
+      for (int n = 0; n < BN; ++n) {
+        const int col = cb * BN + n;
+        if (col >= ncols) break;
+        for (int i = 0; i < nconst; ++i) epi[((size_t)cb * (nconst + 1) + i) * BN + n] = gconst_white[(size_t)i * ncols + col];
+        epi[((size_t)cb * (nconst + 1) + nconst) * BN + n] = vec[col];
+      }
+    DLB_TRY(upload(plan, epi.data(), epi.size(), pass == 0 ? &blk.d_epi_white : &blk.d_epi_plain));
   }
-  if (t0_plain) {
-    std::copy(t0_plain, t0_plain + ncols, pad.begin());
-    DLB_TRY(upload(plan, pad.data(), pad.size(), &blk.d_t0_plain));
-  }
-  std::vector<double> gpad((size_t)std::max(nconst, 1) * blk.ncb * BN, 0.);
-  for (int i = 0; i < nconst; ++i) std::copy(gconst_white + (size_t)i * ncols, gconst_white + (size_t)(i + 1) * ncols, gpad.begin() + (size_t)i * blk.ncb * BN);
-  DLB_TRY(upload(plan, gpad.data(), gpad.size(), &blk.d_gconst));
   return DLB_OK;
 }
 
-static int build_block(dlb_plan* plan, const dlb_plan_desc* desc, const dlb_block_desc& bd, Block& blk) {
-  DLB_REQUIRE(bd.ncols > 0 && bd.nslots >= 1 && bd.nslots <= 8, "block: ncols > 0 and 1 <= nslots <= 8 required");
-  DLB_REQUIRE(bd.nterms > 0 && bd.terms && bd.matrices_white && bd.r0_white, "block: terms / matrices_white / r0_white required");
+static int build_block(dlb_plan* plan, const dlb_plan_desc* desc, const dlb_block_desc& bd, const Variant& var, Block& blk) {
   std::vector<TermSpec> terms;
+  blk.gen = bd.terms[0].gen;
   for (int t = 0; t < bd.nterms; ++t) {
     const dlb_term_desc& td = bd.terms[t];
-    DLB_REQUIRE(td.slot >= 0 && td.slot < bd.nslots, "term slot out of range");
-    DLB_REQUIRE(td.coef >= -1 && td.coef < desc->ncoef, "term coef out of range");
-    DLB_REQUIRE(td.gen >= 0 && td.gen < desc->ngen, "term generator out of range");
-    DLB_REQUIRE(td.K > 0 && td.foff >= 0 && (td.foff % 2) == 0 && td.foff + td.K <= plan->gens[td.gen].nfeat, "term feature range invalid (foff must be even)");
-    terms.push_back(TermSpec{td.slot, td.coef, plan->gens[td.gen].foff + td.foff, td.K, bd.matrices_white + td.moff,
+    terms.push_back(TermSpec{td.slot, td.coef, plan->gens[td.gen].foff + td.foff, td.foff, td.K, bd.matrices_white + td.moff,
                              bd.matrices_plain ? bd.matrices_plain + td.moff : nullptr});
   }
-  DLB_TRY(build_block_core(plan, bd.ncols, bd.nslots, terms, bd.r0_white, bd.t0_plain, bd.nconst, bd.gconst_white, blk));
+  DLB_TRY(build_block_core(plan, var, plan->resident, bd.ncols, bd.nslots, terms, bd.r0_white, bd.t0_plain, bd.nconst, bd.gconst_white, blk));
   // entry map of the Gram partials (order fixed by contract_kernel's epilogue)
   std::vector<EntryMap> map(blk.npart);
   const int R = bd.nslots;
@@ -181,6 +206,34 @@ static int build_block(dlb_plan* plan, const dlb_plan_desc* desc, const dlb_bloc
   for (const EntryMap& m : map)
     DLB_REQUIRE(m.kind == 0 || (m.i >= 0 && m.i < desc->ns && (m.kind == 1 || (m.j >= 0 && m.j < desc->ns))), "solved-parameter index out of range");
   DLB_TRY(upload(plan, map.data(), map.size(), &blk.d_map));
+  return DLB_OK;
+}
+
+// Device block tables + launch configuration (stage count from the shared-memory budget) of one persistent launch.
+static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool resident, int ast, int ncoef, Launch& L) {
+  L.var = blocks[0]->var; L.nblocks = (int)blocks.size(); L.resident = resident ? 1 : 0; L.ast = resident ? ast : 0;
+  L.npart_max = 1;
+  for (const Block* b : blocks) L.npart_max = std::max(L.npart_max, b->npart);
+  L.nstages = 0;
+  for (int s = 4; s >= 2; --s)
+    if (contract_smem_bytes(L.var, s, resident, L.ast, plan->dpad, ncoef, L.npart_max, plan->ngen) <= 227 * 1024) { L.nstages = s; break; }
+  DLB_REQUIRE(L.nstages >= 2, "contraction launch needs too much shared memory (too many parameters, coefficients or solved templates)");
+  for (int pass = 0; pass < 2; ++pass) {
+    std::vector<BlockDev> tab;
+    bool ok = true;
+    for (const Block* b : blocks) {
+      BlockDev bd;
+      std::memset(&bd, 0, sizeof(bd));
+      bd.chunks = b->d_chunks; bd.tiles = pass == 0 ? b->d_tiles_white : b->d_tiles_plain; bd.epi = pass == 0 ? b->d_epi_white : b->d_epi_plain;
+      if (!bd.tiles || !bd.epi) ok = false;
+      bd.paths = (resident && b->gen >= 0) ? plan->d_paths[b->gen] : nullptr; bd.poff = b->poff;
+      bd.nchunks = b->nchunks; bd.ncb = b->ncb; bd.nslots = b->nslots; bd.nconst = b->nconst; bd.npart = b->npart; bd.ncols = b->ncols;
+      bd.ocol0 = b->coloff; bd.gen = b->gen; bd.fill = b->fill; bd.fbase = b->fbase; bd.acols = std::min((b->maxcol + 1) & ~1, L.ast);
+      tab.push_back(bd);
+    }
+    if (!ok) continue;
+    DLB_TRY(upload(plan, tab.data(), tab.size(), pass == 0 ? &L.d_white : &L.d_plain));
+  }
   return DLB_OK;
 }
 
@@ -213,13 +266,18 @@ static int build_mlp(dlb_plan* plan, const dlb_generator_desc& gd, DevGen& g, Ml
   g.aux[0] = off[0];
   mlp.act = act;
   const double* w = gd.ddata + 2 * d;
+  mlp.layers.resize(nh);
   for (int l = 0; l < nh; ++l) {
-    Block blk;
-    std::vector<TermSpec> terms{TermSpec{0, -1, g.foff + off[l], width[l], nullptr, w}};
+    Block& blk = mlp.layers[l];
+    std::vector<TermSpec> terms{TermSpec{0, -1, g.foff + off[l], 0, width[l], nullptr, w}};
     const double* bias = w + (size_t)width[l] * width[l + 1];
-    DLB_TRY(build_block_core(plan, width[l + 1], 1, terms, nullptr, bias, 0, nullptr, blk));
+    const Variant var = choose_variant(1);
+    const int ast = round_ast(chunk_extent(width[l]));
+    const bool resident = contract_smem_bytes(var, 2, true, ast, plan->dpad, 0, 1, plan->ngen) <= 227 * 1024;
+    DLB_TRY(build_block_core(plan, var, resident, width[l + 1], 1, terms, nullptr, bias, 0, nullptr, blk));
     blk.coloff = g.foff + off[l + 1];
-    mlp.layers.push_back(blk);
+    blk.fill = 1; blk.fbase = g.foff + off[l]; blk.gen = -1;
+    blk.maxcol = resident ? blk.maxcol : -1;   // -1: streaming launch
     w = bias + width[l + 1];
   }
   return DLB_OK;
@@ -227,13 +285,12 @@ static int build_mlp(dlb_plan* plan, const dlb_generator_desc& gd, DevGen& g, Ml
 
 static int ensure_workspace(dlb_plan* plan, long long npad) {
   if (npad <= plan->cap) return DLB_OK;
-  for (void* ptr : {(void*)plan->w_F, (void*)plan->w_C, (void*)plan->w_partial, (void*)plan->w_params, (void*)plan->w_out, (void*)plan->w_status})
+  for (void* ptr : {(void*)plan->w_F, (void*)plan->w_partial, (void*)plan->w_params, (void*)plan->w_out, (void*)plan->w_status})
     if (ptr) cudaFree(ptr);
-  plan->w_F = plan->w_C = plan->w_partial = plan->w_params = plan->w_out = nullptr; plan->w_status = nullptr;
+  plan->w_F = plan->w_partial = plan->w_params = plan->w_out = nullptr; plan->w_status = nullptr;
   plan->cap = 0;
   DLB_CUDA(cudaMalloc((void**)&plan->w_F, ((size_t)npad * plan->fstride + 64) * sizeof(double)));
   DLB_CUDA(cudaMemset(plan->w_F, 0, ((size_t)npad * plan->fstride + 64) * sizeof(double)));
-  DLB_CUDA(cudaMalloc((void**)&plan->w_C, (size_t)npad * plan->cstride * sizeof(double)));
   DLB_CUDA(cudaMalloc((void**)&plan->w_partial, (size_t)std::max(plan->ptotal, 1LL) * npad * sizeof(double)));
   DLB_CUDA(cudaMalloc((void**)&plan->w_params, (size_t)npad * std::max(plan->d, 1) * sizeof(double)));
   DLB_CUDA(cudaMalloc((void**)&plan->w_out, (size_t)npad * (3 + std::max(plan->ns, 0)) * sizeof(double)));
@@ -242,50 +299,45 @@ static int ensure_workspace(dlb_plan* plan, long long npad) {
   return DLB_OK;
 }
 
-static int run_front(dlb_plan* plan, const double* d_params, long long N, long long npad, cudaStream_t stream) {
-  if (plan->ncoef) {
-    int rc = launch_coefs(plan->d_coefs, plan->ncoef, d_params, plan->d, N, npad, plan->w_C, plan->cstride, stream);
-    if (rc) return rc;
-  }
+static void fill_params(const dlb_plan* plan, const Launch& L, ContractParams& cp, const double* d_params, long long N, long long npad) {
+  std::memset(&cp, 0, sizeof(cp));
+  cp.nblocks = L.nblocks; cp.gens = plan->d_gens; cp.ngen = plan->ngen; cp.coefs = plan->d_coefs; cp.ncoef = plan->ncoef;
+  cp.params = d_params; cp.d = plan->d; cp.N = N; cp.F = plan->w_F; cp.fstride = plan->fstride;
+  cp.partial = plan->w_partial; cp.npad = npad;
+  cp.nstages = L.nstages; cp.resident = L.resident; cp.ast = L.ast; cp.dpad = plan->dpad; cp.npart_max = L.npart_max;
+}
+
+// Feature generators that run as their own kernels (everything except Taylor monomials in resident mode).
+static int run_front(dlb_plan* plan, const double* d_params, long long N, long long npad, cudaStream_t stream, bool force_taylor = false) {
   for (size_t ig = 0; ig < plan->gens.size(); ++ig) {
     const DevGen& g = plan->gens[ig];
     if (g.kind == DLB_GEN_MLP) {
       DLB_TRY(launch_mlp_input(g, d_params, plan->d, N, npad, plan->w_F, plan->fstride, stream));
-      for (const Block& blk : plan->mlps[ig].layers) {
+      for (const Launch& L : plan->mlps[ig].launches) {
         ContractParams cp;
-        std::memset(&cp, 0, sizeof(cp));
-        cp.F = plan->w_F; cp.fstride = plan->fstride; cp.C = plan->w_C; cp.cstride = plan->cstride;
-        cp.chunks = blk.d_chunks; cp.nchunks = blk.nchunks; cp.tiles = blk.d_tiles_plain; cp.r0 = blk.d_t0_plain;
-        cp.gconst = blk.d_gconst; cp.nslots = 1; cp.npad = npad;
-        cp.out = plan->w_F; cp.ostride = plan->fstride; cp.ocol0 = blk.coloff; cp.ncols = blk.ncols; cp.out_rows = npad;
-        cp.act = plan->mlps[ig].act; cp.mode = 1; cp.nstages = blk.nstages;
-        const int BM = variant_bm(blk.var);
-        DLB_TRY(launch_contract(blk.var, cp, (int)((npad + BM - 1) / BM), blk.ncb, stream));
+        fill_params(plan, L, cp, d_params, N, npad);
+        cp.blocks = L.d_plain; cp.ncoef = 0;
+        cp.out = plan->w_F; cp.ostride = plan->fstride; cp.out_rows = npad; cp.act = plan->mlps[ig].act; cp.mode = 1;
+        cp.U = npad / variant_unit(L.var);
+        DLB_TRY(launch_contract(L.var, cp, plan->nsm, stream));
       }
       continue;
     }
+    if (g.kind == DLB_GEN_TAYLOR && g.aux[6] && plan->resident && !force_taylor) continue;   // evaluated inside the contraction kernel
     DLB_TRY(launch_features(g, d_params, plan->d, N, npad, plan->w_F, plan->fstride, stream));
   }
   return DLB_OK;
 }
 
-static int run_contract(dlb_plan* plan, long long N, long long npad, int mode, double* d_theory, cudaStream_t stream) {
-  for (const Block& blk : plan->blocks) {
-    ContractParams cp;
-    cp.F = plan->w_F; cp.fstride = plan->fstride; cp.C = plan->w_C; cp.cstride = plan->cstride;
-    cp.chunks = blk.d_chunks; cp.nchunks = blk.nchunks;
-    cp.tiles = mode == 0 ? blk.d_tiles_white : blk.d_tiles_plain;
-    cp.r0 = mode == 0 ? blk.d_r0_white : blk.d_t0_plain;
-    cp.gconst = blk.d_gconst; cp.nconst = blk.nconst; cp.nslots = blk.nslots; cp.npart = blk.npart;
-    cp.partial = plan->w_partial; cp.npad = npad; cp.poff = blk.poff;
-    cp.out = d_theory; cp.ostride = plan->ntheory; cp.ocol0 = blk.coloff; cp.ncols = blk.ncols;
-    cp.out_rows = N; cp.act = 0; cp.mode = mode; cp.nstages = blk.nstages;
-    if (mode == 1 && (!cp.tiles || !cp.r0)) { set_error("plan was built without un-whitened matrices: theory_batch unavailable"); return DLB_ERR_ARG; }
-    const int BM = variant_bm(blk.var);
-    int rc = launch_contract(blk.var, cp, (int)((N + BM - 1) / BM), blk.ncb, stream);
-    if (rc) return rc;
-  }
-  return DLB_OK;
+static int run_contract(dlb_plan* plan, const double* d_params, long long N, long long npad, int mode, double* d_theory, cudaStream_t stream) {
+  const Launch& L = plan->launch;
+  ContractParams cp;
+  fill_params(plan, L, cp, d_params, N, npad);
+  cp.blocks = mode == 0 ? L.d_white : L.d_plain;
+  if (!cp.blocks) { set_error("plan was built without un-whitened matrices: theory_batch unavailable"); return DLB_ERR_ARG; }
+  cp.out = d_theory; cp.ostride = plan->ntheory; cp.out_rows = N; cp.act = 0; cp.mode = mode;
+  cp.U = (N + variant_unit(L.var) - 1) / variant_unit(L.var);
+  return launch_contract(L.var, cp, plan->nsm, stream);
 }
 
 }  // namespace dlb
@@ -311,7 +363,7 @@ void dlb_plan_destroy(dlb_plan* plan) {
   if (!plan) return;
   cudaSetDevice(plan->device);
   for (void* ptr : plan->owned) cudaFree(ptr);
-  for (void* ptr : {(void*)plan->w_F, (void*)plan->w_C, (void*)plan->w_partial, (void*)plan->w_params, (void*)plan->w_out, (void*)plan->w_status, (void*)plan->w_theory})
+  for (void* ptr : {(void*)plan->w_F, (void*)plan->w_partial, (void*)plan->w_params, (void*)plan->w_out, (void*)plan->w_status, (void*)plan->w_theory})
     if (ptr) cudaFree(ptr);
   for (auto& e : plan->ev) if (e) cudaEventDestroy(e);
   delete plan;
@@ -330,15 +382,18 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
   struct Guard { dlb_plan* p; ~Guard() { if (p) dlb_plan_destroy(p); } } guard{plan};
   DLB_CUDA(cudaGetDevice(&plan->device));
   plan->d = desc->d; plan->ngen = desc->ngen; plan->ncoef = desc->ncoef; plan->ns = desc->ns; plan->nmarg = desc->nmarg;
-  plan->cstride = std::max(desc->ncoef, 1);
+  plan->dpad = (desc->d + 1) | 1;   // + the constant-one column; odd stride keeps per-row accesses conflict free
+  DLB_CUDA(cudaDeviceGetAttribute(&plan->nsm, cudaDevAttrMultiProcessorCount, plan->device));
   // generators / feature layout
   int foff = 0;
+  std::vector<GenDev> gendev(desc->ngen);
   for (int ig = 0; ig < desc->ngen; ++ig) {
     const dlb_generator_desc& gd = desc->gens[ig];
     DLB_REQUIRE(gd.nparams >= 0 && gd.nparams <= MAXP, "generator: too many parameters");
     DLB_REQUIRE(gd.nfeat > 0, "generator: nfeat must be positive");
     DevGen g;
     std::memset(&g, 0, sizeof(g));
+    std::memset(&gendev[ig], 0, sizeof(GenDev));
     g.kind = gd.kind; g.nparams = gd.nparams; g.nfeat = gd.nfeat; g.fpad = (gd.nfeat + 3) & ~3; g.foff = foff;
     for (int j = 0; j < gd.nparams; ++j) {
       DLB_REQUIRE(gd.param_idx[j] >= -1 && gd.param_idx[j] < desc->d, "generator: parameter index out of range");
@@ -349,7 +404,18 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
     DLB_TRY(upload(plan, gd.idata, (size_t)gd.ni, &di));
     DLB_TRY(upload(plan, gd.ddata, (size_t)gd.nd, &dd));
     g.idata = di; g.ni = gd.ni; g.ddata = dd; g.nd = gd.nd;
-    if (gd.kind == DLB_GEN_TAYLOR) DLB_REQUIRE(gd.nfeat > 2 && gd.ni == (gd.nfeat - 2) * gd.nparams && gd.nd == gd.nparams, "taylor generator: nfeat = 2 + T, idata = powers[T, d], ddata = center[d]");
+    if (gd.kind == DLB_GEN_TAYLOR) {
+      DLB_REQUIRE(gd.nfeat > 2 && gd.ni == (gd.nfeat - 2) * gd.nparams && gd.nd == gd.nparams, "taylor generator: nfeat = 2 + T, idata = powers[T, d], ddata = center[d]");
+      GenDev& gv = gendev[ig];
+      gv.nparams = gd.nparams;
+      for (int j = 0; j < gd.nparams; ++j) { gv.pidx[j] = g.pidx[j]; gv.pdef[j] = g.pdef[j]; gv.center[j] = gd.ddata[j]; }
+      for (int t = 0; t < gd.nfeat - 2; ++t) {
+        int deg = 0;
+        for (int j = 0; j < gd.nparams; ++j) { DLB_REQUIRE(gd.idata[t * gd.nparams + j] >= 0, "taylor generator: negative power"); deg += gd.idata[t * gd.nparams + j]; }
+        gv.maxdeg = std::max(gv.maxdeg, deg);
+      }
+      g.aux[6] = gv.maxdeg <= 7 ? 1 : 0;   // in-kernel monomials (factor lists hold 7 entries; higher orders go through the feature kernel)
+    }
     plan->mlps.emplace_back();
     if (gd.kind == DLB_GEN_MLP) DLB_TRY(build_mlp(plan, gd, g, plan->mlps.back()));
     if (gd.kind == DLB_GEN_KAISER || gd.kind == DLB_GEN_BAO) {
@@ -382,19 +448,74 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
   DLB_TRY(upload(plan, desc->prior_hi, (size_t)desc->d, &plan->d_prior_hi));
   DLB_TRY(upload(plan, desc->prior_loc, (size_t)desc->d, &plan->d_prior_loc));
   DLB_TRY(upload(plan, desc->prior_scale, (size_t)desc->d, &plan->d_prior_scale));
-  // blocks
+  // blocks: validate, pick the kernel variant (plan-wide) and the A-operand mode
+  int max_slots = 1, ast = 4;
+  bool resident = true;
+  for (int ib = 0; ib < desc->nblocks; ++ib) {
+    const dlb_block_desc& bd = desc->blocks[ib];
+    DLB_REQUIRE(bd.ncols > 0 && bd.nslots >= 1 && bd.nslots <= 8, "block: ncols > 0 and 1 <= nslots <= 8 required");
+    DLB_REQUIRE(bd.nterms > 0 && bd.terms && bd.matrices_white && bd.r0_white, "block: terms / matrices_white / r0_white required");
+    max_slots = std::max(max_slots, bd.nslots);
+    for (int t = 0; t < bd.nterms; ++t) {
+      const dlb_term_desc& td = bd.terms[t];
+      DLB_REQUIRE(td.slot >= 0 && td.slot < bd.nslots, "term slot out of range");
+      DLB_REQUIRE(td.coef >= -1 && td.coef < desc->ncoef, "term coef out of range");
+      DLB_REQUIRE(td.gen >= 0 && td.gen < desc->ngen, "term generator out of range");
+      DLB_REQUIRE(td.K > 0 && td.foff >= 0 && (td.foff % 2) == 0 && td.foff + td.K <= plan->gens[td.gen].nfeat, "term feature range invalid (foff must be even)");
+      if (td.gen != bd.terms[0].gen) resident = false;   // resident A holds ONE generator segment per block
+      ast = std::max(ast, td.foff + chunk_extent(td.K));
+    }
+  }
+  const Variant var = choose_variant(max_slots);
+  ast = round_ast(ast);
+  {
+    int npart_bound = 1;
+    for (int ib = 0; ib < desc->nblocks; ++ib) npart_bound = std::max(npart_bound, desc->blocks[ib].nslots * (desc->blocks[ib].nslots + 1) / 2 + desc->blocks[ib].nslots * desc->blocks[ib].nconst);
+    if (resident && contract_smem_bytes(var, 2, true, ast, plan->dpad, desc->ncoef, npart_bound, desc->ngen) > 227 * 1024 || desc->ngen > 32) resident = false;
+  }
+  plan->resident = resident;
+  if (resident) {   // factor lists of the monomials, one table per generator, indexed by segment column
+    plan->d_paths.resize(desc->ngen, nullptr);
+    for (int ig = 0; ig < desc->ngen; ++ig) {
+      const dlb_generator_desc& gd = desc->gens[ig];
+      if (!plan->gens[ig].aux[6]) continue;
+      std::vector<unsigned long long> paths(ast, 0xFF00000000000000ull);   // structural zeros
+      paths[0] = 0ull;                                                       // column 0 = 1 (empty product)
+      for (int t = 0; t < gd.nfeat - 2 && 2 + t < ast; ++t) {
+        unsigned long long q = 0ull;
+        int k = 0;
+        for (int j = 0; j < gd.nparams; ++j)
+          for (int e = 0; e < gd.idata[t * gd.nparams + j]; ++e) q |= (unsigned long long)(j + 1) << (8 * k++);
+        paths[2 + t] = q;
+      }
+      DLB_TRY(upload(plan, paths.data(), paths.size(), &plan->d_paths[ig]));
+    }
+  }
+  DLB_TRY(upload(plan, gendev.data(), gendev.size(), &plan->d_gens));
   plan->blocks.resize(desc->nblocks);
   int coloff = 0; long long poff = 0;
+  std::vector<Block*> bptr;
   for (int ib = 0; ib < desc->nblocks; ++ib) {
     Block& blk = plan->blocks[ib];
-    int rc = build_block(plan, desc, desc->blocks[ib], blk);
+    int rc = build_block(plan, desc, desc->blocks[ib], var, blk);
     if (rc) return rc;
     blk.coloff = coloff; coloff += blk.ncols;
-    blk.poff = poff; poff += (long long)blk.ncb * blk.npart;
+    blk.poff = poff; poff += blk.npart;     // the kernel sums the Gram partials over column blocks
+    blk.fill = plan->gens[blk.gen].aux[6] ? 0 : 1; blk.fbase = plan->gens[blk.gen].foff;
+    DLB_REQUIRE(!resident || blk.maxcol <= ast, "internal: resident A tile narrower than a chunk extent");
+    bptr.push_back(&blk);
   }
   plan->ntheory = coloff; plan->ptotal = poff;
+  DLB_TRY(build_launch(plan, bptr, resident, ast, desc->ncoef, plan->launch));
+  for (MlpLayers& mlp : plan->mlps) {
+    mlp.launches.resize(mlp.layers.size());
+    for (size_t l = 0; l < mlp.layers.size(); ++l) {
+      const bool res = mlp.layers[l].maxcol >= 0;
+      DLB_TRY(build_launch(plan, std::vector<Block*>{&mlp.layers[l]}, res, res ? round_ast(mlp.layers[l].maxcol) : 0, 0, mlp.launches[l]));
+    }
+  }
   std::vector<SolveBlock> sb(desc->nblocks);
-  for (int ib = 0; ib < desc->nblocks; ++ib) sb[ib] = SolveBlock{plan->blocks[ib].poff, plan->blocks[ib].ncb, plan->blocks[ib].npart, plan->blocks[ib].d_map};
+  for (int ib = 0; ib < desc->nblocks; ++ib) sb[ib] = SolveBlock{plan->blocks[ib].poff, 1, plan->blocks[ib].npart, plan->blocks[ib].d_map};
   DLB_TRY(upload(plan, sb.data(), sb.size(), &plan->d_solve_blocks));
   // solved parameters: M0 = diag(prior precision) + constant-row Gram, g0 = prior gradient at x0
   const int ns = desc->ns;
@@ -461,7 +582,7 @@ int dlb_eval_batch(dlb_plan* plan, const double* params, int64_t N, double* logp
     rc = run_front(plan, d_params, n, npad, stream);
     if (rc) return rc;
     if (plan->timing) DLB_CUDA(cudaEventRecord(plan->ev[1], stream));
-    rc = run_contract(plan, n, npad, 0, nullptr, stream);
+    rc = run_contract(plan, d_params, n, npad, 0, nullptr, stream);
     if (rc) return rc;
     if (plan->timing) DLB_CUDA(cudaEventRecord(plan->ev[2], stream));
     SolveParams sp;
@@ -528,7 +649,7 @@ int dlb_theory_batch(dlb_plan* plan, const double* params, int64_t N, double* th
     }
     rc = run_front(plan, d_params, n, npad, stream);
     if (rc) return rc;
-    rc = run_contract(plan, n, npad, 1, d_theory, stream);
+    rc = run_contract(plan, d_params, n, npad, 1, d_theory, stream);
     if (rc) return rc;
     if (!out_dev) DLB_CUDA(cudaMemcpyAsync(theory + start * plan->ntheory, d_theory, (size_t)n * plan->ntheory * sizeof(double), cudaMemcpyDeviceToHost, stream));
     if (!out_dev || !in_dev || start + chunk < N) DLB_CUDA(cudaStreamSynchronize(stream));
@@ -554,7 +675,7 @@ int dlb_features_batch(dlb_plan* plan, int32_t gen, const double* params, int64_
       DLB_CUDA(cudaMemcpyAsync(plan->w_params, d_params, (size_t)n * plan->d * sizeof(double), cudaMemcpyHostToDevice, stream));
       d_params = plan->w_params;
     }
-    rc = launch_features(g, d_params, plan->d, n, npad, plan->w_F, plan->fstride, stream);
+    rc = run_front(plan, d_params, n, npad, stream, true);
     if (rc) return rc;
     DLB_CUDA(cudaMemcpy2DAsync(features + start * g.nfeat, (size_t)g.nfeat * sizeof(double), plan->w_F + g.foff, (size_t)plan->fstride * sizeof(double),
                                (size_t)g.nfeat * sizeof(double), (size_t)n, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));

@@ -133,5 +133,5 @@ def launch_count():
 
 def measure_fp64_peak(kind='dmma'):
     val = ctypes.c_double()
-    _capi.check(_capi.load().dlb_measure_fp64_peak(0 if kind == 'dmma' else 1, ctypes.byref(val)))
+    _capi.check(_capi.load().dlb_measure_fp64_peak(kind if isinstance(kind, int) else (0 if kind == 'dmma' else 1), ctypes.byref(val)))
     return val.value
