@@ -41,10 +41,11 @@ extern std::atomic<long long> g_launches;
 // ---------------------------------------------------------------------------------------------------------------------
 // tiling constants of the contraction kernel (csrc/contract.cu)
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int KC = 36;        // k-chunk length == shared-memory row stride in doubles; 36 = 4 (mod 8) -> conflict-free 64-bit fragment loads
+constexpr int KC = 28;        // k-chunk length == shared-memory row stride in doubles; 28 = 4 (mod 8) -> conflict-free 64-bit fragment loads
 constexpr int ROW_ALIGN = 384;  // batch rows are padded to a multiple of every variant's row unit (64, 48) and tile
 
-struct Variant { int R, MT, NT, WM; };      // accumulator slots, m-tiles (of 8 rows) and n-tiles (of 8 columns) per warp; warp grid is WM (m) x 2 (n)
+struct Variant { int R, MT, NT, WM, CPS; }; // accumulator slots, m-tiles (of 8 rows) and n-tiles (of 8 columns) per warp; warp grid is WM (m) x 2 (n);
+                                            // CPS = co-resident CTAs per SM
 inline int variant_unit(const Variant& v) { return 8 * v.WM; }          // rows per unit (one m-tile of every warp row)
 inline int variant_bm(const Variant& v) { return 8 * v.WM * v.MT; }
 inline int variant_bn(const Variant& v) { return 16 * v.NT; }
@@ -92,6 +93,7 @@ struct ContractParams {
   long long U;                           // number of row units (variant_unit rows each) to process
 };
 
+size_t contract_smem_limit(int ctas_per_sm);
 size_t contract_smem_bytes(const Variant& v, int nstages, bool resident, int ast, int dpad, int ncoef, int npart_max, int ngen);
 int launch_contract(const Variant& v, const ContractParams& p, int nsm, cudaStream_t stream);
 

@@ -109,129 +109,153 @@ __device__ __forceinline__ void mma_chunk_dispatch(double (&acc)[MT][NT][2], con
 }
 
 // Position in the CTA's chunk sequence (tile, block, column block, chunk); chunk == nchunks is the epilogue-constants chunk.
+// Lives in shared memory: only warp 0 (the warp that re-arms the TMA ring) touches it.
 struct Cursor {
   long long u;
-  int b, cb, c, nchunks, ncb;
-  bool done;
+  int b, cb, c, nchunks, ncb, done, pad;
 };
 
-template <int R, int MT, int NT, int WM, bool RESIDENT>
-__global__ void __launch_bounds__(WM * 64, 1) contract_kernel(const __grid_constant__ ContractParams p) {
+// barrier over the two warps (wn = 0, 1) that share a set of rows: everything a warp pair needs between the TMA ring and
+// its Gram flush (parameters, coefficients, A rows, Gram copies) is produced by the pair itself, so pairs drift freely
+// and one pair's tile prologue / epilogue overlaps the other pairs' DMMAs.
+__device__ __forceinline__ void pair_barrier(int wm) { asm volatile("bar.sync %0, 64;" ::"r"(wm + 1) : "memory"); }
+
+__device__ __forceinline__ unsigned atom_add_acq_rel(unsigned* addr, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
+  return old;
+}
+
+template <int R, int MT, int NT, int WM, int CPS, bool RESIDENT>
+__global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_constant__ ContractParams p) {
   constexpr int NW = 2 * WM, NTH = NW * 32, UNIT = WM * 8, BM = UNIT * MT, BN = 16 * NT;
   constexpr int STAGE_DOUBLES = BN * KC + (RESIDENT ? 0 : BM * KC);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int S = p.nstages;
   double* stage_base = reinterpret_cast<double*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(stage_base + (size_t)S * STAGE_DOUBLES);
-  uint64_t* empty = full + S;
-  uint64_t* abar = empty + S;                                         // resident A tile copied from the feature matrix
-  double* A_s = reinterpret_cast<double*>(abar + 2);                  // [BM][ast]           (RESIDENT)
+  unsigned* cnt = reinterpret_cast<unsigned*>(full + S);              // [S] warps that released the stage (the last one re-arms it)
+  uint64_t* abar = full + 2 * S;                                      // [WM] resident A rows copied from the feature matrix (per warp pair)
+  Cursor* cur = reinterpret_cast<Cursor*>(abar + WM);
+  double* A_s = reinterpret_cast<double*>(abar + WM + 6);             // [BM][ast]           (RESIDENT)
   double* xs0 = A_s + (RESIDENT ? (size_t)BM * p.ast : 0);            // [2][BM][dpad]       parameter tiles (double buffered)
   double* cs = xs0 + (size_t)2 * BM * p.dpad;                         // [ncoef][BM]         bias monomials
   double* red = cs + (size_t)(p.ncoef > 0 ? p.ncoef : 1) * BM;        // [2][BM][npart_max]  Gram partials (per warp column)
   GenDev* gens_s = reinterpret_cast<GenDev*>(red + (size_t)2 * BM * p.npart_max);   // [ngen]   (RESIDENT)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int ptid = wn * 32 + lane;        // thread index inside the warp pair
   const long long U = p.U;
   const long long u0 = U * blockIdx.x / gridDim.x, u1 = U * (blockIdx.x + 1) / gridDim.x;
+  // Tile schedule: MT units per tile; with two CTAs per SM the second-resident CTA starts with a half tile, so that the two
+  // CTAs of an SM run out of phase and one's tile prologue / epilogue overlaps the other's DMMAs.
+  const bool half_first = CPS == 2 && MT > 1 && blockIdx.x >= (gridDim.x + 1) / 2;
+  auto tile_units = [&](long long u) { return (int)min((long long)((half_first && u == u0) ? MT / 2 : MT), u1 - u); };
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
-    mbar_init(abar, 1);
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); cnt[s] = 0u; }
+    for (int i = 0; i < WM; ++i) mbar_init(&abar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    cur->u = u0; cur->b = 0; cur->cb = 0; cur->c = 0; cur->done = 0;
+    cur->nchunks = p.blocks[0].nchunks; cur->ncb = p.blocks[0].ncb;
   }
   if constexpr (RESIDENT) {
     for (int i = tid; i < p.ngen * (int)(sizeof(GenDev) / 4); i += NTH) reinterpret_cast<int*>(gens_s)[i] = reinterpret_cast<const int*>(p.gens)[i];
   }
   for (int i = tid; i < 2 * BM; i += NTH) xs0[(size_t)i * p.dpad + p.d] = 1.;   // constant-one column (absent monomial factors)
-  // parameter tile of the first row tile
-  {
-    const int h = UNIT * (int)min((long long)MT, u1 - u0);
-    for (int i = tid; i < h * p.d; i += NTH) {
-      const int r = i / p.d, j = i - r * p.d;
-      cp_async8(xs0 + (size_t)r * p.dpad + j, p.params + min(u0 * UNIT + r, p.N - 1) * p.d + j);
+  // Parameter rows of this warp pair for a tile starting at unit u with mtc units -> buffer xb (cp.async; rows beyond N replicate
+  // the last point, their results are never read)
+  auto load_params = [&](long long u, int mtc, double* xb) {
+    for (int i = ptid; i < mtc * 8 * p.d; i += 64) {
+      const int rr = i / p.d, j = i - rr * p.d;
+      const int r = (rr >> 3) * UNIT + wm * 8 + (rr & 7);
+      cp_async8(xb + (size_t)r * p.dpad + j, p.params + min(u * UNIT + r, p.N - 1) * p.d + j);
     }
-  }
+  };
+  load_params(u0, tile_units(u0), xs0);
   __syncthreads();
 
-  // ---- TMA refill state (used by warp 0 only; uniform across its lanes) ----
-  Cursor cur;
-  cur.u = u0; cur.b = 0; cur.cb = 0; cur.c = 0; cur.done = false;
-  cur.nchunks = p.blocks[0].nchunks; cur.ncb = p.blocks[0].ncb;
-  int rs = 0;
-  uint32_t rph = 0;
-  auto refill = [&]() {
-    if (cur.done) return;
-    mbar_wait(&empty[rs], rph ^ 1);
-    const BlockDev* blk = p.blocks + cur.b;
+  // ---- TMA ring: stage rs has been released by every warp (or is fresh); load the next chunk of the sequence into it.
+  //      Executed by one whole warp (the last one to release the stage); sequence state lives in shared memory. ----
+  auto refill = [&](int rs) {
+    if (cur->done) return;
+    const int c = cur->c, nchunks = cur->nchunks, cb = cur->cb;
+    const BlockDev* blk = p.blocks + cur->b;
     double* dst = stage_base + (size_t)rs * STAGE_DOUBLES;
-    if (cur.c == cur.nchunks) {   // epilogue constants of this column block: [nconst + 1][BN]
+    if (c == nchunks) {   // epilogue constants of this column block: [nconst + 1][BN]
       const int nrow = blk->nconst + 1;
       if (lane == 0) {
         mbar_arrive_expect_tx(&full[rs], (uint32_t)(nrow * BN * 8));
-        tma_bulk_g2s(dst, blk->epi + (size_t)cur.cb * nrow * BN, nrow * BN * 8, &full[rs]);
+        tma_bulk_g2s(dst, blk->epi + (size_t)cb * nrow * BN, nrow * BN * 8, &full[rs]);
       }
     } else {
-      const double* src = blk->tiles + ((size_t)cur.cb * cur.nchunks + cur.c) * (BN * KC);
+      const double* src = blk->tiles + ((size_t)cb * nchunks + c) * (BN * KC);
       if constexpr (RESIDENT) {
         if (lane == 0) {
           mbar_arrive_expect_tx(&full[rs], (uint32_t)(BN * KC * 8));
           tma_bulk_g2s(dst, src, BN * KC * 8, &full[rs]);
         }
       } else {
-        const int4 ch = __ldg(reinterpret_cast<const int4*>(blk->chunks + cur.c));   // slot, coef, fcol, kc
-        const int h = UNIT * (int)min((long long)MT, u1 - cur.u);
+        const int4 ch = __ldg(reinterpret_cast<const int4*>(blk->chunks + c));   // slot, coef, fcol, kc
+        const long long cu = cur->u;
+        const int h = UNIT * tile_units(cu);
         if (lane == 0) {
           mbar_arrive_expect_tx(&full[rs], (uint32_t)(h * ch.w * 8 + BN * KC * 8));
           tma_bulk_g2s(dst, src, BN * KC * 8, &full[rs]);
         }
         __syncwarp();
-        const double* Fsrc = p.F + cur.u * UNIT * p.fstride + ch.z;
+        const double* Fsrc = p.F + cu * UNIT * p.fstride + ch.z;
         for (int r = lane; r < h; r += 32) tma_bulk_g2s(dst + BN * KC + r * KC, Fsrc + (size_t)r * p.fstride, ch.w * 8, &full[rs]);
       }
     }
-    // advance
-    if (++cur.c > cur.nchunks) {
-      cur.c = 0;
-      if (++cur.cb == cur.ncb) {
-        cur.cb = 0;
-        if (++cur.b == p.nblocks) {
-          cur.b = 0;
-          cur.u += MT;
-          if (cur.u >= u1) cur.done = true;
+    __syncwarp();
+    if (lane == 0) {   // advance
+      if (++cur->c > nchunks) {
+        cur->c = 0;
+        if (++cur->cb == cur->ncb) {
+          cur->cb = 0;
+          if (++cur->b == p.nblocks) {
+            cur->b = 0;
+            cur->u += tile_units(cur->u);
+            if (cur->u >= u1) cur->done = 1;
+          }
+          cur->nchunks = p.blocks[cur->b].nchunks; cur->ncb = p.blocks[cur->b].ncb;
         }
-        cur.nchunks = p.blocks[cur.b].nchunks; cur.ncb = p.blocks[cur.b].ncb;
       }
     }
-    if (++rs == S) { rs = 0; rph ^= 1; }
+    __syncwarp();
+  };
+  // this warp is done with stage rs: the last warp to say so re-arms it
+  auto release = [&](int rs) {
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) {
+      last = atom_add_acq_rel(&cnt[rs], 1u) == (unsigned)(NW - 1);
+      if (last) cnt[rs] = 0u;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) refill(rs);
   };
   if (warp == 0)
-    for (int i = 0; i < S - 1; ++i) refill();
+    for (int i = 0; i < S; ++i) refill(i);
 
-  const int wm = warp >> 1, wn = warp & 1;
-  const int lr = lane >> 2, lc = lane & 3;
   const int npm = p.npart_max;
   int s = 0, xbuf = 0;
   uint32_t ph = 0, aph = 0;
-  for (long long u = u0; u < u1; u += MT) {
-    const int mtc = (int)min((long long)MT, u1 - u);
-    const int h = UNIT * mtc;
+  for (long long u = u0; u < u1;) {
+    const int mtc = tile_units(u);
     const long long row0 = u * UNIT;
     double* xs = xs0 + (size_t)xbuf * BM * p.dpad;
     cp_async_wait_all();
-    __syncthreads();   // this tile's parameters have landed; previous tile completely finished (red flushed, cs / A_s free)
-    if (u + MT < u1) {  // prefetch the next tile's parameters (rows beyond N replicate the last point; their results are never read)
-      const int hn = UNIT * (int)min((long long)MT, u1 - u - MT);
-      double* xn = xs0 + (size_t)(xbuf ^ 1) * BM * p.dpad;
-      for (int i = tid; i < hn * p.d; i += NTH) {
-        const int r = i / p.d, j = i - r * p.d;
-        cp_async8(xn + (size_t)r * p.dpad + j, p.params + min(row0 + BM + r, p.N - 1) * p.d + j);
-      }
-    }
+    pair_barrier(wm);   // this tile's parameter rows have landed; the pair has completely finished its previous tile
+    if (u + mtc < u1) load_params(u + mtc, tile_units(u + mtc), xs0 + (size_t)(xbuf ^ 1) * BM * p.dpad);
     xbuf ^= 1;
     // ---- bias monomials c = scale * prod_f theta[idx_f]^pow_f (tracer combine, reference full_shape.py:545-550) ----
-    for (int i = tid; i < p.ncoef * h; i += NTH) {
-      const int j = i / h, r = i - j * h;
+    for (int i = ptid; i < p.ncoef * mtc * 8; i += 64) {
+      const int j = i / (mtc * 8), rr = i - j * (mtc * 8);
+      const int r = (rr >> 3) * UNIT + wm * 8 + (rr & 7);
       const DevCoef* cf = p.coefs + j;
       double c = cf->scale;
       const int nf = cf->nf;
@@ -246,16 +270,18 @@ __global__ void __launch_bounds__(WM * 64, 1) contract_kernel(const __grid_const
       const BlockDev* blk = p.blocks + b;
       const int nchunks = blk->nchunks, ncb = blk->ncb, npart = blk->npart, Rb = blk->nslots, nconst = blk->nconst;
       const Chunk* chunks = blk->chunks;
-      if (b > 0) __syncthreads();   // flush of the previous block done; every warp finished reading A_s
+      if (b > 0) pair_barrier(wm);   // the pair's flush of the previous block is done and both warps finished reading their A rows
       if (RESIDENT && blk->fill == 1) {
-        // ---- resident A tile = this block's generator segment of the feature matrix (MLP activations, ...): one TMA row copy
+        // ---- resident A rows = this block's generator segment of the feature matrix (MLP activations, ...): one TMA row copy
         //      per point, once per (tile, block) ----
         const int acols = blk->acols;
-        if (tid == 0) mbar_arrive_expect_tx(abar, (uint32_t)(h * acols * 8));
-        __syncthreads();
-        const double* Fsrc = p.F + row0 * p.fstride + blk->fbase;
-        for (int r = tid; r < h; r += NTH) tma_bulk_g2s(A_s + (size_t)r * p.ast, Fsrc + (size_t)r * p.fstride, acols * 8, abar);
-        mbar_wait(abar, aph);
+        if (ptid == 0) mbar_arrive_expect_tx(&abar[wm], (uint32_t)(mtc * 8 * acols * 8));
+        pair_barrier(wm);
+        if (ptid < mtc * 8) {
+          const int r = (ptid >> 3) * UNIT + wm * 8 + (ptid & 7);
+          tma_bulk_g2s(A_s + (size_t)r * p.ast, p.F + (row0 + r) * p.fstride + blk->fbase, acols * 8, &abar[wm]);
+        }
+        mbar_wait(&abar[wm], aph);
         aph ^= 1;
       } else if constexpr (RESIDENT) {
         // ---- Taylor monomials of this block's emulator, straight into shared memory ----
@@ -282,7 +308,8 @@ __global__ void __launch_bounds__(WM * 64, 1) contract_kernel(const __grid_const
           const bool zero = (path >> 56) != 0ull;
           if (j < p.ast) {
 #pragma unroll 4
-            for (int r = warp; r < h; r += NW) {
+            for (int rr = wn; rr < mtc * 8; rr += 2) {
+              const int r = (rr >> 3) * UNIT + wm * 8 + (rr & 7);
               const double* xr = xs + (size_t)r * p.dpad;
               double m = xr[col[0]] - ck[0];
 #pragma unroll
@@ -297,7 +324,7 @@ __global__ void __launch_bounds__(WM * 64, 1) contract_kernel(const __grid_const
         for (int mt = 0; mt < mtc; ++mt)
           for (int i = lane; i < 8 * npart; i += 32) red[((size_t)wn * BM + mt * UNIT + wm * 8 + i / npart) * npm + (i % npart)] = 0.;
       }
-      __syncthreads();
+      pair_barrier(wm);
 
       int4 ch_next = __ldg(reinterpret_cast<const int4*>(chunks));   // slot, coef, fcol, kc (prefetched one chunk ahead)
       for (int cb = 0; cb < ncb; ++cb) {
@@ -325,9 +352,7 @@ __global__ void __launch_bounds__(WM * 64, 1) contract_kernel(const __grid_const
 #pragma unroll
           for (int sl = 0; sl < R; ++sl)
             if (ch.x == sl) mma_chunk_dispatch<MT, NT>(acc[sl], Ap, astride, Bp, beta, nk4, mtc);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[s]);
-          if (warp == 0) refill();
+          release(s);
           if (++s == S) { s = 0; ph ^= 1; }
         }
 
@@ -406,48 +431,52 @@ __global__ void __launch_bounds__(WM * 64, 1) contract_kernel(const __grid_const
             }
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-        if (warp == 0) refill();
+        release(s);
         if (++s == S) { s = 0; ph ^= 1; }
       }  // cb
 
       if (p.mode == 0) {
-        __syncthreads();   // every warp's contributions are in its Gram copy
+        pair_barrier(wm);   // both warps' contributions are in their Gram copies
         double* out = p.partial + blk->poff * p.npad + row0;
-        for (int i = tid; i < h * npart; i += NTH) {
-          const int e = i / h, r = i - e * h;
+        for (int i = ptid; i < mtc * 8 * npart; i += 64) {
+          const int e = i / (mtc * 8), rr = i - e * (mtc * 8);
+          const int r = (rr >> 3) * UNIT + wm * 8 + (rr & 7);
           out[(long long)e * p.npad + r] = red[(size_t)r * npm + e] + red[((size_t)BM + r) * npm + e];
         }
       }
     }  // blocks
+    u += mtc;
   }    // tiles
 }
 
-template <int R, int MT, int NT, int WM, bool RESIDENT>
+template <int R, int MT, int NT, int WM, int CPS, bool RESIDENT>
 int launch_variant(const ContractParams& p, int grid, size_t smem, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    DLB_CUDA(cudaFuncSetAttribute(contract_kernel<R, MT, NT, WM, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DLB_CUDA(cudaFuncSetAttribute(contract_kernel<R, MT, NT, WM, CPS, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)contract_smem_limit(CPS)));
     configured = true;
   }
-  contract_kernel<R, MT, NT, WM, RESIDENT><<<grid, WM * 64, smem, stream>>>(p);
+  contract_kernel<R, MT, NT, WM, CPS, RESIDENT><<<grid, WM * 64, smem, stream>>>(p);
   g_launches++;
   DLB_CUDA(cudaGetLastError());
   return DLB_OK;
 }
 
-template <int R, int MT, int NT, int WM>
+template <int R, int MT, int NT, int WM, int CPS>
 int launch_mode(const ContractParams& p, int grid, size_t smem, cudaStream_t stream) {
-  return p.resident ? launch_variant<R, MT, NT, WM, true>(p, grid, smem, stream) : launch_variant<R, MT, NT, WM, false>(p, grid, smem, stream);
+  return p.resident ? launch_variant<R, MT, NT, WM, CPS, true>(p, grid, smem, stream) : launch_variant<R, MT, NT, WM, CPS, false>(p, grid, smem, stream);
 }
 
 }  // namespace
 
+size_t contract_smem_limit(int ctas_per_sm) {   // dynamic shared memory available to one CTA
+  return ctas_per_sm == 2 ? (size_t)(233472 / 2 - 1024 - 512) : (size_t)227 * 1024;
+}
+
 size_t contract_smem_bytes(const Variant& v, int nstages, bool resident, int ast, int dpad, int ncoef, int npart_max, int ngen) {
   const int BM = variant_bm(v), BN = variant_bn(v);
   const size_t stage = (size_t)(BN * KC + (resident ? 0 : BM * KC)) * 8;
-  size_t bytes = nstages * stage + (size_t)(2 * nstages + 2) * 8;
+  size_t bytes = nstages * stage + (size_t)(2 * nstages + v.WM + 6) * 8;
   if (resident) bytes += (size_t)BM * ast * 8 + (size_t)ngen * sizeof(GenDev);
   bytes += (size_t)2 * BM * dpad * 8 + (size_t)std::max(ncoef, 1) * BM * 8 + (size_t)2 * BM * std::max(npart_max, 1) * 8;
   return bytes;
@@ -455,11 +484,12 @@ size_t contract_smem_bytes(const Variant& v, int nstages, bool resident, int ast
 
 int launch_contract(const Variant& v, const ContractParams& p, int nsm, cudaStream_t stream) {
   const size_t smem = contract_smem_bytes(v, p.nstages, p.resident != 0, p.ast, p.dpad, p.ncoef, p.npart_max, p.ngen);
-  if (smem > 227 * 1024) { set_error("contraction kernel: shared-memory budget exceeded"); return DLB_ERR_UNSUPPORTED; }
-  const int grid = (int)std::min<long long>(nsm, std::max<long long>(p.U, 1));
-  if (v.R == 1 && v.MT == 2 && v.NT == 7 && v.WM == 8) return launch_mode<1, 2, 7, 8>(p, grid, smem, stream);
-  if (v.R == 4 && v.MT == 2 && v.NT == 4 && v.WM == 6) return launch_mode<4, 2, 4, 6>(p, grid, smem, stream);
-  if (v.R == 8 && v.MT == 1 && v.NT == 4 && v.WM == 6) return launch_mode<8, 1, 4, 6>(p, grid, smem, stream);
+  if (smem > contract_smem_limit(v.CPS)) { set_error("contraction kernel: shared-memory budget exceeded"); return DLB_ERR_UNSUPPORTED; }
+  const int grid = (int)std::min<long long>((long long)nsm * v.CPS, std::max<long long>(p.U, 1));
+  if (v.R == 1 && v.MT == 2 && v.NT == 7 && v.WM == 4 && v.CPS == 2) return launch_mode<1, 2, 7, 4, 2>(p, grid, smem, stream);
+  if (v.R == 1 && v.MT == 2 && v.NT == 7 && v.WM == 8 && v.CPS == 1) return launch_mode<1, 2, 7, 8, 1>(p, grid, smem, stream);
+  if (v.R == 4 && v.MT == 2 && v.NT == 4 && v.WM == 6 && v.CPS == 1) return launch_mode<4, 2, 4, 6, 1>(p, grid, smem, stream);
+  if (v.R == 8 && v.MT == 1 && v.NT == 4 && v.WM == 6 && v.CPS == 1) return launch_mode<8, 1, 4, 6, 1>(p, grid, smem, stream);
   set_error("no contraction kernel variant for requested tile shape");
   return DLB_ERR_UNSUPPORTED;
 }

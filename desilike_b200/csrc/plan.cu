@@ -84,9 +84,9 @@ static bool is_device_ptr(const void* ptr) {
 }
 
 static Variant choose_variant(int nslots) {
-  if (nslots <= 1) return Variant{1, 2, 7, 8};   // 16 warps, 128 x 112 tile
-  if (nslots <= 4) return Variant{4, 2, 4, 6};   // 12 warps,  96 x  64 tile
-  return Variant{8, 1, 4, 6};                    // 12 warps,  48 x  64 tile
+  if (nslots <= 1) return Variant{1, 2, 7, 8, 1};   // 16 warps, 128 x 112 tile (build_launch prefers the 2-CTA/SM 8-warp 64 x 112 form)
+  if (nslots <= 4) return Variant{4, 2, 4, 6, 1};   // 12 warps,  96 x  64 tile
+  return Variant{8, 1, 4, 6, 1};                    // 12 warps,  48 x  64 tile
 }
 
 static int round_ast(int n) {   // row stride of the resident A tile: = 4 (mod 8) keeps the 64-bit fragment loads bank-conflict free
@@ -215,8 +215,13 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
   L.npart_max = 1;
   for (const Block* b : blocks) L.npart_max = std::max(L.npart_max, b->npart);
   L.nstages = 0;
-  for (int s = 4; s >= 2; --s)
-    if (contract_smem_bytes(L.var, s, resident, L.ast, plan->dpad, ncoef, L.npart_max, plan->ngen) <= 227 * 1024) { L.nstages = s; break; }
+  if (L.var.R == 1) {   // two co-resident 8-warp CTAs per SM (run out of phase) when their shared memory fits
+    const Variant v2{1, 2, 7, 4, 2};
+    for (int s = 3; s >= 2; --s)
+      if (contract_smem_bytes(v2, s, resident, L.ast, plan->dpad, ncoef, L.npart_max, plan->ngen) <= contract_smem_limit(2)) { L.var = v2; L.nstages = s; break; }
+  }
+  for (int s = 4; s >= 2 && !L.nstages; --s)
+    if (contract_smem_bytes(L.var, s, resident, L.ast, plan->dpad, ncoef, L.npart_max, plan->ngen) <= contract_smem_limit(1)) { L.nstages = s; break; }
   DLB_REQUIRE(L.nstages >= 2, "contraction launch needs too much shared memory (too many parameters, coefficients or solved templates)");
   for (int pass = 0; pass < 2; ++pass) {
     std::vector<BlockDev> tab;
@@ -273,7 +278,7 @@ static int build_mlp(dlb_plan* plan, const dlb_generator_desc& gd, DevGen& g, Ml
     const double* bias = w + (size_t)width[l] * width[l + 1];
     const Variant var = choose_variant(1);
     const int ast = round_ast(chunk_extent(width[l]));
-    const bool resident = contract_smem_bytes(var, 2, true, ast, plan->dpad, 0, 1, plan->ngen) <= 227 * 1024;
+    const bool resident = contract_smem_bytes(var, 2, true, ast, plan->dpad, 0, 1, plan->ngen) <= contract_smem_limit(1);
     DLB_TRY(build_block_core(plan, var, resident, width[l + 1], 1, terms, nullptr, bias, 0, nullptr, blk));
     blk.coloff = g.foff + off[l + 1];
     blk.fill = 1; blk.fbase = g.foff + off[l]; blk.gen = -1;
@@ -471,7 +476,7 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
   {
     int npart_bound = 1;
     for (int ib = 0; ib < desc->nblocks; ++ib) npart_bound = std::max(npart_bound, desc->blocks[ib].nslots * (desc->blocks[ib].nslots + 1) / 2 + desc->blocks[ib].nslots * desc->blocks[ib].nconst);
-    if (resident && contract_smem_bytes(var, 2, true, ast, plan->dpad, desc->ncoef, npart_bound, desc->ngen) > 227 * 1024 || desc->ngen > 32) resident = false;
+    if (resident && contract_smem_bytes(var, 2, true, ast, plan->dpad, desc->ncoef, npart_bound, desc->ngen) > contract_smem_limit(1) || desc->ngen > 32) resident = false;
   }
   plan->resident = resident;
   if (resident) {   // factor lists of the monomials, one table per generator, indexed by segment column
