@@ -36,6 +36,10 @@ UNIT = 'evals/s'
 
 def build_spec(workload):
     from oracle import configs
+    if workload == 'c1':
+        return configs.config_c1(), 'C1: KaiserTracerPowerSpectrumMultipoles (ShapeFit template, ell=0,2,4, k=0.02-0.2, 36 bins/ell) -> chi2 (n=108, d=6), direct theory (no emulator)'
+    if workload == 'c3':
+        return configs.config_c3(), 'C3: damped-BAO P(k) -> FFTLog (2048->4096) -> xi_ell(s) + solved broadband -> chi2 (n=66, d=7, ns=4)'
     if workload == 'c2':
         return configs.config_c2(coefficients='random'), 'C2: TaylorEmulator(order 4, T=70) pt tables 3x[3,350] -> Kaiser combine -> window [108,1050] -> chi2 (n=108, d=6)'
     if workload == 'c5':

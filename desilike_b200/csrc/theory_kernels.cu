@@ -252,102 +252,232 @@ __global__ void __launch_bounds__(BAO_WARPS * 32) bao_kernel(const DevGen g, con
 
 // ---------------------------------------------------------------------------------------------------------------------
 // FFTLog P_ell(kin) -> xi_ell(s) (reference theories/galaxy_clustering/base.py:62-77,127-136; algorithm restated in
-// oracle/fftlog.py).  One CTA per (point, ell): resample onto the 2048-point log grid (+ high-k extrapolation), multiply by
-// k^(3-q)/(2 pi)^(3/2), zero-pad to 4096, radix-2 DIF forward FFT (natural -> bit-reversed), multiply by u_ell(m)
-// (Hermitian extension handled analytically: for m > N/2 the factor is conj(u[N-m])), radix-2 DIT forward FFT
-// (bit-reversed -> natural) == numpy's hfft, scale by s^-q (-1)^(ell/2) / N, un-pad, linear interpolation onto s.
-// FFT block of ddata at idata[10]: wgt[Ng] lh[Ng] dh[Ng] pre[Ng] u[nell][Np/2+1][2] post[nell][Ng] (slope_inv, 0) tw[Np/2][2] outw[nell][ns]
-// FFT block of idata at idata[11]: jmap[Ng] outj[nell][ns]
+// oracle/fftlog.py).  One CTA of 128 threads per (point, ell):
+//   1. resample P_ell(kin) onto the 2048-point log grid: interpolation and high-k extrapolation (reference base.py:127-133)
+//      are both 2-point linear combinations  x[i] = c0[i] pin[j0[i]] + c1[i] pin[j0[i] + 1]  with the power-law prefactor
+//      k^(3-q) / (2 pi)^(3/2) folded into c0, c1 at plan time; zero padding to Np = 4096 is implicit;
+//   2. rfft(4096) as ONE 2048-point complex FFT of z[n] = x[2n] + i x[2n+1] (Stockham autosort, radix 16 x 16 x 8 butterflies in
+//      registers, 3 shared-memory passes instead of 12 radix-2 ones) followed by the real-input untangling
+//          X[m] = (Z[m] + conj Z[M-m]) / 2 - i/2 e^(-2 pi i m / Np) (Z[m] - conj Z[M-m]);
+//   3. the Hankel kernel multiply Y[m] = u_ell(m) X[m] fused with both untanglings (numpy's hfft = the same operator applied to Y);
+//   4. a second 2048-point complex FFT: xi_grid[2n] = Re g[n] / M, xi_grid[2n+1] = -Im g[n] / M, times s^-q (-1)^(ell/2);
+//   5. un-pad and interpolate linearly onto the requested s (:136).
+// FFT block of ddata at idata[10]: c0[Ng] c1[Ng] u[nell][Np/2+1][2] post[nell][Ng] tw[Np/2][2] outw[nell][ns]   (tw[j] = e^(-2 pi i j / Np))
+// FFT block of idata at idata[11]: j0[Ng] outj[nell][ns]
+// Shared memory: 2048 complex, index i stored at i + (i >> 4) (padding keeps the radix-16 scatter conflict free) + pin[nkin].
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int FFT_THREADS = 256;
+constexpr int FFT_THREADS = 128;
+constexpr int FFT_M = 2048;                                  // complex transform length (Np = 4096)
+__device__ __forceinline__ int fidx(int i) { return i + (i >> 4); }
+constexpr int FFT_SMEM_COMPLEX = FFT_M + (FFT_M >> 4);
 
-__device__ __forceinline__ unsigned bitrev(unsigned x, int bits) { return __brev(x) >> (32 - bits); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+
+// forward 4-point DFT in place: (x0, x1, x2, x3) -> (X0, X1, X2, X3)
+__device__ __forceinline__ void dft4(double2& x0, double2& x1, double2& x2, double2& x3) {
+  const double2 s02 = cadd(x0, x2), d02 = csub(x0, x2), s13 = cadd(x1, x3), d13 = csub(x1, x3);
+  x0 = cadd(s02, s13);
+  x2 = csub(s02, s13);
+  x1 = make_double2(d02.x + d13.y, d02.y - d13.x);   // d02 - i d13
+  x3 = make_double2(d02.x - d13.y, d02.y + d13.x);   // d02 + i d13
+}
+
+// forward 16-point DFT in registers; on return X[k] is in v[(k >> 2) + 4 * (k & 3)]
+__device__ __forceinline__ void dft16(double2 (&v)[16]) {
+  constexpr double C1 = 0.92387953251128673848, S1 = 0.38268343236508978178, H = 0.70710678118654752440;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) dft4(v[b], v[b + 4], v[b + 8], v[b + 12]);   // v[b + 4 q] = I[b][q]
+  // twiddles W16^(b q)
+  v[1 + 4] = cmul(v[1 + 4], make_double2(C1, -S1));      // b=1,q=1 : W^1
+  v[1 + 8] = cmul(v[1 + 8], make_double2(H, -H));        // b=1,q=2 : W^2
+  v[1 + 12] = cmul(v[1 + 12], make_double2(S1, -C1));    // b=1,q=3 : W^3
+  v[2 + 4] = cmul(v[2 + 4], make_double2(H, -H));        // b=2,q=1 : W^2
+  v[2 + 8] = make_double2(v[2 + 8].y, -v[2 + 8].x);      // b=2,q=2 : W^4 = -i
+  v[2 + 12] = cmul(v[2 + 12], make_double2(-H, -H));     // b=2,q=3 : W^6
+  v[3 + 4] = cmul(v[3 + 4], make_double2(S1, -C1));      // b=3,q=1 : W^3
+  v[3 + 8] = cmul(v[3 + 8], make_double2(-H, -H));       // b=3,q=2 : W^6
+  v[3 + 12] = cmul(v[3 + 12], make_double2(-C1, S1));    // b=3,q=3 : W^9
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dft4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);   // v[p + 4 q] = X[q + 4 p]
+}
+
+// forward 8-point DFT in registers; on return X[k] is in v[2 k] (k < 4) and v[2 (k - 4) + 1] (k >= 4)
+__device__ __forceinline__ void dft8(double2 (&v)[8]) {
+  constexpr double H = 0.70710678118654752440;
+  dft4(v[0], v[2], v[4], v[6]);   // v[2 q] = I[0][q]
+  dft4(v[1], v[3], v[5], v[7]);   // v[1 + 2 q] = I[1][q]
+  v[3] = cmul(v[3], make_double2(H, -H));
+  v[5] = make_double2(v[5].y, -v[5].x);
+  v[7] = cmul(v[7], make_double2(-H, -H));
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const double2 a = v[2 * q], b = v[2 * q + 1];
+    v[2 * q] = cadd(a, b);
+    v[2 * q + 1] = csub(a, b);
+  }
+}
+
+// e^(-2 pi i t / 2048) from the table tw[j] = e^(-2 pi i j / 4096), j < 2048
+__device__ __forceinline__ double2 w2048(const double2* __restrict__ tw, int t) {
+  t &= (FFT_M - 1);
+  if (t < FFT_M / 2) return __ldg(&tw[2 * t]);
+  const double2 w = __ldg(&tw[2 * t - FFT_M]);
+  return make_double2(-w.x, -w.y);
+}
+
+// powers w^1 .. w^(R-1) with multiplication depth <= 4 (rounding ~ 4 ulp)
+template <int R>
+__device__ __forceinline__ void twiddle_powers(double2 w1, double2 (&w)[R]) {
+  w[0] = make_double2(1., 0.);
+  w[1] = w1;
+  w[2] = cmul(w1, w1);
+  w[3] = cmul(w[2], w1);
+  w[4] = cmul(w[2], w[2]);
+  w[5] = cmul(w[4], w1);
+  w[6] = cmul(w[4], w[2]);
+  w[7] = cmul(w[4], w[3]);
+  if constexpr (R > 8) {
+    w[8] = cmul(w[4], w[4]);
+#pragma unroll
+    for (int r = 1; r < 8; ++r) w[8 + r] = cmul(w[8], w[r]);
+  }
+}
+
+// passes 2 and 3 of the 2048-point Stockham FFT (pass 1 is done by the caller, which owns the loads); data in D (padded indexing)
+__device__ __forceinline__ void fft2048_tail(double2* D, const double2* __restrict__ tw, int tid) {
+  {  // pass 2: radix 16, Ns = 16
+    const int j = tid, k = j & 15;
+    double2 v[16], w[16];
+    twiddle_powers<16>(w2048(tw, k * 8), w);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = D[fidx(j + r * 128)];
+#pragma unroll
+    for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], w[r]);
+    dft16(v);
+    __syncthreads();
+    const int j0 = (j >> 4) * 256 + k;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) D[fidx(j0 + r * 16)] = v[(r >> 2) + 4 * (r & 3)];
+    __syncthreads();
+  }
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {  // pass 3: radix 8, Ns = 256 (in place: every thread writes where it read)
+    const int k = tid + h * 128;
+    double2 v[8], w[8];
+    twiddle_powers<8>(w2048(tw, k), w);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = D[fidx(k + r * 256)];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], w[r]);
+    dft8(v);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) D[fidx(k + r * 256)] = r < 4 ? v[2 * r] : v[2 * (r - 4) + 1];
+  }
+  __syncthreads();
+}
 
 __global__ void __launch_bounds__(FFT_THREADS) fftlog_kernel(const DevGen g, long long N, double* __restrict__ F, int fstride) {
-  extern __shared__ double2 cdata[];
+  extern __shared__ double2 D[];
   const int nkin = g.idata[0], nell = g.idata[1], ns = g.idata[8], poff = g.idata[12];
   const int Ng = g.idata[13], Np = g.idata[14], padl = g.idata[15];
-  const int bits = 31 - __clz(Np);
+  const int tid = threadIdx.x;
   const long long pt = blockIdx.x;
   const int ell = blockIdx.y;
   double* row = F + pt * fstride + g.foff;
   if (pt >= N) {
-    for (int i = threadIdx.x; i < ns; i += FFT_THREADS) row[2 + ell * ns + i] = 0.;
-    if (ell == 0 && threadIdx.x < 2) row[threadIdx.x] = 0.;
+    for (int i = tid; i < ns; i += FFT_THREADS) row[2 + ell * ns + i] = 0.;
+    if (ell == 0 && tid < 2) row[tid] = 0.;
     return;
   }
-  double* pin = reinterpret_cast<double*>(cdata + Np);
+  double* pin = reinterpret_cast<double*>(D + FFT_SMEM_COMPLEX);
   const double* fd = g.ddata + g.idata[10];
   const int* fi = g.idata + g.idata[11];
-  const double *wgt = fd, *lh = wgt + Ng, *dh = lh + Ng, *pre = dh + Ng;
-  const double2* u = reinterpret_cast<const double2*>(pre + Ng) + (size_t)ell * (Np / 2 + 1);
-  const double* post0 = pre + Ng + (size_t)nell * (Np / 2 + 1) * 2;
-  const double* post = post0 + (size_t)ell * Ng;
-  const double slope_inv = post0[(size_t)nell * Ng];            // followed by one pad double (keeps tw 16-byte aligned)
-  const double2* tw = reinterpret_cast<const double2*>(post0 + (size_t)nell * Ng + 2);
-  const double* outw = post0 + (size_t)nell * Ng + 2 + Np + (size_t)ell * ns;
-  const int* jmap = fi;
+  const double *c0 = fd, *c1 = fd + Ng;
+  const double2* u = reinterpret_cast<const double2*>(fd + 2 * Ng) + (size_t)ell * (Np / 2 + 1);
+  const double* post = fd + 2 * Ng + (size_t)nell * (Np / 2 + 1) * 2 + (size_t)ell * Ng;
+  const double2* tw = reinterpret_cast<const double2*>(fd + 2 * Ng + (size_t)nell * (Np / 2 + 1) * 2 + (size_t)nell * Ng);
+  const double* outw = reinterpret_cast<const double*>(tw + Np / 2) + (size_t)ell * ns;
+  const int* j0tab = fi;
   const int* outj = fi + Ng + ell * ns;
-  for (int i = threadIdx.x; i < nkin; i += FFT_THREADS) pin[i] = row[poff + ell * nkin + i];
+  for (int i = tid; i < nkin; i += FFT_THREADS) pin[i] = row[poff + ell * nkin + i];
   __syncthreads();
-  const double plast = pin[nkin - 1];
-  const double slope = (plast - pin[nkin - 2]) * slope_inv;
-  for (int n = threadIdx.x; n < Np; n += FFT_THREADS) {
-    const int i = n - padl;
-    double v = 0.;
-    if (i >= 0 && i < Ng) {
-      const int j = jmap[i];
-      v = j >= 0 ? pin[j] + wgt[i] * (pin[j + 1] - pin[j]) : (plast + slope * lh[i]) * dh[i];
-      v *= pre[i];
-    }
-    cdata[n] = make_double2(v, 0.);
-  }
-  __syncthreads();
-  // forward DIF: natural order in, bit-reversed order out
-  for (int half = Np >> 1; half >= 1; half >>= 1) {
-    const int tstride = (Np >> 1) / half;
-    for (int b = threadIdx.x; b < (Np >> 1); b += FFT_THREADS) {
-      const int j = b & (half - 1);
-      const int i0 = ((b - j) << 1) + j, i1 = i0 + half;
-      const double2 a = cdata[i0], c = cdata[i1];
-      const double2 w = __ldg(&tw[j * tstride]);
-      const double dr = a.x - c.x, di = a.y - c.y;
-      cdata[i0] = make_double2(a.x + c.x, a.y + c.y);
-      cdata[i1] = make_double2(dr * w.x - di * w.y, dr * w.y + di * w.x);
-    }
+
+  // resampled, pre-factored, zero-padded input sample x[i], i in [0, Np)
+  auto xval = [&](int i) -> double {
+    i -= padl;
+    if (i < 0 || i >= Ng) return 0.;
+    const int j = __ldg(&j0tab[i]);
+    return __ldg(&c0[i]) * pin[j] + __ldg(&c1[i]) * pin[j + 1];
+  };
+
+  {  // forward FFT, pass 1: radix 16, Ns = 1, inputs z[n] = x[2n] + i x[2n+1] built on the fly
+    double2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) { const int n = tid + r * 128; v[r] = make_double2(xval(2 * n), xval(2 * n + 1)); }
+    dft16(v);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) D[fidx(tid * 16 + r)] = v[(r >> 2) + 4 * (r & 3)];
     __syncthreads();
   }
-  // multiply by the kernel u_ell(m); position p holds X[bitrev(p)]
-  for (int p = threadIdx.x; p < Np; p += FFT_THREADS) {
-    const int m = (int)bitrev((unsigned)p, bits);
-    double2 f = m <= (Np >> 1) ? __ldg(&u[m]) : __ldg(&u[Np - m]);
-    if (m > (Np >> 1)) f.y = -f.y;
-    const double2 x = cdata[p];
-    cdata[p] = make_double2(x.x * f.x - x.y * f.y, x.x * f.y + x.y * f.x);
+  fft2048_tail(D, tw, tid);
+
+  // untangle (real-input FFT) -> multiply by u_ell -> tangle (Hermitian -> real inverse), pairs (m, M - m)
+  constexpr int M = FFT_M;
+  auto T = [](double2 a, double2 bconj, double2 e) {   // (a + b*) / 2 - i/2 e (a - b*), with bconj = conj(b)
+    const double2 s = cadd(a, bconj), d = csub(a, bconj);
+    const double2 ed = cmul(e, d);
+    return make_double2(0.5 * (s.x + ed.y), 0.5 * (s.y - ed.x));
+  };
+  for (int m = tid; m <= M / 2; m += FFT_THREADS) {
+    if (m == 0) {
+      const double2 z = D[fidx(0)];
+      const double2 y0 = cmul(__ldg(&u[0]), make_double2(z.x + z.y, 0.));
+      const double2 yM = cmul(__ldg(&u[M]), make_double2(z.x - z.y, 0.));
+      D[fidx(0)] = T(y0, cconj(yM), make_double2(1., 0.));
+    } else if (m == M / 2) {
+      const double2 z = D[fidx(m)];
+      const double2 y = cmul(__ldg(&u[m]), cconj(z));
+      D[fidx(m)] = cconj(y);
+    } else {
+      const double2 za = D[fidx(m)], zb = D[fidx(M - m)];
+      const double2 e = __ldg(&tw[m]);                       // e^(-2 pi i m / Np)
+      const double2 e2 = make_double2(-e.x, e.y);            // e^(-2 pi i (M - m) / Np) = -conj(e)
+      const double2 xa = T(za, cconj(zb), e), xb = T(zb, cconj(za), e2);
+      const double2 ya = cmul(__ldg(&u[m]), xa), yb = cmul(__ldg(&u[M - m]), xb);
+      D[fidx(m)] = T(ya, cconj(yb), e);
+      D[fidx(M - m)] = T(yb, cconj(ya), e2);
+    }
   }
   __syncthreads();
-  // forward DIT: bit-reversed order in, natural order out
-  for (int half = 1; half < Np; half <<= 1) {
-    const int tstride = (Np >> 1) / half;
-    for (int b = threadIdx.x; b < (Np >> 1); b += FFT_THREADS) {
-      const int j = b & (half - 1);
-      const int i0 = ((b - j) << 1) + j, i1 = i0 + half;
-      const double2 a = cdata[i0], c = cdata[i1];
-      const double2 w = __ldg(&tw[j * tstride]);
-      const double tr = c.x * w.x - c.y * w.y, ti = c.x * w.y + c.y * w.x;
-      cdata[i0] = make_double2(a.x + tr, a.y + ti);
-      cdata[i1] = make_double2(a.x - tr, a.y - ti);
-    }
+
+  {  // second FFT, pass 1: radix 16, Ns = 1
+    double2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = D[fidx(tid + r * 128)];
+    dft16(v);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) D[fidx(tid * 16 + r)] = v[(r >> 2) + 4 * (r & 3)];
     __syncthreads();
   }
-  const double invn = 1. / (double)Np;
+  fft2048_tail(D, tw, tid);
+
+  const double invm = 1. / (double)M;
   const int padout = Np - Ng - padl;   // pad_out_left = npad - npad // 2
-  for (int i = threadIdx.x; i < ns; i += FFT_THREADS) {
+  auto grid = [&](int j) -> double {   // xi on the FFTLog output grid, index j in [0, Ng)
+    const int t = j + padout;
+    const double2 gq = D[fidx(t >> 1)];
+    return ((t & 1) ? -gq.y : gq.x) * invm * __ldg(&post[j]);
+  };
+  for (int i = tid; i < ns; i += FFT_THREADS) {
     const int j = outj[i];
-    const double x0 = cdata[j + padout].x * invn * post[j], x1 = cdata[j + 1 + padout].x * invn * post[j + 1];
+    const double x0 = grid(j), x1 = grid(j + 1);
     row[2 + ell * ns + i] = x0 + outw[i] * (x1 - x0);
   }
-  if (ell == 0 && threadIdx.x == 0) { row[0] = 1.; row[1] = 0.; }
+  if (ell == 0 && tid == 0) { row[0] = 1.; row[1] = 0.; }
 }
 
 }  // namespace
@@ -373,7 +503,8 @@ int launch_theory_features(const DevGen& g, const double* params, int d, long lo
     DLB_CUDA(cudaGetLastError());
     if (g.aux[4] & 2) {   // flags bit 1: P -> xi through FFTLog
       const int Np = g.aux[5], nkin = g.aux[2], nell = g.aux[3];
-      const size_t smem = (size_t)Np * sizeof(double2) + (size_t)((nkin + 1) & ~1) * sizeof(double);
+      if (Np != 2 * FFT_M) { set_error("FFTLog kernel is specialised for the reference's 2048-point grid padded to 4096"); return DLB_ERR_UNSUPPORTED; }
+      const size_t smem = (size_t)FFT_SMEM_COMPLEX * sizeof(double2) + (size_t)((nkin + 1) & ~1) * sizeof(double);
       static size_t configured = 0;
       if (smem > 48 * 1024 && smem > configured) {
         DLB_CUDA(cudaFuncSetAttribute(fftlog_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

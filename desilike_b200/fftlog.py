@@ -55,7 +55,13 @@ def fftlog_constants(kin, ells, s_out, ng=2048, kmin=1e-4, kmax=1e3, q=0., minfo
         outw.append((s_out - s[jj]) / (s[jj + 1] - s[jj]))
         s_grids.append(s)
     tw = np.exp(-2j * np.pi * np.arange(npad_size // 2) / npad_size)
-    ddata = np.concatenate([wgt, lh, dh, pre, np.array(u).ravel(), np.array(post).ravel(), [slope_inv, 0.],
+    # interpolation and extrapolation as ONE 2-point rule  x[i] = c0[i] pin[j0[i]] + c1[i] pin[j0[i] + 1]  (prefactor folded in):
+    #   k <= kin[-1]:  (1 - wgt) pin[j] + wgt pin[j + 1]
+    #   k >  kin[-1]:  (pin[-1] + (pin[-1] - pin[-2]) slope_inv lh) dh
+    j0 = np.where(mask, kin.size - 2, jmap).astype(np.int32)
+    c0 = np.where(mask, -slope_inv * lh * dh, 1. - wgt) * pre
+    c1 = np.where(mask, (1. + slope_inv * lh) * dh, wgt) * pre
+    ddata = np.concatenate([c0, c1, np.array(u).ravel(), np.array(post).ravel(),
                             np.stack([tw.real, tw.imag], axis=-1).ravel(), np.array(outw).ravel()])
-    idata = np.concatenate([jmap, np.array(outj).ravel()]).astype(np.int32)
+    idata = np.concatenate([j0, np.array(outj).ravel()]).astype(np.int32)
     return dict(ddata=ddata, idata=idata, ng=ng, npad_size=npad_size, pad_in_left=pad_in_left, pad_out_left=pad_out_left, k=k, s=np.array(s_grids))

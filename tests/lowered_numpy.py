@@ -157,22 +157,20 @@ def theory_features(ig, gen, Xe):
         return out
     ns, off_d, off_i, Ng, Np, padl = idata[8], idata[10], idata[11], idata[13], idata[14], idata[15]
     fd, fi = dd[off_d:], idata[off_i:]
-    wgt, lh, dh, pre = (fd[i * Ng:(i + 1) * Ng] for i in range(4)); o = 4 * Ng
+    c0, c1 = (fd[i * Ng:(i + 1) * Ng] for i in range(2)); o = 2 * Ng
     nu = Np // 2 + 1
     u = fd[o:o + nell * nu * 2].reshape(nell, nu, 2); o += nell * nu * 2
     u = u[..., 0] + 1j * u[..., 1]
     post = fd[o:o + nell * Ng].reshape(nell, Ng); o += nell * Ng
-    slope_inv = fd[o]; o += 2 + Np
+    o += Np   # twiddle table e^(-2 pi i j / Np), j < Np / 2
     outw = fd[o:o + nell * ns].reshape(nell, ns)
-    jmap, outj = fi[:Ng], fi[Ng:Ng + nell * ns].reshape(nell, ns)
+    j0, outj = fi[:Ng], fi[Ng:Ng + nell * ns].reshape(nell, ns)
     out = np.zeros((N, gen.nfeat)); out[:, 0] = 1.
     padout = Np - Ng - padl
     for ip in range(N):
         for ell in range(nell):
             pin = power[ip, ell]
-            slope = (pin[-1] - pin[-2]) * slope_inv
-            jj = np.maximum(jmap, 0)
-            v = np.where(jmap >= 0, pin[jj] + wgt * (pin[np.minimum(jj + 1, nk - 1)] - pin[jj]), (pin[-1] + slope * lh) * dh) * pre
+            v = c0 * pin[j0] + c1 * pin[j0 + 1]   # interpolation / extrapolation as one 2-point rule, prefactor folded in
             x = np.zeros(Np); x[padl:padl + Ng] = v
             X = np.fft.fft(x)
             m = np.arange(Np)
