@@ -31,6 +31,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = 'logL evals/sec (batched, emulated FS+window+chi2)'
+# algorithmic FLOP per evaluation of the UN-collapsed chain
+UNCOLLAPSED_FLOPS = {'c1': 0.1e6, 'c2': 0.7e6, 'c3': 1.3e6, 'c4': 20e6, 'c5': 8e6, 'c5solved': 19e6}
 UNIT = 'evals/s'
 
 
@@ -174,6 +176,7 @@ def main():
                 logprior=torch.empty(N, dtype=torch.float64, device=dev), status=torch.empty(N, dtype=torch.int32, device=dev))
     if plan.ns: outs['x_solved_plan_order'] = torch.empty((N, plan.ns), dtype=torch.float64, device=dev)
     gathered = torch.empty(world * N, dtype=torch.float64, device=dev) if world > 1 else None
+    if world > 1: outs['logposterior'] = gathered[rank * N:(rank + 1) * N]   # the finish kernel writes straight into the all-gather buffer (in-place collective)
 
     def step(i):
         plan.eval(pool[i % npool], out=outs)
@@ -235,28 +238,57 @@ def main():
     h2d = N * d * 8
     d2h = N * (3 * 8 + 4) + (N * plan.ns * 8 if plan.ns else 0)
 
-    # ---- roofline of the dominant kernel (contraction), timed live with CUDA events on the launching stream ----
+    # ---- roofline of the dominant kernel, timed live with CUDA events on the launching stream ----
     flops = plan.lowered.flops_per_point()
     plan.set_timing(True)
-    tms = {'features': [], 'contract': [], 'solve': []}
+    tms = {'features': [], 'contract': [], 'solve': [], 'fftlog': []}
     for i in range(max(5, min(args.steps, 30))):
         plan.eval(pool[i % npool], out=outs)
         for k, v in plan.last_kernel_ms().items(): tms[k].append(v)
     plan.set_timing(False)
-    contract_ms = float(np.mean(tms['contract'][2:]))
-    nlaunch_contract = 1   # one persistent launch covers all blocks
-    peak = desilike_b200.measure_fp64_peak('dmma')
-    achieved = (flops['contract'] + flops['gram']) * N / (contract_ms * 1e-3) / 1e12
+    phase = {k: float(np.mean(v[2:])) for k, v in tms.items()}
+    step_ms = phase['features'] + phase['contract'] + phase['solve']
+    peak_dmma = desilike_b200.measure_fp64_peak('dmma')
     traffic = None
     prof = os.path.join(ROOT, 'profiles', 'traffic_{}.json'.format(args.workload))
     if os.path.exists(prof):
         try: traffic = json.load(open(prof)).get('dram_bytes_per_launch')
         except Exception: traffic = None
-    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
-                'kernel': 'dlb::contract_kernel (FP64 DMMA.8x8x4)', 'launches_per_step': nlaunch_contract, 'ms_per_step_in_kernel': contract_ms,
-                'flops_per_eval_folded': flops, 'peak_source': 'dlb_measure_fp64_peak(DMMA.8x8x4 register loop) measured in this run; MEASURED_PEAKS.json has no FP64 entry',
-                'share_of_step': contract_ms / (float(np.mean(tms['features'][2:])) + contract_ms + float(np.mean(tms['solve'][2:]))),
-                'phase_ms': {k: float(np.mean(v[2:])) for k, v in tms.items()}}
+    uncollapsed = UNCOLLAPSED_FLOPS.get(args.workload)
+    if args.workload == 'c3':
+        # dominant kernel: FFTLog (one CTA per point and multipole; FP64 FMA pipe + shared-memory passes).  Algorithmic work =
+        # n_ell (2 * 2.5 Np log2 Np + 6 Np) FLOP per evaluation with Np = 4096.
+        nell, Np = 2, 4096
+        fft_flops = nell * (2 * 2.5 * Np * np.log2(Np) + 6 * Np)
+        peak = desilike_b200.measure_fp64_peak('dfma')
+        achieved = fft_flops * N / (phase['fftlog'] * 1e-3) / 1e12
+        roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
+                    'kernel': 'dlb::fftlog_kernel (FP64 FMA pipe, radix 16x16x8 passes in shared memory)', 'launches_per_step': 1,
+                    'ms_per_step_in_kernel': phase['fftlog'], 'flops_per_eval': {'fftlog': fft_flops},
+                    'peak_source': 'dlb_measure_fp64_peak(DFMA register loop) measured in this run (no tensor-core FP64 FFT path); MEASURED_PEAKS.json has no FP64 entry',
+                    'share_of_step': phase['fftlog'] / step_ms, 'phase_ms': phase}
+    elif args.workload == 'c1':
+        # dominant kernel: Kaiser + ShapeFit + AP (one warp per point).  Algorithmic work = SURVEY.md section 8d:
+        # Nkin * nmu * 60 + 500 * (exp, tanh) ~ 0.05 MFLOP per evaluation (special functions at ~30 FLOP each).
+        kaiser_flops = 36 * 8 * 60 + 500 * 2 * 30
+        peak = desilike_b200.measure_fp64_peak('dfma')
+        achieved = kaiser_flops * N / (phase['features'] * 1e-3) / 1e12
+        roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
+                    'kernel': 'dlb::kaiser_kernel (FP64 FMA pipe; spline + Gauss-Legendre quadrature, one warp per point)', 'launches_per_step': 1,
+                    'ms_per_step_in_kernel': phase['features'], 'flops_per_eval': {'kaiser': kaiser_flops},
+                    'peak_source': 'dlb_measure_fp64_peak(DFMA register loop) measured in this run; MEASURED_PEAKS.json has no FP64 entry',
+                    'share_of_step': phase['features'] / step_ms, 'phase_ms': phase}
+    else:
+        contract_ms = phase['contract']
+        achieved = (flops['contract'] + flops['gram']) * N / (contract_ms * 1e-3) / 1e12
+        roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak_dmma, 'unit': 'TFLOP/s', 'frac': achieved / peak_dmma, 'traffic': traffic,
+                    'kernel': 'dlb::contract_kernel (FP64 DMMA.8x8x4, persistent, one launch per likelihood)', 'launches_per_step': 1,
+                    'ms_per_step_in_kernel': contract_ms, 'flops_per_eval_folded': flops,
+                    'peak_source': 'dlb_measure_fp64_peak(DMMA.8x8x4 register loop) measured in this run; MEASURED_PEAKS.json has no FP64 entry',
+                    'share_of_step': contract_ms / step_ms, 'phase_ms': phase}
+    if uncollapsed:   # the reference's un-collapsed chain: what the same evaluations cost without plan-time folding
+        roofline['flops_per_eval_uncollapsed'] = uncollapsed
+        roofline['achieved_uncollapsed_equivalent'] = uncollapsed * value / 1e12
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',

@@ -64,6 +64,7 @@ SYMBOLS = {
     'dlb_measure_fp64_peak': (ctypes.c_int, [ctypes.c_int32, c_double_p]),
     'dlb_last_kernel_ms': (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_double_p]),
     'dlb_set_timing': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
+    'dlb_last_fftlog_ms': (ctypes.c_int, [c_double_p]),
 }
 
 _lib = None
@@ -77,10 +78,11 @@ def load():
     """Load the shared library (built by ``desilike_b200.build.build()``); raise if it is missing -- no fallback."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIBPATH):
+        libpath = os.environ.get('DESILIKE_B200_LIB', LIBPATH)   # override: e.g. a -DDLB_PROFILE build of the same sources
+        if not os.path.exists(libpath):
             raise DesilikeB200Error('{} not found: run `python -m desilike_b200.build` (or __graft_entry__.build()); '
-                                    'desilike_b200 has no CPU fallback'.format(LIBPATH))
-        lib = ctypes.CDLL(LIBPATH)
+                                    'desilike_b200 has no CPU fallback'.format(libpath))
+        lib = ctypes.CDLL(libpath)
         for name, (restype, argtypes) in SYMBOLS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = restype, argtypes

@@ -17,6 +17,8 @@ namespace dlb {
 // ---------------------------------------------------------------------------------------------------------------------
 void set_error(const std::string& msg);
 extern std::atomic<long long> g_launches;
+extern std::atomic<bool> g_timing;     // per-kernel CUDA-event timing requested (dlb_set_timing)
+int last_fftlog_ms(double* ms);
 
 #define DLB_CUDA(call)                                                                                      \
   do {                                                                                                      \
@@ -62,8 +64,8 @@ constexpr int MAXP = 16;  // max input parameters of one generator
 
 struct GenDev {       // Taylor generator constants for the in-kernel monomial evaluation (resident A)
   int nparams, maxdeg;
-  int pidx[MAXP];
-  double center[MAXP], pdef[MAXP];
+  double cval[MAXP + 2];   // subtracted from the factor's parameter column: center_j; [MAXP] = 0 (absent factor: column "one" - 0);
+                           // fixed parameters use the constant-one column with cval = 1 - (default_j - center_j)
 };
 
 struct BlockDev {     // one output block as seen by the contraction kernel (device table)
@@ -71,7 +73,9 @@ struct BlockDev {     // one output block as seen by the contraction kernel (dev
   const double* tiles;                 // [ncb][nchunks][BN][KC] pre-tiled term matrices (n-major, zero padded)
   const double* epi;                   // [ncb][nconst + 1][BN] epilogue constants per column block: constant whitened Jacobian rows,
                                        // then r0 (subtracted from slot 0 in eval mode / added in output mode)
-  const unsigned long long* paths;     // [ast] monomial factor lists of the block's Taylor generator (resident A), else NULL
+  const unsigned long long* paths;     // [ast][2] monomial factor lists of the block's Taylor generator (resident A), else NULL:
+                                       // word 0: byte k = parameter-tile column of factor k (top byte 0xFF: structural zero column),
+                                       // word 1: byte k = index into GenDev::cval
   long long poff;                      // first Gram-partial row of the block: partial[(poff + e) * npad + point]
   int nchunks, ncb, nslots, nconst, npart, ncols, ocol0, gen;
   int fill, fbase, acols;              // resident A: 0 = evaluate Taylor monomials, 1 = copy acols columns of F from column fbase
@@ -79,8 +83,15 @@ struct BlockDev {     // one output block as seen by the contraction kernel (dev
 
 struct DevCoef { double scale; int nf; int idx[DLB_COEF_MAXF]; int pow[DLB_COEF_MAXF]; };
 
+struct SchedEntry {   // one TMA transaction of the per-tile chunk sequence (k-chunks and epilogue constants of every block / column block)
+  const double* src;
+  unsigned bytes;
+  int chunk;          // streaming A: index of the chunk in its block (-1 for epilogue constants), block in the high 16 bits
+};
+
 struct ContractParams {
   const BlockDev* blocks; int nblocks;
+  const SchedEntry* sched; int nsched;
   const GenDev* gens; int ngen;
   const DevCoef* coefs; int ncoef;
   const double* params; int d; long long N;
@@ -91,6 +102,7 @@ struct ContractParams {
   int mode;                              // 0 eval (Gram partials), 1 output (theory vectors / MLP layer)
   int nstages, resident, ast, dpad, npart_max;
   long long U;                           // number of row units (variant_unit rows each) to process
+  long long* prof;                       // DLB_PROFILE builds: 8 cycle counters (summed over warps)
 };
 
 size_t contract_smem_limit(int ctas_per_sm);

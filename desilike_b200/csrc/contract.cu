@@ -111,8 +111,8 @@ __device__ __forceinline__ void mma_chunk_dispatch(double (&acc)[MT][NT][2], con
 // Position in the CTA's chunk sequence (tile, block, column block, chunk); chunk == nchunks is the epilogue-constants chunk.
 // Lives in shared memory: only warp 0 (the warp that re-arms the TMA ring) touches it.
 struct Cursor {
-  long long u;
-  int b, cb, c, nchunks, ncb, done, pad;
+  long long u;     // first unit of the tile being loaded
+  int q, done;     // index into the per-tile TMA schedule
 };
 
 // barrier over the two warps (wn = 0, 1) that share a set of rows: everything a warp pair needs between the TMA ring and
@@ -125,6 +125,16 @@ __device__ __forceinline__ unsigned atom_add_acq_rel(unsigned* addr, unsigned v)
   asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
   return old;
 }
+
+#ifdef DLB_PROFILE
+#define PROF_DECL long long prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long prof_c = clock64();
+#define PROF(i) { const long long t_ = clock64(); prof_t[i] += t_ - prof_c; prof_c = t_; }
+#define PROF_FLUSH if (lane == 0 && p.prof) { for (int i_ = 0; i_ < 8; ++i_) atomicAdd((unsigned long long*)p.prof + i_, (unsigned long long)prof_t[i_]); }
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_FLUSH
+#endif
 
 template <int R, int MT, int NT, int WM, int CPS, bool RESIDENT>
 __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_constant__ ContractParams p) {
@@ -158,8 +168,7 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); cnt[s] = 0u; }
     for (int i = 0; i < WM; ++i) mbar_init(&abar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    cur->u = u0; cur->b = 0; cur->cb = 0; cur->c = 0; cur->done = 0;
-    cur->nchunks = p.blocks[0].nchunks; cur->ncb = p.blocks[0].ncb;
+    cur->u = u0; cur->q = 0; cur->done = 0;
   }
   if constexpr (RESIDENT) {
     for (int i = tid; i < p.ngen * (int)(sizeof(GenDev) / 4); i += NTH) reinterpret_cast<int*>(gens_s)[i] = reinterpret_cast<const int*>(p.gens)[i];
@@ -177,53 +186,48 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
   load_params(u0, tile_units(u0), xs0);
   __syncthreads();
 
-  // ---- TMA ring: stage rs has been released by every warp (or is fresh); load the next chunk of the sequence into it.
-  //      Executed by one whole warp (the last one to release the stage); sequence state lives in shared memory. ----
+  // ---- TMA ring: stage rs has been released by every warp (or is fresh); load the next transaction of the sequence into it.
+  //      Executed by one whole warp (the last one to release the stage); the sequence position lives in shared memory and the
+  //      per-tile schedule (source pointer + bytes of every k-chunk / epilogue-constants tile) is a plan-time table. ----
   auto refill = [&](int rs) {
     if (cur->done) return;
-    const int c = cur->c, nchunks = cur->nchunks, cb = cur->cb;
-    const BlockDev* blk = p.blocks + cur->b;
+    const int q = cur->q;
+    const long long cu = cur->u;
     double* dst = stage_base + (size_t)rs * STAGE_DOUBLES;
-    if (c == nchunks) {   // epilogue constants of this column block: [nconst + 1][BN]
-      const int nrow = blk->nconst + 1;
+    const SchedEntry* e = p.sched + q;
+    if constexpr (RESIDENT) {
       if (lane == 0) {
-        mbar_arrive_expect_tx(&full[rs], (uint32_t)(nrow * BN * 8));
-        tma_bulk_g2s(dst, blk->epi + (size_t)cb * nrow * BN, nrow * BN * 8, &full[rs]);
+        const int4 ev = __ldg(reinterpret_cast<const int4*>(e));
+        const double* src = reinterpret_cast<const double*>(((unsigned long long)(unsigned)ev.y << 32) | (unsigned)ev.x);
+        mbar_arrive_expect_tx(&full[rs], (unsigned)ev.z);
+        tma_bulk_g2s(dst, src, (unsigned)ev.z, &full[rs]);
       }
     } else {
-      const double* src = blk->tiles + ((size_t)cb * nchunks + c) * (BN * KC);
-      if constexpr (RESIDENT) {
-        if (lane == 0) {
-          mbar_arrive_expect_tx(&full[rs], (uint32_t)(BN * KC * 8));
-          tma_bulk_g2s(dst, src, BN * KC * 8, &full[rs]);
-        }
+      const int4 ev = __ldg(reinterpret_cast<const int4*>(e));
+      const double* src = reinterpret_cast<const double*>(((unsigned long long)(unsigned)ev.y << 32) | (unsigned)ev.x);
+      if (ev.w < 0) {   // epilogue constants
+        if (lane == 0) { mbar_arrive_expect_tx(&full[rs], (unsigned)ev.z); tma_bulk_g2s(dst, src, (unsigned)ev.z, &full[rs]); }
       } else {
-        const int4 ch = __ldg(reinterpret_cast<const int4*>(blk->chunks + c));   // slot, coef, fcol, kc
-        const long long cu = cur->u;
+        const BlockDev* blk = p.blocks + (ev.w >> 16);
+        const int4 ch = __ldg(reinterpret_cast<const int4*>(blk->chunks + (ev.w & 0xFFFF)));   // slot, coef, fcol, kc
         const int h = UNIT * tile_units(cu);
         if (lane == 0) {
-          mbar_arrive_expect_tx(&full[rs], (uint32_t)(h * ch.w * 8 + BN * KC * 8));
-          tma_bulk_g2s(dst, src, BN * KC * 8, &full[rs]);
+          mbar_arrive_expect_tx(&full[rs], (uint32_t)(h * ch.w * 8) + (unsigned)ev.z);
+          tma_bulk_g2s(dst, src, (unsigned)ev.z, &full[rs]);
         }
         __syncwarp();
         const double* Fsrc = p.F + cu * UNIT * p.fstride + ch.z;
         for (int r = lane; r < h; r += 32) tma_bulk_g2s(dst + BN * KC + r * KC, Fsrc + (size_t)r * p.fstride, ch.w * 8, &full[rs]);
       }
     }
-    __syncwarp();
     if (lane == 0) {   // advance
-      if (++cur->c > nchunks) {
-        cur->c = 0;
-        if (++cur->cb == cur->ncb) {
-          cur->cb = 0;
-          if (++cur->b == p.nblocks) {
-            cur->b = 0;
-            cur->u += tile_units(cur->u);
-            if (cur->u >= u1) cur->done = 1;
-          }
-          cur->nchunks = p.blocks[cur->b].nchunks; cur->ncb = p.blocks[cur->b].ncb;
-        }
-      }
+      if (q + 1 == p.nsched) {
+        cur->q = 0;
+        const long long nu = cu + tile_units(cu);
+        cur->u = nu;
+        if (nu >= u1) cur->done = 1;
+      } else cur->q = q + 1;
+      __threadfence_block();   // publish the position before this thread's next stage-release count
     }
     __syncwarp();
   };
@@ -231,12 +235,13 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
   auto release = [&](int rs) {
     __syncwarp();
     int last = 0;
-    if (lane == 0) {
-      last = atom_add_acq_rel(&cnt[rs], 1u) == (unsigned)(NW - 1);
-      if (last) cnt[rs] = 0u;
-    }
+    if (lane == 0) last = atomicAdd(&cnt[rs], 1u) == (unsigned)(NW - 1);
     last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) refill(rs);
+    if (last) {
+      if (lane == 0) { cnt[rs] = 0u; __threadfence_block(); }
+      __syncwarp();
+      refill(rs);
+    }
   };
   if (warp == 0)
     for (int i = 0; i < S; ++i) refill(i);
@@ -244,12 +249,14 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
   const int npm = p.npart_max;
   int s = 0, xbuf = 0;
   uint32_t ph = 0, aph = 0;
+  PROF_DECL
   for (long long u = u0; u < u1;) {
     const int mtc = tile_units(u);
     const long long row0 = u * UNIT;
     double* xs = xs0 + (size_t)xbuf * BM * p.dpad;
     cp_async_wait_all();
     pair_barrier(wm);   // this tile's parameter rows have landed; the pair has completely finished its previous tile
+    PROF(5)
     if (u + mtc < u1) load_params(u + mtc, tile_units(u + mtc), xs0 + (size_t)(xbuf ^ 1) * BM * p.dpad);
     xbuf ^= 1;
     // ---- bias monomials c = scale * prod_f theta[idx_f]^pow_f (tracer combine, reference full_shape.py:545-550) ----
@@ -270,7 +277,9 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
       const BlockDev* blk = p.blocks + b;
       const int nchunks = blk->nchunks, ncb = blk->ncb, npart = blk->npart, Rb = blk->nslots, nconst = blk->nconst;
       const Chunk* chunks = blk->chunks;
+      PROF(5)
       if (b > 0) pair_barrier(wm);   // the pair's flush of the previous block is done and both warps finished reading their A rows
+      PROF(5)
       if (RESIDENT && blk->fill == 1) {
         // ---- resident A rows = this block's generator segment of the feature matrix (MLP activations, ...): one TMA row copy
         //      per point, once per (tile, block) ----
@@ -292,30 +301,28 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
         const int maxdeg = g->maxdeg;
         for (int j0 = 0; j0 < p.ast; j0 += 32) {
           const int j = j0 + lane;
-          const unsigned long long path = j < p.ast ? __ldg(blk->paths + j) : 0xFF00000000000000ull;
-          int col[7];
-          double ck[7];
-#pragma unroll
-          for (int k = 0; k < 7; ++k) {
-            const int v = (int)((path >> (8 * k)) & 0xFFull);
-            col[k] = p.d; ck[k] = 0.;
-            if (k < maxdeg && v) {
-              const int pc = g->pidx[v - 1];
-              if (pc >= 0) { col[k] = pc; ck[k] = g->center[v - 1]; }
-              else ck[k] = 1. - (g->pdef[v - 1] - g->center[v - 1]);
-            }
-          }
-          const bool zero = (path >> 56) != 0ull;
           if (j < p.ast) {
-#pragma unroll 4
-            for (int rr = wn; rr < mtc * 8; rr += 2) {
-              const int r = (rr >> 3) * UNIT + wm * 8 + (rr & 7);
-              const double* xr = xs + (size_t)r * p.dpad;
-              double m = xr[col[0]] - ck[0];
+            const ulonglong2 fw = __ldg(reinterpret_cast<const ulonglong2*>(blk->paths) + j);
+            int col[7];
+            double ck[7];
 #pragma unroll
-              for (int k = 1; k < 7; ++k)
-                if (k < maxdeg) m *= xr[col[k]] - ck[k];
-              A_s[(size_t)r * p.ast + j] = zero ? 0. : m;
+            for (int k = 0; k < 7; ++k) {
+              col[k] = (int)((fw.x >> (8 * k)) & 0xFFull);
+              ck[k] = g->cval[(fw.y >> (8 * k)) & 0xFFull];
+            }
+            const bool zero = (fw.x >> 56) != 0ull;
+            for (int mt = 0; mt < mtc; ++mt) {
+              const double* xb = xs + (size_t)(mt * UNIT + wm * 8 + wn) * p.dpad;
+              double* ab = A_s + (size_t)(mt * UNIT + wm * 8 + wn) * p.ast + j;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {   // rows wn, wn + 2, wn + 4, wn + 6 of this pair's 8-row strip
+                const double* xr = xb + (size_t)(2 * i) * p.dpad;
+                double m = xr[col[0]] - ck[0];
+#pragma unroll
+                for (int k = 1; k < 7; ++k)
+                  if (k < maxdeg) m *= xr[col[k]] - ck[k];
+                ab[(size_t)(2 * i) * p.ast] = zero ? 0. : m;
+              }
             }
           }
         }
@@ -324,7 +331,9 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
         for (int mt = 0; mt < mtc; ++mt)
           for (int i = lane; i < 8 * npart; i += 32) red[((size_t)wn * BM + mt * UNIT + wm * 8 + i / npart) * npm + (i % npart)] = 0.;
       }
+      PROF(2)
       pair_barrier(wm);
+      PROF(5)
 
       int4 ch_next = __ldg(reinterpret_cast<const int4*>(chunks));   // slot, coef, fcol, kc (prefetched one chunk ahead)
       for (int cb = 0; cb < ncb; ++cb) {
@@ -342,7 +351,9 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
           double beta[MT];
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) beta[mt] = ch.y >= 0 ? cs[ch.y * BM + mt * UNIT + wm * 8 + lr] : 1.;
+          PROF(3)
           mbar_wait(&full[s], ph);
+          PROF((c == 0 ? (cb == 0 ? 1 : 7) : 4))
           const double* Bp = stage_base + (size_t)s * STAGE_DOUBLES + (wn * (NT * 8) + lr) * KC + lc;
           const double* Ap;
           int astride;
@@ -352,13 +363,16 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
 #pragma unroll
           for (int sl = 0; sl < R; ++sl)
             if (ch.x == sl) mma_chunk_dispatch<MT, NT>(acc[sl], Ap, astride, Bp, beta, nk4, mtc);
+          PROF(3)
           release(s);
+          PROF(5)
           if (++s == S) { s = 0; ph ^= 1; }
         }
 
         // ===== epilogue: constants of this column block arrive as one more chunk: rows [0, nconst) = constant whitened
         //       Jacobian rows, row nconst = r0 =====
         mbar_wait(&full[s], ph);
+        PROF(0)
         const int colw = wn * (NT * 8) + 2 * lc;  // + nt * 8 + e
         const double* epi = stage_base + (size_t)s * STAGE_DOUBLES;
         const double* r0 = epi + (size_t)nconst * BN;
@@ -431,12 +445,15 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
             }
           }
         }
+        PROF(6)
         release(s);
+        PROF(5)
         if (++s == S) { s = 0; ph ^= 1; }
       }  // cb
 
       if (p.mode == 0) {
         pair_barrier(wm);   // both warps' contributions are in their Gram copies
+        PROF(5)
         double* out = p.partial + blk->poff * p.npad + row0;
         for (int i = ptid; i < mtc * 8 * npart; i += 64) {
           const int e = i / (mtc * 8), rr = i - e * (mtc * 8);
@@ -444,9 +461,11 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
           out[(long long)e * p.npad + r] = red[(size_t)r * npm + e] + red[((size_t)BM + r) * npm + e];
         }
       }
+      PROF(5)
     }  // blocks
     u += mtc;
   }    // tiles
+  PROF_FLUSH
 }
 
 template <int R, int MT, int NT, int WM, int CPS, bool RESIDENT>

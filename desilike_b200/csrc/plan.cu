@@ -6,6 +6,8 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <cstdio>
+#include <cstdlib>
 
 namespace dlb {
 
@@ -28,6 +30,8 @@ struct Launch {
   Variant var;
   int nblocks = 0, nstages = 2, resident = 0, ast = 0, npart_max = 1;
   BlockDev *d_white = nullptr, *d_plain = nullptr;
+  SchedEntry *d_sched_white = nullptr, *d_sched_plain = nullptr;   // per-tile TMA schedule
+  int nsched = 0;
 };
 
 struct MlpLayers { int act = 0; std::vector<Block> layers; std::vector<Launch> launches; };
@@ -220,7 +224,7 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
     for (int s = 3; s >= 2; --s)
       if (contract_smem_bytes(v2, s, resident, L.ast, plan->dpad, ncoef, L.npart_max, plan->ngen) <= contract_smem_limit(2)) { L.var = v2; L.nstages = s; break; }
   }
-  for (int s = 4; s >= 2 && !L.nstages; --s)
+  for (int s = 8; s >= 2 && !L.nstages; --s)
     if (contract_smem_bytes(L.var, s, resident, L.ast, plan->dpad, ncoef, L.npart_max, plan->ngen) <= contract_smem_limit(1)) { L.nstages = s; break; }
   DLB_REQUIRE(L.nstages >= 2, "contraction launch needs too much shared memory (too many parameters, coefficients or solved templates)");
   for (int pass = 0; pass < 2; ++pass) {
@@ -238,6 +242,20 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
     }
     if (!ok) continue;
     DLB_TRY(upload(plan, tab.data(), tab.size(), pass == 0 ? &L.d_white : &L.d_plain));
+    // per-tile TMA schedule: for every block, column block: the k-chunk tiles in order, then the epilogue constants
+    const int BN = variant_bn(L.var);
+    std::vector<SchedEntry> sched;
+    for (size_t ib = 0; ib < blocks.size(); ++ib) {
+      const Block* b = blocks[ib];
+      DLB_REQUIRE(b->nchunks < 65536 && blocks.size() < 32768, "too many chunks / blocks in one launch");
+      for (int cb = 0; cb < b->ncb; ++cb) {
+        for (int c = 0; c < b->nchunks; ++c)
+          sched.push_back(SchedEntry{tab[ib].tiles + ((size_t)cb * b->nchunks + c) * ((size_t)BN * KC), (unsigned)(BN * KC * 8), (int)((ib << 16) | (unsigned)c)});
+        sched.push_back(SchedEntry{tab[ib].epi + (size_t)cb * (b->nconst + 1) * BN, (unsigned)((b->nconst + 1) * BN * 8), -1});
+      }
+    }
+    L.nsched = (int)sched.size();
+    DLB_TRY(upload(plan, sched.data(), sched.size(), pass == 0 ? &L.d_sched_white : &L.d_sched_plain));
   }
   return DLB_OK;
 }
@@ -321,7 +339,7 @@ static int run_front(dlb_plan* plan, const double* d_params, long long N, long l
       for (const Launch& L : plan->mlps[ig].launches) {
         ContractParams cp;
         fill_params(plan, L, cp, d_params, N, npad);
-        cp.blocks = L.d_plain; cp.ncoef = 0;
+        cp.blocks = L.d_plain; cp.sched = L.d_sched_plain; cp.nsched = L.nsched; cp.ncoef = 0;
         cp.out = plan->w_F; cp.ostride = plan->fstride; cp.out_rows = npad; cp.act = plan->mlps[ig].act; cp.mode = 1;
         cp.U = npad / variant_unit(L.var);
         DLB_TRY(launch_contract(L.var, cp, plan->nsm, stream));
@@ -339,10 +357,26 @@ static int run_contract(dlb_plan* plan, const double* d_params, long long N, lon
   ContractParams cp;
   fill_params(plan, L, cp, d_params, N, npad);
   cp.blocks = mode == 0 ? L.d_white : L.d_plain;
+  cp.sched = mode == 0 ? L.d_sched_white : L.d_sched_plain; cp.nsched = L.nsched;
   if (!cp.blocks) { set_error("plan was built without un-whitened matrices: theory_batch unavailable"); return DLB_ERR_ARG; }
   cp.out = d_theory; cp.ostride = plan->ntheory; cp.out_rows = N; cp.act = 0; cp.mode = mode;
   cp.U = (N + variant_unit(L.var) - 1) / variant_unit(L.var);
+#ifdef DLB_PROFILE
+  static long long* d_prof = nullptr;
+  if (!d_prof) { cudaMalloc((void**)&d_prof, 8 * sizeof(long long)); }
+  cudaMemsetAsync(d_prof, 0, 8 * sizeof(long long), stream);
+  cp.prof = d_prof;
+  int rc = launch_contract(L.var, cp, plan->nsm, stream);
+  long long h[8];
+  cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+  long long tot = 0; for (int i = 0; i < 8; ++i) tot += h[i];
+  if (getenv("DLB_PROFILE_PRINT") && tot > 0)
+    fprintf(stderr, "[prof] wait-epi-chunk %.1f%% wait-first-of-block %.1f%% agen %.1f%% mma %.1f%% wait-other %.1f%% release+barriers+setup+flush %.1f%% epilogue %.1f%% wait-first-of-cb %.1f%%\n",
+            100. * h[0] / tot, 100. * h[1] / tot, 100. * h[2] / tot, 100. * h[3] / tot, 100. * h[4] / tot, 100. * h[5] / tot, 100. * h[6] / tot, 100. * h[7] / tot);
+  return rc;
+#else
   return launch_contract(L.var, cp, plan->nsm, stream);
+#endif
 }
 
 }  // namespace dlb
@@ -413,7 +447,8 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
       DLB_REQUIRE(gd.nfeat > 2 && gd.ni == (gd.nfeat - 2) * gd.nparams && gd.nd == gd.nparams, "taylor generator: nfeat = 2 + T, idata = powers[T, d], ddata = center[d]");
       GenDev& gv = gendev[ig];
       gv.nparams = gd.nparams;
-      for (int j = 0; j < gd.nparams; ++j) { gv.pidx[j] = g.pidx[j]; gv.pdef[j] = g.pdef[j]; gv.center[j] = gd.ddata[j]; }
+      for (int j = 0; j < gd.nparams; ++j) gv.cval[j] = g.pidx[j] >= 0 ? gd.ddata[j] : 1. - (g.pdef[j] - gd.ddata[j]);
+      gv.cval[MAXP] = 0.;
       for (int t = 0; t < gd.nfeat - 2; ++t) {
         int deg = 0;
         for (int j = 0; j < gd.nparams; ++j) { DLB_REQUIRE(gd.idata[t * gd.nparams + j] >= 0, "taylor generator: negative power"); deg += gd.idata[t * gd.nparams + j]; }
@@ -484,14 +519,24 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
     for (int ig = 0; ig < desc->ngen; ++ig) {
       const dlb_generator_desc& gd = desc->gens[ig];
       if (!plan->gens[ig].aux[6]) continue;
-      std::vector<unsigned long long> paths(ast, 0xFF00000000000000ull);   // structural zeros
-      paths[0] = 0ull;                                                       // column 0 = 1 (empty product)
+      // per column: word 0 = parameter-tile column of each factor (desc->d = the constant-one column), word 1 = index into cval
+      const unsigned long long one = (unsigned long long)desc->d, none = (unsigned long long)MAXP;
+      unsigned long long w0 = 0ull, w1 = 0ull;
+      for (int k = 0; k < 7; ++k) { w0 |= one << (8 * k); w1 |= none << (8 * k); }
+      std::vector<unsigned long long> paths((size_t)2 * ast);
+      for (int c = 0; c < ast; ++c) { paths[2 * c] = w0 | 0xFF00000000000000ull; paths[2 * c + 1] = w1; }   // structural zeros
+      paths[0] = w0;                                                                                          // column 0 = 1 (empty product)
+      DLB_REQUIRE(desc->d < 255, "too many parameters for the in-kernel monomial evaluation");
       for (int t = 0; t < gd.nfeat - 2 && 2 + t < ast; ++t) {
-        unsigned long long q = 0ull;
+        unsigned long long a0 = w0, a1 = w1;
         int k = 0;
         for (int j = 0; j < gd.nparams; ++j)
-          for (int e = 0; e < gd.idata[t * gd.nparams + j]; ++e) q |= (unsigned long long)(j + 1) << (8 * k++);
-        paths[2 + t] = q;
+          for (int e = 0; e < gd.idata[t * gd.nparams + j]; ++e, ++k) {
+            const unsigned long long colj = plan->gens[ig].pidx[j] >= 0 ? (unsigned long long)plan->gens[ig].pidx[j] : one;
+            a0 = (a0 & ~(0xFFull << (8 * k))) | (colj << (8 * k));
+            a1 = (a1 & ~(0xFFull << (8 * k))) | ((unsigned long long)j << (8 * k));
+          }
+        paths[2 * (2 + t)] = a0; paths[2 * (2 + t) + 1] = a1;
       }
       DLB_TRY(upload(plan, paths.data(), paths.size(), &plan->d_paths[ig]));
     }
@@ -692,6 +737,7 @@ int dlb_features_batch(dlb_plan* plan, int32_t gen, const double* params, int64_
 int dlb_set_timing(dlb_plan* plan, int32_t enabled) {
   DLB_REQUIRE(plan, "NULL plan");
   plan->timing = enabled != 0;
+  g_timing.store(plan->timing);
   return DLB_OK;
 }
 
@@ -701,6 +747,11 @@ int dlb_last_kernel_ms(const dlb_plan* plan, double* features_ms, double* contra
   if (contract_ms) *contract_ms = plan->ms_contract;
   if (solve_ms) *solve_ms = plan->ms_solve;
   return DLB_OK;
+}
+
+int dlb_last_fftlog_ms(double* ms) {
+  DLB_REQUIRE(ms, "NULL output");
+  return last_fftlog_ms(ms);
 }
 
 int dlb_measure_fp64_peak(int32_t kind, double* tflops) {

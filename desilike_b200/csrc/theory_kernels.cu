@@ -482,6 +482,18 @@ __global__ void __launch_bounds__(FFT_THREADS) fftlog_kernel(const DevGen g, lon
 
 }  // namespace
 
+std::atomic<bool> g_timing{false};
+cudaEvent_t g_fft_ev[2] = {nullptr, nullptr};
+
+int last_fftlog_ms(double* ms) {
+  *ms = 0.;
+  if (!g_fft_ev[0]) return DLB_OK;
+  float t = 0.f;
+  if (cudaEventElapsedTime(&t, g_fft_ev[0], g_fft_ev[1]) != cudaSuccess) { cudaGetLastError(); return DLB_OK; }
+  *ms = t;
+  return DLB_OK;
+}
+
 int launch_theory_features(const DevGen& g, const double* params, int d, long long N, long long npad, double* F, int fstride, cudaStream_t stream) {
   if (g.kind == DLB_GEN_KAISER) {
     // nt is needed on the host for the shared-memory size: it is mirrored in aux[1] at plan creation
@@ -511,7 +523,12 @@ int launch_theory_features(const DevGen& g, const double* params, int d, long lo
         configured = smem;
       }
       dim3 grid((unsigned)npad, nell);
+      if (g_timing.load()) {
+        if (!g_fft_ev[0]) { DLB_CUDA(cudaEventCreate(&g_fft_ev[0])); DLB_CUDA(cudaEventCreate(&g_fft_ev[1])); }
+        DLB_CUDA(cudaEventRecord(g_fft_ev[0], stream));
+      }
       fftlog_kernel<<<grid, FFT_THREADS, smem, stream>>>(g, N, F, fstride);
+      if (g_timing.load()) DLB_CUDA(cudaEventRecord(g_fft_ev[1], stream));
       g_launches++;
       DLB_CUDA(cudaGetLastError());
     }

@@ -117,7 +117,9 @@ class Plan(object):
     def last_kernel_ms(self):
         a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
         _capi.check(self._lib.dlb_last_kernel_ms(self._handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
-        return dict(features=a.value, contract=b.value, solve=c.value)
+        f = ctypes.c_double()
+        _capi.check(self._lib.dlb_last_fftlog_ms(ctypes.byref(f)))
+        return dict(features=a.value, contract=b.value, solve=c.value, fftlog=f.value)
 
 
 def pinned_empty(shape, dtype=np.float64):
