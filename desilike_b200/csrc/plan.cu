@@ -48,6 +48,7 @@ struct dlb_plan {
   std::vector<dlb::DevGen> gens;
   std::vector<dlb::Block> blocks;
   std::vector<dlb::MlpLayers> mlps;   // one per generator (empty unless kind == MLP)
+  std::vector<std::pair<dlb::Launch, int>> mlp_launches;   // hidden layers of ALL MLP generators, one launch per (depth, activation, A mode)
   dlb::DevCoef* d_coefs = nullptr;
   int* d_prior_kind = nullptr;
   double *d_prior_lo = nullptr, *d_prior_hi = nullptr, *d_prior_loc = nullptr, *d_prior_scale = nullptr;
@@ -219,7 +220,7 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
   L.npart_max = 1;
   for (const Block* b : blocks) L.npart_max = std::max(L.npart_max, b->npart);
   L.nstages = 0;
-  if (L.var.R == 1) {   // two co-resident 8-warp CTAs per SM (run out of phase) when their shared memory fits
+  if (L.var.R == 1 && !getenv("DLB_FORCE_CPS1")) {   // two co-resident 8-warp CTAs per SM (run out of phase) when their shared memory fits
     const Variant v2{1, 2, 7, 4, 2};
     for (int s = 3; s >= 2; --s)
       if (contract_smem_bytes(v2, s, resident, L.ast, plan->dpad, ncoef, L.npart_max, plan->ngen) <= contract_smem_limit(2)) { L.var = v2; L.nstages = s; break; }
@@ -334,20 +335,18 @@ static void fill_params(const dlb_plan* plan, const Launch& L, ContractParams& c
 static int run_front(dlb_plan* plan, const double* d_params, long long N, long long npad, cudaStream_t stream, bool force_taylor = false) {
   for (size_t ig = 0; ig < plan->gens.size(); ++ig) {
     const DevGen& g = plan->gens[ig];
-    if (g.kind == DLB_GEN_MLP) {
-      DLB_TRY(launch_mlp_input(g, d_params, plan->d, N, npad, plan->w_F, plan->fstride, stream));
-      for (const Launch& L : plan->mlps[ig].launches) {
-        ContractParams cp;
-        fill_params(plan, L, cp, d_params, N, npad);
-        cp.blocks = L.d_plain; cp.sched = L.d_sched_plain; cp.nsched = L.nsched; cp.ncoef = 0;
-        cp.out = plan->w_F; cp.ostride = plan->fstride; cp.out_rows = npad; cp.act = plan->mlps[ig].act; cp.mode = 1;
-        cp.U = npad / variant_unit(L.var);
-        DLB_TRY(launch_contract(L.var, cp, plan->nsm, stream));
-      }
-      continue;
-    }
+    if (g.kind == DLB_GEN_MLP) { DLB_TRY(launch_mlp_input(g, d_params, plan->d, N, npad, plan->w_F, plan->fstride, stream)); continue; }
     if (g.kind == DLB_GEN_TAYLOR && g.aux[6] && plan->resident && !force_taylor) continue;   // evaluated inside the contraction kernel
     DLB_TRY(launch_features(g, d_params, plan->d, N, npad, plan->w_F, plan->fstride, stream));
+  }
+  for (const auto& la : plan->mlp_launches) {   // hidden layers, depth by depth, all MLP emulators of the likelihood in one launch
+    const Launch& L = la.first;
+    ContractParams cp;
+    fill_params(plan, L, cp, d_params, N, npad);
+    cp.blocks = L.d_plain; cp.sched = L.d_sched_plain; cp.nsched = L.nsched; cp.ncoef = 0;
+    cp.out = plan->w_F; cp.ostride = plan->fstride; cp.out_rows = npad; cp.act = la.second; cp.mode = 1;
+    cp.U = npad / variant_unit(L.var);
+    DLB_TRY(launch_contract(L.var, cp, plan->nsm, stream));
   }
   return DLB_OK;
 }
@@ -557,12 +556,24 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
   }
   plan->ntheory = coloff; plan->ptotal = poff;
   DLB_TRY(build_launch(plan, bptr, resident, ast, desc->ncoef, plan->launch));
-  for (MlpLayers& mlp : plan->mlps) {
-    mlp.launches.resize(mlp.layers.size());
-    for (size_t l = 0; l < mlp.layers.size(); ++l) {
-      const bool res = mlp.layers[l].maxcol >= 0;
-      DLB_TRY(build_launch(plan, std::vector<Block*>{&mlp.layers[l]}, res, res ? round_ast(mlp.layers[l].maxcol) : 0, 0, mlp.launches[l]));
-    }
+  {
+    size_t maxdepth = 0;
+    for (MlpLayers& mlp : plan->mlps) maxdepth = std::max(maxdepth, mlp.layers.size());
+    for (size_t l = 0; l < maxdepth; ++l)
+      for (int act = 0; act <= 3; ++act)
+        for (int res = 0; res < 2; ++res) {
+          std::vector<Block*> group;
+          int gast = 4;
+          for (MlpLayers& mlp : plan->mlps)
+            if (l < mlp.layers.size() && mlp.act == act && (mlp.layers[l].maxcol >= 0) == (res == 1)) {
+              group.push_back(&mlp.layers[l]);
+              if (res) gast = std::max(gast, round_ast(mlp.layers[l].maxcol));
+            }
+          if (group.empty()) continue;
+          plan->mlp_launches.emplace_back();
+          plan->mlp_launches.back().second = act;
+          DLB_TRY(build_launch(plan, group, res == 1, res ? gast : 0, 0, plan->mlp_launches.back().first));
+        }
   }
   std::vector<SolveBlock> sb(desc->nblocks);
   for (int ib = 0; ib < desc->nblocks; ++ib) sb[ib] = SolveBlock{plan->blocks[ib].poff, 1, plan->blocks[ib].npart, plan->blocks[ib].d_map};
