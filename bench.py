@@ -132,6 +132,95 @@ def run_reference(args, spec, label, X):
     print(json.dumps(line))
 
 
+def run_ensemble(args):
+    """BASELINE.json configs[4]: one ensemble-sampler iteration (stretch move, red-blue halves) for 2^20 walkers of the 5-tracer
+    Taylor-emulated likelihood, walkers sharded over the GPUs (strong scaling), NCCL all-gather of the log-posteriors per step.
+    Walkers, proposals and log-posteriors are device resident (dlb_ensemble_step); `value` = log-posterior evaluations / s."""
+    import torch
+    import desilike_b200
+    from oracle import configs
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+    spec = configs.config_c5(coefficients='random')
+    plan = desilike_b200.Plan(spec, with_theory=False)
+    total = 1 << 20
+    n = total // world
+    X = configs.sample_points(spec, n, seed=500 + rank)
+    X = X.mean(axis=0) + 0.05 * (X - X.mean(axis=0))
+    es = desilike_b200.EnsembleSampler(plan, n, seed=2026, rank_offset=rank * (n // 2))
+    es.set_start(X)
+    gathered = torch.empty((world, n), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step():
+        es.step()
+        if world > 1: dist.all_gather_into_tensor(gathered, es.logposterior)
+
+    def barrier():
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)): step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    launches0 = desilike_b200.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    barrier()
+    e0.record()
+    for _ in range(args.steps): step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = desilike_b200.launch_count() - launches0
+    clocks = sampler.result()
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = total * args.steps / (ms_total * 1e-3)
+    # e2e: the same iteration driven from HOST walkers each step (H2D of the walkers + D2H of positions and log-posteriors)
+    hX = desilike_b200.pinned_empty((n, plan.d)); hX[...] = es.walkers.cpu().numpy()
+    hlp = desilike_b200.pinned_empty(n)
+    e2e_steps = max(3, min(args.steps, 20))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        es.walkers.copy_(torch.from_numpy(hX), non_blocking=True)
+        step()
+        torch.from_numpy(hX).copy_(es.walkers, non_blocking=True)
+        torch.from_numpy(hlp).copy_(es.logposterior, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    flops = plan.lowered.flops_per_point()
+    peak = desilike_b200.measure_fp64_peak('dmma')
+    achieved = (flops['contract'] + flops['gram']) * value / world / 1e12
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'C5 ensemble step: 2^20 walkers, stretch move (2 half-ensemble batches / iteration), 5-tracer Taylor likelihood (n=2010, d=14), device-resident walkers',
+                       'walkers_per_gpu': n, 'parallelism': 'walkers sharded over {:d} GPU(s); all-gather of logposterior per iteration'.format(world),
+                       'l2_policy': 'proposals ({:.0f} MB per half) are regenerated every iteration; inputs exceed L2 over an iteration'.format(n // 2 * plan.d * 8 / 2**20)},
+            'clocks': clocks, 'acceptance_fraction': es.acceptance_fraction,
+            'e2e': {'value': total * e2e_steps / dt, 'unit': UNIT, 'h2d_bytes_per_step': n * plan.d * 8, 'd2h_bytes_per_step': n * (plan.d + 1) * 8, 'steps': e2e_steps,
+                    'api': 'desilike_b200.EnsembleSampler.step with host walkers copied in and out every iteration'},
+            'gpu_launches': int(launches),
+            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+                         'kernel': 'dlb::contract_kernel inside the whole iteration (propose + likelihood + accept)', 'flops_per_eval_folded': flops,
+                         'peak_source': 'dlb_measure_fp64_peak(DMMA.8x8x4 register loop) measured in this run'}}
+    if rank == 0: print(json.dumps(line))
+    if world > 1: dist.destroy_process_group()
+
+
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument('--gpus', type=int, default=1)
@@ -146,7 +235,9 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
     from oracle import configs
-    spec, label = build_spec(args.workload)
+    if args.workload == 'c5step' and args.impl == 'ours':
+        return run_ensemble(args)
+    spec, label = build_spec('c5' if args.workload == 'c5step' else args.workload)
     N = args.batch
     if args.impl == 'reference':
         X = configs.sample_points(spec, N, seed=100)

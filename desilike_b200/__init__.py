@@ -15,10 +15,11 @@ from .emulators import Emulator, EmulatedCalculator
 from .observables import TracerPowerSpectrumMultipolesObservable, TracerCorrelationFunctionMultipolesObservable
 from .likelihoods import ObservablesGaussianLikelihood, SumLikelihood, PipelineError
 from .base import vmap, status_to_errors
+from .samplers import EnsembleSampler
 
 __all__ = ['Parameter', 'ParameterCollection', 'Samples', 'ShapeFitPowerSpectrumTemplate', 'BAOPowerSpectrumTemplate',
            'KaiserTracerPowerSpectrumMultipoles', 'EFTLikeKaiserTracerPowerSpectrumMultipoles', 'DampedBAOWigglesTracerPowerSpectrumMultipoles',
            'DampedBAOWigglesTracerCorrelationFunctionMultipoles', 'Emulator', 'EmulatedCalculator', 'TracerPowerSpectrumMultipolesObservable',
-           'TracerCorrelationFunctionMultipolesObservable', 'ObservablesGaussianLikelihood', 'SumLikelihood', 'PipelineError', 'vmap', 'status_to_errors',
+           'TracerCorrelationFunctionMultipolesObservable', 'ObservablesGaussianLikelihood', 'SumLikelihood', 'PipelineError', 'vmap', 'status_to_errors', 'EnsembleSampler',
            'Plan', 'Lowered', 'LoweringError', 'DesilikeB200Error', 'load_library', 'launch_count', 'measure_fp64_peak', 'pinned_empty']
 __version__ = '0.1.0'

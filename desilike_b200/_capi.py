@@ -60,6 +60,8 @@ SYMBOLS = {
     'dlb_eval_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 5 + [ctypes.c_void_p]),
     'dlb_theory_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     'dlb_features_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
+    'dlb_ensemble_step': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_double,
+                                         ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     'dlb_launch_count': (ctypes.c_int64, []),
     'dlb_measure_fp64_peak': (ctypes.c_int, [ctypes.c_int32, c_double_p]),
     'dlb_last_kernel_ms': (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_double_p]),

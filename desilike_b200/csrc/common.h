@@ -142,10 +142,18 @@ struct SolveParams {
   const double* g0;       // [ns] prior gradient at x0
   const double* gL0;      // [ns] likelihood gradient part that is constant (none at present: zeros)
   const double* x0; const double* xprec; const double* xloc; const double* xlo; const double* xhi; const int* xkind;
+  // independent groups of solved parameters (connected components over the likelihood blocks); ncomp = 0 -> one dense problem
+  int ncomp; const int* comp_off; const int* comp_idx; const int* comp_nmarg;
   double* logpost; double* loglike; double* logprior; double* xsolved; int* status;
 };
 int launch_solve(const SolveParams& p, cudaStream_t stream);
 
 int measure_fp64_peak(int kind, double* tflops);
+
+// ensemble sampler kernels (csrc/sampler.cu)
+int launch_stretch_propose(const double* X, int d, long long n0, long long n1, int half, uint64_t seed, uint64_t iteration, double a,
+                           long long rank_offset, double* Y, cudaStream_t stream);
+int launch_stretch_accept(double* X, double* logp, const double* Y, const double* logpy, int d, long long n0, long long n1, int half, uint64_t seed,
+                          uint64_t iteration, double a, long long rank_offset, unsigned long long* naccept, cudaStream_t stream);
 
 }  // namespace dlb

@@ -54,6 +54,8 @@ struct dlb_plan {
   double *d_prior_lo = nullptr, *d_prior_hi = nullptr, *d_prior_loc = nullptr, *d_prior_scale = nullptr;
   double *d_M0 = nullptr, *d_g0 = nullptr, *d_x0 = nullptr, *d_xprec = nullptr, *d_xloc = nullptr, *d_xlo = nullptr, *d_xhi = nullptr;
   int* d_xkind = nullptr;
+  int ncomp = 0;                       // independent groups of solved parameters (0: solve one dense system)
+  int *d_comp_off = nullptr, *d_comp_idx = nullptr, *d_comp_nmarg = nullptr;
   dlb::SolveBlock* d_solve_blocks = nullptr;
   long long ptotal = 0;  // partial rows (in units of npad doubles)
   std::vector<void*> owned;
@@ -62,7 +64,9 @@ struct dlb_plan {
   double *w_F = nullptr, *w_partial = nullptr, *w_params = nullptr, *w_out = nullptr, *w_theory = nullptr;
   int* w_status = nullptr;
   long long theory_cap = 0;
-  std::mutex mutex;
+  double *w_prop = nullptr, *w_logpy = nullptr;   // ensemble sampler: proposals of one half and their log-posteriors
+  long long prop_cap = 0;
+  std::mutex mutex, sampler_mutex;
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   double ms_features = 0., ms_contract = 0., ms_solve = 0.;
@@ -404,6 +408,8 @@ void dlb_plan_destroy(dlb_plan* plan) {
   for (void* ptr : {(void*)plan->w_F, (void*)plan->w_partial, (void*)plan->w_params, (void*)plan->w_out, (void*)plan->w_status, (void*)plan->w_theory})
     if (ptr) cudaFree(ptr);
   for (auto& e : plan->ev) if (e) cudaEventDestroy(e);
+  if (plan->w_prop) cudaFree(plan->w_prop);
+  if (plan->w_logpy) cudaFree(plan->w_logpy);
   delete plan;
 }
 
@@ -608,6 +614,35 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
     DLB_TRY(upload(plan, desc->xprior_lo, (size_t)ns, &plan->d_xlo));
     DLB_TRY(upload(plan, desc->xprior_hi, (size_t)ns, &plan->d_xhi));
     DLB_TRY(upload(plan, desc->xprior_kind, (size_t)ns, &plan->d_xkind));
+    // connected components of the solved parameters over the likelihood blocks (parameters sharing a block are coupled;
+    // the reference groups likelihoods sharing solved parameters the same way, likelihoods/base.py:60-97)
+    std::vector<int> parent(ns);
+    for (int i = 0; i < ns; ++i) parent[i] = i;
+    auto find = [&](int i) { while (parent[i] != i) { parent[i] = parent[parent[i]]; i = parent[i]; } return i; };
+    for (int ib = 0; ib < desc->nblocks; ++ib) {
+      const dlb_block_desc& bd = desc->blocks[ib];
+      int first = -1;
+      auto join = [&](int i) { if (first < 0) first = i; else parent[find(i)] = find(first); };
+      for (int a = 0; a < bd.nslots - 1; ++a) join(bd.slot_solved[a]);
+      for (int a = 0; a < bd.nconst; ++a) join(bd.const_solved[a]);
+    }
+    std::vector<int> comp_off{0}, comp_idx, comp_nmarg;
+    int maxsize = 0;
+    for (int r = 0; r < ns; ++r) {
+      if (find(r) != r) continue;
+      int nm = 0;
+      for (int i = 0; i < ns; ++i) if (find(i) == r && i < desc->nmarg) { comp_idx.push_back(i); ++nm; }   // '.marg' members first
+      for (int i = 0; i < ns; ++i) if (find(i) == r && i >= desc->nmarg) comp_idx.push_back(i);
+      comp_nmarg.push_back(nm);
+      comp_off.push_back((int)comp_idx.size());
+      maxsize = std::max(maxsize, comp_off.back() - comp_off[comp_off.size() - 2]);
+    }
+    if (maxsize <= 12) {   // small groups: one lane factorises one group
+      plan->ncomp = (int)comp_nmarg.size();
+      DLB_TRY(upload(plan, comp_off.data(), comp_off.size(), &plan->d_comp_off));
+      DLB_TRY(upload(plan, comp_idx.data(), comp_idx.size(), &plan->d_comp_idx));
+      DLB_TRY(upload(plan, comp_nmarg.data(), comp_nmarg.size(), &plan->d_comp_nmarg));
+    }
   }
   for (auto& e : plan->ev) DLB_CUDA(cudaEventCreate(&e));
   guard.p = nullptr;
@@ -653,6 +688,7 @@ int dlb_eval_batch(dlb_plan* plan, const double* params, int64_t N, double* logp
     sp.partial = plan->w_partial; sp.blocks = plan->d_solve_blocks; sp.nblocks = (int)plan->blocks.size();
     sp.ns = ns; sp.nmarg = plan->nmarg; sp.M0 = plan->d_M0; sp.g0 = plan->d_g0; sp.x0 = plan->d_x0; sp.xprec = plan->d_xprec;
     sp.xloc = plan->d_xloc; sp.xlo = plan->d_xlo; sp.xhi = plan->d_xhi; sp.xkind = plan->d_xkind;
+    sp.ncomp = plan->ncomp; sp.comp_off = plan->d_comp_off; sp.comp_idx = plan->d_comp_idx; sp.comp_nmarg = plan->d_comp_nmarg;
     double* w = plan->w_out;
     sp.logpost = logposterior ? (lp_dev ? logposterior + start : w) : nullptr;
     sp.loglike = loglikelihood ? (ll_dev ? loglikelihood + start : w + npad) : nullptr;
@@ -757,6 +793,33 @@ int dlb_last_kernel_ms(const dlb_plan* plan, double* features_ms, double* contra
   if (features_ms) *features_ms = plan->ms_features;
   if (contract_ms) *contract_ms = plan->ms_contract;
   if (solve_ms) *solve_ms = plan->ms_solve;
+  return DLB_OK;
+}
+
+int dlb_ensemble_step(dlb_plan* plan, double* walkers, double* logposterior, int64_t nwalkers, uint64_t seed, uint64_t iteration, double a,
+                      int64_t rank_offset, uint64_t* naccept, void* stream_) {
+  DLB_REQUIRE(plan && walkers && logposterior && nwalkers >= 2 && a > 1., "NULL plan / walkers / logposterior, fewer than 2 walkers or a <= 1");
+  DLB_REQUIRE(is_device_ptr(walkers) && is_device_ptr(logposterior) && (!naccept || is_device_ptr(naccept)),
+              "ensemble step: walkers, logposterior (and naccept) must be device memory");
+  std::lock_guard<std::mutex> lock(plan->sampler_mutex);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DLB_CUDA(cudaSetDevice(plan->device));
+  const long long n0 = nwalkers / 2, n1 = nwalkers - n0;
+  if (n1 > plan->prop_cap) {
+    if (plan->w_prop) cudaFree(plan->w_prop);
+    if (plan->w_logpy) cudaFree(plan->w_logpy);
+    plan->w_prop = plan->w_logpy = nullptr; plan->prop_cap = 0;
+    DLB_CUDA(cudaMalloc((void**)&plan->w_prop, (size_t)n1 * plan->d * sizeof(double)));
+    DLB_CUDA(cudaMalloc((void**)&plan->w_logpy, (size_t)n1 * sizeof(double)));
+    plan->prop_cap = n1;
+  }
+  for (int half = 0; half < 2; ++half) {
+    const long long na = half == 0 ? n0 : n1;
+    DLB_TRY(launch_stretch_propose(walkers, plan->d, n0, n1, half, seed, iteration, a, rank_offset, plan->w_prop, stream));
+    DLB_TRY(dlb_eval_batch(plan, plan->w_prop, na, plan->w_logpy, nullptr, nullptr, nullptr, nullptr, stream_));
+    DLB_TRY(launch_stretch_accept(walkers, logposterior, plan->w_prop, plan->w_logpy, plan->d, n0, n1, half, seed, iteration, a, rank_offset,
+                                  reinterpret_cast<unsigned long long*>(naccept), stream));
+  }
   return DLB_OK;
 }
 

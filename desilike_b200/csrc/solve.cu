@@ -78,14 +78,62 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) finish_solve_kernel(const So
   for (int i = lane; i < ns; i += 32) g[i] = p.g0[i] + gL[i];
   __syncwarp();
 
-  // ---- Cholesky M = L L^T (lower, in place) ----
   bool spd = true;
   double logdet = 0.;
+  double lp = 0.;
+  bool inside = true;
+  for (int j = lane; j < p.d; j += 32) {
+    bool in_j = true;
+    lp += prior_logpdf(p.prior_kind[j], p.params[pt * p.d + j], p.prior_lo[j], p.prior_hi[j], p.prior_loc[j], p.prior_scale[j], &in_j);
+    inside = inside && in_j;
+  }
+  double quad = 0.;
+  if (p.ncomp > 0) {
+    // ---- block-diagonal normal equations: the solved parameters split into independent groups (connected components of
+    //      the likelihood blocks sharing them -- the reference solves such groups jointly, likelihoods/base.py:60-97); one lane
+    //      factorises one small group serially (Cholesky + two triangular solves), groups run in parallel across the warp ----
+    for (int c = lane; c < p.ncomp; c += 32) {
+      const int o = p.comp_off[c], n = p.comp_off[c + 1] - o, nm = p.comp_nmarg[c];
+      const int* idx = p.comp_idx + o;
+      bool ok = true;
+      for (int j = 0; j < n && ok; ++j) {
+        const int J = idx[j];
+        const double djj = M[J * ld + J];
+        if (!(djj > 0.) || !isfinite(djj)) { ok = false; break; }
+        const double l = sqrt(djj), inv = 1. / l;
+        if (j < nm) logdet += 2. * log(l);
+        M[J * ld + J] = l;
+        for (int i = j + 1; i < n; ++i) M[idx[i] * ld + J] *= inv;
+        for (int i = j + 1; i < n; ++i) {
+          const int I = idx[i];
+          const double lij = M[I * ld + J];
+          for (int k = j + 1; k <= i; ++k) M[I * ld + idx[k]] -= lij * M[idx[k] * ld + J];
+        }
+      }
+      if (!ok) { spd = false; continue; }
+      for (int j = 0; j < n; ++j) y[idx[j]] = g[idx[j]];
+      for (int j = 0; j < n; ++j) {   // forward L y = g
+        const int J = idx[j];
+        const double yj = y[J] / M[J * ld + J];
+        y[J] = yj;
+        for (int i = j + 1; i < n; ++i) y[idx[i]] -= M[idx[i] * ld + J] * yj;
+      }
+      for (int j = n - 1; j >= 0; --j) {   // backward L^T dx = y
+        const int J = idx[j];
+        const double xj = y[J] / M[J * ld + J];
+        dx[J] = xj;
+        for (int i = 0; i < j; ++i) y[idx[i]] -= M[J * ld + idx[i]] * xj;
+      }
+    }
+    spd = __all_sync(0xffffffffu, spd);
+    __syncwarp();
+  } else {
+  // ---- Cholesky M = L L^T (lower, in place), cooperative over the warp (densely coupled solved parameters) ----
   for (int j = 0; j < ns; ++j) {
     const double djj = M[j * ld + j];
     if (!(djj > 0.) || !isfinite(djj)) { spd = false; break; }
     const double l = sqrt(djj);
-    if (j < p.nmarg) logdet += 2. * log(l);
+    if (j < p.nmarg && lane == 0) logdet += 2. * log(l);
     const double inv = 1. / l;
     for (int i = j + 1 + lane; i < ns; i += 32) M[i * ld + j] *= inv;
     __syncwarp();
@@ -96,14 +144,6 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) finish_solve_kernel(const So
     }
     __syncwarp();
   }
-  double lp = 0.;
-  bool inside = true;
-  for (int j = lane; j < p.d; j += 32) {
-    bool in_j = true;
-    lp += prior_logpdf(p.prior_kind[j], p.params[pt * p.d + j], p.prior_lo[j], p.prior_hi[j], p.prior_loc[j], p.prior_scale[j], &in_j);
-    inside = inside && in_j;
-  }
-  double quad = 0.;
   if (spd) {
     // forward L y = g
     for (int i = lane; i < ns; i += 32) y[i] = g[i];
@@ -123,6 +163,9 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) finish_solve_kernel(const So
       for (int i = lane; i < j; i += 32) y[i] -= M[j * ld + i] * xj;
       __syncwarp();
     }
+  }
+  }
+  if (spd) {
     for (int i = lane; i < ns; i += 32) {
       const double di = dx[i];
       const double xi = p.x0[i] + di;
@@ -140,6 +183,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) finish_solve_kernel(const So
   for (int o = 16; o > 0; o >>= 1) {
     lp += __shfl_xor_sync(0xffffffffu, lp, o);
     quad += __shfl_xor_sync(0xffffffffu, quad, o);
+    logdet += __shfl_xor_sync(0xffffffffu, logdet, o);
     inside = __shfl_xor_sync(0xffffffffu, (int)inside, o) && inside;
   }
   if (lane == 0) {

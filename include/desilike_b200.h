@@ -148,6 +148,17 @@ int dlb_theory_batch(dlb_plan* plan, const double* params, int64_t N, double* th
 /* Per-point features of one generator [N, nfeat] (parity / debug entry for the theory kernels, e.g. Kaiser tables). */
 int dlb_features_batch(dlb_plan* plan, int32_t gen, const double* params, int64_t N, double* features, void* stream);
 
+/* One iteration of the affine-invariant ensemble sampler (stretch move, red-blue split) with walkers resident on the device:
+ * replaces one `emcee.EnsembleSampler.sample` iteration driving the vectorised log-posterior (reference desilike/samplers/emcee.py:68,
+ * :100-110; desilike/samplers/base.py:144-200).  walkers [nwalkers, d] and logposterior [nwalkers] are DEVICE buffers updated in
+ * place (logposterior must hold the current values, e.g. from dlb_eval_batch); the first nwalkers / 2 rows are one half, the rest
+ * the other.  Randomness: Philox4x32-10 keyed by `seed`, counter (rank_offset + walker index in its half, iteration, half):
+ * reproducible for any launch geometry; ranks sharding an ensemble pass distinct rank_offset.  `a` is the stretch scale (emcee
+ * default 2).  naccept (device uint64, may be NULL) is incremented by the number of accepted proposals.  Work is enqueued on
+ * `stream`; no host synchronisation. */
+int dlb_ensemble_step(dlb_plan* plan, double* walkers, double* logposterior, int64_t nwalkers, uint64_t seed, uint64_t iteration, double a,
+                      int64_t rank_offset, uint64_t* naccept, void* stream);
+
 /* Instrumentation ----------------------------------------------------------------------------------------------- */
 int64_t dlb_launch_count(void);                  /* kernels launched by this library since load (all plans) */
 /* Achieved FP64 rate (TFLOP/s) of a register-resident DMMA.8x8x4 loop (kind 0) or DFMA loop (kind 1) on the current

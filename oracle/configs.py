@@ -177,7 +177,10 @@ def taylor_tracer(name='', seed=2, order=4, nkin=350, nbins=36, coefficients='fi
     rng = rng or np.random.default_rng(seed)
     prefix = (name + '.') if name else ''
     kin = np.arange(1, nkin + 1) * (0.35 / nkin)
-    kout = klim_edges((0.02, 0.02 + nbins * 0.005, 0.005))[:nbins]
+    # bin width 0.005 (reference notebooks) unless that would run past the emulator's k range (kin <= 0.35): then the bins
+    # share [0.02, 0.34] (5-tracer configs with 134 bins per multipole)
+    dk = min(0.005, (0.34 - 0.02) / nbins)
+    kout = 0.02 + dk * (np.arange(nbins) + 0.5)
     nd = 1e-4
     if coefficients == 'finite-difference':
         engine = _kaiser_taylor_engine(kin, ells, order, template or shapefit_template(), with_pk11=solved)
@@ -202,7 +205,7 @@ def taylor_tracer(name='', seed=2, order=4, nkin=350, nbins=36, coefficients='fi
     shotnoiseout = shotnoise * np.concatenate([np.full(nbins, float(ell == 0)) for ell in ells])
     offset = W.dot(np.repeat(shotnoisein, nkin)) - shotnoiseout  # reference window.py:445-473 folded into one constant
     obs = dict(name=name or 'tracer', theory=engine, terms=terms, nin=len(ells) * nkin, wmatrix=W, offset=offset)
-    return obs, params, solved_list, (kout, ells, nd)
+    return obs, params, solved_list, (kout, ells, nd, dk)
 
 
 def _finish(spec, observables_meta, rng, fid_values, coupling=0.1):
@@ -211,9 +214,11 @@ def _finish(spec, observables_meta, rng, fid_values, coupling=0.1):
     fid = np.array([[fid_values[n.split('.')[-1]] for n in names]])
     x0 = {s['name']: s['value'] for s in spec['solved']}
     precs = []
-    for obs, (kout, ells, nd) in zip(spec['observables'], observables_meta):
+    for obs, meta in zip(spec['observables'], observables_meta):
+        kout, ells, nd = meta[:3]
+        dk = meta[3] if len(meta) > 3 else 0.005
         obs['data'] = observable_flat(obs, fid, names, x0)[0]
-        cov = gaussian_covariance(kout, ells, np.abs(obs['data'][:len(kout)]) + 1. / nd, rng=rng, coupling=coupling)
+        cov = gaussian_covariance(kout, ells, np.abs(obs['data'][:len(kout)]) + 1. / nd, dk=dk, rng=rng, coupling=coupling)
         precs.append(np.linalg.inv(cov))
     spec['precision'] = precs
     spec['priors'] = default_priors(names)

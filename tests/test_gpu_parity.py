@@ -100,6 +100,16 @@ def test_full_size_properties(gpu_required):
     plan.close()
 
 
+@pytest.mark.parametrize('name', ['c5', 'c5solved', 'c4'])
+def test_five_tracer_bench_configs_full_size(gpu_required, name):
+    """The 5-tracer configurations exactly as bench.py runs them (n = 2010 data points, T = 70 / MLP 64x3, 35 marginalised terms):
+    every log-posterior finite, parity with the oracle on a seeded subset."""
+    spec = {'c5': lambda: configs.config_c5(coefficients='random'), 'c5solved': lambda: configs.config_c5(coefficients='random', solved=True),
+            'c4': lambda: configs.config_c4()}[name]()
+    got, ref = check(spec, 96, seed=77, solved=bool(spec['solved']))
+    assert np.all(np.isfinite(ref['logposterior'])) and np.all(np.isfinite(got['logposterior']))
+
+
 def test_fp64_peak_measurement(gpu_required):
     import desilike_b200
     dmma = desilike_b200.measure_fp64_peak('dmma')
