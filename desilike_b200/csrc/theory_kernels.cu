@@ -84,6 +84,60 @@ __device__ void spline_second_derivatives(const SplineConst& sc, const double* y
   __syncwarp();
 }
 
+// Same sweeps with (a) the constants pre-transposed to lane-major order (coalesced loads) and (b) the second derivatives
+// stored at padded positions i + (i >> lgL) (one pad per lane chunk of L = 2^lgL knots: chunk stride L + 1 is odd, so the
+// per-lane sequential sweeps are shared-memory bank-conflict free).  Mp must hold nt + nt / L + 1 doubles.
+__device__ __forceinline__ int pidx(int i, int lgL) { return i + (i >> lgL); }
+
+__device__ void spline_second_derivatives_padded(const SplineConst& sc, const double* __restrict__ wT, const double* __restrict__ invbT,
+                                                 const double* __restrict__ cbT, int lgL, const double* y, double* Mp, int lane) {
+  const int n = sc.nt, m = n - 2, L = 1 << lgL;
+  for (int i = 1 + lane; i <= m; i += 32)
+    Mp[pidx(i, lgL)] = 6. * ((y[i + 1] - y[i]) * sc.invh[i] - (y[i] - y[i - 1]) * sc.invh[i - 1]);
+  __syncwarp();
+  const int lo = 1 + lane * L, hi = min(lo + L, m + 1);
+  double A = 1., B = 0.;
+  for (int i = lo, t = 0; i < hi; ++i, ++t) { const double wi = wT[t * 32 + lane]; B = Mp[pidx(i, lgL)] - wi * B; A = -wi * A; }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double Ap = __shfl_up_sync(0xffffffffu, A, o), Bp = __shfl_up_sync(0xffffffffu, B, o);
+    if (lane >= o) { B = A * Bp + B; A = A * Ap; }
+  }
+  double carry = __shfl_up_sync(0xffffffffu, B, 1);
+  if (lane == 0) carry = 0.;
+  for (int i = lo, t = 0; i < hi; ++i, ++t) { carry = Mp[pidx(i, lgL)] - wT[t * 32 + lane] * carry; Mp[pidx(i, lgL)] = carry; }
+  __syncwarp();
+  const int rhi = m - lane * L, rlo = max(rhi - L, 0);   // indices rhi, rhi-1, .. rlo+1
+  A = 1.; B = 0.;
+  for (int i = rhi, t = 0; i > rlo; --i, ++t) { const double c = cbT[t * 32 + lane]; B = Mp[pidx(i, lgL)] * invbT[t * 32 + lane] - c * B; A = -c * A; }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double Ap = __shfl_up_sync(0xffffffffu, A, o), Bp = __shfl_up_sync(0xffffffffu, B, o);
+    if (lane >= o) { B = A * Bp + B; A = A * Ap; }
+  }
+  carry = __shfl_up_sync(0xffffffffu, B, 1);
+  if (lane == 0) carry = 0.;
+  for (int i = rhi, t = 0; i > rlo; --i, ++t) { carry = Mp[pidx(i, lgL)] * invbT[t * 32 + lane] - cbT[t * 32 + lane] * carry; Mp[pidx(i, lgL)] = carry; }
+  __syncwarp();
+  if (lane == 0) {
+    Mp[pidx(0, lgL)] = (1. + sc.r0) * Mp[pidx(1, lgL)] - sc.r0 * Mp[pidx(2, lgL)];
+    Mp[pidx(n - 1, lgL)] = (1. + sc.r1) * Mp[pidx(n - 2, lgL)] - sc.r1 * Mp[pidx(n - 3, lgL)];
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ double spline_eval_hp(const SplineConst& sc, const double* __restrict__ hh, const double* y, const double* Mp, int lgL, double xq) {
+  const int n = sc.nt;
+  int i = (int)((xq - sc.x0) * sc.inv_dx);
+  i = max(0, min(i, n - 2));
+  while (i > 0 && xq < sc.x[i]) --i;
+  while (i < n - 2 && xq >= sc.x[i + 1]) ++i;
+  const double h = hh[i], ih = sc.invh[i], t = xq - sc.x[i];
+  const double Mi = Mp[pidx(i, lgL)], Mj = Mp[pidx(i + 1, lgL)], yi = y[i];
+  const double b = (y[i + 1] - yi) * ih - h * (2. * Mi + Mj) * (1. / 6.);
+  return yi + t * (b + t * (0.5 * Mi + t * (Mj - Mi) * ih * (1. / 6.)));
+}
+
 __device__ __forceinline__ double spline_eval(const SplineConst& sc, const double* y, const double* M, double xq) {
   const int n = sc.nt;
   int i = (int)((xq - sc.x0) * sc.inv_dx);
@@ -94,6 +148,19 @@ __device__ __forceinline__ double spline_eval(const SplineConst& sc, const doubl
   const double Mi = M[i], Mj = M[i + 1];
   const double b = (y[i + 1] - y[i]) * sc.invh[i] - h * (2. * Mi + Mj) * (1. / 6.);
   return y[i] + t * (b + t * (0.5 * Mi + t * (Mj - Mi) * sc.invh[i] * (1. / 6.)));
+}
+
+// same cubic, interval width from a table (no division) -- used with the derived tables appended by theory_lowering.py
+__device__ __forceinline__ double spline_eval_h(const SplineConst& sc, const double* __restrict__ hh, const double* y, const double* M, double xq) {
+  const int n = sc.nt;
+  int i = (int)((xq - sc.x0) * sc.inv_dx);
+  i = max(0, min(i, n - 2));
+  while (i > 0 && xq < sc.x[i]) --i;
+  while (i < n - 2 && xq >= sc.x[i + 1]) ++i;
+  const double h = hh[i], ih = sc.invh[i], t = xq - sc.x[i];
+  const double Mi = M[i], Mj = M[i + 1], yi = y[i];
+  const double b = (y[i + 1] - yi) * ih - h * (2. * Mi + Mj) * (1. / 6.);
+  return yi + t * (b + t * (0.5 * Mi + t * (Mj - Mi) * ih * (1. / 6.)));
 }
 
 __device__ __forceinline__ SplineConst load_spline(const double* d, int nt) {
@@ -126,7 +193,9 @@ __global__ void __launch_bounds__(KAISER_WARPS * 32) kaiser_kernel(const DevGen 
     for (int j = lane; j < g.fpad; j += 32) row[j] = 0.;
     return;
   }
-  double* y = sm + (size_t)warp * 2 * nt;
+  const int L = g.idata[9], lgL = 31 - __clz(L);
+  const int mstride = nt + nt / L + 2;
+  double* y = sm + (size_t)warp * (nt + mstride);
   double* M = y + nt;
   const double* dd = g.ddata;
   const double eta = dd[0], f_fid = dd[2];
@@ -145,20 +214,33 @@ __global__ void __launch_bounds__(KAISER_WARPS * 32) kaiser_kernel(const DevGen 
   const double dm = par[2], dn = par[3], f = f_fid * par[4], sigmapar = par[5], sigmaper = par[6];
   for (int i = lane; i < nt; i += 32) y[i] = pk_fid[i] * exp(dm * Tt[i] + dn * Lt[i]);
   __syncwarp();
-  spline_second_derivatives(sc, y, M, lane);
   const double qap = qpar / qper, jac = 1. / (qpar * qper * qper), iq2 = 1. / (qap * qap) - 1.;
   const bool damped = (sigmapar != 0.) || (sigmaper != 0.);
+  // per-mu AP quantities, once per point: log10(F / qper), mu_ap^2, damping coefficient (reference base.py:211-223, full_shape.py:491-495)
+  const double* lkk = dd + g.idata[8];
+  const double* hh = lkk + nk;
+  const double* wT = hh + nt;
+  const double* invbT = wT + 32 * L;
+  const double* cbT = invbT + 32 * L;
+  spline_second_derivatives_padded(sc, wT, invbT, cbT, lgL, y, M, lane);
+  __shared__ double smu[KAISER_WARPS][16][3];
+  if (lane < nmu) {
+    const double m_ = mu[lane];
+    const double fap = sqrt(1. + m_ * m_ * iq2);
+    const double kfac = fap / qper, muap = m_ / (qap * fap), m2 = muap * muap;
+    smu[warp][lane][0] = log10(kfac);
+    smu[warp][lane][1] = m2;
+    smu[warp][lane][2] = 0.5 * kfac * kfac * (sigmapar * sigmapar * m2 + sigmaper * sigmaper * (1. - m2));
+  }
+  __syncwarp();
   if (lane == 0) { row[0] = 1.; row[1] = 0.; }
   for (int ik = lane; ik < nk; ik += 32) {
     double sdd[MAX_ELL] = {0., 0., 0.}, sdt[MAX_ELL] = {0., 0., 0.}, stt[MAX_ELL] = {0., 0., 0.};
-    const double k = kk[ik];
+    const double k = kk[ik], lk0 = lkk[ik];
     for (int im = 0; im < nmu; ++im) {
-      const double m_ = mu[im];
-      const double fap = sqrt(1. + m_ * m_ * iq2);
-      const double kap = k / qper * fap, muap = m_ / qap / fap;
-      double p = jac * spline_eval(sc, y, M, log10(kap));
-      if (damped) p *= exp(-0.5 * kap * kap * (sigmapar * sigmapar * muap * muap + sigmaper * sigmaper * (1. - muap * muap)));
-      const double m2 = muap * muap;
+      const double m2 = smu[warp][im][1];
+      double p = jac * spline_eval_hp(sc, hh, y, M, lgL, lk0 + smu[warp][im][0]);
+      if (damped) p *= exp(-k * k * smu[warp][im][2]);
       const double pdt = f * m2 * p, ptt = f * f * m2 * m2 * p;
 #pragma unroll
       for (int l = 0; l < MAX_ELL; ++l)
@@ -220,24 +302,36 @@ __global__ void __launch_bounds__(BAO_WARPS * 32) bao_kernel(const DevGen g, con
   ap_qpar_qper(apmode, par[0], par[1], eta, qpar, qper);
   const double b1 = par[2], f = par[3] * f_fid * par[7], sigmas = par[4], sigmapar = par[5], sigmaper = par[6];
   const double qap = qpar / qper, iq2 = 1. / (qap * qap) - 1.;
-  const bool reciso = flags & 1;
+  // derived tables (theory_lowering.py): log10 k, S(k), k^2, wiggle spline ordinates / second derivatives, interval widths
+  const double* lkk = dd + g.idata[6];
+  const double* skt = lkk + nk;
+  const double* k2t = skt + nk;
+  const double* Dw = k2t + nk;
+  const double* MDw = Dw + nt;
+  const double* hh = MDw + nt;
+  // per-mu quantities, once per point (reference base.py:211-223, bao.py:123-134)
+  __shared__ double smu[BAO_WARPS][16][5];
+  if (lane < nmu) {
+    const double m_ = mu[lane];
+    const double fap = sqrt(1. + m_ * m_ * iq2);
+    const double kfac = fap / qper, muap = m_ / (qap * fap), m2 = muap * muap;
+    smu[warp][lane][0] = log10(kfac);
+    smu[warp][lane][1] = 0.5 * kfac * kfac * (sigmapar * sigmapar * m2 + sigmaper * sigmaper * (1. - m2));   // exp(-k^2 [1])
+    smu[warp][lane][2] = f * m2;                    // (b1 + [2] (1 - S))^2 damped wiggles
+    smu[warp][lane][3] = f * m_ * m_;               // (b1 + [3] (1 - S))^2 smooth part
+    smu[warp][lane][4] = 0.5 * sigmas * sigmas * m_ * m_;   // FoG: 1 / (1 + [4] k^2)^2
+  }
+  __syncwarp();
   if (lane == 0) { row[0] = 1.; row[1] = 0.; }
   for (int ik = lane; ik < nk; ik += 32) {
     double acc[MAX_ELL] = {0., 0., 0.};
-    const double k = kk[ik];
-    const double sk = reciso ? exp(-0.5 * (k * rs) * (k * rs)) : 0.;
-    const double pknow = pknow_k[ik];
+    const double lk0 = lkk[ik], k2 = k2t[ik], oms = 1. - skt[ik], pknow = pknow_k[ik];
     for (int im = 0; im < nmu; ++im) {
-      const double m_ = mu[im];
-      const double fap = sqrt(1. + m_ * m_ * iq2);
-      const double kap = k / qper * fap, muap = m_ / qap / fap;
-      const double lk = log10(kap);
-      const double pkwap = spline_eval(sc, pk_t, M_pk, lk) - spline_eval(sc, pknow_t, M_now, lk);
-      const double snl2 = kap * kap * (sigmapar * sigmapar * muap * muap + sigmaper * sigmaper * (1. - muap * muap));
-      const double ca = b1 + f * muap * muap * (1. - sk);
-      const double Cap = ca * ca * exp(-0.5 * snl2);
-      const double fg = 1. + 0.5 * (sigmas * k * m_) * (sigmas * k * m_);
-      const double cb = b1 + f * m_ * m_ * (1. - sk);
+      const double pkwap = spline_eval_h(sc, hh, Dw, MDw, lk0 + smu[warp][im][0]);
+      const double ca = b1 + smu[warp][im][2] * oms;
+      const double Cap = ca * ca * exp(-k2 * smu[warp][im][1]);
+      const double fg = 1. + smu[warp][im][4] * k2;
+      const double cb = b1 + smu[warp][im][3] * oms;
       const double B = cb * cb / (fg * fg);
       const double pkmu = B * pknow + Cap * pkwap;
 #pragma unroll
@@ -498,7 +592,9 @@ int launch_theory_features(const DevGen& g, const double* params, int d, long lo
   if (g.kind == DLB_GEN_KAISER) {
     // nt is needed on the host for the shared-memory size: it is mirrored in aux[1] at plan creation
     const int nt = g.aux[1];
-    const size_t smem = (size_t)KAISER_WARPS * 2 * nt * sizeof(double);
+    int L = 1;
+    while (L * 32 < nt - 2) L *= 2;
+    const size_t smem = (size_t)KAISER_WARPS * (2 * nt + nt / L + 2) * sizeof(double);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
       DLB_CUDA(cudaFuncSetAttribute(kaiser_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -41,6 +41,8 @@ def lower_theory(gen, theory, defaults, names=None):
     ells = tuple(theory['ells'])
     if len(ells) > 3:
         raise ValueError('at most 3 multipoles on the CUDA path')
+    if int(theory.get('nmu', 8)) > 16:
+        raise ValueError('at most 16 mu nodes on the CUDA path (reference defaults: 8 Kaiser, 10 BAO)')
     apmode = tpl.get('apmode', 'qparqper')
     q0, q1 = _AP_SLOTS[apmode]
     names = gen._names
@@ -61,9 +63,26 @@ def lower_theory(gen, theory, defaults, names=None):
         gen.param_idx, gen.param_default, gen.params = _slots(gen, slots, defaults, names)
         ell0 = ells.index(0) if 0 in ells else -1
         total = 2 + 4 * ntab
-        gen.idata = np.array([nk, nell, nmu, nt, APMODES[apmode], (ell0 << 8), ntab, total], dtype=np.int32)
-        gen.ddata = np.concatenate([[float(tpl.get('eta', 1. / 3.)), a, float(tpl['f_fid']), 0.], k, mu, wmu.ravel(), pk, Tt, Lt,
-                                    spline_constants(np.log10(k_t))])
+        base = np.concatenate([[float(tpl.get('eta', 1. / 3.)), a, float(tpl['f_fid']), 0.], k, mu, wmu.ravel(), pk, Tt, Lt,
+                               spline_constants(np.log10(k_t))])
+        # derived tables appended for the kernel: log10 k (so that log10(k_ap) = log10 k + log10(F(mu) / qper) costs one add per node)
+        # and the spline interval widths (no division in the evaluation)
+        # + the tridiagonal-sweep constants transposed to lane-major order: lane l owns the chunk of L knots starting at 1 + l L
+        #   (forward) / ending at m - l L (backward); element t of every lane's chunk is contiguous -> coalesced loads
+        consts = spline_constants(np.log10(k_t))
+        m = nt - 2
+        L = 1
+        while L * 32 < m: L *= 2
+        w_, invb_, cb_ = consts[2 * nt:3 * nt], consts[3 * nt:4 * nt], consts[4 * nt:5 * nt]
+        wT, invbT, cbT = np.zeros((L, 32)), np.zeros((L, 32)), np.zeros((L, 32))
+        for lane in range(32):
+            for t in range(L):
+                i = 1 + lane * L + t
+                if i <= m: wT[t, lane] = w_[i]
+                i = m - lane * L - t
+                if i >= 1: invbT[t, lane], cbT[t, lane] = invb_[i], cb_[i]
+        gen.idata = np.array([nk, nell, nmu, nt, APMODES[apmode], (ell0 << 8), ntab, total, base.size, L], dtype=np.int32)
+        gen.ddata = np.concatenate([base, np.log10(k), np.append(np.diff(np.log10(k_t)), 0.), wT.ravel(), invbT.ravel(), cbT.ravel()])
         gen.nfeat = total
         for t, name in enumerate(['pk_dd', 'pk_dt', 'pk_tt', 'pk11_l0']):
             gen.tables[name] = (2 + t * ntab, nin, None)
@@ -96,6 +115,13 @@ def lower_theory(gen, theory, defaults, names=None):
         flags = (1 if theory.get('mode', '') == 'reciso' else 0) | (2 if xi else 0)
         head = [float(tpl.get('eta', 1. / 3.)), float(tpl['f_fid']), float(theory.get('smoothing_radius', 15.)), 0.]
         ddata = [head, k, mu, wmu.ravel(), pknow_k, pk_t, M_pk, pknow_t, M_now, consts]
+        # derived tables for the kernel (offset in idata[6]): log10 k, reconstruction smoothing S(k) = exp(-(k R)^2 / 2) ('reciso' only),
+        # k^2, the WIGGLE spline (the spline is linear in its ordinates: spline(pk) - spline(pknow) = spline(pk - pknow)) and the
+        # spline interval widths
+        off_derived = sum(np.size(a) for a in ddata)
+        rs_ = float(theory.get('smoothing_radius', 15.))
+        sk = np.exp(-0.5 * (k * rs_)**2) if flags & 1 else np.zeros(nk)
+        ddata += [np.log10(k), sk, k**2, pk_t - pknow_t, M_pk - M_now, np.append(np.diff(np.log10(k_t)), 0.)]
         nin = nell * nk
         if xi:
             ns = s_out.size
@@ -106,13 +132,13 @@ def lower_theory(gen, theory, defaults, names=None):
             off_d = sum(np.size(a) for a in ddata)
             off_d += off_d % 2    # keep the complex tables 16-byte aligned
             ddata = ddata + [np.zeros(off_d - sum(np.size(a) for a in ddata)), fc['ddata']]
-            header = [nk, nell, nmu, nt, APMODES[apmode], flags, 0, total, ns, nk, off_d, 16, poff, fc['ng'], fc['npad_size'], fc['pad_in_left']]
+            header = [nk, nell, nmu, nt, APMODES[apmode], flags, off_derived, total, ns, nk, off_d, 16, poff, fc['ng'], fc['npad_size'], fc['pad_in_left']]
             gen.idata = np.concatenate([np.array(header, dtype=np.int32), fc['idata']])
             gen.nfeat = nvis
             gen.tables['corr'] = (2, nell * ns, None)
         else:
             total = 2 + nin
-            header = [nk, nell, nmu, nt, APMODES[apmode], flags, 0, total, 0, nk, 0, 16, 2, 0, 0, 0]
+            header = [nk, nell, nmu, nt, APMODES[apmode], flags, off_derived, total, 0, nk, 0, 16, 2, 0, 0, 0]
             gen.idata = np.array(header, dtype=np.int32)
             gen.nfeat = total
             gen.tables['power'] = (2, nin, None)
