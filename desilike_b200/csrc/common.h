@@ -43,11 +43,12 @@ int last_fftlog_ms(double* ms);
 // ---------------------------------------------------------------------------------------------------------------------
 // tiling constants of the contraction kernel (csrc/contract.cu)
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int KC = 28;        // k-chunk length == shared-memory row stride in doubles; 28 = 4 (mod 8) -> conflict-free 64-bit fragment loads
+// k-chunk length == shared-memory row stride (doubles) of the B tiles is a per-variant constant (Variant::KC): 28 or 36, both = 4 (mod 8)
+// -> conflict-free 64-bit fragment loads
 constexpr int ROW_ALIGN = 384;  // batch rows are padded to a multiple of every variant's row unit (64, 48) and tile
 
-struct Variant { int R, MT, NT, WM, CPS; }; // accumulator slots, m-tiles (of 8 rows) and n-tiles (of 8 columns) per warp; warp grid is WM (m) x 2 (n);
-                                            // CPS = co-resident CTAs per SM
+struct Variant { int R, MT, NT, WM, CPS, KC; }; // accumulator slots, m-tiles (of 8 rows) and n-tiles (of 8 columns) per warp; warp grid is WM (m) x 2 (n);
+                                            // CPS = co-resident CTAs per SM; KC = k-chunk length
 inline int variant_unit(const Variant& v) { return 8 * v.WM; }          // rows per unit (one m-tile of every warp row)
 inline int variant_bm(const Variant& v) { return 8 * v.WM * v.MT; }
 inline int variant_bn(const Variant& v) { return 16 * v.NT; }
@@ -57,7 +58,7 @@ struct Chunk {        // one k-chunk of one term (device table, one per output b
   int coef;           // coefficient index, -1 -> 1
   int fcol;           // first feature column: absolute in the per-point feature row (streaming A) or relative to the
                       // block's generator segment (resident A)
-  int kc;             // chunk length (multiple of 4, <= KC)
+  int kc;             // chunk length (multiple of 4, <= Variant::KC)
 };
 
 constexpr int MAXP = 16;  // max input parameters of one generator

@@ -21,7 +21,7 @@
 //     warp grid WM (m) x 2 (n).
 //   * B operand (pre-tiled term matrices, L2 resident) streamed with 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) into an
 //     mbarrier full/empty ring; there is no dedicated producer warp: warp 0 re-arms the stage that was released one chunk
-//     earlier after finishing its own chunk (S - 1 chunks of prefetch).  Rows are KC = 36 doubles (36 = 4 mod 8 makes the
+//     earlier after finishing its own chunk (S - 1 chunks of prefetch).  Rows are KC = 28 or 36 doubles (= 4 mod 8 makes the
 //     64-bit fragment loads bank-conflict free).  The per-column-block epilogue constants (r0, constant Jacobian rows)
 //     travel through the same ring as one extra chunk.
 //   * A operand, RESIDENT mode (Taylor emulators): the warps evaluate the monomials prod_j (theta_j - c_j)^p_tj of their
@@ -82,7 +82,7 @@ __device__ __forceinline__ double ipow(double x, int n) {
 }
 
 // One k-chunk of DMMAs for MTC active m-tiles: acc[mt][nt] += (beta[mt] * A[mt-rows, k]) . B[k, nt-cols]
-template <int MT, int NT, int MTC>
+template <int MT, int NT, int MTC, int KC>
 __device__ __forceinline__ void mma_chunk(double (&acc)[MT][NT][2], const double* __restrict__ A, int astride, const double* __restrict__ B,
                                           const double (&beta)[MT], int nk4) {
 #pragma unroll 3
@@ -99,13 +99,13 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[MT][NT][2], const double
   }
 }
 
-template <int MT, int NT>
+template <int MT, int NT, int KC>
 __device__ __forceinline__ void mma_chunk_dispatch(double (&acc)[MT][NT][2], const double* A, int astride, const double* B, const double (&beta)[MT],
                                                    int nk4, int mtc) {
-  if (mtc == MT) { mma_chunk<MT, NT, MT>(acc, A, astride, B, beta, nk4); return; }
-  if constexpr (MT > 1) { if (mtc == 1) { mma_chunk<MT, NT, 1>(acc, A, astride, B, beta, nk4); return; } }
-  if constexpr (MT > 2) { if (mtc == 2) { mma_chunk<MT, NT, 2>(acc, A, astride, B, beta, nk4); return; } }
-  if constexpr (MT > 3) { if (mtc == 3) { mma_chunk<MT, NT, 3>(acc, A, astride, B, beta, nk4); return; } }
+  if (mtc == MT) { mma_chunk<MT, NT, MT, KC>(acc, A, astride, B, beta, nk4); return; }
+  if constexpr (MT > 1) { if (mtc == 1) { mma_chunk<MT, NT, 1, KC>(acc, A, astride, B, beta, nk4); return; } }
+  if constexpr (MT > 2) { if (mtc == 2) { mma_chunk<MT, NT, 2, KC>(acc, A, astride, B, beta, nk4); return; } }
+  if constexpr (MT > 3) { if (mtc == 3) { mma_chunk<MT, NT, 3, KC>(acc, A, astride, B, beta, nk4); return; } }
 }
 
 // Position in the CTA's chunk sequence (tile, block, column block, chunk); chunk == nchunks is the epilogue-constants chunk.
@@ -136,7 +136,7 @@ __device__ __forceinline__ unsigned atom_add_acq_rel(unsigned* addr, unsigned v)
 #define PROF_FLUSH
 #endif
 
-template <int R, int MT, int NT, int WM, int CPS, bool RESIDENT>
+template <int R, int MT, int NT, int WM, int CPS, int KC, bool RESIDENT>
 __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_constant__ ContractParams p) {
   constexpr int NW = 2 * WM, NTH = NW * 32, UNIT = WM * 8, BM = UNIT * MT, BN = 16 * NT;
   constexpr int STAGE_DOUBLES = BN * KC + (RESIDENT ? 0 : BM * KC);
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
           const int nk4 = ch.w >> 2;
 #pragma unroll
           for (int sl = 0; sl < R; ++sl)
-            if (ch.x == sl) mma_chunk_dispatch<MT, NT>(acc[sl], Ap, astride, Bp, beta, nk4, mtc);
+            if (ch.x == sl) mma_chunk_dispatch<MT, NT, KC>(acc[sl], Ap, astride, Bp, beta, nk4, mtc);
           PROF(3)
           release(s);
           PROF(5)
@@ -468,22 +468,22 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
   PROF_FLUSH
 }
 
-template <int R, int MT, int NT, int WM, int CPS, bool RESIDENT>
+template <int R, int MT, int NT, int WM, int CPS, int KC, bool RESIDENT>
 int launch_variant(const ContractParams& p, int grid, size_t smem, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    DLB_CUDA(cudaFuncSetAttribute(contract_kernel<R, MT, NT, WM, CPS, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)contract_smem_limit(CPS)));
+    DLB_CUDA(cudaFuncSetAttribute(contract_kernel<R, MT, NT, WM, CPS, KC, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)contract_smem_limit(CPS)));
     configured = true;
   }
-  contract_kernel<R, MT, NT, WM, CPS, RESIDENT><<<grid, WM * 64, smem, stream>>>(p);
+  contract_kernel<R, MT, NT, WM, CPS, KC, RESIDENT><<<grid, WM * 64, smem, stream>>>(p);
   g_launches++;
   DLB_CUDA(cudaGetLastError());
   return DLB_OK;
 }
 
-template <int R, int MT, int NT, int WM, int CPS>
+template <int R, int MT, int NT, int WM, int CPS, int KC>
 int launch_mode(const ContractParams& p, int grid, size_t smem, cudaStream_t stream) {
-  return p.resident ? launch_variant<R, MT, NT, WM, CPS, true>(p, grid, smem, stream) : launch_variant<R, MT, NT, WM, CPS, false>(p, grid, smem, stream);
+  return p.resident ? launch_variant<R, MT, NT, WM, CPS, KC, true>(p, grid, smem, stream) : launch_variant<R, MT, NT, WM, CPS, KC, false>(p, grid, smem, stream);
 }
 
 }  // namespace
@@ -493,7 +493,7 @@ size_t contract_smem_limit(int ctas_per_sm) {   // dynamic shared memory availab
 }
 
 size_t contract_smem_bytes(const Variant& v, int nstages, bool resident, int ast, int dpad, int ncoef, int npart_max, int ngen) {
-  const int BM = variant_bm(v), BN = variant_bn(v);
+  const int BM = variant_bm(v), BN = variant_bn(v), KC = v.KC;
   const size_t stage = (size_t)(BN * KC + (resident ? 0 : BM * KC)) * 8;
   size_t bytes = nstages * stage + (size_t)(2 * nstages + v.WM + 6) * 8;
   if (resident) bytes += (size_t)BM * ast * 8 + (size_t)ngen * sizeof(GenDev);
@@ -505,10 +505,13 @@ int launch_contract(const Variant& v, const ContractParams& p, int nsm, cudaStre
   const size_t smem = contract_smem_bytes(v, p.nstages, p.resident != 0, p.ast, p.dpad, p.ncoef, p.npart_max, p.ngen);
   if (smem > contract_smem_limit(v.CPS)) { set_error("contraction kernel: shared-memory budget exceeded"); return DLB_ERR_UNSUPPORTED; }
   const int grid = (int)std::min<long long>((long long)nsm * v.CPS, std::max<long long>(p.U, 1));
-  if (v.R == 1 && v.MT == 2 && v.NT == 7 && v.WM == 4 && v.CPS == 2) return launch_mode<1, 2, 7, 4, 2>(p, grid, smem, stream);
-  if (v.R == 1 && v.MT == 2 && v.NT == 7 && v.WM == 8 && v.CPS == 1) return launch_mode<1, 2, 7, 8, 1>(p, grid, smem, stream);
-  if (v.R == 4 && v.MT == 2 && v.NT == 4 && v.WM == 6 && v.CPS == 1) return launch_mode<4, 2, 4, 6, 1>(p, grid, smem, stream);
-  if (v.R == 8 && v.MT == 1 && v.NT == 4 && v.WM == 6 && v.CPS == 1) return launch_mode<8, 1, 4, 6, 1>(p, grid, smem, stream);
+  if (v.R == 1 && v.MT == 2 && v.NT == 7 && v.WM == 4 && v.CPS == 2 && v.KC == 28) return launch_mode<1, 2, 7, 4, 2, 28>(p, grid, smem, stream);
+  if (v.R == 1 && v.MT == 2 && v.NT == 7 && v.WM == 6 && v.CPS == 1 && v.KC == 76) return launch_mode<1, 2, 7, 6, 1, 76>(p, grid, smem, stream);
+  if (v.R == 1 && v.MT == 2 && v.NT == 7 && v.WM == 8 && v.CPS == 1 && v.KC == 36) return launch_mode<1, 2, 7, 8, 1, 36>(p, grid, smem, stream);
+  if (v.R == 4 && v.MT == 1 && v.NT == 7 && v.WM == 6 && v.CPS == 1 && v.KC == 36) return launch_mode<4, 1, 7, 6, 1, 36>(p, grid, smem, stream);
+  if (v.R == 4 && v.MT == 1 && v.NT == 7 && v.WM == 6 && v.CPS == 1 && v.KC == 76) return launch_mode<4, 1, 7, 6, 1, 76>(p, grid, smem, stream);
+  if (v.R == 8 && v.MT == 1 && v.NT == 4 && v.WM == 6 && v.CPS == 1 && v.KC == 36) return launch_mode<8, 1, 4, 6, 1, 36>(p, grid, smem, stream);
+  if (v.R == 8 && v.MT == 1 && v.NT == 4 && v.WM == 6 && v.CPS == 1 && v.KC == 76) return launch_mode<8, 1, 4, 6, 1, 76>(p, grid, smem, stream);
   set_error("no contraction kernel variant for requested tile shape");
   return DLB_ERR_UNSUPPORTED;
 }

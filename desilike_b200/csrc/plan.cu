@@ -92,10 +92,27 @@ static bool is_device_ptr(const void* ptr) {
   return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
 }
 
-static Variant choose_variant(int nslots) {
-  if (nslots <= 1) return Variant{1, 2, 7, 8, 1};   // 16 warps, 128 x 112 tile (build_launch prefers the 2-CTA/SM 8-warp 64 x 112 form)
-  if (nslots <= 4) return Variant{4, 2, 4, 6, 1};   // 12 warps,  96 x  64 tile
-  return Variant{8, 1, 4, 6, 1};                    // 12 warps,  48 x  64 tile
+// Kernel variant for a launch whose blocks need `nslots` accumulator slots: the first candidate whose shared memory fits with
+// at least 2 TMA stages.  Long k-chunks (one per term when K <= 76) amortise the per-chunk cost (stage release, barrier wait,
+// coefficient loads) best; `maxK` is the longest contraction of the launch.
+static Variant pick_variant(const dlb_plan* plan, int nslots, bool resident, int ast, int ncoef, int npart_max, int maxK) {
+  std::vector<Variant> cand;
+  const bool longk = maxK > 36;
+  if (nslots <= 1) {
+    cand.push_back(Variant{1, 2, 7, 4, 2, 28});              // 2 CTAs / SM x 8 warps, 64 x 112 tiles (measured best: C2 62 %, C5 70 %)
+    if (longk) cand.push_back(Variant{1, 2, 7, 6, 1, 76});   // 12 warps,  96 x 112 tile                (C2 60 %, C5 68 %)
+    cand.push_back(Variant{1, 2, 7, 8, 1, 36});              // 16 warps, 128 x 112 tile                (C2 62 %, C5 69 %)
+    if (const char* e = getenv("DLB_R1_VARIANT")) { const Variant v = cand[std::min<size_t>(atoi(e), cand.size() - 1)]; cand.assign(1, v); }
+  } else if (nslots <= 4) {
+    if (longk) cand.push_back(Variant{4, 1, 7, 6, 1, 76});   // 12 warps,  48 x 112 tile, one k-chunk per term (C5 + marg. 59 %; 52 % with KC = 36)
+    cand.push_back(Variant{4, 1, 7, 6, 1, 36});
+  } else {
+    if (longk) cand.push_back(Variant{8, 1, 4, 6, 1, 76});   // 12 warps,  48 x  64 tile
+    cand.push_back(Variant{8, 1, 4, 6, 1, 36});
+  }
+  for (const Variant& v : cand)
+    if (contract_smem_bytes(v, 2, resident, ast, plan->dpad, ncoef, npart_max, plan->ngen) <= contract_smem_limit(v.CPS)) return v;
+  return cand.back();
 }
 
 static int round_ast(int n) {   // row stride of the resident A tile: = 4 (mod 8) keeps the 64-bit fragment loads bank-conflict free
@@ -105,14 +122,7 @@ static int round_ast(int n) {   // row stride of the resident A tile: = 4 (mod 8
 }
 
 // Extent (in feature columns) covered by the k-chunks of a term of length K (mirrors the chunking in build_block_core).
-static int chunk_extent(int K) {
-  const int Kpad = (K + 3) & ~3;
-  const int nch = (Kpad + KC - 1) / KC;
-  int kc = (Kpad + nch - 1) / nch;
-  kc = (kc + 3) & ~3;
-  return Kpad;   // chunks are [k0, min(k0 + kc, Kpad)): they never reach beyond Kpad
-  (void)kc;
-}
+static int chunk_extent(int K) { return (K + 3) & ~3; }   // chunks are [k0, min(k0 + kc, Kpad)): they never reach beyond Kpad
 
 // fcol: absolute first feature column of the term in the per-point feature row; frel: the same relative to its generator's segment
 struct TermSpec { int slot, coef, fcol, frel, K; const double* white; const double* plain; };  // matrices [K, ncols] row-major
@@ -122,7 +132,7 @@ static int build_block_core(dlb_plan* plan, const Variant& var, bool resident, i
                             const double* r0_white, const double* t0_plain, int nconst, const double* gconst_white, Block& blk) {
   blk.ncols = ncols; blk.nslots = nslots; blk.nconst = nconst;
   blk.var = var;
-  const int BN = variant_bn(blk.var);
+  const int BN = variant_bn(blk.var), KC = var.KC;
   blk.ncb = (ncols + BN - 1) / BN;
   std::vector<Chunk> chunks;
   struct Src { int term; int k0; };
@@ -171,7 +181,7 @@ static int build_block_core(dlb_plan* plan, const Variant& var, bool resident, i
     DLB_TRY(upload(plan, tiles.data(), tiles.size(), pass == 0 ? &blk.d_tiles_white : &blk.d_tiles_plain));
   }
   // epilogue constants per column block: [ncb][nconst + 1][BN] = constant whitened Jacobian rows, then r0 / t0 (zero padded)
-  DLB_REQUIRE(nconst + 1 <= KC, "too many constant solved templates in one block (max 35)");
+  DLB_REQUIRE(nconst + 1 <= KC, "too many constant solved templates in one block");
   for (int pass = 0; pass < 2; ++pass) {
     const double* vec = pass == 0 ? r0_white : t0_plain;
     if (!vec) continue;
@@ -224,13 +234,8 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
   L.npart_max = 1;
   for (const Block* b : blocks) L.npart_max = std::max(L.npart_max, b->npart);
   L.nstages = 0;
-  if (L.var.R == 1 && !getenv("DLB_FORCE_CPS1")) {   // two co-resident 8-warp CTAs per SM (run out of phase) when their shared memory fits
-    const Variant v2{1, 2, 7, 4, 2};
-    for (int s = 3; s >= 2; --s)
-      if (contract_smem_bytes(v2, s, resident, L.ast, plan->dpad, ncoef, L.npart_max, plan->ngen) <= contract_smem_limit(2)) { L.var = v2; L.nstages = s; break; }
-  }
   for (int s = 8; s >= 2 && !L.nstages; --s)
-    if (contract_smem_bytes(L.var, s, resident, L.ast, plan->dpad, ncoef, L.npart_max, plan->ngen) <= contract_smem_limit(1)) { L.nstages = s; break; }
+    if (contract_smem_bytes(L.var, s, resident, L.ast, plan->dpad, ncoef, L.npart_max, plan->ngen) <= contract_smem_limit(L.var.CPS)) { L.nstages = s; break; }
   DLB_REQUIRE(L.nstages >= 2, "contraction launch needs too much shared memory (too many parameters, coefficients or solved templates)");
   for (int pass = 0; pass < 2; ++pass) {
     std::vector<BlockDev> tab;
@@ -248,7 +253,7 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
     if (!ok) continue;
     DLB_TRY(upload(plan, tab.data(), tab.size(), pass == 0 ? &L.d_white : &L.d_plain));
     // per-tile TMA schedule: for every block, column block: the k-chunk tiles in order, then the epilogue constants
-    const int BN = variant_bn(L.var);
+    const int BN = variant_bn(L.var), KC = L.var.KC;
     std::vector<SchedEntry> sched;
     for (size_t ib = 0; ib < blocks.size(); ++ib) {
       const Block* b = blocks[ib];
@@ -299,9 +304,9 @@ static int build_mlp(dlb_plan* plan, const dlb_generator_desc& gd, DevGen& g, Ml
     Block& blk = mlp.layers[l];
     std::vector<TermSpec> terms{TermSpec{0, -1, g.foff + off[l], 0, width[l], nullptr, w}};
     const double* bias = w + (size_t)width[l] * width[l + 1];
-    const Variant var = choose_variant(1);
     const int ast = round_ast(chunk_extent(width[l]));
-    const bool resident = contract_smem_bytes(var, 2, true, ast, plan->dpad, 0, 1, plan->ngen) <= contract_smem_limit(1);
+    const bool resident = contract_smem_bytes(Variant{1, 2, 7, 8, 1, 36}, 2, true, ast, plan->dpad, 0, 1, plan->ngen) <= contract_smem_limit(1);
+    const Variant var = pick_variant(plan, 1, resident, resident ? ast : 0, 0, 1, width[l]);
     DLB_TRY(build_block_core(plan, var, resident, width[l + 1], 1, terms, nullptr, bias, 0, nullptr, blk));
     blk.coloff = g.foff + off[l + 1];
     blk.fill = 1; blk.fbase = g.foff + off[l]; blk.gen = -1;
@@ -494,7 +499,7 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
   DLB_TRY(upload(plan, desc->prior_loc, (size_t)desc->d, &plan->d_prior_loc));
   DLB_TRY(upload(plan, desc->prior_scale, (size_t)desc->d, &plan->d_prior_scale));
   // blocks: validate, pick the kernel variant (plan-wide) and the A-operand mode
-  int max_slots = 1, ast = 4;
+  int max_slots = 1, ast = 4, maxK = 0;
   bool resident = true;
   for (int ib = 0; ib < desc->nblocks; ++ib) {
     const dlb_block_desc& bd = desc->blocks[ib];
@@ -509,15 +514,21 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
       DLB_REQUIRE(td.K > 0 && td.foff >= 0 && (td.foff % 2) == 0 && td.foff + td.K <= plan->gens[td.gen].nfeat, "term feature range invalid (foff must be even)");
       if (td.gen != bd.terms[0].gen) resident = false;   // resident A holds ONE generator segment per block
       ast = std::max(ast, td.foff + chunk_extent(td.K));
+      maxK = std::max(maxK, td.K);
     }
   }
-  const Variant var = choose_variant(max_slots);
   ast = round_ast(ast);
-  {
-    int npart_bound = 1;
-    for (int ib = 0; ib < desc->nblocks; ++ib) npart_bound = std::max(npart_bound, desc->blocks[ib].nslots * (desc->blocks[ib].nslots + 1) / 2 + desc->blocks[ib].nslots * desc->blocks[ib].nconst);
-    if (resident && contract_smem_bytes(var, 2, true, ast, plan->dpad, desc->ncoef, npart_bound, desc->ngen) > contract_smem_limit(1) || desc->ngen > 32) resident = false;
+  int npart_bound = 1;
+  for (int ib = 0; ib < desc->nblocks; ++ib) npart_bound = std::max(npart_bound, desc->blocks[ib].nslots * (desc->blocks[ib].nslots + 1) / 2 + desc->blocks[ib].nslots * desc->blocks[ib].nconst);
+  {   // resident A must fit the one-CTA-per-SM form of the slot class with at least 2 TMA stages
+    const Variant v1 = max_slots <= 1 ? Variant{1, 2, 7, 4, 2, 28} : (max_slots <= 4 ? Variant{4, 1, 7, 6, 1, 36} : Variant{8, 1, 4, 6, 1, 36});
+    if (resident && (contract_smem_bytes(v1, 2, true, ast, plan->dpad, desc->ncoef, npart_bound, desc->ngen) > contract_smem_limit(v1.CPS) || desc->ngen > 32)) {
+      // single-slot launches: a 16-warp CTA with the whole SM's shared memory is the roomiest form
+      if (max_slots > 1 || contract_smem_bytes(Variant{1, 2, 7, 8, 1, 36}, 2, true, ast, plan->dpad, desc->ncoef, npart_bound, desc->ngen) > contract_smem_limit(1) || desc->ngen > 32)
+        resident = false;
+    }
   }
+  const Variant var = pick_variant(plan, max_slots, resident, resident ? ast : 0, desc->ncoef, npart_bound, maxK);
   plan->resident = resident;
   if (resident) {   // factor lists of the monomials, one table per generator, indexed by segment column
     plan->d_paths.resize(desc->ngen, nullptr);
