@@ -72,8 +72,8 @@ struct GenDev {       // Taylor generator constants for the in-kernel monomial e
 struct BlockDev {     // one output block as seen by the contraction kernel (device table)
   const Chunk* chunks;
   const double* tiles;                 // [ncb][nchunks][BN][KC] pre-tiled term matrices (n-major, zero padded)
-  const double* epi;                   // [ncb][nconst + 1][BN] epilogue constants per column block: constant whitened Jacobian rows,
-                                       // then r0 (subtracted from slot 0 in eval mode / added in output mode)
+  const double* epi;                   // [ncb][BN] epilogue constants per column block: r0 (subtracted from slot 0 in eval mode / added in
+                                       // output mode); the nconst auxiliary columns ncols .. ncols + nconst - 1 carry r0 . g_i
   const unsigned long long* paths;     // [ast][2] monomial factor lists of the block's Taylor generator (resident A), else NULL:
                                        // word 0: byte k = parameter-tile column of factor k (top byte 0xFF: structural zero column),
                                        // word 1: byte k = index into GenDev::cval

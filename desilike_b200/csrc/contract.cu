@@ -369,13 +369,12 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
           if (++s == S) { s = 0; ph ^= 1; }
         }
 
-        // ===== epilogue: constants of this column block arrive as one more chunk: rows [0, nconst) = constant whitened
-        //       Jacobian rows, row nconst = r0 =====
+        // ===== epilogue: r0 of this column block arrives as one more transaction of the ring =====
         mbar_wait(&full[s], ph);
         PROF(0)
         const int colw = wn * (NT * 8) + 2 * lc;  // + nt * 8 + e
         const double* epi = stage_base + (size_t)s * STAGE_DOUBLES;
-        const double* r0 = epi + (size_t)nconst * BN;
+        const double* r0 = epi;
         if (p.mode == 1) {
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
@@ -403,6 +402,31 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) { acc[0][mt][nt][0] -= rr.x; acc[0][mt][nt][1] -= rr.y; }
           }
+          // auxiliary columns ncols .. ncols + nconst - 1 of the block hold slot_a . g_i (dot products with the constant whitened
+          // Jacobian rows, produced by the contraction itself): move them to their Gram entries and clear them so that the
+          // pairwise sums below only see data-vector columns
+          const int nS = (Rb * (Rb + 1)) / 2;
+          for (int i = 0; i < nconst; ++i) {
+            const int within = blk->ncols + i - cb * BN;
+            if (within < 0 || within >= BN) continue;
+            const int wni = within / (NT * 8), w2 = within - wni * (NT * 8), nti = w2 >> 3, lci = (w2 & 7) >> 1, ei = w2 & 1;
+            const bool mine = wn == wni && lc == lci;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+              for (int e = 0; e < 2; ++e)
+                if (nt == nti && e == ei) {
+#pragma unroll
+                  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int a = 0; a < R; ++a) {
+                      if (mine) {   // only the lane that owns this column: the same register index is a data column elsewhere
+                        if (mt < mtc && a < Rb) red[((size_t)wn * BM + mt * UNIT + wm * 8 + lr) * npm + nS + i * Rb + a] += acc[a][mt][nt][e];
+                        acc[a][mt][nt][e] = 0.;
+                      }
+                    }
+                }
+          }
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             if (mt < mtc) {
@@ -418,27 +442,6 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
                     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
                     sum += __shfl_xor_sync(0xffffffffu, sum, 2);
                     if (lc == 0) redrow[a * Rb - (a * (a - 1)) / 2 + (bb - a)] += sum;
-                  }
-                }
-              }
-              const int nS = (Rb * (Rb + 1)) / 2;
-              for (int i = 0; i < nconst; ++i) {
-                const double* g = epi + (size_t)i * BN + colw;
-                double gv[NT][2];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                  const double2 t = *reinterpret_cast<const double2*>(g + nt * 8);
-                  gv[nt][0] = t.x; gv[nt][1] = t.y;
-                }
-#pragma unroll
-                for (int a = 0; a < R; ++a) {
-                  if (a < Rb) {
-                    double sum = 0.;
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) sum += acc[a][mt][nt][0] * gv[nt][0] + acc[a][mt][nt][1] * gv[nt][1];
-                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                    if (lc == 0) redrow[nS + i * Rb + a] += sum;
                   }
                 }
               }

@@ -133,7 +133,12 @@ static int build_block_core(dlb_plan* plan, const Variant& var, bool resident, i
   blk.ncols = ncols; blk.nslots = nslots; blk.nconst = nconst;
   blk.var = var;
   const int BN = variant_bn(blk.var), KC = var.KC;
-  blk.ncb = (ncols + BN - 1) / BN;
+  // Auxiliary columns: the dot products of every slot with the constant whitened Jacobian rows g_i are linear in the features,
+  //   slot_a . g_i = sum_t coef_t f_t . (M_t g_i),
+  // so they are obtained for free from the contraction itself by appending the nconst columns M_t g_i to the term matrices
+  // (usually inside the zero padding of the last column block) instead of nconst extra dot products per column block.
+  const int ncols_ext = ncols + nconst;
+  blk.ncb = (ncols_ext + BN - 1) / BN;
   std::vector<Chunk> chunks;
   struct Src { int term; int k0; };
   std::vector<Src> srcs;
@@ -171,27 +176,33 @@ static int build_block_core(dlb_plan* plan, const Variant& var, bool resident, i
         if (!mat) continue;
         for (int n = 0; n < BN; ++n) {
           const int col = cb * BN + n;
-          if (col >= ncols) break;
+          if (col >= ncols_ext) break;
           for (int k = 0; k < chunks[c].kc; ++k) {
             const int kk = srcs[c].k0 + k;
-            if (kk < td.K) dst[(size_t)n * KC + k] = mat[(long long)kk * ncols + col];
+            if (kk >= td.K) continue;
+            if (col < ncols) dst[(size_t)n * KC + k] = mat[(long long)kk * ncols + col];
+            else if (pass == 0) {   // auxiliary column i = col - ncols: (M_t g_i)[kk]
+              const double* g = gconst_white + (size_t)(col - ncols) * ncols;
+              double acc = 0.;
+              for (int j = 0; j < ncols; ++j) acc += mat[(long long)kk * ncols + j] * g[j];
+              dst[(size_t)n * KC + k] = acc;
+            }
           }
         }
       }
     DLB_TRY(upload(plan, tiles.data(), tiles.size(), pass == 0 ? &blk.d_tiles_white : &blk.d_tiles_plain));
   }
-  // epilogue constants per column block: [ncb][nconst + 1][BN] = constant whitened Jacobian rows, then r0 / t0 (zero padded)
-  DLB_REQUIRE(nconst + 1 <= KC, "too many constant solved templates in one block");
+  // epilogue constants per column block: [ncb][BN] = r0 / t0, zero padded; auxiliary columns carry r0 . g_i
   for (int pass = 0; pass < 2; ++pass) {
     const double* vec = pass == 0 ? r0_white : t0_plain;
     if (!vec) continue;
-    std::vector<double> epi((size_t)blk.ncb * (nconst + 1) * BN, 0.);
-    for (int cb = 0; cb < blk.ncb; ++cb)
-      for (int n = 0; n < BN; ++n) {
-        const int col = cb * BN + n;
-        if (col >= ncols) break;
-        for (int i = 0; i < nconst; ++i) epi[((size_t)cb * (nconst + 1) + i) * BN + n] = gconst_white[(size_t)i * ncols + col];
-        epi[((size_t)cb * (nconst + 1) + nconst) * BN + n] = vec[col];
+    std::vector<double> epi((size_t)blk.ncb * BN, 0.);
+    for (int col = 0; col < ncols; ++col) epi[col] = vec[col];
+    if (pass == 0)
+      for (int i = 0; i < nconst; ++i) {
+        double acc = 0.;
+        for (int j = 0; j < ncols; ++j) acc += vec[j] * gconst_white[(size_t)i * ncols + j];
+        epi[ncols + i] = acc;
       }
     DLB_TRY(upload(plan, epi.data(), epi.size(), pass == 0 ? &blk.d_epi_white : &blk.d_epi_plain));
   }
@@ -261,7 +272,7 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
       for (int cb = 0; cb < b->ncb; ++cb) {
         for (int c = 0; c < b->nchunks; ++c)
           sched.push_back(SchedEntry{tab[ib].tiles + ((size_t)cb * b->nchunks + c) * ((size_t)BN * KC), (unsigned)(BN * KC * 8), (int)((ib << 16) | (unsigned)c)});
-        sched.push_back(SchedEntry{tab[ib].epi + (size_t)cb * (b->nconst + 1) * BN, (unsigned)((b->nconst + 1) * BN * 8), -1});
+        sched.push_back(SchedEntry{tab[ib].epi + (size_t)cb * BN, (unsigned)(BN * 8), -1});
       }
     }
     L.nsched = (int)sched.size();

@@ -270,9 +270,11 @@ class Lowered(object):
         contract = 0
         gram = 0
         for blk in self.blocks:
-            for (slot, coef, gen, foff, K) in blk['terms']:
-                contract += 2 * K * blk['ncols']
             R, nc = blk['nslots'], len(blk['const_solved'])
-            gram += 2 * blk['ncols'] * (R * (R + 1) // 2 + R * nc)
+            for (slot, coef, gen, foff, K) in blk['terms']:
+                # + nc auxiliary columns per term: the dot products with the constant whitened Jacobian rows come out of the
+                # contraction itself (csrc/plan.cu: build_block_core)
+                contract += 2 * K * (blk['ncols'] + nc)
+            gram += 2 * blk['ncols'] * (R * (R + 1) // 2)
         solve = self.ns**3 // 3 + 2 * self.ns**2
         return dict(contract=contract, gram=gram, solve=solve, total=contract + gram + solve)
