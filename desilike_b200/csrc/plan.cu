@@ -48,6 +48,8 @@ struct dlb_plan {
   std::vector<dlb::DevGen> gens;
   std::vector<dlb::Block> blocks;
   std::vector<dlb::MlpLayers> mlps;   // one per generator (empty unless kind == MLP)
+  size_t mlp_fused_smem = 0;           // > 0: every MLP emulator runs in the fused kernel (csrc/mlp.cu)
+  dlb::DevGen* d_devgens = nullptr; int* d_mlp_index = nullptr; int nmlp = 0;
   std::vector<std::pair<dlb::Launch, int>> mlp_launches;   // hidden layers of ALL MLP generators, one launch per (depth, activation, A mode)
   dlb::DevCoef* d_coefs = nullptr;
   int* d_prior_kind = nullptr;
@@ -317,7 +319,7 @@ static int build_mlp(dlb_plan* plan, const dlb_generator_desc& gd, DevGen& g, Ml
     const double* bias = w + (size_t)width[l] * width[l + 1];
     const int ast = round_ast(chunk_extent(width[l]));
     const bool resident = contract_smem_bytes(Variant{1, 2, 7, 8, 1, 36}, 2, true, ast, plan->dpad, 0, 1, plan->ngen) <= contract_smem_limit(1);
-    const Variant var = pick_variant(plan, 1, resident, resident ? ast : 0, 0, 1, width[l]);
+    const Variant var = resident ? Variant{1, 2, 7, 8, 1, 36} : pick_variant(plan, 1, resident, 0, 0, 1, width[l]);   // 128-row tiles amortise the per-(tile, layer) latency
     DLB_TRY(build_block_core(plan, var, resident, width[l + 1], 1, terms, nullptr, bias, 0, nullptr, blk));
     blk.coloff = g.foff + off[l + 1];
     blk.fill = 1; blk.fbase = g.foff + off[l]; blk.gen = -1;
@@ -355,10 +357,16 @@ static void fill_params(const dlb_plan* plan, const Launch& L, ContractParams& c
 static int run_front(dlb_plan* plan, const double* d_params, long long N, long long npad, cudaStream_t stream, bool force_taylor = false) {
   for (size_t ig = 0; ig < plan->gens.size(); ++ig) {
     const DevGen& g = plan->gens[ig];
-    if (g.kind == DLB_GEN_MLP) { DLB_TRY(launch_mlp_input(g, d_params, plan->d, N, npad, plan->w_F, plan->fstride, stream)); continue; }
+    if (g.kind == DLB_GEN_MLP) {
+      if (!plan->mlp_fused_smem) DLB_TRY(launch_mlp_input(g, d_params, plan->d, N, npad, plan->w_F, plan->fstride, stream));
+      continue;
+    }
     if (g.kind == DLB_GEN_TAYLOR && g.aux[6] && plan->resident && !force_taylor) continue;   // evaluated inside the contraction kernel
     DLB_TRY(launch_features(g, d_params, plan->d, N, npad, plan->w_F, plan->fstride, stream));
   }
+  if (plan->mlp_fused_smem)
+    return launch_mlp_fused(plan->d_devgens, plan->d_mlp_index, plan->nmlp, plan->mlp_fused_smem, d_params, plan->d, N, npad, plan->w_F, plan->fstride,
+                            plan->nsm, stream);
   for (const auto& la : plan->mlp_launches) {   // hidden layers, depth by depth, all MLP emulators of the likelihood in one launch
     const Launch& L = la.first;
     ContractParams cp;
@@ -490,6 +498,23 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
     plan->gens.push_back(g);
   }
   plan->fstride = foff;
+  {   // fused MLP forward when every MLP emulator qualifies (hidden widths <= 64, weights fit in shared memory)
+    std::vector<int> mlp_index;
+    size_t smem = 0;
+    bool ok = true;
+    for (int ig = 0; ig < desc->ngen; ++ig)
+      if (desc->gens[ig].kind == DLB_GEN_MLP) {
+        mlp_index.push_back(ig);
+        const size_t need = mlp_fused_smem(desc->gens[ig].idata);
+        if (!need || need > (size_t)200 * 1024) ok = false;
+        smem = std::max(smem, need);
+      }
+    if (ok && !mlp_index.empty() && !getenv("DLB_NO_FUSED_MLP")) {
+      plan->mlp_fused_smem = smem; plan->nmlp = (int)mlp_index.size();
+      DLB_TRY(upload(plan, plan->gens.data(), plan->gens.size(), &plan->d_devgens));
+      DLB_TRY(upload(plan, mlp_index.data(), mlp_index.size(), &plan->d_mlp_index));
+    }
+  }
   // coefficients
   std::vector<DevCoef> coefs(std::max(desc->ncoef, 1));
   for (int j = 0; j < desc->ncoef; ++j) {
