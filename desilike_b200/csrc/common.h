@@ -149,6 +149,7 @@ struct SolveParams {
   const double* x0; const double* xprec; const double* xloc; const double* xlo; const double* xhi; const int* xkind;
   // independent groups of solved parameters (connected components over the likelihood blocks); ncomp = 0 -> one dense problem
   int ncomp; const int* comp_off; const int* comp_idx; const int* comp_nmarg;
+  int npos; const int* comp_pos; const double* comp_m0;   // intra-group matrix positions (i * (ns + 1) + j) and their constant part
   double* logpost; double* loglike; double* logprior; double* xsolved; int* status;
 };
 int launch_solve(const SolveParams& p, cudaStream_t stream);

@@ -57,7 +57,8 @@ struct dlb_plan {
   double *d_M0 = nullptr, *d_g0 = nullptr, *d_x0 = nullptr, *d_xprec = nullptr, *d_xloc = nullptr, *d_xlo = nullptr, *d_xhi = nullptr;
   int* d_xkind = nullptr;
   int ncomp = 0;                       // independent groups of solved parameters (0: solve one dense system)
-  int *d_comp_off = nullptr, *d_comp_idx = nullptr, *d_comp_nmarg = nullptr;
+  int *d_comp_off = nullptr, *d_comp_idx = nullptr, *d_comp_nmarg = nullptr, *d_comp_pos = nullptr;
+  double* d_comp_m0 = nullptr; int npos = 0;
   dlb::SolveBlock* d_solve_blocks = nullptr;
   long long ptotal = 0;  // partial rows (in units of npad doubles)
   std::vector<void*> owned;
@@ -689,6 +690,17 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
       DLB_TRY(upload(plan, comp_off.data(), comp_off.size(), &plan->d_comp_off));
       DLB_TRY(upload(plan, comp_idx.data(), comp_idx.size(), &plan->d_comp_idx));
       DLB_TRY(upload(plan, comp_nmarg.data(), comp_nmarg.size(), &plan->d_comp_nmarg));
+      std::vector<int> pos;
+      std::vector<double> m0v;
+      for (size_t c = 0; c + 1 < comp_off.size(); ++c)
+        for (int a = comp_off[c]; a < comp_off[c + 1]; ++a)
+          for (int b = comp_off[c]; b < comp_off[c + 1]; ++b) {
+            pos.push_back(comp_idx[a] * (ns + 1) + comp_idx[b]);
+            m0v.push_back(M0[(size_t)comp_idx[a] * ns + comp_idx[b]]);
+          }
+      plan->npos = (int)pos.size();
+      DLB_TRY(upload(plan, pos.data(), pos.size(), &plan->d_comp_pos));
+      DLB_TRY(upload(plan, m0v.data(), m0v.size(), &plan->d_comp_m0));
     }
   }
   for (auto& e : plan->ev) DLB_CUDA(cudaEventCreate(&e));
@@ -736,6 +748,7 @@ int dlb_eval_batch(dlb_plan* plan, const double* params, int64_t N, double* logp
     sp.ns = ns; sp.nmarg = plan->nmarg; sp.M0 = plan->d_M0; sp.g0 = plan->d_g0; sp.x0 = plan->d_x0; sp.xprec = plan->d_xprec;
     sp.xloc = plan->d_xloc; sp.xlo = plan->d_xlo; sp.xhi = plan->d_xhi; sp.xkind = plan->d_xkind;
     sp.ncomp = plan->ncomp; sp.comp_off = plan->d_comp_off; sp.comp_idx = plan->d_comp_idx; sp.comp_nmarg = plan->d_comp_nmarg;
+    sp.npos = plan->npos; sp.comp_pos = plan->d_comp_pos; sp.comp_m0 = plan->d_comp_m0;
     double* w = plan->w_out;
     sp.logpost = logposterior ? (lp_dev ? logposterior + start : w) : nullptr;
     sp.loglike = loglikelihood ? (ll_dev ? loglikelihood + start : w + npad) : nullptr;

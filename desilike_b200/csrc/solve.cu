@@ -44,6 +44,7 @@ __global__ void finish_nosolve_kernel(const SolveParams p) {
 }
 
 constexpr int SOLVE_WARPS = 4;
+constexpr int SOLVE_NREG = 8;   // groups of up to 8 solved parameters are factorised in registers
 
 __global__ void __launch_bounds__(SOLVE_WARPS * 32) finish_solve_kernel(const SolveParams p) {
   extern __shared__ double sm[];
@@ -57,7 +58,11 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) finish_solve_kernel(const So
   const long long pt = (long long)blockIdx.x * SOLVE_WARPS + warp;
   if (pt >= p.N) return;
 
-  for (int i = lane; i < ns * ns; i += 32) M[(i / ns) * ld + (i % ns)] = p.M0[i];
+  if (p.ncomp > 0) {   // only the intra-group entries are ever read: initialise those (prior precision + constant-row Gram)
+    for (int t = lane; t < p.npos; t += 32) M[p.comp_pos[t]] = p.comp_m0[t];
+  } else {
+    for (int i = lane; i < ns * ns; i += 32) M[(i / ns) * ld + (i % ns)] = p.M0[i];
+  }
   for (int i = lane; i < ns; i += 32) { gL[i] = 0.; }
   __syncwarp();
   double chi2 = 0.;
@@ -95,6 +100,51 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) finish_solve_kernel(const So
     for (int c = lane; c < p.ncomp; c += 32) {
       const int o = p.comp_off[c], n = p.comp_off[c + 1] - o, nm = p.comp_nmarg[c];
       const int* idx = p.comp_idx + o;
+      if (n <= SOLVE_NREG) {
+        // ---- register-resident factorisation (fully unrolled, guarded by the group size): no shared-memory round trips ----
+        double a[SOLVE_NREG][SOLVE_NREG], yy[SOLVE_NREG];
+        int id[SOLVE_NREG];
+#pragma unroll
+        for (int i = 0; i < SOLVE_NREG; ++i) id[i] = i < n ? idx[i] : 0;
+#pragma unroll
+        for (int i = 0; i < SOLVE_NREG; ++i) {
+          yy[i] = i < n ? g[id[i]] : 0.;
+#pragma unroll
+          for (int j = 0; j <= i; ++j) a[i][j] = (i < n) ? M[id[i] * ld + id[j]] : (i == j ? 1. : 0.);
+        }
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < SOLVE_NREG; ++j) {
+          const double djj = a[j][j];
+          if (j < n && (!(djj > 0.) || !isfinite(djj))) ok = false;
+          const double l = sqrt(djj), inv = 1. / l;
+          if (j < nm) logdet += 2. * log(l);
+          a[j][j] = l;
+#pragma unroll
+          for (int i = j + 1; i < SOLVE_NREG; ++i) a[i][j] *= inv;
+#pragma unroll
+          for (int i = j + 1; i < SOLVE_NREG; ++i)
+#pragma unroll
+            for (int k = j + 1; k <= i; ++k) a[i][k] -= a[i][j] * a[k][j];
+        }
+        if (!ok) { spd = false; continue; }
+#pragma unroll
+        for (int j = 0; j < SOLVE_NREG; ++j) {   // forward L y = g
+          yy[j] /= a[j][j];
+#pragma unroll
+          for (int i = j + 1; i < SOLVE_NREG; ++i) yy[i] -= a[i][j] * yy[j];
+        }
+#pragma unroll
+        for (int j = SOLVE_NREG - 1; j >= 0; --j) {   // backward L^T dx = y
+          yy[j] /= a[j][j];
+#pragma unroll
+          for (int i = 0; i < j; ++i) yy[i] -= a[j][i] * yy[j];
+        }
+#pragma unroll
+        for (int i = 0; i < SOLVE_NREG; ++i)
+          if (i < n) dx[id[i]] = yy[i];
+        continue;
+      }
       bool ok = true;
       for (int j = 0; j < n && ok; ++j) {
         const int J = idx[j];

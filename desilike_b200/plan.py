@@ -37,6 +37,7 @@ class Plan(object):
         self._handle = handle
         # plan order -> spec order of the solved parameters
         self._unperm = np.argsort(self.lowered.solved_order) if self.ns else np.zeros(0, dtype=int)
+        self._identity_perm = bool(np.array_equal(self._unperm, np.arange(self.ns)))   # all '.marg' (or all '.best'): plan order == spec order
 
     def close(self):
         if getattr(self, '_handle', None):
@@ -66,7 +67,7 @@ class Plan(object):
         _capi.check(self._lib.dlb_eval_batch(self._handle, X.ctypes.data, N, res['logposterior'].ctypes.data, res['loglikelihood'].ctypes.data,
                                              res['logprior'].ctypes.data, xs.ctypes.data if xs is not None else None,
                                              st.ctypes.data if st is not None else None, None))
-        if xs is not None: res['x_solved'] = xs[:, self._unperm]
+        if xs is not None: res['x_solved'] = xs if self._identity_perm else xs[:, self._unperm]
         if st is not None: res['status'] = st
         return res
 
@@ -86,7 +87,7 @@ class Plan(object):
         _capi.check(self._lib.dlb_eval_batch(self._handle, X.data_ptr(), N, ptr('logposterior'), ptr('loglikelihood'), ptr('logprior'),
                                              ptr('x_solved_plan_order'), ptr('status'), ctypes.c_void_p(stream)))
         if own and 'x_solved_plan_order' in out:
-            out['x_solved'] = out['x_solved_plan_order'][:, torch.as_tensor(self._unperm, device=X.device)]
+            out['x_solved'] = out['x_solved_plan_order'] if self._identity_perm else out['x_solved_plan_order'][:, torch.as_tensor(self._unperm, device=X.device)]
         return out
 
     def theory(self, X):
