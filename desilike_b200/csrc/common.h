@@ -129,7 +129,6 @@ int launch_mlp_input(const DevGen& g, const double* params, int d, long long N, 
 size_t mlp_fused_smem(const int* idata_host);
 int launch_mlp_fused(const DevGen* d_gens, const int* d_mlp_index, int nmlp, size_t smem, const double* params, int d, long long N, long long npad,
                      double* F, int fstride, int nsm, cudaStream_t stream);
-int launch_coefs(const DevCoef* coefs, int ncoef, const double* params, int d, long long N, long long npad, double* C, int cstride, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------------------------------
 // prior + marginalisation solve (csrc/solve.cu)

@@ -1,5 +1,5 @@
-// Feature generators: theta[N, d] -> per-point feature rows F[Npad, fstride] (one padded segment per generator) and
-// per-point bias-monomial coefficients C[Npad, cstride].  Rows >= N and the padding columns are written as zeros so the
+// Feature generators: theta[N, d] -> per-point feature rows F[Npad, fstride] (one padded segment per generator).  The Taylor kernel is
+// only used by the debug entry dlb_features_batch and for orders > 7 (otherwise the monomials are evaluated inside contract_kernel).  Rows >= N and the padding columns are written as zeros so the
 // contraction kernel can consume full tiles without masking.
 #include "common.h"
 
@@ -63,28 +63,6 @@ __global__ void mlp_input_kernel(const DevGen g, const double* __restrict__ para
   row[g.aux[0] + j] = v;
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// bias-monomial coefficients  c = scale * prod_f theta[idx_f]^pow_f   (tracer combine, reference full_shape.py:545-550)
-// ---------------------------------------------------------------------------------------------------------------------
-__global__ void coef_kernel(const DevCoef* __restrict__ coefs, int ncoef, const double* __restrict__ params, int d, long long N,
-                            long long npad, double* __restrict__ C, int cstride) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long p = idx / cstride;
-  const int j = (int)(idx - p * cstride);
-  if (p >= npad) return;
-  double c = 0.;
-  if (p < N && j < ncoef) {
-    const DevCoef cf = coefs[j];
-    c = cf.scale;
-    for (int f = 0; f < cf.nf; ++f) {
-      const double x = params[p * d + cf.idx[f]];
-      const int e = cf.pow[f];
-      c *= e >= 0 ? ipow(x, e) : 1. / ipow(x, -e);
-    }
-  }
-  C[p * cstride + j] = c;
-}
-
 }  // namespace
 
 int launch_features(const DevGen& g, const double* params, int d, long long N, long long npad, double* F, int fstride, cudaStream_t stream) {
@@ -103,16 +81,6 @@ int launch_mlp_input(const DevGen& g, const double* params, int d, long long N, 
   const int threads = 256;
   const long long total = npad * (g.nparams + 2);
   mlp_input_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(g, params, d, N, npad, F, fstride);
-  g_launches++;
-  DLB_CUDA(cudaGetLastError());
-  return DLB_OK;
-}
-
-int launch_coefs(const DevCoef* coefs, int ncoef, const double* params, int d, long long N, long long npad, double* C, int cstride,
-                 cudaStream_t stream) {
-  const int threads = 256;
-  const long long total = npad * cstride;
-  coef_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(coefs, ncoef, params, d, N, npad, C, cstride);
   g_launches++;
   DLB_CUDA(cudaGetLastError());
   return DLB_OK;

@@ -473,7 +473,7 @@ __device__ __forceinline__ void fft2048_tail(double2* D, const double2* __restri
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(FFT_THREADS) fftlog_kernel(const DevGen g, long long N, double* __restrict__ F, int fstride) {
+__global__ void __launch_bounds__(FFT_THREADS, 5) fftlog_kernel(const DevGen g, long long N, double* __restrict__ F, int fstride) {
   extern __shared__ double2 D[];
   const int nkin = g.idata[0], nell = g.idata[1], ns = g.idata[8], poff = g.idata[12];
   const int Ng = g.idata[13], Np = g.idata[14], padl = g.idata[15];
