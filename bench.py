@@ -25,7 +25,21 @@ import sys
 import threading
 import time
 
+# stdout must carry exactly ONE JSON line: libraries (NCCL's version banner, ...) write to file descriptor 1 directly, so the real
+# stdout is kept aside for the result line and fd 1 is pointed at stderr for everything else
+_RESULT = os.fdopen(os.dup(1), 'w')
+os.dup2(2, 1)
+if 'reference' in sys.argv:   # the CPU arm uses every host core (torchrun exports OMP_NUM_THREADS=1); must precede the NumPy import
+    for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_v] = str(os.cpu_count())
+
 import numpy as np
+
+
+def emit(line):
+    _RESULT.write(json.dumps(line) + '\n')
+    _RESULT.flush()
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -129,7 +143,7 @@ def run_reference(args, spec, label, X):
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                              'sample': '{:d} points/step x {:d} steps, oracle/pipeline.py (vectorised NumPy, threaded BLAS)'.format(sample, args.steps)},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ensemble(args):
@@ -217,7 +231,7 @@ def run_ensemble(args):
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
                          'kernel': 'dlb::contract_kernel inside the whole iteration (propose + likelihood + accept)', 'flops_per_eval_folded': flops,
                          'peak_source': 'dlb_measure_fp64_peak(DMMA.8x8x4 register loop) measured in this run'}}
-    if rank == 0: print(json.dumps(line))
+    if rank == 0: emit(line)
     if world > 1: dist.destroy_process_group()
 
 
@@ -266,16 +280,27 @@ def main():
     outs = dict(logposterior=torch.empty(N, dtype=torch.float64, device=dev), loglikelihood=torch.empty(N, dtype=torch.float64, device=dev),
                 logprior=torch.empty(N, dtype=torch.float64, device=dev), status=torch.empty(N, dtype=torch.int32, device=dev))
     if plan.ns: outs['x_solved_plan_order'] = torch.empty((N, plan.ns), dtype=torch.float64, device=dev)
-    gathered = torch.empty(world * N, dtype=torch.float64, device=dev) if world > 1 else None
-    if world > 1: outs['logposterior'] = gathered[rank * N:(rank + 1) * N]   # the finish kernel writes straight into the all-gather buffer (in-place collective)
+    # The path's only exchange: all-gather of the log-posteriors (reference base.py:335, samplers/base.py:200).  The finish kernel
+    # writes straight into this rank's slice of the gather buffer (in-place collective); two buffers alternate so that the NCCL
+    # all-gather of step i (its own stream) overlaps the evaluation of step i + 1 -- no rank needs the other ranks' values to go on.
+    gathered = [torch.empty(world * N, dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
+    works = [None, None]
 
     def step(i):
-        plan.eval(pool[i % npool], out=outs)
-        if world > 1:   # the path's only exchange: all-gather of the log-posteriors (reference base.py:335, samplers/base.py:200)
-            dist.all_gather_into_tensor(gathered, outs['logposterior'])
+        if world > 1:
+            b = i % 2
+            if works[b] is not None: works[b].wait()
+            outs['logposterior'] = gathered[b][rank * N:(rank + 1) * N]
+            plan.eval(pool[i % npool], out=outs)
+            works[b] = dist.all_gather_into_tensor(gathered[b], outs['logposterior'], async_op=True)
+        else:
+            plan.eval(pool[i % npool], out=outs)
 
     def barrier():
-        if world > 1: dist.barrier()
+        if world > 1:
+            for b in range(2):
+                if works[b] is not None: works[b].wait(); works[b] = None
+            dist.barrier()
         torch.cuda.synchronize()
 
     for i in range(args.warmup): step(i)
@@ -294,8 +319,8 @@ def main():
     if len(sampler.samples) < 5:   # timed region too short for NVML sampling: keep sampling over an untimed replay of the same steps
         t_end = time.perf_counter() + 0.5
         i = 0
-        while time.perf_counter() < t_end:
-            step(i); i += 1
+        while time.perf_counter() < t_end:   # no collective here: the number of replayed steps is time based, hence rank dependent
+            plan.eval(pool[i % npool], out=outs); i += 1
             if i % 32 == 0: torch.cuda.synchronize()
         torch.cuda.synchronize()
     clocks = sampler.result()
@@ -318,7 +343,9 @@ def main():
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         plan.eval(hosts[i % 4], out=hout)
-        if world > 1: dist.all_gather_into_tensor(gathered, outs['logposterior'])
+        if world > 1:   # the host result goes back to the device-side gather buffer: H2D of this rank's slice + all-gather
+            gathered[0][rank * N:(rank + 1) * N].copy_(torch.from_numpy(hout['logposterior']), non_blocking=True)
+            dist.all_gather_into_tensor(gathered[0], gathered[0][rank * N:(rank + 1) * N])
     barrier()
     dt = time.perf_counter() - t0
     if world > 1:
@@ -395,7 +422,7 @@ def main():
         line['cpu_baseline'] = {'value': cpu_value, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
                                 'sample': '{:d} points of the same workload, oracle/pipeline.py (vectorised NumPy, threaded BLAS), {:.0f} s'.format(cpu_done, args.cpu_seconds)}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
