@@ -100,6 +100,37 @@ def test_full_size_properties(gpu_required):
     plan.close()
 
 
+@pytest.mark.parametrize('nbins', [36, 37, 38])
+def test_auxiliary_columns_across_column_block_boundary(gpu_required, nbins):
+    """Marginalised tracer whose data vector (3 nbins columns) + 4 auxiliary columns (constant Jacobian rows) exactly fills (108 + 4),
+    straddles (111 + 4) or starts a new 112-wide column block (114 + 4)."""
+    spec = configs.config_c5(ntracers=1, nkin=60, nbins=nbins, order=2, solved=True)
+    check(spec, 200, seed=51 + nbins, solved=True)
+
+
+def test_fused_mlp_matches_per_layer_launches(gpu_required):
+    """The fused MLP forward kernel and the per-layer launches of the contraction kernel (DLB_NO_FUSED_MLP=1) agree to rounding."""
+    import os
+    import desilike_b200
+    spec = configs.config_c4(ntracers=2, nkin=40, nbins=10)
+    X = configs.sample_points(spec, 300, seed=9)
+    plan = desilike_b200.Plan(spec)
+    fused = plan.eval(X)
+    theory_fused = plan.theory(X)
+    plan.close()
+    os.environ['DLB_NO_FUSED_MLP'] = '1'
+    try:
+        plan = desilike_b200.Plan(spec)
+        layered = plan.eval(X)
+        theory_layered = plan.theory(X)
+        plan.close()
+    finally:
+        del os.environ['DLB_NO_FUSED_MLP']
+    scale = np.max(np.abs(theory_layered), axis=0)
+    assert np.max(np.abs(theory_fused - theory_layered) / scale) < 1e-12
+    assert np.allclose(fused['logposterior'], layered['logposterior'], rtol=1e-10, atol=1e-8)
+
+
 @pytest.mark.parametrize('name', ['c5', 'c5solved', 'c4'])
 def test_five_tracer_bench_configs_full_size(gpu_required, name):
     """The 5-tracer configurations exactly as bench.py runs them (n = 2010 data points, T = 70 / MLP 64x3, 35 marginalised terms):
