@@ -102,7 +102,8 @@ static Variant pick_variant(const dlb_plan* plan, int nslots, bool resident, int
   std::vector<Variant> cand;
   const bool longk = maxK > 36;
   if (nslots <= 1) {
-    cand.push_back(Variant{1, 2, 7, 4, 2, 28});              // 2 CTAs / SM x 8 warps, 64 x 112 tiles (measured best: C2 62 %, C5 70 %)
+    if (maxK > 28) cand.push_back(Variant{1, 2, 7, 4, 2, 36});   // 2 CTAs / SM x 8 warps, 64 x 112 tiles, longer k-chunks when they fit
+    cand.push_back(Variant{1, 2, 7, 4, 2, 28});              // 2 CTAs / SM x 8 warps, 64 x 112 tiles (measured: C2 62 %, C5 70 %)
     if (longk) cand.push_back(Variant{1, 2, 7, 6, 1, 76});   // 12 warps,  96 x 112 tile                (C2 60 %, C5 68 %)
     cand.push_back(Variant{1, 2, 7, 8, 1, 36});              // 16 warps, 128 x 112 tile                (C2 62 %, C5 69 %)
     if (const char* e = getenv("DLB_R1_VARIANT")) { const Variant v = cand[std::min<size_t>(atoi(e), cand.size() - 1)]; cand.assign(1, v); }
