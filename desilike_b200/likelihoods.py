@@ -48,13 +48,12 @@ class BaseLikelihood(object):
         all_params = self.all_params
         varied = [p.name for p in all_params if p.varied and not p.solved]
         solved = [p for p in all_params if p.solved]
-        for p in solved:
-            if p.derived.startswith('.prec'):
-                raise NotImplementedError("'.prec' pre-marginalisation (reference likelihoods/base.py:280-309) is a plan-time 'next' row; use '.marg' / '.best'")
         solved_names = [p.name for p in solved]
         fixed = {p.name: p.value for p in all_params if not p.varied}
         spec = dict(params=varied, priors={p.name: p.prior for p in all_params if p.name in varied}, observables=[], precision=None,
-                    solved=[dict(name=p.name, value=p.value, prior=p.prior, marg=p.derived.replace('.auto', self.solved_default).startswith('.marg')) for p in solved])
+                    solved=[dict(name=p.name, value=p.value, prior=p.prior, marg=p.derived.replace('.auto', self.solved_default).startswith('.marg'),
+                                 mode='prec' if p.derived.startswith('.prec') else None) for p in solved],
+                    fiducial={p.name: p.value for p in all_params if p.name in varied})   # '.prec': Jacobian at the default values (reference likelihoods/base.py:288-296)
         for obs in self.observables:
             ospec = obs.observable_spec()
             theory = obs.theory.theory_spec()

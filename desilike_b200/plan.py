@@ -28,6 +28,8 @@ class Plan(object):
         if device is not None:
             import torch
             torch.cuda.set_device(device)
+        spec = premarginalize_precision(spec)   # '.prec' parameters (plan-time, reference likelihoods/base.py:257-312)
+        self.spec = spec
         self.lowered = Lowered(spec, with_plain=with_theory)
         self.params = list(self.lowered.names)
         self.d, self.ns, self.ntheory = self.lowered.d, self.lowered.ns, self.lowered.ntheory
@@ -121,6 +123,83 @@ class Plan(object):
         f = ctypes.c_double()
         _capi.check(self._lib.dlb_last_fftlog_ms(ctypes.byref(f)))
         return dict(features=a.value, contract=b.value, solve=c.value, fftlog=f.value)
+
+
+def premarginalize_precision(spec):
+    """
+    '.prec' pre-marginalisation at plan time, what the reference does once in ``BaseLikelihood._marginalize_precision``
+    (desilike/likelihoods/base.py:257-312): with J = d flattheory / d x over the '.prec' parameters at the fiducial point
+    (spec['fiducial']: the sampled parameters' default values) and their Gaussian priors N(loc, scale),
+
+        precision <- P - (J P)^T (J P J^T + diag(1 / scale^2))^-1 (J P),   flatdata <- flatdata - sum_i loc_i J_i
+
+    per precision block; the parameters then stay in the theory at their default values and are no longer solved.
+    The Jacobian rows are evaluated ON THE GPU through ``dlb_theory_batch``: a temporary plan treats the '.prec' parameters as
+    sampled columns, and J_i = theory(fiducial, x = e_i) - theory(fiducial, x = 0) is exact because the theory is linear in them.
+    """
+    solved = list(spec.get('solved', []))
+    prec = [s for s in solved if s.get('mode') == 'prec']
+    if not prec:
+        return spec
+    if 'fiducial' not in spec:
+        raise ValueError("'.prec' parameters need spec['fiducial'] (default values of the sampled parameters)")
+    names = list(spec['params'])
+    pnames = [s['name'] for s in prec]
+    # temporary plan: '.prec' parameters become sampled columns (factors of their terms)
+    tmp = dict(spec)
+    tmp['params'] = names + pnames
+    tmp['priors'] = dict(spec.get('priors', {}))
+    tmp['solved'] = [dict(s) for s in solved if s.get('mode') != 'prec']
+    tmp['observables'] = []
+    for obs in spec['observables']:
+        o = dict(obs)
+        o['terms'] = [dict(t, solved=None, factors=list(t.get('factors', [])) + [(t['solved'], 1)]) if t.get('solved') in pnames else t for t in obs['terms']]
+        tmp['observables'].append(o)
+    tmp.pop('fiducial', None)
+    plan = Plan(tmp, with_theory=True)
+    X = np.tile([float(spec['fiducial'][n]) for n in names] + [0.] * len(pnames), (len(pnames) + 1, 1))
+    for i in range(len(pnames)): X[i + 1, len(names) + i] = 1.
+    theory = plan.theory(X)
+    plan.close()
+    J = theory[1:] - theory[0]
+    loc = np.array([float((s.get('prior') or {}).get('loc', 0.)) for s in prec])
+    scale = np.array([float((s.get('prior') or {}).get('scale', np.inf)) if (s.get('prior') or {}).get('dist') == 'norm' else np.inf for s in prec])
+    prior_prec = np.where(np.isinf(scale), 0., 1. / scale**2)
+    sizes = [len(obs['data']) for obs in spec['observables']]
+    precision = spec['precision']
+    blocks = [np.asarray(p, dtype=np.float64) for p in precision] if isinstance(precision, (list, tuple)) else [np.asarray(precision, dtype=np.float64)]
+    bsizes = sizes if isinstance(precision, (list, tuple)) else [sum(sizes)]
+    new_prec, start = [], 0
+    for P, n in zip(blocks, bsizes):
+        Jb = J[:, start:start + n]
+        start += n
+        idx = np.flatnonzero(np.any(Jb != 0., axis=1))
+        if idx.size == 0:
+            new_prec.append(P); continue
+        Jb = Jb[idx]
+        derivp = Jb * P if P.ndim == 1 else Jb.dot(P)
+        H = derivp.dot(Jb.T) + np.diag(prior_prec[idx])
+        new_prec.append((np.diag(P) if P.ndim == 1 else P) - derivp.T.dot(np.linalg.solve(H, derivp)))
+    shift = J.T.dot(loc)
+    out = dict(spec)
+    out['solved'] = [dict(s) for s in solved if s.get('mode') != 'prec']
+    out['precision'] = new_prec if isinstance(precision, (list, tuple)) else new_prec[0]
+    values = {s['name']: float(s.get('value', 0.)) for s in prec}
+    out['observables'], start = [], 0
+    for obs in spec['observables']:
+        o = dict(obs)
+        n = len(obs['data'])
+        o['data'] = np.asarray(obs['data'], dtype=np.float64) - shift[start:start + n]
+        start += n
+        terms = []
+        for t in obs['terms']:
+            if t.get('solved') in values:
+                if values[t['solved']] == 0.: continue
+                t = dict(t, solved=None, scale=float(t.get('scale', 1.)) * values[t['solved']])
+            terms.append(t)
+        o['terms'] = terms
+        out['observables'].append(o)
+    return out
 
 
 def pinned_empty(shape, dtype=np.float64):

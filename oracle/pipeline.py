@@ -120,8 +120,74 @@ def _precision_blocks(spec):
     return [(slice(0, sum(sizes)), np.asarray(prec, dtype='f8'))]
 
 
+def marginalize_precision(spec):
+    """'.prec' pre-marginalisation, restated from reference desilike/likelihoods/base.py:257-312 (``_marginalize_precision``):
+    once, at the fiducial point (the parameters' default values, spec['fiducial']), with J = d flattheory / d x over the '.prec'
+    parameters (solved entries with mode='prec') and their Gaussian priors N(loc, scale),
+
+        precision <- P - (J P)^T (J P J^T + diag(1 / scale^2))^-1 (J P)          (:305-308)
+        flatdata  <- flatdata - sum_i loc_i J_i                                   (:309; flatdiff(x = loc) - flatdiff(x = 0))
+
+    per likelihood (= precision block); afterwards these parameters are no longer solved: their terms stay in the theory at the
+    parameters' default values.  Returns a new spec without mode='prec' entries."""
+    solved = list(spec.get('solved', []))
+    prec = [s for s in solved if s.get('mode') == 'prec']
+    if not prec:
+        return spec
+    names = list(spec['params'])
+    Xf = np.array([[float(spec['fiducial'][n]) for n in names]])
+    x0 = {s['name']: float(s.get('value', 0.)) for s in solved}
+    J = []   # [nprec][n]
+    for s in prec:
+        rows = []
+        for obs in spec['observables']:
+            if any(t.get('solved') == s['name'] for t in obs['terms']):
+                rows.append(observable_flat(obs, Xf, names, x0, only_solved=s['name'])[0])
+            else:
+                rows.append(np.zeros(len(obs['data'])))
+        J.append(np.concatenate(rows))
+    J = np.array(J)
+    loc = np.array([float((s.get('prior') or {}).get('loc', 0.)) for s in prec])
+    scale = np.array([float((s.get('prior') or {}).get('scale', np.inf)) if (s.get('prior') or {}).get('dist') == 'norm' else np.inf for s in prec])
+    prior_prec = np.where(np.isinf(scale), 0., 1. / scale**2)
+    blocks = _precision_blocks(spec)
+    new_prec, shift = [], J.T.dot(loc)
+    for sl, P in blocks:
+        Jb = J[:, sl]
+        idx = np.flatnonzero(np.any(Jb != 0., axis=1))
+        if idx.size == 0:
+            new_prec.append(P); continue
+        Jb = Jb[idx]
+        derivp = Jb * P if P.ndim == 1 else Jb.dot(P)
+        H = derivp.dot(Jb.T) + np.diag(prior_prec[idx])
+        full = np.diag(P) if P.ndim == 1 else P
+        new_prec.append(full - derivp.T.dot(np.linalg.solve(H, derivp)))
+    out = dict(spec)
+    out['solved'] = [dict(s) for s in solved if s.get('mode') != 'prec']
+    out['precision'] = new_prec if isinstance(spec['precision'], (list, tuple)) else new_prec[0]
+    pnames = {s['name']: float(s.get('value', 0.)) for s in prec}
+    observables, start = [], 0
+    for obs in spec['observables']:
+        o = dict(obs)
+        n = len(obs['data'])
+        o['data'] = np.asarray(obs['data'], dtype='f8') - shift[start:start + n]
+        start += n
+        terms = []
+        for t in obs['terms']:
+            if t.get('solved') in pnames:
+                value = pnames[t['solved']]
+                if value == 0.: continue
+                t = dict(t, solved=None, scale=float(t.get('scale', 1.)) * value)
+            terms.append(t)
+        o['terms'] = terms
+        observables.append(o)
+    out['observables'] = observables
+    return out
+
+
 def evaluate(spec, X, return_theory=False):
     """X [N, d] -> dict(logposterior, loglikelihood, logprior, x_solved [N, ns], flattheory [N, n])."""
+    spec = marginalize_precision(spec)
     X = np.atleast_2d(np.asarray(X, dtype='f8'))
     names = list(spec['params'])
     solved = spec.get('solved', [])

@@ -23,6 +23,7 @@ CASES = {
     'eftlike_sampled': dict(config='config_kaiser_window', kwargs=dict(eftlike=True, solved=False), eftlike=True, mode=None, n=48, seed=103),
     'eftlike_marg': dict(config='config_kaiser_window', kwargs=dict(eftlike=True, solved=True), eftlike=True, mode='.marg', n=48, seed=104),
     'eftlike_best': dict(config='config_kaiser_window', kwargs=dict(eftlike=True, solved=True), eftlike=True, mode='.best', n=48, seed=105),
+    'eftlike_prec': dict(config='config_kaiser_window', kwargs=dict(eftlike=True, solved=True), eftlike=True, mode='.prec', n=48, seed=109),
     'kaiser_window_cubic': dict(config='config_kaiser_window', kwargs=dict(eftlike=False, solved=False, transform='cubic'), eftlike=False, mode=None, n=32, seed=106),
 }
 
@@ -31,6 +32,8 @@ def build_spec(case):
     spec = getattr(configs, case['config'])(**case['kwargs'])
     if case['mode'] == '.best':
         for s in spec['solved']: s['marg'] = False
+    if case['mode'] == '.prec':
+        for s in spec['solved']: s['mode'] = 'prec'
     return spec
 
 
@@ -43,6 +46,8 @@ def main():
         if not spec['solved']:
             X[1, 0] = 1.3   # out of prior -> -inf
         ref = ref_harness.run_vmap(like, spec, X)
+        if case['mode'] == '.prec':   # the Jacobian of the pre-marginalisation is taken at the reference's default parameter values
+            case = dict(case, fiducial={p.name: float(p.value) for p in like.all_params if p.name in spec['params']})
         np.savez_compressed(os.path.join(HERE, name + '.npz'), case=json.dumps(case), X=X, **ref)
         print(name, X.shape, ref['logposterior'][:3])
 

@@ -56,7 +56,7 @@ def test_vmap_conventions(gpu_required):
     assert np.isfinite(out[0]) and np.isneginf(out[1])
 
 
-@pytest.mark.parametrize('name', ['c1_kaiser_shapefit', 'kaiser_window', 'eftlike_sampled', 'eftlike_marg', 'eftlike_best'])
+@pytest.mark.parametrize('name', ['c1_kaiser_shapefit', 'kaiser_window', 'eftlike_sampled', 'eftlike_marg', 'eftlike_best', 'eftlike_prec'])
 def test_api_matches_reference_outputs(gpu_required, name):
     """Mirror classes -> plan -> CUDA vs the reference's own outputs on the same inputs."""
     data = np.load(os.path.join(HERE, 'golden', name + '.npz'))

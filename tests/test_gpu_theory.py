@@ -40,6 +40,9 @@ def test_cuda_matches_reference_fixture(gpu_required, fn):
     spec = getattr(configs, case['config'])(**case['kwargs'])
     if case['mode'] == '.best':
         for s in spec['solved']: s['marg'] = False
+    if case['mode'] == '.prec':   # pre-marginalised precision (reference likelihoods/base.py:257-312), Jacobian evaluated on the GPU at plan time
+        for s in spec['solved']: s['mode'] = 'prec'
+        spec['fiducial'] = case['fiducial']
     plan = desilike_b200.Plan(spec)
     X = data['X']
     got = plan.eval(X)

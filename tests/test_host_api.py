@@ -38,7 +38,7 @@ def make_kaiser_likelihood(spec, eftlike=False, mode=None):
     return likelihood
 
 
-@pytest.mark.parametrize('name', ['c1_kaiser_shapefit', 'kaiser_window', 'eftlike_sampled', 'eftlike_marg', 'eftlike_best'])
+@pytest.mark.parametrize('name', ['c1_kaiser_shapefit', 'kaiser_window', 'eftlike_sampled', 'eftlike_marg', 'eftlike_best', 'eftlike_prec'])
 def test_mirror_classes_reproduce_reference_outputs(name):
     data = np.load(os.path.join(HERE, 'golden', name + '.npz'))
     case = json.loads(str(data['case']))

@@ -18,11 +18,14 @@ def load_case(fn):
     spec = getattr(configs, case['config'])(**case['kwargs'])
     if case['mode'] == '.best':
         for s in spec['solved']: s['marg'] = False
+    if case['mode'] == '.prec':
+        for s in spec['solved']: s['mode'] = 'prec'
+        spec['fiducial'] = case['fiducial']
     return case, spec, data
 
 
 def test_fixtures_present():
-    assert len(FIXTURES) >= 6
+    assert len(FIXTURES) >= 7
 
 
 @pytest.mark.parametrize('fn', FIXTURES, ids=[os.path.basename(f)[:-4] for f in FIXTURES])
