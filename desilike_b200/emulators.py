@@ -97,6 +97,64 @@ class Emulator(object):
         return cls(state)
 
     @classmethod
+    def fit_taylor(cls, theory, order=4, delta=None, params=None, nbatch=None):
+        """
+        Build a Taylor emulator of the perturbation-theory tables of a direct tracer theory (e.g. ``KaiserTracerPowerSpectrumMultipoles``),
+        the ``.fit`` half of the reference's emulator API (``Emulator(calculator, engine=TaylorEmulatorEngine(order=4)).set_samples().fit()``,
+        reference emulators/__init__.py:438-507; docs/user/getting_started.rst:281-288).
+
+        The reference differentiates the calculator with ``Differentiation`` (jax autodiff or finite differences, differentiation.py:469-551)
+        and stores ``derivatives[t] = d^alpha y / alpha!`` for the term list ``powers`` (emulators/__init__.py:471-507).  Here the theory
+        tables are evaluated ON THE GPU (the Kaiser kernel, through ``dlb_features_batch``) on the tensor-product stencil of
+        ``order + 1`` (odd) nodes per parameter around the parameters' default values, and the Taylor coefficients follow from the
+        exact polynomial interpolation of the stencil (central finite differences, exact for polynomials of degree <= order).
+
+        ``delta``: stencil spacing per parameter (default: ``Parameter.delta`` or 0.02); ``params``: subset of the theory's varied
+        perturbation-theory parameters (default: all of them).
+        """
+        import itertools
+        from .plan import Plan
+        tspec = theory.theory_spec()
+        if tspec['kind'] != 'kaiser':
+            raise ValueError('fit_taylor expects a direct Kaiser tracer theory (got kind {!r})'.format(tspec['kind']))
+        names = list(params) if params is not None else [n for n in tspec['params'] if not theory.all_params[n].fixed]
+        ndim = len(names)
+        center = np.array([float(theory.all_params[n].value) for n in names])
+        if delta is None:
+            delta = [getattr(theory.all_params[n], 'delta', None) or 0.02 for n in names]
+        delta = np.broadcast_to(np.asarray(delta, dtype='f8'), (ndim,)).copy()
+        # term list in the enumeration order of the reference's fit (emulators/__init__.py:485-503)
+        powers = []
+        for o in range(order + 1):
+            for indices in itertools.product(range(ndim), repeat=o):
+                orders = tuple(int(c) for c in np.bincount(indices, minlength=ndim)) if o else (0,) * ndim
+                if orders not in powers: powers.append(orders)
+        powers = np.array(powers, dtype='i4')
+        npts = order + 1 if (order + 1) % 2 else order + 2
+        nodes = np.arange(npts, dtype='f8') - npts // 2
+        grids = np.meshgrid(*[nodes] * ndim, indexing='ij')
+        X = np.stack([g.ravel() for g in grids], axis=-1) * delta + center
+        # a minimal plan around the theory generator: the tables ARE its features
+        tspec = dict(tspec, params=names)
+        nin = len(theory.k) * len(theory.ells)
+        obs = dict(name='fit', theory=tspec, terms=[dict(scale=1., factors=[], table='pk_dd')], nin=nin, wmatrix=None, offset=None, data=np.zeros(nin))
+        plan = Plan(dict(params=names, priors={}, solved=[], observables=[obs], precision=[np.ones(nin)]), with_theory=False)
+        feats = plan.features(0, X)
+        gen = plan.lowered.gens[0]
+        tables = {}
+        for name in ['pk_dd', 'pk_dt', 'pk_tt']:
+            foff, K, _ = gen.tables[name]
+            Y = feats[:, foff:foff + K].reshape((npts,) * ndim + (K,))
+            Vinv = np.linalg.inv(np.vander(nodes, npts, increasing=True))
+            for ax in range(ndim):
+                Y = np.moveaxis(np.tensordot(Vinv, np.moveaxis(Y, ax, 0), axes=(1, 0)), 0, ax)
+            tables[name] = np.array([Y[tuple(p)] / np.prod(delta**p) for p in powers]).reshape(len(powers), len(theory.ells), len(theory.k))
+        plan.close()
+        fixed = dict(k=np.asarray(theory.k, dtype='f8'), ells=tuple(theory.ells), z=getattr(theory.template, 'z', 1.))
+        all_params = [theory.all_params[n] for n in tspec['params'] if n in theory.all_params.names()] if hasattr(theory.all_params, 'names') else None
+        return cls.from_taylor(names, center, powers, tables, fixed, all_params=all_params)
+
+    @classmethod
     def from_mlp(cls, params, mlp, tables, yshapes, fixed, defaults=None, all_params=None,
                  calculator_class=('desilike.theories.galaxy_clustering.full_shape', 'KaiserPowerSpectrumMultipoles')):
         """``mlp``: dict(xlimits, layers [(kernel, bias)], activation, ylimits, pca); ``tables``: {name: slice into the network output}."""

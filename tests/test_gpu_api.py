@@ -71,7 +71,7 @@ def test_api_matches_reference_outputs(gpu_required, name):
     assert errs == {} and np.array_equal(np.isneginf(ref), np.isneginf(res))
     assert np.allclose(res[finite], ref[finite], rtol=1e-9, atol=1e-7)
     assert np.allclose(derived['loglikelihood'][finite], data['loglikelihood'][finite], rtol=1e-9, atol=1e-7)
-    if spec['solved']:
+    if spec['solved'] and case['mode'] != '.prec':   # '.prec' parameters are marginalised into the precision: no solved values
         orc = pipeline.evaluate(spec, X)
         for i, s in enumerate(spec['solved']):
             assert np.allclose(derived[s['name']], orc['x_solved'][:, i], rtol=1e-7, atol=1e-7)
@@ -128,3 +128,41 @@ def test_bao_correlation_function_likelihood(gpu_required):
     orc = pipeline.evaluate(built, X)
     assert np.max(np.abs(res - orc['logposterior']) / np.maximum(1., np.abs(orc['logposterior']))) < 1e-7
     assert np.allclose(derived['al0_0'], orc['x_solved'][:, 0], rtol=1e-6, atol=1e-9)
+
+
+def test_fit_taylor_emulator_on_gpu(gpu_required, tmp_path):
+    """``Emulator.fit_taylor``: Taylor coefficients of the Kaiser pt tables from GPU theory evaluations on a finite-difference stencil
+    (the .fit half of the emulator API, reference emulators/__init__.py:438-507).  Pins: the coefficients equal the oracle's
+    finite-difference fit of the oracle theory; the emulated theory reproduces the direct theory at the expansion centre and
+    differs away from it by the truncation error only (reference emulators/tests/test_taylor.py:90-104); save -> load -> same output."""
+    template = dl.ShapeFitPowerSpectrumTemplate(pk_dd_fid=synthetic.pk_fid, pknow_dd_fid=synthetic.pknow_fid, f_fid=synthetic.F_FID)
+    k, ells = np.linspace(0.01, 0.25, 30), (0, 2, 4)
+    direct = dl.KaiserTracerPowerSpectrumMultipoles(template=template, k=k, ells=ells)
+    delta = [0.02, 0.02, 0.02, 0.04]
+    emu = dl.Emulator.fit_taylor(direct, order=3, delta=delta)
+    eng = emu.state['engines']['pk_dd']
+    assert list(eng['params']) == ['qpar', 'qper', 'dm', 'df'] and np.allclose(eng['center'], [1., 1., 0., 1.])
+    ref = configs._kaiser_taylor_engine(k, ells, 3, configs.shapefit_template(), delta=delta)
+    assert np.array_equal(eng['powers'], ref['powers'])
+    rng = np.random.default_rng(0)
+    dx = rng.uniform(-1., 1., (64, 4)) * np.array(delta)
+    mono = np.prod(dx[:, None, :]**ref['powers'][None, :, :], axis=-1)
+    for name in ['pk_dd', 'pk_dt', 'pk_tt']:   # identically-zero derivatives are rounding noise: compare the polynomials, not the coefficients
+        got = np.asarray(emu.state['engines'][name]['derivatives']).reshape(len(ref['powers']), -1)
+        pg, pr = mono.dot(got), mono.dot(ref['tables'][name])
+        assert np.max(np.abs(pg - pr)) < 1e-9 * np.max(np.abs(pr)), name
+    fn = str(tmp_path / 'fitted.npy')
+    emu.save(fn)
+    emulated = dl.KaiserTracerPowerSpectrumMultipoles(pt=dl.EmulatedCalculator.load(fn))
+
+    def likelihood(theory):
+        observable = dl.TracerPowerSpectrumMultipolesObservable(data={'b1': 2.}, k=[k] * 3, ells=ells, theory=theory, covariance=np.eye(90) * 1e4)
+        return dl.ObservablesGaussianLikelihood([observable])
+
+    like_d, like_e = likelihood(direct), likelihood(emulated)
+    like_d(b1=2.); like_e(b1=2.)
+    scale = np.max(np.abs(like_d.flattheory))
+    assert np.max(np.abs(like_e.flattheory - like_d.flattheory)) < 1e-9 * scale          # at the centre
+    like_d(b1=2., qpar=1.03, dm=0.02); like_e(b1=2., qpar=1.03, dm=0.02)
+    err = np.max(np.abs(like_e.flattheory - like_d.flattheory)) / scale
+    assert 1e-12 < err < 5e-3                                                              # away: truncation error of an order-3 expansion
