@@ -4,7 +4,7 @@ Scope: ONE hot path -- N parameter points through emulated / Kaiser / BAO theory
 analytic marginalisation -> prior -- behind desilike's calling conventions.  See DESIGN.md / INTEGRATION.md.
 """
 from ._capi import DesilikeB200Error, load as load_library
-from .plan import Plan, launch_count, measure_fp64_peak, pinned_empty
+from .plan import Plan, launch_count, measure_fp64_peak, pinned_empty, sample_solved
 from .lowering import Lowered, LoweringError
 
 from .parameter import Parameter, ParameterCollection, Samples
@@ -21,5 +21,5 @@ __all__ = ['Parameter', 'ParameterCollection', 'Samples', 'ShapeFitPowerSpectrum
            'KaiserTracerPowerSpectrumMultipoles', 'EFTLikeKaiserTracerPowerSpectrumMultipoles', 'DampedBAOWigglesTracerPowerSpectrumMultipoles',
            'DampedBAOWigglesTracerCorrelationFunctionMultipoles', 'Emulator', 'EmulatedCalculator', 'TracerPowerSpectrumMultipolesObservable',
            'TracerCorrelationFunctionMultipolesObservable', 'ObservablesGaussianLikelihood', 'SumLikelihood', 'PipelineError', 'vmap', 'status_to_errors', 'EnsembleSampler',
-           'Plan', 'Lowered', 'LoweringError', 'DesilikeB200Error', 'load_library', 'launch_count', 'measure_fp64_peak', 'pinned_empty']
+           'Plan', 'sample_solved', 'Lowered', 'LoweringError', 'DesilikeB200Error', 'load_library', 'launch_count', 'measure_fp64_peak', 'pinned_empty']
 __version__ = '0.1.0'

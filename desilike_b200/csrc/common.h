@@ -150,6 +150,7 @@ struct SolveParams {
   int ncomp; const int* comp_off; const int* comp_idx; const int* comp_nmarg;
   int npos; const int* comp_pos; const double* comp_m0;   // intra-group matrix positions (i * (ns + 1) + j) and their constant part
   double* logpost; double* loglike; double* logprior; double* xsolved; int* status;
+  double* hess; int nhess; const int* hess_ij; const int* comp_of;   // optional packed upper triangle of M = -H_posterior per point
 };
 int launch_solve(const SolveParams& p, cudaStream_t stream);
 

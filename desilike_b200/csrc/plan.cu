@@ -59,6 +59,8 @@ struct dlb_plan {
   int ncomp = 0;                       // independent groups of solved parameters (0: solve one dense system)
   int *d_comp_off = nullptr, *d_comp_idx = nullptr, *d_comp_nmarg = nullptr, *d_comp_pos = nullptr;
   double* d_comp_m0 = nullptr; int npos = 0;
+  int *d_hess_ij = nullptr, *d_comp_of = nullptr;
+  double* w_hess = nullptr; long long hess_cap = 0;
   dlb::SolveBlock* d_solve_blocks = nullptr;
   long long ptotal = 0;  // partial rows (in units of npad doubles)
   std::vector<void*> owned;
@@ -434,6 +436,7 @@ void dlb_plan_destroy(dlb_plan* plan) {
   for (void* ptr : {(void*)plan->w_F, (void*)plan->w_partial, (void*)plan->w_params, (void*)plan->w_out, (void*)plan->w_status, (void*)plan->w_theory})
     if (ptr) cudaFree(ptr);
   for (auto& e : plan->ev) if (e) cudaEventDestroy(e);
+  if (plan->w_hess) cudaFree(plan->w_hess);
   if (plan->w_prop) cudaFree(plan->w_prop);
   if (plan->w_logpy) cudaFree(plan->w_logpy);
   delete plan;
@@ -686,6 +689,12 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
       comp_off.push_back((int)comp_idx.size());
       maxsize = std::max(maxsize, comp_off.back() - comp_off[comp_off.size() - 2]);
     }
+    {
+      std::vector<int> hij, comp_of(ns);
+      for (int i = 0; i < ns; ++i) { comp_of[i] = find(i); for (int j = i; j < ns; ++j) hij.push_back((i << 16) | j); }
+      DLB_TRY(upload(plan, hij.data(), hij.size(), &plan->d_hess_ij));
+      DLB_TRY(upload(plan, comp_of.data(), comp_of.size(), &plan->d_comp_of));
+    }
     if (maxsize <= 12) {   // small groups: one lane factorises one group
       plan->ncomp = (int)comp_nmarg.size();
       DLB_TRY(upload(plan, comp_off.data(), comp_off.size(), &plan->d_comp_off));
@@ -714,21 +723,36 @@ static const long long MAX_CHUNK = 1LL << 20;
 
 int dlb_eval_batch(dlb_plan* plan, const double* params, int64_t N, double* logposterior, double* loglikelihood, double* logprior,
                    double* x_solved, int32_t* status, void* stream_) {
+  return dlb_eval_batch_hessian(plan, params, N, logposterior, loglikelihood, logprior, x_solved, nullptr, status, stream_);
+}
+
+int dlb_eval_batch_hessian(dlb_plan* plan, const double* params, int64_t N, double* logposterior, double* loglikelihood, double* logprior,
+                           double* x_solved, double* hessian, int32_t* status, void* stream_) {
   DLB_REQUIRE(plan && params && N >= 0, "NULL plan / params or negative N");
   if (N == 0) return DLB_OK;
+  if (plan->ns == 0) hessian = nullptr;
+  const int nhess = plan->ns * (plan->ns + 1) / 2;
+  const bool hs_dev = is_device_ptr(hessian);
   std::lock_guard<std::mutex> lock(plan->mutex);
   cudaStream_t stream = (cudaStream_t)stream_;
   DLB_CUDA(cudaSetDevice(plan->device));
   const bool in_dev = is_device_ptr(params);
   const bool lp_dev = is_device_ptr(logposterior), ll_dev = is_device_ptr(loglikelihood), pr_dev = is_device_ptr(logprior),
              xs_dev = is_device_ptr(x_solved), st_dev = is_device_ptr(status);
-  bool any_host = !in_dev || (logposterior && !lp_dev) || (loglikelihood && !ll_dev) || (logprior && !pr_dev) || (x_solved && !xs_dev) || (status && !st_dev);
+  bool any_host = !in_dev || (logposterior && !lp_dev) || (loglikelihood && !ll_dev) || (logprior && !pr_dev) || (x_solved && !xs_dev) || (status && !st_dev) ||
+                  (hessian && !hs_dev);
   const int ns = plan->ns;
   for (long long start = 0; start < N; start += MAX_CHUNK) {
     const long long n = std::min<long long>(MAX_CHUNK, N - start);
     const long long npad = (n + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
     int rc = ensure_workspace(plan, npad);
     if (rc) return rc;
+    if (hessian && !hs_dev && plan->hess_cap < n) {
+      if (plan->w_hess) cudaFree(plan->w_hess);
+      plan->w_hess = nullptr; plan->hess_cap = 0;
+      DLB_CUDA(cudaMalloc((void**)&plan->w_hess, (size_t)n * nhess * sizeof(double)));
+      plan->hess_cap = n;
+    }
     const double* d_params = params + start * plan->d;
     if (!in_dev) {
       DLB_CUDA(cudaMemcpyAsync(plan->w_params, d_params, (size_t)n * plan->d * sizeof(double), cudaMemcpyHostToDevice, stream));
@@ -756,6 +780,8 @@ int dlb_eval_batch(dlb_plan* plan, const double* params, int64_t N, double* logp
     sp.logprior = logprior ? (pr_dev ? logprior + start : w + 2 * npad) : nullptr;
     sp.xsolved = (x_solved && ns) ? (xs_dev ? x_solved + start * ns : w + 3 * npad) : nullptr;
     sp.status = status ? (st_dev ? status + start : plan->w_status) : nullptr;
+    sp.hess = hessian ? (hs_dev ? hessian + start * nhess : plan->w_hess) : nullptr;
+    sp.nhess = nhess; sp.hess_ij = plan->d_hess_ij; sp.comp_of = plan->d_comp_of;
     rc = launch_solve(sp, stream);
     if (rc) return rc;
     if (plan->timing) DLB_CUDA(cudaEventRecord(plan->ev[3], stream));
@@ -764,6 +790,7 @@ int dlb_eval_batch(dlb_plan* plan, const double* params, int64_t N, double* logp
     if (logprior && !pr_dev) DLB_CUDA(cudaMemcpyAsync(logprior + start, sp.logprior, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
     if (x_solved && ns && !xs_dev) DLB_CUDA(cudaMemcpyAsync(x_solved + start * ns, sp.xsolved, (size_t)n * ns * sizeof(double), cudaMemcpyDeviceToHost, stream));
     if (status && !st_dev) DLB_CUDA(cudaMemcpyAsync(status + start, sp.status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (hessian && !hs_dev) DLB_CUDA(cudaMemcpyAsync(hessian + start * nhess, sp.hess, (size_t)n * nhess * sizeof(double), cudaMemcpyDeviceToHost, stream));
     if (any_host || plan->timing || start + MAX_CHUNK < N) DLB_CUDA(cudaStreamSynchronize(stream));
     if (plan->timing) {
       float a = 0, b = 0, c = 0;
@@ -867,7 +894,8 @@ int dlb_ensemble_step(dlb_plan* plan, double* walkers, double* logposterior, int
   DLB_CUDA(cudaSetDevice(plan->device));
   const long long n0 = nwalkers / 2, n1 = nwalkers - n0;
   if (n1 > plan->prop_cap) {
-    if (plan->w_prop) cudaFree(plan->w_prop);
+    if (plan->w_hess) cudaFree(plan->w_hess);
+  if (plan->w_prop) cudaFree(plan->w_prop);
     if (plan->w_logpy) cudaFree(plan->w_logpy);
     plan->w_prop = plan->w_logpy = nullptr; plan->prop_cap = 0;
     DLB_CUDA(cudaMalloc((void**)&plan->w_prop, (size_t)n1 * plan->d * sizeof(double)));

@@ -83,6 +83,14 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) finish_solve_kernel(const So
   for (int i = lane; i < ns; i += 32) g[i] = p.g0[i] + gL[i];
   __syncwarp();
 
+  if (p.hess) {   // -Hessian of the log-posterior in the solved parameters (prior precision + J~ J~^T), packed upper triangle, plan order
+    for (int e = lane; e < p.nhess; e += 32) {
+      const int ij = p.hess_ij[e], i = ij >> 16, j = ij & 0xFFFF;
+      const bool coupled = p.ncomp == 0 || p.comp_of[i] == p.comp_of[j];   // entries between independent groups are exactly zero
+      p.hess[pt * p.nhess + e] = coupled ? M[i * ld + j] : 0.;
+    }
+    __syncwarp();
+  }
   bool spd = true;
   double logdet = 0.;
   double lp = 0.;

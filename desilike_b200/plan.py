@@ -51,8 +51,11 @@ class Plan(object):
         except Exception: pass
 
     # ---- evaluation --------------------------------------------------------------------------------------------------
-    def eval(self, X, return_solved=True, return_status=True, out=None):
-        """-> dict(logposterior, loglikelihood, logprior[, x_solved (spec order), status])."""
+    def eval(self, X, return_solved=True, return_status=True, out=None, return_hessian=False):
+        """-> dict(logposterior, loglikelihood, logprior[, x_solved (spec order), status, hessian]).
+
+        ``return_hessian`` (NumPy input): ``hessian`` [N, ns, ns] = Hessian of the log-posterior in the solved parameters (spec order),
+        the reference's ``posterior_hessian`` (likelihoods/base.py:187); ``sample_solved`` draws the marginalised parameters from it."""
         if _is_torch_cuda(X):
             return self._eval_torch(X, return_solved, return_status, out)
         X = np.ascontiguousarray(X, dtype=np.float64)
@@ -66,9 +69,16 @@ class Plan(object):
             res = dict(logposterior=np.empty(N), loglikelihood=np.empty(N), logprior=np.empty(N))
             xs = np.empty((N, self.ns)) if (return_solved and self.ns) else None
             st = np.empty(N, dtype=np.int32) if return_status else None
-        _capi.check(self._lib.dlb_eval_batch(self._handle, X.ctypes.data, N, res['logposterior'].ctypes.data, res['loglikelihood'].ctypes.data,
-                                             res['logprior'].ctypes.data, xs.ctypes.data if xs is not None else None,
-                                             st.ctypes.data if st is not None else None, None))
+        hs = np.empty((N, self.ns * (self.ns + 1) // 2)) if (return_hessian and self.ns) else None
+        _capi.check(self._lib.dlb_eval_batch_hessian(self._handle, X.ctypes.data, N, res['logposterior'].ctypes.data, res['loglikelihood'].ctypes.data,
+                                                     res['logprior'].ctypes.data, xs.ctypes.data if xs is not None else None,
+                                                     hs.ctypes.data if hs is not None else None, st.ctypes.data if st is not None else None, None))
+        if hs is not None:
+            iu = np.triu_indices(self.ns)
+            H = np.zeros((N, self.ns, self.ns))
+            H[:, iu[0], iu[1]] = hs
+            H[:, iu[1], iu[0]] = hs
+            res['hessian'] = -H[:, self._unperm][:, :, self._unperm]
         if xs is not None: res['x_solved'] = xs if self._identity_perm else xs[:, self._unperm]
         if st is not None: res['status'] = st
         return res
@@ -200,6 +210,17 @@ def premarginalize_precision(spec):
         o['terms'] = terms
         out['observables'].append(o)
     return out
+
+
+def sample_solved(x_solved, hessian, rng=None):
+    """Draw the analytically marginalised parameters around their best fit, x ~ N(x_best, (-H)^-1), per point -- what the reference's
+    ``Chain.sample_solved`` does with the stored Hessians (desilike/samples/chain.py:46-72, :229-260).  ``x_solved`` [N, ns],
+    ``hessian`` [N, ns, ns] as returned by ``Plan.eval(..., return_hessian=True)``."""
+    rng = rng or np.random.default_rng()
+    x_solved, hessian = np.asarray(x_solved, dtype=np.float64), np.asarray(hessian, dtype=np.float64)
+    L = np.linalg.cholesky(-hessian)                       # -H = L L^T  ->  covariance = L^-T L^-1
+    z = rng.standard_normal(x_solved.shape)
+    return x_solved + np.linalg.solve(np.swapaxes(L, -1, -2), z[..., None])[..., 0]
 
 
 def pinned_empty(shape, dtype=np.float64):

@@ -141,6 +141,14 @@ int dlb_eval_batch(dlb_plan* plan, const double* params, int64_t N,
                    double* logposterior, double* loglikelihood, double* logprior,
                    double* x_solved, int32_t* status, void* stream);
 
+/* Same, additionally returning (hessian may be NULL) the NEGATIVE Hessian of the log-posterior in the solved parameters at every point,
+ * M = diag(1 / scale^2) + J~ J~^T (reference likelihoods/base.py:165-187: -posterior_hessian; its entries are what the reference
+ * exports as derivs-tagged derived values, :342-352, :388-390, and what Chain.sample_solved draws from): packed upper triangle,
+ * row-major over the plan's solved order, [N, ns (ns + 1) / 2]. */
+int dlb_eval_batch_hessian(dlb_plan* plan, const double* params, int64_t N,
+                           double* logposterior, double* loglikelihood, double* logprior,
+                           double* x_solved, double* hessian, int32_t* status, void* stream);
+
 /* Theory vectors (parity / debug entry; reference `likelihood.flattheory`, likelihoods/base.py:662-664): theory [N, n],
  * evaluated at the solved parameters' defaults x0. */
 int dlb_theory_batch(dlb_plan* plan, const double* params, int64_t N, double* theory, void* stream);

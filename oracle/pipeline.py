@@ -185,8 +185,8 @@ def marginalize_precision(spec):
     return out
 
 
-def evaluate(spec, X, return_theory=False):
-    """X [N, d] -> dict(logposterior, loglikelihood, logprior, x_solved [N, ns], flattheory [N, n])."""
+def evaluate(spec, X, return_theory=False, return_hessian=False):
+    """X [N, d] -> dict(logposterior, loglikelihood, logprior, x_solved [N, ns], flattheory [N, n][, hessian [N, ns, ns]])."""
     spec = marginalize_precision(spec)
     X = np.atleast_2d(np.asarray(X, dtype='f8'))
     names = list(spec['params'])
@@ -222,10 +222,12 @@ def evaluate(spec, X, return_theory=False):
         priors = [s.get('prior') for s in solved]
         marg = [bool(s.get('marg', True)) for s in solved]
         xx0 = [x0[s['name']] for s in solved]
+        hess = np.empty((N, len(solved), len(solved)))
         for ip in range(N):
             res = core.solve_marginalised([flatdiff[ip, sl] for sl, P in blocks], [J[ip][:, sl] for sl, P in blocks], [P for sl, P in blocks],
-                                          xx0, priors, marg)
-            loglike[ip], xs[ip], lp_solved[ip] = res['loglikelihood'], res['x'], res['logprior_solved']
+                                          xx0, priors, marg, with_hessian=True)
+            loglike[ip], xs[ip], lp_solved[ip], hess[ip] = res['loglikelihood'], res['x'], res['logprior_solved'], res['hessian']
+        if return_hessian: out['hessian'] = hess
         logprior = logprior + lp_solved
         out['x_solved'] = xs
     out.update(loglikelihood=loglike, logprior=logprior, logposterior=loglike + logprior)

@@ -147,3 +147,23 @@ def test_fp64_peak_measurement(gpu_required):
     dfma = desilike_b200.measure_fp64_peak('dfma')
     print('FP64 peak TFLOP/s: DMMA {:.2f} DFMA {:.2f}'.format(dmma, dfma))
     assert dmma > 1. and dfma > 1.
+
+
+def test_posterior_hessian_and_sample_solved(gpu_required):
+    """Hessian of the log-posterior in the solved parameters (dlb_eval_batch_hessian; reference likelihoods/base.py:165-187) against
+    the oracle, with independent groups (block-diagonal) and one dense group; sample_solved draws with covariance (-H)^-1."""
+    import desilike_b200
+    for spec in [configs.config_c5(ntracers=2, nkin=40, nbins=10, order=2, solved=True), configs.config_c5(ntracers=2, nkin=40, nbins=10, order=2, solved=True, dense=True)]:
+        plan = desilike_b200.Plan(spec)
+        X = configs.sample_points(spec, 64, seed=3)
+        got = plan.eval(X, return_hessian=True)
+        ref = pipeline.evaluate(spec, X, return_hessian=True)
+        scale = np.sqrt(np.abs(np.einsum('nii,njj->nij', ref['hessian'], ref['hessian'])))
+        assert np.max(np.abs(got['hessian'] - ref['hessian']) / scale) < 1e-9
+        assert np.allclose(got['x_solved'], ref['x_solved'], rtol=1e-7, atol=1e-9)
+        plan.close()
+    rng = np.random.default_rng(0)
+    draws = np.array([desilike_b200.sample_solved(got['x_solved'][:1], got['hessian'][:1], rng=rng)[0] for _ in range(4000)])
+    cov = np.linalg.inv(-got['hessian'][0])
+    assert np.allclose(draws.mean(axis=0), got['x_solved'][0], atol=5. * np.sqrt(np.diag(cov) / 4000.))
+    assert np.max(np.abs(np.cov(draws.T) - cov) / np.sqrt(np.outer(np.diag(cov), np.diag(cov)))) < 0.1
