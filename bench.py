@@ -46,7 +46,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'logL evals/sec (batched, emulated FS+window+chi2)'
 # algorithmic FLOP per evaluation of the UN-collapsed chain
-UNCOLLAPSED_FLOPS = {'c1': 0.1e6, 'c2': 0.7e6, 'c3': 1.3e6, 'c4': 20e6, 'c5': 8e6, 'c5solved': 19e6}
+UNCOLLAPSED_FLOPS = {'c1': 0.1e6, 'c2': 0.7e6, 'c3': 1.3e6, 'c3fft': 1.3e6, 'c4': 20e6, 'c5': 8e6, 'c5solved': 19e6}
 UNIT = 'evals/s'
 
 
@@ -55,7 +55,11 @@ def build_spec(workload):
     if workload == 'c1':
         return configs.config_c1(), 'C1: KaiserTracerPowerSpectrumMultipoles (ShapeFit template, ell=0,2,4, k=0.02-0.2, 36 bins/ell) -> chi2 (n=108, d=6), direct theory (no emulator)'
     if workload == 'c3':
-        return configs.config_c3(), 'C3: damped-BAO P(k) -> FFTLog (2048->4096) -> xi_ell(s) + solved broadband -> chi2 (n=66, d=7, ns=4)'
+        return configs.config_c3(), 'C3: damped-BAO P(k) -> FFTLog (2048->4096) -> xi_ell(s) + solved broadband -> chi2 (n=66, d=7, ns=4); P -> xi operator folded into the term matrices at plan time'
+    if workload == 'c3fft':
+        spec = configs.config_c3()
+        spec['observables'][0]['theory']['fftlog'] = 'kernel'
+        return spec, 'C3 with the explicit FFTLog kernel: damped-BAO P(k) -> fftlog_kernel (2048->4096) -> xi_ell(s) + solved broadband -> chi2 (n=66, d=7, ns=4)'
     if workload == 'c2':
         return configs.config_c2(coefficients='random'), 'C2: TaylorEmulator(order 4, T=70) pt tables 3x[3,350] -> Kaiser combine -> window [108,1050] -> chi2 (n=108, d=6)'
     if workload == 'c5':
@@ -374,6 +378,19 @@ def main():
         except Exception: traffic = None
     uncollapsed = UNCOLLAPSED_FLOPS.get(args.workload)
     if args.workload == 'c3':
+        # dominant kernel: damped-BAO P_ell(kin) (one warp per point; FP64 FMA pipe).  Algorithmic work (SURVEY.md section 8a row a12,
+        # 8d "BAO P(k)"): nk * nmu nodes x (3 cubic interpolations ~ 20 FLOP each + damping exp ~ 30 + AP / Kaiser / FoG factors ~ 40)
+        # + the Legendre sums 2 nell nk nmu, with nk = 300, nmu = 10, nell = 2
+        nk_, nmu_, nell_ = 300, 10, 2
+        bao_flops = nk_ * nmu_ * (3 * 20 + 30 + 40) + 2 * nell_ * nk_ * nmu_
+        peak = desilike_b200.measure_fp64_peak('dfma')
+        achieved = bao_flops * N / (phase['features'] * 1e-3) / 1e12
+        roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
+                    'kernel': 'dlb::bao_kernel (FP64 FMA pipe; AP + wiggle spline + Gauss-Legendre quadrature, one warp per point)', 'launches_per_step': 1,
+                    'ms_per_step_in_kernel': phase['features'], 'flops_per_eval': {'bao': bao_flops, 'contract_folded': flops},
+                    'peak_source': 'dlb_measure_fp64_peak(DFMA register loop) measured in this run; MEASURED_PEAKS.json has no FP64 entry',
+                    'share_of_step': phase['features'] / step_ms, 'phase_ms': phase}
+    elif args.workload == 'c3fft':
         # dominant kernel: FFTLog (one CTA per point and multipole; FP64 FMA pipe + shared-memory passes).  Algorithmic work =
         # n_ell (2 * 2.5 Np log2 Np + 6 Np) FLOP per evaluation with Np = 4096.
         nell, Np = 2, 4096

@@ -64,4 +64,27 @@ def fftlog_constants(kin, ells, s_out, ng=2048, kmin=1e-4, kmax=1e3, q=0., minfo
     ddata = np.concatenate([c0, c1, np.array(u).ravel(), np.array(post).ravel(),
                             np.stack([tw.real, tw.imag], axis=-1).ravel(), np.array(outw).ravel()])
     idata = np.concatenate([j0, np.array(outj).ravel()]).astype(np.int32)
-    return dict(ddata=ddata, idata=idata, ng=ng, npad_size=npad_size, pad_in_left=pad_in_left, pad_out_left=pad_out_left, k=k, s=np.array(s_grids))
+    return dict(ddata=ddata, idata=idata, ng=ng, npad_size=npad_size, pad_in_left=pad_in_left, pad_out_left=pad_out_left, k=k, s=np.array(s_grids),
+                j0=j0, c0=c0, c1=c1, u=[uu[..., 0] + 1j * uu[..., 1] for uu in u], post=post, outj=outj, outw=outw)
+
+
+def fftlog_operator(kin, ells, s_out, **kwargs):
+    """The whole P_ell(kin) -> xi_ell(s_out) chain of ``get_corr`` (reference desilike/theories/galaxy_clustering/base.py:127-136:
+    log-k resampling + damped high-k extrapolation, FFTLog, linear interpolation onto ``s_out``) is LINEAR in P_ell(kin): returns
+    the operators ``T`` [nell, nkin, ns] with ``xi_ell(s_out) = P_ell(kin) @ T[ell]``, obtained at plan time by pushing the unit
+    vectors through the transform (NumPy real FFTs of 4096 points, once).  The lowering folds ``T`` into the term matrices together
+    with the window and the whitening, so the per-point path is the damped-BAO kernel followed by the contraction; the explicit
+    FFTLog kernel (csrc/theory_kernels.cu:fftlog_kernel) remains available with ``theory['fftlog'] = 'kernel'``."""
+    fc = fftlog_constants(kin, ells, s_out, **kwargs)
+    nkin, ng, npad_size = np.size(kin), fc['ng'], fc['npad_size']
+    X = np.zeros((nkin, npad_size))
+    idx = np.arange(ng)
+    np.add.at(X, (fc['j0'], fc['pad_in_left'] + idx), fc['c0'])
+    np.add.at(X, (fc['j0'] + 1, fc['pad_in_left'] + idx), fc['c1'])
+    spec = np.fft.rfft(X, axis=-1)
+    T = []
+    for ill in range(len(ells)):
+        xi = np.fft.hfft(spec * fc['u'][ill], n=npad_size, axis=-1)[:, fc['pad_out_left']:fc['pad_out_left'] + ng] / npad_size * fc['post'][ill]
+        jj, w = fc['outj'][ill], fc['outw'][ill]
+        T.append(xi[:, jj] * (1. - w) + xi[:, jj + 1] * w)
+    return np.array(T)

@@ -247,8 +247,10 @@ class DampedBAOWigglesTracerCorrelationFunctionMultipoles(_BaseBAOTracer):
     al{ell}_{pow} (s / sp)^pow, pow in [-2, 2], sp = 2 pi / 0.02 (reference bao.py:849-853, :867, :905)."""
     is_correlation = True
 
-    def __init__(self, template, s=None, sp=None, **kwargs):
+    def __init__(self, template, s=None, sp=None, fftlog='fold', **kwargs):
         super().__init__(template, **kwargs)
+        # fftlog: 'fold' = the (linear) P_ell(kin) -> xi_ell(s) operator is folded into the plan's term matrices; 'kernel' = explicit FFTLog kernel
+        self.fftlog = str(fftlog)
         self.s = np.linspace(20., 200., 101) if s is None else np.asarray(s, dtype='f8')
         self.sp = 2. * np.pi / 0.02 if sp is None else float(sp)
         for ell in self.ells:
@@ -263,7 +265,7 @@ class DampedBAOWigglesTracerCorrelationFunctionMultipoles(_BaseBAOTracer):
         return len(self.ells) * len(self.s)
 
     def theory_spec(self):
-        return dict(self._theory_common(), kind='bao_xi', s=self.s)
+        return dict(self._theory_common(), kind='bao_xi', s=self.s, fftlog=self.fftlog)
 
     def terms(self):
         return [dict(scale=1., factors=[], table='corr')] + self._broadband_terms(self.s, self.sp, range(-2, 3))

@@ -123,7 +123,25 @@ def lower_theory(gen, theory, defaults, names=None):
         sk = np.exp(-0.5 * (k * rs_)**2) if flags & 1 else np.zeros(nk)
         ddata += [np.log10(k), sk, k**2, pk_t - pknow_t, M_pk - M_now, np.append(np.diff(np.log10(k_t)), 0.)]
         nin = nell * nk
-        if xi:
+        fold = xi and theory.get('fftlog', 'fold') == 'fold'
+        if theory.get('fftlog', 'fold') not in ('fold', 'kernel'):
+            raise ValueError("theory['fftlog'] must be 'fold' (P -> xi operator folded into the term matrices) or 'kernel' (explicit FFTLog kernel)")
+        if fold:
+            # P_ell(kin) -> xi_ell(s) (resampling, FFTLog, interpolation onto s) is linear: fold it at plan time like the window matrix;
+            # the generator is the damped-BAO kernel in P(k) mode on kin, the table 'corr' a linear map of its P_ell(kin) features
+            from .fftlog import fftlog_operator
+            T = fftlog_operator(k, ells, s_out)
+            ns = s_out.size
+            D = np.zeros((nin, nell * ns))
+            for ill in range(nell): D[ill * nk:(ill + 1) * nk, ill * ns:(ill + 1) * ns] = T[ill]
+            flags &= ~2
+            total = 2 + nin
+            header = [nk, nell, nmu, nt, APMODES[apmode], flags, off_derived, total, 0, nk, 0, 16, 2, 0, 0, 0]
+            gen.idata = np.array(header, dtype=np.int32)
+            gen.nfeat = total
+            gen.tables['corr'] = (2, nin, D)
+            gen.tables['power'] = (2, nin, None)
+        elif xi:
             ns = s_out.size
             nvis = 2 + nell * ns
             poff = (nvis + 3) & ~3

@@ -103,10 +103,17 @@ def test_unsupported_features_fail_loudly():
         Lowered(spec)
 
 
+def _c3_kernel():
+    spec = configs.config_c3()
+    spec['observables'][0]['theory']['fftlog'] = 'kernel'
+    return spec
+
+
 THEORY_CASES = {
     'c1_kaiser': lambda: configs.config_c1(),
     'kaiser_window_eft_marg': lambda: configs.config_kaiser_window(eftlike=True, solved=True),
-    'c3_bao_fftlog': lambda: configs.config_c3(),
+    'c3_bao_fftlog': lambda: configs.config_c3(),                    # P -> xi operator folded into the term matrices (default)
+    'c3_bao_fftlog_kernel': lambda: _c3_kernel(),                    # explicit FFTLog kernel payload
     'c4_mlp': lambda: configs.config_c4(ntracers=2, nkin=40, nbins=10, hidden=(16, 16)),
 }
 

@@ -124,10 +124,13 @@ def test_mlp_full_width(gpu_required):
         plan.close()
 
 
-def test_c3_bao_fftlog(gpu_required):
-    """BASELINE configs[2]: damped-BAO P(k) -> FFTLog -> xi_ell(s) (+ marginalised broadband) -> chi2."""
+@pytest.mark.parametrize('fftlog', ['fold', 'kernel'])
+def test_c3_bao_fftlog(gpu_required, fftlog):
+    """BASELINE configs[2]: damped-BAO P(k) -> FFTLog -> xi_ell(s) (+ marginalised broadband) -> chi2; with the P -> xi operator folded
+    into the term matrices (default) and through the explicit FFTLog kernel."""
     import desilike_b200
     spec = configs.config_c3()
+    spec['observables'][0]['theory']['fftlog'] = fftlog
     plan = desilike_b200.Plan(spec)
     X = configs.sample_points(spec, 96, seed=33)
     ref = pipeline.evaluate(spec, X, return_theory=True)
@@ -185,7 +188,8 @@ def test_bao_power_spectrum(gpu_required):
     plan.close()
 
 
-def test_bao_kernels_match_reference_classes(gpu_required):
+@pytest.mark.parametrize('fftlog', ['fold', 'kernel'])
+def test_bao_kernels_match_reference_classes(gpu_required, fftlog):
     """GPU damped-BAO P_ell(k) and FFTLog xi_ell(s) vs the outputs of the reference's own classes (tests/golden/bao_theory.npz)."""
     import desilike_b200
     from oracle import synthetic
@@ -194,7 +198,7 @@ def test_bao_kernels_match_reference_classes(gpu_required):
     names = ['qpar', 'qper', 'b1', 'dbeta', 'sigmas', 'sigmapar', 'sigmaper']
     for which, kt in [('power', data['k_template_pk']), ('corr', data['k_template_xi'])]:
         tpl = dict(kind='bao', k=kt, pk_dd_fid=synthetic.pk_fid(kt), pknow_dd_fid=synthetic.pknow_fid(kt), f_fid=synthetic.F_FID, apmode='qparqper', eta=1. / 3.)
-        theory = dict(ells=ells, nmu=10, template=tpl, mode='', params=names, defaults={})
+        theory = dict(ells=ells, nmu=10, template=tpl, mode='', params=names, defaults={}, fftlog=fftlog)
         theory.update(dict(kind='bao_pk', k=k) if which == 'power' else dict(kind='bao_xi', s=s))
         n = 2 * (k.size if which == 'power' else s.size)
         obs = dict(name='x', theory=theory, terms=[dict(scale=1., factors=[], table=which)], nin=n, wmatrix=None, offset=None, data=np.zeros(n))
