@@ -12,7 +12,7 @@ from .build import LIBPATH
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
 
-DLB_ABI_VERSION = 1
+DLB_ABI_VERSION = 2
 DLB_COEF_MAXF = 4
 GEN_TAYLOR, GEN_MLP, GEN_KAISER, GEN_BAO = 1, 2, 3, 4
 PT_NONFINITE, PT_OUT_OF_PRIOR, PT_NOT_SPD = 1, 2, 4
@@ -35,7 +35,8 @@ class TermDesc(ctypes.Structure):
 class BlockDesc(ctypes.Structure):
     _fields_ = [('ncols', ctypes.c_int32), ('nslots', ctypes.c_int32), ('nterms', ctypes.c_int32), ('terms', ctypes.POINTER(TermDesc)),
                 ('matrices_white', c_double_p), ('matrices_plain', c_double_p), ('r0_white', c_double_p), ('t0_plain', c_double_p),
-                ('slot_solved', c_int32_p), ('nconst', ctypes.c_int32), ('const_solved', c_int32_p), ('gconst_white', c_double_p)]
+                ('slot_solved', c_int32_p), ('nconst', ctypes.c_int32), ('const_solved', c_int32_p), ('gconst_white', c_double_p),
+                ('transform_data', c_double_p), ('whitening_t', c_double_p), ('r0_data_white', c_double_p)]
 
 
 class PlanDesc(ctypes.Structure):

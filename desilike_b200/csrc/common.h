@@ -80,6 +80,7 @@ struct BlockDev {     // one output block as seen by the contraction kernel (dev
   long long poff;                      // first Gram-partial row of the block: partial[(poff + e) * npad + point]
   int nchunks, ncb, nslots, nconst, npart, ncols, ocol0, gen;
   int fill, fbase, acols;              // resident A: 0 = evaluate Taylor monomials, 1 = copy acols columns of F from column fbase
+  const double* tdata;                 // output mode: [ncols] data d of the 'cubic'-transformed columns (0: untransformed column), or NULL
 };
 
 struct DevCoef { double scale; int nf; int idx[DLB_COEF_MAXF]; int pow[DLB_COEF_MAXF]; };

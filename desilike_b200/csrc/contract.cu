@@ -421,6 +421,10 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
                     if (p.act == 1) v = silu(v);                   // silu  (reference emulators/conversion.py:27)
                     else if (p.act == 2) v = fmax(v, 0.);          // relu  (:29)
                     else if (p.act == 3) v = tanh(v);              // tanh  (:31)
+                    if (blk->tdata) {   // observable transform (reference observables/galaxy_clustering/power_spectrum.py:402-404)
+                      const double dcol = __ldg(blk->tdata + col);
+                      if (dcol != 0.) v = (3. * cbrt(v / dcol) - 2.) * dcol;
+                    }
                     p.out[row * p.ostride + blk->ocol0 + col] = v;
                   }
                 }

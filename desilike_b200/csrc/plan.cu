@@ -23,6 +23,8 @@ struct Block {
   Chunk* d_chunks = nullptr;
   double *d_tiles_white = nullptr, *d_tiles_plain = nullptr, *d_epi_white = nullptr, *d_epi_plain = nullptr;
   EntryMap* d_map = nullptr;
+  double* d_tdata = nullptr;   // 'cubic' observable transform: data of the transformed columns (two-stage plans)
+  int tcol = 0;                // first column of the block in the transformed-theory buffer of a two-stage plan
 };
 
 // launch configuration of one persistent contraction launch (a list of blocks sharing one kernel variant)
@@ -30,6 +32,7 @@ struct Launch {
   Variant var;
   int nblocks = 0, nstages = 2, resident = 0, ast = 0, npart_max = 1;
   BlockDev *d_white = nullptr, *d_plain = nullptr;
+  BlockDev* d_plain_t = nullptr;   // two-stage plans: the un-whitened table writing into the transformed-theory buffer (ocol0 = Block::tcol)
   SchedEntry *d_sched_white = nullptr, *d_sched_plain = nullptr;   // per-tile TMA schedule
   int nsched = 0;
 };
@@ -43,6 +46,13 @@ struct dlb_plan {
   int d = 0, ngen = 0, ncoef = 0, fstride = 4, ns = 0, nmarg = 0, ntheory = 0, nsm = 1, dpad = 1;
   bool resident = false;               // Taylor monomials evaluated inside the contraction kernel (no feature matrix in HBM)
   dlb::Launch launch;                  // the likelihood blocks
+  // two-stage plans (an observable transform that is non-linear in the theory, reference power_spectrum.py:400-404): stage 1 = `launch` in output
+  // mode with the un-whitened matrices and the transform in its epilogue -> w_T [npad, tstride]; stage 2 = `wlaunch`: r = u . L^T - L data
+  bool two_stage = false;
+  dlb::Launch wlaunch;
+  std::vector<dlb::Block> wblocks;
+  int tstride = 0;
+  double* w_T = nullptr;
   dlb::GenDev* d_gens = nullptr;
   std::vector<unsigned long long*> d_paths;   // per generator (resident mode)
   std::vector<dlb::DevGen> gens;
@@ -267,10 +277,16 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
       bd.paths = (resident && b->gen >= 0) ? plan->d_paths[b->gen] : nullptr; bd.poff = b->poff;
       bd.nchunks = b->nchunks; bd.ncb = b->ncb; bd.nslots = b->nslots; bd.nconst = b->nconst; bd.npart = b->npart; bd.ncols = b->ncols;
       bd.ocol0 = b->coloff; bd.gen = b->gen; bd.fill = b->fill; bd.fbase = b->fbase; bd.acols = std::min((b->maxcol + 1) & ~1, L.ast);
+      bd.tdata = pass == 1 ? b->d_tdata : nullptr;
       tab.push_back(bd);
     }
     if (!ok) continue;
     DLB_TRY(upload(plan, tab.data(), tab.size(), pass == 0 ? &L.d_white : &L.d_plain));
+    if (pass == 1 && blocks[0]->d_tdata) {
+      std::vector<BlockDev> tab_t(tab);
+      for (size_t ib = 0; ib < blocks.size(); ++ib) tab_t[ib].ocol0 = blocks[ib]->tcol;
+      DLB_TRY(upload(plan, tab_t.data(), tab_t.size(), &L.d_plain_t));
+    }
     // per-tile TMA schedule: for every block, column block: the k-chunk tiles in order, then the epilogue constants
     const int BN = variant_bn(L.var), KC = L.var.KC;
     std::vector<SchedEntry> sched;
@@ -337,10 +353,14 @@ static int build_mlp(dlb_plan* plan, const dlb_generator_desc& gd, DevGen& g, Ml
 
 static int ensure_workspace(dlb_plan* plan, long long npad) {
   if (npad <= plan->cap) return DLB_OK;
-  for (void* ptr : {(void*)plan->w_F, (void*)plan->w_partial, (void*)plan->w_params, (void*)plan->w_out, (void*)plan->w_status})
+  for (void* ptr : {(void*)plan->w_F, (void*)plan->w_partial, (void*)plan->w_params, (void*)plan->w_out, (void*)plan->w_status, (void*)plan->w_T})
     if (ptr) cudaFree(ptr);
-  plan->w_F = plan->w_partial = plan->w_params = plan->w_out = nullptr; plan->w_status = nullptr;
+  plan->w_F = plan->w_partial = plan->w_params = plan->w_out = plan->w_T = nullptr; plan->w_status = nullptr;
   plan->cap = 0;
+  if (plan->two_stage) {
+    DLB_CUDA(cudaMalloc((void**)&plan->w_T, ((size_t)npad * plan->tstride + 64) * sizeof(double)));
+    DLB_CUDA(cudaMemset(plan->w_T, 0, ((size_t)npad * plan->tstride + 64) * sizeof(double)));
+  }
   DLB_CUDA(cudaMalloc((void**)&plan->w_F, ((size_t)npad * plan->fstride + 64) * sizeof(double)));
   DLB_CUDA(cudaMemset(plan->w_F, 0, ((size_t)npad * plan->fstride + 64) * sizeof(double)));
   DLB_CUDA(cudaMalloc((void**)&plan->w_partial, (size_t)std::max(plan->ptotal, 1LL) * npad * sizeof(double)));
@@ -385,7 +405,29 @@ static int run_front(dlb_plan* plan, const double* d_params, long long N, long l
   return DLB_OK;
 }
 
+// Two-stage plans: theory vectors (un-whitened matrices) with the observable transform applied in the epilogue -> w_T, then the
+// whitening contraction r = u . L^T - L data with its chi2 reduction (one Gram partial per block).
+static int run_two_stage(dlb_plan* plan, const double* d_params, long long N, long long npad, cudaStream_t stream) {
+  {
+    const Launch& L = plan->launch;
+    ContractParams cp;
+    fill_params(plan, L, cp, d_params, N, npad);
+    cp.blocks = L.d_plain_t; cp.sched = L.d_sched_plain; cp.nsched = L.nsched;
+    cp.out = plan->w_T; cp.ostride = plan->tstride; cp.out_rows = npad; cp.act = 0; cp.mode = 1;
+    cp.U = (N + variant_unit(L.var) - 1) / variant_unit(L.var);
+    DLB_TRY(launch_contract(L.var, cp, plan->nsm, stream));
+  }
+  const Launch& L = plan->wlaunch;
+  ContractParams cp;
+  fill_params(plan, L, cp, d_params, N, npad);
+  cp.blocks = L.d_white; cp.sched = L.d_sched_white; cp.nsched = L.nsched; cp.ncoef = 0;
+  cp.F = plan->w_T; cp.fstride = plan->tstride; cp.mode = 0;
+  cp.U = (N + variant_unit(L.var) - 1) / variant_unit(L.var);
+  return launch_contract(L.var, cp, plan->nsm, stream);
+}
+
 static int run_contract(dlb_plan* plan, const double* d_params, long long N, long long npad, int mode, double* d_theory, cudaStream_t stream) {
+  if (mode == 0 && plan->two_stage) return run_two_stage(plan, d_params, N, npad, stream);
   const Launch& L = plan->launch;
   ContractParams cp;
   fill_params(plan, L, cp, d_params, N, npad);
@@ -435,7 +477,7 @@ void dlb_plan_destroy(dlb_plan* plan) {
   if (!plan) return;
   cudaSetDevice(plan->device);
   for (void* ptr : plan->owned) cudaFree(ptr);
-  for (void* ptr : {(void*)plan->w_F, (void*)plan->w_partial, (void*)plan->w_params, (void*)plan->w_out, (void*)plan->w_status, (void*)plan->w_theory})
+  for (void* ptr : {(void*)plan->w_F, (void*)plan->w_partial, (void*)plan->w_params, (void*)plan->w_out, (void*)plan->w_status, (void*)plan->w_theory, (void*)plan->w_T})
     if (ptr) cudaFree(ptr);
   for (auto& e : plan->ev) if (e) cudaEventDestroy(e);
   if (plan->w_hess) cudaFree(plan->w_hess);
@@ -618,7 +660,37 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
     bptr.push_back(&blk);
   }
   plan->ntheory = coloff; plan->ptotal = poff;
+  for (int ib = 0; ib < desc->nblocks; ++ib) plan->two_stage = plan->two_stage || desc->blocks[ib].transform_data != nullptr;
+  if (plan->two_stage) {
+    DLB_REQUIRE(desc->ns == 0, "observable transform: solved parameters are not supported in a two-stage plan");
+    int tcol = 0;
+    for (int ib = 0; ib < desc->nblocks; ++ib) {
+      const dlb_block_desc& bd = desc->blocks[ib];
+      DLB_REQUIRE(bd.transform_data && bd.whitening_t && bd.r0_data_white && bd.matrices_plain && bd.t0_plain && bd.nslots == 1 && bd.nconst == 0,
+                  "observable transform: every block needs transform_data, whitening_t, r0_data_white, matrices_plain, t0_plain");
+      DLB_TRY(upload(plan, bd.transform_data, (size_t)bd.ncols, &plan->blocks[ib].d_tdata));
+      plan->blocks[ib].tcol = tcol;
+      tcol += (bd.ncols + 3) & ~3;   // blocks start on 32-byte boundaries; k-chunks may read up to the padded length (zeros)
+    }
+    plan->tstride = tcol;
+  }
   DLB_TRY(build_launch(plan, bptr, resident, ast, desc->ncoef, plan->launch));
+  if (plan->two_stage) {
+    int maxn = 0;
+    for (int ib = 0; ib < desc->nblocks; ++ib) maxn = std::max(maxn, desc->blocks[ib].ncols);
+    const Variant wvar = pick_variant(plan, 1, false, 0, 0, 1, maxn);
+    plan->wblocks.resize(desc->nblocks);
+    std::vector<Block*> wptr;
+    for (int ib = 0; ib < desc->nblocks; ++ib) {
+      const dlb_block_desc& bd = desc->blocks[ib];
+      Block& wb = plan->wblocks[ib];
+      std::vector<TermSpec> terms{TermSpec{0, -1, plan->blocks[ib].tcol, plan->blocks[ib].tcol, bd.ncols, bd.whitening_t, nullptr}};
+      DLB_TRY(build_block_core(plan, wvar, false, bd.ncols, 1, terms, bd.r0_data_white, nullptr, 0, nullptr, wb));
+      wb.poff = plan->blocks[ib].poff; wb.coloff = plan->blocks[ib].coloff; wb.gen = -1; wb.d_map = plan->blocks[ib].d_map;
+      wptr.push_back(&wb);
+    }
+    DLB_TRY(build_launch(plan, wptr, false, 0, 0, plan->wlaunch));
+  }
   {
     size_t maxdepth = 0;
     for (MlpLayers& mlp : plan->mlps) maxdepth = std::max(maxdepth, mlp.layers.size());

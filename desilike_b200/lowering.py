@@ -144,6 +144,7 @@ class Lowered(object):
         else:
             groups = [(list(observables), np.asarray(prec, dtype=np.float64))]
         self.blocks = []
+        self.two_stage = False   # any transformed observable: theory -> transform -> whitening as two contraction launches
         for group, P in groups:
             ncols = sum(len(o['data']) for o in group)
             if P.shape[0] != ncols: raise LoweringError('precision size {} != data size {}'.format(P.shape, ncols))
@@ -153,10 +154,17 @@ class Lowered(object):
             const_plain = np.zeros(ncols)
             data = np.concatenate([f64(o['data']) for o in group])
             c0 = 0
+            tdata = np.zeros(ncols)   # flat data of the 'cubic'-transformed columns (reference power_spectrum.py:400-404), 0 elsewhere
             for obs in group:
-                if obs.get('transform') is not None:
-                    raise LoweringError('observable transform {!r} is not on the CUDA path yet'.format(obs['transform']))
                 n_o, nin = len(obs['data']), int(obs['nin'])
+                if obs.get('transform') is not None:
+                    if obs['transform'] != 'cubic': raise LoweringError('unknown observable transform {!r}'.format(obs['transform']))
+                    if solved:
+                        raise LoweringError("observable transform 'cubic' is non-linear in the theory: analytically solved parameters are not "
+                                            "supported together with it on the CUDA path")
+                    if np.any(f64(obs['data']) == 0.): raise LoweringError("transform 'cubic' divides by the data vector: zero entries found")
+                    tdata[c0:c0 + n_o] = f64(obs['data'])
+                    self.two_stage = True
                 W = f64(obs['wmatrix']) if obs.get('wmatrix') is not None else None
                 if W is None and nin != n_o: raise LoweringError('wmatrix=None requires nin == len(data)')
                 gi = gen_of[id(obs['theory'])]
@@ -213,6 +221,7 @@ class Lowered(object):
             blk['white'] = [terms[k] @ L.T for k in keys]
             blk['r0_white'] = L @ (data - const_plain)
             blk['t0_plain'] = const_plain
+            blk['transform_data'], blk['whitening_t'], blk['r0_data_white'] = tdata, np.ascontiguousarray(L.T), L @ data
             inv = sorted(slot_of.items(), key=lambda kv: kv[1])
             blk['slot_solved'] = i32([si for si, _ in inv])
             blk['const_solved'] = i32(sorted(const_rows.keys()))
@@ -249,10 +258,14 @@ class Lowered(object):
                 t.moff = moff
                 moff += mat.size
             white = f64(np.concatenate([m.ravel() for m in blk['white']]))
-            plain = f64(np.concatenate([m.ravel() for m in blk['plain']])) if self.with_plain else None
+            plain = f64(np.concatenate([m.ravel() for m in blk['plain']])) if (self.with_plain or self.two_stage) else None
             r0, t0 = f64(blk['r0_white']), f64(blk['t0_plain'])
             ss, cs, gc = i32(blk['slot_solved']), i32(blk['const_solved']), f64(blk['gconst_white'])
             keep += [terms, white, plain, r0, t0, ss, cs, gc]
+            if self.two_stage:
+                td, wt, rd = f64(blk['transform_data']), f64(blk['whitening_t']), f64(blk['r0_data_white'])
+                keep += [td, wt, rd]
+                b.transform_data, b.whitening_t, b.r0_data_white = as_ptr(td), as_ptr(wt), as_ptr(rd)
             b.ncols, b.nslots, b.nterms, b.terms = blk['ncols'], blk['nslots'], nt, terms
             b.matrices_white, b.matrices_plain = as_ptr(white), as_ptr(plain)
             b.r0_white, b.t0_plain = as_ptr(r0), as_ptr(t0)
@@ -276,5 +289,6 @@ class Lowered(object):
                 # contraction itself (csrc/plan.cu: build_block_core)
                 contract += 2 * K * (blk['ncols'] + nc)
             gram += 2 * blk['ncols'] * (R * (R + 1) // 2)
+            if self.two_stage: contract += 2 * blk['ncols']**2   # second stage: whitening of the transformed theory vector
         solve = self.ns**3 // 3 + 2 * self.ns**2
         return dict(contract=contract, gram=gram, solve=solve, total=contract + gram + solve)

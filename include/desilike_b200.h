@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DLB_ABI_VERSION 1
+#define DLB_ABI_VERSION 2
 
 typedef enum {
   DLB_OK = 0,
@@ -102,6 +102,14 @@ typedef struct {
   int32_t nconst;                /* constant (theta-independent) whitened Jacobian rows */
   const int32_t* const_solved;   /* [nconst] solved-parameter index */
   const double* gconst_white;    /* [nconst, ncols] */
+  /* Optional observable transform (reference observables/galaxy_clustering/power_spectrum.py:400-404, 'cubic':
+   * u = (3 (t / d)^(1/3) - 2) d).  It is non-linear in the theory vector, so a plan with a transformed block is evaluated in two
+   * stages: t = slot 0 + t0_plain through the un-whitened matrices (required), u on the columns with transform_data != 0, then the
+   * whitened residual r = u . whitening_t - r0_data_white.  Either no block or every block of a plan provides these three; solved
+   * parameters are not supported together with a transform (ns must be 0). */
+  const double* transform_data;  /* [ncols] flat data d of the transformed columns, 0 on untransformed columns (NULL: one-stage plan) */
+  const double* whitening_t;     /* [ncols, ncols] row-major L^T:  r_c = sum_j u_j whitening_t[j, c] */
+  const double* r0_data_white;   /* [ncols] L . data */
 } dlb_block_desc;
 
 typedef struct {

@@ -51,10 +51,21 @@ def evaluate(low, X, feature_fn=None, white=True):
             slot, coef, gen, foff, K = key
             c = C[:, coef] if coef >= 0 else 1.
             slots[slot] += (np.atleast_1d(c)[:, None] if coef >= 0 else 1.) * (F[gen][:, foff:foff + K] @ (mw if white else mp))
-        if not white:
-            theory.append(slots[0] + blk['t0_plain'])
-            continue
-        r = slots[0] - blk['r0_white']
+        if not white or low.two_stage:
+            # two-stage plans (observable transform, csrc/plan.cu:run_two_stage): theory through the un-whitened matrices, transform in
+            # the epilogue, then the whitening contraction
+            t = slots[0] + blk['t0_plain'] if not white else sum((np.atleast_1d(C[:, key[1]])[:, None] if key[1] >= 0 else 1.) * (F[key[2]][:, key[3]:key[3] + key[4]] @ mp)
+                                                                 for key, mp in zip(blk['terms'], blk['plain'])) + blk['t0_plain']
+            if low.two_stage:
+                d = blk['transform_data']
+                with np.errstate(divide='ignore', invalid='ignore'):
+                    t = np.where(d != 0., (3. * np.cbrt(t / np.where(d != 0., d, 1.)) - 2.) * d, t)
+            if not white:
+                theory.append(t)
+                continue
+            r = t @ blk['whitening_t'] - blk['r0_data_white']
+        else:
+            r = slots[0] - blk['r0_white']
         chi2 += np.sum(r**2, axis=-1)
         rows = [(int(si), slots[1 + a]) for a, si in enumerate(blk['slot_solved'])]
         rows += [(int(si), np.broadcast_to(blk['gconst_white'][i], (N, blk['ncols']))) for i, si in enumerate(blk['const_solved'])]

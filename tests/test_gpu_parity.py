@@ -184,3 +184,28 @@ def test_pipelined_host_path_large_batch(gpu_required):
     for key in ['logposterior', 'loglikelihood', 'logprior', 'x_solved', 'status']:
         assert np.array_equal(host[key], dev[key].cpu().numpy()), key
     plan.close()
+
+
+def test_cubic_observable_transform_two_stage(gpu_required):
+    """Observable transform 'cubic' (reference observables/galaxy_clustering/power_spectrum.py:400-404) on Taylor-emulated tracers: the plan runs
+    theory -> transform -> whitening as two contraction launches; one tracer transformed, one not, block-diagonal and joint dense precision."""
+    import desilike_b200
+    for joint in [False, True]:
+        spec = configs.config_c5(ntracers=2, nkin=40, nbins=10, order=2, solved=False)
+        spec['observables'][0]['transform'] = 'cubic'
+        if joint:
+            P = spec['precision']
+            n = sum(p.shape[0] for p in P)
+            dense = np.zeros((n, n)); o = 0
+            for p in P: dense[o:o + p.shape[0], o:o + p.shape[0]] = p; o += p.shape[0]
+            rng = np.random.default_rng(3)
+            v = rng.standard_normal(n) * np.sqrt(np.diag(dense)) * 0.1
+            spec['precision'] = dense + np.outer(v, v)
+        plan = desilike_b200.Plan(spec)
+        X = configs.sample_points(spec, 777, seed=21)
+        ref = pipeline.evaluate(spec, X, return_theory=True)
+        got = plan.eval(X)
+        assert np.max(np.abs(plan.theory(X) - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-10
+        assert np.max(np.abs(got['loglikelihood'] - ref['loglikelihood']) / np.maximum(1., np.abs(ref['loglikelihood']))) < 1e-9
+        assert np.array_equal(np.isneginf(got['logposterior']), np.isneginf(ref['logposterior']))
+        plan.close()
