@@ -136,6 +136,8 @@ int launch_mlp_fused(const DevGen* d_gens, const int* d_mlp_index, int nmlp, siz
 // ---------------------------------------------------------------------------------------------------------------------
 struct EntryMap { int kind; int i; int j; };   // kind 0: chi2 += v; 1: g[i] -= v; 2: M[i][j] += v (and M[j][i])
 struct SolveBlock { long long poff; int ncb; int npart; const EntryMap* map; };
+// thread-per-point solve (small independent groups): Gram-partial row -> entry of its group's local system
+struct GroupEntry { long long prow; int kind; int li; int lj; };   // kind 1: g[li] -= v; 2: M[li][lj] += v (li >= lj)
 
 struct SolveParams {
   const double* params; int d; long long N; long long npad;
@@ -152,6 +154,8 @@ struct SolveParams {
   int npos; const int* comp_pos; const double* comp_m0;   // intra-group matrix positions (i * (ns + 1) + j) and their constant part
   double* logpost; double* loglike; double* logprior; double* xsolved; int* status;
   double* hess; int nhess; const int* hess_ij; const int* comp_of;   // optional packed upper triangle of M = -H_posterior per point
+  // thread-per-point form (every group <= 8 parameters): entries sorted by group, chi2 rows, offsets of the groups' constant blocks in comp_m0
+  const GroupEntry* gent; const int* gent_off; const long long* chi_rows; int nchi; const int* m0_off; int comp_max;
 };
 int launch_solve(const SolveParams& p, cudaStream_t stream);
 

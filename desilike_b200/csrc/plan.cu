@@ -23,6 +23,7 @@ struct Block {
   Chunk* d_chunks = nullptr;
   double *d_tiles_white = nullptr, *d_tiles_plain = nullptr, *d_epi_white = nullptr, *d_epi_plain = nullptr;
   EntryMap* d_map = nullptr;
+  std::vector<EntryMap> h_map;
   double* d_tdata = nullptr;   // 'cubic' observable transform: data of the transformed columns (two-stage plans)
   int tcol = 0;                // first column of the block in the transformed-theory buffer of a two-stage plan
 };
@@ -70,6 +71,7 @@ struct dlb_plan {
   int *d_comp_off = nullptr, *d_comp_idx = nullptr, *d_comp_nmarg = nullptr, *d_comp_pos = nullptr;
   double* d_comp_m0 = nullptr; int npos = 0;
   int *d_hess_ij = nullptr, *d_comp_of = nullptr;
+  dlb::GroupEntry* d_gent = nullptr; int *d_gent_off = nullptr, *d_m0_off = nullptr; long long* d_chi_rows = nullptr; int nchi = 0, comp_max = 0;
   double* w_hess = nullptr; long long hess_cap = 0;
   cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host-buffer path
   cudaEvent_t ev_pipe[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -254,6 +256,7 @@ static int build_block(dlb_plan* plan, const dlb_plan_desc* desc, const dlb_bloc
   for (const EntryMap& m : map)
     DLB_REQUIRE(m.kind == 0 || (m.i >= 0 && m.i < desc->ns && (m.kind == 1 || (m.j >= 0 && m.j < desc->ns))), "solved-parameter index out of range");
   DLB_TRY(upload(plan, map.data(), map.size(), &blk.d_map));
+  blk.h_map = map;
   return DLB_OK;
 }
 
@@ -788,6 +791,41 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
       plan->npos = (int)pos.size();
       DLB_TRY(upload(plan, pos.data(), pos.size(), &plan->d_comp_pos));
       DLB_TRY(upload(plan, m0v.data(), m0v.size(), &plan->d_comp_m0));
+      plan->comp_max = maxsize;
+      if (maxsize <= 8 && !getenv("DLB_SOLVE_WARP")) {   // tables of the thread-per-point solve kernel (csrc/solve.cu)
+        const int nc = plan->ncomp;
+        std::vector<int> group_of(ns, -1), local_of(ns, -1), m0_off(nc, 0);
+        for (int c = 0, acc = 0; c < nc; ++c) {
+          m0_off[c] = acc;
+          const int n = comp_off[c + 1] - comp_off[c];
+          acc += n * n;
+          for (int a = 0; a < n; ++a) { group_of[comp_idx[comp_off[c] + a]] = c; local_of[comp_idx[comp_off[c] + a]] = a; }
+        }
+        std::vector<std::vector<GroupEntry>> per(nc);
+        std::vector<long long> chi_rows;
+        for (int ib = 0; ib < desc->nblocks; ++ib) {
+          const Block& blk = plan->blocks[ib];
+          for (int e = 0; e < blk.npart; ++e) {
+            const EntryMap& m = blk.h_map[e];
+            const long long prow = blk.poff + e;
+            if (m.kind == 0) { chi_rows.push_back(prow); continue; }
+            const int c = group_of[m.i];
+            if (m.kind == 1) per[c].push_back(GroupEntry{prow, 1, local_of[m.i], 0});
+            else {
+              DLB_REQUIRE(group_of[m.j] == c, "internal: coupled solved parameters in different groups");
+              per[c].push_back(GroupEntry{prow, 2, std::max(local_of[m.i], local_of[m.j]), std::min(local_of[m.i], local_of[m.j])});
+            }
+          }
+        }
+        std::vector<GroupEntry> gent;
+        std::vector<int> gent_off{0};
+        for (int c = 0; c < nc; ++c) { gent.insert(gent.end(), per[c].begin(), per[c].end()); gent_off.push_back((int)gent.size()); }
+        plan->nchi = (int)chi_rows.size();
+        DLB_TRY(upload(plan, gent.data(), gent.size(), &plan->d_gent));
+        DLB_TRY(upload(plan, gent_off.data(), gent_off.size(), &plan->d_gent_off));
+        DLB_TRY(upload(plan, chi_rows.data(), chi_rows.size(), &plan->d_chi_rows));
+        DLB_TRY(upload(plan, m0_off.data(), m0_off.size(), &plan->d_m0_off));
+      }
     }
   }
   for (auto& e : plan->ev) DLB_CUDA(cudaEventCreate(&e));
@@ -832,7 +870,7 @@ int dlb_eval_batch_hessian(dlb_plan* plan, const double* params, int64_t N, doub
     }
     // Host buffers: split the chunk into sub-chunks and pipeline  H2D (copy-in stream) | kernels (caller's stream) | D2H (copy-out
     // stream)  so that the PCIe transfers of one sub-chunk overlap the kernels of its neighbours.  Device buffers: one pass.
-    const long long SUB_MIN = 65536;   // smaller sub-chunks cost more in kernel efficiency than the overlap gains (measured at 16384: C5 e2e -19 %)
+    static const long long SUB_MIN = getenv("DLB_SUB_MIN") ? atoll(getenv("DLB_SUB_MIN")) : 65536;   // smaller sub-chunks cost more in kernel efficiency than the overlap gains (measured at 16384: C5 e2e -19 %)
     int nsub = 1;
     if (any_host && !plan->timing && n >= 2 * SUB_MIN) nsub = (int)std::min<long long>(4, n / SUB_MIN);
     cudaStream_t s_in = stream, s_out = stream;
@@ -883,6 +921,7 @@ int dlb_eval_batch_hessian(dlb_plan* plan, const double* params, int64_t N, doub
       sp.status = status ? (st_dev ? status + g0 : plan->w_status + off) : nullptr;
       sp.hess = hessian ? (hs_dev ? hessian + g0 * nhess : plan->w_hess + off * nhess) : nullptr;
       sp.nhess = nhess; sp.hess_ij = plan->d_hess_ij; sp.comp_of = plan->d_comp_of;
+      sp.gent = plan->d_gent; sp.gent_off = plan->d_gent_off; sp.chi_rows = plan->d_chi_rows; sp.nchi = plan->nchi; sp.m0_off = plan->d_m0_off; sp.comp_max = plan->comp_max;
       rc = launch_solve(sp, stream);
       if (rc) return rc;
       if (plan->timing) DLB_CUDA(cudaEventRecord(plan->ev[3], stream));

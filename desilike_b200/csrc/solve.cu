@@ -257,12 +257,132 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) finish_solve_kernel(const So
   }
 }
 
+// ---- thread-per-point form: when every independent group of solved parameters has <= SOLVE_NREG members, ONE thread assembles and
+//      factorises all the groups of its point.  Consecutive threads read consecutive points of every Gram-partial row (coalesced; the
+//      warp-per-point kernel above reads one row per lane, a 32-way strided access), the per-thread local system lives in shared memory
+//      interleaved over the block's threads (conflict free) while it is accumulated and in registers while it is factorised. ----
+constexpr int ST_THREADS = 128;
+
+__global__ void __launch_bounds__(ST_THREADS) finish_solve_thread_kernel(const SolveParams p) {
+  extern __shared__ double sm[];   // [SOLVE_NREG * SOLVE_NREG + SOLVE_NREG][ST_THREADS]
+  const int tid = threadIdx.x;
+  const long long pt = (long long)blockIdx.x * ST_THREADS + tid;
+  if (pt >= p.N) return;
+  double* M = sm + tid;                                            // element (a, b), b <= a, at M[(a * SOLVE_NREG + b) * ST_THREADS]
+  double* gl = sm + (size_t)SOLVE_NREG * SOLVE_NREG * ST_THREADS + tid;
+  const int ns = p.ns;
+  double chi2 = 0.;
+  for (int t = 0; t < p.nchi; ++t) chi2 += p.partial[p.chi_rows[t] * p.npad + pt];
+  double lp = 0.;
+  bool inside = true;
+  for (int j = 0; j < p.d; ++j)
+    lp += prior_logpdf(p.prior_kind[j], p.params[pt * p.d + j], p.prior_lo[j], p.prior_hi[j], p.prior_loc[j], p.prior_scale[j], &inside);
+  bool spd = true;
+  double logdet = 0., quad = 0.;
+  for (int c = 0; c < p.ncomp; ++c) {
+    const int o = p.comp_off[c], n = p.comp_off[c + 1] - o, nm = p.comp_nmarg[c];
+    const int* idx = p.comp_idx + o;
+    const double* m0 = p.comp_m0 + p.m0_off[c];
+    for (int a = 0; a < n; ++a) {
+      gl[a * ST_THREADS] = 0.;
+      for (int b = 0; b <= a; ++b) M[(a * SOLVE_NREG + b) * ST_THREADS] = m0[a * n + b];
+    }
+    const int t1 = p.gent_off[c + 1];
+    int t = p.gent_off[c];
+    for (; t + 4 <= t1; t += 4) {   // four independent loads in flight
+      GroupEntry e[4];
+      double v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { e[q] = p.gent[t + q]; v[q] = p.partial[e[q].prow * p.npad + pt]; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (e[q].kind == 1) gl[e[q].li * ST_THREADS] -= v[q];
+        else M[(e[q].li * SOLVE_NREG + e[q].lj) * ST_THREADS] += v[q];
+      }
+    }
+    for (; t < t1; ++t) {
+      const GroupEntry e = p.gent[t];
+      const double v = p.partial[e.prow * p.npad + pt];
+      if (e.kind == 1) gl[e.li * ST_THREADS] -= v;
+      else M[(e.li * SOLVE_NREG + e.lj) * ST_THREADS] += v;
+    }
+    double a[SOLVE_NREG][SOLVE_NREG], yy[SOLVE_NREG], gr[SOLVE_NREG], glr[SOLVE_NREG];
+    int id[SOLVE_NREG];
+#pragma unroll
+    for (int i = 0; i < SOLVE_NREG; ++i) {
+      id[i] = i < n ? idx[i] : 0;
+      glr[i] = i < n ? gl[i * ST_THREADS] : 0.;
+      gr[i] = i < n ? p.g0[id[i]] + glr[i] : 0.;
+      yy[i] = gr[i];
+#pragma unroll
+      for (int j = 0; j <= i; ++j) a[i][j] = (i < n) ? M[(i * SOLVE_NREG + j) * ST_THREADS] : (i == j ? 1. : 0.);
+    }
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < SOLVE_NREG; ++j) {
+      const double djj = a[j][j];
+      if (j < n && (!(djj > 0.) || !isfinite(djj))) ok = false;
+      const double l = sqrt(djj), inv = 1. / l;
+      if (j < nm) logdet += 2. * log(l);
+      a[j][j] = l;
+#pragma unroll
+      for (int i = j + 1; i < SOLVE_NREG; ++i) a[i][j] *= inv;
+#pragma unroll
+      for (int i = j + 1; i < SOLVE_NREG; ++i)
+#pragma unroll
+        for (int k = j + 1; k <= i; ++k) a[i][k] -= a[i][j] * a[k][j];
+    }
+    if (!ok) { spd = false; continue; }
+#pragma unroll
+    for (int j = 0; j < SOLVE_NREG; ++j) {   // forward L y = g
+      yy[j] /= a[j][j];
+#pragma unroll
+      for (int i = j + 1; i < SOLVE_NREG; ++i) yy[i] -= a[i][j] * yy[j];
+    }
+#pragma unroll
+    for (int j = SOLVE_NREG - 1; j >= 0; --j) {   // backward L^T dx = y
+      yy[j] /= a[j][j];
+#pragma unroll
+      for (int i = 0; i < j; ++i) yy[i] -= a[j][i] * yy[j];
+    }
+#pragma unroll
+    for (int i = 0; i < SOLVE_NREG; ++i)
+      if (i < n) {
+        const int I = id[i];
+        const double di = yy[i], xi = p.x0[I] + di, prec = p.xprec[I];
+        quad += 0.5 * (-gr[i] * di + prec * di * di) + glr[i] * di;
+        bool in_i = true;
+        lp += prior_logpdf(p.xkind[I], xi, p.xlo[I], p.xhi[I], p.xloc[I], p.xkind[I] == 2 ? rsqrt(prec) : 1., &in_i);
+        if (p.xsolved) p.xsolved[pt * ns + I] = xi;
+      }
+  }
+  if (!spd && p.xsolved)
+    for (int i = 0; i < ns; ++i) p.xsolved[pt * ns + i] = CUDART_NAN;
+  int st = 0;
+  double ll = -0.5 * chi2 + quad - 0.5 * logdet;
+  if (!inside) st |= DLB_PT_OUT_OF_PRIOR;
+  if (!spd) { st |= DLB_PT_NOT_SPD; ll = CUDART_NAN; }
+  if (!isfinite(chi2)) { st |= DLB_PT_NONFINITE; ll = CUDART_NAN; }
+  if (p.loglike) p.loglike[pt] = ll;
+  if (p.logprior) p.logprior[pt] = lp;
+  if (p.logpost) p.logpost[pt] = inside ? ll + lp : -CUDART_INF;
+  if (p.status) p.status[pt] = st;
+}
+
 }  // namespace
 
 int launch_solve(const SolveParams& p, cudaStream_t stream) {
   if (p.ns == 0) {
     const int threads = 256;
     finish_nosolve_kernel<<<(unsigned)((p.N + threads - 1) / threads), threads, 0, stream>>>(p);
+  } else if (p.gent && p.ncomp > 0 && p.comp_max <= SOLVE_NREG && !p.hess) {
+    const size_t smem = (size_t)(SOLVE_NREG * SOLVE_NREG + SOLVE_NREG) * ST_THREADS * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+      DLB_CUDA(cudaFuncSetAttribute(finish_solve_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    finish_solve_thread_kernel<<<(unsigned)((p.N + ST_THREADS - 1) / ST_THREADS), ST_THREADS, smem, stream>>>(p);
   } else {
     const size_t smem = (size_t)SOLVE_WARPS * (p.ns * (p.ns + 1) + 4 * p.ns) * sizeof(double);
     static size_t configured = 0;
