@@ -38,6 +38,21 @@ def build(force=False, verbose=False):
     return LIBPATH
 
 
+def build_profile():
+    """Phase-profiling build of the same sources (-DDLB_PROFILE: per-phase cycle counters in the contraction kernel) ->
+    lib/libdesilike_b200_prof.so, loaded by scripts/phase_profile.py through DESILIKE_B200_LIB."""
+    out = os.path.join(LIBDIR, 'libdesilike_b200_prof.so')
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + ['-DDLB_PROFILE', '-o', out] + sources()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed:\n{}\n{}'.format(' '.join(cmd), res.stderr))
+    return out
+
+
 if __name__ == '__main__':
     import sys
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    if '--profile' in sys.argv:
+        print(build_profile())
+    else:
+        print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -80,6 +80,11 @@ struct BlockDev {     // one output block as seen by the contraction kernel (dev
   long long poff;                      // first Gram-partial row of the block: partial[(poff + e) * npad + point]
   int nchunks, ncb, nslots, nconst, npart, ncols, ocol0, gen;
   int fill, fbase, acols;              // resident A: 0 = evaluate Taylor monomials, 1 = copy acols columns of F from column fbase
+  const unsigned long long* mono2;     // two-pass monomial table of the block's Taylor generator (maxdeg <= 4 and every half product of a
+                                       // degree 3-4 monomial is itself a column), else NULL:  [n1] pass-1 words (columns of degree <= 2:
+                                       // bytes colA, colB, cvalA, cvalB, then the column as 16 bits, top byte != 0: structural zero) followed
+                                       // by [n2] pass-2 words (16-bit column of the left half, of the right half, of the product)
+  int n1, n2;
   const double* tdata;                 // output mode: [ncols] data d of the 'cubic'-transformed columns (0: untransformed column), or NULL
 };
 

@@ -330,6 +330,46 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
         //   Every factor is read as xs[row][col_k] - c_k; absent factors point at the constant-one column with c_k = 0.
         const GenDev* g = gens_s + blk->gen;
         const int maxdeg = g->maxdeg;
+        if (blk->mono2) {
+          // two-pass form: columns of degree <= 2 from their two factors, then every column of degree 3 - 4 as ONE product of two
+          // columns of the same row.  A warp only reads rows it wrote itself (rows wn, wn + 2, ...): __syncwarp orders the passes.
+          const unsigned long long* m2 = blk->mono2;
+          const int n1 = blk->n1, n2 = blk->n2;
+          for (int e0 = 0; e0 < n1; e0 += 32) {
+            const int e = e0 + lane;
+            if (e < n1) {
+              const unsigned long long w = __ldg(m2 + e);
+              const int ca = (int)(w & 0xFFull), cb = (int)((w >> 8) & 0xFFull), col = (int)((w >> 32) & 0xFFFFull);
+              const double va = g->cval[(w >> 16) & 0xFFull], vb = g->cval[(w >> 24) & 0xFFull];
+              const bool zero = (w >> 56) != 0ull;
+              for (int mt = 0; mt < mtc; ++mt) {
+                const double* xb = xs + (size_t)(mt * UNIT + wm * 8 + wn) * p.dpad;
+                double* ab = A_s + (size_t)(mt * UNIT + wm * 8 + wn) * p.ast + col;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const double* xr = xb + (size_t)(2 * i) * p.dpad;
+                  ab[(size_t)(2 * i) * p.ast] = zero ? 0. : (xr[ca] - va) * (xr[cb] - vb);
+                }
+              }
+            }
+          }
+          __syncwarp();
+          for (int e0 = 0; e0 < n2; e0 += 32) {
+            const int e = e0 + lane;
+            if (e < n2) {
+              const unsigned long long w = __ldg(m2 + n1 + e);
+              const int cl = (int)(w & 0xFFFFull), cr = (int)((w >> 16) & 0xFFFFull), col = (int)((w >> 32) & 0xFFFFull);
+              for (int mt = 0; mt < mtc; ++mt) {
+                double* ab = A_s + (size_t)(mt * UNIT + wm * 8 + wn) * p.ast;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  double* ar = ab + (size_t)(2 * i) * p.ast;
+                  ar[col] = ar[cl] * ar[cr];
+                }
+              }
+            }
+          }
+        } else
         for (int j0 = 0; j0 < p.ast; j0 += 32) {
           const int j = j0 + lane;
           if (j < p.ast) {

@@ -56,6 +56,8 @@ struct dlb_plan {
   double* w_T = nullptr;
   dlb::GenDev* d_gens = nullptr;
   std::vector<unsigned long long*> d_paths;   // per generator (resident mode)
+  std::vector<unsigned long long*> d_mono2;   // per generator: two-pass monomial table (NULL: factor-list evaluation)
+  std::vector<int> mono_n1, mono_n2;
   std::vector<dlb::DevGen> gens;
   std::vector<dlb::Block> blocks;
   std::vector<dlb::MlpLayers> mlps;   // one per generator (empty unless kind == MLP)
@@ -278,6 +280,9 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
       bd.chunks = b->d_chunks; bd.tiles = pass == 0 ? b->d_tiles_white : b->d_tiles_plain; bd.epi = pass == 0 ? b->d_epi_white : b->d_epi_plain;
       if (!bd.tiles || !bd.epi) ok = false;
       bd.paths = (resident && b->gen >= 0) ? plan->d_paths[b->gen] : nullptr; bd.poff = b->poff;
+      if (resident && b->gen >= 0 && !plan->d_mono2.empty() && plan->d_mono2[b->gen]) {
+        bd.mono2 = plan->d_mono2[b->gen]; bd.n1 = plan->mono_n1[b->gen]; bd.n2 = plan->mono_n2[b->gen];
+      }
       bd.nchunks = b->nchunks; bd.ncb = b->ncb; bd.nslots = b->nslots; bd.nconst = b->nconst; bd.npart = b->npart; bd.ncols = b->ncols;
       bd.ocol0 = b->coloff; bd.gen = b->gen; bd.fill = b->fill; bd.fbase = b->fbase; bd.acols = std::min((b->maxcol + 1) & ~1, L.ast);
       bd.tdata = pass == 1 ? b->d_tdata : nullptr;
@@ -623,6 +628,7 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
   plan->resident = resident;
   if (resident) {   // factor lists of the monomials, one table per generator, indexed by segment column
     plan->d_paths.resize(desc->ngen, nullptr);
+    plan->d_mono2.resize(desc->ngen, nullptr); plan->mono_n1.resize(desc->ngen, 0); plan->mono_n2.resize(desc->ngen, 0);
     for (int ig = 0; ig < desc->ngen; ++ig) {
       const dlb_generator_desc& gd = desc->gens[ig];
       if (!plan->gens[ig].aux[6]) continue;
@@ -646,6 +652,52 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
         paths[2 * (2 + t)] = a0; paths[2 * (2 + t) + 1] = a1;
       }
       DLB_TRY(upload(plan, paths.data(), paths.size(), &plan->d_paths[ig]));
+      // Two-pass form (Taylor order <= 4, the reference default): the columns of degree <= 2 are evaluated from their (at most two)
+      // factors, every column of degree 3 - 4 is then ONE product of two of those columns of the same row -- 1 FP64 multiply per entry
+      // instead of 3 multiplies + 4 subtractions queued behind the co-resident CTA's DMMAs in the FP64 pipe.
+      if (gendev[ig].maxdeg <= 4 && ast < 65536 && !getenv("DLB_MONO_FACTORS")) {
+        const int T = gd.nfeat - 2, np_ = gd.nparams;
+        auto key_of = [&](const std::vector<int>& pw) { std::string k; for (int v : pw) k.push_back((char)('0' + v)); return k; };
+        std::vector<std::pair<std::string, int>> col_of;   // powers -> column (first occurrence)
+        auto find_col = [&](const std::string& k) { for (auto& kv : col_of) if (kv.first == k) return kv.second; return -1; };
+        for (int t = 0; t < T && 2 + t < ast; ++t) {
+          std::vector<int> pw(gd.idata + (size_t)t * np_, gd.idata + (size_t)(t + 1) * np_);
+          if (find_col(key_of(pw)) < 0) col_of.emplace_back(key_of(pw), 2 + t);
+        }
+        std::vector<unsigned long long> pass1, pass2;
+        const unsigned long long one = (unsigned long long)desc->d, none = (unsigned long long)MAXP;
+        auto word1 = [&](int col, unsigned long long ca, unsigned long long cb, unsigned long long ia, unsigned long long ib, bool zero) {
+          return ca | (cb << 8) | (ia << 16) | (ib << 24) | ((unsigned long long)col << 32) | (zero ? 0xFF00000000000000ull : 0ull);
+        };
+        bool ok = true;
+        pass1.push_back(word1(0, one, one, none, none, false));
+        for (int c = 1; c < ast; ++c) {
+          const int t = c - 2;
+          if (t < 0 || t >= T) { pass1.push_back(word1(c, one, one, none, none, true)); continue; }
+          std::vector<std::pair<unsigned long long, unsigned long long>> fac;   // (parameter-tile column, cval index) per factor
+          std::vector<int> jf;
+          for (int j = 0; j < np_; ++j)
+            for (int e = 0; e < gd.idata[(size_t)t * np_ + j]; ++e) {
+              fac.emplace_back(plan->gens[ig].pidx[j] >= 0 ? (unsigned long long)plan->gens[ig].pidx[j] : one, (unsigned long long)j);
+              jf.push_back(j);
+            }
+          if (fac.size() <= 2) {
+            while (fac.size() < 2) fac.emplace_back(one, none);
+            pass1.push_back(word1(c, fac[0].first, fac[1].first, fac[0].second, fac[1].second, false));
+          } else {
+            std::vector<int> pl(np_, 0), pr(np_, 0);
+            for (size_t f = 0; f < jf.size(); ++f) (f < 2 ? pl : pr)[jf[f]] += 1;
+            const int cl = find_col(key_of(pl)), cr = find_col(key_of(pr));
+            if (cl < 0 || cr < 0) { ok = false; break; }
+            pass2.push_back((unsigned long long)cl | ((unsigned long long)cr << 16) | ((unsigned long long)c << 32));
+          }
+        }
+        if (ok) {
+          plan->mono_n1[ig] = (int)pass1.size(); plan->mono_n2[ig] = (int)pass2.size();
+          pass1.insert(pass1.end(), pass2.begin(), pass2.end());
+          DLB_TRY(upload(plan, pass1.data(), pass1.size(), &plan->d_mono2[ig]));
+        }
+      }
     }
   }
   DLB_TRY(upload(plan, gendev.data(), gendev.size(), &plan->d_gens));
