@@ -421,6 +421,10 @@ def main():
                     'ms_per_step_in_kernel': contract_ms, 'flops_per_eval_folded': flops,
                     'peak_source': 'dlb_measure_fp64_peak(DMMA.8x8x4 register loop) measured in this run; MEASURED_PEAKS.json has no FP64 entry',
                     'share_of_step': contract_ms / step_ms, 'phase_ms': phase}
+    if args.workload not in ('c1', 'c3', 'c3fft'):   # what the kernel multiplies (padding inside tiles included) next to the algorithmic count above
+        roofline['flops_per_eval_executed'] = plan.executed_flops()
+        roofline['achieved_executed'] = plan.executed_flops() * N / (phase['contract'] * 1e-3) / 1e12
+        roofline['frac_executed'] = roofline['achieved_executed'] / peak_dmma
     if uncollapsed:   # the reference's un-collapsed chain: what the same evaluations cost without plan-time folding
         roofline['flops_per_eval_uncollapsed'] = uncollapsed
         roofline['achieved_uncollapsed_equivalent'] = uncollapsed * value / 1e12

@@ -29,14 +29,14 @@ class CoefDesc(ctypes.Structure):
 
 class TermDesc(ctypes.Structure):
     _fields_ = [('slot', ctypes.c_int32), ('coef', ctypes.c_int32), ('gen', ctypes.c_int32), ('foff', ctypes.c_int32), ('K', ctypes.c_int32),
-                ('moff', ctypes.c_int64)]
+                ('moff', ctypes.c_int64), ('moff_plain', ctypes.c_int64)]
 
 
 class BlockDesc(ctypes.Structure):
     _fields_ = [('ncols', ctypes.c_int32), ('nslots', ctypes.c_int32), ('nterms', ctypes.c_int32), ('terms', ctypes.POINTER(TermDesc)),
                 ('matrices_white', c_double_p), ('matrices_plain', c_double_p), ('r0_white', c_double_p), ('t0_plain', c_double_p),
                 ('slot_solved', c_int32_p), ('nconst', ctypes.c_int32), ('const_solved', c_int32_p), ('gconst_white', c_double_p),
-                ('transform_data', c_double_p), ('whitening_t', c_double_p), ('r0_data_white', c_double_p)]
+                ('transform_data', c_double_p), ('whitening_t', c_double_p), ('r0_data_white', c_double_p), ('ncols_white', ctypes.c_int32)]
 
 
 class PlanDesc(ctypes.Structure):
@@ -58,6 +58,7 @@ SYMBOLS = {
     'dlb_plan_destroy': (None, [ctypes.c_void_p]),
     'dlb_plan_ntheory': (ctypes.c_int, [ctypes.c_void_p]),
     'dlb_plan_nsolved': (ctypes.c_int, [ctypes.c_void_p]),
+    'dlb_plan_executed_flops': (ctypes.c_double, [ctypes.c_void_p]),
     'dlb_eval_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 5 + [ctypes.c_void_p]),
     'dlb_eval_batch_hessian': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 6 + [ctypes.c_void_p]),
     'dlb_theory_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),

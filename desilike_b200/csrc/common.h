@@ -85,6 +85,8 @@ struct BlockDev {     // one output block as seen by the contraction kernel (dev
                                        // bytes colA, colB, cvalA, cvalB, then the column as 16 bits, top byte != 0: structural zero) followed
                                        // by [n2] pass-2 words (16-bit column of the left half, of the right half, of the product)
   int n1, n2;
+  const int* cb_first;                 // [ncb] first k-chunk with a non-zero tile in each column block (leading all-zero tiles of a
+                                       // rank-reduced, lower-triangular problem are neither loaded nor multiplied), or NULL
   const double* tdata;                 // output mode: [ncols] data d of the 'cubic'-transformed columns (0: untransformed column), or NULL
 };
 

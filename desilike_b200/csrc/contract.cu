@@ -406,8 +406,10 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
       pair_barrier(wm);
       PROF(5)
 
-      int4 ch_next = __ldg(reinterpret_cast<const int4*>(chunks));   // slot, coef, fcol, kc (prefetched one chunk ahead)
+      const int* cb_first = blk->cb_first;
       for (int cb = 0; cb < ncb; ++cb) {
+        const int cfirst = cb_first ? __ldg(cb_first + cb) : 0;
+        int4 ch_next = __ldg(reinterpret_cast<const int4*>(chunks + (cfirst < nchunks ? cfirst : 0)));   // slot, coef, fcol, kc (prefetched one chunk ahead)
         double acc[R][MT][NT][2];
 #pragma unroll
         for (int sl = 0; sl < R; ++sl)
@@ -416,15 +418,15 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) acc[sl][mt][nt][0] = acc[sl][mt][nt][1] = 0.;
 
-        for (int c = 0; c < nchunks; ++c) {
+        for (int c = cfirst; c < nchunks; ++c) {
           const int4 ch = ch_next;
-          ch_next = __ldg(reinterpret_cast<const int4*>(chunks + (c + 1 < nchunks ? c + 1 : 0)));
+          ch_next = __ldg(reinterpret_cast<const int4*>(chunks + (c + 1 < nchunks ? c + 1 : c)));
           double beta[MT];
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) beta[mt] = ch.y >= 0 ? cs[ch.y * BM + mt * UNIT + wm * 8 + lr] : 1.;
           PROF(3)
           mbar_wait(&full[s], ph);
-          PROF((c == 0 ? (cb == 0 ? 1 : 7) : 4))
+          PROF((c == cfirst ? (cb == 0 ? 1 : 7) : 4))
           const double* Bp = stage_base + (size_t)s * STAGE_DOUBLES + (wn * (NT * 8) + lr) * KC + lc;
           const double* Ap;
           int astride;

@@ -18,6 +18,9 @@ void set_error(const std::string& msg) { g_error = msg; }
 struct Block {
   Variant var;
   int ncols = 0, nslots = 1, nconst = 0, ncb = 0, nchunks = 0, npart = 0, coloff = 0, gen = -1, maxcol = 0;
+  std::vector<Chunk> h_chunks;
+  int* d_cb_first = nullptr; std::vector<int> cb_first;   // whitened tiles: first non-zero k-chunk per column block
+  int ncols_w = 0, ncb_plain = 0;   // columns of the whitened matrices (rank-reduced plans: < ncols) / column blocks of the un-whitened tiles
   int fill = 0, fbase = 0;   // resident A: 0 = Taylor monomials evaluated in the kernel, 1 = copied from the feature matrix at column fbase
   long long poff = 0;
   Chunk* d_chunks = nullptr;
@@ -35,7 +38,8 @@ struct Launch {
   BlockDev *d_white = nullptr, *d_plain = nullptr;
   BlockDev* d_plain_t = nullptr;   // two-stage plans: the un-whitened table writing into the transformed-theory buffer (ocol0 = Block::tcol)
   SchedEntry *d_sched_white = nullptr, *d_sched_plain = nullptr;   // per-tile TMA schedule
-  int nsched = 0;
+  int nsched = 0, nsched_plain = 0;
+  double flops_exec = 0., flops_exec_plain = 0.;   // 2 * kc * BN * slots-independent tile count per point (whitened / un-whitened tables)
 };
 
 struct MlpLayers { int act = 0; std::vector<Block> layers; std::vector<Launch> launches; };
@@ -151,16 +155,17 @@ struct TermSpec { int slot, coef, fcol, frel, K; const double* white; const doub
 
 // Chunk the terms, pre-tile their matrices into the contraction kernel's shared-memory image and upload everything.
 static int build_block_core(dlb_plan* plan, const Variant& var, bool resident, int ncols, int nslots, const std::vector<TermSpec>& terms,
-                            const double* r0_white, const double* t0_plain, int nconst, const double* gconst_white, Block& blk) {
-  blk.ncols = ncols; blk.nslots = nslots; blk.nconst = nconst;
+                            const double* r0_white, const double* t0_plain, int nconst, const double* gconst_white, Block& blk, int ncols_white = 0) {
+  if (ncols_white <= 0) ncols_white = ncols;
+  blk.ncols = ncols; blk.ncols_w = ncols_white; blk.nslots = nslots; blk.nconst = nconst;
   blk.var = var;
   const int BN = variant_bn(blk.var), KC = var.KC;
   // Auxiliary columns: the dot products of every slot with the constant whitened Jacobian rows g_i are linear in the features,
   //   slot_a . g_i = sum_t coef_t f_t . (M_t g_i),
   // so they are obtained for free from the contraction itself by appending the nconst columns M_t g_i to the term matrices
   // (usually inside the zero padding of the last column block) instead of nconst extra dot products per column block.
-  const int ncols_ext = ncols + nconst;
-  blk.ncb = (ncols_ext + BN - 1) / BN;
+  blk.ncb = (ncols_white + nconst + BN - 1) / BN;
+  blk.ncb_plain = (ncols + nconst + BN - 1) / BN;
   std::vector<Chunk> chunks;
   struct Src { int term; int k0; };
   std::vector<Src> srcs;
@@ -182,15 +187,16 @@ static int build_block_core(dlb_plan* plan, const Variant& var, bool resident, i
   blk.nchunks = (int)chunks.size();
   blk.npart = nslots * (nslots + 1) / 2 + nslots * nconst;
   DLB_TRY(upload(plan, chunks.data(), chunks.size(), &blk.d_chunks));
+  blk.h_chunks = chunks;
   // pre-tile: [ncb][nchunks][BN][KC], n-major rows, zero padded
   const size_t tile = (size_t)BN * KC;
-  std::vector<double> tiles((size_t)blk.ncb * blk.nchunks * tile);
   for (int pass = 0; pass < 2; ++pass) {
     bool any = false;
     for (const TermSpec& td : terms) any = any || (pass == 0 ? td.white : td.plain) != nullptr;
     if (!any) continue;
-    std::fill(tiles.begin(), tiles.end(), 0.);
-    for (int cb = 0; cb < blk.ncb; ++cb)
+    const int ncols = pass == 0 ? blk.ncols_w : blk.ncols, ncols_ext = ncols + nconst, ncb = pass == 0 ? blk.ncb : blk.ncb_plain;   // this pass's matrix width
+    std::vector<double> tiles((size_t)ncb * blk.nchunks * tile, 0.);
+    for (int cb = 0; cb < ncb; ++cb)
       for (int c = 0; c < blk.nchunks; ++c) {
         double* dst = tiles.data() + ((size_t)cb * blk.nchunks + c) * tile;
         const TermSpec& td = terms[srcs[c].term];
@@ -213,12 +219,30 @@ static int build_block_core(dlb_plan* plan, const Variant& var, bool resident, i
         }
       }
     DLB_TRY(upload(plan, tiles.data(), tiles.size(), pass == 0 ? &blk.d_tiles_white : &blk.d_tiles_plain));
+    if (pass == 0 && !getenv("DLB_NO_TILE_SKIP")) {   // leading all-zero tiles per column block (rank-reduced problems are lower triangular)
+      blk.cb_first.assign(ncb, 0);
+      bool any_skip = false;
+      for (int cb = 0; cb < ncb; ++cb) {
+        int c = 0;
+        for (; c < blk.nchunks; ++c) {
+          const double* t = tiles.data() + ((size_t)cb * blk.nchunks + c) * tile;
+          bool zero = true;
+          for (size_t i = 0; i < tile && zero; ++i) zero = t[i] == 0.;
+          if (!zero) break;
+        }
+        blk.cb_first[cb] = c;
+        any_skip = any_skip || c > 0;
+      }
+      if (any_skip) DLB_TRY(upload(plan, blk.cb_first.data(), blk.cb_first.size(), &blk.d_cb_first));
+      else blk.cb_first.clear();
+    }
   }
   // epilogue constants per column block: [ncb][BN] = r0 / t0, zero padded; auxiliary columns carry r0 . g_i
   for (int pass = 0; pass < 2; ++pass) {
     const double* vec = pass == 0 ? r0_white : t0_plain;
     if (!vec) continue;
-    std::vector<double> epi((size_t)blk.ncb * BN, 0.);
+    const int ncols = pass == 0 ? blk.ncols_w : blk.ncols, ncb = pass == 0 ? blk.ncb : blk.ncb_plain;
+    std::vector<double> epi((size_t)ncb * BN, 0.);
     for (int col = 0; col < ncols; ++col) epi[col] = vec[col];
     if (pass == 0)
       for (int i = 0; i < nconst; ++i) {
@@ -237,9 +261,9 @@ static int build_block(dlb_plan* plan, const dlb_plan_desc* desc, const dlb_bloc
   for (int t = 0; t < bd.nterms; ++t) {
     const dlb_term_desc& td = bd.terms[t];
     terms.push_back(TermSpec{td.slot, td.coef, plan->gens[td.gen].foff + td.foff, td.foff, td.K, bd.matrices_white + td.moff,
-                             bd.matrices_plain ? bd.matrices_plain + td.moff : nullptr});
+                             bd.matrices_plain ? bd.matrices_plain + td.moff_plain : nullptr});
   }
-  DLB_TRY(build_block_core(plan, var, plan->resident, bd.ncols, bd.nslots, terms, bd.r0_white, bd.t0_plain, bd.nconst, bd.gconst_white, blk));
+  DLB_TRY(build_block_core(plan, var, plan->resident, bd.ncols, bd.nslots, terms, bd.r0_white, bd.t0_plain, bd.nconst, bd.gconst_white, blk, bd.ncols_white));
   // entry map of the Gram partials (order fixed by contract_kernel's epilogue)
   std::vector<EntryMap> map(blk.npart);
   const int R = bd.nslots;
@@ -283,9 +307,11 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
       if (resident && b->gen >= 0 && !plan->d_mono2.empty() && plan->d_mono2[b->gen]) {
         bd.mono2 = plan->d_mono2[b->gen]; bd.n1 = plan->mono_n1[b->gen]; bd.n2 = plan->mono_n2[b->gen];
       }
-      bd.nchunks = b->nchunks; bd.ncb = b->ncb; bd.nslots = b->nslots; bd.nconst = b->nconst; bd.npart = b->npart; bd.ncols = b->ncols;
+      bd.nchunks = b->nchunks; bd.ncb = pass == 0 ? b->ncb : b->ncb_plain; bd.nslots = b->nslots; bd.nconst = b->nconst; bd.npart = b->npart;
+      bd.ncols = pass == 0 ? b->ncols_w : b->ncols;
       bd.ocol0 = b->coloff; bd.gen = b->gen; bd.fill = b->fill; bd.fbase = b->fbase; bd.acols = std::min((b->maxcol + 1) & ~1, L.ast);
       bd.tdata = pass == 1 ? b->d_tdata : nullptr;
+      bd.cb_first = pass == 0 ? b->d_cb_first : nullptr;
       tab.push_back(bd);
     }
     if (!ok) continue;
@@ -301,13 +327,15 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
     for (size_t ib = 0; ib < blocks.size(); ++ib) {
       const Block* b = blocks[ib];
       DLB_REQUIRE(b->nchunks < 65536 && blocks.size() < 32768, "too many chunks / blocks in one launch");
-      for (int cb = 0; cb < b->ncb; ++cb) {
-        for (int c = 0; c < b->nchunks; ++c)
+      for (int cb = 0; cb < tab[ib].ncb; ++cb) {
+        for (int c = (pass == 0 && !b->cb_first.empty()) ? b->cb_first[cb] : 0; c < b->nchunks; ++c) {
+          (pass == 0 ? L.flops_exec : L.flops_exec_plain) += 2. * b->h_chunks[c].kc * BN;
           sched.push_back(SchedEntry{tab[ib].tiles + ((size_t)cb * b->nchunks + c) * ((size_t)BN * KC), (unsigned)(BN * KC * 8), (int)((ib << 16) | (unsigned)c)});
+        }
         sched.push_back(SchedEntry{tab[ib].epi + (size_t)cb * BN, (unsigned)(BN * 8), -1});
       }
     }
-    L.nsched = (int)sched.size();
+    (pass == 0 ? L.nsched : L.nsched_plain) = (int)sched.size();
     DLB_TRY(upload(plan, sched.data(), sched.size(), pass == 0 ? &L.d_sched_white : &L.d_sched_plain));
   }
   return DLB_OK;
@@ -405,7 +433,7 @@ static int run_front(dlb_plan* plan, const double* d_params, long long N, long l
     const Launch& L = la.first;
     ContractParams cp;
     fill_params(plan, L, cp, d_params, N, npad);
-    cp.blocks = L.d_plain; cp.sched = L.d_sched_plain; cp.nsched = L.nsched; cp.ncoef = 0;
+    cp.blocks = L.d_plain; cp.sched = L.d_sched_plain; cp.nsched = L.nsched_plain; cp.ncoef = 0;
     cp.out = plan->w_F; cp.ostride = plan->fstride; cp.out_rows = npad; cp.act = la.second; cp.mode = 1;
     cp.U = npad / variant_unit(L.var);
     DLB_TRY(launch_contract(L.var, cp, plan->nsm, stream));
@@ -420,7 +448,7 @@ static int run_two_stage(dlb_plan* plan, const double* d_params, long long N, lo
     const Launch& L = plan->launch;
     ContractParams cp;
     fill_params(plan, L, cp, d_params, N, npad);
-    cp.blocks = L.d_plain_t; cp.sched = L.d_sched_plain; cp.nsched = L.nsched;
+    cp.blocks = L.d_plain_t; cp.sched = L.d_sched_plain; cp.nsched = L.nsched_plain;
     cp.out = plan->w_T; cp.ostride = plan->tstride; cp.out_rows = npad; cp.act = 0; cp.mode = 1;
     cp.U = (N + variant_unit(L.var) - 1) / variant_unit(L.var);
     DLB_TRY(launch_contract(L.var, cp, plan->nsm, stream));
@@ -440,7 +468,7 @@ static int run_contract(dlb_plan* plan, const double* d_params, long long N, lon
   ContractParams cp;
   fill_params(plan, L, cp, d_params, N, npad);
   cp.blocks = mode == 0 ? L.d_white : L.d_plain;
-  cp.sched = mode == 0 ? L.d_sched_white : L.d_sched_plain; cp.nsched = L.nsched;
+  cp.sched = mode == 0 ? L.d_sched_white : L.d_sched_plain; cp.nsched = mode == 0 ? L.nsched : L.nsched_plain;
   if (!cp.blocks) { set_error("plan was built without un-whitened matrices: theory_batch unavailable"); return DLB_ERR_ARG; }
   cp.out = d_theory; cp.ostride = plan->ntheory; cp.out_rows = N; cp.act = 0; cp.mode = mode;
   cp.U = (N + variant_unit(L.var) - 1) / variant_unit(L.var);
@@ -480,6 +508,10 @@ int dlb_device_count(void) {
 
 int dlb_plan_ntheory(const dlb_plan* plan) { return plan ? plan->ntheory : -1; }
 int dlb_plan_nsolved(const dlb_plan* plan) { return plan ? plan->ns : -1; }
+double dlb_plan_executed_flops(const dlb_plan* plan) {
+  if (!plan) return -1.;
+  return plan->two_stage ? plan->launch.flops_exec_plain + plan->wlaunch.flops_exec : plan->launch.flops_exec;
+}
 
 void dlb_plan_destroy(dlb_plan* plan) {
   if (!plan) return;
@@ -600,6 +632,8 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
   for (int ib = 0; ib < desc->nblocks; ++ib) {
     const dlb_block_desc& bd = desc->blocks[ib];
     DLB_REQUIRE(bd.ncols > 0 && bd.nslots >= 1 && bd.nslots <= 8, "block: ncols > 0 and 1 <= nslots <= 8 required");
+    DLB_REQUIRE(bd.ncols_white == 0 || bd.ncols_white == bd.ncols || (bd.ncols_white > 0 && bd.nslots == 1 && bd.nconst == 0),
+                "block: a rank-reduced whitened problem (ncols_white != ncols) requires nslots == 1 and nconst == 0");
     DLB_REQUIRE(bd.nterms > 0 && bd.terms && bd.matrices_white && bd.r0_white, "block: terms / matrices_white / r0_white required");
     max_slots = std::max(max_slots, bd.nslots);
     for (int t = 0; t < bd.nterms; ++t) {

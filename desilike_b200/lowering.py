@@ -103,7 +103,7 @@ class _Generator(object):
 class Lowered(object):
     """Flat arrays + ctypes descriptor (keeps every buffer alive until the plan has been created)."""
 
-    def __init__(self, spec, with_plain=True):
+    def __init__(self, spec, with_plain=True, reduce_rank=True):
         self.spec = spec
         names = self.names = list(spec['params'])
         self.d = len(names)
@@ -220,6 +220,23 @@ class Lowered(object):
             blk['plain'] = [terms[k] for k in keys]
             blk['white'] = [terms[k] @ L.T for k in keys]
             blk['r0_white'] = L @ (data - const_plain)
+            blk['ncols_white'] = ncols
+            Ktot = sum(k[4] for k in keys)
+            if reduce_rank and nslots == 1 and not const_rows and ncols > Ktot + 1:
+                # Rank reduction of the whitened residual.  r = g . M - r0 with g = (c_t f_t)_t in R^Ktot lives in the row space of the
+                # stacked term matrices M [Ktot, n]; with the thin QR factorisation M^T = Q R (Q [n, Ktot] orthonormal)
+                #     |g M - r0|^2 = |g R^T - Q^T r0|^2 + |r0 - Q Q^T r0|^2,
+                # i.e. the same chi2 from Ktot + 1 columns instead of n (the last column carries the constant |r0_perp|), and R^T is
+                # lower triangular.  Exact linear algebra, done once here in FP64 -- like the whitening and window folding above.
+                M = np.concatenate(blk['white'], axis=0)
+                Q, R = np.linalg.qr(M.T)
+                proj = Q.T @ blk['r0_white']
+                perp = blk['r0_white'] - Q @ proj
+                Rt = np.concatenate([R.T, np.zeros((Ktot, 1))], axis=1)
+                off, white = 0, []
+                for k in keys:
+                    white.append(np.ascontiguousarray(Rt[off:off + k[4]])); off += k[4]
+                blk['white'], blk['r0_white'], blk['ncols_white'] = white, np.append(proj, np.sqrt(perp.dot(perp))), Ktot + 1
             blk['t0_plain'] = const_plain
             blk['transform_data'], blk['whitening_t'], blk['r0_data_white'] = tdata, np.ascontiguousarray(L.T), L @ data
             inv = sorted(slot_of.items(), key=lambda kv: kv[1])
@@ -252,11 +269,12 @@ class Lowered(object):
         for b, blk in zip(blocks, self.blocks):
             nt = len(blk['terms'])
             terms = (_capi.TermDesc * nt)()
-            moff = 0
-            for t, key, mat in zip(terms, blk['terms'], blk['white']):
+            moff = moff_plain = 0
+            for t, key, mat, mat_plain in zip(terms, blk['terms'], blk['white'], blk['plain']):
                 t.slot, t.coef, t.gen, t.foff, t.K = key
-                t.moff = moff
+                t.moff, t.moff_plain = moff, moff_plain
                 moff += mat.size
+                moff_plain += mat_plain.size
             white = f64(np.concatenate([m.ravel() for m in blk['white']]))
             plain = f64(np.concatenate([m.ravel() for m in blk['plain']])) if (self.with_plain or self.two_stage) else None
             r0, t0 = f64(blk['r0_white']), f64(blk['t0_plain'])
@@ -267,6 +285,7 @@ class Lowered(object):
                 keep += [td, wt, rd]
                 b.transform_data, b.whitening_t, b.r0_data_white = as_ptr(td), as_ptr(wt), as_ptr(rd)
             b.ncols, b.nslots, b.nterms, b.terms = blk['ncols'], blk['nslots'], nt, terms
+            b.ncols_white = blk['ncols_white']
             b.matrices_white, b.matrices_plain = as_ptr(white), as_ptr(plain)
             b.r0_white, b.t0_plain = as_ptr(r0), as_ptr(t0)
             b.slot_solved, b.nconst, b.const_solved, b.gconst_white = as_ptr(ss, ctypes.c_int32), len(cs), as_ptr(cs, ctypes.c_int32), as_ptr(gc)
@@ -284,11 +303,12 @@ class Lowered(object):
         gram = 0
         for blk in self.blocks:
             R, nc = blk['nslots'], len(blk['const_solved'])
-            for (slot, coef, gen, foff, K) in blk['terms']:
+            for (slot, coef, gen, foff, K), mat in zip(blk['terms'], blk['white']):
                 # + nc auxiliary columns per term: the dot products with the constant whitened Jacobian rows come out of the
-                # contraction itself (csrc/plan.cu: build_block_core)
-                contract += 2 * K * (blk['ncols'] + nc)
-            gram += 2 * blk['ncols'] * (R * (R + 1) // 2)
+                # contraction itself (csrc/plan.cu: build_block_core).  Rank-reduced blocks are lower triangular: only the non-zero
+                # entries count (the kernel skips the leading all-zero tiles of every column block and executes slightly more)
+                contract += 2 * (K * (blk['ncols_white'] + nc) if blk['ncols_white'] == blk['ncols'] else int(np.count_nonzero(mat)))
+            gram += 2 * blk['ncols_white'] * (R * (R + 1) // 2)
             if self.two_stage: contract += 2 * blk['ncols']**2   # second stage: whitening of the transformed theory vector
         solve = self.ns**3 // 3 + 2 * self.ns**2
         return dict(contract=contract, gram=gram, solve=solve, total=contract + gram + solve)

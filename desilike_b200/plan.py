@@ -21,7 +21,7 @@ class Plan(object):
     current torch stream, torch outputs, no host round trip.
     """
 
-    def __init__(self, spec, device=None, with_theory=True):
+    def __init__(self, spec, device=None, with_theory=True, reduce_rank=True):
         self._lib = _capi.load()
         if self._lib.dlb_device_count() <= 0:
             raise _capi.DesilikeB200Error('no CUDA device visible: desilike_b200 has no CPU fallback')
@@ -30,7 +30,9 @@ class Plan(object):
             torch.cuda.set_device(device)
         spec = premarginalize_precision(spec)   # '.prec' parameters (plan-time, reference likelihoods/base.py:257-312)
         self.spec = spec
-        self.lowered = Lowered(spec, with_plain=with_theory)
+        # reduce_rank: blocks without solved parameters whose data vector is longer than their feature count are evaluated in the
+        # row space of their term matrices (lowering.py: QR at plan time) -- same chi2, fewer columns
+        self.lowered = Lowered(spec, with_plain=with_theory, reduce_rank=reduce_rank)
         self.params = list(self.lowered.names)
         self.d, self.ns, self.ntheory = self.lowered.d, self.lowered.ns, self.lowered.ntheory
         self.solved_names = [s['name'] for s in spec.get('solved', [])]
@@ -124,6 +126,10 @@ class Plan(object):
         return out
 
     # ---- instrumentation ---------------------------------------------------------------------------------------------
+    def executed_flops(self):
+        """FP64 tensor-pipe FLOPs per evaluation executed by the contraction launch(es) (tile padding included, skipped tiles excluded)."""
+        return float(self._lib.dlb_plan_executed_flops(self._handle))
+
     def set_timing(self, enabled=True):
         _capi.check(self._lib.dlb_set_timing(self._handle, int(enabled)))
 

@@ -85,7 +85,8 @@ typedef struct {
   int32_t gen;        /* generator whose feature segment is contracted */
   int32_t foff;       /* offset inside that segment */
   int32_t K;          /* contraction length */
-  int64_t moff;       /* offset (doubles) of M[K, ncols] (row-major) in `matrices` */
+  int64_t moff;       /* offset (doubles) of M[K, ncols_white] (row-major) in `matrices_white` */
+  int64_t moff_plain; /* offset (doubles) of M[K, ncols] (row-major) in `matrices_plain` */
 } dlb_term_desc;
 
 /* ---- output blocks: independent groups of data-vector columns (one per tracer when the precision is block-diagonal) */
@@ -110,6 +111,10 @@ typedef struct {
   const double* transform_data;  /* [ncols] flat data d of the transformed columns, 0 on untransformed columns (NULL: one-stage plan) */
   const double* whitening_t;     /* [ncols, ncols] row-major L^T:  r_c = sum_j u_j whitening_t[j, c] */
   const double* r0_data_white;   /* [ncols] L . data */
+  /* Columns of the WHITENED matrices / r0_white (0: ncols).  The host may hand over a rank-reduced whitened problem: chi2 only needs
+   * |r|^2, and r = g . M - r0 lives in the row space of the stacked term matrices, so a QR factorisation at plan time replaces the n
+   * data-space columns by sum_t K_t + 1 columns (desilike_b200/lowering.py); requires nslots == 1 and nconst == 0. */
+  int32_t ncols_white;
 } dlb_block_desc;
 
 typedef struct {
@@ -140,6 +145,10 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out);
 void dlb_plan_destroy(dlb_plan* plan);
 int dlb_plan_ntheory(const dlb_plan* plan);      /* total data-vector length n */
 int dlb_plan_nsolved(const dlb_plan* plan);
+/* FP64 tensor-pipe FLOPs per evaluation EXECUTED by the contraction launch(es) of dlb_eval_batch: 2 * k-chunk length * tile width over
+ * the (column block, k-chunk) tiles actually multiplied (zero padding inside tiles included, skipped leading zero tiles excluded).
+ * Diagnostic for bench.py: the gap to the algorithmic count is padding. */
+double dlb_plan_executed_flops(const dlb_plan* plan);
 
 /* Batched evaluation (replaces the per-point loop of reference base.py:239-273 + likelihoods/base.py:242-245,314-413).
  * params [N, d].  Outputs (each may be NULL): logposterior/loglikelihood/logprior [N], x_solved [N, ns] (in the plan's solved

@@ -46,11 +46,11 @@ def evaluate(low, X, feature_fn=None, white=True):
     chi2 = np.zeros(N)
     theory = []
     for blk in low.blocks:
-        slots = np.zeros((blk['nslots'], N, blk['ncols']))
+        slots = np.zeros((blk['nslots'], N, blk['ncols'] if (not white or low.two_stage) else blk['ncols_white']))
         for key, mw, mp in zip(blk['terms'], blk['white'], blk['plain']):
             slot, coef, gen, foff, K = key
             c = C[:, coef] if coef >= 0 else 1.
-            slots[slot] += (np.atleast_1d(c)[:, None] if coef >= 0 else 1.) * (F[gen][:, foff:foff + K] @ (mw if white else mp))
+            slots[slot] += (np.atleast_1d(c)[:, None] if coef >= 0 else 1.) * (F[gen][:, foff:foff + K] @ (mw if (white and not low.two_stage) else mp))
         if not white or low.two_stage:
             # two-stage plans (observable transform, csrc/plan.cu:run_two_stage): theory through the un-whitened matrices, transform in
             # the epilogue, then the whitening contraction

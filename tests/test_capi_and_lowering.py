@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     import ctypes
     from desilike_b200 import _capi
     assert ctypes.sizeof(_capi.CoefDesc) == 8 + 4 + 4 * 4 + 4 * 4 + 4
-    assert ctypes.sizeof(_capi.TermDesc) == 32
+    assert ctypes.sizeof(_capi.TermDesc) == 40
     assert _capi.PlanDesc.abi_version.offset == 0 and _capi.PlanDesc.prior_kind.offset == 8
 
 
@@ -151,6 +151,25 @@ def test_theory_payloads_reproduce_oracle(name):
     theory = lowered_numpy.evaluate(low, X, feature_fn=fn, white=False)
     assert np.max(np.abs(theory - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-11
     assert np.allclose(got['logposterior'], ref['logposterior'], rtol=1e-9, atol=1e-7)
+
+
+def test_rank_reduced_whitened_problem():
+    """Blocks with more data-vector columns than features are lowered onto the row space of their term matrices (QR at plan time):
+    same log-likelihood, fewer columns and FLOPs; blocks with solved parameters are left alone."""
+    from desilike_b200.lowering import Lowered
+    spec = configs.config_c5(ntracers=2, nkin=40, nbins=40, order=2, solved=False)
+    low, full = Lowered(spec), Lowered(spec, reduce_rank=False)
+    assert all(b['ncols_white'] == sum(k[4] for k in b['terms']) + 1 < b['ncols'] for b in low.blocks)
+    assert all(b['ncols_white'] == b['ncols'] for b in full.blocks)
+    assert low.flops_per_point()['contract'] < 0.5 * full.flops_per_point()['contract']
+    X = configs.sample_points(spec, 16, seed=5)
+    ref = pipeline.evaluate(spec, X)
+    for lw in (low, full):
+        got = lowered_numpy.evaluate(lw, X)
+        assert np.allclose(got['loglikelihood'], ref['loglikelihood'], rtol=1e-12, atol=1e-9)
+    assert np.allclose(lowered_numpy.evaluate(low, X, white=False), lowered_numpy.evaluate(full, X, white=False), rtol=0, atol=0)   # theory vectors untouched
+    solved = Lowered(configs.config_c5(ntracers=2, nkin=40, nbins=40, order=2, solved=True))
+    assert all(b['ncols_white'] == b['ncols'] for b in solved.blocks)
 
 
 def test_spline_constants_match_scipy():

@@ -209,3 +209,33 @@ def test_cubic_observable_transform_two_stage(gpu_required):
         assert np.max(np.abs(got['loglikelihood'] - ref['loglikelihood']) / np.maximum(1., np.abs(ref['loglikelihood']))) < 1e-9
         assert np.array_equal(np.isneginf(got['logposterior']), np.isneginf(ref['logposterior']))
         plan.close()
+
+
+def test_rank_reduced_plan_matches_full_plan(gpu_required):
+    """Rank-reduced whitened problem (lowering.py: QR at plan time, n -> sum K_t + 1 columns) vs the full-width plan and the oracle at the
+    C5 tracer size (n = 402 per tracer, block-diagonal) and for one dense joint precision."""
+    import desilike_b200
+    spec = configs.config_c5(ntracers=2, coefficients='random')
+    X = configs.sample_points(spec, 1000, seed=31)
+    ref = pipeline.evaluate(spec, X)
+    red, full = desilike_b200.Plan(spec), desilike_b200.Plan(spec, reduce_rank=False)
+    assert red.lowered.blocks[0]['ncols_white'] < full.lowered.blocks[0]['ncols_white'] == 402
+    a, b = red.eval(X), full.eval(X)
+    scale = np.maximum(1., np.abs(ref['loglikelihood']))
+    assert np.max(np.abs(a['loglikelihood'] - ref['loglikelihood']) / scale) < 1e-10
+    assert np.max(np.abs(a['loglikelihood'] - b['loglikelihood']) / scale) < 1e-10
+    assert np.array_equal(a['status'], b['status'])
+    assert np.max(np.abs(red.theory(X[:64]) - full.theory(X[:64]))) == 0.
+    red.close(); full.close()
+    P = spec['precision']
+    n = sum(p.shape[0] for p in P)
+    dense = np.zeros((n, n)); o = 0
+    for p in P: dense[o:o + p.shape[0], o:o + p.shape[0]] = p; o += p.shape[0]
+    v = np.random.default_rng(4).standard_normal(n) * np.sqrt(np.diag(dense)) * 0.05
+    spec['precision'] = dense + np.outer(v, v)
+    ref = pipeline.evaluate(spec, X[:200])
+    plan = desilike_b200.Plan(spec)
+    assert plan.lowered.blocks[0]['ncols_white'] < n
+    got = plan.eval(X[:200])
+    assert np.max(np.abs(got['loglikelihood'] - ref['loglikelihood']) / np.maximum(1., np.abs(ref['loglikelihood']))) < 1e-10
+    plan.close()
