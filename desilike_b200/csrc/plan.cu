@@ -130,6 +130,8 @@ static Variant pick_variant(const dlb_plan* plan, int nslots, bool resident, int
     cand.push_back(Variant{1, 2, 7, 8, 1, 36});              // 16 warps, 128 x 112 tile                (C2 62 %, C5 69 %)
     if (const char* e = getenv("DLB_R1_VARIANT")) { const Variant v = cand[std::min<size_t>(atoi(e), cand.size() - 1)]; cand.assign(1, v); }
   } else if (nslots <= 4) {
+    // (measured and rejected: 96 x 64 tiles, 2 m-tiles x 4 n-tiles per warp -- fewer fragment loads per DMMA but twice the column
+    //  blocks and Gram epilogues: C4 58.9 - 60.6 % vs 61.7 % of FP64 peak)
     if (longk) cand.push_back(Variant{4, 1, 7, 6, 1, 76});   // 12 warps,  48 x 112 tile, one k-chunk per term (C5 + marg. 59 %; 52 % with KC = 36)
     cand.push_back(Variant{4, 1, 7, 6, 1, 36});
   } else {
