@@ -300,3 +300,16 @@ class EmulatedCalculator(BaseCalculator):
                 tables['pk11_l0'] = np.tile(base, nell)
             return dict(kind='mlp', params=params, mlp=mlp, tables=tables, defaults=defaults)
         raise ValueError('emulator engine {!r} is not on the CUDA path'.format(kind))
+
+    def table_spec(self, name):
+        """Taylor engine ``name`` as (theory spec without tables, derivatives [T, *yshape]) -- for tracer theories that post-process the
+        emulated table themselves (``LPTVelocileptorsTracerPowerSpectrumMultipoles``: bias combination + re-interpolation in k)."""
+        state = self.emulator.state
+        if name not in state['engines']: raise ValueError('emulator has no engine {!r} (engines: {})'.format(name, sorted(state['engines'])))
+        e = state['engines'][name]
+        if e['name'] != 'taylor': raise ValueError('table models on the CUDA path need a Taylor emulator of {!r} (got {!r})'.format(name, e['name']))
+        if e.get('xoperations') or e.get('yoperations'): raise ValueError('operations are not supported for the Taylor engine (reference emulators/__init__.py:435-436)')
+        deriv = np.asarray(e['derivatives'], dtype='f8')
+        spec = dict(kind='taylor', params=list(e['params']), center=np.asarray(e['center'], dtype='f8'), powers=np.asarray(e['powers'], dtype='i4'),
+                    tables={}, defaults=dict(state.get('defaults', {})))
+        return spec, deriv

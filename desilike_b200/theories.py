@@ -178,6 +178,58 @@ class EFTLikeKaiserTracerPowerSpectrumMultipoles(KaiserTracerPowerSpectrumMultip
         return terms
 
 
+class LPTVelocileptorsTracerPowerSpectrumMultipoles(BaseTracerPowerSpectrumMultipoles):
+    """Velocileptors-style table model behind an emulator file (reference full_shape.py:1182-1186, :1252-1313, standard bias basis):
+
+        P_ell(k) = interp1d(k, pt.k, sum_i pktable[ell, :, i] * m_i),
+        m = [1, b1, b1^2, b2, b1 b2, b2^2, bs, b1 bs, b2 bs, bs^2, b3, b1 b3, alpha0, alpha2, alpha4, alpha6, sn0 / nd, sn2 / nd, sn4 / nd]
+
+    with ``pktable`` [nell, nk_pt, 19] predicted by a Taylor emulator (``pt``: ``EmulatedCalculator`` with an engine 'pktable'; velocileptors
+    itself is third party and absent).  The cubic (not-a-knot) re-interpolation pt.k -> k is linear in the ordinates, so it is folded
+    into the 19 table maps at plan time; per point the CUDA path evaluates 19 bias monomials x table contractions.  alpha* and sn* enter
+    linearly: tag them ``derived='.marg'`` for analytic marginalisation (each becomes a theta-dependent Jacobian row of the plan)."""
+    _monomials = [(), ('b1',), ('b1', 'b1'), ('b2',), ('b1', 'b2'), ('b2', 'b2'), ('bs',), ('b1', 'bs'), ('b2', 'bs'), ('bs', 'bs'), ('b3',), ('b1', 'b3'),
+                  ('alpha0',), ('alpha2',), ('alpha4',), ('alpha6',), ('sn0',), ('sn2',), ('sn4',)]
+
+    def __init__(self, pt, k=None, ells=(0, 2, 4), shotnoise=1e4, tracer=None, prior_basis='standard'):
+        if prior_basis not in (None, 'standard'):
+            raise ValueError("only the standard bias basis is on the CUDA path (prior_basis='physical' divides by the emulated sigma8, reference full_shape.py:1299-1306)")
+        super().__init__(template=None, pt=pt, k=k, ells=ells, shotnoise=shotnoise, tracer=tracer)
+        norm = lambda scale: dict(dist='norm', loc=0., scale=scale)
+        P = lambda name, **kw: Parameter(name, namespace=self.tracer, **kw)
+        # reference full_shape.yaml:476-578
+        self.params = ParameterCollection([
+            P('b1', value=1., prior=dict(limits=[-1., 10.]), ref=dict(limits=[0.4, 0.6])), P('b2', value=0., prior=norm(10.), ref=norm(0.5)),
+            P('bs', value=0., prior=norm(5.), ref=norm(0.5)), P('b3', value=0., fixed=True, prior=norm(5.), ref=norm(0.5)),
+            P('alpha0', value=0., prior=norm(30.), ref=norm(1.)), P('alpha2', value=0., prior=norm(50.), ref=norm(1.)), P('alpha4', value=0., prior=norm(50.), ref=norm(1.)),
+            P('alpha6', value=0., fixed=True, prior=norm(50.), ref=norm(1.)),
+            P('sn0', value=0., prior=norm(4.), ref=norm(0.1)), P('sn2', value=0., prior=norm(100.), ref=norm(0.1)), P('sn4', value=0., prior=norm(500.), ref=norm(0.1))])
+
+    def theory_spec(self):
+        from scipy import interpolate
+        spec, deriv = self.pt.table_spec('pktable')   # [T, nell_pt, nk_pt, 19]
+        kpt, ells_pt = self.pt.k, self.pt.ells
+        if deriv.ndim != 4 or deriv.shape[1:] != (len(ells_pt), len(kpt), len(self._monomials)):
+            raise ValueError('pktable emulator must have yshape (nell, nk, 19), got {}'.format(deriv.shape[1:]))
+        if self.k[0] < kpt[0] or self.k[-1] > kpt[-1]: raise ValueError('requested k outside the emulated pt.k range')
+        index = [ells_pt.index(ell) for ell in self.ells]
+        # interp1d(k, pt.k, .) (reference jax.py:211-265; SciPy not-a-knot cubic in the NumPy fallback) as a matrix [nk, nk_pt]
+        C = interpolate.interp1d(kpt, np.eye(len(kpt)), kind='cubic', axis=0, fill_value='extrapolate')(self.k)
+        T = deriv.shape[0]
+        for i in range(len(self._monomials)):
+            spec['tables']['pktable_{:d}'.format(i)] = np.einsum('tlk,qk->tlq', deriv[..., i][:, index], C).reshape(T, -1)
+        return spec
+
+    def terms(self):
+        terms = []
+        for i, mono in enumerate(self._monomials):
+            factors = {}
+            for name in mono: factors[self._ns(name)] = factors.get(self._ns(name), 0) + 1
+            scale = 1. / self.nd if mono and mono[0].startswith('sn') else 1.
+            terms.append(dict(scale=scale, factors=list(factors.items()), table='pktable_{:d}'.format(i)))
+        return terms
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 class _BaseBAOTracer(BaseCalculator):
 

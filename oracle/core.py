@@ -279,6 +279,29 @@ def cubic_transform(flattheory, flatdata):
 
 
 # --------------------------------------------------------------------------------------------------------------------
+# velocileptors-style table models: reference desilike/theories/galaxy_clustering/full_shape.py:1182-1186 (bias combine),
+# :1295-1313 (LPTVelocileptorsTracerPowerSpectrumMultipoles.calculate, standard bias basis: cubic re-interpolation pt.k -> k)
+# --------------------------------------------------------------------------------------------------------------------
+LPT_BIAS_PARAMS = ['b1', 'b2', 'bs', 'b3', 'alpha0', 'alpha2', 'alpha4', 'alpha6', 'sn0', 'sn2', 'sn4']
+
+
+def lpt_bias_monomials(pars, nd=1e-4):
+    b1, b2, bs, b3, alpha0, alpha2, alpha4, alpha6, sn0, sn2, sn4 = pars
+    return np.array([1, b1, b1**2, b2, b1 * b2, b2**2, bs, b1 * bs, b2 * bs, bs**2, b3, b1 * b3, alpha0, alpha2, alpha4, alpha6,
+                     sn0 / nd, sn2 / nd, sn4 / nd])
+
+
+def tablevel_combine_bias_terms_poles(pktable, pars, nd=1e-4):
+    """pktable [nell, nk, 19] -> P_ell(k) [nell, nk]."""
+    return np.sum(pktable * lpt_bias_monomials(pars, nd=nd), axis=-1)
+
+
+def lpt_tracer_power(pktable, kpt, k, pars, nd=1e-4):
+    """reference full_shape.py:1310-1312: ``interp1d(self.k, self.pt.k, combine(...)[index].T).T`` (cubic; SciPy not-a-knot in the NumPy fallback)."""
+    return interp1d_cubic(k, kpt, tablevel_combine_bias_terms_poles(pktable, pars, nd=nd).T).T
+
+
+# --------------------------------------------------------------------------------------------------------------------
 # chi2: reference desilike/likelihoods/base.py:13-17, :658-664
 # --------------------------------------------------------------------------------------------------------------------
 def chi2(flatdiff, precision):

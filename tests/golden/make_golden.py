@@ -71,6 +71,29 @@ def bao_theory():
     print('bao_theory', power.shape, corr.shape)
 
 
+def lpt_combine():
+    """Function-level fixture: the reference's ``tablevel_combine_bias_terms_poles`` (full_shape.py:1182-1186) and its ``interp1d``
+    (jax.py:211-265, NumPy fallback) as chained in ``LPTVelocileptorsTracerPowerSpectrumMultipoles.calculate`` (:1310-1312), on a
+    seeded random pktable (velocileptors itself is a third-party code, absent here)."""
+    ref_harness.setup()
+    from desilike.theories.galaxy_clustering.full_shape import tablevel_combine_bias_terms_poles
+    from desilike.jax import interp1d
+    rng = np.random.default_rng(110)
+    nell = 3
+    kpt = np.concatenate([[0.0005], np.geomspace(0.0015, 0.025, 20, endpoint=True), np.arange(0.03, 0.5 + 0.0075, 0.005)])   # full_shape.py:1283
+    k = np.arange(0.02, 0.2, 0.005)
+    pktable = rng.standard_normal((nell, kpt.size, 19)) * (1e4 * np.exp(-kpt / 0.2))[None, :, None]
+    pars = np.column_stack([rng.uniform(0.5, 2., 8), rng.uniform(-2., 2., 8), rng.uniform(-2., 2., 8), rng.uniform(-1., 1., 8)] + [rng.uniform(-20., 20., 8) for i in range(4)]
+                           + [rng.uniform(-1., 1., 8) for i in range(3)])
+    nd = 1e-4
+    table = np.array([np.asarray(tablevel_combine_bias_terms_poles(pktable, list(p), nd=nd)) for p in pars])
+    power = np.array([np.asarray(interp1d(k, kpt, t.T)).T for t in table])
+    np.savez_compressed(os.path.join(HERE, 'lpt_combine.npz'), case=json.dumps(dict(kind='lpt_combine')), pktable=pktable, kpt=kpt, k=k, pars=pars, nd=nd,
+                        table=table, power=power)
+    print('lpt_combine', table.shape, power.shape)
+
+
 if __name__ == '__main__':
+    lpt_combine()
     bao_theory()
     main()

@@ -1,0 +1,61 @@
+"""Shared construction of a velocileptors-style (pktable) Taylor-emulated likelihood for the CPU and GPU tests."""
+import itertools
+
+import numpy as np
+
+
+def taylor_powers(d, order):
+    return np.array([p for total in range(order + 1) for p in itertools.product(range(order + 1), repeat=d) if sum(p) == total], dtype='i4')
+
+
+def make_lpt_likelihood(marg=True, seed=11, order=2, nk=24, tracer=None):
+    """-> (likelihood, emulator-state pieces) with a random Taylor emulator of pktable [3, nk_pt, 19] in (qpar, qper, dm, df)."""
+    import desilike_b200 as dl
+    from oracle import synthetic
+    rng = np.random.default_rng(seed)
+    ells = (0, 2, 4)
+    kpt = np.concatenate([[0.0005], np.geomspace(0.0015, 0.025, 20, endpoint=True), np.arange(0.03, 0.5 + 0.0075, 0.005)])   # reference full_shape.py:1283
+    k = np.linspace(0.02, 0.2, nk)
+    params = ['qpar', 'qper', 'dm', 'df']
+    center = np.array([1., 1., 0., 1.])
+    powers = taylor_powers(len(params), order)
+    base = synthetic.pk_fid(kpt)
+    amp = np.array([1., 1., 1., 0.3, 0.3, 0.1, 0.3, 0.3, 0.1, 0.1, 0.2, 0.2, 0.05, 0.05, 0.05, 0.05, 1e-4, 1e-4, 1e-4])
+    kfac = np.ones((len(kpt), 19)); kfac[:, 12:16] = (kpt**2)[:, None] * 10.; kfac[:, 16:] = np.stack([np.ones_like(kpt), kpt**2, kpt**4], axis=-1) / base[:, None]
+    deriv = rng.standard_normal((len(powers), len(ells), len(kpt), 19)) * (0.2**powers.sum(axis=-1))[:, None, None, None] * base[None, None, :, None] * (amp * kfac)[None, None]
+    deriv[0] = np.abs(deriv[0]) + base[None, :, None] * (amp * kfac)[None] * np.array([1., 0.5, 0.2])[:, None, None]
+    all_params = [dl.Parameter('qpar', value=1., prior=dict(limits=[0.8, 1.2])), dl.Parameter('qper', value=1., prior=dict(limits=[0.8, 1.2])),
+                  dl.Parameter('dm', value=0., prior=dict(limits=[-0.5, 0.5])), dl.Parameter('df', value=1., prior=dict(limits=[0.5, 1.5]))]
+    emu = dl.Emulator.from_taylor(params, center, powers, {'pktable': deriv}, fixed=dict(k=kpt, ells=ells, z=1.), all_params=all_params,
+                                  calculator_class=('desilike.theories.galaxy_clustering.full_shape', 'LPTVelocileptorsPowerSpectrumMultipoles'))
+    theory = dl.LPTVelocileptorsTracerPowerSpectrumMultipoles(pt=emu.to_calculator(), k=k, ells=ells, shotnoise=1e4, tracer=tracer)
+    if marg:
+        for name in ['alpha0', 'alpha2', 'alpha4', 'sn0', 'sn2', 'sn4']:
+            theory.params[theory._ns(name)].update(derived='.marg')
+    n = len(ells) * nk
+    fid = dict(b1=1.8, b2=0.4, bs=-0.3)
+    # data = the model at a fiducial point (linear parameters at 0) + noise
+    m = np.zeros(19); m[[0, 1, 2, 3, 4, 5, 6, 7, 8, 9]] = [1., fid['b1'], fid['b1']**2, fid['b2'], fid['b1'] * fid['b2'], fid['b2']**2, fid['bs'], fid['b1'] * fid['bs'], fid['b2'] * fid['bs'], fid['bs']**2]
+    from scipy import interpolate
+    data = interpolate.interp1d(kpt, (deriv[0] * m).sum(axis=-1), kind='cubic', axis=-1)(k).ravel()
+    sig = 0.05 * np.abs(data) + 20.
+    A = rng.standard_normal((n, n // 3)); C = A.dot(A.T); C /= np.sqrt(np.outer(np.diag(C), np.diag(C)))
+    cov = (0.85 * np.eye(n) + 0.15 * C) * np.outer(sig, sig)
+    data = data + 0.3 * sig * rng.standard_normal(n)
+    obs = dl.TracerPowerSpectrumMultipolesObservable(data=data.reshape(len(ells), nk), k=[k] * len(ells), ells=ells, theory=theory, name='lpt')
+    like = dl.ObservablesGaussianLikelihood(observables=[obs], covariance=cov)
+    return like, dict(kpt=kpt, k=k, ells=ells, params=params, center=center, powers=powers, deriv=deriv, cov=cov, data=data)
+
+
+def direct_theory(info, X, names, nd=1e-4):
+    """Un-collapsed restatement through the oracle: Taylor predict of pktable -> bias combine -> cubic re-interpolation."""
+    from oracle import core
+    out = []
+    for x in X:
+        v = dict(zip(names, x))
+        diffs = np.array([v[p] for p in info['params']]) - info['center']
+        mono = np.prod(diffs**info['powers'], axis=-1)
+        pktable = np.tensordot(mono, info['deriv'], axes=(0, 0))
+        pars = [v.get(n, 0.) for n in core.LPT_BIAS_PARAMS]
+        out.append(core.lpt_tracer_power(pktable, info['kpt'], info['k'], pars, nd=nd).ravel())
+    return np.array(out)

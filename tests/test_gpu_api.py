@@ -166,3 +166,29 @@ def test_fit_taylor_emulator_on_gpu(gpu_required, tmp_path):
     like_d(b1=2., qpar=1.03, dm=0.02); like_e(b1=2., qpar=1.03, dm=0.02)
     err = np.max(np.abs(like_e.flattheory - like_d.flattheory)) / scale
     assert 1e-12 < err < 5e-3                                                              # away: truncation error of an order-3 expansion
+
+
+@pytest.mark.parametrize('marg', [False, True])
+def test_lpt_velocileptors_table_model(gpu_required, marg):
+    """Velocileptors-style table model behind a Taylor emulator of pktable (reference full_shape.py:1182-1186, :1295-1313) on the CUDA path:
+    theory vectors vs the un-collapsed restatement (Taylor predict -> bias combine -> cubic re-interpolation, pinned against the reference's own
+    functions by tests/golden/lpt_combine.npz), log-posterior and marginalised alpha / sn values vs the oracle; 6 theta-dependent
+    Jacobian rows exercise the 8-slot contraction variant."""
+    import lpt_helpers
+    like, info = lpt_helpers.make_lpt_likelihood(marg=marg)
+    plan, spec = like.plan, like.spec
+    rng = np.random.default_rng(4)
+    N = 500
+    X = np.column_stack([rng.uniform(0.95, 1.05, N), rng.uniform(0.95, 1.05, N), rng.uniform(-0.05, 0.05, N), rng.uniform(0.9, 1.1, N),
+                         rng.uniform(1.5, 2.2, N), rng.uniform(-1., 1., N), rng.uniform(-1., 1., N)]
+                        + ([] if marg else [rng.uniform(-5., 5., N) for i in range(3)] + [rng.uniform(-0.5, 0.5, N) for i in range(3)]))
+    direct = lpt_helpers.direct_theory(info, X[:50], spec['params'])
+    assert np.max(np.abs(plan.theory(X[:50]) - direct)) < 1e-10 * np.max(np.abs(direct))
+    ref = pipeline.evaluate(spec, X)
+    got = plan.eval(X)
+    assert np.max(np.abs(got['logposterior'] - ref['logposterior']) / np.maximum(1., np.abs(ref['logposterior']))) < 1e-8
+    if marg:
+        assert np.max(np.abs(got['x_solved'] - ref['x_solved']) / np.maximum(1., np.abs(ref['x_solved']))) < 1e-7
+    # calculator-style call (reference base.py:124-128, likelihoods/base.py:245)
+    point = dict(zip(spec['params'], X[0]))
+    assert abs(like(**point) - ref['logposterior'][0]) < 1e-8 * max(1., abs(ref['logposterior'][0]))

@@ -149,3 +149,30 @@ def test_unknown_operation_fails_loudly(tmp_path):
     emu.state['engines']['pk_dd']['model_operations'][1]['expression'] = 'jnp.sin(v)'
     with pytest.raises(ValueError):
         emu.to_calculator().theory_spec()
+
+
+@pytest.mark.parametrize('marg', [False, True])
+def test_lpt_velocileptors_table_model_lowering(marg):
+    """Velocileptors-style table model (reference full_shape.py:1182-1186, :1295-1313) behind a Taylor emulator of pktable: the lowered plan
+    (19 bias monomials x table maps with the cubic re-interpolation folded in; alpha / sn as marginalised Jacobian rows) evaluated by the
+    NumPy mirror of the kernels reproduces (a) the un-collapsed restatement Taylor predict -> combine -> interp1d and (b) the oracle pipeline."""
+    import lowered_numpy
+    import lpt_helpers
+    from desilike_b200.lowering import Lowered
+    like, info = lpt_helpers.make_lpt_likelihood(marg=marg)
+    spec = like._finalize_spec(like.build_spec())
+    assert spec['params'] == (['qpar', 'qper', 'dm', 'df', 'b1', 'b2', 'bs'] if marg else ['qpar', 'qper', 'dm', 'df', 'b1', 'b2', 'bs', 'alpha0', 'alpha2', 'alpha4', 'sn0', 'sn2', 'sn4'])
+    assert len(spec['solved']) == (6 if marg else 0)
+    low = Lowered(spec)
+    assert low.blocks[0]['nslots'] == (7 if marg else 1)
+    rng = np.random.default_rng(2)
+    X = np.column_stack([rng.uniform(0.95, 1.05, 9), rng.uniform(0.95, 1.05, 9), rng.uniform(-0.05, 0.05, 9), rng.uniform(0.9, 1.1, 9),
+                         rng.uniform(1.5, 2.2, 9), rng.uniform(-1., 1., 9), rng.uniform(-1., 1., 9)] + ([] if marg else [rng.uniform(-5., 5., 9) for i in range(3)] + [rng.uniform(-0.5, 0.5, 9) for i in range(3)]))
+    theory = lowered_numpy.evaluate(low, X, white=False)
+    direct = lpt_helpers.direct_theory(info, X, spec['params'])
+    assert np.max(np.abs(theory - direct)) < 1e-11 * np.max(np.abs(direct))
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    assert np.max(np.abs(ref['flattheory'] - direct)) < 1e-11 * np.max(np.abs(direct))
+    got = lowered_numpy.evaluate(low, X)
+    assert np.allclose(got['logposterior'], ref['logposterior'], rtol=1e-9, atol=1e-7)
+    if marg: assert np.allclose(got['x_solved'], ref['x_solved'], rtol=1e-7, atol=1e-7)

@@ -9,7 +9,7 @@ import pytest
 from oracle import configs, pipeline
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURES = sorted(f for f in glob.glob(os.path.join(HERE, 'golden', '*.npz')) if 'bao_theory' not in f)
+FIXTURES = sorted(f for f in glob.glob(os.path.join(HERE, 'golden', '*.npz')) if 'bao_theory' not in f and 'lpt_combine' not in f)
 
 
 def load_case(fn):
@@ -59,3 +59,14 @@ def test_bao_theory_fixture():
             else:
                 got = p2c(core.bao_damped_power(p2c.kin, mu, wmu, kt, pk_t, pknow_t, synthetic.F_FID, x[0], x[1], **kw))
             assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref)), which
+
+
+def test_lpt_combine_fixture():
+    """Oracle velocileptors-style bias combination + cubic re-interpolation against the reference's own functions
+    (tests/golden/make_golden.py:lpt_combine; reference full_shape.py:1182-1186, :1310-1312)."""
+    from oracle import core
+    data = np.load(os.path.join(HERE, 'golden', 'lpt_combine.npz'))
+    nd = float(data['nd'])
+    for pars, table, power in zip(data['pars'], data['table'], data['power']):
+        assert np.allclose(core.tablevel_combine_bias_terms_poles(data['pktable'], pars, nd=nd), table, rtol=1e-13, atol=0.)
+        assert np.max(np.abs(core.lpt_tracer_power(data['pktable'], data['kpt'], data['k'], pars, nd=nd) - power)) <= 1e-12 * np.max(np.abs(power))
