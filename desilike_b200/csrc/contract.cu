@@ -72,37 +72,6 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// exp(x) for |x| <= 708 with ~1e-15 relative error in ~18 FP64 instructions (the activation epilogue of the MLP layers is bound by
-// the FP64 pipe: CUDA's exp() + IEEE division cost ~60 FP64 instructions per element): k = rint(x log2 e) by the magic-number
-// trick, r = x - k ln 2 in two steps, degree-11 Taylor polynomial of e^r on |r| <= ln 2 / 2 (remainder 6e-15), 2^k by exponent add.
-__device__ __forceinline__ double fast_exp(double x) {
-  const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
-  const int k = __double2loint(t);
-  const double kf = t - 6755399441055744.0;
-  double r = fma(-kf, 6.93147180369123816490e-01, x);
-  r = fma(-kf, 1.90821492927058770002e-10, r);
-  double p = 2.50521083854417187751e-08;            // 1 / 11!
-  p = fma(p, r, 2.75573192239858906526e-07);        // 1 / 10!
-  p = fma(p, r, 2.75573192239858906526e-06);        // 1 / 9!
-  p = fma(p, r, 2.48015873015873015873e-05);        // 1 / 8!
-  p = fma(p, r, 1.98412698412698412698e-04);        // 1 / 7!
-  p = fma(p, r, 1.38888888888888888889e-03);        // 1 / 6!
-  p = fma(p, r, 8.33333333333333333333e-03);        // 1 / 5!
-  p = fma(p, r, 4.16666666666666666667e-02);        // 1 / 4!
-  p = fma(p, r, 1.66666666666666666667e-01);        // 1 / 3!
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.);
-  p = fma(p, r, 1.);
-  return __longlong_as_double(__double_as_longlong(p) + ((long long)k << 52));
-}
-// 1 / y for finite y >= 1: hardware approximation (MUFU.RCP64H, ~20 bits) + two Newton steps
-__device__ __forceinline__ double fast_rcp(double y) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
-  r = r * fma(-y, r, 2.);
-  r = r * fma(-y, r, 2.);
-  return r;
-}
 // v / (1 + exp(-v))  (reference emulators/conversion.py:27)
 __device__ __forceinline__ double silu(double v) { return v * fast_rcp(1. + fast_exp(fmin(fmax(-v, -708.), 708.))); }
 

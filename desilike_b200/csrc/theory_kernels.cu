@@ -212,7 +212,8 @@ __global__ void __launch_bounds__(KAISER_WARPS * 32) kaiser_kernel(const DevGen 
   double qpar, qper;
   ap_qpar_qper(apmode, par[0], par[1], eta, qpar, qper);
   const double dm = par[2], dn = par[3], f = f_fid * par[4], sigmapar = par[5], sigmaper = par[6];
-  for (int i = lane; i < nt; i += 32) y[i] = pk_fid[i] * exp(dm * Tt[i] + dn * Lt[i]);
+  // fast_exp (common.h): ~1e-15 relative error in ~18 instructions instead of ~45 (the kernel is instruction-issue bound)
+  for (int i = lane; i < nt; i += 32) y[i] = pk_fid[i] * fast_exp(fmin(fmax(dm * Tt[i] + dn * Lt[i], -708.), 708.));
   __syncwarp();
   const double qap = qpar / qper, jac = 1. / (qpar * qper * qper), iq2 = 1. / (qap * qap) - 1.;
   const bool damped = (sigmapar != 0.) || (sigmaper != 0.);
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(KAISER_WARPS * 32) kaiser_kernel(const DevGen 
     for (int im = 0; im < nmu; ++im) {
       const double m2 = smu[warp][im][1];
       double p = jac * spline_eval_hp(sc, hh, y, M, lgL, lk0 + smu[warp][im][0]);
-      if (damped) p *= exp(-k * k * smu[warp][im][2]);
+      if (damped) p *= fast_exp(fmax(-k * k * smu[warp][im][2], -708.));
       const double pdt = f * m2 * p, ptt = f * f * m2 * m2 * p;
 #pragma unroll
       for (int l = 0; l < MAX_ELL; ++l)
@@ -329,10 +330,11 @@ __global__ void __launch_bounds__(BAO_WARPS * 32) bao_kernel(const DevGen g, con
     for (int im = 0; im < nmu; ++im) {
       const double pkwap = spline_eval_h(sc, hh, Dw, MDw, lk0 + smu[warp][im][0]);
       const double ca = b1 + smu[warp][im][2] * oms;
-      const double Cap = ca * ca * exp(-k2 * smu[warp][im][1]);
+      const double Cap = ca * ca * fast_exp(fmax(-k2 * smu[warp][im][1], -708.));
       const double fg = 1. + smu[warp][im][4] * k2;
       const double cb = b1 + smu[warp][im][3] * oms;
-      const double B = cb * cb / (fg * fg);
+      const double ifg = fast_rcp(fg);   // fg >= 1: hardware reciprocal + two Newton steps instead of an IEEE division
+      const double B = cb * cb * ifg * ifg;
       const double pkmu = B * pknow + Cap * pkwap;
 #pragma unroll
       for (int l = 0; l < MAX_ELL; ++l)
