@@ -183,3 +183,16 @@ def test_spline_constants_match_scipy():
         xq = np.random.default_rng(1).uniform(x[0] - 0.05, x[-1] + 0.05, 1000)
         ref = interpolate.interp1d(x, y, kind='cubic', fill_value='extrapolate')(xq)
         assert np.max(np.abs(spline.evaluate(c, x.size, y, M, xq) / ref - 1)) < 1e-11
+
+
+def test_torch_custom_op_registered_with_fake_impl():
+    """torch.ops.desilike_b200.eval_batch: registered, and shape inference works without a GPU (meta tensors)."""
+    import torch
+    from desilike_b200 import torch_ops
+    pid = torch_ops.register_plan(None, d=6, ns=3)
+    outs = torch.ops.desilike_b200.eval_batch(pid, torch.empty((17, 6), dtype=torch.float64, device='meta'))
+    assert [tuple(o.shape) for o in outs] == [(17,), (17,), (17,), (17, 3), (17,)]
+    assert outs[4].dtype == torch.int32 and outs[0].dtype == torch.float64
+    with pytest.raises(Exception):
+        torch.ops.desilike_b200.eval_batch(pid, torch.empty((17, 5), dtype=torch.float64, device='meta'))
+    torch_ops.unregister_plan(pid)

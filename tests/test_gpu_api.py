@@ -192,3 +192,22 @@ def test_lpt_velocileptors_table_model(gpu_required, marg):
     # calculator-style call (reference base.py:124-128, likelihoods/base.py:245)
     point = dict(zip(spec['params'], X[0]))
     assert abs(like(**point) - ref['logposterior'][0]) < 1e-8 * max(1., abs(ref['logposterior'][0]))
+
+
+def test_torch_custom_op(gpu_required):
+    """torch.ops.desilike_b200.eval_batch on device tensors == Plan.eval (C-ABI on the current torch stream)."""
+    import torch
+    from desilike_b200 import torch_ops
+    spec = configs.config_c5(ntracers=2, nkin=40, nbins=10, order=2, solved=True)
+    plan = dl.Plan(spec)
+    pid = torch_ops.register_plan(plan)
+    X = configs.sample_points(spec, 333, seed=9)
+    ref = plan.eval(X)
+    with torch.cuda.stream(torch.cuda.Stream()):
+        lp, ll, pr, xs, st = torch.ops.desilike_b200.eval_batch(pid, torch.as_tensor(X, device='cuda'))
+        torch.cuda.current_stream().synchronize()
+    assert np.array_equal(lp.cpu().numpy(), ref['logposterior']) and np.array_equal(ll.cpu().numpy(), ref['loglikelihood'])
+    assert np.array_equal(pr.cpu().numpy(), ref['logprior']) and np.array_equal(st.cpu().numpy(), ref['status'])
+    assert np.array_equal(xs.cpu().numpy()[:, plan._unperm], ref['x_solved'])
+    torch_ops.unregister_plan(pid)
+    plan.close()
