@@ -561,7 +561,6 @@ int launch_contract(const Variant& v, const ContractParams& p, int nsm, cudaStre
   if (v.R == 4 && v.MT == 1 && v.NT == 7 && v.WM == 6 && v.CPS == 1 && v.KC == 36) return launch_mode<4, 1, 7, 6, 1, 36>(p, grid, smem, stream);
   if (v.R == 4 && v.MT == 1 && v.NT == 7 && v.WM == 6 && v.CPS == 1 && v.KC == 76) return launch_mode<4, 1, 7, 6, 1, 76>(p, grid, smem, stream);
   if (v.R == 4 && v.MT == 1 && v.NT == 4 && v.WM == 8 && v.CPS == 1 && v.KC == 76) return launch_mode<4, 1, 4, 8, 1, 76>(p, grid, smem, stream);
-  if (v.R == 4 && v.MT == 1 && v.NT == 4 && v.WM == 8 && v.CPS == 1 && v.KC == 36) return launch_mode<4, 1, 4, 8, 1, 36>(p, grid, smem, stream);
   if (v.R == 8 && v.MT == 1 && v.NT == 4 && v.WM == 6 && v.CPS == 1 && v.KC == 36) return launch_mode<8, 1, 4, 6, 1, 36>(p, grid, smem, stream);
   if (v.R == 8 && v.MT == 1 && v.NT == 4 && v.WM == 6 && v.CPS == 1 && v.KC == 76) return launch_mode<8, 1, 4, 6, 1, 76>(p, grid, smem, stream);
   set_error("no contraction kernel variant for requested tile shape");

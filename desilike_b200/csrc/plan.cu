@@ -132,10 +132,7 @@ static Variant pick_variant(const dlb_plan* plan, int nslots, bool resident, int
   } else if (nslots <= 4) {
     // (measured and rejected: 96 x 64 tiles, 2 m-tiles x 4 n-tiles per warp -- fewer fragment loads per DMMA but twice the column
     //  blocks and Gram epilogues: C4 58.9 - 60.6 % vs 61.7 % of FP64 peak)
-    if (const char* e = getenv("DLB_R4_VARIANT")) {   // experiment: 16 warps (4 per scheduler), 64 x 64 tiles
-      if (atoi(e) == 1) cand.push_back(Variant{4, 1, 4, 8, 1, 76});
-      if (atoi(e) == 2) cand.push_back(Variant{4, 1, 4, 8, 1, 36});
-    }
+    if (longk && !getenv("DLB_R4_WIDE")) cand.push_back(Variant{4, 1, 4, 8, 1, 76});   // 16 warps (4 per scheduler: slack for the DMMA issue rate), 64 x 64 tile (C4 63.1 %, C5 + marg. 64.6 %)
     if (longk) cand.push_back(Variant{4, 1, 7, 6, 1, 76});   // 12 warps,  48 x 112 tile, one k-chunk per term (C5 + marg. 59 %; 52 % with KC = 36)
     cand.push_back(Variant{4, 1, 7, 6, 1, 36});
   } else {

@@ -33,7 +33,9 @@ struct SplineConst {          // device views into ddata
   const double* cb;           // super-diagonal / pivot          [nt]
   double r0, r1;              // not-a-knot boundary ratios
   double x0, inv_dx;          // for the initial interval guess
+  double dx;                  // uniform grids (the reference's geomspace template grids are uniform in log10 k): knot spacing
   int nt;
+  bool uniform;               // knots are x0 + i dx: interval index, width and offset in closed form (no table loads, no search)
 };
 
 __device__ __forceinline__ void ap_qpar_qper(int apmode, double q0, double q1, double eta, double& qpar, double& qper) {
@@ -130,9 +132,14 @@ __device__ __forceinline__ double spline_eval_hp(const SplineConst& sc, const do
   const int n = sc.nt;
   int i = (int)((xq - sc.x0) * sc.inv_dx);
   i = max(0, min(i, n - 2));
-  while (i > 0 && xq < sc.x[i]) --i;
-  while (i < n - 2 && xq >= sc.x[i + 1]) ++i;
-  const double h = hh[i], ih = sc.invh[i], t = xq - sc.x[i];
+  double h, ih, t;
+  if (sc.uniform) {   // a rounding-induced off-by-one interval evaluates the neighbouring cubic an ulp outside its interval: the spline is C2, no search needed
+    h = sc.dx; ih = sc.inv_dx; t = xq - fma((double)i, sc.dx, sc.x0);
+  } else {
+    while (i > 0 && xq < sc.x[i]) --i;
+    while (i < n - 2 && xq >= sc.x[i + 1]) ++i;
+    h = hh[i]; ih = sc.invh[i]; t = xq - sc.x[i];
+  }
   const double Mi = Mp[pidx(i, lgL)], Mj = Mp[pidx(i + 1, lgL)], yi = y[i];
   const double b = (y[i + 1] - yi) * ih - h * (2. * Mi + Mj) * (1. / 6.);
   return yi + t * (b + t * (0.5 * Mi + t * (Mj - Mi) * ih * (1. / 6.)));
@@ -155,19 +162,25 @@ __device__ __forceinline__ double spline_eval_h(const SplineConst& sc, const dou
   const int n = sc.nt;
   int i = (int)((xq - sc.x0) * sc.inv_dx);
   i = max(0, min(i, n - 2));
-  while (i > 0 && xq < sc.x[i]) --i;
-  while (i < n - 2 && xq >= sc.x[i + 1]) ++i;
-  const double h = hh[i], ih = sc.invh[i], t = xq - sc.x[i];
+  double h, ih, t;
+  if (sc.uniform) {
+    h = sc.dx; ih = sc.inv_dx; t = xq - fma((double)i, sc.dx, sc.x0);
+  } else {
+    while (i > 0 && xq < sc.x[i]) --i;
+    while (i < n - 2 && xq >= sc.x[i + 1]) ++i;
+    h = hh[i]; ih = sc.invh[i]; t = xq - sc.x[i];
+  }
   const double Mi = M[i], Mj = M[i + 1], yi = y[i];
   const double b = (y[i + 1] - yi) * ih - h * (2. * Mi + Mj) * (1. / 6.);
   return yi + t * (b + t * (0.5 * Mi + t * (Mj - Mi) * ih * (1. / 6.)));
 }
 
-__device__ __forceinline__ SplineConst load_spline(const double* d, int nt) {
+__device__ __forceinline__ SplineConst load_spline(const double* d, int nt, bool uniform = false) {
   // layout: x[nt] invh[nt] w[nt] invb[nt] cb[nt] then (r0, r1, x0, inv_dx)
   SplineConst sc;
   sc.nt = nt; sc.x = d; sc.invh = d + nt; sc.w = d + 2 * nt; sc.invb = d + 3 * nt; sc.cb = d + 4 * nt;
   sc.r0 = d[5 * nt]; sc.r1 = d[5 * nt + 1]; sc.x0 = d[5 * nt + 2]; sc.inv_dx = d[5 * nt + 3];
+  sc.dx = 1. / sc.inv_dx; sc.uniform = uniform;
   return sc;
 }
 constexpr int SPLINE_DOUBLES(int nt) { return 5 * nt + 4; }
@@ -205,7 +218,7 @@ __global__ void __launch_bounds__(KAISER_WARPS * 32) kaiser_kernel(const DevGen 
   const double* pk_fid = wmu + nell * nmu;
   const double* Tt = pk_fid + nt;
   const double* Lt = Tt + nt;
-  const SplineConst sc = load_spline(Lt + nt, nt);
+  const SplineConst sc = load_spline(Lt + nt, nt, (g.idata[5] & 1) != 0);   // idata[5] bit 0: template grid uniform in log10 k
   double par[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) par[j] = (j < g.nparams && g.pidx[j] >= 0) ? params[pt * d + g.pidx[j]] : g.pdef[j];
@@ -248,12 +261,17 @@ __global__ void __launch_bounds__(KAISER_WARPS * 32) kaiser_kernel(const DevGen 
         if (l < nell) { const double w = wmu[l * nmu + im]; sdd[l] += p * w; sdt[l] += pdt * w; stt[l] += ptt * w; }
     }
 #pragma unroll
+    double s11 = 0.;   // pk11 = the ell = 0 row of pk_dd (static selects: a dynamic index would push the accumulators to local memory)
+#pragma unroll
+    for (int l = 0; l < MAX_ELL; ++l)
+      if (l == ell0) s11 = sdd[l];
+#pragma unroll
     for (int l = 0; l < MAX_ELL; ++l)
       if (l < nell) {
         row[2 + l * nk + ik] = sdd[l];
         row[2 + ntab + l * nk + ik] = sdt[l];
         row[2 + 2 * ntab + l * nk + ik] = stt[l];
-        row[2 + 3 * ntab + l * nk + ik] = ell0 >= 0 ? sdd[ell0 < MAX_ELL ? ell0 : 0] : 0.;
+        row[2 + 3 * ntab + l * nk + ik] = s11;
       }
   }
   // zero the padding between / after the tables
@@ -295,7 +313,7 @@ __global__ void __launch_bounds__(BAO_WARPS * 32) bao_kernel(const DevGen g, con
   const double* M_pk = pk_t + nt;
   const double* pknow_t = M_pk + nt;
   const double* M_now = pknow_t + nt;
-  const SplineConst sc = load_spline(M_now + nt, nt);
+  const SplineConst sc = load_spline(M_now + nt, nt, (flags & 4) != 0);   // flags bit 2: template grid uniform in log10 k
   double par[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) par[j] = (j < g.nparams && g.pidx[j] >= 0) ? params[pt * d + g.pidx[j]] : g.pdef[j];

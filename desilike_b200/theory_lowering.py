@@ -81,7 +81,8 @@ def lower_theory(gen, theory, defaults, names=None):
                 if i <= m: wT[t, lane] = w_[i]
                 i = m - lane * L - t
                 if i >= 1: invbT[t, lane], cbT[t, lane] = invb_[i], cb_[i]
-        gen.idata = np.array([nk, nell, nmu, nt, APMODES[apmode], (ell0 << 8), ntab, total, base.size, L], dtype=np.int32)
+        from .spline import is_uniform
+        gen.idata = np.array([nk, nell, nmu, nt, APMODES[apmode], (ell0 << 8) | int(is_uniform(np.log10(k_t))), ntab, total, base.size, L], dtype=np.int32)
         gen.ddata = np.concatenate([base, np.log10(k), np.append(np.diff(np.log10(k_t)), 0.), wT.ravel(), invbT.ravel(), cbT.ravel()])
         gen.nfeat = total
         for t, name in enumerate(['pk_dd', 'pk_dt', 'pk_tt', 'pk11_l0']):
@@ -112,7 +113,8 @@ def lower_theory(gen, theory, defaults, names=None):
         pknow_k = evaluate(consts, nt, pknow_t, M_now, np.log10(k))
         slots = [(q0, 1.), (q1, 1.), ('b1', 1.), ('dbeta', 1.), ('sigmas', 0.), ('sigmapar', 9.), ('sigmaper', 6.), ('df', 1.)]
         gen.param_idx, gen.param_default, gen.params = _slots(gen, slots, defaults, names)
-        flags = (1 if theory.get('mode', '') == 'reciso' else 0) | (2 if xi else 0)
+        from .spline import is_uniform
+        flags = (1 if theory.get('mode', '') == 'reciso' else 0) | (2 if xi else 0) | (4 if is_uniform(np.log10(k_t)) else 0)
         head = [float(tpl.get('eta', 1. / 3.)), float(tpl['f_fid']), float(theory.get('smoothing_radius', 15.)), 0.]
         ddata = [head, k, mu, wmu.ravel(), pknow_k, pk_t, M_pk, pknow_t, M_now, consts]
         # derived tables for the kernel (offset in idata[6]): log10 k, reconstruction smoothing S(k) = exp(-(k R)^2 / 2) ('reciso' only),
