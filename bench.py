@@ -15,6 +15,10 @@ Default workload = BASELINE.json configs[1] ("TaylorEmulator (order 4) of full-s
             of those launches, against the FP64 DMMA peak measured in this run (MEASURED_PEAKS.json has no FP64 entry).
   cpu_baseline  the NumPy oracle port (threaded BLAS) on a bounded sample of the same workload on this box's host cores.
 
+Synthetic inputs: the workload definitions (spec constants, fiducial data vector, covariance) of SURVEY.md section 8d live in
+oracle/configs.py, shared with the tests; bench.py imports them to BUILD its inputs before any timing.  Every timed region of the default
+arm executes desilike_b200 (the C-ABI library) only; oracle/pipeline.py runs in the cpu_baseline leg and in ``--impl reference``.
+
 ``--impl reference``: the reference is pure Python and /root/reference does not travel to the GPU box, so the reference
 arm times the oracle port (oracle/pipeline.py -- the one other place bench.py may execute oracle/) with all host threads.
 """
