@@ -28,7 +28,7 @@ class BaseLikelihood(object):
     @property
     def all_params(self):
         params = ParameterCollection()
-        for obs in self.observables: params = params + obs.theory.all_params
+        for obs in self.observables: params = params + obs.theory.all_params + obs.params
         return params
 
     @property
@@ -60,7 +60,7 @@ class BaseLikelihood(object):
             theory['params'] = [n for n in theory['params'] if n in varied]
             theory['defaults'] = dict(theory.get('defaults', {}))
             terms = []
-            for term in obs.theory.terms():
+            for term in list(obs.theory.terms()) + list(obs.systematic_terms()):
                 term = dict(term)
                 scale, factors, sname = float(term.get('scale', 1.)), [], term.get('solved')
                 for name, power in term.get('factors', []):

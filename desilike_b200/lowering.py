@@ -18,7 +18,7 @@ Likelihood spec (plain dicts / ndarrays; the same structure the oracle evaluates
               solved=[dict(name, value, prior, marg)], observables=[obs, ...],
               precision=[P_b per observable] | P joint [n, n] | diag [n])
   obs  = dict(theory=dict(kind='taylor'|'mlp'|'kaiser'|'bao_xi'|'bao_pk', params=[...], ...constants...),
-              terms=[dict(scale, factors=[(param, pow)], solved=name|None, table=name|None, colvec=[nin]|None)],
+              terms=[dict(scale, factors=[(param, pow)], solved=name|None, table=name|None, colvec=[nin]|None, outvec=[nobs]|None)],
               nin=int, wmatrix=[nobs, nin]|None, offset=[nobs]|None, data=[nobs], transform=None)
 """
 import ctypes
@@ -191,8 +191,12 @@ class Lowered(object):
                             mat = scale * (Dc @ W.T if W is not None else Dc)
                         theta_dep = True
                     else:
-                        cv = np.ones(nin) if colvec is None else colvec
-                        vec = scale * (W @ cv if W is not None else cv)
+                        if term.get('outvec') is not None:   # output-space template, added after the window (systematic templates, reference window.py:470-473)
+                            vec = scale * f64(term['outvec'])
+                            if vec.shape != (n_o,): raise LoweringError('outvec must have the length of the observable ({:d})'.format(n_o))
+                        else:
+                            cv = np.ones(nin) if colvec is None else colvec
+                            vec = scale * (W @ cv if W is not None else cv)
                         foff, K, mat = 0, 1, vec[None, :]
                         theta_dep = bool(factors)
                     if sname is None:

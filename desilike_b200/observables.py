@@ -30,6 +30,30 @@ def _block_diag(mats):
 
 class BaseTwoPointObservable(object):
     _default_step = 0.01
+    params = None   # parameters owned by the observable itself (systematic-template amplitudes)
+
+    def _set_systematic_templates(self, templates, x):
+        """Systematic templates added to the windowed theory, ``flat += sum_i syst_i * template_i`` (reference observables/galaxy_clustering/
+        window.py:470-473, :717-735; ``get_templates`` :1253-1274, parameters ``syst_{i}`` with value 0 :1279-1283).  ``templates``: list / dict of
+        arrays over the stacked multipoles, or callables ``template(ell, x)``.  The amplitudes are linear: tag them ``derived='.marg'`` to
+        marginalise them analytically (constant Jacobian rows of the plan)."""
+        from .parameter import Parameter, ParameterCollection
+        self.templates = {}
+        if templates is None: templates = {}
+        if not isinstance(templates, dict):
+            if not isinstance(templates, (list, tuple)): templates = [templates]
+            templates = {'syst_{:d}'.format(i): t for i, t in enumerate(templates)}
+        size = sum(len(xx) for xx in x)
+        for name, template in templates.items():
+            if callable(template): template = np.concatenate([template(ell, xx) for ell, xx in zip(self.ells, x)])
+            template = np.ravel(np.asarray(template, dtype='f8'))
+            if template.size != size:
+                raise ValueError('provided template is size {:d}, but expected {:d} = sum({})'.format(template.size, size, [len(xx) for xx in x]))
+            self.templates[name] = template
+        self.params = ParameterCollection([Parameter(name, value=0., ref=dict(limits=[-1e-3, 1e-3]), delta=0.005) for name in self.templates])
+
+    def systematic_terms(self):
+        return [dict(scale=1., factors=[(name, 1)], table=None, outvec=template) for name, template in (self.templates or {}).items()]
 
     def _set_binning(self, x, xlim, ells, step_default):
         """(reference window.py:218-292, simplified to arrays): -> list of per-multipole coordinates."""
@@ -70,11 +94,12 @@ class BaseTwoPointObservable(object):
 class TracerPowerSpectrumMultipolesObservable(BaseTwoPointObservable):
 
     def __init__(self, data=None, covariance=None, klim=None, k=None, ells=None, wmatrix=None, kin=None, kinrebin=1, kinlim=None, ellsin=None,
-                 theory=None, shotnoise=None, wshotnoise=None, transform=None, name='spectrum2poles'):
+                 theory=None, shotnoise=None, wshotnoise=None, transform=None, systematic_templates=None, name='spectrum2poles'):
         from .theories import KaiserTracerPowerSpectrumMultipoles
         self.name, self.transform = name, transform
         if transform not in (None, 'cubic'): raise ValueError('transform must be one of [None, "cubic"]')
         self.k, self.ells, masklim = self._set_binning(k, klim, ells, self._default_step)
+        self._set_systematic_templates(systematic_templates, self.k)
         if theory is None: raise ValueError('provide a theory (the reference default needs a cosmoprimo fiducial)')
         self.theory = theory
         self.matrix_full, self.kmask, self.offset = None, None, None
@@ -144,17 +169,37 @@ class TracerPowerSpectrumMultipolesObservable(BaseTwoPointObservable):
 class TracerCorrelationFunctionMultipolesObservable(BaseTwoPointObservable):
     _default_step = 5.
 
-    def __init__(self, data=None, covariance=None, slim=None, s=None, ells=None, theory=None, transform=None, name='correlation2poles'):
+    def __init__(self, data=None, covariance=None, slim=None, s=None, ells=None, theory=None, transform=None, wmatrix=None, sin=None, ellsin=None,
+                 matrix_diag=None, offset=None, systematic_templates=None, name='correlation2poles'):
+        """``wmatrix`` [sum_ell ns_ell, nellin * nsin] (ndarray branch of reference window.py:651-676), ``matrix_diag`` [nell, nellin, nsin]
+        (per-separation multipole mixing, e.g. the fiber-collision kernel :690-702) and ``offset`` are the constants of
+        ``WindowedCorrelationFunctionMultipoles._apply`` (:717-728); all linear, folded into one matrix at plan time."""
         self.name, self.transform = name, None
         self.s, self.ells, masklim = self._set_binning(s, slim, ells, self._default_step)
+        self._set_systematic_templates(systematic_templates, self.s)
         if theory is None: raise ValueError('provide a theory')
         self.theory = theory
-        self.sin = np.unique(np.concatenate(self.s, axis=0))
-        self.smask = None
-        if not all(ss.shape == self.sin.shape and np.allclose(ss, self.sin) for ss in self.s):
-            smask = [np.searchsorted(self.sin, ss, side='left') for ss in self.s]
-            self.smask = np.concatenate([self.sin.size * i + sm for i, sm in enumerate(smask)], axis=0)
-        self.theory.set_k(self.sin, self.ells)
+        self.smask, self.matrix_full, self.matrix_diag, self.offset = None, None, None, None
+        if wmatrix is None:
+            self.sin, self.ellsin = np.unique(np.concatenate(self.s, axis=0)), tuple(self.ells if ellsin is None else ellsin)
+            if not all(ss.shape == self.sin.shape and np.allclose(ss, self.sin) for ss in self.s):
+                smask = [np.searchsorted(self.sin, ss, side='left') for ss in self.s]
+                self.smask = np.concatenate([self.sin.size * i + sm for i, sm in enumerate(smask)], axis=0)
+        else:
+            if sin is None: raise ValueError('provide the input separations sin of wmatrix')
+            self.sin, self.ellsin = np.asarray(sin, dtype='f8').ravel(), tuple(self.ells if ellsin is None else ellsin)
+            self.matrix_full = np.array(wmatrix, dtype='f8')
+            if self.matrix_full.shape != (sum(len(ss) for ss in self.s), len(self.ellsin) * self.sin.size):
+                raise ValueError('wmatrix must be of shape ({:d}, {:d})'.format(sum(len(ss) for ss in self.s), len(self.ellsin) * self.sin.size))
+        if matrix_diag is not None:
+            self.matrix_diag = np.asarray(matrix_diag, dtype='f8')
+            nout = len(self.ellsin) if self.matrix_full is not None else len(self.ells)
+            if self.matrix_diag.ndim != 3 or self.matrix_diag.shape[0] != nout or self.matrix_diag.shape[2] != self.sin.size:
+                raise ValueError('matrix_diag must be of shape (nell, nellin, nsin)')
+            self.ellsin = tuple(ellsin) if ellsin is not None else (self.ellsin if self.matrix_diag.shape[1] == len(self.ellsin) else None)
+            if self.ellsin is None or len(self.ellsin) != self.matrix_diag.shape[1]: raise ValueError('provide ellsin matching matrix_diag')
+        if offset is not None: self.offset = np.ravel(np.asarray(offset, dtype='f8'))
+        self.theory.set_k(self.sin, self.ellsin)
         self.covariance = None if covariance is None else np.array(covariance, dtype='f8')
         self._data_params = dict(data) if isinstance(data, dict) else None
         self.flatdata = None if (data is None or self._data_params is not None) else np.ravel(np.asarray(data, dtype='f8'))
@@ -164,6 +209,16 @@ class TracerCorrelationFunctionMultipolesObservable(BaseTwoPointObservable):
         return sum(len(ss) for ss in self.s)
 
     def observable_spec(self):
-        nin = self.theory.nin
-        W = np.eye(nin)[self.smask] if self.smask is not None else None
-        return dict(name=self.name, nin=nin, wmatrix=W, offset=None, transform=None)
+        nin, ns = self.theory.nin, self.sin.size
+        W = None
+        if self.matrix_diag is not None:   # out[l, s] = sum_l' matrix_diag[l, l', s] theory[l', s]  (reference window.py:719-720)
+            nlo, nli = self.matrix_diag.shape[:2]
+            W = np.zeros((nlo * ns, nli * ns))
+            for lo in range(nlo):
+                for li in range(nli): W[lo * ns:(lo + 1) * ns, li * ns:(li + 1) * ns] = np.diag(self.matrix_diag[lo, li])
+        if self.matrix_full is not None: W = self.matrix_full if W is None else self.matrix_full.dot(W)
+        offset = None if self.offset is None else self.offset.copy()
+        if self.smask is not None:
+            W = np.eye(nin)[self.smask] if W is None else W[self.smask]
+            if offset is not None: offset = offset[self.smask]
+        return dict(name=self.name, nin=nin, wmatrix=W, offset=offset, transform=None)

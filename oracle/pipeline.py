@@ -91,17 +91,21 @@ def observable_flat(obs, X, names, xvalues, tables=None, only_solved=None):
     if tables is None:
         tables = theory_tables(obs['theory'], X, names)
     P = np.zeros((X.shape[0], obs['nin']), dtype='f8')
+    out = 0.   # systematic templates: added after the window (reference observables/galaxy_clustering/window.py:470-473, :1285-1287)
     for term in obs['terms']:
         if only_solved is not None:
             if term.get('solved') != only_solved: continue
             c = _coef(term, X, names, {only_solved: 1.})
         else:
             c = _coef(term, X, names, xvalues)
+        if term.get('outvec') is not None:
+            out = out + c[:, None] * np.asarray(term['outvec'], dtype='f8')
+            continue
         vec = tables[term['table']] if term.get('table') is not None else 1.
         if term.get('colvec') is not None:
             vec = vec * term['colvec']
         P = P + c[:, None] * vec
-    flat = P @ obs['wmatrix'].T if obs.get('wmatrix') is not None else P
+    flat = (P @ obs['wmatrix'].T if obs.get('wmatrix') is not None else P) + out
     if only_solved is None and obs.get('offset') is not None:
         flat = flat + obs['offset']
     return flat

@@ -211,3 +211,18 @@ def test_torch_custom_op(gpu_required):
     assert np.array_equal(xs.cpu().numpy()[:, plan._unperm], ref['x_solved'])
     torch_ops.unregister_plan(pid)
     plan.close()
+
+
+def test_systematic_templates(gpu_required):
+    """Systematic templates of the windowed power spectrum (reference window.py:470-473, :1285-1287), one sampled and one analytically
+    marginalised amplitude, through the mirror classes on the CUDA path vs the oracle."""
+    from test_host_api import make_systematics_likelihood
+    like, base_spec, templates, kout = make_systematics_likelihood()
+    spec = like.spec
+    X0 = configs.sample_points(base_spec, 200, seed=13)
+    X = np.column_stack([X0, np.random.default_rng(1).uniform(-1., 1., 200)])
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    got = like.plan.eval(X)
+    assert np.max(np.abs(like.plan.theory(X) - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-10
+    assert np.max(np.abs(got['logposterior'] - ref['logposterior']) / np.maximum(1., np.abs(ref['logposterior']))) < 1e-8
+    assert np.max(np.abs(got['x_solved'] - ref['x_solved'])) < 1e-7 * max(1., np.max(np.abs(ref['x_solved'])))

@@ -176,3 +176,71 @@ def test_lpt_velocileptors_table_model_lowering(marg):
     got = lowered_numpy.evaluate(low, X)
     assert np.allclose(got['logposterior'], ref['logposterior'], rtol=1e-9, atol=1e-7)
     if marg: assert np.allclose(got['x_solved'], ref['x_solved'], rtol=1e-7, atol=1e-7)
+
+
+def make_systematics_likelihood():
+    """Kaiser + window likelihood with two systematic templates (one sampled amplitude, one analytically marginalised)."""
+    spec = configs.config_kaiser_window(eftlike=False, solved=False)
+    obs0 = spec['observables'][0]
+    th = obs0['theory']
+    nell, kout = len(th['ells']), obs0['kout']
+    template = dl.ShapeFitPowerSpectrumTemplate(pk_dd_fid=synthetic.pk_fid, pknow_dd_fid=synthetic.pknow_fid, f_fid=synthetic.F_FID)
+    theory = dl.KaiserTracerPowerSpectrumMultipoles(template=template, mu=th['nmu'])
+    templates = {'syst_a': lambda ell, k: (ell == 0) * 3e3 * np.exp(-k / 0.05), 'syst_b': np.concatenate([1e3 * (kout / 0.1)**-1 * (ell == 2) for ell in th['ells']])}
+    observable = dl.TracerPowerSpectrumMultipolesObservable(data=np.asarray(obs0['data']), theory=theory, wmatrix=np.asarray(obs0['wmatrix_raw']), kin=th['k'], ellsin=th['ells'],
+                                                            k=[kout] * nell, ells=th['ells'], shotnoise=obs0.get('shotnoise'), systematic_templates=templates)
+    like = dl.ObservablesGaussianLikelihood(observables=[observable], precision=np.array(spec['precision'][0]))
+    for param in like.all_params:
+        if param.name in spec['params']: param.update(fixed=False, prior=spec['priors'].get(param.name))
+        elif param.name == 'syst_a': param.update(fixed=False, prior=dict(limits=[-2., 2.]))
+        elif param.name == 'syst_b': param.update(fixed=False, prior=dict(dist='norm', loc=0., scale=3.), derived='.marg')
+        else: param.update(fixed=True)
+    return like, spec, templates, kout
+
+
+def test_systematic_templates_lowering():
+    """``flat += sum_i syst_i template_i`` after the window (reference window.py:470-473, :1285-1287): spec terms with an output-space vector;
+    lowered plan (NumPy mirror) == oracle == the windowed theory without templates + the templates."""
+    import lowered_numpy
+    from desilike_b200.lowering import Lowered
+    like, base_spec, templates, kout = make_systematics_likelihood()
+    spec = like._finalize_spec(like.build_spec())
+    assert spec['params'] == base_spec['params'] + ['syst_a'] and [s['name'] for s in spec['solved']] == ['syst_b']
+    X0 = configs.sample_points(base_spec, 7, seed=12)
+    a = np.linspace(-1., 1., 7)
+    X = np.column_stack([X0, a])
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    base = pipeline.evaluate(base_spec, X0, return_theory=True)
+    ta = np.concatenate([templates['syst_a'](ell, kout) for ell in (0, 2, 4)])
+    assert np.allclose(ref['flattheory'], base['flattheory'] + a[:, None] * ta, rtol=1e-13, atol=1e-9)   # syst_b at its default 0
+    low = Lowered(spec)
+    assert len(low.blocks[0]['const_solved']) == 1
+    got = lowered_numpy.evaluate(low, X, feature_fn=lowered_numpy.theory_features)
+    assert np.allclose(got['logposterior'], ref['logposterior'], rtol=1e-9, atol=1e-7)
+    assert np.allclose(got['x_solved'], ref['x_solved'], rtol=1e-7, atol=1e-9)
+
+
+def test_correlation_window_constants_fold():
+    """``WindowedCorrelationFunctionMultipoles._apply`` (reference window.py:717-728): matrix_diag (per-s multipole mixing), matrix_full, offset and
+    the s mask fold into ONE matrix + offset of the observable spec."""
+    rng = np.random.default_rng(8)
+    template = dl.BAOPowerSpectrumTemplate(pk_dd_fid=synthetic.pk_fid, pknow_dd_fid=synthetic.pknow_fid, f_fid=synthetic.F_FID, rs_drag=synthetic.RS_DRAG)
+    theory = dl.DampedBAOWigglesTracerCorrelationFunctionMultipoles(template=template, ells=(0, 2))
+    sin = np.arange(20., 152., 4.)
+    s = [sin[:-2], sin[3:]]   # union = sin (reference window.py:640-649: sin = unique of the output separations when no wmatrix is given)
+    nout, ns = sum(len(ss) for ss in s), sin.size
+    matrix_diag = np.array([[np.ones(ns) - 0.02, 0.01 * np.ones(ns)], [0.03 * sin / 100., np.ones(ns) * 0.97]])
+    offset_full = 1e-4 * rng.standard_normal(2 * ns)
+    obs = dl.TracerCorrelationFunctionMultipolesObservable(data=np.zeros(nout), s=s, ells=(0, 2), theory=theory, matrix_diag=matrix_diag, offset=offset_full)
+    ospec = obs.observable_spec()
+    th = rng.standard_normal((2, ns))
+    # reference _apply, line by line
+    ref = np.sum(matrix_diag * th[None, ...], axis=1).ravel() + offset_full
+    ref = ref[obs.smask]
+    assert np.allclose(ospec['wmatrix'] @ th.ravel() + ospec['offset'], ref, rtol=1e-14, atol=1e-14)
+    wm = rng.standard_normal((nout, 2 * ns))
+    obs = dl.TracerCorrelationFunctionMultipolesObservable(data=np.zeros(nout), s=s, ells=(0, 2), theory=theory, wmatrix=wm, sin=sin, matrix_diag=matrix_diag,
+                                                           offset=1e-4 * np.ones(nout))
+    ospec = obs.observable_spec()
+    ref = wm.dot(np.sum(matrix_diag * th[None, ...], axis=1).ravel()) + 1e-4
+    assert np.allclose(ospec['wmatrix'] @ th.ravel() + ospec['offset'], ref, rtol=1e-13, atol=1e-13)
