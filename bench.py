@@ -50,7 +50,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'logL evals/sec (batched, emulated FS+window+chi2)'
 # algorithmic FLOP per evaluation of the UN-collapsed chain
-UNCOLLAPSED_FLOPS = {'c1': 0.1e6, 'c2': 0.7e6, 'c3': 1.3e6, 'c3fft': 1.3e6, 'c4': 20e6, 'c5': 8e6, 'c5solved': 19e6}
+UNCOLLAPSED_FLOPS = {'c1': 0.1e6, 'c2': 0.7e6, 'c3': 1.3e6, 'c3fft': 1.3e6, 'c4': 20e6, 'c4wide': 47e6, 'c5': 8e6, 'c5solved': 19e6}
 UNIT = 'evals/s'
 
 
@@ -72,6 +72,8 @@ def build_spec(workload):
         return configs.config_c5(coefficients='random', solved=True), 'C5 + analytic marginalisation of 35 ct/sn terms (n=2010, d=9, ns=35)'
     if workload == 'c4':
         return configs.config_c4(), 'C4: 5 tracers x [MLP 4-64-64-64 pt emulator -> EFT-like combine -> window [402,1050]] -> chi2 + marginalisation (ns=35)'
+    if workload == 'c4wide':
+        return configs.config_c4(hidden=(512, 512, 512, 512)), 'C4 stress variant: 5 tracers x [MLP 4-512-512-512-512 pt emulator -> EFT-like combine -> window [402,1050]] -> chi2 + marginalisation (ns=35)'
     raise ValueError(workload)
 
 

@@ -9,7 +9,7 @@ from .lowering import Lowered, LoweringError
 
 from .parameter import Parameter, ParameterCollection, Samples
 from .theories import (ShapeFitPowerSpectrumTemplate, BAOPowerSpectrumTemplate, KaiserTracerPowerSpectrumMultipoles,
-                       EFTLikeKaiserTracerPowerSpectrumMultipoles, LPTVelocileptorsTracerPowerSpectrumMultipoles, DampedBAOWigglesTracerPowerSpectrumMultipoles,
+                       EFTLikeKaiserTracerPowerSpectrumMultipoles, LPTVelocileptorsTracerPowerSpectrumMultipoles, TableBiasTracerPowerSpectrumMultipoles, DampedBAOWigglesTracerPowerSpectrumMultipoles,
                        DampedBAOWigglesTracerCorrelationFunctionMultipoles)
 from .emulators import Emulator, EmulatedCalculator
 from .observables import TracerPowerSpectrumMultipolesObservable, TracerCorrelationFunctionMultipolesObservable
@@ -18,7 +18,7 @@ from .base import vmap, status_to_errors
 from .samplers import EnsembleSampler
 
 __all__ = ['Parameter', 'ParameterCollection', 'Samples', 'ShapeFitPowerSpectrumTemplate', 'BAOPowerSpectrumTemplate',
-           'KaiserTracerPowerSpectrumMultipoles', 'EFTLikeKaiserTracerPowerSpectrumMultipoles', 'LPTVelocileptorsTracerPowerSpectrumMultipoles', 'DampedBAOWigglesTracerPowerSpectrumMultipoles',
+           'KaiserTracerPowerSpectrumMultipoles', 'EFTLikeKaiserTracerPowerSpectrumMultipoles', 'LPTVelocileptorsTracerPowerSpectrumMultipoles', 'TableBiasTracerPowerSpectrumMultipoles', 'DampedBAOWigglesTracerPowerSpectrumMultipoles',
            'DampedBAOWigglesTracerCorrelationFunctionMultipoles', 'Emulator', 'EmulatedCalculator', 'TracerPowerSpectrumMultipolesObservable',
            'TracerCorrelationFunctionMultipolesObservable', 'ObservablesGaussianLikelihood', 'SumLikelihood', 'PipelineError', 'vmap', 'status_to_errors', 'EnsembleSampler',
            'Plan', 'sample_solved', 'Lowered', 'LoweringError', 'DesilikeB200Error', 'load_library', 'launch_count', 'measure_fp64_peak', 'pinned_empty']

@@ -178,7 +178,51 @@ class EFTLikeKaiserTracerPowerSpectrumMultipoles(KaiserTracerPowerSpectrumMultip
         return terms
 
 
-class LPTVelocileptorsTracerPowerSpectrumMultipoles(BaseTracerPowerSpectrumMultipoles):
+class TableBiasTracerPowerSpectrumMultipoles(BaseTracerPowerSpectrumMultipoles):
+    """Generic table model ``P_ell(k) = interp1d(k, pt.k, sum_i table[ell, :, i] * m_i(bias))`` behind a Taylor emulator of ``table`` [nell, nk_pt, nm]:
+    the structure shared by the reference's perturbation-theory tracers (``combine_bias_terms_poles``, reference full_shape.py:1168, :1214, :1479,
+    :1711, :1976 ...).  ``monomials``: one tuple of parameter basenames per table slice (``('b1', 'b1')`` = b1^2, ``()`` = 1), optionally
+    ``(scale, names)``; ``params``: the bias ``Parameter`` objects.  Parameters entering linearly can be tagged ``derived='.marg'``."""
+    table_name = 'pktable'
+
+    def __init__(self, pt, monomials=None, params=(), k=None, ells=(0, 2, 4), shotnoise=1e4, tracer=None, table=None):
+        super().__init__(template=None, pt=pt, k=k, ells=ells, shotnoise=shotnoise, tracer=tracer)
+        if table is not None: self.table_name = str(table)
+        if monomials is not None: self._monomials = [tuple(m) for m in monomials]
+        self.params = ParameterCollection([Parameter(p.basename, value=p.value, fixed=p.fixed, prior=p.prior, ref=p.ref, derived=p.derived, namespace=self.tracer) for p in params])
+
+    def _monomial(self, i):
+        """-> (scale, names) of table slice i."""
+        mono = self._monomials[i]
+        if len(mono) == 2 and not isinstance(mono[0], str): return float(mono[0]), tuple(mono[1])
+        return 1., tuple(mono)
+
+    def theory_spec(self):
+        from scipy import interpolate
+        spec, deriv = self.pt.table_spec(self.table_name)   # [T, nell_pt, nk_pt, nm]
+        kpt, ells_pt = self.pt.k, self.pt.ells
+        if deriv.ndim != 4 or deriv.shape[1:] != (len(ells_pt), len(kpt), len(self._monomials)):
+            raise ValueError('{} emulator must have yshape (nell, nk, {:d}), got {}'.format(self.table_name, len(self._monomials), deriv.shape[1:]))
+        if self.k[0] < kpt[0] or self.k[-1] > kpt[-1]: raise ValueError('requested k outside the emulated pt.k range')
+        index = [ells_pt.index(ell) for ell in self.ells]
+        # interp1d(k, pt.k, .) (reference jax.py:211-265; SciPy not-a-knot cubic in the NumPy fallback) as a matrix [nk, nk_pt]
+        C = interpolate.interp1d(kpt, np.eye(len(kpt)), kind='cubic', axis=0, fill_value='extrapolate')(self.k)
+        T = deriv.shape[0]
+        for i in range(len(self._monomials)):
+            spec['tables']['{}_{:d}'.format(self.table_name, i)] = np.einsum('tlk,qk->tlq', deriv[..., i][:, index], C).reshape(T, -1)
+        return spec
+
+    def terms(self):
+        terms = []
+        for i in range(len(self._monomials)):
+            scale, names = self._monomial(i)
+            factors = {}
+            for name in names: factors[self._ns(name)] = factors.get(self._ns(name), 0) + 1
+            terms.append(dict(scale=scale, factors=list(factors.items()), table='{}_{:d}'.format(self.table_name, i)))
+        return terms
+
+
+class LPTVelocileptorsTracerPowerSpectrumMultipoles(TableBiasTracerPowerSpectrumMultipoles):
     """Velocileptors-style table model behind an emulator file (reference full_shape.py:1182-1186, :1252-1313, standard bias basis):
 
         P_ell(k) = interp1d(k, pt.k, sum_i pktable[ell, :, i] * m_i),
@@ -194,7 +238,7 @@ class LPTVelocileptorsTracerPowerSpectrumMultipoles(BaseTracerPowerSpectrumMulti
     def __init__(self, pt, k=None, ells=(0, 2, 4), shotnoise=1e4, tracer=None, prior_basis='standard'):
         if prior_basis not in (None, 'standard'):
             raise ValueError("only the standard bias basis is on the CUDA path (prior_basis='physical' divides by the emulated sigma8, reference full_shape.py:1299-1306)")
-        super().__init__(template=None, pt=pt, k=k, ells=ells, shotnoise=shotnoise, tracer=tracer)
+        BaseTracerPowerSpectrumMultipoles.__init__(self, template=None, pt=pt, k=k, ells=ells, shotnoise=shotnoise, tracer=tracer)
         norm = lambda scale: dict(dist='norm', loc=0., scale=scale)
         P = lambda name, **kw: Parameter(name, namespace=self.tracer, **kw)
         # reference full_shape.yaml:476-578
@@ -205,29 +249,9 @@ class LPTVelocileptorsTracerPowerSpectrumMultipoles(BaseTracerPowerSpectrumMulti
             P('alpha6', value=0., fixed=True, prior=norm(50.), ref=norm(1.)),
             P('sn0', value=0., prior=norm(4.), ref=norm(0.1)), P('sn2', value=0., prior=norm(100.), ref=norm(0.1)), P('sn4', value=0., prior=norm(500.), ref=norm(0.1))])
 
-    def theory_spec(self):
-        from scipy import interpolate
-        spec, deriv = self.pt.table_spec('pktable')   # [T, nell_pt, nk_pt, 19]
-        kpt, ells_pt = self.pt.k, self.pt.ells
-        if deriv.ndim != 4 or deriv.shape[1:] != (len(ells_pt), len(kpt), len(self._monomials)):
-            raise ValueError('pktable emulator must have yshape (nell, nk, 19), got {}'.format(deriv.shape[1:]))
-        if self.k[0] < kpt[0] or self.k[-1] > kpt[-1]: raise ValueError('requested k outside the emulated pt.k range')
-        index = [ells_pt.index(ell) for ell in self.ells]
-        # interp1d(k, pt.k, .) (reference jax.py:211-265; SciPy not-a-knot cubic in the NumPy fallback) as a matrix [nk, nk_pt]
-        C = interpolate.interp1d(kpt, np.eye(len(kpt)), kind='cubic', axis=0, fill_value='extrapolate')(self.k)
-        T = deriv.shape[0]
-        for i in range(len(self._monomials)):
-            spec['tables']['pktable_{:d}'.format(i)] = np.einsum('tlk,qk->tlq', deriv[..., i][:, index], C).reshape(T, -1)
-        return spec
-
-    def terms(self):
-        terms = []
-        for i, mono in enumerate(self._monomials):
-            factors = {}
-            for name in mono: factors[self._ns(name)] = factors.get(self._ns(name), 0) + 1
-            scale = 1. / self.nd if mono and mono[0].startswith('sn') else 1.
-            terms.append(dict(scale=scale, factors=list(factors.items()), table='pktable_{:d}'.format(i)))
-        return terms
+    def _monomial(self, i):
+        mono = self._monomials[i]
+        return (1. / self.nd if mono and mono[0].startswith('sn') else 1.), mono
 
 
 # ---------------------------------------------------------------------------------------------------------------------

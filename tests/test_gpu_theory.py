@@ -124,6 +124,22 @@ def test_mlp_full_width(gpu_required):
         plan.close()
 
 
+@pytest.mark.parametrize('hidden', [(128, 96), (512, 512, 512, 512), (64, 64, 64, 64, 64)])
+def test_mlp_wide_networks(gpu_required, hidden):
+    """MLP emulators beyond the fused kernel's limits (SURVEY.md section 8d stress variant 4 x 512; widths > 64 run layer by layer as output-mode
+    launches of the contraction kernel, resident or streaming A) -- and a deeper 64-wide one through the fused kernel."""
+    import desilike_b200
+    spec = configs.config_c4(ntracers=2, nkin=40, nbins=10, hidden=hidden)
+    plan = desilike_b200.Plan(spec)
+    X = configs.sample_points(spec, 300, seed=16)
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    got = plan.eval(X)
+    assert np.max(np.abs(plan.theory(X) - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-10
+    assert np.max(np.abs(got['logposterior'] - ref['logposterior']) / np.maximum(1., np.abs(ref['logposterior']))) < 1e-8
+    assert np.max(np.abs(got['x_solved'] - ref['x_solved']) / np.maximum(1., np.abs(ref['x_solved']))) < 1e-7
+    plan.close()
+
+
 @pytest.mark.parametrize('fftlog', ['fold', 'kernel'])
 def test_c3_bao_fftlog(gpu_required, fftlog):
     """BASELINE configs[2]: damped-BAO P(k) -> FFTLog -> xi_ell(s) (+ marginalised broadband) -> chi2; with the P -> xi operator folded

@@ -244,3 +244,27 @@ def test_correlation_window_constants_fold():
     ospec = obs.observable_spec()
     ref = wm.dot(np.sum(matrix_diag * th[None, ...], axis=1).ravel()) + 1e-4
     assert np.allclose(ospec['wmatrix'] @ th.ravel() + ospec['offset'], ref, rtol=1e-13, atol=1e-13)
+
+
+def test_generic_table_bias_model():
+    """TableBiasTracerPowerSpectrumMultipoles with a user-defined monomial list (here: b1^2, b1, 1 and a linear counter-term with scale 0.5)
+    equals the hand-written combination of the emulated table slices."""
+    import lpt_helpers
+    like, info = lpt_helpers.make_lpt_likelihood(marg=False)
+    emu_calc = like.observables[0].theory.pt
+    params = [dl.Parameter('b1', value=1.5, prior=dict(limits=[0., 4.])), dl.Parameter('c0', value=0., prior=dict(dist='norm', loc=0., scale=10.))]
+    monos = [('b1', 'b1'), ('b1',), ()] + [(0.5, ('c0',))] + [(0., ())] * 15
+    theory = dl.TableBiasTracerPowerSpectrumMultipoles(pt=emu_calc, monomials=monos, params=params, k=info['k'], ells=info['ells'])
+    terms = theory.terms()
+    assert terms[0]['factors'] == [('b1', 2)] and terms[3]['scale'] == 0.5 and terms[3]['factors'] == [('c0', 1)]
+    tspec = theory.theory_spec()
+    names = ['qpar', 'qper', 'dm', 'df']
+    X = np.array([[1.02, 0.98, 0.03, 1.05]])
+    tabs = pipeline.theory_tables(tspec, X, names)
+    from oracle import core
+    diffs = X[0] - info['center']
+    pktable = np.tensordot(np.prod(diffs**info['powers'], axis=-1), info['deriv'], axes=(0, 0))
+    b1, c0 = 1.7, 3.
+    direct = core.interp1d_cubic(info['k'], info['kpt'], (b1**2 * pktable[..., 0] + b1 * pktable[..., 1] + pktable[..., 2] + 0.5 * c0 * pktable[..., 3]).T).T.ravel()
+    got = b1**2 * tabs['pktable_0'][0] + b1 * tabs['pktable_1'][0] + tabs['pktable_2'][0] + 0.5 * c0 * tabs['pktable_3'][0]
+    assert np.allclose(got, direct, rtol=1e-12, atol=1e-8)
