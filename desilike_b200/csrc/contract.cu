@@ -556,6 +556,8 @@ int launch_contract(const Variant& v, const ContractParams& p, int nsm, cudaStre
   const int grid = (int)std::min<long long>((long long)nsm * v.CPS, std::max<long long>(p.U, 1));
   if (v.R == 1 && v.MT == 2 && v.NT == 7 && v.WM == 4 && v.CPS == 2 && v.KC == 28) return launch_mode<1, 2, 7, 4, 2, 28>(p, grid, smem, stream);
   if (v.R == 1 && v.MT == 2 && v.NT == 7 && v.WM == 4 && v.CPS == 2 && v.KC == 36) return launch_mode<1, 2, 7, 4, 2, 36>(p, grid, smem, stream);
+  if (v.R == 1 && v.MT == 2 && v.NT == 5 && v.WM == 4 && v.CPS == 2 && v.KC == 28) return launch_mode<1, 2, 5, 4, 2, 28>(p, grid, smem, stream);
+  if (v.R == 1 && v.MT == 2 && v.NT == 5 && v.WM == 4 && v.CPS == 2 && v.KC == 36) return launch_mode<1, 2, 5, 4, 2, 36>(p, grid, smem, stream);
   if (v.R == 1 && v.MT == 2 && v.NT == 7 && v.WM == 6 && v.CPS == 1 && v.KC == 76) return launch_mode<1, 2, 7, 6, 1, 76>(p, grid, smem, stream);
   if (v.R == 1 && v.MT == 2 && v.NT == 7 && v.WM == 8 && v.CPS == 1 && v.KC == 36) return launch_mode<1, 2, 7, 8, 1, 36>(p, grid, smem, stream);
   if (v.R == 4 && v.MT == 1 && v.NT == 7 && v.WM == 6 && v.CPS == 1 && v.KC == 36) return launch_mode<4, 1, 7, 6, 1, 36>(p, grid, smem, stream);

@@ -120,10 +120,14 @@ static bool is_device_ptr(const void* ptr) {
 // Kernel variant for a launch whose blocks need `nslots` accumulator slots: the first candidate whose shared memory fits with
 // at least 2 TMA stages.  Long k-chunks (one per term when K <= 76) amortise the per-chunk cost (stage release, barrier wait,
 // coefficient loads) best; `maxK` is the longest contraction of the launch.
-static Variant pick_variant(const dlb_plan* plan, int nslots, bool resident, int ast, int ncoef, int npart_max, int maxK) {
+static Variant pick_variant(const dlb_plan* plan, int nslots, bool resident, int ast, int ncoef, int npart_max, int maxK, bool narrow = false) {
   std::vector<Variant> cand;
   const bool longk = maxK > 36;
   if (nslots <= 1) {
+    if (narrow && !getenv("DLB_NO_NARROW")) {   // 64 x 80 tiles: less zero padding when the blocks' column counts fit 80-column blocks much better than 112
+      if (maxK > 28) cand.push_back(Variant{1, 2, 5, 4, 2, 36});
+      cand.push_back(Variant{1, 2, 5, 4, 2, 28});
+    }
     if (maxK > 28) cand.push_back(Variant{1, 2, 7, 4, 2, 36});   // 2 CTAs / SM x 8 warps, 64 x 112 tiles, longer k-chunks when they fit
     cand.push_back(Variant{1, 2, 7, 4, 2, 28});              // 2 CTAs / SM x 8 warps, 64 x 112 tiles (measured: C2 62 %, C5 70 %)
     if (longk) cand.push_back(Variant{1, 2, 7, 6, 1, 76});   // 12 warps,  96 x 112 tile                (C2 60 %, C5 68 %)
@@ -661,7 +665,13 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
         resident = false;
     }
   }
-  const Variant var = pick_variant(plan, max_slots, resident, resident ? ast : 0, desc->ncoef, npart_bound, maxK);
+  long long pad7 = 0, pad5 = 0;   // padded column totals with 112- and 80-column blocks
+  for (int ib = 0; ib < desc->nblocks; ++ib) {
+    const dlb_block_desc& bd = desc->blocks[ib];
+    const int cols = (bd.ncols_white > 0 ? bd.ncols_white : bd.ncols) + bd.nconst;
+    pad7 += (cols + 111) / 112 * 112; pad5 += (cols + 79) / 80 * 80;
+  }
+  const Variant var = pick_variant(plan, max_slots, resident, resident ? ast : 0, desc->ncoef, npart_bound, maxK, pad5 * 10 < pad7 * 9);
   plan->resident = resident;
   if (resident) {   // factor lists of the monomials, one table per generator, indexed by segment column
     plan->d_paths.resize(desc->ngen, nullptr);
