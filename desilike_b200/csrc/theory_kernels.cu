@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(KAISER_WARPS * 32) kaiser_kernel(const DevGen 
   for (int ik = lane; ik < nk; ik += 32) {
     double sdd[MAX_ELL] = {0., 0., 0.}, sdt[MAX_ELL] = {0., 0., 0.}, stt[MAX_ELL] = {0., 0., 0.};
     const double k = kk[ik], lk0 = lkk[ik];
+#pragma unroll 2
     for (int im = 0; im < nmu; ++im) {
       const double m2 = smu[warp][im][1];
       double p = jac * spline_eval_hp(sc, hh, y, M, lgL, lk0 + smu[warp][im][0]);
@@ -345,7 +346,8 @@ __global__ void __launch_bounds__(BAO_WARPS * 32) bao_kernel(const DevGen g, con
   for (int ik = lane; ik < nk; ik += 32) {
     double acc[MAX_ELL] = {0., 0., 0.};
     const double lk0 = lkk[ik], k2 = k2t[ik], oms = 1. - skt[ik], pknow = pknow_k[ik];
-    for (int im = 0; im < nmu; ++im) {
+#pragma unroll 2
+    for (int im = 0; im < nmu; ++im) {   // two mu nodes in flight: their table loads and FP64 chains are independent
       const double pkwap = spline_eval_h(sc, hh, Dw, MDw, lk0 + smu[warp][im][0]);
       const double ca = b1 + smu[warp][im][2] * oms;
       const double Cap = ca * ca * fast_exp(fmax(-k2 * smu[warp][im][1], -708.));

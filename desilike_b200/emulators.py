@@ -307,7 +307,10 @@ class EmulatedCalculator(BaseCalculator):
         state = self.emulator.state
         if name not in state['engines']: raise ValueError('emulator has no engine {!r} (engines: {})'.format(name, sorted(state['engines'])))
         e = state['engines'][name]
-        if e['name'] != 'taylor': raise ValueError('table models on the CUDA path need a Taylor emulator of {!r} (got {!r})'.format(name, e['name']))
+        if e['name'] == 'mlp':   # -> (spec, yshape): the table is a slice of the network output, selected by index
+            spec = dict(kind='mlp', params=list(e['params']), mlp=_parse_mlp_engine(e), tables={}, defaults=dict(state.get('defaults', {})))
+            return spec, tuple(e['yshape'])
+        if e['name'] != 'taylor': raise ValueError('table models on the CUDA path need a Taylor or MLP emulator of {!r} (got {!r})'.format(name, e['name']))
         if e.get('xoperations') or e.get('yoperations'): raise ValueError('operations are not supported for the Taylor engine (reference emulators/__init__.py:435-436)')
         deriv = np.asarray(e['derivatives'], dtype='f8')
         spec = dict(kind='taylor', params=list(e['params']), center=np.asarray(e['center'], dtype='f8'), powers=np.asarray(e['powers'], dtype='i4'),

@@ -44,5 +44,8 @@ def lower_mlp(gen, theory, defaults):
         scale = lim[:, 1] - lim[:, 0]
         A, c = A * scale, c * scale + lim[:, 0]
     for name, sl in theory['tables'].items():
+        post = None
+        if isinstance(sl, tuple): sl, post = sl   # (output indices, linear map [len(indices), nin]) applied after the selection (e.g. re-interpolation in k)
         D = np.concatenate([c[sl][None, :], np.zeros((1, c[sl].size)), A[:, sl]], axis=0)
+        if post is not None: D = D @ f64(post)
         gen.tables[name] = (0, H + 2, D)

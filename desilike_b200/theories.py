@@ -199,17 +199,24 @@ class TableBiasTracerPowerSpectrumMultipoles(BaseTracerPowerSpectrumMultipoles):
 
     def theory_spec(self):
         from scipy import interpolate
-        spec, deriv = self.pt.table_spec(self.table_name)   # [T, nell_pt, nk_pt, nm]
+        spec, deriv = self.pt.table_spec(self.table_name)   # Taylor: derivatives [T, nell_pt, nk_pt, nm]; MLP: the output's yshape
         kpt, ells_pt = self.pt.k, self.pt.ells
-        if deriv.ndim != 4 or deriv.shape[1:] != (len(ells_pt), len(kpt), len(self._monomials)):
-            raise ValueError('{} emulator must have yshape (nell, nk, {:d}), got {}'.format(self.table_name, len(self._monomials), deriv.shape[1:]))
+        yshape = tuple(deriv.shape[1:]) if spec['kind'] == 'taylor' else tuple(deriv)
+        if yshape != (len(ells_pt), len(kpt), len(self._monomials)):
+            raise ValueError('{} emulator must have yshape (nell, nk, {:d}), got {}'.format(self.table_name, len(self._monomials), yshape))
         if self.k[0] < kpt[0] or self.k[-1] > kpt[-1]: raise ValueError('requested k outside the emulated pt.k range')
         index = [ells_pt.index(ell) for ell in self.ells]
         # interp1d(k, pt.k, .) (reference jax.py:211-265; SciPy not-a-knot cubic in the NumPy fallback) as a matrix [nk, nk_pt]
         C = interpolate.interp1d(kpt, np.eye(len(kpt)), kind='cubic', axis=0, fill_value='extrapolate')(self.k)
-        T = deriv.shape[0]
         for i in range(len(self._monomials)):
-            spec['tables']['{}_{:d}'.format(self.table_name, i)] = np.einsum('tlk,qk->tlq', deriv[..., i][:, index], C).reshape(T, -1)
+            name = '{}_{:d}'.format(self.table_name, i)
+            if spec['kind'] == 'taylor':
+                spec['tables'][name] = np.einsum('tlk,qk->tlq', deriv[..., i][:, index], C).reshape(deriv.shape[0], -1)
+            else:   # indices of [ell, :, i] in the flat network output, then the block-diagonal interpolation over the multipoles
+                idx = np.arange(int(np.prod(yshape))).reshape(yshape)[index, :, i].ravel()
+                post = np.zeros((len(index) * len(kpt), len(index) * len(self.k)))
+                for l in range(len(index)): post[l * len(kpt):(l + 1) * len(kpt), l * len(self.k):(l + 1) * len(self.k)] = C.T
+                spec['tables'][name] = (idx, post)
         return spec
 
     def terms(self):

@@ -37,7 +37,7 @@ def theory_tables(theory, X, names):
         return {name: mono @ deriv.reshape(deriv.shape[0], -1) for name, deriv in theory['tables'].items()}
     if kind == 'mlp':
         y = core.mlp_predict(Xe, theory['mlp'])
-        return {name: y[:, sl] for name, sl in theory['tables'].items()}
+        return {name: (y[:, sl[0]] @ np.asarray(sl[1], dtype='f8') if isinstance(sl, tuple) else y[:, sl]) for name, sl in theory['tables'].items()}
     if kind == 'kaiser':
         tpl = theory['template']
         mu, wmu = core.legendre_weights(theory['ells'], theory['nmu'])

@@ -8,7 +8,7 @@ def taylor_powers(d, order):
     return np.array([p for total in range(order + 1) for p in itertools.product(range(order + 1), repeat=d) if sum(p) == total], dtype='i4')
 
 
-def make_lpt_likelihood(marg=True, seed=11, order=2, nk=24, tracer=None):
+def make_lpt_likelihood(marg=True, seed=11, order=2, nk=24, tracer=None, engine='taylor'):
     """-> (likelihood, emulator-state pieces) with a random Taylor emulator of pktable [3, nk_pt, 19] in (qpar, qper, dm, df)."""
     import desilike_b200 as dl
     from oracle import synthetic
@@ -26,8 +26,19 @@ def make_lpt_likelihood(marg=True, seed=11, order=2, nk=24, tracer=None):
     deriv[0] = np.abs(deriv[0]) + base[None, :, None] * (amp * kfac)[None] * np.array([1., 0.5, 0.2])[:, None, None]
     all_params = [dl.Parameter('qpar', value=1., prior=dict(limits=[0.8, 1.2])), dl.Parameter('qper', value=1., prior=dict(limits=[0.8, 1.2])),
                   dl.Parameter('dm', value=0., prior=dict(limits=[-0.5, 0.5])), dl.Parameter('df', value=1., prior=dict(limits=[0.5, 1.5]))]
-    emu = dl.Emulator.from_taylor(params, center, powers, {'pktable': deriv}, fixed=dict(k=kpt, ells=ells, z=1.), all_params=all_params,
-                                  calculator_class=('desilike.theories.galaxy_clustering.full_shape', 'LPTVelocileptorsPowerSpectrumMultipoles'))
+    mlp = None
+    if engine == 'mlp':   # a small random network whose output is the flat pktable [3, nk_pt, 19] (affine y-scaling onto the table amplitudes)
+        ny = len(ells) * len(kpt) * 19
+        widths = [len(params), 12, 10, ny]
+        layers = [(rng.standard_normal((a, b)) * np.sqrt(2. / a), 0.1 * rng.standard_normal(b)) for a, b in zip(widths[:-1], widths[1:])]
+        scale = np.abs(deriv[0]).ravel() + 1e-3
+        mlp = dict(xlimits=np.array([[0.8, 1.2], [0.8, 1.2], [-0.5, 0.5], [0.5, 1.5]]), layers=layers, activation='silu',
+                   ylimits=np.stack([deriv[0].ravel() - 0.05 * scale, deriv[0].ravel() + 0.05 * scale], axis=-1), pca=None)
+        emu = dl.Emulator.from_mlp(params, mlp, {'pktable': slice(0, ny)}, {'pktable': (len(ells), len(kpt), 19)}, fixed=dict(k=kpt, ells=ells, z=1.), all_params=all_params,
+                                   defaults=dict(zip(params, center)), calculator_class=('desilike.theories.galaxy_clustering.full_shape', 'LPTVelocileptorsPowerSpectrumMultipoles'))
+    else:
+        emu = dl.Emulator.from_taylor(params, center, powers, {'pktable': deriv}, fixed=dict(k=kpt, ells=ells, z=1.), all_params=all_params,
+                                      calculator_class=('desilike.theories.galaxy_clustering.full_shape', 'LPTVelocileptorsPowerSpectrumMultipoles'))
     theory = dl.LPTVelocileptorsTracerPowerSpectrumMultipoles(pt=emu.to_calculator(), k=k, ells=ells, shotnoise=1e4, tracer=tracer)
     if marg:
         for name in ['alpha0', 'alpha2', 'alpha4', 'sn0', 'sn2', 'sn4']:
@@ -44,7 +55,7 @@ def make_lpt_likelihood(marg=True, seed=11, order=2, nk=24, tracer=None):
     data = data + 0.3 * sig * rng.standard_normal(n)
     obs = dl.TracerPowerSpectrumMultipolesObservable(data=data.reshape(len(ells), nk), k=[k] * len(ells), ells=ells, theory=theory, name='lpt')
     like = dl.ObservablesGaussianLikelihood(observables=[obs], covariance=cov)
-    return like, dict(kpt=kpt, k=k, ells=ells, params=params, center=center, powers=powers, deriv=deriv, cov=cov, data=data)
+    return like, dict(kpt=kpt, k=k, ells=ells, params=params, center=center, powers=powers, deriv=deriv, cov=cov, data=data, mlp=mlp)
 
 
 def direct_theory(info, X, names, nd=1e-4):
@@ -53,9 +64,12 @@ def direct_theory(info, X, names, nd=1e-4):
     out = []
     for x in X:
         v = dict(zip(names, x))
-        diffs = np.array([v[p] for p in info['params']]) - info['center']
-        mono = np.prod(diffs**info['powers'], axis=-1)
-        pktable = np.tensordot(mono, info['deriv'], axes=(0, 0))
+        if info.get('mlp') is not None:
+            pktable = core.mlp_predict(np.array([[v[p] for p in info['params']]]), info['mlp'])[0].reshape(len(info['ells']), len(info['kpt']), 19)
+        else:
+            diffs = np.array([v[p] for p in info['params']]) - info['center']
+            mono = np.prod(diffs**info['powers'], axis=-1)
+            pktable = np.tensordot(mono, info['deriv'], axes=(0, 0))
         pars = [v.get(n, 0.) for n in core.LPT_BIAS_PARAMS]
         out.append(core.lpt_tracer_power(pktable, info['kpt'], info['k'], pars, nd=nd).ravel())
     return np.array(out)

@@ -168,14 +168,14 @@ def test_fit_taylor_emulator_on_gpu(gpu_required, tmp_path):
     assert 1e-12 < err < 5e-3                                                              # away: truncation error of an order-3 expansion
 
 
-@pytest.mark.parametrize('marg', [False, True])
-def test_lpt_velocileptors_table_model(gpu_required, marg):
+@pytest.mark.parametrize('marg,engine', [(False, 'taylor'), (True, 'taylor'), (True, 'mlp')])
+def test_lpt_velocileptors_table_model(gpu_required, marg, engine):
     """Velocileptors-style table model behind a Taylor emulator of pktable (reference full_shape.py:1182-1186, :1295-1313) on the CUDA path:
     theory vectors vs the un-collapsed restatement (Taylor predict -> bias combine -> cubic re-interpolation, pinned against the reference's own
     functions by tests/golden/lpt_combine.npz), log-posterior and marginalised alpha / sn values vs the oracle; 6 theta-dependent
     Jacobian rows exercise the 8-slot contraction variant."""
     import lpt_helpers
-    like, info = lpt_helpers.make_lpt_likelihood(marg=marg)
+    like, info = lpt_helpers.make_lpt_likelihood(marg=marg, engine=engine)
     plan, spec = like.plan, like.spec
     rng = np.random.default_rng(4)
     N = 500

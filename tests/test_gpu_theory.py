@@ -223,3 +223,39 @@ def test_bao_kernels_match_reference_classes(gpu_required, fftlog):
         got = plan.theory(X).reshape(data[which].shape)
         assert np.max(np.abs(got - data[which])) <= 1e-10 * np.max(np.abs(data[which])), which
         plan.close()
+
+
+def test_nonuniform_template_grids(gpu_required):
+    """Template grids that are NOT uniform in log10 k take the searched-interval spline path of the Kaiser / BAO kernels (the closed-form
+    interval lookup is only enabled when spline.is_uniform holds at plan time): parity with the oracle on a jittered grid."""
+    import desilike_b200
+    from oracle import synthetic
+    from desilike_b200.spline import is_uniform
+    rng = np.random.default_rng(17)
+    # Kaiser + window
+    spec = configs.config_kaiser_window(eftlike=False, solved=False)
+    tpl = spec['observables'][0]['theory']['template']
+    k = np.sort(tpl['k'] * np.exp(0.3 * np.log(tpl['k'][1] / tpl['k'][0]) * rng.uniform(-1., 1., tpl['k'].size)))
+    assert is_uniform(np.log10(tpl['k'])) and not is_uniform(np.log10(k))
+    tpl.update(k=k, pk_dd_fid=synthetic.pk_fid(k), pknow_dd_fid=synthetic.pknow_fid(k))
+    plan = desilike_b200.Plan(spec)
+    X = configs.sample_points(spec, 64, seed=18)
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    assert np.max(np.abs(plan.theory(X) - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-10
+    plan.close()
+    # damped BAO P(k)
+    kk = np.arange(0.02, 0.3, 0.005)
+    tplb = configs.bao_template()
+    kb = np.sort(tplb['k'] * np.exp(0.3 * np.log(tplb['k'][1] / tplb['k'][0]) * rng.uniform(-1., 1., tplb['k'].size)))
+    tplb.update(k=kb, pk_dd_fid=synthetic.pk_fid(kb), pknow_dd_fid=synthetic.pknow_fid(kb))
+    names = ['qpar', 'qper', 'b1', 'dbeta', 'sigmas', 'sigmapar', 'sigmaper']
+    theory = dict(kind='bao_pk', k=kk, ells=(0, 2), nmu=10, template=tplb, mode='', params=names, defaults={})
+    n = 2 * kk.size
+    obs = dict(name='x', theory=theory, terms=[dict(scale=1., factors=[], table='power')], nin=n, wmatrix=None, offset=None, data=np.zeros(n))
+    specb = dict(params=names, priors={}, solved=[], observables=[obs], precision=[np.ones(n)])
+    Xb = np.column_stack([rng.uniform(0.95, 1.05, 32), rng.uniform(0.95, 1.05, 32), rng.uniform(1.5, 2.5, 32), rng.uniform(0.8, 1.2, 32), rng.uniform(2., 8., 32),
+                          rng.uniform(2., 8., 32), rng.uniform(2., 8., 32)])
+    planb = desilike_b200.Plan(specb)
+    refb = pipeline.evaluate(specb, Xb, return_theory=True)
+    assert np.max(np.abs(planb.theory(Xb) - refb['flattheory'])) < 1e-10 * np.max(np.abs(refb['flattheory']))
+    planb.close()

@@ -151,6 +151,28 @@ def test_unknown_operation_fails_loudly(tmp_path):
         emu.to_calculator().theory_spec()
 
 
+def test_lpt_table_model_mlp_emulated():
+    """The same table model behind an MLP emulator of pktable: table slices selected by index from the network output, re-interpolation as a linear
+    map after the selection; lowered plan (NumPy mirror) == oracle pipeline == direct restatement (MLP predict -> combine -> interp1d)."""
+    import lowered_numpy
+    import lpt_helpers
+    from test_capi_and_lowering import _mlp_features
+    from desilike_b200.lowering import Lowered
+    like, info = lpt_helpers.make_lpt_likelihood(marg=True, engine='mlp')
+    spec = like._finalize_spec(like.build_spec())
+    low = Lowered(spec)
+    rng = np.random.default_rng(3)
+    X = np.column_stack([rng.uniform(0.95, 1.05, 6), rng.uniform(0.95, 1.05, 6), rng.uniform(-0.05, 0.05, 6), rng.uniform(0.9, 1.1, 6),
+                         rng.uniform(1.5, 2.2, 6), rng.uniform(-1., 1., 6), rng.uniform(-1., 1., 6)])
+    direct = lpt_helpers.direct_theory(info, X, spec['params'])
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    assert np.max(np.abs(ref['flattheory'] - direct)) < 1e-11 * np.max(np.abs(direct))
+    theory = lowered_numpy.evaluate(low, X, feature_fn=_mlp_features, white=False)
+    assert np.max(np.abs(theory - direct)) < 1e-11 * np.max(np.abs(direct))
+    got = lowered_numpy.evaluate(low, X, feature_fn=_mlp_features)
+    assert np.allclose(got['logposterior'], ref['logposterior'], rtol=1e-9, atol=1e-7)
+
+
 @pytest.mark.parametrize('marg', [False, True])
 def test_lpt_velocileptors_table_model_lowering(marg):
     """Velocileptors-style table model (reference full_shape.py:1182-1186, :1295-1313) behind a Taylor emulator of pktable: the lowered plan
