@@ -935,6 +935,14 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
 
 static const long long MAX_CHUNK = 1LL << 20;
 
+// Points per pass of the batched entry points: at most 2^20, fewer when the per-point workspace (feature rows of wide MLP emulators,
+// Gram partials, transformed theory vectors) would exceed ~16 GiB -- the workspace stays a small part of the 180 GB of HBM.
+static long long chunk_points(const dlb_plan* plan) {
+  const long long per_point = 8LL * ((long long)plan->fstride + std::max(plan->ptotal, 1LL) + plan->d + 4 + plan->ns + plan->tstride);
+  long long n = (16LL << 30) / std::max(per_point, 1LL) / ROW_ALIGN * ROW_ALIGN;
+  return std::max<long long>(ROW_ALIGN * 32, std::min(MAX_CHUNK, n));
+}
+
 int dlb_eval_batch(dlb_plan* plan, const double* params, int64_t N, double* logposterior, double* loglikelihood, double* logprior,
                    double* x_solved, int32_t* status, void* stream_) {
   return dlb_eval_batch_hessian(plan, params, N, logposterior, loglikelihood, logprior, x_solved, nullptr, status, stream_);
@@ -956,8 +964,9 @@ int dlb_eval_batch_hessian(dlb_plan* plan, const double* params, int64_t N, doub
   bool any_host = !in_dev || (logposterior && !lp_dev) || (loglikelihood && !ll_dev) || (logprior && !pr_dev) || (x_solved && !xs_dev) || (status && !st_dev) ||
                   (hessian && !hs_dev);
   const int ns = plan->ns;
-  for (long long start = 0; start < N; start += MAX_CHUNK) {
-    const long long n = std::min<long long>(MAX_CHUNK, N - start);
+  const long long CHUNK = chunk_points(plan);
+  for (long long start = 0; start < N; start += CHUNK) {
+    const long long n = std::min<long long>(CHUNK, N - start);
     const long long npad = (n + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
     int rc = ensure_workspace(plan, npad);
     if (rc) return rc;
@@ -1036,7 +1045,7 @@ int dlb_eval_batch_hessian(dlb_plan* plan, const double* params, int64_t N, doub
       DLB_CUDA(cudaEventRecord(plan->ev_pipe[9], s_out));
       DLB_CUDA(cudaStreamWaitEvent(stream, plan->ev_pipe[9], 0));
     }
-    if (any_host || plan->timing || start + MAX_CHUNK < N) DLB_CUDA(cudaStreamSynchronize(stream));
+    if (any_host || plan->timing || start + CHUNK < N) DLB_CUDA(cudaStreamSynchronize(stream));
     if (plan->timing) {
       float a = 0, b = 0, c = 0;
       cudaEventElapsedTime(&a, plan->ev[0], plan->ev[1]);
