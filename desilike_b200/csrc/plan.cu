@@ -940,7 +940,9 @@ static const long long MAX_CHUNK = 1LL << 20;
 static long long chunk_points(const dlb_plan* plan) {
   const long long per_point = 8LL * ((long long)plan->fstride + std::max(plan->ptotal, 1LL) + plan->d + 4 + plan->ns + plan->tstride);
   long long n = (16LL << 30) / std::max(per_point, 1LL) / ROW_ALIGN * ROW_ALIGN;
-  return std::max<long long>(ROW_ALIGN * 32, std::min(MAX_CHUNK, n));
+  n = std::max<long long>(ROW_ALIGN * 32, std::min(MAX_CHUNK, n));
+  if (const char* e = getenv("DLB_MAX_CHUNK")) n = std::max<long long>(ROW_ALIGN, std::min(n, atoll(e) / ROW_ALIGN * ROW_ALIGN));   // tests: force several passes
+  return n;
 }
 
 int dlb_eval_batch(dlb_plan* plan, const double* params, int64_t N, double* logposterior, double* loglikelihood, double* logprior,

@@ -239,3 +239,22 @@ def test_rank_reduced_plan_matches_full_plan(gpu_required):
     got = plan.eval(X[:200])
     assert np.max(np.abs(got['loglikelihood'] - ref['loglikelihood']) / np.maximum(1., np.abs(ref['loglikelihood']))) < 1e-10
     plan.close()
+
+
+def test_multi_pass_batches(gpu_required, monkeypatch):
+    """Batches larger than one pass of the entry point (2^20 points, or fewer when the per-point workspace is large) are evaluated in several
+    passes over the same workspace: forced here with a small pass size; host and device buffers, ragged last pass, solved parameters."""
+    import torch
+    import desilike_b200
+    spec = configs.config_c5(ntracers=2, nkin=40, nbins=10, order=2, solved=True)
+    plan = desilike_b200.Plan(spec)
+    X = configs.sample_points(spec, 5000, seed=41)
+    one = plan.eval(X)
+    monkeypatch.setenv('DLB_MAX_CHUNK', '1536')
+    many = plan.eval(X)
+    dev = plan.eval(torch.as_tensor(X, device='cuda'))
+    torch.cuda.synchronize()
+    for key in ['logposterior', 'loglikelihood', 'logprior', 'x_solved', 'status']:
+        assert np.array_equal(one[key], many[key]), key
+        assert np.array_equal(one[key], dev[key].cpu().numpy()), key
+    plan.close()
