@@ -328,7 +328,7 @@ def config_c3(seed=3, ns_theory=33, broadband_solved=True):
     return spec
 
 
-def config_kaiser_window(seed=7, nkin=60, nbins=12, eftlike=False, solved=True, transform=None, nmu=8):
+def config_kaiser_window(seed=7, nkin=60, nbins=12, eftlike=False, solved=True, transform=None, nmu=8, systematic=False):
     """Direct (non-emulated) Kaiser + ShapeFit -> window -> chi2, optionally with EFT-like ct/sn terms (solved or sampled).
     Mirrors what reference classes KaiserTracerPowerSpectrumMultipoles / EFTLikeKaiserTracerPowerSpectrumMultipoles +
     WindowedPowerSpectrumMultipoles (ndarray wmatrix branch, reference window.py:309-323) compute; used to pin the oracle."""
@@ -361,9 +361,17 @@ def config_kaiser_window(seed=7, nkin=60, nbins=12, eftlike=False, solved=True, 
     offset = W.dot(np.repeat(shotnoisein, nkin)) - shotnoiseout
     obs = dict(name='LRG', theory=theory, terms=terms, nin=len(ells) * nkin, wmatrix=W, offset=offset, transform=transform,
                kout=kout, wmatrix_raw=W, shotnoise=shotnoise)
+    if systematic:   # two systematic templates (reference window.py:470-473, :1253-1287): syst_0 sampled, syst_1 analytically marginalised
+        t0 = np.concatenate([(ell == 0) * 3e3 * np.exp(-kout / 0.05) for ell in ells])
+        t1 = np.concatenate([(ell == 2) * 1e3 * (kout / 0.1)**-1 for ell in ells])
+        terms += [dict(scale=1., factors=[('syst_0', 1)], table=None, outvec=t0), dict(scale=1., factors=[], solved='syst_1', table=None, outvec=t1)]
+        params.append('syst_0')
+        solved_list.append(dict(name='syst_1', value=0., prior=dict(dist='norm', loc=0., scale=3.), marg=True))
+        obs['systematic_templates'] = [t0, t1]
     spec = dict(params=params, observables=[obs], solved=solved_list)
-    fidv = dict(_FID, ct0_2=0., ct2_2=0., ct4_2=0., sn0_2=0., sn2_2=0., sn4_2=0.)
+    fidv = dict(_FID, ct0_2=0., ct2_2=0., ct4_2=0., sn0_2=0., sn2_2=0., sn4_2=0., syst_0=0.)
     spec = _finish(spec, [(kout, ells, nd)], rng, fidv)
+    if systematic: spec['priors']['syst_0'] = dict(dist='uniform', limits=(-2., 2.))
     for n in params:
         if n.startswith('ct') or (n.startswith('sn') and n != 'sn0'):
             spec['priors'][n] = dict(dist='norm', loc=0., scale=10.)

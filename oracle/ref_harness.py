@@ -70,6 +70,7 @@ def reference_kaiser_likelihood(spec, eftlike=False, solved_mode=None):
         kw = dict(wmatrix=np.asarray(obs['wmatrix_raw']), kin=th['k'], ellsin=th['ells'], k=[kout] * nell, ells=th['ells'], shotnoise=obs.get('shotnoise'))
     else:
         kw = dict(k=[th['k']] * nell, ells=th['ells'])
+    if obs.get('systematic_templates') is not None: kw['systematic_templates'] = [np.asarray(t) for t in obs['systematic_templates']]
     observable = TracerPowerSpectrumMultipolesObservable(data=np.asarray(obs['data']), theory=theory, transform=obs.get('transform'), **kw)
     precision = spec['precision'][0] if isinstance(spec['precision'], (list, tuple)) else spec['precision']
     likelihood = ObservablesGaussianLikelihood(observables=[observable], precision=np.array(precision))

@@ -24,6 +24,7 @@ CASES = {
     'eftlike_marg': dict(config='config_kaiser_window', kwargs=dict(eftlike=True, solved=True), eftlike=True, mode='.marg', n=48, seed=104),
     'eftlike_best': dict(config='config_kaiser_window', kwargs=dict(eftlike=True, solved=True), eftlike=True, mode='.best', n=48, seed=105),
     'eftlike_prec': dict(config='config_kaiser_window', kwargs=dict(eftlike=True, solved=True), eftlike=True, mode='.prec', n=48, seed=109),
+    'kaiser_window_syst': dict(config='config_kaiser_window', kwargs=dict(eftlike=False, solved=False, systematic=True), eftlike=False, mode='.marg', n=32, seed=111),
     'kaiser_window_cubic': dict(config='config_kaiser_window', kwargs=dict(eftlike=False, solved=False, transform='cubic'), eftlike=False, mode=None, n=32, seed=106),
 }
 
