@@ -94,7 +94,32 @@ def lpt_combine():
     print('lpt_combine', table.shape, power.shape)
 
 
+def xi_window():
+    """Method-level fixture: the reference's ``WindowedCorrelationFunctionMultipoles._apply`` (window.py:717-728) called on an instance carrying
+    only the constants it reads (matrix_diag, matrix_full, offset, smask), for the two combinations the mirror class folds."""
+    ref_harness.setup()
+    from desilike.observables.galaxy_clustering.window import WindowedCorrelationFunctionMultipoles
+    rng = np.random.default_rng(112)
+    sin = np.arange(20., 152., 4.)
+    ns = sin.size
+    s0, s1 = sin[:-2], sin[3:]
+    smask = np.concatenate([np.searchsorted(sin, s0), ns + np.searchsorted(sin, s1)])
+    nout = smask.size
+    matrix_diag = np.array([[np.ones(ns) - 0.02, 0.01 * np.ones(ns)], [0.03 * sin / 100., np.ones(ns) * 0.97]])
+    theory = rng.standard_normal((4, 2, ns))
+    out = {}
+    for name, (mf, off, mask) in {'diag': (None, 1e-4 * rng.standard_normal(2 * ns), smask), 'full': (rng.standard_normal((nout, 2 * ns)), 1e-4 * rng.standard_normal(nout), None)}.items():
+        w = object.__new__(WindowedCorrelationFunctionMultipoles)
+        for key, value in dict(matrix_diag=matrix_diag, matrix_full=mf, offset=off, smask=mask).items(): object.__setattr__(w, key, value)
+        out['out_' + name] = np.array([np.asarray(WindowedCorrelationFunctionMultipoles._apply(w, th)) for th in theory])
+        out['offset_' + name] = off
+        if mf is not None: out['matrix_full'] = mf
+    np.savez_compressed(os.path.join(HERE, 'xi_window.npz'), case=json.dumps(dict(kind='xi_window')), sin=sin, s0=s0, s1=s1, matrix_diag=matrix_diag, theory=theory, **out)
+    print('xi_window', out['out_diag'].shape, out['out_full'].shape)
+
+
 if __name__ == '__main__':
+    xi_window()
     lpt_combine()
     bao_theory()
     main()

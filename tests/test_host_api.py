@@ -244,28 +244,23 @@ def test_systematic_templates_lowering():
 
 def test_correlation_window_constants_fold():
     """``WindowedCorrelationFunctionMultipoles._apply`` (reference window.py:717-728): matrix_diag (per-s multipole mixing), matrix_full, offset and
-    the s mask fold into ONE matrix + offset of the observable spec."""
-    rng = np.random.default_rng(8)
+    the s mask fold into ONE matrix + offset of the observable spec; checked against the outputs of the reference's own method
+    (tests/golden/xi_window.npz, generated by tests/golden/make_golden.py:xi_window)."""
+    data = np.load(os.path.join(HERE, 'golden', 'xi_window.npz'))
     template = dl.BAOPowerSpectrumTemplate(pk_dd_fid=synthetic.pk_fid, pknow_dd_fid=synthetic.pknow_fid, f_fid=synthetic.F_FID, rs_drag=synthetic.RS_DRAG)
     theory = dl.DampedBAOWigglesTracerCorrelationFunctionMultipoles(template=template, ells=(0, 2))
-    sin = np.arange(20., 152., 4.)
-    s = [sin[:-2], sin[3:]]   # union = sin (reference window.py:640-649: sin = unique of the output separations when no wmatrix is given)
-    nout, ns = sum(len(ss) for ss in s), sin.size
-    matrix_diag = np.array([[np.ones(ns) - 0.02, 0.01 * np.ones(ns)], [0.03 * sin / 100., np.ones(ns) * 0.97]])
-    offset_full = 1e-4 * rng.standard_normal(2 * ns)
-    obs = dl.TracerCorrelationFunctionMultipolesObservable(data=np.zeros(nout), s=s, ells=(0, 2), theory=theory, matrix_diag=matrix_diag, offset=offset_full)
+    sin, s = data['sin'], [data['s0'], data['s1']]
+    nout = sum(len(ss) for ss in s)
+    obs = dl.TracerCorrelationFunctionMultipolesObservable(data=np.zeros(nout), s=s, ells=(0, 2), theory=theory, matrix_diag=data['matrix_diag'], offset=data['offset_diag'])
     ospec = obs.observable_spec()
-    th = rng.standard_normal((2, ns))
-    # reference _apply, line by line
-    ref = np.sum(matrix_diag * th[None, ...], axis=1).ravel() + offset_full
-    ref = ref[obs.smask]
-    assert np.allclose(ospec['wmatrix'] @ th.ravel() + ospec['offset'], ref, rtol=1e-14, atol=1e-14)
-    wm = rng.standard_normal((nout, 2 * ns))
-    obs = dl.TracerCorrelationFunctionMultipolesObservable(data=np.zeros(nout), s=s, ells=(0, 2), theory=theory, wmatrix=wm, sin=sin, matrix_diag=matrix_diag,
-                                                           offset=1e-4 * np.ones(nout))
+    for th, ref in zip(data['theory'], data['out_diag']):
+        assert np.allclose(ospec['wmatrix'] @ th.ravel() + ospec['offset'], ref, rtol=1e-14, atol=1e-14)
+    obs = dl.TracerCorrelationFunctionMultipolesObservable(data=np.zeros(nout), s=s, ells=(0, 2), theory=theory, wmatrix=data['matrix_full'], sin=sin,
+                                                           matrix_diag=data['matrix_diag'], offset=data['offset_full'])
     ospec = obs.observable_spec()
-    ref = wm.dot(np.sum(matrix_diag * th[None, ...], axis=1).ravel()) + 1e-4
-    assert np.allclose(ospec['wmatrix'] @ th.ravel() + ospec['offset'], ref, rtol=1e-13, atol=1e-13)
+    for th, ref in zip(data['theory'], data['out_full']):
+        assert np.allclose(ospec['wmatrix'] @ th.ravel() + ospec['offset'], ref, rtol=1e-13, atol=1e-13)
+
 
 
 def test_generic_table_bias_model():
