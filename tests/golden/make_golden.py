@@ -94,6 +94,39 @@ def lpt_combine():
     print('lpt_combine', table.shape, power.shape)
 
 
+def covariance_corrections():
+    """Likelihood-level fixture: the reference's ObservablesGaussianLikelihood built from a COVARIANCE with ``scale_covariance`` and the
+    Hartlap 2007 / Percival 2014 corrections (likelihoods/base.py:605-656) on the EFT-like marginalised configuration."""
+    ref_harness.setup()
+    from desilike.theories.galaxy_clustering import ShapeFitPowerSpectrumTemplate, EFTLikeKaiserTracerPowerSpectrumMultipoles
+    from desilike.observables.galaxy_clustering import TracerPowerSpectrumMultipolesObservable
+    from desilike.likelihoods import ObservablesGaussianLikelihood
+    spec = configs.config_kaiser_window(eftlike=True, solved=True)
+    obs = spec['observables'][0]
+    th = obs['theory']
+    template = ShapeFitPowerSpectrumTemplate(z=1., a=th['template']['a'], kp=th['template']['kp'], apmode=th['template']['apmode'])
+    theory = EFTLikeKaiserTracerPowerSpectrumMultipoles(template=template, mu=th['nmu'])
+    nell = len(th['ells'])
+    observable = TracerPowerSpectrumMultipolesObservable(data=np.asarray(obs['data']), theory=theory, wmatrix=np.asarray(obs['wmatrix_raw']), kin=th['k'], ellsin=th['ells'],
+                                                         k=[obs['kout']] * nell, ells=th['ells'], shotnoise=obs.get('shotnoise'))
+    cov = np.linalg.inv(spec['precision'][0])
+    nobs, scale = 400, 1.3
+    like = ObservablesGaussianLikelihood(observables=[observable], covariance=cov, scale_covariance=scale, correct_covariance={'nobs': nobs, 'correction': 'hartlap-percival2014'})
+    for param in like.all_params:
+        name = param.name
+        if name in spec['params']: param.update(fixed=False, prior=dict(spec['priors'][name]) if spec['priors'].get(name) else None)
+        elif any(s_['name'] == name for s_ in spec['solved']):
+            s_ = [s_ for s_ in spec['solved'] if s_['name'] == name][0]
+            param.update(fixed=False, value=s_['value'], prior=dict(s_['prior']), derived='.marg')
+        elif not param.derived: param.update(fixed=True)
+    ref_harness.install_jacfwd_stub()
+    X = configs.sample_points(spec, 16, seed=113)
+    ref = ref_harness.run_vmap(like, spec, X)
+    np.savez_compressed(os.path.join(HERE, 'covariance_corrections.npz'), case=json.dumps(dict(kind='covariance_corrections', nobs=nobs, scale_covariance=scale)), X=X,
+                        covariance=cov, hartlap2007_factor=like.hartlap2007_factor, percival2014_factor=like.percival2014_factor, precision=np.array(like.precision), **ref)
+    print('covariance_corrections', like.hartlap2007_factor, like.percival2014_factor)
+
+
 def xi_window():
     """Method-level fixture: the reference's ``WindowedCorrelationFunctionMultipoles._apply`` (window.py:717-728) called on an instance carrying
     only the constants it reads (matrix_diag, matrix_full, offset, smask), for the two combinations the mirror class folds."""
@@ -119,6 +152,7 @@ def xi_window():
 
 
 if __name__ == '__main__':
+    covariance_corrections()
     xi_window()
     lpt_combine()
     bao_theory()

@@ -285,3 +285,26 @@ def test_generic_table_bias_model():
     direct = core.interp1d_cubic(info['k'], info['kpt'], (b1**2 * pktable[..., 0] + b1 * pktable[..., 1] + pktable[..., 2] + 0.5 * c0 * pktable[..., 3]).T).T.ravel()
     got = b1**2 * tabs['pktable_0'][0] + b1 * tabs['pktable_1'][0] + tabs['pktable_2'][0] + 0.5 * c0 * tabs['pktable_3'][0]
     assert np.allclose(got, direct, rtol=1e-12, atol=1e-8)
+
+
+def test_covariance_corrections_match_reference():
+    """ObservablesGaussianLikelihood from a covariance with scale_covariance and the Hartlap 2007 / Percival 2014 factors (reference
+    likelihoods/base.py:605-656): factors, precision and log-posterior against the reference's own run (tests/golden/covariance_corrections.npz)."""
+    data = np.load(os.path.join(HERE, 'golden', 'covariance_corrections.npz'))
+    case = json.loads(str(data['case']))
+    spec = configs.config_kaiser_window(eftlike=True, solved=True)
+    like = make_kaiser_likelihood(spec, eftlike=True, mode='.marg')
+    obs = like.observables[0]
+    like = dl.ObservablesGaussianLikelihood(observables=[obs], covariance=data['covariance'], scale_covariance=case['scale_covariance'],
+                                            correct_covariance={'nobs': case['nobs'], 'correction': 'hartlap-percival2014'})
+    built = like._finalize_spec(like.build_spec())
+    assert np.isclose(like.hartlap2007_factor, float(data['hartlap2007_factor']), rtol=1e-14)
+    assert np.isclose(like.percival2014_factor, float(data['percival2014_factor']), rtol=1e-14)
+    P = built['precision'][0] if isinstance(built['precision'], list) else built['precision']
+    assert np.allclose(P, data['precision'], rtol=1e-9, atol=1e-9 * np.max(np.abs(data['precision'])))
+    got = pipeline.evaluate(built, data['X'])
+    for key in ['logposterior', 'loglikelihood', 'logprior']:
+        ref = data[key]
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isneginf(ref), np.isneginf(got[key]))
+        assert np.allclose(got[key][fin], ref[fin], rtol=1e-10, atol=1e-8), key
