@@ -202,8 +202,7 @@ class SumLikelihood(BaseLikelihood):
             sub = dict(spec, observables=spec['observables'][offset:offset + nobs])
             sub = like._finalize_spec(sub)
             if not isinstance(sub['precision'], list):
-                if nobs > 1: raise NotImplementedError('SumLikelihood members with a joint precision over several observables')
-                precisions.append(sub['precision'])
+                precisions.append(sub['precision'])   # one block for the member (joint over its observables)
             else:
                 precisions += list(sub['precision'])
             offset += nobs

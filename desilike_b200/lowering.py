@@ -139,8 +139,16 @@ class Lowered(object):
         # ---- blocks ----
         prec = spec['precision']
         observables = spec['observables']
-        if isinstance(prec, (list, tuple)):
-            groups = [([obs], np.asarray(p, dtype=np.float64)) for obs, p in zip(observables, prec)]
+        if isinstance(prec, (list, tuple)):   # one block per run of consecutive observables (usually one observable each; a SumLikelihood
+            groups, io = [], 0                # member with a joint covariance over several observables gives one block for all of them)
+            for p in prec:
+                p = np.asarray(p, dtype=np.float64)
+                group, size = [], 0
+                while size < p.shape[0] and io < len(observables):
+                    group.append(observables[io]); size += len(observables[io]['data']); io += 1
+                if size != p.shape[0]: raise LoweringError('precision block of size {:d} does not match a run of observables'.format(p.shape[0]))
+                groups.append((group, p))
+            if io != len(observables): raise LoweringError('precision blocks do not cover all observables')
         else:
             groups = [(list(observables), np.asarray(prec, dtype=np.float64))]
         self.blocks = []

@@ -184,7 +184,7 @@ def premarginalize_precision(spec):
     sizes = [len(obs['data']) for obs in spec['observables']]
     precision = spec['precision']
     blocks = [np.asarray(p, dtype=np.float64) for p in precision] if isinstance(precision, (list, tuple)) else [np.asarray(precision, dtype=np.float64)]
-    bsizes = sizes if isinstance(precision, (list, tuple)) else [sum(sizes)]
+    bsizes = [P.shape[0] for P in blocks]   # a block covers one observable or a run of consecutive observables
     new_prec, start = [], 0
     for P, n in zip(blocks, bsizes):
         Jb = J[:, start:start + n]

@@ -115,11 +115,13 @@ def _precision_blocks(spec):
     """-> list of (slice over the joint data vector, precision block) -- one entry when the precision is joint."""
     sizes = [len(obs['data']) for obs in spec['observables']]
     prec = spec['precision']
-    if isinstance(prec, (list, tuple)):
+    if isinstance(prec, (list, tuple)):   # each block covers a run of consecutive observables (one, or several with a joint covariance)
         out, start = [], 0
-        for size, pb in zip(sizes, prec):
-            out.append((slice(start, start + size), np.asarray(pb, dtype='f8')))
-            start += size
+        for pb in prec:
+            pb = np.asarray(pb, dtype='f8')
+            out.append((slice(start, start + pb.shape[0]), pb))
+            start += pb.shape[0]
+        assert start == sum(sizes), 'precision blocks do not cover the data vector'
         return out
     return [(slice(0, sum(sizes)), np.asarray(prec, dtype='f8'))]
 

@@ -196,3 +196,28 @@ def test_torch_custom_op_registered_with_fake_impl():
     with pytest.raises(Exception):
         torch.ops.desilike_b200.eval_batch(pid, torch.empty((17, 5), dtype=torch.float64, device='meta'))
     torch_ops.unregister_plan(pid)
+
+
+def test_precision_blocks_over_runs_of_observables():
+    """A precision list whose blocks cover RUNS of consecutive observables (a SumLikelihood member with a joint covariance over two
+    observables + a single-observable member): lowering (NumPy mirror) == oracle == the equivalent dense joint precision."""
+    from desilike_b200.lowering import Lowered, LoweringError
+    spec = configs.config_c5(ntracers=3, nkin=40, nbins=10, order=2, solved=True)
+    P = spec['precision']
+    n01 = P[0].shape[0] + P[1].shape[0]
+    joint = np.zeros((n01, n01)); joint[:P[0].shape[0], :P[0].shape[0]] = P[0]; joint[P[0].shape[0]:, P[0].shape[0]:] = P[1]
+    v = np.random.default_rng(6).standard_normal(n01) * np.sqrt(np.diag(joint)) * 0.1
+    joint += np.outer(v, v)   # couples observables 0 and 1
+    runs = dict(spec, precision=[joint, P[2]])
+    n = n01 + P[2].shape[0]
+    dense = np.zeros((n, n)); dense[:n01, :n01] = joint; dense[n01:, n01:] = P[2]
+    X = configs.sample_points(spec, 9, seed=7)
+    ref_runs, ref_dense = pipeline.evaluate(runs, X), pipeline.evaluate(dict(spec, precision=dense), X)
+    assert np.allclose(ref_runs['logposterior'], ref_dense['logposterior'], rtol=1e-11, atol=1e-8)
+    low = Lowered(runs)
+    assert [b['ncols'] for b in low.blocks] == [n01, P[2].shape[0]]
+    got = lowered_numpy.evaluate(low, X)
+    assert np.allclose(got['logposterior'], ref_runs['logposterior'], rtol=1e-9, atol=1e-7)
+    assert np.allclose(got['x_solved'], ref_runs['x_solved'], rtol=1e-7, atol=1e-7)
+    with pytest.raises(LoweringError):
+        Lowered(dict(spec, precision=[joint[:-1, :-1], P[2]]))
