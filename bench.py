@@ -240,6 +240,7 @@ def run_ensemble(args):
             'gpu_launches': int(launches),
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
                          'kernel': 'dlb::contract_kernel inside the whole iteration (propose + likelihood + accept)', 'flops_per_eval_folded': flops,
+                         'flops_per_eval_executed': plan.executed_flops(), 'frac_executed': plan.executed_flops() * value / world / 1e12 / peak,
                          'peak_source': 'dlb_measure_fp64_peak(DMMA.8x8x4 register loop) measured in this run'}}
     if rank == 0: emit(line)
     if world > 1: dist.destroy_process_group()
