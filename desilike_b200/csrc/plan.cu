@@ -665,13 +665,20 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
         resident = false;
     }
   }
-  long long pad7 = 0, pad5 = 0;   // padded column totals with 112- and 80-column blocks
+  // Multiplied tile area (contraction rows x padded columns) with 112- and with 80-column blocks.  Rank-reduced blocks are lower
+  // triangular: column block cb only needs the rows >= cb * BN (the leading zero tiles are skipped), so narrower blocks also skip more.
+  long long area7 = 0, area5 = 0;
   for (int ib = 0; ib < desc->nblocks; ++ib) {
     const dlb_block_desc& bd = desc->blocks[ib];
     const int cols = (bd.ncols_white > 0 ? bd.ncols_white : bd.ncols) + bd.nconst;
-    pad7 += (cols + 111) / 112 * 112; pad5 += (cols + 79) / 80 * 80;
+    const bool reduced = bd.ncols_white > 0 && bd.ncols_white < bd.ncols;
+    long long rows = 0;
+    for (int t = 0; t < bd.nterms; ++t) rows += bd.terms[t].K;
+    for (int cb = 0; cb * 112 < cols; ++cb) area7 += std::max(0LL, reduced ? rows - (long long)cb * 112 : rows) * 112;
+    for (int cb = 0; cb * 80 < cols; ++cb) area5 += std::max(0LL, reduced ? rows - (long long)cb * 80 : rows) * 80;
   }
-  const Variant var = pick_variant(plan, max_slots, resident, resident ? ast : 0, desc->ncoef, npart_bound, maxK, pad5 * 10 < pad7 * 9);
+  const bool narrow = area5 * 100 < area7 * 93 || getenv("DLB_FORCE_NARROW");   // the 80-column variant is ~3-4 % less efficient per multiplied tile
+  const Variant var = pick_variant(plan, max_slots, resident, resident ? ast : 0, desc->ncoef, npart_bound, maxK, narrow);
   plan->resident = resident;
   if (resident) {   // factor lists of the monomials, one table per generator, indexed by segment column
     plan->d_paths.resize(desc->ngen, nullptr);
