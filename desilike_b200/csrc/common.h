@@ -148,6 +148,10 @@ __device__ __forceinline__ double fast_rcp(double y) {
 }
 #endif
 
+// Function attributes (opt-in dynamic shared memory) are per device: the "already configured" caches of the launchers are indexed by device
+// so that one process may drive several GPUs (one thread + one plan per GPU).
+inline int current_device_slot() { int dev = 0; cudaGetDevice(&dev); return dev & 63; }
+
 size_t contract_smem_limit(int ctas_per_sm);
 size_t contract_smem_bytes(const Variant& v, int nstages, bool resident, int ast, int dpad, int ncoef, int npart_max, int ngen);
 int launch_contract(const Variant& v, const ContractParams& p, int nsm, cudaStream_t stream);

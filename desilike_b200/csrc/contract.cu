@@ -519,7 +519,8 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
 
 template <int R, int MT, int NT, int WM, int CPS, int KC, bool RESIDENT>
 int launch_variant(const ContractParams& p, int grid, size_t smem, cudaStream_t stream) {
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[current_device_slot()];
   if (!configured) {
     DLB_CUDA(cudaFuncSetAttribute(contract_kernel<R, MT, NT, WM, CPS, KC, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)contract_smem_limit(CPS)));
     configured = true;

@@ -160,7 +160,8 @@ size_t mlp_fused_smem(const int* idata_host) {
 
 int launch_mlp_fused(const DevGen* d_gens, const int* d_mlp_index, int nmlp, size_t smem, const double* params, int d, long long N, long long npad,
                      double* F, int fstride, int nsm, cudaStream_t stream) {
-  static size_t configured = 0;
+  static size_t configured_dev[64] = {};
+  size_t& configured = configured_dev[current_device_slot()];
   if (smem > configured) {
     DLB_CUDA(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

@@ -377,7 +377,8 @@ int launch_solve(const SolveParams& p, cudaStream_t stream) {
     finish_nosolve_kernel<<<(unsigned)((p.N + threads - 1) / threads), threads, 0, stream>>>(p);
   } else if (p.gent && p.ncomp > 0 && p.comp_max <= SOLVE_NREG && !p.hess) {
     const size_t smem = (size_t)(SOLVE_NREG * SOLVE_NREG + SOLVE_NREG) * ST_THREADS * sizeof(double);
-    static bool configured = false;
+    static bool configured_dev[64] = {};
+    bool& configured = configured_dev[current_device_slot()];
     if (!configured) {
       DLB_CUDA(cudaFuncSetAttribute(finish_solve_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = true;
@@ -385,7 +386,8 @@ int launch_solve(const SolveParams& p, cudaStream_t stream) {
     finish_solve_thread_kernel<<<(unsigned)((p.N + ST_THREADS - 1) / ST_THREADS), ST_THREADS, smem, stream>>>(p);
   } else {
     const size_t smem = (size_t)SOLVE_WARPS * (p.ns * (p.ns + 1) + 4 * p.ns) * sizeof(double);
-    static size_t configured = 0;
+    static size_t configured_dev[64] = {};
+    size_t& configured = configured_dev[current_device_slot()];
     if (smem > 48 * 1024 && smem > configured) {
       DLB_CUDA(cudaFuncSetAttribute(finish_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;

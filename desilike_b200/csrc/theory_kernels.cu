@@ -617,7 +617,8 @@ int launch_theory_features(const DevGen& g, const double* params, int d, long lo
     int L = 1;
     while (L * 32 < nt - 2) L *= 2;
     const size_t smem = (size_t)KAISER_WARPS * (2 * nt + nt / L + 2) * sizeof(double);
-    static size_t configured = 0;
+    static size_t configured_dev[64] = {};
+    size_t& configured = configured_dev[current_device_slot()];
     if (smem > 48 * 1024 && smem > configured) {
       DLB_CUDA(cudaFuncSetAttribute(kaiser_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
@@ -635,7 +636,8 @@ int launch_theory_features(const DevGen& g, const double* params, int d, long lo
       const int Np = g.aux[5], nkin = g.aux[2], nell = g.aux[3];
       if (Np != 2 * FFT_M) { set_error("FFTLog kernel is specialised for the reference's 2048-point grid padded to 4096"); return DLB_ERR_UNSUPPORTED; }
       const size_t smem = (size_t)FFT_SMEM_COMPLEX * sizeof(double2) + (size_t)((nkin + 1) & ~1) * sizeof(double);
-      static size_t configured = 0;
+      static size_t configured_dev[64] = {};
+      size_t& configured = configured_dev[current_device_slot()];
       if (smem > 48 * 1024 && smem > configured) {
         DLB_CUDA(cudaFuncSetAttribute(fftlog_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
