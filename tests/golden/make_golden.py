@@ -70,6 +70,15 @@ def bao_theory():
     np.savez_compressed(os.path.join(HERE, 'bao_theory.npz'), case=json.dumps(dict(kind='bao_theory')), X=X, k=k, s=s, power=power, corr=corr,
                         k_template_pk=np.array(pk.template.k), k_template_xi=np.array(xi.template.k))
     print('bao_theory', power.shape, corr.shape)
+    # broadband terms (reference bao.py:467-476, :527-534 power law in k / kp; :849-853, :867, :905 in s / sp)
+    rng = np.random.default_rng(114)
+    bb_pk, bb_xi = ['al0_-1', 'al0_0', 'al2_1', 'al2_-3'], ['al0_0', 'al0_2', 'al2_-2', 'al2_1']
+    A_pk, A_xi = rng.uniform(-50., 50., (X.shape[0], len(bb_pk))), rng.uniform(-1e-3, 1e-3, (X.shape[0], len(bb_xi)))
+    power_bb = np.array([pk(**dict(zip(names, x)), **dict(zip(bb_pk, a))) for x, a in zip(X, A_pk)])
+    corr_bb = np.array([xi(**dict(zip(names, x)), **dict(zip(bb_xi, a))) for x, a in zip(X, A_xi)])
+    np.savez_compressed(os.path.join(HERE, 'bao_broadband.npz'), case=json.dumps(dict(kind='bao_broadband', bb_pk=bb_pk, bb_xi=bb_xi)), X=X, k=k, s=s,
+                        A_pk=A_pk, A_xi=A_xi, power=power_bb, corr=corr_bb, kp=float(pk.kp), sp=float(xi.sp))
+    print('bao_broadband', power_bb.shape, corr_bb.shape, float(pk.kp), float(xi.sp))
 
 
 def lpt_combine():

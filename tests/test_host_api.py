@@ -308,3 +308,27 @@ def test_covariance_corrections_match_reference():
         fin = np.isfinite(ref)
         assert np.array_equal(np.isneginf(ref), np.isneginf(got[key]))
         assert np.allclose(got[key][fin], ref[fin], rtol=1e-10, atol=1e-8), key
+
+
+def test_bao_broadband_terms_match_reference_classes():
+    """Broadband terms of the damped-BAO tracers (reference bao.py:467-476, :527-534: al{ell}_{pow} (k / kp)^pow; :849-853, :905: (s / sp)^pow) through
+    the mirror classes' spec (oracle evaluation) against the outputs of the reference's own classes (tests/golden/bao_broadband.npz)."""
+    data = np.load(os.path.join(HERE, 'golden', 'bao_broadband.npz'))
+    case = json.loads(str(data['case']))
+    names = ['qpar', 'qper', 'b1', 'dbeta', 'sigmas', 'sigmapar', 'sigmaper']
+    template = dl.BAOPowerSpectrumTemplate(pk_dd_fid=synthetic.pk_fid, pknow_dd_fid=synthetic.pknow_fid, f_fid=synthetic.F_FID, rs_drag=synthetic.RS_DRAG)
+    for which, cls, x, bb, A in [('power', dl.DampedBAOWigglesTracerPowerSpectrumMultipoles, data['k'], case['bb_pk'], data['A_pk']),
+                                 ('corr', dl.DampedBAOWigglesTracerCorrelationFunctionMultipoles, data['s'], case['bb_xi'], data['A_xi'])]:
+        theory = cls(template=template, ells=(0, 2), **({'k': x} if which == 'power' else {'s': x}))
+        assert np.isclose(theory.kp if which == 'power' else theory.sp, float(data['kp' if which == 'power' else 'sp']), rtol=1e-14)
+        for p in theory.all_params: p.update(fixed=p.basename not in names + bb)
+        params = names + bb
+        terms = []
+        for term in theory.terms():   # fixed broadband amplitudes (value 0) drop out, as in ObservablesGaussianLikelihood.build_spec
+            factors = [(n, pw) for n, pw in term.get('factors', []) if n in params]
+            if len(factors) == len(term.get('factors', [])): terms.append(dict(term, factors=factors))
+        obs = dict(theory=dict(theory.theory_spec(), params=names), terms=terms, nin=theory.nin, wmatrix=None, offset=None)
+        X = np.column_stack([data['X'], A])
+        got = pipeline.observable_flat(obs, X, params, {})
+        ref = data[which].reshape(len(X), -1)
+        assert np.max(np.abs(got - ref)) <= 1e-10 * np.max(np.abs(ref)), which
