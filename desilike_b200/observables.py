@@ -166,11 +166,42 @@ class TracerPowerSpectrumMultipolesObservable(BaseTwoPointObservable):
         return dict(name=self.name, nin=nin, wmatrix=W, offset=offset, transform=self.transform)
 
 
+def tophat_fiber_collisions_correlation(s, ells, ellsin=None, fs=1., Dfc=0., mu_range_cut=False):
+    """Top-hat fiber-collision kernels on correlation-function multipoles (Hahn et al. 2016; reference window.py:1192-1249): pairs with
+    transverse separation below ``Dfc``, i.e. |mu| > mu_min(s) = sqrt(1 - (Dfc / s)^2), are lost with probability ``fs``.  With
+    I[p] = int_{mu_min <= |mu| <= 1} p(mu) dmu:
+
+        kernel_uncorrelated[l, s] = -(2 l + 1) / 2 fs I[L_l],     kernel_correlated[l, l', s] = delta_ll' - (2 l + 1) / 2 fs I[L_l L_l']
+
+    (``mu_range_cut``: the correlated kernel divided by mu_min where mu_min > 0).  Plan-time constants: the observable feeds them to the
+    window as ``matrix_diag`` / ``offset``."""
+    from numpy.polynomial import Polynomial
+    from numpy.polynomial.legendre import leg2poly
+    s = np.asarray(s, dtype='f8')
+    ells = tuple(ells)
+    ellsin = ells if ellsin is None else tuple(ellsin)
+    mu_min = np.sqrt(np.clip(1. - (float(Dfc) / s)**2, 0., None))
+    leg = lambda ell: Polynomial(leg2poly([0.] * ell + [1.]))
+
+    def lost(poly):   # integral over mu_min <= |mu| <= 1
+        Q = poly.integ()
+        return Q(1.) - Q(mu_min) + Q(-mu_min) - Q(-1.)
+
+    uncorrelated = -np.array([(2 * lo + 1.) / 2. * fs * lost(leg(lo)) for lo in ells])
+    correlated = np.empty((len(ells), len(ellsin), s.size))
+    for io, lo in enumerate(ells):
+        for ii, li in enumerate(ellsin):
+            tmp = float(lo == li) - (2 * lo + 1.) / 2. * fs * lost(leg(lo) * leg(li))
+            if mu_range_cut: tmp = np.where(mu_min > 0., tmp / np.where(mu_min > 0., mu_min, 1.), tmp)
+            correlated[io, ii] = tmp
+    return correlated, uncorrelated
+
+
 class TracerCorrelationFunctionMultipolesObservable(BaseTwoPointObservable):
     _default_step = 5.
 
     def __init__(self, data=None, covariance=None, slim=None, s=None, ells=None, theory=None, transform=None, wmatrix=None, sin=None, ellsin=None,
-                 matrix_diag=None, offset=None, systematic_templates=None, name='correlation2poles'):
+                 matrix_diag=None, offset=None, fiber_collisions=None, systematic_templates=None, name='correlation2poles'):
         """``wmatrix`` [sum_ell ns_ell, nellin * nsin] (ndarray branch of reference window.py:651-676), ``matrix_diag`` [nell, nellin, nsin]
         (per-separation multipole mixing, e.g. the fiber-collision kernel :690-702) and ``offset`` are the constants of
         ``WindowedCorrelationFunctionMultipoles._apply`` (:717-728); all linear, folded into one matrix at plan time."""
@@ -191,6 +222,13 @@ class TracerCorrelationFunctionMultipolesObservable(BaseTwoPointObservable):
             self.matrix_full = np.array(wmatrix, dtype='f8')
             if self.matrix_full.shape != (sum(len(ss) for ss in self.s), len(self.ellsin) * self.sin.size):
                 raise ValueError('wmatrix must be of shape ({:d}, {:d})'.format(sum(len(ss) for ss in self.s), len(self.ellsin) * self.sin.size))
+        if fiber_collisions is not None:   # reference window.py:686-702 (no matrix_full): matrix_diag = kernel_correlated, offset = kernel_uncorrelated
+            if wmatrix is not None or matrix_diag is not None or offset is not None:
+                raise ValueError('fiber_collisions cannot be combined with wmatrix / matrix_diag / offset here: fold the kernels yourself')
+            fc = dict(fiber_collisions)
+            with_uncorrelated = fc.pop('with_uncorrelated', True)
+            matrix_diag, unc = tophat_fiber_collisions_correlation(self.sin, self.ells, ellsin=ellsin, **fc)
+            if with_uncorrelated: offset = unc.ravel()
         if matrix_diag is not None:
             self.matrix_diag = np.asarray(matrix_diag, dtype='f8')
             nout = len(self.ellsin) if self.matrix_full is not None else len(self.ells)

@@ -103,6 +103,31 @@ def lpt_combine():
     print('lpt_combine', table.shape, power.shape)
 
 
+def fiber_collisions():
+    """Class-level fixture: kernels of the reference's TopHatFiberCollisionsCorrelationFunctionMultipoles (window.py:1192-1249), instantiated
+    with a stub theory that only carries (s, ells)."""
+    ref_harness.setup()
+    from desilike.observables.galaxy_clustering.window import TopHatFiberCollisionsCorrelationFunctionMultipoles as Cls
+
+    class Theory(object):
+        s, ells = np.arange(2., 80., 3.), (0, 2, 4)
+
+        class init(object):
+            update = staticmethod(lambda **kw: None)
+
+        class runtime_info(object):
+            initialize = staticmethod(lambda: None)
+
+    out = {}
+    for name, kw in {'a': dict(fs=0.6, Dfc=3., mu_range_cut=False), 'b': dict(fs=0.35, Dfc=10., mu_range_cut=True)}.items():
+        fc = object.__new__(Cls)
+        Cls.initialize(fc, ells=(0, 2), theory=Theory(), **kw)
+        out['correlated_' + name], out['uncorrelated_' + name] = np.array(fc.kernel_correlated), np.array(fc.kernel_uncorrelated)
+    np.savez_compressed(os.path.join(HERE, 'fiber_collisions.npz'), case=json.dumps(dict(kind='fiber_collisions', a=dict(fs=0.6, Dfc=3., mu_range_cut=False), b=dict(fs=0.35, Dfc=10., mu_range_cut=True))),
+                        s=Theory.s, ells=np.array([0, 2]), ellsin=np.array(Theory.ells), **out)
+    print('fiber_collisions', out['correlated_a'].shape)
+
+
 def covariance_corrections():
     """Likelihood-level fixture: the reference's ObservablesGaussianLikelihood built from a COVARIANCE with ``scale_covariance`` and the
     Hartlap 2007 / Percival 2014 corrections (likelihoods/base.py:605-656) on the EFT-like marginalised configuration."""
@@ -161,6 +186,7 @@ def xi_window():
 
 
 if __name__ == '__main__':
+    fiber_collisions()
     covariance_corrections()
     xi_window()
     lpt_combine()

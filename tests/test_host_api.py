@@ -332,3 +332,22 @@ def test_bao_broadband_terms_match_reference_classes():
         got = pipeline.observable_flat(obs, X, params, {})
         ref = data[which].reshape(len(X), -1)
         assert np.max(np.abs(got - ref)) <= 1e-10 * np.max(np.abs(ref)), which
+
+
+def test_fiber_collision_kernels_match_reference_class():
+    """Top-hat fiber-collision kernels on xi multipoles against the reference's own class (tests/golden/fiber_collisions.npz; reference
+    window.py:1192-1249) and their folding into the observable spec (reference window.py:686-702, :717-728)."""
+    from desilike_b200.observables import tophat_fiber_collisions_correlation
+    data = np.load(os.path.join(HERE, 'golden', 'fiber_collisions.npz'))
+    case = json.loads(str(data['case']))
+    for n in 'ab':
+        corr, unc = tophat_fiber_collisions_correlation(data['s'], tuple(data['ells']), ellsin=tuple(data['ellsin']), **case[n])
+        assert np.allclose(corr, data['correlated_' + n], rtol=0., atol=1e-14) and np.allclose(unc, data['uncorrelated_' + n], rtol=0., atol=1e-14)
+    template = dl.BAOPowerSpectrumTemplate(pk_dd_fid=synthetic.pk_fid, pknow_dd_fid=synthetic.pknow_fid, f_fid=synthetic.F_FID, rs_drag=synthetic.RS_DRAG)
+    theory = dl.DampedBAOWigglesTracerCorrelationFunctionMultipoles(template=template, ells=(0, 2))
+    s = data['s'][6:]
+    obs = dl.TracerCorrelationFunctionMultipolesObservable(data=np.zeros(2 * s.size), s=[s, s], ells=(0, 2), theory=theory, fiber_collisions=dict(fs=0.6, Dfc=3.))
+    ospec = obs.observable_spec()
+    th = np.random.default_rng(0).standard_normal((2, s.size))
+    corr, unc = tophat_fiber_collisions_correlation(s, (0, 2), fs=0.6, Dfc=3.)
+    assert np.allclose(ospec['wmatrix'] @ th.ravel() + ospec['offset'], (np.sum(corr * th[None], axis=1) + unc).ravel(), rtol=1e-14, atol=1e-14)

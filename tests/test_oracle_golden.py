@@ -9,7 +9,7 @@ import pytest
 from oracle import configs, pipeline
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURES = sorted(f for f in glob.glob(os.path.join(HERE, 'golden', '*.npz')) if 'bao_theory' not in f and 'bao_broadband' not in f and 'lpt_combine' not in f and 'xi_window' not in f and 'covariance_corrections' not in f)
+FIXTURES = sorted(f for f in glob.glob(os.path.join(HERE, 'golden', '*.npz')) if 'bao_theory' not in f and 'bao_broadband' not in f and 'lpt_combine' not in f and 'xi_window' not in f and 'covariance_corrections' not in f and 'fiber_collisions' not in f)
 
 
 def load_case(fn):
