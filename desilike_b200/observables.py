@@ -94,7 +94,7 @@ class BaseTwoPointObservable(object):
 class TracerPowerSpectrumMultipolesObservable(BaseTwoPointObservable):
 
     def __init__(self, data=None, covariance=None, klim=None, k=None, ells=None, wmatrix=None, kin=None, kinrebin=1, kinlim=None, ellsin=None,
-                 theory=None, shotnoise=None, wshotnoise=None, transform=None, systematic_templates=None, name='spectrum2poles'):
+                 theory=None, shotnoise=None, wshotnoise=None, transform=None, systematic_templates=None, fiber_collisions=None, name='spectrum2poles'):
         from .theories import KaiserTracerPowerSpectrumMultipoles
         self.name, self.transform = name, transform
         if transform not in (None, 'cubic'): raise ValueError('transform must be one of [None, "cubic"]')
@@ -123,6 +123,18 @@ class TracerPowerSpectrumMultipolesObservable(BaseTwoPointObservable):
             self.matrix_full = matrix_full.dot(rebin.T)
         else:
             raise ValueError('only ndarray window matrices are supported on this path (file readers of pypower / lsstypes are out of scope)')
+        if fiber_collisions is not None:   # reference window.py:428-438: kernels on (kin, ellsin), folded into matrix_full / offset
+            fc = dict(fiber_collisions)
+            with_uncorrelated = fc.pop('with_uncorrelated', True)
+            corr, unc = tophat_fiber_collisions_power(self.kin, self.ellsin, **fc)
+            block = np.block([[corr[io, ii] for ii in range(corr.shape[1])] for io in range(corr.shape[0])])
+            if self.matrix_full is None:
+                if self.kmask is not None: raise ValueError('fiber_collisions without a window matrix needs the same k for every multipole')
+                if with_uncorrelated: self.offset = unc.ravel()
+                self.matrix_full = block
+            else:
+                if with_uncorrelated: self.offset = self.matrix_full.dot(unc.ravel())
+                self.matrix_full = self.matrix_full.dot(block)
         self.theory.set_k(self.kin, self.ellsin)
         # shot noise in / out (reference window.py:445-457)
         shotnoise = 0. if shotnoise is None else float(shotnoise)
@@ -164,6 +176,52 @@ class TracerPowerSpectrumMultipolesObservable(BaseTwoPointObservable):
         if self.offset is not None: offset = offset + self.offset
         offset = offset - self.shotnoiseout
         return dict(name=self.name, nin=nin, wmatrix=W, offset=offset, transform=self.transform)
+
+
+# Hahn et al. 2016 (arXiv:1609.01714, appendix): mixing polynomials H_{l l'}(r), l > l', ascending powers of r = min(k, q) / max(k, q)
+_FC_H = {(2, 0): [-1., 0., 1.], (4, 0): [3. / 4., 0., -5. / 2., 0., 7. / 4.], (4, 2): [0., 0., -1., 0., 1.],
+         (6, 0): [-5. / 8., 0., 35. / 8., 0., -63. / 8., 0., 33. / 8.], (6, 2): [0., 0., 7. / 4., 0., -9. / 2., 0., 11. / 4.], (6, 4): [0., 0., 0., 0., -1., 0., 1.]}
+
+
+def tophat_fiber_collisions_power(k, ells, kin=None, ellsin=None, fs=1., Dfc=0.):
+    """Top-hat fiber-collision kernels on power-spectrum multipoles (Hahn et al. 2016; reference window.py:967-1049).  With
+    W2D(x) = 2 J1(x) / x, output wavenumbers k, integration nodes q = kin (trapezoid weights w_q), r = min(k, q) / max(k, q):
+
+        kernel_uncorrelated[l, k]        = -(2 l + 1) L_l(0) fs (pi Dfc)^2 / k  W2D(k Dfc)
+        kernel_correlated[l, l', k, q]   = delta_ll' Interp(q -> k) - fs Dfc^2 / 2  F_ll'(k, q)  q w_q
+        F_ll  = min(q / k, 1) W2D(q Dfc) r^l
+        F_ll' = min(q / k, 1) W2D(q Dfc) (2 l + 1) / 2 H_{max(l,l') min(l,l')}(r)   where (l >= l' and k >= q) or (l <= l' and k <= q), else 0
+
+    -> (kernel_correlated [nell, nellin, nk, nq], kernel_uncorrelated [nell, nk]); plan-time constants folded into the window matrix / offset."""
+    from scipy import special
+    from numpy.polynomial import Polynomial
+    from numpy.polynomial.legendre import legval
+    k = np.asarray(k, dtype='f8')
+    q = k if kin is None else np.asarray(kin, dtype='f8')
+    ells = tuple(ells)
+    ellsin = ells if ellsin is None else tuple(ellsin)
+    w2d = lambda x: 2. * special.j1(x) / x
+    leg0 = np.array([legval(0., [0.] * ell + [1.]) for ell in ells])
+    uncorrelated = -((2. * np.array(ells) + 1.) * leg0)[:, None] * fs * (np.pi * Dfc)**2 / k * w2d(k * Dfc)
+    wq = np.empty_like(q)   # trapezoid weights
+    if q.size > 2:
+        wq[1:-1] = (q[2:] - q[:-2]) / 2.; wq[0] = (q[1] - q[0]) / 2.; wq[-1] = (q[-1] - q[-2]) / 2.
+    elif q.size == 2: wq[:] = (q[1] - q[0]) / 2.
+    else: wq[:] = 1.
+    K, Q = np.meshgrid(k, q, indexing='ij')
+    ratio = np.minimum(K, Q) / np.maximum(K, Q)
+    common = np.minimum(Q / K, 1.) * w2d(Q * Dfc)
+    interp = matrix_lininterp(q, k).T
+    correlated = np.empty((len(ells), len(ellsin), k.size, q.size))
+    for io, lo in enumerate(ells):
+        for ii, li in enumerate(ellsin):
+            if lo == li:
+                F = common * ratio**lo
+            else:
+                F = common * (2. * lo + 1.) / 2. * Polynomial(_FC_H[(max(lo, li), min(lo, li))])(ratio)
+                F = np.where((K >= Q) if lo > li else (K <= Q), F, 0.)
+            correlated[io, ii] = float(lo == li) * interp - fs * Dfc**2 / 2. * F * q * wq
+    return correlated, uncorrelated
 
 
 def tophat_fiber_collisions_correlation(s, ells, ellsin=None, fs=1., Dfc=0., mu_range_cut=False):

@@ -123,6 +123,21 @@ def fiber_collisions():
         fc = object.__new__(Cls)
         Cls.initialize(fc, ells=(0, 2), theory=Theory(), **kw)
         out['correlated_' + name], out['uncorrelated_' + name] = np.array(fc.kernel_correlated), np.array(fc.kernel_uncorrelated)
+    from desilike.observables.galaxy_clustering.window import TopHatFiberCollisionsPowerSpectrumMultipoles as ClsP
+
+    class TheoryP(object):
+        k, ells = np.linspace(0.005, 0.4, 60), (0, 2, 4)
+
+        class runtime_info(object):
+            initialize = staticmethod(lambda: None)
+
+    # the reference's utils.weights_trapz (utils.py:614-622) relies on jax.numpy.insert clipping the out-of-range index len(x) - 1 (NumPy raises):
+    # shim it with the jax semantics (the last weight is appended) so that the reference class runs unmodified in the NumPy fallback
+    from desilike import utils as ref_utils
+    ref_utils.weights_trapz = lambda x: np.concatenate([[x[1] - x[0]], x[2:] - x[:-2], [x[-1] - x[-2]]]) / 2.
+    fcp = object.__new__(ClsP)
+    ClsP.initialize(fcp, k=TheoryP.k, ells=(0, 2, 4), theory=TheoryP(), fs=0.5, Dfc=0.8)
+    out['p_correlated'], out['p_uncorrelated'], out['p_k'] = np.array(fcp.kernel_correlated), np.array(fcp.kernel_uncorrelated), TheoryP.k
     np.savez_compressed(os.path.join(HERE, 'fiber_collisions.npz'), case=json.dumps(dict(kind='fiber_collisions', a=dict(fs=0.6, Dfc=3., mu_range_cut=False), b=dict(fs=0.35, Dfc=10., mu_range_cut=True))),
                         s=Theory.s, ells=np.array([0, 2]), ellsin=np.array(Theory.ells), **out)
     print('fiber_collisions', out['correlated_a'].shape)

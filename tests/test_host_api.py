@@ -351,3 +351,31 @@ def test_fiber_collision_kernels_match_reference_class():
     th = np.random.default_rng(0).standard_normal((2, s.size))
     corr, unc = tophat_fiber_collisions_correlation(s, (0, 2), fs=0.6, Dfc=3.)
     assert np.allclose(ospec['wmatrix'] @ th.ravel() + ospec['offset'], (np.sum(corr * th[None], axis=1) + unc).ravel(), rtol=1e-14, atol=1e-14)
+
+
+def test_power_fiber_collision_kernels_match_reference_class():
+    """Top-hat fiber-collision kernels on P_ell(k) (Hahn et al. 2016) against the reference's own class (tests/golden/fiber_collisions.npz;
+    reference window.py:967-1049) and their folding into the window matrix / offset of the observable (reference window.py:428-438)."""
+    from desilike_b200.observables import tophat_fiber_collisions_power
+    data = np.load(os.path.join(HERE, 'golden', 'fiber_collisions.npz'))
+    k = data['p_k']
+    corr, unc = tophat_fiber_collisions_power(k, (0, 2, 4), fs=0.5, Dfc=0.8)
+    assert np.allclose(corr, data['p_correlated'], rtol=1e-13, atol=1e-15)
+    assert np.allclose(unc, data['p_uncorrelated'], rtol=1e-12, atol=1e-12 * np.max(np.abs(data['p_uncorrelated'])))
+    template = dl.ShapeFitPowerSpectrumTemplate(pk_dd_fid=synthetic.pk_fid, pknow_dd_fid=synthetic.pknow_fid, f_fid=synthetic.F_FID)
+    rng = np.random.default_rng(3)
+    power = rng.standard_normal((3, k.size))
+    ref = np.sum(corr * power[None, :, None, :], axis=(1, 3)) + unc   # reference BaseFiberCollisionsPowerSpectrumMultipoles.calculate (window.py:812-821)
+    # without a window matrix
+    theory = dl.KaiserTracerPowerSpectrumMultipoles(template=template)
+    obs = dl.TracerPowerSpectrumMultipolesObservable(data=np.zeros(3 * k.size), k=[k] * 3, ells=(0, 2, 4), theory=theory, fiber_collisions=dict(fs=0.5, Dfc=0.8))
+    ospec = obs.observable_spec()
+    assert np.allclose(ospec['wmatrix'] @ power.ravel() + ospec['offset'], ref.ravel(), rtol=1e-12, atol=1e-9)
+    # behind a window matrix: W . (kernels . P + uncorrelated)
+    kout = k[5:40:5]
+    W = rng.standard_normal((3 * kout.size, 3 * k.size))
+    theory = dl.KaiserTracerPowerSpectrumMultipoles(template=template)
+    obs = dl.TracerPowerSpectrumMultipolesObservable(data=np.zeros(3 * kout.size), k=[kout] * 3, ells=(0, 2, 4), theory=theory, wmatrix=W, kin=k, ellsin=(0, 2, 4),
+                                                     fiber_collisions=dict(fs=0.5, Dfc=0.8))
+    ospec = obs.observable_spec()
+    assert np.allclose(ospec['wmatrix'] @ power.ravel() + ospec['offset'], W @ ref.ravel(), rtol=1e-11, atol=1e-8)
