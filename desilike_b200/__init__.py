@@ -16,10 +16,11 @@ from .observables import TracerPowerSpectrumMultipolesObservable, TracerCorrelat
 from .likelihoods import ObservablesGaussianLikelihood, SumLikelihood, PipelineError
 from .base import vmap, status_to_errors
 from .samplers import EnsembleSampler
+from .adapters import spec_from_likelihood
 
 __all__ = ['Parameter', 'ParameterCollection', 'Samples', 'ShapeFitPowerSpectrumTemplate', 'BAOPowerSpectrumTemplate',
            'KaiserTracerPowerSpectrumMultipoles', 'EFTLikeKaiserTracerPowerSpectrumMultipoles', 'LPTVelocileptorsTracerPowerSpectrumMultipoles', 'TableBiasTracerPowerSpectrumMultipoles', 'DampedBAOWigglesTracerPowerSpectrumMultipoles',
            'DampedBAOWigglesTracerCorrelationFunctionMultipoles', 'Emulator', 'EmulatedCalculator', 'TracerPowerSpectrumMultipolesObservable',
-           'TracerCorrelationFunctionMultipolesObservable', 'ObservablesGaussianLikelihood', 'SumLikelihood', 'PipelineError', 'vmap', 'status_to_errors', 'EnsembleSampler',
+           'TracerCorrelationFunctionMultipolesObservable', 'ObservablesGaussianLikelihood', 'SumLikelihood', 'PipelineError', 'vmap', 'status_to_errors', 'EnsembleSampler', 'spec_from_likelihood',
            'Plan', 'sample_solved', 'Lowered', 'LoweringError', 'DesilikeB200Error', 'load_library', 'launch_count', 'measure_fp64_peak', 'pinned_empty']
 __version__ = '0.1.0'

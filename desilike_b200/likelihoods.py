@@ -16,6 +16,26 @@ class PipelineError(Exception):
     """reference desilike/base.py (unknown parameter name etc.)."""
 
 
+def resolve_terms(terms, solved_names, fixed):
+    """Theory terms with parameter factors -> spec terms: a factor that is a solved parameter (must enter linearly) becomes the term's
+    ``solved`` tag, a fixed parameter is folded into the scale (terms with zero scale drop out), sampled parameters stay factors."""
+    out = []
+    for term in terms:
+        term = dict(term)
+        scale, factors, sname = float(term.get('scale', 1.)), [], term.get('solved')
+        for name, power in term.get('factors', []):
+            if name in solved_names:
+                if power != 1 or sname is not None: raise ValueError('solved parameter {} must enter linearly'.format(name))
+                sname = name
+            elif name in fixed:
+                scale *= fixed[name]**power
+            else:
+                factors.append((name, power))
+        if scale == 0.: continue
+        out.append(dict(term, scale=scale, factors=factors, solved=sname))
+    return out
+
+
 class BaseLikelihood(object):
     solved_default = '.marg'   # reference likelihoods/base.py:207
 
@@ -59,20 +79,7 @@ class BaseLikelihood(object):
             theory = obs.theory.theory_spec()
             theory['params'] = [n for n in theory['params'] if n in varied]
             theory['defaults'] = dict(theory.get('defaults', {}))
-            terms = []
-            for term in list(obs.theory.terms()) + list(obs.systematic_terms()):
-                term = dict(term)
-                scale, factors, sname = float(term.get('scale', 1.)), [], term.get('solved')
-                for name, power in term.get('factors', []):
-                    if name in solved_names:
-                        if power != 1 or sname is not None: raise ValueError('solved parameter {} must enter linearly'.format(name))
-                        sname = name
-                    elif name in fixed:
-                        scale *= fixed[name]**power
-                    else:
-                        factors.append((name, power))
-                if scale == 0.: continue
-                terms.append(dict(term, scale=scale, factors=factors, solved=sname))
+            terms = resolve_terms(list(obs.theory.terms()) + list(obs.systematic_terms()), solved_names, fixed)
             ospec.update(theory=theory, terms=terms)
             spec['observables'].append(ospec)
         return spec

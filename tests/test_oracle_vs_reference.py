@@ -33,3 +33,29 @@ def test_reference_vmap_conventions():
     assert res[0].shape == (2, 3) and res[1] == {}
     ora = pipeline.evaluate(spec, X.reshape(6, -1))['logposterior'].reshape(2, 3)
     assert np.allclose(res[0], ora, rtol=1e-11, atol=2e-9)
+
+
+@pytest.mark.parametrize('kwargs,eftlike,mode', [(dict(eftlike=False, solved=False), False, None), (dict(eftlike=True, solved=True), True, '.marg'),
+                                                  (dict(eftlike=True, solved=True), True, '.best'), (dict(eftlike=False, solved=False, systematic=True), False, '.marg'),
+                                                  (dict(eftlike=False, solved=False, transform='cubic'), False, None)])
+def test_spec_from_reference_likelihood(kwargs, eftlike, mode):
+    """desilike_b200.spec_from_likelihood: the spec extracted from the reference's OWN initialised likelihood object
+    evaluates -- through the oracle here, through the CUDA path on a GPU -- to the reference's own log-posteriors."""
+    import desilike_b200 as dl
+    spec0 = configs.config_kaiser_window(seed=13, **kwargs)
+    if mode == '.best':
+        for s in spec0['solved']: s['marg'] = False
+    like = ref_harness.reference_kaiser_likelihood(spec0, eftlike=eftlike, solved_mode=mode)
+    if spec0['solved']: ref_harness.install_jacfwd_stub()
+    X0 = configs.sample_points(spec0, 8, seed=6)
+    ref = ref_harness.run_vmap(like, spec0, X0)
+    spec = dl.spec_from_likelihood(like)
+    assert sorted(spec['params']) == sorted(spec0['params']) and sorted(s['name'] for s in spec['solved']) == sorted(s['name'] for s in spec0['solved'])
+    X = np.column_stack([X0[:, spec0['params'].index(name)] for name in spec['params']])
+    got = pipeline.evaluate(spec, X, return_theory=True)
+    assert np.max(np.abs(got['flattheory'] - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-12
+    fin = np.isfinite(ref['logposterior'])
+    assert np.array_equal(np.isneginf(ref['logposterior']), np.isneginf(got['logposterior']))
+    assert np.allclose(got['logposterior'][fin], ref['logposterior'][fin], rtol=1e-11, atol=2e-9)
+    from desilike_b200.lowering import Lowered
+    Lowered(spec)   # lowers without error
