@@ -9,7 +9,8 @@ module works on whatever desilike installation the caller has.
 
 Supported (everything else fails loudly): ``ObservablesGaussianLikelihood`` over ``TracerPowerSpectrumMultipolesObservable``s whose theory is
 ``KaiserTracerPowerSpectrumMultipoles`` / ``EFTLikeKaiserTracerPowerSpectrumMultipoles`` with a ``ShapeFitPowerSpectrumTemplate`` (direct
-theory), including systematic templates, the 'cubic' transform and '.marg' / '.best' solved parameters ('.prec' parameters are folded into
+theory), and over power-spectrum / correlation-function observables of the damped-BAO tracers (``DampedBAOWigglesTracer*Multipoles``, power-law
+broadband), including systematic templates, the 'cubic' transform and '.marg' / '.best' solved parameters ('.prec' parameters are folded into
 the reference object's precision when it initialises, so a likelihood carrying them is rejected).  Tested against live reference objects in
 tests/test_oracle_vs_reference.py (build container; the reference does not travel to the GPU box).
 """
@@ -47,45 +48,82 @@ def spec_from_likelihood(likelihood, solved_default='.marg'):
                 solved=[dict(name=p.name, value=float(p.value), prior=_prior(p.prior), marg=str(p.derived).replace('.auto', solved_default).startswith('.marg'),
                              mode='prec' if str(p.derived).startswith('.prec') else None) for p in solved],
                 fiducial={name: defaults[name] for name in varied}, observables=[])
+    solved_names = [p.name for p in solved]
     for obs in likelihood.observables:
         w = getattr(obs, 'wmatrix', None)
-        if w is None or not hasattr(w, 'kin'):
-            raise NotImplementedError('observable {} is not a windowed power-spectrum observable'.format(type(obs).__name__))
+        if w is None or not (hasattr(w, 'kin') or hasattr(w, 'sin')):
+            raise NotImplementedError('observable {} is not a windowed two-point observable'.format(type(obs).__name__))
         th = w.theory
-        cls = _THEORIES.get(type(th).__name__)
-        if cls is None: raise NotImplementedError('theory {} is not on the CUDA path through this adapter'.format(type(th).__name__))
-        pt, tpl = th.pt, th.pt.template
-        if type(tpl).__name__ != 'ShapeFitPowerSpectrumTemplate':
-            raise NotImplementedError('template {} is not on the CUDA path through this adapter'.format(type(tpl).__name__))
-        kin, ellsin = np.asarray(w.kin, dtype='f8'), tuple(w.ellsin)
-        b1 = [p for p in th.all_params if p.basename == 'b1'][0]
-        # bias-combine terms from the mirror class (full_shape.py:545-550, :628-634); only k, ells, nd and the parameter names are needed
-        mirror = cls(template=None, k=kin, ells=ellsin, shotnoise=1. / float(th.nd), tracer=b1.namespace or None)
-        if hasattr(th, 'kp'): mirror.kp = float(th.kp)
-        terms = list(mirror.terms())
+        tname = type(th).__name__
+        is_xi = hasattr(w, 'sin')
+        xin, ellsin = np.asarray(w.sin if is_xi else w.kin, dtype='f8'), tuple(w.ellsin)
+        nin = len(ellsin) * xin.size
+        basenames = {n.split('.')[-1]: v for n, v in defaults.items()}
+        if tname in _THEORIES and not is_xi:
+            pt, tpl = th.pt, th.pt.template
+            if type(tpl).__name__ != 'ShapeFitPowerSpectrumTemplate':
+                raise NotImplementedError('template {} is not on the CUDA path through this adapter'.format(type(tpl).__name__))
+            b1 = [p for p in th.all_params if p.basename == 'b1'][0]
+            # bias-combine terms from the mirror class (full_shape.py:545-550, :628-634); only k, ells, nd and the parameter names are needed
+            mirror = _THEORIES[tname](template=None, k=xin, ells=ellsin, shotnoise=1. / float(th.nd), tracer=b1.namespace or None)
+            if hasattr(th, 'kp'): mirror.kp = float(th.kp)
+            terms = list(mirror.terms())
+            theory = dict(kind='kaiser', k=xin, ells=ellsin, nmu=len(pt.mu),
+                          template=dict(kind='shapefit', k=np.array(tpl.k, dtype='f8'), pk_dd_fid=np.array(tpl.pk_dd_fid, dtype='f8'),
+                                        pknow_dd_fid=np.array(tpl.pknow_dd_fid, dtype='f8'), f_fid=float(tpl.f_fid), a=float(tpl.a), kp=float(tpl.kp),
+                                        apmode=str(tpl.apeffect.mode), eta=float(getattr(tpl, 'eta', 1. / 3.)), only_now=bool(getattr(tpl, 'only_now', False))),
+                          params=[n for n in varied if n.split('.')[-1] in ('qpar', 'qper', 'qiso', 'qap', 'dm', 'dn', 'df', 'sigmapar', 'sigmaper')], defaults=basenames)
+        elif tname in ('DampedBAOWigglesTracerPowerSpectrumMultipoles', 'DampedBAOWigglesTracerCorrelationFunctionMultipoles') and is_xi == tname.endswith('CorrelationFunctionMultipoles'):
+            # damped BAO (bao.py:117-151) + power-law broadband in x / pivot (bao.py:467-476, :527-534; :849-853, :905)
+            pt, tpl = th.pt, th.pt.template
+            if str(getattr(th, 'broadband', 'power')) != 'power': raise NotImplementedError('only the power-law broadband is on the CUDA path')
+            pivot = float(th.sp if is_xi else th.kp)
+            names = {p.basename: p.name for p in th.all_params}
+            terms = [dict(scale=1., factors=[], table='corr' if is_xi else 'power')]
+            for ill, ell in enumerate(ellsin):
+                for name, power in th.broadband_orders.get(ell, {}).items():
+                    colvec = np.zeros((len(ellsin), xin.size)); colvec[ill] = (xin / pivot)**power
+                    terms.append(dict(scale=1., factors=[(names.get(name, name), 1)], table=None, colvec=colvec.ravel()))
+            theory = dict(kind='bao_xi' if is_xi else 'bao_pk', ells=ellsin, nmu=len(pt.mu), mode=str(pt.mode), smoothing_radius=float(pt.smoothing_radius),
+                          template=dict(kind='bao', k=np.array(tpl.k, dtype='f8'), pk_dd_fid=np.array(tpl.pk_dd_fid, dtype='f8'), pknow_dd_fid=np.array(tpl.pknow_dd_fid, dtype='f8'),
+                                        f_fid=float(tpl.f_fid), apmode=str(tpl.apeffect.mode), eta=float(getattr(tpl, 'eta', 1. / 3.))),
+                          params=[n for n in varied if n.split('.')[-1] in ('qpar', 'qper', 'qiso', 'qap', 'df', 'b1', 'dbeta', 'sigmas', 'sigmapar', 'sigmaper')], defaults=basenames)
+            if is_xi: theory.update(s=xin, kin=np.array(th.kin, dtype='f8') if hasattr(th, 'kin') else None)
+            else: theory.update(k=xin)
+        else:
+            raise NotImplementedError('theory {} is not on the CUDA path through this adapter'.format(tname))
         st = getattr(w, 'systematic_templates', None)
-        if st is not None:   # window.py:470-473: flatpower += sum_i syst_i template_i
+        if st is not None:   # window.py:470-473 / :732-733: flat += sum_i syst_i template_i
             names = {p.basename: p.name for p in st.all_params}
             for name, template in st.templates.items():
                 terms.append(dict(scale=1., factors=[(names.get(name, name), 1)], table=None, outvec=np.array(template, dtype='f8')))
-        theory = dict(kind='kaiser', k=kin, ells=ellsin, nmu=len(pt.mu),
-                      template=dict(kind='shapefit', k=np.array(tpl.k, dtype='f8'), pk_dd_fid=np.array(tpl.pk_dd_fid, dtype='f8'),
-                                    pknow_dd_fid=np.array(tpl.pknow_dd_fid, dtype='f8'), f_fid=float(tpl.f_fid), a=float(tpl.a), kp=float(tpl.kp),
-                                    apmode=str(tpl.apeffect.mode), eta=float(getattr(tpl, 'eta', 1. / 3.)), only_now=bool(getattr(tpl, 'only_now', False))),
-                      params=[n for n in varied if n.split('.')[-1] in ('qpar', 'qper', 'qiso', 'qap', 'dm', 'dn', 'df', 'sigmapar', 'sigmaper')],
-                      defaults={n.split('.')[-1]: v for n, v in defaults.items()})
-        # window constants (window.py:459-473): flat = (W . ravel(P + N_in) + offset)[kmask] - N_out
-        nin = len(ellsin) * kin.size
-        W = None if w.matrix_full is None else np.array(w.matrix_full, dtype='f8')
-        noise_in = np.repeat(np.asarray(w.shotnoisein, dtype='f8'), kin.size)
-        offset = W.dot(noise_in) if W is not None else noise_in.copy()
-        if getattr(w, 'offset', None) is not None: offset = offset + np.asarray(w.offset, dtype='f8')
-        if getattr(w, 'kmask', None) is not None:
-            W = (np.eye(nin) if W is None else W)[w.kmask]
-            offset = offset[w.kmask]
-        offset = offset - np.asarray(w.shotnoiseout, dtype='f8')
+        # window constants -> one matrix + offset
+        W = None
+        if is_xi:   # window.py:717-728: flat = (matrix_full . ravel(sum_l' matrix_diag[:, l'] theory[l']) + offset)[smask]
+            md = getattr(w, 'matrix_diag', None)
+            if md is not None:
+                md = np.asarray(md, dtype='f8')
+                ns = xin.size
+                W = np.zeros((md.shape[0] * ns, md.shape[1] * ns))
+                for lo in range(md.shape[0]):
+                    for li in range(md.shape[1]): W[lo * ns:(lo + 1) * ns, li * ns:(li + 1) * ns] = np.diag(md[lo, li])
+            if w.matrix_full is not None: W = np.array(w.matrix_full, dtype='f8') if W is None else np.asarray(w.matrix_full, dtype='f8').dot(W)
+            offset = None if getattr(w, 'offset', None) is None else np.array(w.offset, dtype='f8')
+            mask = getattr(w, 'smask', None)
+            if mask is not None:
+                W = (np.eye(nin) if W is None else W)[mask]
+                if offset is not None: offset = offset[mask]
+        else:       # window.py:459-473: flat = (W . ravel(P + N_in) + offset)[kmask] - N_out
+            W = None if w.matrix_full is None else np.array(w.matrix_full, dtype='f8')
+            noise_in = np.repeat(np.asarray(w.shotnoisein, dtype='f8'), xin.size)
+            offset = W.dot(noise_in) if W is not None else noise_in.copy()
+            if getattr(w, 'offset', None) is not None: offset = offset + np.asarray(w.offset, dtype='f8')
+            if getattr(w, 'kmask', None) is not None:
+                W = (np.eye(nin) if W is None else W)[w.kmask]
+                offset = offset[w.kmask]
+            offset = offset - np.asarray(w.shotnoiseout, dtype='f8')
         spec['observables'].append(dict(name=getattr(obs, 'name', 'observable'), nin=nin, wmatrix=W, offset=offset, transform=getattr(obs, 'transform', None), theory=theory,
-                                        terms=resolve_terms(terms, [p.name for p in solved], fixed), data=np.array(obs.flatdata, dtype='f8')))
+                                        terms=resolve_terms(terms, solved_names, fixed), data=np.array(obs.flatdata, dtype='f8')))
     spec['precision'] = np.array(likelihood.precision, dtype='f8')
     if len(spec['observables']) == 1: spec['precision'] = [spec['precision']]
     return spec

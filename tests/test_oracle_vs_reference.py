@@ -59,3 +59,40 @@ def test_spec_from_reference_likelihood(kwargs, eftlike, mode):
     assert np.allclose(got['logposterior'][fin], ref['logposterior'][fin], rtol=1e-11, atol=2e-9)
     from desilike_b200.lowering import Lowered
     Lowered(spec)   # lowers without error
+
+
+@pytest.mark.parametrize('which', ['corr', 'power'])
+def test_spec_from_reference_bao_likelihood(which):
+    """spec_from_likelihood on the reference's damped-BAO xi_ell(s) / P_ell(k) likelihoods with analytically marginalised broadband terms."""
+    import desilike_b200 as dl
+    ref_harness.setup()
+    from desilike.theories.galaxy_clustering import (BAOPowerSpectrumTemplate, DampedBAOWigglesTracerPowerSpectrumMultipoles,
+                                                     DampedBAOWigglesTracerCorrelationFunctionMultipoles)
+    from desilike.observables.galaxy_clustering import TracerCorrelationFunctionMultipolesObservable, TracerPowerSpectrumMultipolesObservable
+    from desilike.likelihoods import ObservablesGaussianLikelihood
+    rng = np.random.default_rng(9)
+    if which == 'corr':
+        x = np.arange(20., 152., 4.)
+        theory = DampedBAOWigglesTracerCorrelationFunctionMultipoles(template=BAOPowerSpectrumTemplate(z=1.), ells=(0, 2))
+        obs = TracerCorrelationFunctionMultipolesObservable(data={'b1': 2., 'sigmas': 3.}, s=[x, x], ells=(0, 2), theory=theory)
+        cov, keep = np.diag(np.full(2 * x.size, 1e-8)), ('_0', '_2')
+    else:
+        x = np.arange(0.02, 0.3, 0.005)
+        theory = DampedBAOWigglesTracerPowerSpectrumMultipoles(template=BAOPowerSpectrumTemplate(z=1.), ells=(0, 2))
+        obs = TracerPowerSpectrumMultipolesObservable(data={'b1': 2., 'sigmas': 3.}, k=[x, x], ells=(0, 2), theory=theory)
+        cov, keep = np.diag(np.full(2 * x.size, 1e4)), ('_-1', '_0', '_1')
+    like = ObservablesGaussianLikelihood(observables=[obs], covariance=cov)
+    for p in like.all_params:
+        if p.basename.startswith('al'):
+            if p.basename.endswith(keep): p.update(fixed=False, derived='.marg', prior=dict(dist='norm', loc=0., scale=1e4))
+            else: p.update(fixed=True)
+    ref_harness.install_jacfwd_stub()
+    names = ['qpar', 'qper', 'b1', 'dbeta', 'sigmas']
+    X = np.column_stack([rng.uniform(0.97, 1.03, 6), rng.uniform(0.97, 1.03, 6), rng.uniform(1.8, 2.2, 6), rng.uniform(0.9, 1.1, 6), rng.uniform(2., 4., 6)])
+    ref = np.array([like(dict(zip(names, xx))) for xx in X])
+    spec = dl.spec_from_likelihood(like)
+    assert spec['params'] == names and len(spec['solved']) == 2 * len(keep)
+    got = pipeline.evaluate(spec, X)
+    assert np.allclose(got['logposterior'], ref, rtol=1e-9, atol=1e-7), np.max(np.abs(got['logposterior'] - ref))
+    from desilike_b200.lowering import Lowered
+    Lowered(spec)
