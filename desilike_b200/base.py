@@ -45,6 +45,33 @@ def _check_params(params, known=None):
     return params, cshapes[0]
 
 
+class ReferenceLikelihoodAdapter(object):
+    """What ``vmap`` needs (``plan``, ``_points``) from one of the reference's own initialised likelihood objects: the plan is built from the
+    spec extracted by ``adapters.spec_from_likelihood``, parameters absent from a call take the reference's current values."""
+
+    def __init__(self, likelihood):
+        from .adapters import spec_from_likelihood
+        self.spec = spec_from_likelihood(likelihood)
+        self._defaults = dict(self.spec['fiducial'])
+        self._known = set(p.name for p in likelihood.all_params)
+        self._plan = None
+
+    @property
+    def plan(self):
+        if self._plan is None:
+            from .plan import Plan
+            self._plan = Plan(self.spec)
+        return self._plan
+
+    def _points(self, params):
+        from .likelihoods import PipelineError
+        for name in params:
+            if name not in self._known: raise PipelineError('input parameter {} is not one of parameters: {}'.format(name, sorted(self._known)))
+        names = self.spec['params']
+        n = max([np.size(params[name]) for name in names if name in params] + [1])
+        return np.column_stack([np.asarray(params[name], dtype='f8').ravel() if name in params else np.full(n, self._defaults[name]) for name in names])
+
+
 def vmap(calculate, backend='cuda', errors='raise', return_derived=False, mpicomm=None, **kwargs):
     """Batched evaluation of a desilike_b200 likelihood.  ``backend`` must be 'cuda' (there is no CPU fallback);
     ``mpicomm`` may be a ``desilike_b200.distributed.Communicator`` to shard the batch over GPUs."""
@@ -53,6 +80,8 @@ def vmap(calculate, backend='cuda', errors='raise', return_derived=False, mpicom
         raise ValueError("desilike_b200.vmap only provides backend='cuda' (the reference's None / 'jax' / 'mpi' backends live in desilike itself)")
     if errors not in ('raise', 'return', 'nan'): raise ValueError("errors must be one of 'raise', 'return', 'nan'")
     likelihood = calculate
+    if not hasattr(likelihood, '_points') and hasattr(likelihood, 'observables') and hasattr(likelihood, 'all_params'):
+        likelihood = ReferenceLikelihoodAdapter(likelihood)   # one of desilike's OWN likelihood objects: extract its constants into a plan
 
     def wrapper(params, **kw):
         rd = kw.pop('return_derived', return_derived)

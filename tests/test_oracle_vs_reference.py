@@ -96,3 +96,22 @@ def test_spec_from_reference_bao_likelihood(which):
     assert np.allclose(got['logposterior'], ref, rtol=1e-9, atol=1e-7), np.max(np.abs(got['logposterior'] - ref))
     from desilike_b200.lowering import Lowered
     Lowered(spec)
+
+
+def test_vmap_accepts_reference_likelihood_objects():
+    """desilike_b200.vmap(reference_likelihood): the adapter extracts the spec and maps parameter dicts to plan columns (no GPU here: the plan
+    itself is not built; the point matrix and the spec are checked)."""
+    from desilike_b200.base import ReferenceLikelihoodAdapter
+    import desilike_b200 as dl
+    spec0 = configs.config_kaiser_window(eftlike=True, solved=True, seed=13)
+    like = ref_harness.reference_kaiser_likelihood(spec0, eftlike=True, solved_mode='.marg')
+    ref_harness.install_jacfwd_stub()
+    like(b1=1.7)
+    adapter = ReferenceLikelihoodAdapter(like)
+    X = adapter._points({'b1': np.array([1.5, 2.]), 'qpar': np.array([1.01, 0.99])})
+    names = adapter.spec['params']
+    assert X.shape == (2, len(names)) and np.array_equal(X[:, names.index('b1')], [1.5, 2.]) and np.all(X[:, names.index('qper')] == 1.)
+    with pytest.raises(dl.PipelineError):
+        adapter._points({'nope': np.zeros(2)})
+    wrapper = dl.vmap(like, backend='cuda')   # wrapping needs no GPU; evaluation does
+    assert callable(wrapper)
