@@ -32,11 +32,20 @@ def _prior(prior):
     return out
 
 
-def spec_from_likelihood(likelihood, solved_default='.marg'):
-    """Initialised reference ``ObservablesGaussianLikelihood`` -> likelihood spec (``desilike_b200.Plan(spec)``)."""
+def spec_from_likelihood(likelihood, solved_default='.marg', all_params=None):
+    """Initialised reference ``ObservablesGaussianLikelihood`` (or ``SumLikelihood`` of them) -> likelihood spec (``desilike_b200.Plan(spec)``).
+    ``all_params``: parameter collection to read values / priors / solved tags from (default: the likelihood's own)."""
+    if hasattr(likelihood, 'likelihoods'):   # SumLikelihood (reference likelihoods/base.py:715-732): independent members, one precision block each;
+        # the parameters of the SUM's pipeline are authoritative (members configured separately may carry different priors for a shared name)
+        members = [spec_from_likelihood(like, solved_default=solved_default, all_params=likelihood.all_params) for like in likelihood.likelihoods]
+        spec = dict(members[0], observables=[], precision=[])
+        for m in members:
+            spec['observables'] += m['observables']
+            spec['precision'] += list(m['precision']) if isinstance(m['precision'], list) else [m['precision']]
+        return spec
     if not hasattr(likelihood, 'observables') or not hasattr(likelihood, 'precision'):
         raise NotImplementedError('spec_from_likelihood expects an ObservablesGaussianLikelihood (got {})'.format(type(likelihood).__name__))
-    params = [p for p in likelihood.all_params if p.derived is not True]   # derived=True: outputs (loglikelihood, f_sqrt_Ap, ...), not inputs
+    params = [p for p in (likelihood.all_params if all_params is None else all_params) if p.derived is not True]   # derived=True: outputs, not inputs
     varied = [p.name for p in params if p.varied and not p.solved]
     solved = [p for p in params if p.solved]
     if any(str(p.derived).startswith('.prec') for p in solved):

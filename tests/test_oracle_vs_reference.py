@@ -115,3 +115,20 @@ def test_vmap_accepts_reference_likelihood_objects():
         adapter._points({'nope': np.zeros(2)})
     wrapper = dl.vmap(like, backend='cuda')   # wrapping needs no GPU; evaluation does
     assert callable(wrapper)
+
+
+def test_spec_from_reference_sum_likelihood():
+    """SumLikelihood of two reference likelihoods sharing their parameters -> one spec with one precision block per member."""
+    import desilike_b200 as dl
+    spec0 = configs.config_kaiser_window(eftlike=False, solved=False, seed=13)
+    like1 = ref_harness.reference_kaiser_likelihood(spec0)
+    like2 = ref_harness.reference_kaiser_likelihood(configs.config_kaiser_window(eftlike=False, solved=False, seed=14))
+    both = like1 + like2
+    X0 = configs.sample_points(spec0, 5, seed=2)
+    ref = np.array([both(dict(zip(spec0['params'], x))) for x in X0])
+    spec = dl.spec_from_likelihood(both)
+    assert len(spec['observables']) == 2 and len(spec['precision']) == 2
+    X = np.column_stack([X0[:, spec0['params'].index(name)] for name in spec['params']])
+    got = pipeline.evaluate(spec, X)
+    fin = np.isfinite(ref)
+    assert np.allclose(got['logposterior'][fin], ref[fin], rtol=1e-11, atol=2e-9)
