@@ -11,7 +11,8 @@ Operations are {expression, inverse, locals} strings (conversion.py:24-33,76-84)
 the expressions the reference itself emits is pattern-matched and lowered to the CUDA MLP generator; anything else raises.
 The schema beyond those call sites is third-party, so compatibility is best effort and round-trip tested with this writer.
 
-Fitting (Taylor finite differences / MLP training) is a 'next' row of SURVEY.md section 8(f) and not part of this module.
+Fitting: ``Emulator.fit_taylor`` builds a Taylor emulator from GPU theory evaluations on a finite-difference stencil (SURVEY.md section 8(f)-3);
+MLP training is not part of this module.
 """
 import os
 import re
