@@ -221,3 +221,17 @@ def test_precision_blocks_over_runs_of_observables():
     assert np.allclose(got['x_solved'], ref_runs['x_solved'], rtol=1e-7, atol=1e-7)
     with pytest.raises(LoweringError):
         Lowered(dict(spec, precision=[joint[:-1, :-1], P[2]]))
+
+
+def test_rank_reduction_with_rank_deficient_terms():
+    """The QR rank reduction stays exact when the stacked term matrices are rank deficient (a table proportional to another one, a zero table)."""
+    from desilike_b200.lowering import Lowered
+    spec = configs.config_c5(ntracers=1, nkin=40, nbins=40, order=2, solved=False)
+    th = spec['observables'][0]['theory']
+    th['tables']['pk_dt'] = 0.5 * th['tables']['pk_dd']
+    th['tables']['pk_tt'] = np.zeros_like(th['tables']['pk_tt'])
+    low = Lowered(spec)
+    assert low.blocks[0]['ncols_white'] < low.blocks[0]['ncols']
+    X = configs.sample_points(spec, 12, seed=3)
+    ref, got = pipeline.evaluate(spec, X), lowered_numpy.evaluate(low, X)
+    assert np.allclose(got['loglikelihood'], ref['loglikelihood'], rtol=1e-12, atol=1e-9)
