@@ -57,8 +57,16 @@ def _whitening(precision):
     """P = L^T L  ->  L (upper triangular for dense P, diagonal for 1-D P)."""
     precision = np.asarray(precision, dtype=np.float64)
     if precision.ndim == 1:
+        if np.any(precision < 0.): raise LoweringError('negative entries in the diagonal precision')
         return np.diag(np.sqrt(precision))
-    return np.linalg.cholesky(precision).T
+    try:
+        return np.linalg.cholesky(precision).T
+    except np.linalg.LinAlgError:
+        # positive SEMI-definite precision (e.g. '.prec' pre-marginalisation over a parameter without prior projects its template out of P):
+        # any L with L^T L = P will do -- take the symmetric eigen-decomposition
+        lam, V = np.linalg.eigh(0.5 * (precision + precision.T))
+        if lam[0] < -1e-10 * max(lam[-1], 0.): raise LoweringError('precision matrix is not positive semi-definite')
+        return np.sqrt(np.clip(lam, 0., None))[:, None] * V.T
 
 
 class _Generator(object):

@@ -235,3 +235,21 @@ def test_rank_reduction_with_rank_deficient_terms():
     X = configs.sample_points(spec, 12, seed=3)
     ref, got = pipeline.evaluate(spec, X), lowered_numpy.evaluate(low, X)
     assert np.allclose(got['loglikelihood'], ref['loglikelihood'], rtol=1e-12, atol=1e-9)
+
+
+def test_semidefinite_precision_is_lowered():
+    """A singular positive semi-definite precision (a direction projected out, as an improper-prior '.prec' marginalisation leaves it) has no
+    Cholesky factor: the lowering falls back to an eigen-decomposition and reproduces the oracle's d^T P d."""
+    from desilike_b200.lowering import Lowered, LoweringError
+    spec = configs.config_c2(nkin=50, nbins=12, order=2)
+    P = spec['precision'][0]
+    v = np.random.default_rng(2).standard_normal(P.shape[0])
+    Pv = P @ v
+    spec['precision'] = [P - np.outer(Pv, Pv) / v.dot(Pv)]   # P v = 0
+    assert abs(np.linalg.eigvalsh(spec['precision'][0])[0]) < 1e-8 * np.linalg.eigvalsh(P)[-1]
+    low = Lowered(spec)
+    X = configs.sample_points(spec, 10, seed=4)
+    ref, got = pipeline.evaluate(spec, X), lowered_numpy.evaluate(low, X)
+    assert np.allclose(got['loglikelihood'], ref['loglikelihood'], rtol=1e-9, atol=1e-7)
+    with pytest.raises(LoweringError):
+        Lowered(dict(spec, precision=[P - 2. * np.outer(Pv, Pv) / v.dot(Pv)]))   # indefinite
