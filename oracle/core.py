@@ -5,12 +5,15 @@ cpu_baseline / --impl reference legs may import anything under oracle/.
 
 Every function cites the reference lines it follows (paths relative to /root/reference).
 Pinning status (tests/golden/make_golden.py):
-  * window, chi2, prior, Kaiser (+ShapeFit, AP), EFT-like add-ons, damped BAO P(k), vmap conventions:
-    PINNED bit-for-bit / to rounding against the reference's own NumPy path run under stub third-party modules
-    (oracle/ref_harness.py) -> committed fixtures tests/golden/*.npz.
-  * Taylor predict, MLP predict, FFTLog, analytic marginalisation: the reference delegates these to packages absent
-    here (cosmoprimo, jax) -> PARITY UNPINNED against those packages; pinned mathematically (Taylor of a polynomial is
-    exact; FFTLog vs the defining integral; marginalised logL vs brute-force maximisation / Gaussian integral).
+  * window (P(k) and xi), chi2, prior, Kaiser (+ShapeFit, AP), EFT-like add-ons, damped BAO P(k) / xi wiring and broadband terms, the
+    'cubic' observable transform, systematic templates, '.marg' / '.best' / '.prec' analytic marginalisation (the reference's own
+    FastFisher / _solve with jax.jacfwd shimmed by an exact central difference), covariance -> precision with Hartlap / Percival factors,
+    the velocileptors-style bias combination + interp1d, vmap conventions:
+    PINNED to rounding against the reference's own NumPy path run under stub third-party modules
+    (oracle/ref_harness.py) -> committed fixtures tests/golden/*.npz, and live in tests/test_oracle_vs_reference.py.
+  * Taylor predict, MLP predict, FFTLog: the reference delegates these to packages absent here (cosmoprimo, jax)
+    -> PARITY UNPINNED against those packages; pinned mathematically (Taylor of a polynomial is exact; the MLP operation vocabulary of
+    emulators/conversion.py; FFTLog vs the defining integral and an analytic pair).
 """
 import numpy as np
 from scipy import special, interpolate
