@@ -132,3 +132,25 @@ def test_spec_from_reference_sum_likelihood():
     got = pipeline.evaluate(spec, X)
     fin = np.isfinite(ref)
     assert np.allclose(got['logposterior'][fin], ref[fin], rtol=1e-11, atol=2e-9)
+
+
+def test_spec_from_reference_likelihood_with_k_mask():
+    """Reference observable defined through ``klim`` with different k ranges per multipole (window ``kmask``, reference window.py:296-303, :466-467)."""
+    import desilike_b200 as dl
+    ref_harness.setup()
+    from desilike.theories.galaxy_clustering import ShapeFitPowerSpectrumTemplate, KaiserTracerPowerSpectrumMultipoles
+    from desilike.observables.galaxy_clustering import TracerPowerSpectrumMultipolesObservable
+    from desilike.likelihoods import ObservablesGaussianLikelihood
+    theory = KaiserTracerPowerSpectrumMultipoles(template=ShapeFitPowerSpectrumTemplate(z=1.))
+    klim = {0: [0.02, 0.2, 0.01], 2: [0.04, 0.16, 0.01], 4: [0.06, 0.1, 0.01]}
+    obs = TracerPowerSpectrumMultipolesObservable(data={'b1': 2.}, klim=klim, theory=theory)
+    like = ObservablesGaussianLikelihood(observables=[obs], covariance=np.diag(np.full(18 + 12 + 4, 1e5)))
+    rng = np.random.default_rng(5)
+    names = ['qpar', 'qper', 'dm', 'df', 'b1', 'sn0']
+    X = np.column_stack([rng.uniform(0.97, 1.03, 5), rng.uniform(0.97, 1.03, 5), rng.uniform(-0.05, 0.05, 5), rng.uniform(0.9, 1.1, 5), rng.uniform(1.8, 2.2, 5), rng.normal(0., 0.1, 5)])
+    ref = np.array([like(dict(zip(names, x))) for x in X])
+    assert obs.wmatrix.kmask is not None
+    spec = dl.spec_from_likelihood(like)
+    assert spec['observables'][0]['wmatrix'].shape[0] == len(obs.flatdata) < spec['observables'][0]['nin']
+    got = pipeline.evaluate(spec, np.column_stack([X[:, names.index(n)] for n in spec['params']]))
+    assert np.allclose(got['logposterior'], ref, rtol=1e-10, atol=1e-8)
