@@ -154,3 +154,34 @@ def test_spec_from_reference_likelihood_with_k_mask():
     assert spec['observables'][0]['wmatrix'].shape[0] == len(obs.flatdata) < spec['observables'][0]['nin']
     got = pipeline.evaluate(spec, np.column_stack([X[:, names.index(n)] for n in spec['params']]))
     assert np.allclose(got['logposterior'], ref, rtol=1e-10, atol=1e-8)
+
+
+def test_spec_from_reference_xi_likelihood_with_fiber_collisions():
+    """Reference xi observable with its top-hat fiber-collision window (reference window.py:686-702, :1192-1249): the adapter reads matrix_diag / offset,
+    and the mirror observable built with ``fiber_collisions=dict(fs, Dfc)`` folds to the same matrix and offset."""
+    import desilike_b200 as dl
+    from oracle import synthetic
+    ref_harness.setup()
+    from desilike.theories.galaxy_clustering import BAOPowerSpectrumTemplate, DampedBAOWigglesTracerCorrelationFunctionMultipoles
+    from desilike.observables.galaxy_clustering import TracerCorrelationFunctionMultipolesObservable, TopHatFiberCollisionsCorrelationFunctionMultipoles
+    from desilike.likelihoods import ObservablesGaussianLikelihood
+    s = np.arange(20., 152., 4.)
+    theory = DampedBAOWigglesTracerCorrelationFunctionMultipoles(template=BAOPowerSpectrumTemplate(z=1.), ells=(0, 2))
+    fc = TopHatFiberCollisionsCorrelationFunctionMultipoles(fs=0.5, Dfc=12.)
+    obs = TracerCorrelationFunctionMultipolesObservable(data={'b1': 2., 'sigmas': 3.}, s=[s, s], ells=(0, 2), theory=theory, fiber_collisions=fc)
+    like = ObservablesGaussianLikelihood(observables=[obs], covariance=np.diag(np.full(66, 1e-8)))
+    for p in like.all_params:
+        if p.basename.startswith('al'): p.update(fixed=True)
+    names = ['qpar', 'qper', 'b1', 'dbeta', 'sigmas']
+    rng = np.random.default_rng(12)
+    X = np.column_stack([rng.uniform(0.97, 1.03, 4), rng.uniform(0.97, 1.03, 4), rng.uniform(1.8, 2.2, 4), rng.uniform(0.9, 1.1, 4), rng.uniform(2., 4., 4)])
+    ref = np.array([like(dict(zip(names, x))) for x in X])
+    assert obs.wmatrix.matrix_diag is not None
+    spec = dl.spec_from_likelihood(like)
+    got = pipeline.evaluate(spec, X)
+    assert np.allclose(got['logposterior'], ref, rtol=1e-9, atol=1e-7)
+    template = dl.BAOPowerSpectrumTemplate(pk_dd_fid=synthetic.pk_fid, pknow_dd_fid=synthetic.pknow_fid, f_fid=synthetic.F_FID, rs_drag=synthetic.RS_DRAG)
+    mirror = dl.TracerCorrelationFunctionMultipolesObservable(data=np.zeros(66), s=[s, s], ells=(0, 2), fiber_collisions=dict(fs=0.5, Dfc=12.),
+                                                              theory=dl.DampedBAOWigglesTracerCorrelationFunctionMultipoles(template=template, ells=(0, 2)))
+    ospec = mirror.observable_spec()
+    assert np.allclose(ospec['wmatrix'], spec['observables'][0]['wmatrix'], rtol=0., atol=1e-14) and np.allclose(ospec['offset'], spec['observables'][0]['offset'], rtol=0., atol=1e-14)
