@@ -185,3 +185,33 @@ def test_spec_from_reference_xi_likelihood_with_fiber_collisions():
                                                               theory=dl.DampedBAOWigglesTracerCorrelationFunctionMultipoles(template=template, ells=(0, 2)))
     ospec = mirror.observable_spec()
     assert np.allclose(ospec['wmatrix'], spec['observables'][0]['wmatrix'], rtol=0., atol=1e-14) and np.allclose(ospec['offset'], spec['observables'][0]['offset'], rtol=0., atol=1e-14)
+
+
+def test_reference_power_observable_with_fiber_collisions():
+    """Reference P(k) observable with its top-hat fiber-collision window (reference window.py:428-438, :967-1049; ``utils.weights_trapz`` shimmed with its
+    jax semantics, see tests/golden/make_golden.py:fiber_collisions): adapter spec == reference log-posterior; mirror fold == the reference's matrix / offset."""
+    import desilike_b200 as dl
+    from oracle import synthetic
+    ref_harness.setup()
+    from desilike import utils as ref_utils
+    ref_utils.weights_trapz = lambda x: np.concatenate([[x[1] - x[0]], x[2:] - x[:-2], [x[-1] - x[-2]]]) / 2.
+    from desilike.theories.galaxy_clustering import ShapeFitPowerSpectrumTemplate, KaiserTracerPowerSpectrumMultipoles
+    from desilike.observables.galaxy_clustering import TracerPowerSpectrumMultipolesObservable, TopHatFiberCollisionsPowerSpectrumMultipoles
+    from desilike.likelihoods import ObservablesGaussianLikelihood
+    k = np.arange(0.02, 0.2, 0.005)
+    theory = KaiserTracerPowerSpectrumMultipoles(template=ShapeFitPowerSpectrumTemplate(z=1.))
+    fc = TopHatFiberCollisionsPowerSpectrumMultipoles(fs=0.5, Dfc=0.8)
+    obs = TracerPowerSpectrumMultipolesObservable(data={'b1': 2.}, k=[k] * 3, ells=(0, 2, 4), theory=theory, fiber_collisions=fc)
+    like = ObservablesGaussianLikelihood(observables=[obs], covariance=np.diag(np.full(3 * k.size, 1e5)))
+    names = ['qpar', 'qper', 'dm', 'df', 'b1', 'sn0']
+    rng = np.random.default_rng(15)
+    X = np.column_stack([rng.uniform(0.97, 1.03, 4), rng.uniform(0.97, 1.03, 4), rng.uniform(-0.05, 0.05, 4), rng.uniform(0.9, 1.1, 4), rng.uniform(1.8, 2.2, 4), rng.normal(0., 0.1, 4)])
+    ref = np.array([like(dict(zip(names, x))) for x in X])
+    spec = dl.spec_from_likelihood(like)
+    got = pipeline.evaluate(spec, np.column_stack([X[:, names.index(n)] for n in spec['params']]))
+    assert np.allclose(got['logposterior'], ref, rtol=1e-10, atol=1e-8)
+    template = dl.ShapeFitPowerSpectrumTemplate(pk_dd_fid=synthetic.pk_fid, pknow_dd_fid=synthetic.pknow_fid, f_fid=synthetic.F_FID)
+    mirror = dl.TracerPowerSpectrumMultipolesObservable(data=np.zeros(3 * k.size), k=[k] * 3, ells=(0, 2, 4), fiber_collisions=dict(fs=0.5, Dfc=0.8),
+                                                        theory=dl.KaiserTracerPowerSpectrumMultipoles(template=template))
+    assert np.allclose(mirror.matrix_full, np.asarray(obs.wmatrix.matrix_full), rtol=1e-12, atol=1e-14)
+    assert np.allclose(mirror.offset, np.asarray(obs.wmatrix.offset), rtol=1e-10, atol=1e-9)
