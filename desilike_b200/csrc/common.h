@@ -184,6 +184,20 @@ struct SolveBlock { long long poff; int ncb; int npart; const EntryMap* map; };
 // thread-per-point solve (small independent groups): Gram-partial row -> entry of its group's local system
 struct GroupEntry { long long prow; int kind; int li; int lj; };   // kind 1: g[li] -= v; 2: M[li][lj] += v (li >= lj)
 
+// Result exchange over NVLink peer memory (csrc/gather.cu): when world > 0 the finish kernels also store logposterior (and x_solved) of
+// their points straight into every rank's gather window, and the last thread block to finish publishes `seq` to every rank's flag word.
+constexpr int DLB_MAX_RANKS = 16;
+struct GatherDev {
+  int world;                               // 0: no gather
+  int signal;                              // publish the sequence number at the end of this launch (last launch of an evaluation)
+  int with_solved;
+  double* lp[DLB_MAX_RANKS];               // every rank's window, at this launch's first point: logposterior [n]
+  double* xs[DLB_MAX_RANKS];               // ... x_solved [n, ns] (plan order), or NULL
+  unsigned long long* flag[DLB_MAX_RANKS]; // this rank's flag word in every rank's window
+  unsigned long long seq;
+  unsigned* counter;                       // thread blocks that have finished (local device memory)
+};
+
 struct SolveParams {
   const double* params; int d; long long N; long long npad;
   const int* prior_kind; const double* prior_lo; const double* prior_hi; const double* prior_loc; const double* prior_scale;
@@ -201,8 +215,13 @@ struct SolveParams {
   double* hess; int nhess; const int* hess_ij; const int* comp_of;   // optional packed upper triangle of M = -H_posterior per point
   // thread-per-point form (every group <= 8 parameters): entries sorted by group, chi2 rows, offsets of the groups' constant blocks in comp_m0
   const GroupEntry* gent; const int* gent_off; const long long* chi_rows; int nchi; const int* m0_off; int comp_max;
+  GatherDev gather;
 };
 int launch_solve(const SolveParams& p, cudaStream_t stream);
+// csrc/gather.cu
+int gather_fill(dlb_gather* g, int buf, long long start, long long n, long long total, int ns, bool with_solved, bool signal, GatherDev* out);
+void gather_next_sequence(dlb_gather* g, int buf);
+int gather_publish_empty(dlb_gather* g, int buf, long long total, cudaStream_t stream);
 
 int measure_fp64_peak(int kind, double* tflops);
 

@@ -957,9 +957,29 @@ int dlb_eval_batch(dlb_plan* plan, const double* params, int64_t N, double* logp
   return dlb_eval_batch_hessian(plan, params, N, logposterior, loglikelihood, logprior, x_solved, nullptr, status, stream_);
 }
 
+static int eval_impl(dlb_plan* plan, const double* params, int64_t N, double* logposterior, double* loglikelihood, double* logprior,
+                     double* x_solved, double* hessian, int32_t* status, void* stream_, dlb_gather* gather, int gbuf, long long gstart, long long gtotal,
+                     bool gsolved);
+
 int dlb_eval_batch_hessian(dlb_plan* plan, const double* params, int64_t N, double* logposterior, double* loglikelihood, double* logprior,
                            double* x_solved, double* hessian, int32_t* status, void* stream_) {
-  DLB_REQUIRE(plan && params && N >= 0, "NULL plan / params or negative N");
+  return eval_impl(plan, params, N, logposterior, loglikelihood, logprior, x_solved, hessian, status, stream_, nullptr, 0, 0, 0, false);
+}
+
+int dlb_eval_batch_gather(dlb_plan* plan, const double* params, int64_t N, dlb_gather* gather, int32_t buf, int64_t slice_start, int64_t total,
+                          int32_t with_solved, double* loglikelihood, double* logprior, int32_t* status, void* stream_) {
+  DLB_REQUIRE(gather, "NULL gather");
+  return eval_impl(plan, params, N, nullptr, loglikelihood, logprior, nullptr, nullptr, status, stream_, gather, buf, slice_start, total, with_solved != 0);
+}
+
+static int eval_impl(dlb_plan* plan, const double* params, int64_t N, double* logposterior, double* loglikelihood, double* logprior,
+                     double* x_solved, double* hessian, int32_t* status, void* stream_, dlb_gather* gather, int gbuf, long long gstart, long long gtotal,
+                     bool gsolved) {
+  DLB_REQUIRE(plan && (params || N == 0) && N >= 0, "NULL plan / params or negative N");
+  if (gather) {
+    gather_next_sequence(gather, gbuf);
+    if (N == 0) return gather_publish_empty(gather, gbuf, gtotal, (cudaStream_t)stream_);   // a rank with an empty slice still publishes its sequence number
+  }
   if (N == 0) return DLB_OK;
   if (plan->ns == 0) hessian = nullptr;
   const int nhess = plan->ns * (plan->ns + 1) / 2;
@@ -1039,6 +1059,10 @@ int dlb_eval_batch_hessian(dlb_plan* plan, const double* params, int64_t N, doub
       sp.hess = hessian ? (hs_dev ? hessian + g0 * nhess : plan->w_hess + off * nhess) : nullptr;
       sp.nhess = nhess; sp.hess_ij = plan->d_hess_ij; sp.comp_of = plan->d_comp_of;
       sp.gent = plan->d_gent; sp.gent_off = plan->d_gent_off; sp.chi_rows = plan->d_chi_rows; sp.nchi = plan->nchi; sp.m0_off = plan->d_m0_off; sp.comp_max = plan->comp_max;
+      if (gather) {   // the finish kernel stores this sub-batch's results into every rank's window; the last launch publishes the sequence number
+        const bool last = start + CHUNK >= N && off + sublen >= n;
+        DLB_TRY(gather_fill(gather, gbuf, gstart + g0, len, gtotal, ns, gsolved, last, &sp.gather));
+      }
       rc = launch_solve(sp, stream);
       if (rc) return rc;
       if (plan->timing) DLB_CUDA(cudaEventRecord(plan->ev[3], stream));

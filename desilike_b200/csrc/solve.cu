@@ -21,7 +21,39 @@ __device__ __forceinline__ double prior_logpdf(int kind, double x, double lo, do
   return 0.;
 }
 
-__global__ void finish_nosolve_kernel(const SolveParams p) {
+// ---- result stores: the caller's buffers and, when the evaluation takes part in a multi-GPU gather, every rank's window (peer memory
+//      over NVLink; replaces the reduce + bcast of reference base.py:335, samplers/base.py:196-200) ----
+__device__ __forceinline__ void store_logpost(const SolveParams& p, long long pt, double v) {
+  if (p.logpost) p.logpost[pt] = v;
+  for (int r = 0; r < p.gather.world; ++r) p.gather.lp[r][pt] = v;
+}
+__device__ __forceinline__ void store_xsolved(const SolveParams& p, long long pt, int i, double v) {
+  if (p.xsolved) p.xsolved[pt * p.ns + i] = v;
+  if (p.gather.with_solved)
+    for (int r = 0; r < p.gather.world; ++r) p.gather.xs[r][pt * p.ns + i] = v;
+}
+__device__ __forceinline__ bool wants_xsolved(const SolveParams& p) { return p.xsolved != nullptr || p.gather.with_solved; }
+
+// End of a finish kernel that takes part in a gather: make this thread's peer stores visible system-wide; the LAST thread block of the
+// launch then publishes the evaluation's sequence number to this rank's flag word in every rank's window (release at system scope).
+// Every thread of the block must reach this call.
+__device__ __forceinline__ void gather_tail(const SolveParams& p) {
+  if (p.gather.world <= 0) return;
+  __threadfence_system();
+  if (!p.gather.signal) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(p.gather.counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *p.gather.counter = 0u;
+      __threadfence_system();
+      for (int r = 0; r < p.gather.world; ++r)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.gather.flag[r]), "l"(p.gather.seq) : "memory");
+    }
+  }
+}
+
+__device__ __forceinline__ void finish_nosolve_body(const SolveParams& p) {
   const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pt >= p.N) return;
   double chi2 = 0.;
@@ -39,15 +71,19 @@ __global__ void finish_nosolve_kernel(const SolveParams p) {
   if (!isfinite(chi2)) { st |= DLB_PT_NONFINITE; ll = CUDART_NAN; }
   if (p.loglike) p.loglike[pt] = ll;
   if (p.logprior) p.logprior[pt] = lp;
-  if (p.logpost) p.logpost[pt] = inside ? ll + lp : -CUDART_INF;
+  store_logpost(p, pt, inside ? ll + lp : -CUDART_INF);
   if (p.status) p.status[pt] = st;
+}
+
+__global__ void finish_nosolve_kernel(const __grid_constant__ SolveParams p) {
+  finish_nosolve_body(p);
+  gather_tail(p);
 }
 
 constexpr int SOLVE_WARPS = 4;
 constexpr int SOLVE_NREG = 8;   // groups of up to 8 solved parameters are factorised in registers
 
-__global__ void __launch_bounds__(SOLVE_WARPS * 32) finish_solve_kernel(const SolveParams p) {
-  extern __shared__ double sm[];
+__device__ __forceinline__ void finish_solve_body(const SolveParams& p, double* sm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ns = p.ns, ld = ns + 1;
   double* M = sm + (size_t)warp * (ns * ld + 4 * ns);
@@ -232,10 +268,10 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) finish_solve_kernel(const So
       bool in_i = true;
       lp += prior_logpdf(p.xkind[i], xi, p.xlo[i], p.xhi[i], p.xloc[i], p.xkind[i] == 2 ? rsqrt(p.xprec[i]) : 1., &in_i);
       // NB: the reference adds -inf to logprior when a solved value leaves its limits, but does not veto the point
-      if (p.xsolved) p.xsolved[pt * ns + i] = xi;
+      store_xsolved(p, pt, i, xi);
     }
-  } else if (p.xsolved) {
-    for (int i = lane; i < ns; i += 32) p.xsolved[pt * ns + i] = CUDART_NAN;
+  } else if (wants_xsolved(p)) {
+    for (int i = lane; i < ns; i += 32) store_xsolved(p, pt, i, CUDART_NAN);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -252,9 +288,15 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) finish_solve_kernel(const So
     if (!isfinite(chi2)) { st |= DLB_PT_NONFINITE; ll = CUDART_NAN; }
     if (p.loglike) p.loglike[pt] = ll;
     if (p.logprior) p.logprior[pt] = lp;
-    if (p.logpost) p.logpost[pt] = inside ? ll + lp : -CUDART_INF;
+    store_logpost(p, pt, inside ? ll + lp : -CUDART_INF);
     if (p.status) p.status[pt] = st;
   }
+}
+
+__global__ void __launch_bounds__(SOLVE_WARPS * 32) finish_solve_kernel(const __grid_constant__ SolveParams p) {
+  extern __shared__ double sm[];
+  finish_solve_body(p, sm);
+  gather_tail(p);
 }
 
 // ---- thread-per-point form: when every independent group of solved parameters has <= SOLVE_NREG members, ONE thread assembles and
@@ -263,8 +305,9 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) finish_solve_kernel(const So
 //      interleaved over the block's threads (conflict free) while it is accumulated and in registers while it is factorised. ----
 constexpr int ST_THREADS = 128;
 
-__global__ void __launch_bounds__(ST_THREADS) finish_solve_thread_kernel(const SolveParams p) {
-  extern __shared__ double sm[];   // [SOLVE_NREG * SOLVE_NREG + SOLVE_NREG][ST_THREADS]
+// sm: [SOLVE_NREG * SOLVE_NREG + SOLVE_NREG][ST_THREADS]; xstage: [ST_THREADS][ns] solved values of the block's points (or NULL), written out
+// coalesced by the kernel below (a thread's own ns values are 8-byte stores ns doubles apart: 4 x write amplification in HBM and over NVLink)
+__device__ __forceinline__ void finish_solve_thread_body(const SolveParams& p, double* sm, double* xstage) {
   const int tid = threadIdx.x;
   const long long pt = (long long)blockIdx.x * ST_THREADS + tid;
   if (pt >= p.N) return;
@@ -353,11 +396,11 @@ __global__ void __launch_bounds__(ST_THREADS) finish_solve_thread_kernel(const S
         quad += 0.5 * (-gr[i] * di + prec * di * di) + glr[i] * di;
         bool in_i = true;
         lp += prior_logpdf(p.xkind[I], xi, p.xlo[I], p.xhi[I], p.xloc[I], p.xkind[I] == 2 ? rsqrt(prec) : 1., &in_i);
-        if (p.xsolved) p.xsolved[pt * ns + I] = xi;
+        if (xstage) xstage[tid * ns + I] = xi;
       }
   }
-  if (!spd && p.xsolved)
-    for (int i = 0; i < ns; ++i) p.xsolved[pt * ns + i] = CUDART_NAN;
+  if (!spd && xstage)
+    for (int i = 0; i < ns; ++i) xstage[tid * ns + i] = CUDART_NAN;
   int st = 0;
   double ll = -0.5 * chi2 + quad - 0.5 * logdet;
   if (!inside) st |= DLB_PT_OUT_OF_PRIOR;
@@ -365,8 +408,26 @@ __global__ void __launch_bounds__(ST_THREADS) finish_solve_thread_kernel(const S
   if (!isfinite(chi2)) { st |= DLB_PT_NONFINITE; ll = CUDART_NAN; }
   if (p.loglike) p.loglike[pt] = ll;
   if (p.logprior) p.logprior[pt] = lp;
-  if (p.logpost) p.logpost[pt] = inside ? ll + lp : -CUDART_INF;
+  store_logpost(p, pt, inside ? ll + lp : -CUDART_INF);
   if (p.status) p.status[pt] = st;
+}
+
+__global__ void __launch_bounds__(ST_THREADS) finish_solve_thread_kernel(const __grid_constant__ SolveParams p) {
+  extern __shared__ double sm[];
+  double* xstage = wants_xsolved(p) ? sm + (size_t)(SOLVE_NREG * SOLVE_NREG + SOLVE_NREG) * ST_THREADS : nullptr;
+  finish_solve_thread_body(p, sm, xstage);
+  if (xstage) {
+    __syncthreads();
+    const long long e0 = (long long)blockIdx.x * ST_THREADS * p.ns;
+    const int cnt = (int)min((long long)ST_THREADS, p.N - (long long)blockIdx.x * ST_THREADS) * p.ns;
+    for (int e = threadIdx.x; e < cnt; e += ST_THREADS) {
+      const double v = xstage[e];
+      if (p.xsolved) p.xsolved[e0 + e] = v;
+      if (p.gather.with_solved)
+        for (int r = 0; r < p.gather.world; ++r) p.gather.xs[r][e0 + e] = v;
+    }
+  }
+  gather_tail(p);
 }
 
 }  // namespace
@@ -376,12 +437,13 @@ int launch_solve(const SolveParams& p, cudaStream_t stream) {
     const int threads = 256;
     finish_nosolve_kernel<<<(unsigned)((p.N + threads - 1) / threads), threads, 0, stream>>>(p);
   } else if (p.gent && p.ncomp > 0 && p.comp_max <= SOLVE_NREG && !p.hess) {
-    const size_t smem = (size_t)(SOLVE_NREG * SOLVE_NREG + SOLVE_NREG) * ST_THREADS * sizeof(double);
-    static bool configured_dev[64] = {};
-    bool& configured = configured_dev[current_device_slot()];
-    if (!configured) {
+    const bool stage = p.xsolved != nullptr || p.gather.with_solved;
+    const size_t smem = (size_t)(SOLVE_NREG * SOLVE_NREG + SOLVE_NREG + (stage ? p.ns : 0)) * ST_THREADS * sizeof(double);
+    static size_t configured_dev[64] = {};
+    size_t& configured = configured_dev[current_device_slot()];
+    if (smem > configured) {
       DLB_CUDA(cudaFuncSetAttribute(finish_solve_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
+      configured = smem;
     }
     finish_solve_thread_kernel<<<(unsigned)((p.N + ST_THREADS - 1) / ST_THREADS), ST_THREADS, smem, stream>>>(p);
   } else {

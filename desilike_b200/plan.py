@@ -104,6 +104,31 @@ class Plan(object):
             out['x_solved'] = out['x_solved_plan_order'] if self._identity_perm else out['x_solved_plan_order'][:, torch.as_tensor(self._unperm, device=X.device)]
         return out
 
+    def eval_gather(self, X, gather, buf, slice_start, total, with_solved=False, out=None):
+        """Evaluate this rank's slice ``X[n, d]`` (rows ``slice_start : slice_start + n`` of a batch of ``total`` points) and let the finish
+        kernel store logposterior (and x_solved, plan order) straight into buffer ``buf`` of EVERY rank's gather window
+        (``distributed.PeerGather``; replaces reference base.py:335 / samplers/base.py:196-200).  ``X``: float64 CUDA tensor (enqueued on the
+        current torch stream) or (pinned) host ndarray (staged by the library).  Optional local outputs in ``out``: ``loglikelihood``,
+        ``logprior`` (float64) and ``status`` (int32), CUDA tensors or host ndarrays of length n."""
+        import torch
+        out = out or {}
+        if _is_torch_cuda(X):
+            if X.dtype != torch.float64 or not X.is_contiguous() or X.dim() != 2 or X.shape[1] != self.d:
+                raise ValueError('expected a contiguous float64 CUDA tensor of shape (n, {:d})'.format(self.d))
+            xptr, device = (X.data_ptr() if X.shape[0] else None), X.device
+        else:
+            X = np.ascontiguousarray(X, dtype=np.float64)
+            if X.ndim != 2 or X.shape[1] != self.d:
+                raise ValueError('expected params of shape (n, {:d}), got {}'.format(self.d, X.shape))
+            xptr, device = (X.ctypes.data if X.shape[0] else None), gather.device
+        stream = torch.cuda.current_stream(device).cuda_stream
+
+        def ptr(key):
+            if key not in out: return None
+            return out[key].data_ptr() if _is_torch_cuda(out[key]) else out[key].ctypes.data
+        _capi.check(self._lib.dlb_eval_batch_gather(self._handle, xptr, X.shape[0], gather._handle, int(buf), int(slice_start),
+                                                    int(total), int(bool(with_solved)), ptr('loglikelihood'), ptr('logprior'), ptr('status'), ctypes.c_void_p(stream)))
+
     def theory(self, X):
         """Flat theory vectors [N, n] at the solved parameters' defaults (reference ``likelihood.flattheory``)."""
         if _is_torch_cuda(X):

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DLB_ABI_VERSION 2
+#define DLB_ABI_VERSION 3
 
 typedef enum {
   DLB_OK = 0,
@@ -183,6 +183,32 @@ int dlb_features_batch(dlb_plan* plan, int32_t gen, const double* params, int64_
  * `stream`; no host synchronisation. */
 int dlb_ensemble_step(dlb_plan* plan, double* walkers, double* logposterior, int64_t nwalkers, uint64_t seed, uint64_t iteration, double a,
                       int64_t rank_offset, uint64_t* naccept, void* stream);
+
+/* Multi-GPU result exchange over NVLink peer memory ---------------------------------------------------------------------------------
+ * The path shards by parameter point (reference desilike/base.py:310-316, partition rule mpi.py:145-150); its only exchange is returning
+ * the per-point results to every rank (reference base.py:335 pickled reduce + bcast; samplers/base.py:196-200).  One process per GPU.
+ * Every rank creates a *window* (device memory: `nbuf` buffers of `capacity` doubles + flag words), exports its CUDA IPC handle
+ * (DLB_IPC_HANDLE_BYTES bytes; the host exchanges the handles with whatever it has -- torch.distributed, MPI, a file) and connects.
+ * dlb_eval_batch_gather is dlb_eval_batch for this rank's slice [slice_start, slice_start + N) of a batch of `total` points whose finish
+ * kernel also stores logposterior (and, with_solved != 0, x_solved) straight into EVERY rank's window (buffer `buf`: logposterior [total],
+ * then x_solved [total, ns] in the plan's solved order) and publishes a per-buffer sequence number; no collective kernel runs.  Every rank
+ * must issue the same sequence of publishing calls per buffer (collective semantics).  dlb_gather_wait enqueues the acquire of all ranks'
+ * sequence numbers on `stream`: kernels enqueued after it see the complete buffer (dlb_gather_buffer).  A rank that does not publish within
+ * the timeout (default 20 s) makes later calls fail with DLB_ERR_CUDA instead of hanging the GPU.  Use one stream per gather. */
+typedef struct dlb_gather dlb_gather;
+#define DLB_IPC_HANDLE_BYTES 64
+int dlb_gather_create(int32_t rank, int32_t world, int64_t capacity, int32_t nbuf, dlb_gather** out);
+int dlb_gather_ipc_handle(const dlb_gather* gather, void* handle /* [DLB_IPC_HANDLE_BYTES] */);
+int dlb_gather_connect(dlb_gather* gather, const void* handles /* [world, DLB_IPC_HANDLE_BYTES], rank-major */);
+double* dlb_gather_buffer(dlb_gather* gather, int32_t buf);   /* this rank's copy of buffer `buf` (device pointer, [capacity]) */
+int dlb_eval_batch_gather(dlb_plan* plan, const double* params, int64_t N, dlb_gather* gather, int32_t buf, int64_t slice_start, int64_t total,
+                          int32_t with_solved, double* loglikelihood, double* logprior, int32_t* status, void* stream);
+/* Generic form: store src[0 : count] (device) at [offset, offset + count) of buffer `buf` of every rank's window and publish. */
+int dlb_gather_publish(dlb_gather* gather, int32_t buf, const double* src, int64_t count, int64_t offset, void* stream);
+int dlb_gather_wait(dlb_gather* gather, int32_t buf, void* stream);
+int dlb_gather_status(const dlb_gather* gather);   /* 0, or 1 + the first rank a wait timed out on */
+int dlb_gather_set_timeout(dlb_gather* gather, double seconds);
+void dlb_gather_destroy(dlb_gather* gather);
 
 /* Instrumentation ----------------------------------------------------------------------------------------------- */
 int64_t dlb_launch_count(void);                  /* kernels launched by this library since load (all plans) */
