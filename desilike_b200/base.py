@@ -4,13 +4,16 @@
 with ``params`` a dict name -> array (all of equal shape, rank >= 1).  The result is shaped ``params.shape`` (+ result
 shape); with ``return_derived=True`` it is the tuple ``(logposterior, derived)`` where ``derived`` holds
 ``loglikelihood``, ``logprior`` and every analytically solved parameter (reference likelihoods/base.py:342-352,363-369).
+With solved parameters, ``loglikelihood`` and ``logprior`` carry the reference's ``derivs`` tags (likelihoods/base.py:342-352,
+:388-390, :409-411): their last axis is ``[value, H[i, j] for solved pairs i <= j]`` -- the likelihood / prior Hessian in the solved
+parameters that ``Chain.sample_solved`` draws from -- addressed as ``array[()]`` and ``array[(name_i, name_j)]``.
 ``errors='return'`` -> ``(results, errs)`` with ``errs = {flat_index: (exception, traceback_str)}`` and failed slots filled
 with a copy of the first good result; ``errors='nan'`` fills them with NaN (reference base.py:193-226).
 """
 import numpy as np
 
 from . import _capi
-from .parameter import Samples
+from .parameter import Samples, ParameterArray
 from .likelihoods import PipelineError
 
 
@@ -87,15 +90,18 @@ def vmap(calculate, backend='cuda', errors='raise', return_derived=False, mpicom
         rd = kw.pop('return_derived', return_derived)
         params, shape = _check_params(params)
         X = likelihood._points(params)
+        plan = likelihood.plan
+        with_hessian = bool(rd and plan.ns and mpicomm is None)
         if mpicomm is not None:
-            res = mpicomm.eval_sharded(likelihood.plan, X)
+            res = mpicomm.eval_sharded(plan, X)   # (the per-point Hessians are not exchanged: sharded calls return untagged derived values)
         else:
-            res = likelihood.plan.eval(X)
+            res = plan.eval(X, return_hessian=with_hessian)
         errs = status_to_errors(res['status'])
         if errs and errors == 'raise':
             raise errs[min(errs)][0]
         out = {key: np.array(res[key]) for key in ['logposterior', 'loglikelihood', 'logprior']}
         xs = np.array(res['x_solved']) if 'x_solved' in res else None
+        good = []
         if errs:
             good = [i for i in range(X.shape[0]) if i not in errs]
             for key in out:
@@ -104,7 +110,26 @@ def vmap(calculate, backend='cuda', errors='raise', return_derived=False, mpicom
             if xs is not None:
                 xs[list(errs)] = np.nan if (errors == 'nan' or not good) else xs[good[0]]
         results = out['logposterior'].reshape(shape)
-        if rd:
+        if rd and with_hessian:
+            # derivs tags: () then every pair of solved parameters exported to derived (reference likelihoods/base.py:342-352)
+            solved = [s for s in plan.spec.get('solved', [])]
+            keep = [i for i, s in enumerate(solved) if not str(s.get('derived', '')).endswith('not_derived')]
+            pairs = [(i, j) for a, i in enumerate(keep) for j in keep[a:]]
+            tags = [()] + [(solved[i]['name'], solved[j]['name']) for i, j in pairs]
+            prec = np.array([1. / float(s['prior']['scale'])**2 if (s.get('prior') or {}).get('dist') == 'norm' and np.isfinite(float(s['prior'].get('scale', np.inf))) else 0.
+                             for s in solved])
+            H = np.array(res['hessian'])                       # posterior Hessian in the solved parameters, spec order
+            if errs: H[list(errs)] = np.nan if (errors == 'nan' or not good) else H[good[0]]
+            ii, jj = [i for i, _ in pairs], [j for _, j in pairs]
+            Hprior = -np.diag(prec)
+            ll = np.concatenate([out['loglikelihood'][:, None], (H - Hprior)[:, ii, jj]], axis=-1)
+            lp = np.concatenate([out['logprior'][:, None], np.broadcast_to(Hprior[ii, jj], (X.shape[0], len(pairs)))], axis=-1)
+            derived = Samples(loglikelihood=ParameterArray(ll.reshape(shape + (len(tags),)), derivs=tags),
+                              logprior=ParameterArray(lp.reshape(shape + (len(tags),)), derivs=tags))
+            for i, name in enumerate(plan.solved_names):
+                derived[name] = xs[:, i].reshape(shape)
+            results = (results, derived)
+        elif rd:
             derived = Samples(loglikelihood=out['loglikelihood'].reshape(shape), logprior=out['logprior'].reshape(shape))
             for i, name in enumerate(likelihood.plan.solved_names):
                 derived[name] = xs[:, i].reshape(shape)

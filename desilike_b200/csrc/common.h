@@ -87,6 +87,8 @@ struct BlockDev {     // one output block as seen by the contraction kernel (dev
   int n1, n2;
   const int* cb_first;                 // [ncb] first k-chunk with a non-zero tile in each column block (leading all-zero tiles of a
                                        // rank-reduced, lower-triangular problem are neither loaded nor multiplied), or NULL
+  const unsigned long long* tmask;     // [ncb][nchunks][2] per (column block, k-chunk, warp of the pair): 3 bits per k4 step = number of leading
+                                       // n-tiles of that warp with a non-zero 4 x 8 sub-tile at or before that step (~0: everything is multiplied), or NULL
   const double* tdata;                 // output mode: [ncols] data d of the 'cubic'-transformed columns (0: untransformed column), or NULL
 };
 

@@ -81,7 +81,9 @@ __device__ __forceinline__ double ipow(double x, int n) {
   return r;
 }
 
-// One k-chunk of DMMAs for MTC active m-tiles: acc[mt][nt] += (beta[mt] * A[mt-rows, k]) . B[k, nt-cols]
+// One k-chunk of DMMAs for MTC active m-tiles: acc[mt][nt] += (beta[mt] * A[mt-rows, k]) . B[k, nt-cols].
+// The two warps of a pair interleave their n-tiles (warp wn owns the 8-column tiles 2 nt + wn of the column block), so that column
+// blocks whose right part is structurally zero (triangular rank-reduced problems, padding of the last block) stay balanced over the pair.
 template <int MT, int NT, int MTC, int KC>
 __device__ __forceinline__ void mma_chunk(double (&acc)[MT][NT][2], const double* __restrict__ A, int astride, const double* __restrict__ B,
                                           const double (&beta)[MT], int nk4) {
@@ -91,7 +93,7 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[MT][NT][2], const double
 #pragma unroll
     for (int mt = 0; mt < MTC; ++mt) a[mt] = A[mt * astride + k4 * 4] * beta[mt];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) b[nt] = B[nt * 8 * KC + k4 * 4];
+    for (int nt = 0; nt < NT; ++nt) b[nt] = B[nt * 16 * KC + k4 * 4];
 #pragma unroll
     for (int mt = 0; mt < MTC; ++mt)
 #pragma unroll
@@ -99,9 +101,56 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[MT][NT][2], const double
   }
 }
 
+// A run of k4 steps restricted to the first NTC n-tiles of the warp
+template <int MT, int NT, int NTC, int KC>
+__device__ __forceinline__ void mma_run(double (&acc)[MT][NT][2], const double* __restrict__ A, int astride, const double* __restrict__ B,
+                                        const double (&beta)[MT], int k4a, int k4b, int mtc) {
+#pragma unroll 2
+  for (int k4 = k4a; k4 < k4b; ++k4) {
+    double a[MT], b[NTC];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) a[mt] = mt < mtc ? A[mt * astride + k4 * 4] * beta[mt] : 0.;
+#pragma unroll
+    for (int nt = 0; nt < NTC; ++nt) b[nt] = B[nt * 16 * KC + k4 * 4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+      if (mt < mtc) {
+#pragma unroll
+        for (int nt = 0; nt < NTC; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+      }
+  }
+}
+
+// Masked k-chunk: `mask` holds, 3 bits per k4 step, the number of leading n-tiles of this warp whose B sub-tile (4 rows x 8 columns) is
+// not structurally zero from that step on (plan-time table, csrc/plan.cu: build_block_core).  Zero sub-tiles of lower-triangular
+// (rank-reduced) term matrices and of the padding of the last column block are neither loaded nor multiplied.  The chunk is walked in
+// runs of constant count (the count never decreases inside a chunk).
+template <int MT, int NT, int KC>
+__device__ __forceinline__ void mma_chunk_masked(double (&acc)[MT][NT][2], const double* A, int astride, const double* B, const double (&beta)[MT],
+                                                 int nk4, int mtc, unsigned long long mask) {
+  int k4 = 0;
+  while (k4 < nk4) {
+    const int nact = (int)((mask >> (3 * k4)) & 7ull);
+    int k4e = k4 + 1;
+    while (k4e < nk4 && (int)((mask >> (3 * k4e)) & 7ull) == nact) ++k4e;
+    switch (nact < NT ? nact : NT) {
+      case 0: break;
+      case 1: mma_run<MT, NT, 1, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+      case 2: if constexpr (NT >= 2) mma_run<MT, NT, 2, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+      case 3: if constexpr (NT >= 3) mma_run<MT, NT, 3, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+      case 4: if constexpr (NT >= 4) mma_run<MT, NT, 4, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+      case 5: if constexpr (NT >= 5) mma_run<MT, NT, 5, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+      case 6: if constexpr (NT >= 6) mma_run<MT, NT, 6, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+      default: if constexpr (NT >= 7) mma_run<MT, NT, 7, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+    }
+    k4 = k4e;
+  }
+}
+
 template <int MT, int NT, int KC>
 __device__ __forceinline__ void mma_chunk_dispatch(double (&acc)[MT][NT][2], const double* A, int astride, const double* B, const double (&beta)[MT],
-                                                   int nk4, int mtc) {
+                                                   int nk4, int mtc, unsigned long long mask) {
+  if (mask != ~0ull) { mma_chunk_masked<MT, NT, KC>(acc, A, astride, B, beta, nk4, mtc, mask); return; }
   if (mtc == MT) { mma_chunk<MT, NT, MT, KC>(acc, A, astride, B, beta, nk4); return; }
   if constexpr (MT > 1) { if (mtc == 1) { mma_chunk<MT, NT, 1, KC>(acc, A, astride, B, beta, nk4); return; } }
   if constexpr (MT > 2) { if (mtc == 2) { mma_chunk<MT, NT, 2, KC>(acc, A, astride, B, beta, nk4); return; } }
@@ -379,6 +428,8 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
       for (int cb = 0; cb < ncb; ++cb) {
         const int cfirst = cb_first ? __ldg(cb_first + cb) : 0;
         int4 ch_next = __ldg(reinterpret_cast<const int4*>(chunks + (cfirst < nchunks ? cfirst : 0)));   // slot, coef, fcol, kc (prefetched one chunk ahead)
+        const unsigned long long* tmask = blk->tmask ? blk->tmask + ((size_t)cb * nchunks) * 2 + wn : nullptr;   // [ncb][nchunks][2]
+        unsigned long long mask_next = tmask ? __ldg(tmask + 2 * (cfirst < nchunks ? cfirst : 0)) : ~0ull;
         double acc[R][MT][NT][2];
 #pragma unroll
         for (int sl = 0; sl < R; ++sl)
@@ -389,14 +440,16 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
 
         for (int c = cfirst; c < nchunks; ++c) {
           const int4 ch = ch_next;
+          const unsigned long long mask = mask_next;
           ch_next = __ldg(reinterpret_cast<const int4*>(chunks + (c + 1 < nchunks ? c + 1 : c)));
+          if (tmask) mask_next = __ldg(tmask + 2 * (c + 1 < nchunks ? c + 1 : c));
           double beta[MT];
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) beta[mt] = ch.y >= 0 ? cs[ch.y * BM + mt * UNIT + wm * 8 + lr] : 1.;
           PROF(3)
           mbar_wait(&full[s], ph);
           PROF((c == cfirst ? (cb == 0 ? 1 : 7) : 4))
-          const double* Bp = stage_base + (size_t)s * STAGE_DOUBLES + (wn * (NT * 8) + lr) * KC + lc;
+          const double* Bp = stage_base + (size_t)s * STAGE_DOUBLES + (wn * 8 + lr) * KC + lc;
           const double* Ap;
           int astride;
           if constexpr (RESIDENT) { Ap = A_s + (wm * 8 + lr) * p.ast + ch.z + lc; astride = UNIT * p.ast; }
@@ -404,7 +457,7 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
           const int nk4 = ch.w >> 2;
 #pragma unroll
           for (int sl = 0; sl < R; ++sl)
-            if (ch.x == sl) mma_chunk_dispatch<MT, NT, KC>(acc[sl], Ap, astride, Bp, beta, nk4, mtc);
+            if (ch.x == sl) mma_chunk_dispatch<MT, NT, KC>(acc[sl], Ap, astride, Bp, beta, nk4, mtc, mask);
           PROF(3)
           release(s);
           PROF(5)
@@ -414,7 +467,7 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
         // ===== epilogue: r0 of this column block arrives as one more transaction of the ring =====
         mbar_wait(&full[s], ph);
         PROF(0)
-        const int colw = wn * (NT * 8) + 2 * lc;  // + nt * 8 + e
+        const int colw = wn * 8 + 2 * lc;  // + nt * 16 + e   (interleaved n-tiles: warp wn owns the 8-column tiles 2 nt + wn)
         const double* epi = stage_base + (size_t)s * STAGE_DOUBLES;
         const double* r0 = epi;
         if (p.mode == 1) {
@@ -426,9 +479,9 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
               for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                  const int col = cb * BN + colw + nt * 8 + e;
+                  const int col = cb * BN + colw + nt * 16 + e;
                   if (row < p.out_rows && col < blk->ncols) {
-                    double v = acc[0][mt][nt][e] + r0[colw + nt * 8 + e];
+                    double v = acc[0][mt][nt][e] + r0[colw + nt * 16 + e];
                     if (p.act == 1) v = silu(v);                   // silu  (reference emulators/conversion.py:27)
                     else if (p.act == 2) v = fmax(v, 0.);          // relu  (:29)
                     else if (p.act == 3) v = tanh(v);              // tanh  (:31)
@@ -444,7 +497,7 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
         } else {
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
-            const double2 rr = *reinterpret_cast<const double2*>(r0 + colw + nt * 8);
+            const double2 rr = *reinterpret_cast<const double2*>(r0 + colw + nt * 16);
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) { acc[0][mt][nt][0] -= rr.x; acc[0][mt][nt][1] -= rr.y; }
           }
@@ -455,7 +508,7 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
           for (int i = 0; i < nconst; ++i) {
             const int within = blk->ncols + i - cb * BN;
             if (within < 0 || within >= BN) continue;
-            const int wni = within / (NT * 8), w2 = within - wni * (NT * 8), nti = w2 >> 3, lci = (w2 & 7) >> 1, ei = w2 & 1;
+            const int jt = within >> 3, wni = jt & 1, nti = jt >> 1, lci = (within & 7) >> 1, ei = within & 1;
             const bool mine = wn == wni && lc == lci;
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)

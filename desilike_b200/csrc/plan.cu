@@ -20,6 +20,8 @@ struct Block {
   int ncols = 0, nslots = 1, nconst = 0, ncb = 0, nchunks = 0, npart = 0, coloff = 0, gen = -1, maxcol = 0;
   std::vector<Chunk> h_chunks;
   int* d_cb_first = nullptr; std::vector<int> cb_first;   // whitened tiles: first non-zero k-chunk per column block
+  unsigned long long *d_tmask_white = nullptr, *d_tmask_plain = nullptr;   // [ncb][nchunks][2] sub-tile masks (contract.cu: mma_chunk_masked), NULL: dense
+  std::vector<double> exec_white, exec_plain;   // [ncb * nchunks] multiplied (row, column) pairs of every (column block, k-chunk) tile
   int ncols_w = 0, ncb_plain = 0;   // columns of the whitened matrices (rank-reduced plans: < ncols) / column blocks of the un-whitened tiles
   int fill = 0, fbase = 0;   // resident A: 0 = Taylor monomials evaluated in the kernel, 1 = copied from the feature matrix at column fbase
   long long poff = 0;
@@ -226,6 +228,46 @@ static int build_block_core(dlb_plan* plan, const Variant& var, bool resident, i
         }
       }
     DLB_TRY(upload(plan, tiles.data(), tiles.size(), pass == 0 ? &blk.d_tiles_white : &blk.d_tiles_plain));
+    {
+      // Sub-tile masks.  Warp wn of a pair owns the 8-column n-tiles j = 2 nt + wn of a column block.  For every (column block, k-chunk,
+      // warp): first k4 step (4 rows) at which n-tile nt holds a non-zero, made monotone in nt (min over nt' >= nt) so that the active
+      // n-tiles at every step form a prefix; encoded as 3 bits per k4 step = number of active n-tiles.  ~0 = multiply everything.
+      const int NT = var.NT, nj = 2 * NT;
+      std::vector<unsigned long long> masks((size_t)ncb * blk.nchunks * 2, ~0ull);
+      std::vector<double>& exec = pass == 0 ? blk.exec_white : blk.exec_plain;
+      exec.assign((size_t)ncb * blk.nchunks, 0.);
+      bool any_mask = false;
+      for (int cb = 0; cb < ncb; ++cb)
+        for (int c = 0; c < blk.nchunks; ++c) {
+          const double* t = tiles.data() + ((size_t)cb * blk.nchunks + c) * tile;
+          const int nk4 = chunks[c].kc >> 2;
+          std::vector<int> kf(nj, nk4);   // first non-zero k4 step of n-tile j (nk4: none)
+          for (int j = 0; j < nj; ++j)
+            for (int k4 = 0; k4 < nk4 && kf[j] == nk4; ++k4)
+              for (int n = 8 * j; n < 8 * j + 8 && kf[j] == nk4; ++n)
+                for (int k = 4 * k4; k < 4 * k4 + 4; ++k)
+                  if (t[(size_t)n * KC + k] != 0.) { kf[j] = k4; break; }
+          for (int wn = 0; wn < 2; ++wn) {
+            std::vector<int> start(NT);
+            int run = nk4;
+            for (int nt = NT - 1; nt >= 0; --nt) { run = std::min(run, kf[2 * nt + wn]); start[nt] = run; }
+            unsigned long long w = 0ull;
+            bool full = true;
+            for (int k4 = 0; k4 < nk4; ++k4) {
+              int nact = 0;
+              for (int nt = 0; nt < NT; ++nt) nact += start[nt] <= k4 ? 1 : 0;
+              full = full && nact == NT;
+              w |= (unsigned long long)nact << (3 * k4);
+              exec[(size_t)cb * blk.nchunks + c] += 4. * 8. * nact;
+            }
+            if (nk4 > 21) { full = true; }   // cannot happen (KC <= 76); keep the dense path if it ever does
+            if (!full && !getenv("DLB_NO_SUBTILE_SKIP")) { masks[((size_t)cb * blk.nchunks + c) * 2 + wn] = w; any_mask = true; }
+            else exec[(size_t)cb * blk.nchunks + c] += 0.;
+          }
+          if (getenv("DLB_NO_SUBTILE_SKIP")) exec[(size_t)cb * blk.nchunks + c] = (double)chunks[c].kc * BN;
+        }
+      if (any_mask) DLB_TRY(upload(plan, masks.data(), masks.size(), pass == 0 ? &blk.d_tmask_white : &blk.d_tmask_plain));
+    }
     if (pass == 0 && !getenv("DLB_NO_TILE_SKIP")) {   // leading all-zero tiles per column block (rank-reduced problems are lower triangular)
       blk.cb_first.assign(ncb, 0);
       bool any_skip = false;
@@ -318,6 +360,7 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
       bd.ncols = pass == 0 ? b->ncols_w : b->ncols;
       bd.ocol0 = b->coloff; bd.gen = b->gen; bd.fill = b->fill; bd.fbase = b->fbase; bd.acols = std::min((b->maxcol + 1) & ~1, L.ast);
       bd.tdata = pass == 1 ? b->d_tdata : nullptr;
+      bd.tmask = pass == 0 ? b->d_tmask_white : b->d_tmask_plain;
       bd.cb_first = pass == 0 ? b->d_cb_first : nullptr;
       tab.push_back(bd);
     }
@@ -336,7 +379,8 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
       DLB_REQUIRE(b->nchunks < 65536 && blocks.size() < 32768, "too many chunks / blocks in one launch");
       for (int cb = 0; cb < tab[ib].ncb; ++cb) {
         for (int c = (pass == 0 && !b->cb_first.empty()) ? b->cb_first[cb] : 0; c < b->nchunks; ++c) {
-          (pass == 0 ? L.flops_exec : L.flops_exec_plain) += 2. * b->h_chunks[c].kc * BN;
+          const std::vector<double>& ex = pass == 0 ? b->exec_white : b->exec_plain;
+          (pass == 0 ? L.flops_exec : L.flops_exec_plain) += 2. * (ex.empty() ? (double)b->h_chunks[c].kc * BN : ex[(size_t)cb * b->nchunks + c]);
           sched.push_back(SchedEntry{tab[ib].tiles + ((size_t)cb * b->nchunks + c) * ((size_t)BN * KC), (unsigned)(BN * KC * 8), (int)((ib << 16) | (unsigned)c)});
         }
         sched.push_back(SchedEntry{tab[ib].epi + (size_t)cb * BN, (unsigned)(BN * 8), -1});

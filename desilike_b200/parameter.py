@@ -112,6 +112,31 @@ class ParameterCollection(object):
         return 'ParameterCollection({})'.format(self.names())
 
 
+class ParameterArray(np.ndarray):
+    """Array of a derived quantity over the batch.  With ``derivs`` (a list of tags: ``()`` = the value, ``(name1, name2)`` = second
+    derivative w.r.t. two solved parameters) the LAST axis runs over the tags, as in the reference's ``ParameterArray``
+    (desilike/parameter.py:407-448, :570-597): ``array[()]`` is the value, ``array[('a', 'b')]`` the Hessian entry (order-insensitive)."""
+
+    def __new__(cls, value, derivs=None):
+        obj = np.asarray(value, dtype='f8').view(cls)
+        obj.derivs = None if derivs is None else [tuple(d) for d in derivs]
+        return obj
+
+    def __array_finalize__(self, obj):
+        self.derivs = getattr(obj, 'derivs', None)
+
+    def __getitem__(self, index):
+        derivs = getattr(self, 'derivs', None)
+        if derivs is not None and isinstance(index, tuple) and all(isinstance(i, str) for i in index):
+            key = tuple(sorted(index))
+            for i, d in enumerate(derivs):
+                if tuple(sorted(d)) == key: return np.asarray(self)[..., i]
+            raise KeyError('{} is not in computed derivatives: {}'.format(index, derivs))
+        out = np.ndarray.__getitem__(self, index)
+        if isinstance(out, ParameterArray): out.derivs = None   # a generic slice no longer spans the tag axis
+        return out
+
+
 class Samples(dict):
     """Derived outputs of a batched call: name -> array shaped like the input batch (stand-in for desilike's Samples)."""
 

@@ -70,11 +70,24 @@ def test_api_matches_reference_outputs(gpu_required, name):
     finite = np.isfinite(ref)
     assert errs == {} and np.array_equal(np.isneginf(ref), np.isneginf(res))
     assert np.allclose(res[finite], ref[finite], rtol=1e-9, atol=1e-7)
-    assert np.allclose(derived['loglikelihood'][finite], data['loglikelihood'][finite], rtol=1e-9, atol=1e-7)
-    if spec['solved'] and case['mode'] != '.prec':   # '.prec' parameters are marginalised into the precision: no solved values
-        orc = pipeline.evaluate(spec, X)
+    tagged = bool(spec['solved']) and case['mode'] != '.prec'
+    dll = derived['loglikelihood'][()] if tagged else derived['loglikelihood']
+    assert np.allclose(dll[finite], data['loglikelihood'][finite], rtol=1e-9, atol=1e-7)
+    if tagged:   # '.prec' parameters are marginalised into the precision: no solved values
+        orc = pipeline.evaluate(spec, X, return_hessian=True)
         for i, s in enumerate(spec['solved']):
             assert np.allclose(derived[s['name']], orc['x_solved'][:, i], rtol=1e-7, atol=1e-7)
+        # derivs-tagged Hessian entries (reference likelihoods/base.py:342-352, :388-390, :409-411): likelihood + prior Hessian = posterior Hessian
+        names = [s['name'] for s in spec['solved']]
+        assert derived['loglikelihood'].derivs[0] == () and derived['loglikelihood'].shape == X.shape[:1] + (1 + len(names) * (len(names) + 1) // 2,)
+        for i, a in enumerate(names):
+            for j, b in enumerate(names[i:], start=i):
+                hp = derived['loglikelihood'][(a, b)] + derived['logprior'][(b, a)]
+                assert np.allclose(hp[finite], orc['hessian'][finite, i, j], rtol=1e-7, atol=1e-9 * np.max(np.abs(orc['hessian'][finite])))
+        prior = spec['solved'][0].get('prior') or {}
+        if prior.get('dist') == 'norm':
+            assert np.allclose(derived['logprior'][(names[0], names[0])], -1. / prior['scale']**2)
+        assert np.allclose(derived['logprior'][()][finite], data['logprior'][finite], rtol=1e-9, atol=1e-7)
 
 
 def test_marg_invariant_under_sum_and_sumlikelihood(gpu_required):
@@ -226,3 +239,41 @@ def test_systematic_templates(gpu_required):
     assert np.max(np.abs(like.plan.theory(X) - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-10
     assert np.max(np.abs(got['logposterior'] - ref['logposterior']) / np.maximum(1., np.abs(ref['logposterior']))) < 1e-8
     assert np.max(np.abs(got['x_solved'] - ref['x_solved'])) < 1e-7 * max(1., np.max(np.abs(ref['x_solved'])))
+
+
+def test_vmap_error_conventions_on_failed_points(gpu_required):
+    """reference base.py:193-226 on the CUDA path: a point whose normal equations are singular is an error -- errors='raise' raises,
+    'return' reports it in ``errs`` and fills its slot with a copy of the first good result, 'nan' fills NaN; a non-finite theory is not an
+    exception (NaN propagates, as in the reference where samplers map it to -inf, samplers/base.py:187-191)."""
+    spec = configs.config_kaiser_window(eftlike=True, solved=True)
+    like = make_kaiser_likelihood(spec, eftlike=True, mode='.marg')
+    for p in like.all_params:
+        if p.name == 'b1': p.update(prior=None)
+    rng = np.random.default_rng(4)
+    n = 6
+    params = {'b1': rng.uniform(1.5, 2.5, n), 'qpar': rng.uniform(0.98, 1.02, n)}
+    good = dl.vmap(like)(params)
+    assert np.all(np.isfinite(good))
+    params['b1'][2] = 1e200          # overflows the theory: NaN, not an error
+    res, errs = dl.vmap(like, errors='return')(params)
+    assert errs == {} and np.isnan(res[2]) and np.allclose(np.delete(res, 2), np.delete(good, 2))
+    # singular normal equations at every point but handled per point: drop the prior of a solved parameter and zero its template
+    plan = like.plan
+    spec2 = dict(plan.spec)
+    spec2['solved'] = [dict(s) for s in spec2['solved']]
+    name = spec2['solved'][0]['name']
+    spec2['solved'][0]['prior'] = None
+    spec2['observables'] = [dict(o, terms=[dict(t, colvec=np.zeros_like(t['colvec'])) if t.get('solved') == name else t for t in o['terms']]) for o in spec2['observables']]
+
+    class Wrapped(object):
+        def __init__(self, like, plan): self._like, self.plan = like, plan
+        def _points(self, params): return self._like._points(params)
+
+    bad = Wrapped(like, dl.Plan(spec2))
+    params['b1'][2] = 2.
+    with pytest.raises(ArithmeticError):
+        dl.vmap(bad, errors='raise')(params)
+    res, errs = dl.vmap(bad, errors='return')(params)
+    assert sorted(errs) == list(range(n)) and isinstance(errs[0][0], ArithmeticError) and np.all(np.isnan(res))   # no good point to copy from
+    res = dl.vmap(bad, errors='nan')(params)
+    assert np.all(np.isnan(res))

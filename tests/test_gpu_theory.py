@@ -11,7 +11,7 @@ from oracle import configs, pipeline
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURES = sorted(f for f in glob.glob(os.path.join(HERE, 'golden', '*.npz')) if 'bao_theory' not in f and 'bao_broadband' not in f and 'lpt_combine' not in f and 'xi_window' not in f and 'covariance_corrections' not in f and 'fiber_collisions' not in f)
+FIXTURES = sorted(f for f in glob.glob(os.path.join(HERE, 'golden', '*.npz')) if 'bao_theory' not in f and 'bao_broadband' not in f and 'lpt_combine' not in f and 'xi_window' not in f and 'covariance_corrections' not in f and 'fiber_collisions' not in f and 'taylor_state' not in f)
 
 
 def test_kaiser_tables_match_oracle(gpu_required):
@@ -259,3 +259,25 @@ def test_nonuniform_template_grids(gpu_required):
     refb = pipeline.evaluate(specb, Xb, return_theory=True)
     assert np.max(np.abs(planb.theory(Xb) - refb['flattheory'])) < 1e-10 * np.max(np.abs(refb['flattheory']))
     planb.close()
+
+
+def test_taylor_state_from_reference_fit_on_gpu(gpu_required):
+    """The 'taylor' generator (monomials evaluated inside the contraction kernel) on the state produced by the reference's own in-tree
+    ``TaylorEmulatorEngine._fit_no_operation`` (tests/golden/taylor_state.npz, generator tests/golden/make_taylor_state.py): theory vectors ==
+    the generating polynomial, element-wise 1e-10 (the reference layout of center / powers / derivatives is what the CUDA path consumes)."""
+    import desilike_b200
+    data = np.load(os.path.join(HERE, 'golden', 'taylor_state.npz'))
+    params = [str(p) for p in data['params']]
+    T = len(data['powers'])
+    ny = int(np.prod(data['yshape']))
+    theory = dict(kind='taylor', params=params, center=data['center'], powers=data['powers'], tables={'y': data['derivatives'].reshape(T, ny)})
+    obs = dict(name='poly', theory=theory, terms=[dict(scale=1., factors=[], table='y')], nin=ny, wmatrix=None, offset=None, data=np.zeros(ny))
+    spec = dict(params=params, priors={p: None for p in params}, solved=[], observables=[obs], precision=[np.eye(ny)])
+    for reduce_rank in (True, False):
+        plan = desilike_b200.Plan(spec, reduce_rank=reduce_rank)
+        got = plan.theory(data['xtest'])
+        want = data['ytest'].reshape(len(got), ny)
+        assert np.max(np.abs(got - want) / np.abs(want)) < 1e-10
+        chi2 = -2. * plan.eval(data['xtest'])['loglikelihood']
+        assert np.allclose(chi2, np.sum(want**2, axis=-1), rtol=1e-11)
+        plan.close()

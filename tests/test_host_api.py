@@ -123,6 +123,31 @@ def test_emulator_file_round_trip(tmp_path):
     assert np.allclose(pipeline.evaluate(built, X[:, cols])['logposterior'], pipeline.evaluate(spec, X)['logposterior'], rtol=1e-12, atol=1e-9)
 
 
+def test_reference_fitted_taylor_state_through_emulator_file(tmp_path):
+    """An emulator file whose Taylor engine arrays come from the reference's own fit (tests/golden/taylor_state.npz, produced by the unmodified
+    ``TaylorEmulatorEngine._fit_no_operation``) and whose keys are the ones the reference writes: load -> theory spec keeps
+    the reference layout bit for bit, and its prediction is the generating polynomial."""
+    from oracle import core
+    data = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'taylor_state.npz'))
+    params = [str(p) for p in data['params']]
+    ny = tuple(int(i) for i in data['yshape'])
+    engine = {'name': 'taylor', 'params': params, 'xshape': (len(params),), 'yshape': ny, 'xoperations': [], 'yoperations': [],
+              'center': data['center'], 'derivatives': data['derivatives'], 'powers': data['powers']}
+    state = {'engines': {'pk_dd': engine}, 'xoperations': [], 'yoperations': [], 'defaults': dict(zip(params, data['center'])),
+             'fixed': {'k': np.linspace(0.01, 0.2, ny[1]), 'ells': (0, 2), 'z': 1., 'names': ['pk_dd']}, 'varied_params': params,
+             'in_calculator_state': ['pk_dd'], 'calculator__class__': ('desilike.theories.galaxy_clustering.full_shape', 'KaiserPowerSpectrumMultipoles'),
+             'is_calculator_sequence': False, 'yaml_data': {}, 'all_params': {'data': [dict(basename=p, namespace='', value=float(c), fixed=False, prior=None, ref=None, derived=False)
+                                                                                       for p, c in zip(params, data['center'])]}}
+    fn = str(tmp_path / 'ref_taylor.npy')
+    np.save(fn, state, allow_pickle=True)
+    got = dl.EmulatedCalculator.load(fn).theory_spec()
+    assert got['kind'] == 'taylor' and list(got['params']) == params
+    assert np.array_equal(got['powers'], data['powers']) and np.array_equal(got['center'], data['center'])
+    assert np.array_equal(got['tables']['pk_dd'], data['derivatives'].reshape(len(data['powers']), -1))
+    pred = core.taylor_predict(data['xtest'], got['center'], got['powers'], got['tables']['pk_dd'])
+    assert np.max(np.abs(pred - data['ytest'].reshape(len(pred), -1))) < 1e-13 * np.max(np.abs(data['ytest']))
+
+
 def test_mlp_emulator_file_round_trip(tmp_path):
     rng = np.random.default_rng(3)
     kin = np.arange(1, 21) * (0.35 / 20)

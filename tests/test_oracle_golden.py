@@ -9,7 +9,7 @@ import pytest
 from oracle import configs, pipeline
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURES = sorted(f for f in glob.glob(os.path.join(HERE, 'golden', '*.npz')) if 'bao_theory' not in f and 'bao_broadband' not in f and 'lpt_combine' not in f and 'xi_window' not in f and 'covariance_corrections' not in f and 'fiber_collisions' not in f)
+FIXTURES = sorted(f for f in glob.glob(os.path.join(HERE, 'golden', '*.npz')) if 'bao_theory' not in f and 'bao_broadband' not in f and 'lpt_combine' not in f and 'xi_window' not in f and 'covariance_corrections' not in f and 'fiber_collisions' not in f and 'taylor_state' not in f)
 
 
 def load_case(fn):
@@ -70,3 +70,21 @@ def test_lpt_combine_fixture():
     for pars, table, power in zip(data['pars'], data['table'], data['power']):
         assert np.allclose(core.tablevel_combine_bias_terms_poles(data['pktable'], pars, nd=nd), table, rtol=1e-13, atol=0.)
         assert np.max(np.abs(core.lpt_tracer_power(data['pktable'], data['kpt'], data['k'], pars, nd=nd) - power)) <= 1e-12 * np.max(np.abs(power))
+
+
+def test_taylor_state_from_reference_fit():
+    """Taylor predict layout pinned to the reference's OWN in-tree fit: tests/golden/taylor_state.npz holds center / powers / derivatives as
+    produced by the unmodified ``TaylorEmulatorEngine._fit_no_operation`` (reference emulators/__init__.py:471-507; generator
+    tests/golden/make_taylor_state.py) from the exact derivatives of a known polynomial; the oracle's predict on that state must return the
+    polynomial, and the oracle's own term enumeration must be the same set of multi-indices in the same order."""
+    from oracle import core
+    data = np.load(os.path.join(HERE, 'golden', 'taylor_state.npz'))
+    center, powers, derivatives = data['center'], data['powers'], data['derivatives']
+    got = core.taylor_predict(data['xtest'], center, powers, derivatives)
+    assert got.shape == data['ytest'].shape
+    assert np.max(np.abs(got - data['ytest'])) < 1e-13 * np.max(np.abs(data['ytest']))
+    assert np.array_equal(core.taylor_terms(len(center), int(powers.sum(axis=-1).max())), powers)
+    # the oracle's own polynomial fit (finite differences on the stencil) lands on the same coefficients as the reference's fit of exact derivatives
+    pw, dv = core.taylor_fit_polynomial(lambda X: core.taylor_predict(X, center, powers, derivatives).reshape(len(X), -1), center, len(center), 4, np.full(len(center), 0.02))
+    assert np.array_equal(pw, powers)
+    assert np.max(np.abs(dv.reshape(derivatives.shape) - derivatives)) < 1e-6 * np.max(np.abs(derivatives))
