@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, 'csrc')
 LIBDIR = os.path.join(ROOT, 'lib')
 LIBPATH = os.path.join(LIBDIR, 'libdesilike_b200.so')
-SOURCES = ['plan.cu', 'contract.cu', 'features.cu', 'theory_kernels.cu', 'solve.cu', 'peaks.cu', 'sampler.cu', 'mlp.cu', 'gather.cu']
+SOURCES = ['plan.cu', 'contract.cu', 'contract_masked.cu', 'features.cu', 'theory_kernels.cu', 'solve.cu', 'peaks.cu', 'sampler.cu', 'mlp.cu', 'gather.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC', '-shared',
               '-cudart', 'static']
 
@@ -27,7 +27,7 @@ def _compile(nvcc, flags, objdir, out, force, verbose, extra=()):
     """Per-source objects compiled in parallel (only the stale ones), then one link step."""
     from concurrent.futures import ThreadPoolExecutor
     os.makedirs(objdir, exist_ok=True)
-    headers = [os.path.join(CSRC, 'common.h'), os.path.join(ROOT, '..', 'include', 'desilike_b200.h')]
+    headers = [os.path.join(CSRC, 'common.h'), os.path.join(CSRC, 'contract.cu'), os.path.join(ROOT, '..', 'include', 'desilike_b200.h')]
     hm = max(os.path.getmtime(h) for h in headers if os.path.exists(h))
     cflags = [f for f in flags if f not in ('-shared',)]
     jobs = []

@@ -87,8 +87,8 @@ struct BlockDev {     // one output block as seen by the contraction kernel (dev
   int n1, n2;
   const int* cb_first;                 // [ncb] first k-chunk with a non-zero tile in each column block (leading all-zero tiles of a
                                        // rank-reduced, lower-triangular problem are neither loaded nor multiplied), or NULL
-  const unsigned long long* tmask;     // [ncb][nchunks][2] per (column block, k-chunk, warp of the pair): 3 bits per k4 step = number of leading
-                                       // n-tiles of that warp with a non-zero 4 x 8 sub-tile at or before that step (~0: everything is multiplied), or NULL
+  const unsigned long long* tmask;     // [ncb][nchunks][2] per (column block, k-chunk, warp of the pair): up to 8 runs of k4 steps, 8 bits each (5 bits
+                                       // length, 3 bits = number of leading n-tiles of that warp with non-zero 4 x 8 sub-tiles); ~0: everything is multiplied; or NULL
   const double* tdata;                 // output mode: [ncols] data d of the 'cubic'-transformed columns (0: untransformed column), or NULL
 };
 
@@ -112,6 +112,7 @@ struct ContractParams {
   int act;                               // output mode: activation applied to (slot 0 + r0): 0 none, 1 silu, 2 relu, 3 tanh
   int mode;                              // 0 eval (Gram partials), 1 output (theory vectors / MLP layer)
   int nstages, resident, ast, dpad, npart_max;
+  int masked;                            // some block of the launch has sub-tile masks (BlockDev::tmask): use the kernel instances with the masked path
   long long U;                           // number of row units (variant_unit rows each) to process
   long long* prof;                       // DLB_PROFILE builds: 8 cycle counters (summed over warps)
 };

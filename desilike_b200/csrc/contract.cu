@@ -32,11 +32,19 @@
 //     coefficients are evaluated per tile into shared memory and applied to the A fragment in registers.
 //   * the Gram epilogue is warp-shuffle reductions accumulated in a per-warp-column shared-memory copy (no atomics), summed
 //     over column blocks in the kernel and written once per (tile, block).
+// This file is compiled twice: as is (kernel instances without the masked sub-tile path) and through contract_masked.cu
+// (DLB_CONTRACT_MASKED = 1: instances with it) -- two translation units, so the two sets of variants compile in parallel.
 #include "common.h"
+
+#ifndef DLB_CONTRACT_MASKED
+#define DLB_CONTRACT_MASKED 0
+#endif
 
 namespace dlb {
 
 namespace {
+
+constexpr bool kMasked = DLB_CONTRACT_MASKED != 0;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -45,6 +53,18 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {   // bar: shared-window address computed once per kernel
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -121,36 +141,40 @@ __device__ __forceinline__ void mma_run(double (&acc)[MT][NT][2], const double* 
   }
 }
 
-// Masked k-chunk: `mask` holds, 3 bits per k4 step, the number of leading n-tiles of this warp whose B sub-tile (4 rows x 8 columns) is
-// not structurally zero from that step on (plan-time table, csrc/plan.cu: build_block_core).  Zero sub-tiles of lower-triangular
-// (rank-reduced) term matrices and of the padding of the last column block are neither loaded nor multiplied.  The chunk is walked in
-// runs of constant count (the count never decreases inside a chunk).
+// Masked k-chunk: `mask` lists up to 8 runs of k4 steps, 8 bits each from the low end: bits 0-4 = run length (0 terminates), bits 5-7 = number of
+// leading n-tiles of this warp whose B sub-tiles (4 rows x 8 columns) are not structurally zero during the run (plan-time table,
+// csrc/plan.cu: build_block_core).  Zero sub-tiles of lower-triangular (rank-reduced) term matrices and of the padding of the last column
+// block are neither loaded nor multiplied.  (Measured and rejected: one code path with the loads / DMMAs predicated on nt < nact instead of
+// one instantiation per count -- C5 0.90 vs 0.75 ms: predicated-off DMMAs are not free.)
 template <int MT, int NT, int KC>
 __device__ __forceinline__ void mma_chunk_masked(double (&acc)[MT][NT][2], const double* A, int astride, const double* B, const double (&beta)[MT],
-                                                 int nk4, int mtc, unsigned long long mask) {
+                                                 int mtc, unsigned long long mask) {
   int k4 = 0;
-  while (k4 < nk4) {
-    const int nact = (int)((mask >> (3 * k4)) & 7ull);
-    int k4e = k4 + 1;
-    while (k4e < nk4 && (int)((mask >> (3 * k4e)) & 7ull) == nact) ++k4e;
-    switch (nact < NT ? nact : NT) {
+  for (;;) {
+    const int len = (int)(mask & 31ull);
+    if (len == 0) break;
+    const int nact = (int)((mask >> 5) & 7ull), k4e = k4 + len;
+    mask >>= 8;
+    if (nact >= NT) mma_run<MT, NT, NT, KC>(acc, A, astride, B, beta, k4, k4e, mtc);
+    else switch (nact) {
       case 0: break;
       case 1: mma_run<MT, NT, 1, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
-      case 2: if constexpr (NT >= 2) mma_run<MT, NT, 2, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
-      case 3: if constexpr (NT >= 3) mma_run<MT, NT, 3, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
-      case 4: if constexpr (NT >= 4) mma_run<MT, NT, 4, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
-      case 5: if constexpr (NT >= 5) mma_run<MT, NT, 5, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
-      case 6: if constexpr (NT >= 6) mma_run<MT, NT, 6, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
-      default: if constexpr (NT >= 7) mma_run<MT, NT, 7, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+      case 2: if constexpr (NT > 2) mma_run<MT, NT, 2, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+      case 3: if constexpr (NT > 3) mma_run<MT, NT, 3, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+      case 4: if constexpr (NT > 4) mma_run<MT, NT, 4, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+      case 5: if constexpr (NT > 5) mma_run<MT, NT, 5, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+      default: if constexpr (NT > 6) mma_run<MT, NT, 6, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
     }
     k4 = k4e;
   }
 }
 
-template <int MT, int NT, int KC>
+template <int MT, int NT, int KC, bool MASKED>
 __device__ __forceinline__ void mma_chunk_dispatch(double (&acc)[MT][NT][2], const double* A, int astride, const double* B, const double (&beta)[MT],
                                                    int nk4, int mtc, unsigned long long mask) {
-  if (mask != ~0ull) { mma_chunk_masked<MT, NT, KC>(acc, A, astride, B, beta, nk4, mtc, mask); return; }
+  if constexpr (MASKED) {
+    if (mask != ~0ull) { mma_chunk_masked<MT, NT, KC>(acc, A, astride, B, beta, mtc, mask); return; }
+  }
   if (mtc == MT) { mma_chunk<MT, NT, MT, KC>(acc, A, astride, B, beta, nk4); return; }
   if constexpr (MT > 1) { if (mtc == 1) { mma_chunk<MT, NT, 1, KC>(acc, A, astride, B, beta, nk4); return; } }
   if constexpr (MT > 2) { if (mtc == 2) { mma_chunk<MT, NT, 2, KC>(acc, A, astride, B, beta, nk4); return; } }
@@ -185,7 +209,9 @@ __device__ __forceinline__ unsigned atom_add_acq_rel(unsigned* addr, unsigned v)
 #define PROF_FLUSH
 #endif
 
-template <int R, int MT, int NT, int WM, int CPS, int KC, bool RESIDENT>
+// MASKED: the launch has sub-tile masks (BlockDev::tmask); plans without any use the instance that carries no masked code at all (the masked
+// path costs registers: C2 is 3 % slower with it compiled in, even when it never runs).
+template <int R, int MT, int NT, int WM, int CPS, int KC, bool RESIDENT, bool MASKED>
 __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_constant__ ContractParams p) {
   constexpr int NW = 2 * WM, NTH = NW * 32, UNIT = WM * 8, BM = UNIT * MT, BN = 16 * NT;
   constexpr int STAGE_DOUBLES = BN * KC + (RESIDENT ? 0 : BM * KC);
@@ -296,6 +322,7 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
     for (int i = 0; i < S; ++i) refill(i);
 
   const int npm = p.npart_max;
+  const uint32_t full_u32 = smem_u32(full);
   int s = 0, xbuf = 0;
   uint32_t ph = 0, aph = 0;
   PROF_DECL
@@ -428,8 +455,7 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
       for (int cb = 0; cb < ncb; ++cb) {
         const int cfirst = cb_first ? __ldg(cb_first + cb) : 0;
         int4 ch_next = __ldg(reinterpret_cast<const int4*>(chunks + (cfirst < nchunks ? cfirst : 0)));   // slot, coef, fcol, kc (prefetched one chunk ahead)
-        const unsigned long long* tmask = blk->tmask ? blk->tmask + ((size_t)cb * nchunks) * 2 + wn : nullptr;   // [ncb][nchunks][2]
-        unsigned long long mask_next = tmask ? __ldg(tmask + 2 * (cfirst < nchunks ? cfirst : 0)) : ~0ull;
+        [[maybe_unused]] const unsigned long long* tmask = (MASKED && blk->tmask) ? blk->tmask + ((size_t)cb * nchunks) * 2 + wn : nullptr;   // [ncb][nchunks][2]
         double acc[R][MT][NT][2];
 #pragma unroll
         for (int sl = 0; sl < R; ++sl)
@@ -440,14 +466,14 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
 
         for (int c = cfirst; c < nchunks; ++c) {
           const int4 ch = ch_next;
-          const unsigned long long mask = mask_next;
+          unsigned long long mask = ~0ull;
+          if constexpr (MASKED) { if (tmask) mask = __ldg(tmask + 2 * c); }   // (L1-resident table; the load overlaps the stage wait below)   // (L1-resident table; the load overlaps the stage wait below)
           ch_next = __ldg(reinterpret_cast<const int4*>(chunks + (c + 1 < nchunks ? c + 1 : c)));
-          if (tmask) mask_next = __ldg(tmask + 2 * (c + 1 < nchunks ? c + 1 : c));
           double beta[MT];
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) beta[mt] = ch.y >= 0 ? cs[ch.y * BM + mt * UNIT + wm * 8 + lr] : 1.;
           PROF(3)
-          mbar_wait(&full[s], ph);
+          mbar_wait_u32(full_u32 + 8u * s, ph);
           PROF((c == cfirst ? (cb == 0 ? 1 : 7) : 4))
           const double* Bp = stage_base + (size_t)s * STAGE_DOUBLES + (wn * 8 + lr) * KC + lc;
           const double* Ap;
@@ -457,7 +483,7 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
           const int nk4 = ch.w >> 2;
 #pragma unroll
           for (int sl = 0; sl < R; ++sl)
-            if (ch.x == sl) mma_chunk_dispatch<MT, NT, KC>(acc[sl], Ap, astride, Bp, beta, nk4, mtc, mask);
+            if (ch.x == sl) mma_chunk_dispatch<MT, NT, KC, MASKED>(acc[sl], Ap, astride, Bp, beta, nk4, mtc, mask);
           PROF(3)
           release(s);
           PROF(5)
@@ -465,7 +491,7 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
         }
 
         // ===== epilogue: r0 of this column block arrives as one more transaction of the ring =====
-        mbar_wait(&full[s], ph);
+        mbar_wait_u32(full_u32 + 8u * s, ph);
         PROF(0)
         const int colw = wn * 8 + 2 * lc;  // + nt * 16 + e   (interleaved n-tiles: warp wn owns the 8-column tiles 2 nt + wn)
         const double* epi = stage_base + (size_t)s * STAGE_DOUBLES;
@@ -575,10 +601,10 @@ int launch_variant(const ContractParams& p, int grid, size_t smem, cudaStream_t 
   static bool configured_dev[64] = {};
   bool& configured = configured_dev[current_device_slot()];
   if (!configured) {
-    DLB_CUDA(cudaFuncSetAttribute(contract_kernel<R, MT, NT, WM, CPS, KC, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)contract_smem_limit(CPS)));
+    DLB_CUDA(cudaFuncSetAttribute(contract_kernel<R, MT, NT, WM, CPS, KC, RESIDENT, kMasked>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)contract_smem_limit(CPS)));
     configured = true;
   }
-  contract_kernel<R, MT, NT, WM, CPS, KC, RESIDENT><<<grid, WM * 64, smem, stream>>>(p);
+  contract_kernel<R, MT, NT, WM, CPS, KC, RESIDENT, kMasked><<<grid, WM * 64, smem, stream>>>(p);
   g_launches++;
   DLB_CUDA(cudaGetLastError());
   return DLB_OK;
@@ -591,6 +617,7 @@ int launch_mode(const ContractParams& p, int grid, size_t smem, cudaStream_t str
 
 }  // namespace
 
+#if !DLB_CONTRACT_MASKED
 size_t contract_smem_limit(int ctas_per_sm) {   // dynamic shared memory available to one CTA
   return ctas_per_sm == 2 ? (size_t)(233472 / 2 - 1024 - 512) : (size_t)227 * 1024;
 }
@@ -604,7 +631,15 @@ size_t contract_smem_bytes(const Variant& v, int nstages, bool resident, int ast
   return bytes;
 }
 
+int launch_contract_masked(const Variant& v, const ContractParams& p, int nsm, cudaStream_t stream);   // contract_masked.cu
+#endif
+
+#if DLB_CONTRACT_MASKED
+int launch_contract_masked(const Variant& v, const ContractParams& p, int nsm, cudaStream_t stream) {
+#else
 int launch_contract(const Variant& v, const ContractParams& p, int nsm, cudaStream_t stream) {
+  if (p.masked) return launch_contract_masked(v, p, nsm, stream);
+#endif
   const size_t smem = contract_smem_bytes(v, p.nstages, p.resident != 0, p.ast, p.dpad, p.ncoef, p.npart_max, p.ngen);
   if (smem > contract_smem_limit(v.CPS)) { set_error("contraction kernel: shared-memory budget exceeded"); return DLB_ERR_UNSUPPORTED; }
   const int grid = (int)std::min<long long>((long long)nsm * v.CPS, std::max<long long>(p.U, 1));

@@ -59,6 +59,50 @@ __global__ void dmma_warps_kernel(double* out, double seed) {
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// DMMA rate with ILP independent accumulators per warp (dependent chains of length PEAK_ITERS): the latency of the accumulate dependency.
+// Tells how few active n-tiles a warp of the contraction kernel can have (masked sub-tiles of triangular blocks) before it becomes
+// latency bound: rate(ILP, warps) = min(pipe, ILP * warps_per_scheduler / latency).
+template <int ILP>
+__global__ void dmma_chain_kernel(double* out, double seed) {
+  double c[ILP][2];
+  const double a = seed + threadIdx.x * 1e-9, b = 1. - 1e-9 * threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) c[i][0] = c[i][1] = i;
+  for (int it = 0; it < PEAK_ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+  }
+  double s = 0.;
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) s += c[i][0] + c[i][1];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int ILP>
+int run_dmma_chain(int nsm, int warps, double* tflops) {
+  double* out = nullptr;
+  DLB_CUDA(cudaMalloc((void**)&out, (size_t)nsm * warps * 32 * sizeof(double)));
+  cudaEvent_t e0, e1;
+  DLB_CUDA(cudaEventCreate(&e0));
+  DLB_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    DLB_CUDA(cudaEventRecord(e0));
+    dmma_chain_kernel<ILP><<<nsm, warps * 32>>>(out, 1.0);
+    g_launches++;
+    DLB_CUDA(cudaEventRecord(e1));
+    DLB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    DLB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep >= 2 && ms < best) best = ms;
+  }
+  DLB_CUDA(cudaGetLastError());
+  *tflops = (double)PEAK_ITERS * ILP * 512. * nsm * warps / (best * 1e-3) / 1e12;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  return DLB_OK;
+}
+
 // DMMA fed from shared memory exactly like the contraction kernel's main loop (warp tile MT x NT m8n8 tiles, 64-bit
 // fragment loads from rows of 36 / 76 doubles, optional per-row scaling of the A fragment): the attainable in-loop rate.
 //   variant bit 0: scale A fragment (DMUL)   bit 1: skip the shared-memory loads (register operands)   bits 4..: NT (default 7), MT = 2
@@ -149,6 +193,19 @@ int measure_fp64_peak(int kind, double* tflops) {
   int dev = 0, nsm = 0;
   DLB_CUDA(cudaGetDevice(&dev));
   DLB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  if (kind >= 2000) {  // kind = 2000 + 100 * ILP + warps per SM: dependent-chain DMMA rate
+    const int ilp = (kind - 2000) / 100, warps = kind % 100;
+    if (warps < 1 || warps > 32) { set_error("measure_fp64_peak: 1..32 warps per SM"); return DLB_ERR_ARG; }
+    switch (ilp) {
+      case 1: return run_dmma_chain<1>(nsm, warps, tflops);
+      case 2: return run_dmma_chain<2>(nsm, warps, tflops);
+      case 4: return run_dmma_chain<4>(nsm, warps, tflops);
+      case 6: return run_dmma_chain<6>(nsm, warps, tflops);
+      case 10: return run_dmma_chain<10>(nsm, warps, tflops);
+      case 14: return run_dmma_chain<14>(nsm, warps, tflops);
+      default: set_error("measure_fp64_peak: ILP in {1, 2, 4, 6, 10, 14}"); return DLB_ERR_ARG;
+    }
+  }
   if (kind >= 1000) {  // kind = 1000 + 100 * tile + 10 * variant-bits + (warps / 4): DMMA fed from shared memory
     const int tile = (kind - 1000) / 100, variant = ((kind - 1000) / 10) % 10, warps = 4 * (kind % 10);
     if (warps < 4 || warps > 32) { set_error("measure_fp64_peak: 4..32 warps"); return DLB_ERR_ARG; }

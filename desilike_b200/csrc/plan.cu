@@ -41,6 +41,7 @@ struct Launch {
   BlockDev* d_plain_t = nullptr;   // two-stage plans: the un-whitened table writing into the transformed-theory buffer (ocol0 = Block::tcol)
   SchedEntry *d_sched_white = nullptr, *d_sched_plain = nullptr;   // per-tile TMA schedule
   int nsched = 0, nsched_plain = 0;
+  bool masked_white = false, masked_plain = false;   // some block has sub-tile masks
   double flops_exec = 0., flops_exec_plain = 0.;   // 2 * kc * BN * slots-independent tile count per point (whitened / un-whitened tables)
 };
 
@@ -253,14 +254,21 @@ static int build_block_core(dlb_plan* plan, const Variant& var, bool resident, i
             for (int nt = NT - 1; nt >= 0; --nt) { run = std::min(run, kf[2 * nt + wn]); start[nt] = run; }
             unsigned long long w = 0ull;
             bool full = true;
+            int nruns = 0, run_len = 0, run_nact = -1;
+            auto flush = [&]() {
+              if (run_len > 0) { w |= ((unsigned long long)run_len | ((unsigned long long)run_nact << 5)) << (8 * nruns); ++nruns; }
+            };
             for (int k4 = 0; k4 < nk4; ++k4) {
               int nact = 0;
               for (int nt = 0; nt < NT; ++nt) nact += start[nt] <= k4 ? 1 : 0;
               full = full && nact == NT;
-              w |= (unsigned long long)nact << (3 * k4);
+              if (nact != run_nact) { flush(); run_len = 0; run_nact = nact; }
+              ++run_len;
               exec[(size_t)cb * blk.nchunks + c] += 4. * 8. * nact;
             }
-            if (nk4 > 21) { full = true; }   // cannot happen (KC <= 76); keep the dense path if it ever does
+            flush();
+            if (nruns > 8) full = true;   // cannot happen: the count is non-decreasing in k4 and takes at most NT + 1 <= 8 values
+            if (nk4 > 31) full = true;   // cannot happen (KC <= 76 -> nk4 <= 19 fits the 5-bit run length)
             if (!full && !getenv("DLB_NO_SUBTILE_SKIP")) { masks[((size_t)cb * blk.nchunks + c) * 2 + wn] = w; any_mask = true; }
             else exec[(size_t)cb * blk.nchunks + c] += 0.;
           }
@@ -361,6 +369,7 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
       bd.ocol0 = b->coloff; bd.gen = b->gen; bd.fill = b->fill; bd.fbase = b->fbase; bd.acols = std::min((b->maxcol + 1) & ~1, L.ast);
       bd.tdata = pass == 1 ? b->d_tdata : nullptr;
       bd.tmask = pass == 0 ? b->d_tmask_white : b->d_tmask_plain;
+      if (bd.tmask) (pass == 0 ? L.masked_white : L.masked_plain) = true;
       bd.cb_first = pass == 0 ? b->d_cb_first : nullptr;
       tab.push_back(bd);
     }
@@ -484,7 +493,7 @@ static int run_front(dlb_plan* plan, const double* d_params, long long N, long l
     const Launch& L = la.first;
     ContractParams cp;
     fill_params(plan, L, cp, d_params, N, npad);
-    cp.blocks = L.d_plain; cp.sched = L.d_sched_plain; cp.nsched = L.nsched_plain; cp.ncoef = 0;
+    cp.blocks = L.d_plain; cp.sched = L.d_sched_plain; cp.nsched = L.nsched_plain; cp.ncoef = 0; cp.masked = L.masked_plain;
     cp.out = plan->w_F; cp.ostride = plan->fstride; cp.out_rows = npad; cp.act = la.second; cp.mode = 1;
     cp.U = npad / variant_unit(L.var);
     DLB_TRY(launch_contract(L.var, cp, plan->nsm, stream));
@@ -499,7 +508,7 @@ static int run_two_stage(dlb_plan* plan, const double* d_params, long long N, lo
     const Launch& L = plan->launch;
     ContractParams cp;
     fill_params(plan, L, cp, d_params, N, npad);
-    cp.blocks = L.d_plain_t; cp.sched = L.d_sched_plain; cp.nsched = L.nsched_plain;
+    cp.blocks = L.d_plain_t; cp.sched = L.d_sched_plain; cp.nsched = L.nsched_plain; cp.masked = L.masked_plain;
     cp.out = plan->w_T; cp.ostride = plan->tstride; cp.out_rows = npad; cp.act = 0; cp.mode = 1;
     cp.U = (N + variant_unit(L.var) - 1) / variant_unit(L.var);
     DLB_TRY(launch_contract(L.var, cp, plan->nsm, stream));
@@ -507,7 +516,7 @@ static int run_two_stage(dlb_plan* plan, const double* d_params, long long N, lo
   const Launch& L = plan->wlaunch;
   ContractParams cp;
   fill_params(plan, L, cp, d_params, N, npad);
-  cp.blocks = L.d_white; cp.sched = L.d_sched_white; cp.nsched = L.nsched; cp.ncoef = 0;
+  cp.blocks = L.d_white; cp.sched = L.d_sched_white; cp.nsched = L.nsched; cp.ncoef = 0; cp.masked = L.masked_white;
   cp.F = plan->w_T; cp.fstride = plan->tstride; cp.mode = 0;
   cp.U = (N + variant_unit(L.var) - 1) / variant_unit(L.var);
   return launch_contract(L.var, cp, plan->nsm, stream);
@@ -520,6 +529,7 @@ static int run_contract(dlb_plan* plan, const double* d_params, long long N, lon
   fill_params(plan, L, cp, d_params, N, npad);
   cp.blocks = mode == 0 ? L.d_white : L.d_plain;
   cp.sched = mode == 0 ? L.d_sched_white : L.d_sched_plain; cp.nsched = mode == 0 ? L.nsched : L.nsched_plain;
+  cp.masked = mode == 0 ? L.masked_white : L.masked_plain;
   if (!cp.blocks) { set_error("plan was built without un-whitened matrices: theory_batch unavailable"); return DLB_ERR_ARG; }
   cp.out = d_theory; cp.ostride = plan->ntheory; cp.out_rows = N; cp.act = 0; cp.mode = mode;
   cp.U = (N + variant_unit(L.var) - 1) / variant_unit(L.var);

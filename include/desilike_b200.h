@@ -215,7 +215,8 @@ int64_t dlb_launch_count(void);                  /* kernels launched by this lib
 /* Achieved FP64 rate (TFLOP/s) of a register-resident DMMA.8x8x4 loop (kind 0) or DFMA loop (kind 1) on the current
  * device: the denominator of the FP64 roofline (MEASURED_PEAKS.json has no FP64 entry).  kind = 100 + w: DMMA loop with w
  * resident warps per SM; kind = 1000 + 100 * tile + 10 * flags + w / 4: DMMA loop fed from shared memory like the
- * contraction kernel's main loop (tile 0: 2x7, 1: 4x7, 2: 2x4, 3: 1x7 m8n8 tiles per warp; w warps per SM). */
+ * contraction kernel's main loop (tile 0: 2x7, 1: 4x7, 2: 2x4, 3: 1x7 m8n8 tiles per warp; w warps per SM); kind = 2000 + 100 * ilp + w:
+ * register-resident DMMA loop with `ilp` independent accumulators per warp (dependent chains; ilp in {1, 2, 4, 6, 10, 14}), w warps per SM. */
 int dlb_measure_fp64_peak(int32_t kind, double* tflops);
 /* Time (ms, CUDA events on `stream`) of the last dlb_eval_batch's contraction kernel launches; for bench.py's roofline. */
 int dlb_last_kernel_ms(const dlb_plan* plan, double* features_ms, double* contract_ms, double* solve_ms);
