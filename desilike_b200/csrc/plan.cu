@@ -646,6 +646,12 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
       g.aux[1] = gd.idata[3];                              // nt (template knots), needed on the host for shared-memory sizing
       g.aux[2] = gd.idata[0]; g.aux[3] = gd.idata[1]; g.aux[4] = gd.idata[5];
       if (gd.kind == DLB_GEN_BAO) { DLB_REQUIRE(gd.ni >= 16, "bao generator: idata header"); g.aux[5] = gd.idata[14]; }
+      if (gd.kind == DLB_GEN_KAISER) {
+        DLB_REQUIRE(gd.ni >= 16 && gd.idata[10] >= 1 && gd.idata[10] <= 8 && gd.idata[2] >= 1 && gd.idata[2] <= 16 && gd.idata[15] >= 4 && gd.idata[15] <= gd.idata[3],
+                    "kaiser generator: idata header (1 <= nseg <= 8, 1 <= nmu <= 16, 4 <= nw_max <= nt)");
+        g.aux[5] = gd.idata[2] | (gd.idata[10] << 8) | (gd.idata[13] << 16);   // nmu, nseg, interp
+        g.aux[7] = gd.idata[15];                                               // largest knot window
+      }
     }
     foff += g.fpad;
     plan->gens.push_back(g);
@@ -1002,6 +1008,13 @@ static long long chunk_points(const dlb_plan* plan) {
   const long long per_point = 8LL * ((long long)plan->fstride + std::max(plan->ptotal, 1LL) + plan->d + 4 + plan->ns + plan->tstride);
   long long n = (16LL << 30) / std::max(per_point, 1LL) / ROW_ALIGN * ROW_ALIGN;
   n = std::max<long long>(ROW_ALIGN * 32, std::min(MAX_CHUNK, n));
+  // Feature matrices written by their own kernels (direct Kaiser / BAO theories) are consumed by the contraction right after: a pass whose
+  // feature matrix fits in L2 (~64 MB of the 126 MB) never sends it to HBM (ncu, C1: 7.5 MB of DRAM writes per 65 536 points instead of 170 MB).
+  // Only when such a pass still holds >= 65 536 points -- smaller passes cost more in kernel efficiency than the traffic saves.
+  if (!plan->resident && plan->fstride > 4 && !getenv("DLB_NO_L2_CHUNK")) {
+    const long long fit = (64LL << 20) / (8LL * plan->fstride) / ROW_ALIGN * ROW_ALIGN;
+    if (fit >= 65536) n = std::min(n, fit);
+  }
   if (const char* e = getenv("DLB_MAX_CHUNK")) n = std::max<long long>(ROW_ALIGN, std::min(n, atoll(e) / ROW_ALIGN * ROW_ALIGN));   // tests: force several passes
   return n;
 }

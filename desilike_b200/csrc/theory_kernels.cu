@@ -186,19 +186,48 @@ __device__ __forceinline__ SplineConst load_spline(const double* d, int nt, bool
 constexpr int SPLINE_DOUBLES(int nt) { return 5 * nt + 4; }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Kaiser.  ddata = [eta, a_inv_unused, f_fid, 0 | k[nk] | mu[nmu] | wmu[nell, nmu] | pk_fid[nt] | Tt[nt] | Lt[nt] | spline consts]
+// Kaiser.  ddata = [eta, a_inv_unused, f_fid, 0 | k[nk] | mu[nmu] | wmu[nell, nmu] | pk_fid[nt] | Tt[nt] | Lt[nt] | spline consts | log10 k[nk] | h[nt]
+//                   | ratios]
 //   Tt = tanh(a ln(k_t / kp)) / a,  Lt = ln(k_t / kp)   =>  pk_dd = pk_fid * exp(dm * Tt + dn * Lt)
-// features = (1, 0 | pk_dd [nell, nk] | pk_dt | pk_tt | pk11_l0 = pk_dd[ell = 0] tiled over ell), tables padded to ntab.
+// idata = [nk, nell, nmu, nt, apmode, flags | ell0 << 8, ntab, total, off_derived, -, nseg, off_seg, off_ratio, interp, pad, nw_max | segment records]
+//
+// Output = `nseg` SEGMENTS of ntab doubles after the (1, 0) pair.  Segment s is a per-point linear combination of the three Kaiser tables
+//     seg_s[ell, k] = sum_mu w_ell(mu) (a_dd + a_dt f mu_ap^2 + a_tt f^2 mu_ap^4) jac D(k, mu) pk(k_ap(k, mu))
+// with (a_dd, a_dt, a_tt) = sum over its records of ratio * prod_f theta[idx_f]^pow_f: the plain tables pk_dd / pk_dt / pk_tt are (1,0,0) / (0,1,0) /
+// (0,0,1); pk11_l0 (the ell = 0 row of pk_dd tiled over ell) is (1,0,0) with flag bit 0; and the tracer combine b1^2 dd + 2 b1 dt + tt (reference
+// full_shape.py:545-550) is ONE segment with weight (b1 + f mu_ap^2)^2 when the lowering merges the three terms (their window matrices coincide):
+// a third of the quadrature sums, a quarter of the feature columns written and contracted.
+// segment record (ints): flag, ncomb, then ncomb x { table (0 dd, 1 dt, 2 tt), nf, idx[4], pow[4] }; ratios (doubles) in record order.
+//
+// One warp per point.  (1) ShapeFit template ordinates y_i = pk_fid_i exp(dm Tt_i + dn Lt_i) only on the WINDOW of knots the AP-distorted nodes
+// of this point can reach (+ `pad` knots each side); (2) interp 0: second derivatives of the not-a-knot spline (SciPy branch of reference
+// jax.py:263-265) by the two sweeps restricted to the window -- a sweep restarted `pad` knots away from the first node differs from the full one by
+// |w|^pad ~ 0.27^28 ~ 1e-16 relative; interp 1: no sweeps at all (interpax C1 local cubic, reference jax.py:258-261: knot slopes = mean of the two
+// adjacent secant slopes); (3) the nk x nmu nodes are spread evenly over the lanes in blocks of KAISER_KB k nodes (node values to shared memory), then
+// (4) the lanes form the mu sums of every (segment, ell, k) output of the block and store them coalesced.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int KAISER_WARPS = 4;
+constexpr int KAISER_KB = 32;
 constexpr int MAX_ELL = 3;
+constexpr int KAISER_MAXSEG = 8;
 
-__global__ void __launch_bounds__(KAISER_WARPS * 32) kaiser_kernel(const DevGen g, const double* __restrict__ params, int d, long long N,
-                                                                   long long npad, double* __restrict__ F, int fstride) {
+__host__ __device__ inline int kaiser_warp_doubles(int nw, int nmu, int nell, int nseg, int interp) {
+  // y | M (padded) | node values | segment weights | per-mu AP quantities | segment coefficients
+  return (nw + 4) + (interp == 0 ? nw + nw / 2 + 8 : 0) + KAISER_KB * (nmu | 1) + nseg * nell * nmu + 3 * nmu + 3 * nseg + 2;
+}
+
+// NMU: number of mu nodes when known at compile time (8: the reference default, full_shape.py:484), 0: generic.  INTERP: 0 not-a-knot, 1 local cubic.
+template <int NMU, int INTERP>
+__global__ void __launch_bounds__(KAISER_WARPS * 32, 6) kaiser_kernel(const DevGen g, const double* __restrict__ params, int d, long long N,
+                                                                   long long npad, double* __restrict__ F, int fstride, int warp_doubles) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nk = g.idata[0], nell = g.idata[1], nmu = g.idata[2], nt = g.idata[3], apmode = g.idata[4], ntab = g.idata[6];
-  const int ell0 = g.idata[5] >> 8;   // index of ell = 0 among the multipoles (or -1)
+  const int* __restrict__ id = g.idata;
+  const int nk = id[0], nell = id[1], nmu = NMU ? NMU : id[2], nt = id[3], apmode = id[4], ntab = id[6];
+  const int ell0 = id[5] >> 8;   // index of ell = 0 among the multipoles (or -1)
+  const bool uniform = (id[5] & 1) != 0;
+  const int nseg = id[10], pad = id[14], nw_max = id[15];
+  const int* __restrict__ segi = id + id[11];
   const long long pt = (long long)blockIdx.x * KAISER_WARPS + warp;
   if (pt >= npad) return;
   double* row = F + pt * fstride + g.foff;
@@ -206,11 +235,14 @@ __global__ void __launch_bounds__(KAISER_WARPS * 32) kaiser_kernel(const DevGen 
     for (int j = lane; j < g.fpad; j += 32) row[j] = 0.;
     return;
   }
-  const int L = g.idata[9], lgL = 31 - __clz(L);
-  const int mstride = nt + nt / L + 2;
-  double* y = sm + (size_t)warp * (nt + mstride);
-  double* M = y + nt;
-  const double* dd = g.ddata;
+  const int pst = nmu | 1;
+  double* y = sm + (size_t)warp * warp_doubles;
+  double* M = y + nw_max + 4;
+  double* P = M + (INTERP == 0 ? nw_max + nw_max / 2 + 8 : 0);
+  double* wseg = P + KAISER_KB * pst;
+  double* smu = wseg + nseg * nell * nmu;      // [nmu][3]: log10(F / qper), mu_ap^2, damping coefficient
+  double* coef = smu + 3 * nmu;                // [nseg][3]
+  const double* __restrict__ dd = g.ddata;
   const double eta = dd[0], f_fid = dd[2];
   const double* kk = dd + 4;
   const double* mu = kk + nk;
@@ -218,68 +250,223 @@ __global__ void __launch_bounds__(KAISER_WARPS * 32) kaiser_kernel(const DevGen 
   const double* pk_fid = wmu + nell * nmu;
   const double* Tt = pk_fid + nt;
   const double* Lt = Tt + nt;
-  const SplineConst sc = load_spline(Lt + nt, nt, (g.idata[5] & 1) != 0);   // idata[5] bit 0: template grid uniform in log10 k
+  const SplineConst sc = load_spline(Lt + nt, nt, uniform);
+  const double* lkk = dd + id[8];
+  const double* hh = lkk + nk;
+  const double* ratio = dd + id[12];
   double par[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) par[j] = (j < g.nparams && g.pidx[j] >= 0) ? params[pt * d + g.pidx[j]] : g.pdef[j];
   double qpar, qper;
   ap_qpar_qper(apmode, par[0], par[1], eta, qpar, qper);
   const double dm = par[2], dn = par[3], f = f_fid * par[4], sigmapar = par[5], sigmaper = par[6];
-  // fast_exp (common.h): ~1e-15 relative error in ~18 instructions instead of ~45 (the kernel is instruction-issue bound)
-  for (int i = lane; i < nt; i += 32) y[i] = pk_fid[i] * fast_exp(fmin(fmax(dm * Tt[i] + dn * Lt[i], -708.), 708.));
-  __syncwarp();
   const double qap = qpar / qper, jac = 1. / (qpar * qper * qper), iq2 = 1. / (qap * qap) - 1.;
   const bool damped = (sigmapar != 0.) || (sigmaper != 0.);
-  // per-mu AP quantities, once per point: log10(F / qper), mu_ap^2, damping coefficient (reference base.py:211-223, full_shape.py:491-495)
-  const double* lkk = dd + g.idata[8];
-  const double* hh = lkk + nk;
-  const double* wT = hh + nt;
-  const double* invbT = wT + 32 * L;
-  const double* cbT = invbT + 32 * L;
-  spline_second_derivatives_padded(sc, wT, invbT, cbT, lgL, y, M, lane);
-  __shared__ double smu[KAISER_WARPS][16][3];
+  // ---- per-mu AP quantities, once per point (reference base.py:211-223, full_shape.py:491-495) ----
+  double lkf = 0.;
   if (lane < nmu) {
     const double m_ = mu[lane];
     const double fap = sqrt(1. + m_ * m_ * iq2);
     const double kfac = fap / qper, muap = m_ / (qap * fap), m2 = muap * muap;
-    smu[warp][lane][0] = log10(kfac);
-    smu[warp][lane][1] = m2;
-    smu[warp][lane][2] = 0.5 * kfac * kfac * (sigmapar * sigmapar * m2 + sigmaper * sigmaper * (1. - m2));
+    lkf = log10(kfac);
+    smu[lane * 3 + 0] = lkf;
+    smu[lane * 3 + 1] = m2;
+    smu[lane * 3 + 2] = 0.5 * kfac * kfac * (sigmapar * sigmapar * m2 + sigmaper * sigmaper * (1. - m2));
+  }
+  // ---- segment coefficients (a_dd, a_dt, a_tt) ----
+  if (lane < nseg) {
+    const int* rec = segi;
+    const double* rt = ratio;
+    for (int s_ = 0; s_ < lane; ++s_) { rt += rec[1]; rec += 2 + 10 * rec[1]; }
+    double a0 = 0., a1 = 0., a2 = 0.;
+    const int ncomb = rec[1];
+    for (int c = 0; c < ncomb; ++c) {
+      const int* cr = rec + 2 + 10 * c;
+      double v = rt[c];
+      for (int q = 0; q < cr[1]; ++q) {
+        const double x = params[pt * d + cr[2 + q]];
+        const int e = cr[6 + q];
+        double pw = 1.;
+        for (int i = 0; i < (e >= 0 ? e : -e); ++i) pw *= x;
+        v *= e >= 0 ? pw : 1. / pw;
+      }
+      if (cr[0] == 0) a0 += v; else if (cr[0] == 1) a1 += v; else a2 += v;
+    }
+    coef[lane * 3 + 0] = a0; coef[lane * 3 + 1] = a1; coef[lane * 3 + 2] = a2;
+  }
+  // ---- window of template knots reached by the nodes: log10 k_ap in [lk_lo, lk_hi] ----
+  double lmin = lane < nmu ? lkf : 1e300, lmax = lane < nmu ? lkf : -1e300;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o)); lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o)); }
+  int i_lo = 0, i_hi = nt - 1;
+  if (uniform) {
+    const double klo = dd[id[8] - 2], khi = dd[id[8] - 1];   // min / max of log10 k over the theory nodes (stored just before the log10 k table)
+    i_lo = (int)floor((klo + lmin - sc.x0) * sc.inv_dx) - pad;
+    i_hi = (int)floor((khi + lmax - sc.x0) * sc.inv_dx) + 2 + pad;
+    i_lo = max(0, min(i_lo, nt - 4));
+    i_hi = max(i_lo + 3, min(i_hi, nt - 1));
+    if (i_hi - i_lo + 1 > nw_max) i_hi = i_lo + nw_max - 1;   // (only for points far outside the prior box the window was sized for)
+  }
+  const int nw = i_hi - i_lo + 1;
+  __syncwarp();
+  // fast_exp (common.h): ~1e-15 relative error in ~18 instructions instead of ~45.  Two knots per lane and iteration: their loads and FP64
+  // chains are independent
+  {
+    const double* pf = pk_fid + i_lo; const double* tt_ = Tt + i_lo; const double* lt_ = Lt + i_lo;
+    int j = lane;
+    for (; j + 32 < nw; j += 64) {
+      const double p0 = pf[j], p1 = pf[j + 32], a0 = dm * tt_[j] + dn * lt_[j], a1 = dm * tt_[j + 32] + dn * lt_[j + 32];
+      y[j] = p0 * fast_exp(fmin(fmax(a0, -708.), 708.));
+      y[j + 32] = p1 * fast_exp(fmin(fmax(a1, -708.), 708.));
+    }
+    if (j < nw) y[j] = pf[j] * fast_exp(fmin(fmax(dm * tt_[j] + dn * lt_[j], -708.), 708.));
+  }
+  __syncwarp();
+  int lgL = 1;
+  if constexpr (INTERP == 0) {
+    // ---- second derivatives on the window: unknowns i = a .. b (global knot indices), M_j stored at pidx(j - i_lo); the window's end knots
+    //      are either the ends of the template grid (not-a-knot conditions below) or lie `pad` knots away from every node (M := 0 there).
+    //      Uniform grids: away from the two ends of the grid the pivots of the tridiagonal solve have converged to constants (their plan-time
+    //      values sit in ddata): no table loads in the sweeps ----
+    const int a = i_lo + 1, b = i_hi - 1, m = b - a + 1;
+    while ((32 << lgL) < m) ++lgL;
+    const int L = 1 << lgL;
+    const double* cst = dd + id[12] - 6;   // w_inf, invb_inf, cb_inf, first / last knot with converged pivots (as doubles), -
+    const bool interior = uniform && a >= (int)cst[3] && b <= (int)cst[4];
+    const double w_c = cst[0], invb_c = cst[1], cb_c = cst[2];
+    if (uniform) {
+      const double c6 = 6. * sc.inv_dx;
+      for (int j = 1 + lane; j <= m; j += 32) M[pidx(j, lgL)] = c6 * ((y[j + 1] - y[j]) - (y[j] - y[j - 1]));
+    } else {
+      for (int i = a + lane; i <= b; i += 32) {
+        const int j = i - i_lo;
+        M[pidx(j, lgL)] = 6. * ((y[j + 1] - y[j]) * sc.invh[i] - (y[j] - y[j - 1]) * sc.invh[i - 1]);
+      }
+    }
+    if (lane == 0) { if (i_lo > 0) M[pidx(0, lgL)] = 0.; if (i_hi < nt - 1) M[pidx(nw - 1, lgL)] = 0.; }
+    __syncwarp();
+    const int lo = a + lane * L, hi = min(lo + L, b + 1);
+    double A = 1., B = 0.;
+    if (interior) { for (int i = lo; i < hi; ++i) { B = M[pidx(i - i_lo, lgL)] - w_c * B; A = -w_c * A; } }
+    else { for (int i = lo; i < hi; ++i) { const double wi = sc.w[i]; B = M[pidx(i - i_lo, lgL)] - wi * B; A = -wi * A; } }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double Ap = __shfl_up_sync(0xffffffffu, A, o), Bp = __shfl_up_sync(0xffffffffu, B, o);
+      if (lane >= o) { B = A * Bp + B; A = A * Ap; }
+    }
+    double carry = __shfl_up_sync(0xffffffffu, B, 1);
+    if (lane == 0) carry = 0.;
+    if (interior) { for (int i = lo; i < hi; ++i) { carry = M[pidx(i - i_lo, lgL)] - w_c * carry; M[pidx(i - i_lo, lgL)] = carry; } }
+    else { for (int i = lo; i < hi; ++i) { carry = M[pidx(i - i_lo, lgL)] - sc.w[i] * carry; M[pidx(i - i_lo, lgL)] = carry; } }
+    __syncwarp();
+    const int rhi = b - lane * L, rlo = max(rhi - L, a - 1);   // indices rhi, rhi - 1, .. rlo + 1
+    A = 1.; B = 0.;
+    if (interior) { for (int i = rhi; i > rlo; --i) { B = M[pidx(i - i_lo, lgL)] * invb_c - cb_c * B; A = -cb_c * A; } }
+    else { for (int i = rhi; i > rlo; --i) { const double c = sc.cb[i]; B = M[pidx(i - i_lo, lgL)] * sc.invb[i] - c * B; A = -c * A; } }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double Ap = __shfl_up_sync(0xffffffffu, A, o), Bp = __shfl_up_sync(0xffffffffu, B, o);
+      if (lane >= o) { B = A * Bp + B; A = A * Ap; }
+    }
+    carry = __shfl_up_sync(0xffffffffu, B, 1);
+    if (lane == 0) carry = 0.;
+    if (interior) { for (int i = rhi; i > rlo; --i) { carry = M[pidx(i - i_lo, lgL)] * invb_c - cb_c * carry; M[pidx(i - i_lo, lgL)] = carry; } }
+    else { for (int i = rhi; i > rlo; --i) { carry = M[pidx(i - i_lo, lgL)] * sc.invb[i] - sc.cb[i] * carry; M[pidx(i - i_lo, lgL)] = carry; } }
+    __syncwarp();
+    if (lane == 0) {   // not-a-knot end conditions where the window reaches an end of the template grid
+      if (i_lo == 0) M[pidx(0, lgL)] = (1. + sc.r0) * M[pidx(1, lgL)] - sc.r0 * M[pidx(2, lgL)];
+      if (i_hi == nt - 1) M[pidx(nw - 1, lgL)] = (1. + sc.r1) * M[pidx(nw - 2, lgL)] - sc.r1 * M[pidx(nw - 3, lgL)];
+    }
+  }
+  // ---- segment weights w_ell(mu) (a_dd + a_dt f mu_ap^2 + a_tt f^2 mu_ap^4) ----
+  {
+    const int* rec = segi;
+    for (int s_ = 0; s_ < nseg; ++s_) {
+      const bool l0 = (rec[0] & 1) != 0;
+      rec += 2 + 10 * rec[1];
+      const double c0 = coef[s_ * 3], c1 = coef[s_ * 3 + 1], c2 = coef[s_ * 3 + 2];
+      for (int l = 0; l < nell; ++l) {
+        const int lw = l0 ? ell0 : l;
+        if (lane < nmu) {
+          const double m2 = smu[lane * 3 + 1];
+          wseg[(s_ * nell + l) * nmu + lane] = lw < 0 ? 0. : wmu[lw * nmu + lane] * (c0 + f * m2 * (c1 + f * m2 * c2));
+        }
+      }
+    }
   }
   __syncwarp();
   if (lane == 0) { row[0] = 1.; row[1] = 0.; }
-  for (int ik = lane; ik < nk; ik += 32) {
-    double sdd[MAX_ELL] = {0., 0., 0.}, sdt[MAX_ELL] = {0., 0., 0.}, stt[MAX_ELL] = {0., 0., 0.};
-    const double k = kk[ik], lk0 = lkk[ik];
-#pragma unroll 2
-    for (int im = 0; im < nmu; ++im) {
-      const double m2 = smu[warp][im][1];
-      double p = jac * spline_eval_hp(sc, hh, y, M, lgL, lk0 + smu[warp][im][0]);
-      if (damped) p *= fast_exp(fmax(-k * k * smu[warp][im][2], -708.));
-      const double pdt = f * m2 * p, ptt = f * f * m2 * m2 * p;
-#pragma unroll
-      for (int l = 0; l < MAX_ELL; ++l)
-        if (l < nell) { const double w = wmu[l * nmu + im]; sdd[l] += p * w; sdt[l] += pdt * w; stt[l] += ptt * w; }
-    }
-    // (measured and rejected: lane pairs sharing a k node and splitting the mu nodes -- 0.49 vs 0.46 ms on C1)
-    double s11 = 0.;   // pk11 = the ell = 0 row of pk_dd (static selects: a dynamic index would push the accumulators to local memory)
-#pragma unroll
-    for (int l = 0; l < MAX_ELL; ++l)
-      if (l == ell0) s11 = sdd[l];
-#pragma unroll
-    for (int l = 0; l < MAX_ELL; ++l)
-      if (l < nell) {
-        row[2 + l * nk + ik] = sdd[l];
-        row[2 + ntab + l * nk + ik] = sdt[l];
-        row[2 + 2 * ntab + l * nk + ik] = stt[l];
-        row[2 + 3 * ntab + l * nk + ik] = s11;
+  // ---- nodes and outputs, KAISER_KB k nodes at a time.  Node e = ikl * nmu + im of the block is handled by lane e mod 32: (ikl, im) advance by
+  //      (32 div nmu, 32 mod nmu) per iteration -- no integer divisions in the loops ----
+  const int q32 = 32 / nmu, r32 = 32 - q32 * nmu;
+  const int ikl0 = lane / nmu, im0 = lane - ikl0 * nmu;
+  for (int k0 = 0; k0 < nk; k0 += KAISER_KB) {
+    const int kc = min(KAISER_KB, nk - k0), nnode = kc * nmu;
+    int ikl = ikl0, im = im0;
+    for (int e = lane; e < nnode; e += 32) {
+      const int ik = k0 + ikl;
+      const double xq = lkk[ik] + smu[im * 3];
+      double p;
+      int i = (int)((xq - sc.x0) * sc.inv_dx);
+      i = max(0, min(i, nt - 2));
+      if (!uniform) {
+        while (i > 0 && xq < sc.x[i]) --i;
+        while (i < nt - 2 && xq >= sc.x[i + 1]) ++i;
       }
+      const double xi = uniform ? fma((double)i, sc.dx, sc.x0) : sc.x[i];
+      const double h = uniform ? sc.dx : hh[i], ih = uniform ? sc.inv_dx : sc.invh[i];
+      const int j = max(0, min(i - i_lo, nw - 2));
+      const double y0 = y[j], y1 = y[j + 1];
+      if constexpr (INTERP == 0) {
+        // cubic of the interval [x_i, x_i+1] from (y, M); a rounding-induced off-by-one interval evaluates the neighbouring cubic an ulp outside
+        // its interval: the spline is C2, no search needed on uniform grids
+        const double t = xq - xi;
+        const double Mi = M[pidx(j, lgL)], Mj = M[pidx(j + 1, lgL)];
+        const double bq = (y1 - y0) * ih - h * (2. * Mi + Mj) * (1. / 6.);
+        p = y0 + t * (bq + t * (0.5 * Mi + t * (Mj - Mi) * ih * (1. / 6.)));
+      } else {
+        // C1 local cubic (interpax 'cubic'): Hermite interpolation with knot slopes = mean of the adjacent secant slopes (one-sided at the
+        // ends); queries outside the template range are NaN (interpax extrap=False)
+        const double s0 = (y1 - y0) * ih;
+        const double sm1 = (i > 0 && j > 0) ? (y0 - y[j - 1]) * (uniform ? sc.inv_dx : sc.invh[i - 1]) : s0;
+        const double sp1 = (i < nt - 2 && j + 2 < nw) ? (y[j + 2] - y1) * (uniform ? sc.inv_dx : sc.invh[i + 1]) : s0;
+        const double d0 = i > 0 ? 0.5 * (sm1 + s0) : s0, d1 = i < nt - 2 ? 0.5 * (s0 + sp1) : s0;
+        const double t = (xq - xi) * ih;
+        const double c2 = 3. * (y1 - y0) - h * (2. * d0 + d1), c3 = -2. * (y1 - y0) + h * (d0 + d1);
+        p = y0 + t * (h * d0 + t * (c2 + t * c3));
+        if (xq < sc.x0 || xq > sc.x[nt - 1]) p = CUDART_NAN;
+      }
+      p *= jac;
+      if (damped) { const double k = kk[ik]; p *= fast_exp(fmax(-k * k * smu[im * 3 + 2], -708.)); }
+      P[ikl * pst + im] = p;
+      ikl += q32; im += r32;
+      if (im >= nmu) { im -= nmu; ++ikl; }
+    }
+    __syncwarp();
+    if (lane < kc) {
+      const double* pv = P + lane * pst;
+      double pr[NMU ? NMU : 16];
+#pragma unroll
+      for (int q = 0; q < (NMU ? NMU : 16); ++q) pr[q] = q < nmu ? pv[q] : 0.;
+      const double* wv = wseg;
+      for (int s_ = 0; s_ < nseg; ++s_) {
+        double* dst = row + 2 + s_ * ntab + k0 + lane;
+        for (int l = 0; l < nell; ++l, wv += nmu) {
+          double acc = 0.;
+#pragma unroll
+          for (int q = 0; q < (NMU ? NMU : 16); ++q)
+            if (q < nmu) acc = fma(wv[q], pr[q], acc);
+          dst[l * nk] = acc;   // k fastest across the lanes: coalesced stores
+        }
+      }
+    }
+    __syncwarp();
   }
-  // zero the padding between / after the tables
+  // zero the padding between / after the segments
   const int nin = nell * nk;
-  for (int t = 0; t < 4; ++t)
+  for (int t = 0; t < nseg; ++t)
     for (int j = nin + lane; j < ntab; j += 32) row[2 + t * ntab + j] = 0.;
-  for (int j = 2 + 4 * ntab + lane; j < g.fpad; j += 32) row[j] = 0.;
+  for (int j = 2 + nseg * ntab + lane; j < g.fpad; j += 32) row[j] = 0.;
 }
 
 
@@ -612,18 +799,17 @@ int last_fftlog_ms(double* ms) {
 
 int launch_theory_features(const DevGen& g, const double* params, int d, long long N, long long npad, double* F, int fstride, cudaStream_t stream) {
   if (g.kind == DLB_GEN_KAISER) {
-    // nt is needed on the host for the shared-memory size: it is mirrored in aux[1] at plan creation
-    const int nt = g.aux[1];
-    int L = 1;
-    while (L * 32 < nt - 2) L *= 2;
-    const size_t smem = (size_t)KAISER_WARPS * (2 * nt + nt / L + 2) * sizeof(double);
-    static size_t configured_dev[64] = {};
-    size_t& configured = configured_dev[current_device_slot()];
-    if (smem > 48 * 1024 && smem > configured) {
-      DLB_CUDA(cudaFuncSetAttribute(kaiser_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
-    kaiser_kernel<<<(unsigned)((npad + KAISER_WARPS - 1) / KAISER_WARPS), KAISER_WARPS * 32, smem, stream>>>(g, params, d, N, npad, F, fstride);
+    // sizes needed on the host for the shared-memory budget are mirrored in aux[] at plan creation (csrc/plan.cu)
+    const int nmu = g.aux[5] & 0xFF, nseg = (g.aux[5] >> 8) & 0xFF, interp = (g.aux[5] >> 16) & 0xFF, nell = g.aux[3], nw_max = g.aux[7];
+    const int wd = kaiser_warp_doubles(nw_max, nmu, nell, nseg, interp);
+    const size_t smem = (size_t)KAISER_WARPS * wd * sizeof(double);
+    auto launch = [&](auto kernel) -> int {
+      DLB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+      kernel<<<(unsigned)((npad + KAISER_WARPS - 1) / KAISER_WARPS), KAISER_WARPS * 32, smem, stream>>>(g, params, d, N, npad, F, fstride, wd);
+      return DLB_OK;
+    };
+    if (nmu == 8) DLB_TRY(interp == 0 ? launch(kaiser_kernel<8, 0>) : launch(kaiser_kernel<8, 1>));
+    else DLB_TRY(interp == 0 ? launch(kaiser_kernel<0, 0>) : launch(kaiser_kernel<0, 1>));
     g_launches++;
     DLB_CUDA(cudaGetLastError());
     return DLB_OK;

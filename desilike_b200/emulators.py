@@ -139,7 +139,7 @@ class Emulator(object):
         tspec = dict(tspec, params=names)
         nin = len(theory.k) * len(theory.ells)
         obs = dict(name='fit', theory=tspec, terms=[dict(scale=1., factors=[], table='pk_dd')], nin=nin, wmatrix=None, offset=None, data=np.zeros(nin))
-        plan = Plan(dict(params=names, priors={}, solved=[], observables=[obs], precision=[np.ones(nin)]), with_theory=False)
+        plan = Plan(dict(params=names, priors={}, solved=[], observables=[obs], precision=[np.ones(nin)]), with_theory=False, merge_terms=False)
         feats = plan.features(0, X)
         gen = plan.lowered.gens[0]
         tables = {}

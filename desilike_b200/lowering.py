@@ -69,10 +69,50 @@ def _whitening(precision):
         return np.sqrt(np.clip(lam, 0., None))[:, None] * V.T
 
 
+def _merge_kaiser_terms(observables, names):
+    """Tracer combine folded into the Kaiser generator.  The sampled terms of an observable that multiply the plain Kaiser tables without a
+    column weight -- b1^2 pk_dd + 2 b1 pk_dt + pk_tt (reference full_shape.py:545-550) -- share one term matrix (the window), so their sum is ONE
+    contraction of the combined table  sum_j scale_j prod theta^pow table_j,  which the Kaiser kernel forms directly in its mu quadrature (weight
+    (b1 + f mu^2)^2): a third of the contraction FLOPs and a quarter of the feature columns.  Returns (observables with rewritten terms,
+    {id(theory): segments}) -- the segments list every direct Kaiser theory's generator must output (csrc/theory_kernels.cu: kaiser_kernel)."""
+    from .theory_lowering import KAISER_TABLE_ID
+    plain = ('pk_dd', 'pk_dt', 'pk_tt')
+    segments, out = {}, []
+    for obs in observables:
+        theory = obs['theory']
+        if theory.get('kind') != 'kaiser':
+            out.append(obs); continue
+        segs = segments.setdefault(id(theory), [])
+
+        def seg_index(seg):
+            for i, s_ in enumerate(segs):
+                if s_['flag'] == seg['flag'] and s_['combs'] == seg['combs']: return i
+            seg['name'] = seg.get('name') or 'combo{:d}'.format(len(segs))
+            segs.append(seg)
+            return len(segs) - 1
+
+        merge = [t for t in obs['terms'] if t.get('table') in plain and t.get('solved') is None and t.get('colvec') is None and t.get('outvec') is None]
+        terms = []
+        if len(merge) >= 2:
+            combs = tuple(sorted((KAISER_TABLE_ID[t['table']], float(t.get('scale', 1.)), tuple(sorted((names.index(n), int(p)) for n, p in t.get('factors', []))))
+                                 for t in merge))
+            i = seg_index(dict(flag=0, combs=combs))
+            terms.append(dict(scale=1., factors=[], table=segs[i]['name']))
+        for t in obs['terms']:
+            if len(merge) >= 2 and any(t is m for m in merge): continue
+            if t.get('table') in plain + ('pk11_l0',):
+                seg_index(dict(name=t['table'], flag=int(t['table'] == 'pk11_l0'), combs=((KAISER_TABLE_ID[t['table']], 1., ()),)))
+            terms.append(t)
+        out.append(dict(obs, terms=terms))
+    for segs in segments.values():
+        if len(segs) > 8: raise LoweringError('more than 8 output segments for one Kaiser theory')
+    return out, segments
+
+
 class _Generator(object):
     """Host description of one feature generator + where each theory table lives in its feature segment."""
 
-    def __init__(self, theory, names):
+    def __init__(self, theory, names, priors=None, segments=None):
         self.kind_name = theory['kind']
         self.params = list(theory['params'])
         defaults = theory.get('defaults', {})
@@ -91,8 +131,9 @@ class _Generator(object):
             from .mlp import lower_mlp
             lower_mlp(self, theory, defaults)
         elif self.kind_name in ('kaiser', 'bao_xi', 'bao_pk'):
-            from .theory_lowering import lower_theory
-            lower_theory(self, theory, defaults)
+            from .theory_lowering import lower_theory, kaiser_set_segments
+            lower_theory(self, theory, defaults, priors=priors)
+            if segments and self.kind_name == 'kaiser': kaiser_set_segments(self, segments)
         else:
             raise LoweringError('unknown theory kind {!r}'.format(self.kind_name))
 
@@ -111,7 +152,7 @@ class _Generator(object):
 class Lowered(object):
     """Flat arrays + ctypes descriptor (keeps every buffer alive until the plan has been created)."""
 
-    def __init__(self, spec, with_plain=True, reduce_rank=True):
+    def __init__(self, spec, with_plain=True, reduce_rank=True, merge_terms=True):
         self.spec = spec
         names = self.names = list(spec['params'])
         self.d = len(names)
@@ -129,11 +170,13 @@ class Lowered(object):
         self.xprior = (skind, sloc, sscale, slo, shi)
         # ---- generators (one per distinct theory object) ----
         self.gens, gen_of = [], {}
-        for obs in spec['observables']:
+        observables, segments = list(spec['observables']), {}
+        if merge_terms: observables, segments = _merge_kaiser_terms(observables, names)
+        for obs in observables:
             key = id(obs['theory'])
             if key not in gen_of:
                 gen_of[key] = len(self.gens)
-                self.gens.append(_Generator(obs['theory'], names))
+                self.gens.append(_Generator(obs['theory'], names, priors=spec.get('priors'), segments=segments.get(key)))
         # ---- coefficients ----
         self.coef_keys = {}
 
@@ -146,7 +189,6 @@ class Lowered(object):
 
         # ---- blocks ----
         prec = spec['precision']
-        observables = spec['observables']
         if isinstance(prec, (list, tuple)):   # one block per run of consecutive observables (usually one observable each; a SumLikelihood
             groups, io = [], 0                # member with a joint covariance over several observables gives one block for all of them)
             for p in prec:

@@ -21,7 +21,7 @@ class Plan(object):
     current torch stream, torch outputs, no host round trip.
     """
 
-    def __init__(self, spec, device=None, with_theory=True, reduce_rank=True):
+    def __init__(self, spec, device=None, with_theory=True, reduce_rank=True, merge_terms=True):
         self._lib = _capi.load()
         if self._lib.dlb_device_count() <= 0:
             raise _capi.DesilikeB200Error('no CUDA device visible: desilike_b200 has no CPU fallback')
@@ -32,7 +32,8 @@ class Plan(object):
         self.spec = spec
         # reduce_rank: blocks without solved parameters whose data vector is longer than their feature count are evaluated in the
         # row space of their term matrices (lowering.py: QR at plan time) -- same chi2, fewer columns
-        self.lowered = Lowered(spec, with_plain=with_theory, reduce_rank=reduce_rank)
+        # merge_terms: the tracer combine b1^2 dd + 2 b1 dt + tt of a direct Kaiser theory is formed inside the Kaiser kernel (lowering.py)
+        self.lowered = Lowered(spec, with_plain=with_theory, reduce_rank=reduce_rank, merge_terms=merge_terms)
         self.params = list(self.lowered.names)
         self.d, self.ns, self.ntheory = self.lowered.d, self.lowered.ns, self.lowered.ntheory
         self.solved_names = [s['name'] for s in spec.get('solved', [])]

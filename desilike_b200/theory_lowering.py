@@ -35,7 +35,83 @@ def _slots(gen, names_by_slot, defaults, names):
     return np.array(idx, dtype=np.int32), f64(dflt), plist
 
 
-def lower_theory(gen, theory, defaults, names=None):
+KAISER_TABLE_ID = {'pk_dd': 0, 'pk_dt': 1, 'pk_tt': 2, 'pk11_l0': 0}
+
+
+def kaiser_set_segments(gen, segments):
+    """(Re)build the payload of a Kaiser generator for the output segments ``segments`` = [dict(name, flag, combs=[(table id, ratio, ((param column,
+    power), ...)), ...])]: segment = sum_combs ratio * prod theta^power * table (csrc/theory_kernels.cu: kaiser_kernel).  Sets gen.tables /
+    gen.nfeat / gen.idata / gen.ddata."""
+    kz = gen._kaiser
+    if not 1 <= len(segments) <= 8:
+        raise ValueError('a Kaiser generator holds 1 to 8 output segments')
+    nseg, ntab, nin = len(segments), kz['ntab'], kz['nin']
+    total = 2 + nseg * ntab
+    recs, ratios = [], []
+    for seg in segments:
+        recs += [int(seg.get('flag', 0)), len(seg['combs'])]
+        for table, ratio, factors in seg['combs']:
+            factors = list(factors)
+            if len(factors) > 4: raise ValueError('too many factors in a merged bias monomial')
+            recs += [int(table), len(factors)] + [int(i) for i, _ in factors] + [0] * (4 - len(factors)) + [int(p) for _, p in factors] + [0] * (4 - len(factors))
+            ratios.append(float(ratio))
+    base, derived = kz['base'], kz['derived']   # derived ends with the 6 converged-pivot constants the kernel reads just before the ratios
+    header = kz['head'] + [total, base.size, 0, nseg, 16, base.size + derived.size, kz['interp'], kz['pad'], kz['nw_max']]
+    gen.idata = np.array(header + recs, dtype=np.int32)
+    gen.ddata = np.concatenate([base, derived, ratios])
+    gen.nfeat = total
+    gen.tables = {seg['name']: (2 + i * ntab, nin, None) for i, seg in enumerate(segments)}
+    gen.segments = list(segments)
+
+
+def _converged_pivots(consts, nt, uniform):
+    """Uniform knots: away from the two ends the pivots (w, 1 / b, c / b) of the not-a-knot tridiagonal solve converge geometrically to
+    constants.  -> [w_inf, invb_inf, cb_inf, first knot, last knot, 0] such that on [first, last] every tabulated pivot equals the constant to
+    1e-15 relative (the kernel then runs its sweeps without table loads); first > last when there is no such range."""
+    w, invb, cb = consts[2 * nt:3 * nt], consts[3 * nt:4 * nt], consts[4 * nt:5 * nt]
+    if not uniform or nt < 64: return np.array([0., 0., 0., 1., 0., 0.])
+    mid = nt // 2
+    ref = np.array([w[mid], invb[mid], cb[mid]])
+    ok = np.all(np.abs(np.stack([w, invb, cb], axis=-1) - ref) <= 1e-15 * np.abs(ref), axis=-1)
+    ok[0] = ok[-1] = False
+    lo = mid
+    while lo - 1 >= 1 and ok[lo - 1]: lo -= 1
+    hi = mid
+    while hi + 1 <= nt - 2 and ok[hi + 1]: hi += 1
+    return np.array([ref[0], ref[1], ref[2], float(lo), float(hi), 0.])
+
+
+def _ap_log_span(apmode, q0, q1, gen, defaults, priors, eta, mu):
+    """[min, max] of log10(F(mu) / qper) over the prior box of the AP parameters, or None when it is unbounded."""
+    base = {p.split('.')[-1]: p for p in gen.params}
+
+    def limits(slot):
+        if slot is None: return (1., 1.)
+        full = base.get(slot)
+        if full is None or full not in gen._names:
+            v = float(defaults.get(slot, 1.)); return (v, v)
+        prior = (priors or {}).get(full) or {}
+        lim = prior.get('limits')
+        if lim is None or lim[0] is None or lim[1] is None or not np.all(np.isfinite(lim)) or lim[0] <= 0.: return None
+        return (float(lim[0]), float(lim[1]))
+
+    l0, l1 = limits(q0), limits(q1)
+    if l0 is None or l1 is None: return None
+    vals = []
+    for a in np.linspace(l0[0], l0[1], 9):
+        for b in np.linspace(l1[0], l1[1], 9):
+            if apmode == 'qparqper': qpar, qper = a, b
+            elif apmode == 'qiso': qpar, qper = a, a
+            elif apmode == 'qap': qpar, qper = a**(1. - eta), a**(-eta)
+            else: qpar, qper = a * b**(1. - eta), a * b**(-eta)
+            qap = qpar / qper
+            fap = np.sqrt(1. + np.append(mu, [0., 1.])**2 * (1. / qap**2 - 1.))
+            vals.append(np.log10(fap / qper))
+    vals = np.concatenate(vals)
+    return float(vals.min()) - 1e-9, float(vals.max()) + 1e-9
+
+
+def lower_theory(gen, theory, defaults, names=None, priors=None):
     kind = theory['kind']
     tpl = theory['template']
     ells = tuple(theory['ells'])
@@ -62,31 +138,30 @@ def lower_theory(gen, theory, defaults, names=None):
         slots = [(q0, 1.), (q1, 1.), ('dm', 0.), ('dn', 0.), ('df', 1.), ('sigmapar', 0.), ('sigmaper', 0.), (None, 0.)]
         gen.param_idx, gen.param_default, gen.params = _slots(gen, slots, defaults, names)
         ell0 = ells.index(0) if 0 in ells else -1
-        total = 2 + 4 * ntab
-        base = np.concatenate([[float(tpl.get('eta', 1. / 3.)), a, float(tpl['f_fid']), 0.], k, mu, wmu.ravel(), pk, Tt, Lt,
-                               spline_constants(np.log10(k_t))])
-        # derived tables appended for the kernel: log10 k (so that log10(k_ap) = log10 k + log10(F(mu) / qper) costs one add per node)
-        # and the spline interval widths (no division in the evaluation)
-        # + the tridiagonal-sweep constants transposed to lane-major order: lane l owns the chunk of L knots starting at 1 + l L
-        #   (forward) / ending at m - l L (backward); element t of every lane's chunk is contiguous -> coalesced loads
-        consts = spline_constants(np.log10(k_t))
-        m = nt - 2
-        L = 1
-        while L * 32 < m: L *= 2
-        w_, invb_, cb_ = consts[2 * nt:3 * nt], consts[3 * nt:4 * nt], consts[4 * nt:5 * nt]
-        wT, invbT, cbT = np.zeros((L, 32)), np.zeros((L, 32)), np.zeros((L, 32))
-        for lane in range(32):
-            for t in range(L):
-                i = 1 + lane * L + t
-                if i <= m: wT[t, lane] = w_[i]
-                i = m - lane * L - t
-                if i >= 1: invbT[t, lane], cbT[t, lane] = invb_[i], cb_[i]
         from .spline import is_uniform
-        gen.idata = np.array([nk, nell, nmu, nt, APMODES[apmode], (ell0 << 8) | int(is_uniform(np.log10(k_t))), ntab, total, base.size, L], dtype=np.int32)
-        gen.ddata = np.concatenate([base, np.log10(k), np.append(np.diff(np.log10(k_t)), 0.), wT.ravel(), invbT.ravel(), cbT.ravel()])
-        gen.nfeat = total
-        for t, name in enumerate(['pk_dd', 'pk_dt', 'pk_tt', 'pk11_l0']):
-            gen.tables[name] = (2 + t * ntab, nin, None)
+        uniform = bool(is_uniform(np.log10(k_t)))
+        interp = {'scipy': 0, 'not-a-knot': 0, 'interpax': 1, 'local': 1}.get(str(theory.get('interp', tpl.get('interp', 'scipy'))), None)
+        if interp is None:
+            raise ValueError("theory['interp'] must be 'scipy' (not-a-knot C2 spline, the reference's NumPy branch jax.py:263-265) or 'interpax' "
+                             "(C1 local cubic, the reference's jax branch jax.py:258-261)")
+        pad = 28 if interp == 0 else 2
+        # largest window of template knots a point INSIDE the prior box can reach (the kernel's per-warp shared memory is sized for it): the AP
+        # factor log10(F(mu) / qper) is bounded from the limits of the AP parameters; without finite limits the whole grid
+        nw_max = nt
+        if uniform:
+            span = _ap_log_span(apmode, q0, q1, gen, defaults, priors, float(tpl.get('eta', 1. / 3.)), mu)
+            if span is not None:
+                dx = (np.log10(k_t[-1]) - np.log10(k_t[0])) / (nt - 1)
+                nw_max = int(min(nt, np.ceil((np.log10(k.max()) - np.log10(k.min()) + span[1] - span[0]) / dx) + 2 * pad + 6))
+        nw_max = max(nw_max, 8)
+        gen._kaiser = dict(head=[nk, nell, nmu, nt, APMODES[apmode], (ell0 << 8) | int(uniform), ntab], interp=interp, pad=pad, nw_max=nw_max,
+                           base=np.concatenate([[float(tpl.get('eta', 1. / 3.)), a, float(tpl['f_fid']), 0.], k, mu, wmu.ravel(), pk, Tt, Lt,
+                                                spline_constants(np.log10(k_t)), [np.log10(k).min(), np.log10(k).max()]]),
+                           derived=np.concatenate([np.log10(k), np.append(np.diff(np.log10(k_t)), 0.), _converged_pivots(spline_constants(np.log10(k_t)), nt, uniform)]),
+                           ntab=ntab, nin=nin)
+        # default output segments = the four plain tables; Lowered may replace them by merged combinations (kaiser_set_segments)
+        kaiser_set_segments(gen, [dict(name='pk_dd', flag=0, combs=[(0, 1., ())]), dict(name='pk_dt', flag=0, combs=[(1, 1., ())]),
+                                  dict(name='pk_tt', flag=0, combs=[(2, 1., ())]), dict(name='pk11_l0', flag=1, combs=[(0, 1., ())])])
         return
     if kind in ('bao_pk', 'bao_xi'):
         from .spline import second_derivatives

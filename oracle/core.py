@@ -68,6 +68,29 @@ def interp1d_cubic(xq, x, f):
     return interpolate.interp1d(x, f, kind='cubic', fill_value='extrapolate', axis=0)(xq)
 
 
+def interp1d_cubic_local(xq, x, f):
+    """The reference's jax branch (desilike/jax.py:258-261): ``interpax.interp1d(xq, x, f, method='cubic')`` -- interpax is a third-party
+    dependency absent from /root/reference and from this image (unpinned in pyproject.toml:33-35), so this RESTATES its published algorithm
+    (interpax/_spline.py: ``interp1d`` + ``approx_df(method='cubic')``), PARITY UNPINNED against interpax itself:
+    C1 cubic Hermite interpolation on [x_i, x_i+1] with knot derivatives fx_i = (s_{i-1} + s_i) / 2 from the secant slopes s_i = (f_i+1 - f_i) /
+    (x_i+1 - x_i) (fx_0 = s_0, fx_{n-1} = s_{n-2}), interval i = clip(searchsorted(x, xq, side='right'), 1, n - 1) - 1, and NaN outside
+    [x_0, x_{n-1}] (interpax default ``extrap=False``)."""
+    xq, x, f = np.asarray(xq, dtype='f8'), np.asarray(x, dtype='f8'), np.asarray(f, dtype='f8')
+    s = np.diff(f, axis=0) / np.diff(x).reshape((-1,) + (1,) * (f.ndim - 1))
+    fx = np.concatenate([s[:1], 0.5 * (s[:-1] + s[1:]), s[-1:]], axis=0)
+    shape = xq.shape
+    q = xq.ravel()
+    i = np.clip(np.searchsorted(x, q, side='right'), 1, x.size - 1) - 1
+    dx = x[i + 1] - x[i]
+    t = (q - x[i]) / dx
+    ex = (-1,) + (1,) * (f.ndim - 1)
+    t, dx = t.reshape(ex), dx.reshape(ex)
+    f0, f1, d0, d1 = f[i], f[i + 1], fx[i] * dx, fx[i + 1] * dx
+    out = f0 + t * (d0 + t * ((3. * (f1 - f0) - 2. * d0 - d1) + t * (-2. * (f1 - f0) + d0 + d1)))
+    out = np.where(((q < x[0]) | (q > x[-1])).reshape(ex), np.nan, out)
+    return out.reshape(shape + f.shape[1:])
+
+
 def interp1d_linear(xq, x, f):
     return interpolate.interp1d(x, f, kind='linear', fill_value='extrapolate', axis=0)(xq)
 
@@ -83,11 +106,12 @@ def shapefit_factor(k_t, dm, dn, a=0.6, kp=0.03):
 # Kaiser: reference desilike/theories/galaxy_clustering/full_shape.py:488-500 (tables), :545-550 (tracer combine),
 # :628-634 (EFT-like counter / stochastic add-ons)
 # --------------------------------------------------------------------------------------------------------------------
-def kaiser_tables(k, mu, wmu, k_t, pk_t, f, qpar, qper, sigmapar=0., sigmaper=0.):
+def kaiser_tables(k, mu, wmu, k_t, pk_t, f, qpar, qper, sigmapar=0., sigmaper=0., interp='scipy'):
     jac, kap, muap = ap_k_mu(k, mu, qpar, qper)
     sigmanl2 = kap**2 * (sigmapar**2 * muap**2 + sigmaper**2 * (1. - muap**2))
     damping = np.exp(-sigmanl2 / 2.)
-    pkmu = jac * damping * interp1d_cubic(np.log10(kap), np.log10(k_t), pk_t)
+    interp1d = interp1d_cubic if interp in ('scipy', 'not-a-knot') else interp1d_cubic_local   # reference jax.py:263-265 / :258-261
+    pkmu = jac * damping * interp1d(np.log10(kap), np.log10(k_t), pk_t)
 
     def to_poles(x):
         return np.sum(x * wmu[:, None, :], axis=-1)

@@ -49,7 +49,7 @@ def theory_tables(theory, X, names):
             qpar, qper = core.ap_qpar_qper(tpl['apmode'], p, tpl.get('eta', 1. / 3.))
             pk_t = tpl['pk_dd_fid'] * core.shapefit_factor(tpl['k'], p.get('dm', 0.), p.get('dn', 0.), tpl['a'], tpl['kp'])
             f = tpl['f_fid'] * p.get('df', 1.)
-            tabs = core.kaiser_tables(k, mu, wmu, tpl['k'], pk_t, f, qpar, qper, p.get('sigmapar', 0.), p.get('sigmaper', 0.))
+            tabs = core.kaiser_tables(k, mu, wmu, tpl['k'], pk_t, f, qpar, qper, p.get('sigmapar', 0.), p.get('sigmaper', 0.), interp=theory.get('interp', tpl.get('interp', 'scipy')))
             for name in ['pk_dd', 'pk_dt', 'pk_tt']:
                 out[name][ip] = tabs[name].ravel()
             out['pk11_l0'][ip] = np.tile(tabs['pk_dd'][list(theory['ells']).index(0)], len(theory['ells'])) if 0 in theory['ells'] else 0.

@@ -22,7 +22,8 @@ def features(low, X, feature_fn=None):
             mono = np.prod((Xe - gen.ddata)[:, None, :]**powers[None], axis=-1)
             out.append(np.concatenate([np.ones((X.shape[0], 1)), np.zeros((X.shape[0], 1)), mono], axis=-1))
         else:
-            out.append(feature_fn(ig, gen, Xe))
+            try: out.append(feature_fn(ig, gen, Xe, X))
+            except TypeError: out.append(feature_fn(ig, gen, Xe))
     return out
 
 
@@ -100,7 +101,7 @@ def evaluate(low, X, feature_fn=None, white=True):
     return dict(loglikelihood=ll, logprior=lp, logposterior=ll + lp, x_solved=xs[:, np.argsort(low.solved_order)] if ns else xs)
 
 
-def theory_features(ig, gen, Xe):
+def theory_features(ig, gen, Xe, X_full=None):
     """NumPy mirror of csrc/theory_kernels.cu for the direct theory generators, driven ONLY by the lowered payloads
     (idata / ddata) -- checks the plan-time constants (spline pivots, FFTLog tables) against the oracle on CPU."""
     from desilike_b200 import spline
@@ -123,21 +124,47 @@ def theory_features(ig, gen, Xe):
         wmu = dd[o:o + nell * nmu].reshape(nell, nmu); o += nell * nmu
         pk_fid, Tt, Lt = dd[o:o + nt], dd[o + nt:o + 2 * nt], dd[o + 2 * nt:o + 3 * nt]; o += 3 * nt
         consts = dd[o:o + 5 * nt + 4]
-        out = np.zeros((N, gen.nfeat)); out[:, 0] = 1.
+        nseg, off_seg, off_ratio, interp = idata[10], idata[11], idata[12], idata[13]
         ell0 = idata[5] >> 8
+        # segment records (csrc/theory_kernels.cu: kaiser_kernel)
+        segs, pos, rpos = [], off_seg, off_ratio
+        for _ in range(nseg):
+            flag, ncomb = idata[pos], idata[pos + 1]; pos += 2
+            combs = []
+            for c in range(ncomb):
+                table, nf = idata[pos], idata[pos + 1]
+                combs.append((table, dd[rpos], [(idata[pos + 2 + q], idata[pos + 6 + q]) for q in range(nf)])); rpos += 1; pos += 10
+            segs.append((flag, combs))
+        out = np.zeros((N, gen.nfeat)); out[:, 0] = 1.
+        xk = consts[:nt]
         for ip in range(N):
             q0, q1, dm, dn, df, spar, sper, _ = Xe[ip]
             qpar, qper = ap(q0, q1, eta)
             y = pk_fid * np.exp(dm * Tt + dn * Lt)
-            M = spline.second_derivatives(consts, nt, y)
             qap, jac = qpar / qper, 1. / (qpar * qper**2)
             fap = np.sqrt(1. + mu**2 * (1. / qap**2 - 1.))
             kap, muap = k[:, None] / qper * fap, np.broadcast_to(mu / qap / fap, (nk, nmu))
-            p = jac * spline.evaluate(consts, nt, y, M, np.log10(kap)) * np.exp(-0.5 * kap**2 * (spar**2 * muap**2 + sper**2 * (1 - muap**2)))
+            if interp == 0:
+                M = spline.second_derivatives(consts, nt, y)
+                pint = spline.evaluate(consts, nt, y, M, np.log10(kap))
+            else:
+                s_ = np.diff(y) / np.diff(xk)
+                fx = np.concatenate([s_[:1], 0.5 * (s_[:-1] + s_[1:]), s_[-1:]])
+                xq = np.log10(kap)
+                i = np.clip(np.searchsorted(xk, xq, side='right'), 1, nt - 1) - 1
+                h = xk[i + 1] - xk[i]; t = (xq - xk[i]) / h
+                d0, d1, dy = fx[i] * h, fx[i + 1] * h, y[i + 1] - y[i]
+                pint = np.where((xq < xk[0]) | (xq > xk[-1]), np.nan, y[i] + t * (d0 + t * ((3. * dy - 2. * d0 - d1) + t * (-2. * dy + d0 + d1))))
+            p = jac * pint * np.exp(-0.5 * kap**2 * (spar**2 * muap**2 + sper**2 * (1 - muap**2)))
             f = f_fid * df
-            tabs = [p @ wmu.T, (f * muap**2 * p) @ wmu.T, (f**2 * muap**4 * p) @ wmu.T]
-            for t, tab in enumerate(tabs): out[ip, 2 + t * ntab:2 + t * ntab + nell * nk] = tab.T.ravel()
-            out[ip, 2 + 3 * ntab:2 + 3 * ntab + nell * nk] = np.tile(tabs[0][:, ell0], nell) if ell0 >= 0 else 0.
+            tabs = [p @ wmu.T, (f * muap**2 * p) @ wmu.T, (f**2 * muap**4 * p) @ wmu.T]   # [nk, nell]
+            for iseg, (flag, combs) in enumerate(segs):
+                val = np.zeros((nk, nell))
+                for table, ratio, factors in combs:
+                    c = ratio * np.prod([X_full[ip, idx]**power for idx, power in factors]) if factors else ratio
+                    val += c * tabs[table]
+                if flag & 1: val = np.tile(val[:, [ell0]], (1, nell)) if ell0 >= 0 else 0. * val
+                out[ip, 2 + iseg * ntab:2 + iseg * ntab + nell * nk] = val.T.ravel()
         return out
     # BAO (+ FFTLog)
     eta, f_fid, rs = dd[0], dd[1], dd[2]

@@ -55,6 +55,11 @@ def test_product_does_not_import_oracle():
                 assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), fn
 
 
+def _with_interp(spec, interp):
+    for obs in spec['observables']: obs['theory']['interp'] = interp
+    return spec
+
+
 CASES = {
     'c2': lambda: configs.config_c2(nkin=50, nbins=12, order=2),
     'c2_random': lambda: configs.config_c2(nkin=30, nbins=8, order=3, coefficients='random'),
@@ -113,8 +118,14 @@ def _c3_kernel():
     return spec
 
 
+def _with_interp(spec, interp):
+    for obs in spec['observables']: obs['theory']['interp'] = interp
+    return spec
+
+
 THEORY_CASES = {
     'c1_kaiser': lambda: configs.config_c1(),
+    'c1_kaiser_interpax': lambda: _with_interp(configs.config_c1(), 'interpax'),
     'kaiser_window_eft_marg': lambda: configs.config_kaiser_window(eftlike=True, solved=True),
     'c3_bao_fftlog': lambda: configs.config_c3(),                    # P -> xi operator folded into the term matrices (default)
     'c3_bao_fftlog_kernel': lambda: _c3_kernel(),                    # explicit FFTLog kernel payload

@@ -18,7 +18,7 @@ def test_kaiser_tables_match_oracle(gpu_required):
     """Feature-level parity: pk_dd / pk_dt / pk_tt tables, relative 1e-10 (FP64)."""
     import desilike_b200
     spec = configs.config_kaiser_window(eftlike=True, solved=True)
-    plan = desilike_b200.Plan(spec)
+    plan = desilike_b200.Plan(spec, merge_terms=False)   # the four plain tables as separate output segments
     X = configs.sample_points(spec, 77, seed=3)
     feats = plan.features(0, X)
     gen = plan.lowered.gens[0]
@@ -281,3 +281,58 @@ def test_taylor_state_from_reference_fit_on_gpu(gpu_required):
         chi2 = -2. * plan.eval(data['xtest'])['loglikelihood']
         assert np.allclose(chi2, np.sum(want**2, axis=-1), rtol=1e-11)
         plan.close()
+
+
+@pytest.mark.parametrize('interp', ['scipy', 'interpax'])
+def test_kaiser_merged_combine_and_interpolants(gpu_required, interp):
+    """Direct Kaiser theory: (a) the tracer combine b1^2 dd + 2 b1 dt + tt formed INSIDE the Kaiser kernel (one merged output segment,
+    lowering._merge_kaiser_terms) == the three-table plan == the oracle; (b) both interpolants of the reference's ``interp1d(method='cubic')``:
+    SciPy not-a-knot (NumPy branch, jax.py:263-265) and the C1 local cubic of interpax (jax branch, jax.py:258-261; restated, oracle/core.py).
+    Theory vectors element-wise to 1e-10 away from zero crossings."""
+    import desilike_b200
+    for spec in [configs.config_c1(), configs.config_kaiser_window(eftlike=True, solved=True), configs.config_kaiser_window(eftlike=False, solved=False, nmu=5)]:
+        for obs in spec['observables']: obs['theory']['interp'] = interp
+        X = configs.sample_points(spec, 150, seed=8)
+        ref = pipeline.evaluate(spec, X, return_theory=True)
+        for merge in (True, False):
+            plan = desilike_b200.Plan(spec, merge_terms=merge)
+            assert ('combo0' in plan.lowered.gens[0].tables) == merge
+            theory, got = plan.theory(X), plan.eval(X)
+            scale = np.max(np.abs(ref['flattheory']), axis=0)
+            assert np.max(np.abs(theory - ref['flattheory']) / scale) < 1e-10
+            away = np.abs(ref['flattheory']) > 1e-3 * scale
+            assert np.max(np.abs(theory - ref['flattheory'])[away] / np.abs(ref['flattheory'])[away]) < 1e-10
+            assert np.all(np.abs(got['logposterior'] - ref['logposterior']) <= 1e-8 * np.maximum(1., np.abs(ref['logposterior'])))
+            plan.close()
+    # the two interpolants differ at the level the jax / NumPy branches of the reference differ (well above 1e-10): the switch is not a no-op
+    spec = configs.config_c1()
+    X = configs.sample_points(spec, 20, seed=9)
+    t0 = pipeline.evaluate(spec, X, return_theory=True)['flattheory']
+    spec['observables'][0]['theory']['interp'] = 'interpax'
+    t1 = pipeline.evaluate(spec, X, return_theory=True)['flattheory']
+    assert 1e-9 < np.max(np.abs(t1 - t0) / np.max(np.abs(t0), axis=0)) < 1e-2
+
+
+def test_kaiser_window_of_knots_edge_cases(gpu_required):
+    """The Kaiser kernel builds the spline only on the window of template knots a point reaches: points at the corners of the prior box, theory
+    nodes reaching both ends of the template grid (window = whole grid), and a prior without limits (window sized for the whole grid)."""
+    import desilike_b200
+    spec = configs.config_c1()
+    X = configs.sample_points(spec, 64, seed=10)
+    X[:4, 0] = [0.8, 1.2, 0.8, 1.2]; X[:4, 1] = [0.8, 0.8, 1.2, 1.2]     # corners of uniform[0.8, 1.2]^2
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    for priors in (spec['priors'], dict(spec['priors'], qpar=None, qper=None)):
+        plan = desilike_b200.Plan(dict(spec, priors=priors))
+        theory = plan.theory(X)
+        assert np.max(np.abs(theory - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-10
+        plan.close()
+    spec = configs.config_kaiser_window(eftlike=False, solved=False)
+    th = spec['observables'][0]['theory']
+    th['k'] = np.geomspace(1.3e-3, 0.75, len(th['k']))     # nodes close to both ends of the template grid geomspace(1e-3, 1, 500)
+    spec = configs._finish(dict(spec, solved=[]), [(spec['observables'][0]['kout'], th['ells'], 1e-4)], np.random.default_rng(1), configs._FID)
+    X = configs.sample_points(spec, 40, seed=11)
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    plan = desilike_b200.Plan(spec)
+    theory = plan.theory(X)
+    assert np.max(np.abs(theory - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-10
+    plan.close()

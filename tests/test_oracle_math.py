@@ -122,3 +122,27 @@ def test_kaiser_closed_form():
     expected = np.array([(b**2 + 2. / 3. * b * f + f**2 / 5.) * pk, (4. / 3. * b * f + 4. / 7. * f**2) * pk, 8. / 35. * f**2 * pk])
     assert np.max(np.abs(flat / expected - 1.)) < 5e-7  # spline interpolation error of the wiggly synthetic P(k)
     assert abs(pipeline.evaluate(spec, X)['loglikelihood'][0]) < 1e-18
+
+
+def test_local_cubic_interpolant_properties():
+    """oracle/core.py:interp1d_cubic_local restates interpax's C1 'cubic' (the reference's jax branch, jax.py:258-261; interpax is absent here):
+    mathematical pins -- interpolates the knots, reproduces quadratics exactly on a uniform grid (mean of secant slopes = exact derivative),
+    equals SciPy's CubicHermiteSpline fed with the same knot slopes, is C1 across knots, NaN outside the knot range."""
+    from scipy.interpolate import CubicHermiteSpline
+    from oracle import core
+    rng = np.random.default_rng(0)
+    x = np.linspace(-1., 2., 40)
+    f = np.stack([np.sin(3. * x), 0.3 * x**2 - x + 2.], axis=-1)
+    assert np.allclose(core.interp1d_cubic_local(x, x, f), f, rtol=0, atol=1e-14)
+    xq = rng.uniform(x[1], x[-2], 200)   # (the end intervals use one-sided slopes)
+    got = core.interp1d_cubic_local(xq, x, f)
+    assert np.allclose(got[:, 1], 0.3 * xq**2 - xq + 2., rtol=1e-12)
+    xn = np.sort(rng.uniform(0., 1., 30)); fn = np.cos(5. * xn)
+    s = np.diff(fn) / np.diff(xn)
+    fx = np.concatenate([s[:1], 0.5 * (s[:-1] + s[1:]), s[-1:]])
+    xq = rng.uniform(xn[0], xn[-1], 300)
+    assert np.allclose(core.interp1d_cubic_local(xq, xn, fn), CubicHermiteSpline(xn, fn, fx)(xq), rtol=1e-12, atol=1e-14)
+    eps = 1e-7
+    left, right = core.interp1d_cubic_local(xn[5:-5] - eps, xn, fn), core.interp1d_cubic_local(xn[5:-5] + eps, xn, fn)
+    assert np.allclose((right - left) / (2. * eps), fx[5:-5], rtol=1e-4, atol=1e-4)
+    assert np.all(np.isnan(core.interp1d_cubic_local(np.array([xn[0] - 0.1, xn[-1] + 0.1]), xn, fn)))
