@@ -173,6 +173,8 @@ struct DevGen {
 
 int launch_features(const DevGen& g, const double* params, int d, long long N, long long npad, double* F, int fstride, cudaStream_t stream);
 int launch_theory_features(const DevGen& g, const double* params, int d, long long N, long long npad, double* F, int fstride, cudaStream_t stream);  // csrc/theory_kernels.cu
+int launch_derived(const double* params, int d_in, int nder, const int* off, const int* code, const double* consts, long long N, double* out,
+                   cudaStream_t stream);   // csrc/features.cu: extended parameter rows
 int launch_mlp_input(const DevGen& g, const double* params, int d, long long N, long long npad, double* F, int fstride, cudaStream_t stream);
 // fused MLP forward (csrc/mlp.cu)
 size_t mlp_fused_smem(const int* idata_host);

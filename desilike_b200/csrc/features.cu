@@ -77,6 +77,44 @@ int launch_features(const DevGen& g, const double* params, int d, long long N, l
   return launch_theory_features(g, params, d, N, npad, F, fstride, stream);
 }
 
+// Derived-expression parameters (reference parameter.py:795-808, applied per point at base.py:537): one thread per point copies the d_in input
+// columns and appends the nder derived values, each a reverse-Polish program over the row (opcodes: include/desilike_b200.h).
+__global__ void derived_kernel(const double* __restrict__ params, int d_in, int nder, const int* __restrict__ off, const int* __restrict__ code,
+                               const double* __restrict__ consts, long long N, double* __restrict__ out) {
+  const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pt >= N) return;
+  const int d = d_in + nder;
+  double* row = out + pt * d;
+  for (int j = 0; j < d_in; ++j) row[j] = params[pt * d_in + j];
+  for (int i = 0; i < nder; ++i) {
+    double st[16];
+    int sp = 0;
+    for (int o = off[i]; o < off[i + 1]; ++o) {
+      const int op = code[2 * o], arg = code[2 * o + 1];
+      if (op == 0) { st[sp++] = row[arg]; continue; }
+      if (op == 1) { st[sp++] = consts[arg]; continue; }
+      if (op <= 6) {
+        const double b = st[--sp], a = st[sp - 1];
+        st[sp - 1] = op == 2 ? a + b : op == 3 ? a - b : op == 4 ? a * b : op == 5 ? a / b : pow(a, b);
+        continue;
+      }
+      const double a = st[sp - 1];
+      st[sp - 1] = op == 7 ? -a : op == 8 ? exp(a) : op == 9 ? log(a) : op == 10 ? sqrt(a) : op == 11 ? log10(a) : op == 12 ? fabs(a) :
+                   op == 13 ? sin(a) : op == 14 ? cos(a) : tanh(a);
+    }
+    row[d_in + i] = st[0];
+  }
+}
+
+int launch_derived(const double* params, int d_in, int nder, const int* off, const int* code, const double* consts, long long N, double* out,
+                   cudaStream_t stream) {
+  const int threads = 128;
+  derived_kernel<<<(unsigned)((N + threads - 1) / threads), threads, 0, stream>>>(params, d_in, nder, off, code, consts, N, out);
+  g_launches++;
+  DLB_CUDA(cudaGetLastError());
+  return DLB_OK;
+}
+
 int launch_mlp_input(const DevGen& g, const double* params, int d, long long N, long long npad, double* F, int fstride, cudaStream_t stream) {
   const int threads = 256;
   const long long total = npad * (g.nparams + 2);

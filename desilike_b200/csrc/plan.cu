@@ -51,7 +51,10 @@ struct MlpLayers { int act = 0; std::vector<Block> layers; std::vector<Launch> l
 
 struct dlb_plan {
   int device = 0;
-  int d = 0, ngen = 0, ncoef = 0, fstride = 4, ns = 0, nmarg = 0, ntheory = 0, nsm = 1, dpad = 1;
+  int d = 0, ngen = 0, ncoef = 0, fstride = 4, ns = 0, nmarg = 0, ntheory = 0, nsm = 1, dpad = 1;   // d: columns of the EXTENDED parameter row (inputs + derived)
+  int d_in = 0, nder = 0;              // input columns of the batch / derived-expression parameters appended to every row
+  int *d_der_off = nullptr, *d_der_code = nullptr; double* d_der_const = nullptr;
+  double* w_pext = nullptr;            // [cap, d] extended parameter rows (plans with derived parameters)
   bool resident = false;               // Taylor monomials evaluated inside the contraction kernel (no feature matrix in HBM)
   dlb::Launch launch;                  // the likelihood blocks
   // two-stage plans (an observable transform that is non-linear in the theory, reference power_spectrum.py:400-404): stage 1 = `launch` in output
@@ -449,9 +452,9 @@ static int build_mlp(dlb_plan* plan, const dlb_generator_desc& gd, DevGen& g, Ml
 
 static int ensure_workspace(dlb_plan* plan, long long npad) {
   if (npad <= plan->cap) return DLB_OK;
-  for (void* ptr : {(void*)plan->w_F, (void*)plan->w_partial, (void*)plan->w_params, (void*)plan->w_out, (void*)plan->w_status, (void*)plan->w_T})
+  for (void* ptr : {(void*)plan->w_F, (void*)plan->w_partial, (void*)plan->w_params, (void*)plan->w_out, (void*)plan->w_status, (void*)plan->w_T, (void*)plan->w_pext})
     if (ptr) cudaFree(ptr);
-  plan->w_F = plan->w_partial = plan->w_params = plan->w_out = plan->w_T = nullptr; plan->w_status = nullptr;
+  plan->w_F = plan->w_partial = plan->w_params = plan->w_out = plan->w_T = plan->w_pext = nullptr; plan->w_status = nullptr;
   plan->cap = 0;
   if (plan->two_stage) {
     DLB_CUDA(cudaMalloc((void**)&plan->w_T, ((size_t)npad * plan->tstride + 64) * sizeof(double)));
@@ -460,7 +463,8 @@ static int ensure_workspace(dlb_plan* plan, long long npad) {
   DLB_CUDA(cudaMalloc((void**)&plan->w_F, ((size_t)npad * plan->fstride + 64) * sizeof(double)));
   DLB_CUDA(cudaMemset(plan->w_F, 0, ((size_t)npad * plan->fstride + 64) * sizeof(double)));
   DLB_CUDA(cudaMalloc((void**)&plan->w_partial, (size_t)std::max(plan->ptotal, 1LL) * npad * sizeof(double)));
-  DLB_CUDA(cudaMalloc((void**)&plan->w_params, (size_t)npad * std::max(plan->d, 1) * sizeof(double)));
+  DLB_CUDA(cudaMalloc((void**)&plan->w_params, (size_t)npad * std::max(plan->d_in, 1) * sizeof(double)));
+  if (plan->nder) DLB_CUDA(cudaMalloc((void**)&plan->w_pext, (size_t)npad * plan->d * sizeof(double)));
   DLB_CUDA(cudaMalloc((void**)&plan->w_out, (size_t)npad * (3 + std::max(plan->ns, 0)) * sizeof(double)));
   DLB_CUDA(cudaMalloc((void**)&plan->w_status, (size_t)npad * sizeof(int)));
   plan->cap = npad;
@@ -578,7 +582,7 @@ void dlb_plan_destroy(dlb_plan* plan) {
   if (!plan) return;
   cudaSetDevice(plan->device);
   for (void* ptr : plan->owned) cudaFree(ptr);
-  for (void* ptr : {(void*)plan->w_F, (void*)plan->w_partial, (void*)plan->w_params, (void*)plan->w_out, (void*)plan->w_status, (void*)plan->w_theory, (void*)plan->w_T})
+  for (void* ptr : {(void*)plan->w_F, (void*)plan->w_partial, (void*)plan->w_params, (void*)plan->w_out, (void*)plan->w_status, (void*)plan->w_theory, (void*)plan->w_T, (void*)plan->w_pext})
     if (ptr) cudaFree(ptr);
   for (auto& e : plan->ev) if (e) cudaEventDestroy(e);
   if (plan->w_hess) cudaFree(plan->w_hess);
@@ -602,8 +606,31 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
   dlb_plan* plan = new dlb_plan();
   struct Guard { dlb_plan* p; ~Guard() { if (p) dlb_plan_destroy(p); } } guard{plan};
   DLB_CUDA(cudaGetDevice(&plan->device));
-  plan->d = desc->d; plan->ngen = desc->ngen; plan->ncoef = desc->ncoef; plan->ns = desc->ns; plan->nmarg = desc->nmarg;
-  plan->dpad = (desc->d + 1) | 1;   // + the constant-one column; odd stride keeps per-row accesses conflict free
+  DLB_REQUIRE(desc->nderived >= 0 && desc->nderived <= 64 && (desc->nderived == 0 || (desc->derived_off && desc->derived_code)), "derived parameters: 0 <= nderived <= 64 and tables required");
+  plan->d_in = desc->d; plan->nder = desc->nderived;
+  plan->d = desc->d + desc->nderived; plan->ngen = desc->ngen; plan->ncoef = desc->ncoef; plan->ns = desc->ns; plan->nmarg = desc->nmarg;
+  plan->dpad = (plan->d + 1) | 1;   // + the constant-one column; odd stride keeps per-row accesses conflict free
+  const int dext = plan->d;         // every index table addresses the extended parameter row
+  if (plan->nder) {
+    const int nops = desc->derived_off[plan->nder];
+    int nconst = 0;
+    for (int i = 0; i < plan->nder; ++i) {
+      DLB_REQUIRE(desc->derived_off[i] <= desc->derived_off[i + 1], "derived parameters: offsets must be non-decreasing");
+      int depth = 0;
+      for (int o = desc->derived_off[i]; o < desc->derived_off[i + 1]; ++o) {
+        const int op = desc->derived_code[2 * o], arg = desc->derived_code[2 * o + 1];
+        DLB_REQUIRE(op >= 0 && op <= 15, "derived parameters: unknown opcode");
+        if (op == 0) DLB_REQUIRE(arg >= 0 && arg < desc->d + i, "derived parameters: a program may read the inputs and EARLIER derived parameters only");
+        if (op == 1) { DLB_REQUIRE(arg >= 0 && desc->derived_const, "derived parameters: constant index"); nconst = std::max(nconst, arg + 1); }
+        depth += op <= 1 ? 1 : (op <= 6 ? -1 : 0);
+        DLB_REQUIRE(depth >= 1 && depth <= 16, "derived parameters: malformed program (stack depth)");
+      }
+      DLB_REQUIRE(depth == 1, "derived parameters: a program must leave exactly one value");
+    }
+    DLB_TRY(upload(plan, desc->derived_off, (size_t)plan->nder + 1, &plan->d_der_off));
+    DLB_TRY(upload(plan, desc->derived_code, (size_t)2 * nops, &plan->d_der_code));
+    DLB_TRY(upload(plan, desc->derived_const, (size_t)nconst, &plan->d_der_const));
+  }
   DLB_CUDA(cudaDeviceGetAttribute(&plan->nsm, cudaDevAttrMultiProcessorCount, plan->device));
   // generators / feature layout
   int foff = 0;
@@ -617,7 +644,7 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
     std::memset(&gendev[ig], 0, sizeof(GenDev));
     g.kind = gd.kind; g.nparams = gd.nparams; g.nfeat = gd.nfeat; g.fpad = (gd.nfeat + 3) & ~3; g.foff = foff;
     for (int j = 0; j < gd.nparams; ++j) {
-      DLB_REQUIRE(gd.param_idx[j] >= -1 && gd.param_idx[j] < desc->d, "generator: parameter index out of range");
+      DLB_REQUIRE(gd.param_idx[j] >= -1 && gd.param_idx[j] < dext, "generator: parameter index out of range");
       g.pidx[j] = gd.param_idx[j];
       g.pdef[j] = gd.param_default ? gd.param_default[j] : 0.;
     }
@@ -681,18 +708,18 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
     DLB_REQUIRE(cd.nf >= 0 && cd.nf <= DLB_COEF_MAXF, "coefficient: too many factors");
     coefs[j].scale = cd.scale; coefs[j].nf = cd.nf;
     for (int f = 0; f < cd.nf; ++f) {
-      DLB_REQUIRE(cd.idx[f] >= 0 && cd.idx[f] < desc->d, "coefficient: parameter index out of range");
+      DLB_REQUIRE(cd.idx[f] >= 0 && cd.idx[f] < dext, "coefficient: parameter index out of range");
       coefs[j].idx[f] = cd.idx[f]; coefs[j].pow[f] = cd.pow[f];
     }
   }
   DLB_TRY(upload(plan, coefs.data(), coefs.size(), &plan->d_coefs));
   // priors
   DLB_REQUIRE(desc->prior_kind && desc->prior_lo && desc->prior_hi && desc->prior_loc && desc->prior_scale, "prior tables required");
-  DLB_TRY(upload(plan, desc->prior_kind, (size_t)desc->d, &plan->d_prior_kind));
-  DLB_TRY(upload(plan, desc->prior_lo, (size_t)desc->d, &plan->d_prior_lo));
-  DLB_TRY(upload(plan, desc->prior_hi, (size_t)desc->d, &plan->d_prior_hi));
-  DLB_TRY(upload(plan, desc->prior_loc, (size_t)desc->d, &plan->d_prior_loc));
-  DLB_TRY(upload(plan, desc->prior_scale, (size_t)desc->d, &plan->d_prior_scale));
+  DLB_TRY(upload(plan, desc->prior_kind, (size_t)dext, &plan->d_prior_kind));
+  DLB_TRY(upload(plan, desc->prior_lo, (size_t)dext, &plan->d_prior_lo));
+  DLB_TRY(upload(plan, desc->prior_hi, (size_t)dext, &plan->d_prior_hi));
+  DLB_TRY(upload(plan, desc->prior_loc, (size_t)dext, &plan->d_prior_loc));
+  DLB_TRY(upload(plan, desc->prior_scale, (size_t)dext, &plan->d_prior_scale));
   // blocks: validate, pick the kernel variant (plan-wide) and the A-operand mode
   int max_slots = 1, ast = 4, maxK = 0;
   bool resident = true;
@@ -747,13 +774,13 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
       const dlb_generator_desc& gd = desc->gens[ig];
       if (!plan->gens[ig].aux[6]) continue;
       // per column: word 0 = parameter-tile column of each factor (desc->d = the constant-one column), word 1 = index into cval
-      const unsigned long long one = (unsigned long long)desc->d, none = (unsigned long long)MAXP;
+      const unsigned long long one = (unsigned long long)dext, none = (unsigned long long)MAXP;
       unsigned long long w0 = 0ull, w1 = 0ull;
       for (int k = 0; k < 7; ++k) { w0 |= one << (8 * k); w1 |= none << (8 * k); }
       std::vector<unsigned long long> paths((size_t)2 * ast);
       for (int c = 0; c < ast; ++c) { paths[2 * c] = w0 | 0xFF00000000000000ull; paths[2 * c + 1] = w1; }   // structural zeros
       paths[0] = w0;                                                                                          // column 0 = 1 (empty product)
-      DLB_REQUIRE(desc->d < 255, "too many parameters for the in-kernel monomial evaluation");
+      DLB_REQUIRE(dext < 255, "too many parameters for the in-kernel monomial evaluation");
       for (int t = 0; t < gd.nfeat - 2 && 2 + t < ast; ++t) {
         unsigned long long a0 = w0, a1 = w1;
         int k = 0;
@@ -779,7 +806,7 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
           if (find_col(key_of(pw)) < 0) col_of.emplace_back(key_of(pw), 2 + t);
         }
         std::vector<unsigned long long> pass1, pass2;
-        const unsigned long long one = (unsigned long long)desc->d, none = (unsigned long long)MAXP;
+        const unsigned long long one = (unsigned long long)dext, none = (unsigned long long)MAXP;
         auto word1 = [&](int col, unsigned long long ca, unsigned long long cb, unsigned long long ia, unsigned long long ib, bool zero) {
           return ca | (cb << 8) | (ia << 16) | (ib << 24) | ((unsigned long long)col << 32) | (zero ? 0xFF00000000000000ull : 0ull);
         };
@@ -1095,11 +1122,15 @@ static int eval_impl(dlb_plan* plan, const double* params, int64_t N, double* lo
       const long long off = (long long)c * sublen, len = std::min(sublen, n - off);
       if (len <= 0) break;
       const long long npad_s = (len + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
-      const double* d_params = params + (start + off) * plan->d;
+      const double* d_params = params + (start + off) * plan->d_in;
       if (!in_dev) {
-        DLB_CUDA(cudaMemcpyAsync(plan->w_params + off * plan->d, d_params, (size_t)len * plan->d * sizeof(double), cudaMemcpyHostToDevice, s_in));
-        d_params = plan->w_params + off * plan->d;
+        DLB_CUDA(cudaMemcpyAsync(plan->w_params + off * plan->d_in, d_params, (size_t)len * plan->d_in * sizeof(double), cudaMemcpyHostToDevice, s_in));
+        d_params = plan->w_params + off * plan->d_in;
         if (nsub > 1) { DLB_CUDA(cudaEventRecord(plan->ev_pipe[c], s_in)); DLB_CUDA(cudaStreamWaitEvent(stream, plan->ev_pipe[c], 0)); }
+      }
+      if (plan->nder) {   // extended rows: inputs + derived-expression parameters (reference base.py:537)
+        DLB_TRY(launch_derived(d_params, plan->d_in, plan->nder, plan->d_der_off, plan->d_der_code, plan->d_der_const, len, plan->w_pext + off * plan->d, stream));
+        d_params = plan->w_pext + off * plan->d;
       }
       if (plan->timing) DLB_CUDA(cudaEventRecord(plan->ev[0], stream));
       rc = run_front(plan, d_params, len, npad_s, stream);
@@ -1171,10 +1202,14 @@ int dlb_theory_batch(dlb_plan* plan, const double* params, int64_t N, double* th
     const long long npad = (n + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
     int rc = ensure_workspace(plan, npad);
     if (rc) return rc;
-    const double* d_params = params + start * plan->d;
+    const double* d_params = params + start * plan->d_in;
     if (!in_dev) {
-      DLB_CUDA(cudaMemcpyAsync(plan->w_params, d_params, (size_t)n * plan->d * sizeof(double), cudaMemcpyHostToDevice, stream));
+      DLB_CUDA(cudaMemcpyAsync(plan->w_params, d_params, (size_t)n * plan->d_in * sizeof(double), cudaMemcpyHostToDevice, stream));
       d_params = plan->w_params;
+    }
+    if (plan->nder) {
+      DLB_TRY(launch_derived(d_params, plan->d_in, plan->nder, plan->d_der_off, plan->d_der_code, plan->d_der_const, n, plan->w_pext, stream));
+      d_params = plan->w_pext;
     }
     double* d_theory = theory + start * plan->ntheory;
     if (!out_dev) {
@@ -1209,10 +1244,14 @@ int dlb_features_batch(dlb_plan* plan, int32_t gen, const double* params, int64_
     const long long npad = (n + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
     int rc = ensure_workspace(plan, npad);
     if (rc) return rc;
-    const double* d_params = params + start * plan->d;
+    const double* d_params = params + start * plan->d_in;
     if (!in_dev) {
-      DLB_CUDA(cudaMemcpyAsync(plan->w_params, d_params, (size_t)n * plan->d * sizeof(double), cudaMemcpyHostToDevice, stream));
+      DLB_CUDA(cudaMemcpyAsync(plan->w_params, d_params, (size_t)n * plan->d_in * sizeof(double), cudaMemcpyHostToDevice, stream));
       d_params = plan->w_params;
+    }
+    if (plan->nder) {
+      DLB_TRY(launch_derived(d_params, plan->d_in, plan->nder, plan->d_der_off, plan->d_der_code, plan->d_der_const, n, plan->w_pext, stream));
+      d_params = plan->w_pext;
     }
     rc = run_front(plan, d_params, n, npad, stream, true);
     if (rc) return rc;
@@ -1251,15 +1290,15 @@ int dlb_ensemble_step(dlb_plan* plan, double* walkers, double* logposterior, int
     if (plan->w_prop) cudaFree(plan->w_prop);
     if (plan->w_logpy) cudaFree(plan->w_logpy);
     plan->w_prop = plan->w_logpy = nullptr; plan->prop_cap = 0;
-    DLB_CUDA(cudaMalloc((void**)&plan->w_prop, (size_t)n1 * plan->d * sizeof(double)));
+    DLB_CUDA(cudaMalloc((void**)&plan->w_prop, (size_t)n1 * plan->d_in * sizeof(double)));
     DLB_CUDA(cudaMalloc((void**)&plan->w_logpy, (size_t)n1 * sizeof(double)));
     plan->prop_cap = n1;
   }
   for (int half = 0; half < 2; ++half) {
     const long long na = half == 0 ? n0 : n1;
-    DLB_TRY(launch_stretch_propose(walkers, plan->d, n0, n1, half, seed, iteration, a, rank_offset, plan->w_prop, stream));
+    DLB_TRY(launch_stretch_propose(walkers, plan->d_in, n0, n1, half, seed, iteration, a, rank_offset, plan->w_prop, stream));
     DLB_TRY(dlb_eval_batch(plan, plan->w_prop, na, plan->w_logpy, nullptr, nullptr, nullptr, nullptr, stream_));
-    DLB_TRY(launch_stretch_accept(walkers, logposterior, plan->w_prop, plan->w_logpy, plan->d, n0, n1, half, seed, iteration, a, rank_offset,
+    DLB_TRY(launch_stretch_accept(walkers, logposterior, plan->w_prop, plan->w_logpy, plan->d_in, n0, n1, half, seed, iteration, a, rank_offset,
                                   reinterpret_cast<unsigned long long*>(naccept), stream));
   }
   return DLB_OK;

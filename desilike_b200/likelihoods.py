@@ -40,7 +40,8 @@ class BaseLikelihood(object):
     solved_default = '.marg'   # reference likelihoods/base.py:207
 
     def __init__(self):
-        self._plan, self._spec = None, None
+        self._plan, self._spec, self._signature = None, None, None
+        self._extra_params = ParameterCollection()   # parameters added through ``likelihood.all_params[name] = {...}`` (inputs of derived expressions)
         self.loglikelihood = self.logprior = None
         self.flattheory = self.flatdiff = None
 
@@ -49,7 +50,15 @@ class BaseLikelihood(object):
     def all_params(self):
         params = ParameterCollection()
         for obs in self.observables: params = params + obs.theory.all_params + obs.params
+        if not hasattr(self, '_extra_params'): self._extra_params = ParameterCollection()
+        params = params + self._extra_params
+        params._on_new = self._extra_params.set
         return params
+
+    def _params_signature(self):
+        """Cheap fingerprint of everything a plan depends on in the parameters: a later ``Parameter.update(fixed=..., prior=..., value=..., derived=...)``
+        rebuilds the plan at the next evaluation (the reference re-initialises its pipeline on parameter updates)."""
+        return tuple((p.name, p.value, p.fixed, repr(p.prior), repr(p.derived)) for p in self.all_params)
 
     @property
     def varied_params(self):
@@ -69,15 +78,32 @@ class BaseLikelihood(object):
         varied = [p.name for p in all_params if p.varied and not p.solved]
         solved = [p for p in all_params if p.solved]
         solved_names = [p.name for p in solved]
-        fixed = {p.name: p.value for p in all_params if not p.varied}
-        spec = dict(params=varied, priors={p.name: p.prior for p in all_params if p.name in varied}, observables=[], precision=None,
+        # derived-expression parameters ('{b}**2', reference parameter.py:795-808): evaluated per point on the device; an expression may only use
+        # sampled parameters and derived ones defined before it (fixed parameters are substituted by their values)
+        exprs = [p for p in all_params if p.depends]
+        fixed = {p.name: p.value for p in all_params if not p.varied and not p.depends}
+        derived, known = [], set(varied)
+        pending = list(exprs)
+        while pending:
+            progress = False
+            for p in list(pending):
+                expr, ok = p.derived, True
+                for name in p.depends:
+                    if name in fixed: expr = expr.replace('{' + name + '}', '({!r})'.format(float(fixed[name])))
+                    elif name not in known: ok = False
+                if ok:
+                    derived.append(dict(name=p.name, expr=expr)); known.add(p.name); pending.remove(p); progress = True
+            if not progress:
+                raise PipelineError('derived parameters {} depend on unknown (or solved) parameters'.format([p.name for p in pending]))
+        derived_names = [dp['name'] for dp in derived]
+        spec = dict(params=varied, derived=derived, priors={p.name: p.prior for p in all_params if p.name in varied}, observables=[], precision=None,
                     solved=[dict(name=p.name, value=p.value, prior=p.prior, marg=p.derived.replace('.auto', self.solved_default).startswith('.marg'),
                                  mode='prec' if p.derived.startswith('.prec') else None) for p in solved],
                     fiducial={p.name: p.value for p in all_params if p.name in varied})   # '.prec': Jacobian at the default values (reference likelihoods/base.py:288-296)
         for obs in self.observables:
             ospec = obs.observable_spec()
             theory = obs.theory.theory_spec()
-            theory['params'] = [n for n in theory['params'] if n in varied]
+            theory['params'] = [n for n in theory['params'] if n in varied or n in derived_names]
             theory['defaults'] = dict(theory.get('defaults', {}))
             terms = resolve_terms(list(obs.theory.terms()) + list(obs.systematic_terms()), solved_names, fixed)
             ospec.update(theory=theory, terms=terms)
@@ -89,9 +115,13 @@ class BaseLikelihood(object):
 
     @property
     def plan(self):
+        signature = self._params_signature()
+        if self._plan is not None and getattr(self, '_signature', None) is None: self._signature = signature   # plan set from outside
+        if self._plan is not None and signature != self._signature: self._invalidate()
         if self._plan is None:
             self._spec = self._finalize_spec(self.build_spec())
             self._plan = Plan(self._spec)
+            self._signature = signature
         return self._plan
 
     @property

@@ -14,7 +14,8 @@ so that per point the GPU only evaluates features f(theta), bias monomials c(the
 Nothing here runs per point.
 
 Likelihood spec (plain dicts / ndarrays; the same structure the oracle evaluates un-collapsed):
-  spec = dict(params=[names], priors={name: dict(dist, limits, loc, scale) | None},
+  spec = dict(params=[names], derived=[dict(name, expr)]  (optional: derived-expression parameters, '{b}**2'; terms / theories may use their names),
+              priors={name: dict(dist, limits, loc, scale) | None},
               solved=[dict(name, value, prior, marg)], observables=[obs, ...],
               precision=[P_b per observable] | P joint [n, n] | diag [n])
   obs  = dict(theory=dict(kind='taylor'|'mlp'|'kaiser'|'bao_xi'|'bao_pk', params=[...], ...constants...),
@@ -154,9 +155,23 @@ class Lowered(object):
 
     def __init__(self, spec, with_plain=True, reduce_rank=True, merge_terms=True):
         self.spec = spec
-        names = self.names = list(spec['params'])
+        # derived-expression parameters (reference parameter.py:795-808, base.py:537): columns appended to every parameter row by a small
+        # kernel; every index table below addresses the extended row, the batch itself has self.d_in columns
+        from .expressions import compile_expression, ExpressionError
+        self.input_names = list(spec['params'])
+        self.d_in = len(self.input_names)
+        names = self.names = self.input_names + [dp['name'] for dp in spec.get('derived', [])]
+        if len(set(names)) != len(names): raise LoweringError('duplicate parameter names (sampled / derived): {}'.format(names))
+        self.derived_programs, self.derived_consts = [], []
+        for i, dp in enumerate(spec.get('derived', [])):
+            try: prog, consts = compile_expression(dp['expr'], {n: j for j, n in enumerate(names[:self.d_in + i])})
+            except ExpressionError as exc: raise LoweringError(str(exc))
+            prog = [(op, arg if op != 1 else self._const_index(consts[arg])) for op, arg in prog]
+            self.derived_programs.append(prog)
         self.d = len(names)
-        self.prior = _prior_tables(names, spec.get('priors', {}))
+        priors = dict(spec.get('priors', {}) or {})
+        for dp in spec.get('derived', []): priors[dp['name']] = None   # the prior is over the sampled parameters (reference parameter.py:1889-1897)
+        self.prior = _prior_tables(names, priors)
         # ---- solved parameters: '.marg' first (so log det(-H[marg, marg]) is a leading-block Cholesky product) ----
         solved = list(spec.get('solved', []))
         order = [i for i, s in enumerate(solved) if s.get('marg', True)] + [i for i, s in enumerate(solved) if not s.get('marg', True)]
@@ -310,10 +325,21 @@ class Lowered(object):
         self.with_plain = with_plain
         self._build_desc()
 
+    def _const_index(self, value):
+        if value not in self.derived_consts: self.derived_consts.append(value)
+        return self.derived_consts.index(value)
+
     def _build_desc(self):
         keep = self._keep = []
         desc = _capi.PlanDesc()
-        desc.abi_version, desc.d = _capi.DLB_ABI_VERSION, self.d
+        desc.abi_version, desc.d = _capi.DLB_ABI_VERSION, self.d_in
+        nder = len(self.derived_programs)
+        if nder:
+            off = i32(np.cumsum([0] + [len(p) for p in self.derived_programs]))
+            code = i32(np.array([pair for p in self.derived_programs for pair in p]).ravel())
+            consts = f64(self.derived_consts if self.derived_consts else [0.])
+            keep += [off, code, consts]
+            desc.nderived, desc.derived_off, desc.derived_code, desc.derived_const = nder, as_ptr(off, ctypes.c_int32), as_ptr(code, ctypes.c_int32), as_ptr(consts)
         kind, lo, hi, loc, scale = [np.ascontiguousarray(a) for a in self.prior]
         keep += [kind, lo, hi, loc, scale]
         desc.prior_kind, desc.prior_lo, desc.prior_hi = as_ptr(kind, ctypes.c_int32), as_ptr(lo), as_ptr(hi)

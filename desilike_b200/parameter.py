@@ -1,7 +1,7 @@
 """Minimal parameter containers mirroring the part of desilike/parameter.py the batched path needs:
-name / value / fixed / prior / derived ('.marg', '.best', '.auto', '.prec' mark analytically solved parameters,
-reference parameter.py:659,864-866) and name-based selection.  Not a re-implementation of the reference's 3000-line
-module: containers only, no expression evaluation, no Samples algebra."""
+name / value / fixed / prior / derived and name-based selection.  ``derived``: '.marg', '.best', '.auto', '.prec' mark analytically solved
+parameters (reference parameter.py:659,864-866); any other string is an EXPRESSION of other parameters, '{b}**2' (reference parameter.py:795-808),
+compiled for the device by desilike_b200/expressions.py.  Not a re-implementation of the reference's 3000-line module: no Samples algebra."""
 import fnmatch
 
 import numpy as np
@@ -37,6 +37,14 @@ class Parameter(object):
     def varied(self):
         return not self.fixed and (self.derived is False or self.solved)
 
+    @property
+    def depends(self):
+        """Names of the parameters a derived-expression parameter is computed from (reference parameter.py ``Parameter.depends``); else []."""
+        if isinstance(self.derived, str) and not self.derived.startswith('.'):
+            from .expressions import depends
+            return depends(self.derived)
+        return []
+
     def update(self, **kwargs):
         for key, val in kwargs.items():
             if key == 'prior' and val is not None:
@@ -58,9 +66,27 @@ class Parameter(object):
 
 class ParameterCollection(object):
 
-    def __init__(self, params=()):
+    def __init__(self, params=(), on_new=None):
         self.data = []
+        self._on_new = on_new   # owner hook: ``collection[name] = {...}`` with a new name registers the parameter with the owner (a likelihood)
         for p in params: self.set(p)
+
+    def __setitem__(self, name, item):
+        """``params['b'] = {'prior': {'limits': [0., 2.]}}`` (reference parameter.py:1855-1871): update an existing parameter or add a new one."""
+        name = getattr(name, 'name', name)
+        if isinstance(item, Parameter):
+            if item.name != name: raise KeyError('Parameter {} must be indexed by name (incorrect {})'.format(item.name, name))
+            new = name not in self
+            self.set(item)
+            if new and self._on_new is not None: self._on_new(item)
+            return
+        if name in self:
+            self[name].update(**dict(item))
+            return
+        namespace, _, basename = str(name).rpartition('.')
+        param = Parameter(basename, namespace=namespace, **dict(item))
+        self.set(param)
+        if self._on_new is not None: self._on_new(param)
 
     def set(self, param):
         for i, p in enumerate(self.data):

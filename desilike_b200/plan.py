@@ -34,8 +34,8 @@ class Plan(object):
         # row space of their term matrices (lowering.py: QR at plan time) -- same chi2, fewer columns
         # merge_terms: the tracer combine b1^2 dd + 2 b1 dt + tt of a direct Kaiser theory is formed inside the Kaiser kernel (lowering.py)
         self.lowered = Lowered(spec, with_plain=with_theory, reduce_rank=reduce_rank, merge_terms=merge_terms)
-        self.params = list(self.lowered.names)
-        self.d, self.ns, self.ntheory = self.lowered.d, self.lowered.ns, self.lowered.ntheory
+        self.params = list(self.lowered.input_names)   # columns of the batch (derived-expression parameters are appended on the device)
+        self.d, self.ns, self.ntheory = self.lowered.d_in, self.lowered.ns, self.lowered.ntheory
         self.solved_names = [s['name'] for s in spec.get('solved', [])]
         handle = ctypes.c_void_p()
         _capi.check(self._lib.dlb_plan_create(ctypes.byref(self.lowered.desc), ctypes.byref(handle)))

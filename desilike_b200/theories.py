@@ -92,6 +92,7 @@ class BaseTracerPowerSpectrumMultipoles(BaseCalculator):
         self.k = np.linspace(0.01, 0.2, 101) if k is None else np.asarray(k, dtype='f8')   # reference base.py:16-19
         self.ells, self.mu, self.nd, self.tracer = tuple(ells), int(mu), 1. / float(shotnoise), tracer
         self.params = ParameterCollection()
+        self._pt = None   # the perturbation-theory parameters are created ONCE (updates through all_params must stick)
 
     def _ns(self, name):
         return '{}.{}'.format(self.tracer, name) if self.tracer else name
@@ -102,7 +103,8 @@ class BaseTracerPowerSpectrumMultipoles(BaseCalculator):
 
     @property
     def all_params(self):
-        base = self.pt.all_params if self.pt is not None else (self.template.params + self._pt_params())
+        if self.pt is None and self._pt is None: self._pt = self._pt_params()
+        base = self.pt.all_params if self.pt is not None else (self.template.params + self._pt)
         return base + self.params
 
     def _pt_params(self):
@@ -268,9 +270,11 @@ class _BaseBAOTracer(BaseCalculator):
         self.template, self.ells, self.mu, self.mode, self.smoothing_radius, self.tracer = template, tuple(ells), int(mu), str(mode), float(smoothing_radius), tracer
         if self.mode not in ('', 'recsym', 'reciso'): raise ValueError('Reconstruction mode {} must be one of ["", "recsym", "reciso"]'.format(mode))
         self.params = ParameterCollection([
-            Parameter('b1', prior=dict(limits=[0.2, 4.]), ref=dict(limits=[1.5, 2.5])), Parameter('dbeta', value=1., prior=dict(limits=[0.7, 1.3]), ref=dict(limits=[0.8, 1.2])),
-            Parameter('sigmas', value=0., prior=dict(limits=[0., 10.]), ref=dict(limits=[0., 1.])),
-            Parameter('sigmapar', value=9., fixed=True, prior=dict(limits=[0.1, 10.])), Parameter('sigmaper', value=6., fixed=True, prior=dict(limits=[0.1, 10.]))])
+            Parameter('b1', prior=dict(limits=[0.2, 4.]), ref=dict(limits=[1.5, 2.5]), namespace=tracer),
+            Parameter('dbeta', value=1., prior=dict(limits=[0.7, 1.3]), ref=dict(limits=[0.8, 1.2]), namespace=tracer),
+            Parameter('sigmas', value=0., prior=dict(limits=[0., 10.]), ref=dict(limits=[0., 1.]), namespace=tracer),
+            Parameter('sigmapar', value=9., fixed=True, prior=dict(limits=[0.1, 10.]), namespace=tracer),
+            Parameter('sigmaper', value=6., fixed=True, prior=dict(limits=[0.1, 10.]), namespace=tracer)])
 
     @property
     def all_params(self):
@@ -309,7 +313,7 @@ class DampedBAOWigglesTracerPowerSpectrumMultipoles(_BaseBAOTracer):
         self.kp = float(kp)
         for ell in self.ells:
             for power in range(-3, 2):
-                self.params.set(Parameter('al{:d}_{:d}'.format(ell, power), value=0., ref=dict(limits=[-1e2, 1e2]), delta=0.005))
+                self.params.set(Parameter('al{:d}_{:d}'.format(ell, power), value=0., ref=dict(limits=[-1e2, 1e2]), delta=0.005, namespace=self.tracer))
 
     def set_k(self, k, ells):
         self.k, self.ells = np.asarray(k, dtype='f8'), tuple(ells)
@@ -338,7 +342,7 @@ class DampedBAOWigglesTracerCorrelationFunctionMultipoles(_BaseBAOTracer):
         self.sp = 2. * np.pi / 0.02 if sp is None else float(sp)
         for ell in self.ells:
             for power in range(-2, 3):
-                self.params.set(Parameter('al{:d}_{:d}'.format(ell, power), value=0., ref=dict(limits=[-1e-3, 1e-3]), delta=0.005))
+                self.params.set(Parameter('al{:d}_{:d}'.format(ell, power), value=0., ref=dict(limits=[-1e-3, 1e-3]), delta=0.005, namespace=self.tracer))
 
     def set_k(self, s, ells):
         self.s, self.ells = np.asarray(s, dtype='f8'), tuple(ells)

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DLB_ABI_VERSION 3
+#define DLB_ABI_VERSION 4
 
 typedef enum {
   DLB_OK = 0,
@@ -119,7 +119,7 @@ typedef struct {
 
 typedef struct {
   int32_t abi_version;      /* DLB_ABI_VERSION */
-  int32_t d;                /* number of columns of the batch `params` */
+  int32_t d;                /* number of columns of the batch `params` (the sampled inputs) */
   /* prior over the d input columns (reference parameter.py:1994-2017): kind 0 none, 1 uniform, 2 normal */
   const int32_t* prior_kind; const double* prior_lo; const double* prior_hi; const double* prior_loc; const double* prior_scale;
   int32_t ngen; const dlb_generator_desc* gens;
@@ -131,6 +131,13 @@ typedef struct {
   const double* x0;          /* [ns] value at which d0 and J are evaluated (the parameter defaults) */
   const int32_t* xprior_kind;/* [ns] 0 none (improper), 1 uniform (limits only), 2 normal */
   const double* xprior_loc; const double* xprior_scale; const double* xprior_lo; const double* xprior_hi; /* [ns] */
+  /* Derived-expression parameters (reference parameter.py:795-808 Parameter.eval, :1872-1887 ParameterCollection.eval, applied per point at
+   * base.py:537): parameter j = d + i of the EXTENDED parameter row is a function of the d input columns (and of earlier derived ones), e.g.
+   * b1 = b**2.  Every index table above (generator param_idx, coefficient idx, the prior tables, which then have d + nderived entries) addresses
+   * the extended row.  Expression i is the reverse-Polish program derived_code[2 * derived_off[i] : 2 * derived_off[i + 1]] of (opcode, argument)
+   * pairs: 0 push column `argument` of the extended row (< d + i), 1 push derived_const[argument], 2 add, 3 sub, 4 mul, 5 div, 6 pow, 7 neg,
+   * 8 exp, 9 log, 10 sqrt, 11 log10, 12 abs, 13 sin, 14 cos, 15 tanh (stack depth <= 16); evaluated by a small kernel in front of every pass. */
+  int32_t nderived; const int32_t* derived_off; const int32_t* derived_code; const double* derived_const;
 } dlb_plan_desc;
 
 typedef struct dlb_plan dlb_plan;

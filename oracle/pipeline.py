@@ -196,6 +196,21 @@ def evaluate(spec, X, return_theory=False, return_hessian=False):
     spec = marginalize_precision(spec)
     X = np.atleast_2d(np.asarray(X, dtype='f8'))
     names = list(spec['params'])
+    if spec.get('derived'):
+        # derived-expression parameters (reference parameter.py:795-808 Parameter.eval -> utils.evaluate(expression, locals); applied per point at
+        # base.py:537): evaluated with Python's eval on the batch columns, like the reference; the prior stays over the sampled parameters
+        cols = {n: X[:, i] for i, n in enumerate(names)}
+        for dp in spec['derived']:
+            import re
+            deps = re.findall(r'\{([^{}]+)\}', dp['expr'])
+            expr = dp['expr']
+            for j, n in enumerate(deps): expr = expr.replace('{' + n + '}', '__p{:d}__'.format(j))
+            cols[dp['name']] = np.broadcast_to(eval(expr, {'np': np, 'jnp': np, 'sqrt': np.sqrt, 'exp': np.exp, 'log': np.log, 'pi': np.pi, '__builtins__': {}},
+                                                    {'__p{:d}__'.format(j): cols[n] for j, n in enumerate(deps)}), (X.shape[0],)).astype('f8')
+        sampled = list(names)
+        names = sampled + [dp['name'] for dp in spec['derived']]
+        X = np.column_stack([cols[n] for n in names])
+        spec = dict(spec, params=names, derived=[], priors=dict(spec.get('priors', {}), **{dp['name']: None for dp in spec['derived']}))
     solved = spec.get('solved', [])
     x0 = {s['name']: float(s.get('value', 0.)) for s in solved}
     N = X.shape[0]

@@ -35,8 +35,27 @@ def coefficients(low, X):
     return C
 
 
-def evaluate(low, X, feature_fn=None, white=True):
+def expand(low, X):
+    """Extended parameter rows: inputs + derived-expression parameters (mirror of csrc/features.cu: derived_kernel)."""
     X = np.asarray(X, dtype='f8')
+    cols = [X[:, j] for j in range(X.shape[1])]
+    for prog in getattr(low, 'derived_programs', []):
+        st = []
+        for op, arg in prog:
+            if op == 0: st.append(cols[arg])
+            elif op == 1: st.append(np.full(X.shape[0], low.derived_consts[arg]))
+            elif op <= 6:
+                b, a = st.pop(), st.pop()
+                st.append({2: a + b, 3: a - b, 4: a * b, 5: a / b}.get(op) if op != 6 else np.power(a, b))
+            else:
+                a = st.pop()
+                st.append({7: np.negative, 8: np.exp, 9: np.log, 10: np.sqrt, 11: np.log10, 12: np.abs, 13: np.sin, 14: np.cos, 15: np.tanh}[op](a))
+        cols.append(st[0])
+    return np.column_stack(cols)
+
+
+def evaluate(low, X, feature_fn=None, white=True):
+    X = expand(low, X)
     N = X.shape[0]
     F, C = features(low, X, feature_fn), coefficients(low, X)
     ns = low.ns

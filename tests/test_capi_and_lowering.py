@@ -264,3 +264,37 @@ def test_semidefinite_precision_is_lowered():
     assert np.allclose(got['loglikelihood'], ref['loglikelihood'], rtol=1e-9, atol=1e-7)
     with pytest.raises(LoweringError):
         Lowered(dict(spec, precision=[P - 2. * np.outer(Pv, Pv) / v.dot(Pv)]))   # indefinite
+
+
+def test_derived_expression_parameters_lowering():
+    """Derived-expression parameters (reference parameter.py:795-808; applied per point at base.py:537) compiled to reverse-Polish programs:
+    the lowered plan (NumPy mirror of the kernels) == the oracle, which evaluates the expression like the reference (Python eval); and the
+    reference's own pin (tests/test_base.py:156-165): b1 = b**2 leaves the marginalised likelihood invariant."""
+    from desilike_b200.lowering import Lowered, LoweringError
+    from desilike_b200 import expressions
+    base = configs.config_c5(ntracers=2, nkin=20, nbins=6, order=2, solved=True)
+    X = configs.sample_points(base, 9, seed=4)
+    ref = pipeline.evaluate(base, X)
+    # T0.b1 = b**2, T1.b1 = 2 * b * exp(-c) + 0.5: the sampled columns become (qpar, qper, dm, df, b, c)
+    spec = dict(base)
+    names = list(base['params'])
+    i0, i1 = names.index('T0.b1'), names.index('T1.b1')
+    spec['params'] = [n for n in names if n not in ('T0.b1', 'T1.b1')] + ['b', 'c']
+    spec['derived'] = [dict(name='T0.b1', expr='{b}**2'), dict(name='T1.b1', expr='2. * {b} * np.exp(-{c}) + 0.5')]
+    spec['priors'] = dict({n: p for n, p in base['priors'].items() if n in spec['params']}, b=dict(dist='uniform', limits=(0., 3.)), c=None)
+    b = np.sqrt(X[:, i0])
+    c = -np.log((X[:, i1] - 0.5) / (2. * b))
+    Xd = np.column_stack([X[:, [names.index(n) for n in spec['params'][:-2]]], b, c])
+    orc = pipeline.evaluate(spec, Xd)
+    assert np.allclose(orc['loglikelihood'], ref['loglikelihood'], rtol=1e-11, atol=1e-9)   # reparametrisation invariance of the marginalised likelihood
+    low = Lowered(spec)
+    assert low.d_in == len(spec['params']) and low.d == low.d_in + 2
+    got = lowered_numpy.evaluate(low, Xd)
+    assert np.allclose(got['loglikelihood'], orc['loglikelihood'], rtol=1e-11, atol=1e-9)
+    assert np.allclose(got['logprior'], orc['logprior'], rtol=1e-12, atol=1e-12)
+    assert np.allclose(got['x_solved'], orc['x_solved'], rtol=1e-9, atol=1e-9)
+    with pytest.raises(LoweringError):
+        Lowered(dict(spec, derived=[dict(name='T0.b1', expr='{nope}**2'), spec['derived'][1]]))
+    with pytest.raises(LoweringError):
+        Lowered(dict(spec, derived=[dict(name='T0.b1', expr='__import__("os").getcwd()'), spec['derived'][1]]))
+    assert expressions.depends('{a} + {b} * {a}') == ['a', 'b']

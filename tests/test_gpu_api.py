@@ -277,3 +277,28 @@ def test_vmap_error_conventions_on_failed_points(gpu_required):
     assert sorted(errs) == list(range(n)) and isinstance(errs[0][0], ArithmeticError) and np.all(np.isnan(res))   # no good point to copy from
     res = dl.vmap(bad, errors='nan')(params)
     assert np.all(np.isnan(res))
+
+
+def test_derived_expression_parameter_reparametrisation(gpu_required):
+    """The reference's own pin for derived-expression parameters (desilike/tests/test_base.py:156-165), through the mirror API on the CUDA path:
+    ``likelihood.all_params['b1'].update(derived='{b}**2', prior=None); likelihood.all_params['b'] = {'prior': {'limits': [0., 2.]}}`` --
+    the marginalised likelihood at b = sqrt(1.5) equals the one at b1 = 1.5.  Also: a later Parameter.update rebuilds the plan."""
+    like = kaiser_likelihood()
+    for p in like.all_params:
+        if p.basename == 'sn0': p.update(derived='.marg')
+    like(b1=1.5)
+    bak = like.loglikelihood
+    assert 'b1' in like.plan.params
+    like.all_params['b1'].update(derived='{b}**2', prior=None)
+    like.all_params['b'] = {'prior': {'limits': [0., 2.]}}
+    assert 'b' in like.varied_params.names() and 'b1' not in like.varied_params.names()
+    like(b=1.5**0.5)
+    assert 'b' in like.plan.params and 'b1' not in like.plan.params       # the plan was rebuilt for the new parametrisation
+    assert np.allclose(like.loglikelihood, bak, rtol=1e-12, atol=1e-9)
+    bs = np.linspace(0.8, 1.6, 7)
+    res = dl.vmap(like)({'b': bs})
+    like.all_params['b1'].update(derived=False, prior=dict(limits=[0., 4.]))
+    like._extra_params = dl.ParameterCollection()
+    res1 = dl.vmap(like)({'b1': bs**2})
+    assert np.allclose(res, res1, rtol=1e-12, atol=1e-9)
+    assert np.isneginf(dl.vmap(like)({'b1': np.array([5.])}))[0]   # b1 prior limits [0, 4] are back
