@@ -67,7 +67,19 @@ def spec_from_likelihood(likelihood, solved_default='.marg', all_params=None):
         is_xi = hasattr(w, 'sin')
         xin, ellsin = np.asarray(w.sin if is_xi else w.kin, dtype='f8'), tuple(w.ellsin)
         nin = len(ellsin) * xin.size
-        basenames = {n.split('.')[-1]: v for n, v in defaults.items()}
+        # the kernel slots of a theory are resolved by BASENAME: restrict names and defaults to the theory's OWN parameters (a SumLikelihood with
+        # namespaced per-tracer parameters LRG.b1 / ELG.b1 must not drive one tracer's kernel with another tracer's values)
+        own = [p.name for p in th.all_params]
+        basenames = {}
+        for n in own:
+            if n not in defaults: continue
+            b = n.split('.')[-1]
+            if b in basenames and n in varied and any(m in varied and m != n and m.split('.')[-1] == b for m in own):
+                raise NotImplementedError('theory {} has two varied parameters with basename {!r}: kernel slots are resolved by basename'.format(tname, b))
+            basenames[b] = defaults[n]
+
+        def own_varied(slots):
+            return [n for n in varied if n in own and n.split('.')[-1] in slots]
         if tname in _THEORIES and not is_xi:
             pt, tpl = th.pt, th.pt.template
             if type(tpl).__name__ != 'ShapeFitPowerSpectrumTemplate':
@@ -81,7 +93,7 @@ def spec_from_likelihood(likelihood, solved_default='.marg', all_params=None):
                           template=dict(kind='shapefit', k=np.array(tpl.k, dtype='f8'), pk_dd_fid=np.array(tpl.pk_dd_fid, dtype='f8'),
                                         pknow_dd_fid=np.array(tpl.pknow_dd_fid, dtype='f8'), f_fid=float(tpl.f_fid), a=float(tpl.a), kp=float(tpl.kp),
                                         apmode=str(tpl.apeffect.mode), eta=float(getattr(tpl, 'eta', 1. / 3.)), only_now=bool(getattr(tpl, 'only_now', False))),
-                          params=[n for n in varied if n.split('.')[-1] in ('qpar', 'qper', 'qiso', 'qap', 'dm', 'dn', 'df', 'sigmapar', 'sigmaper')], defaults=basenames)
+                          params=own_varied(('qpar', 'qper', 'qiso', 'qap', 'dm', 'dn', 'df', 'sigmapar', 'sigmaper')), defaults=basenames)
         elif tname in ('DampedBAOWigglesTracerPowerSpectrumMultipoles', 'DampedBAOWigglesTracerCorrelationFunctionMultipoles') and is_xi == tname.endswith('CorrelationFunctionMultipoles'):
             # damped BAO (bao.py:117-151) + power-law broadband in x / pivot (bao.py:467-476, :527-534; :849-853, :905)
             pt, tpl = th.pt, th.pt.template
@@ -96,7 +108,7 @@ def spec_from_likelihood(likelihood, solved_default='.marg', all_params=None):
             theory = dict(kind='bao_xi' if is_xi else 'bao_pk', ells=ellsin, nmu=len(pt.mu), mode=str(pt.mode), smoothing_radius=float(pt.smoothing_radius),
                           template=dict(kind='bao', k=np.array(tpl.k, dtype='f8'), pk_dd_fid=np.array(tpl.pk_dd_fid, dtype='f8'), pknow_dd_fid=np.array(tpl.pknow_dd_fid, dtype='f8'),
                                         f_fid=float(tpl.f_fid), apmode=str(tpl.apeffect.mode), eta=float(getattr(tpl, 'eta', 1. / 3.))),
-                          params=[n for n in varied if n.split('.')[-1] in ('qpar', 'qper', 'qiso', 'qap', 'df', 'b1', 'dbeta', 'sigmas', 'sigmapar', 'sigmaper')], defaults=basenames)
+                          params=own_varied(('qpar', 'qper', 'qiso', 'qap', 'df', 'b1', 'dbeta', 'sigmas', 'sigmapar', 'sigmaper')), defaults=basenames)
             if is_xi: theory.update(s=xin, kin=np.array(th.kin, dtype='f8') if hasattr(th, 'kin') else None)
             else: theory.update(k=xin)
         else:

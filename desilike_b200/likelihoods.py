@@ -200,10 +200,24 @@ class ObservablesGaussianLikelihood(BaseLikelihood):
             nbins = sum(obs.size for obs in self.observables)
             A = 2. / (self.nobs - nbins - 1.) / (self.nobs - nbins - 4.)
             B = (self.nobs - nbins - 2.) / (self.nobs - nbins - 1.) / (self.nobs - nbins - 4.)
-            nparams = len(spec['params']) + len(spec['solved'])
+            # varied (sampled + solved) parameters reachable from THIS likelihood's observables (reference likelihoods/base.py:641-652): in a
+            # SumLikelihood the spec carries the union of all members' parameters
+            used = set()
+            for ospec in spec['observables']:
+                used |= set(ospec['theory'].get('params', []))
+                for term in ospec['terms']:
+                    used |= {n for n, _ in term.get('factors', [])}
+                    if term.get('solved') is not None: used.add(term['solved'])
+            for dp in spec.get('derived', []):   # a derived-expression parameter stands for the sampled parameters it is computed from
+                if dp['name'] in used:
+                    from .expressions import depends
+                    used |= set(depends(dp['expr']))
+            varied_names = set(spec['params']) | {s['name'] for s in spec['solved']}
+            nparams = len(used & varied_names)
             self.percival2014_factor = (1 + B * (nbins - nparams)) / (1 + A + B * (nparams + 1))
             precision = [p / self.percival2014_factor for p in precision] if isinstance(precision, list) else precision / self.percival2014_factor
         spec['precision'] = precision
+        if isinstance(precision, list): spec['prec_groups'] = [list(range(len(precision)))]   # the blocks of ONE likelihood: '.prec' updates them jointly
         # synthetic data generated from the theory at given parameters (reference power_spectrum.py:95-97)
         pending = [obs for obs in self.observables if obs.flatdata is None]
         for obs, ospec in zip(self.observables, spec['observables']):
@@ -233,16 +247,19 @@ class SumLikelihood(BaseLikelihood):
         self.observables = [obs for like in self.likelihoods for obs in like.observables]
 
     def _finalize_spec(self, spec):
-        precisions, offset = [], 0
+        precisions, groups, offset = [], [], 0
         for like in self.likelihoods:
             nobs = len(like.observables)
             sub = dict(spec, observables=spec['observables'][offset:offset + nobs])
+            sub.pop('prec_groups', None)
             sub = like._finalize_spec(sub)
+            first = len(precisions)
             if not isinstance(sub['precision'], list):
                 precisions.append(sub['precision'])   # one block for the member (joint over its observables)
             else:
                 precisions += list(sub['precision'])
+            groups.append(list(range(first, len(precisions))))   # '.prec' pre-marginalisation acts per member likelihood
             offset += nobs
-        spec['precision'] = precisions
+        spec['precision'], spec['prec_groups'] = precisions, groups
         self.flatdata = np.concatenate([obs.flatdata for obs in self.observables])
         return spec

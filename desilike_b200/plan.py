@@ -207,25 +207,51 @@ def premarginalize_precision(spec):
     loc = np.array([float((s.get('prior') or {}).get('loc', 0.)) for s in prec])
     scale = np.array([float((s.get('prior') or {}).get('scale', np.inf)) if (s.get('prior') or {}).get('dist') == 'norm' else np.inf for s in prec])
     prior_prec = np.where(np.isinf(scale), 0., 1. / scale**2)
-    sizes = [len(obs['data']) for obs in spec['observables']]
     precision = spec['precision']
     blocks = [np.asarray(p, dtype=np.float64) for p in precision] if isinstance(precision, (list, tuple)) else [np.asarray(precision, dtype=np.float64)]
     bsizes = [P.shape[0] for P in blocks]   # a block covers one observable or a run of consecutive observables
-    new_prec, start = [], 0
-    for P, n in zip(blocks, bsizes):
-        Jb = J[:, start:start + n]
-        start += n
-        idx = np.flatnonzero(np.any(Jb != 0., axis=1))
-        if idx.size == 0:
-            new_prec.append(P); continue
-        Jb = Jb[idx]
-        derivp = Jb * P if P.ndim == 1 else Jb.dot(P)
+    starts = np.concatenate([[0], np.cumsum(bsizes)])
+    # The reference updates the precision per LIKELIHOOD, with that likelihood's full precision (likelihoods/base.py:298-308): blocks that belong
+    # to one likelihood (an ObservablesGaussianLikelihood built from per-observable covariances; spec['prec_groups']) are updated JOINTLY -- a
+    # '.prec' parameter entering two of its observables couples them, the group becomes one dense block -- and a '.prec' parameter shared between
+    # likelihoods is an error there too (:285-288).
+    groups = [list(g) for g in spec.get('prec_groups', [])] or [[b] for b in range(len(blocks))]
+    if sorted(b for g in groups for b in g) != list(range(len(blocks))) or any(g != list(range(g[0], g[0] + len(g))) for g in groups):
+        raise ValueError("spec['prec_groups'] must partition the precision blocks into runs of consecutive blocks")
+    member = [[i for i in range(len(prec)) if any(np.any(J[i, starts[b]:starts[b + 1]] != 0.) for b in g)] for g in groups]
+    shared = [pnames[i] for i in range(len(prec)) if sum(i in m for m in member) > 1]
+    if shared:
+        raise ValueError('cannot use .prec for parameters that are shared between likelihoods (we would need to create a joint covariance matrix!); '
+                         'common block is {}'.format(shared))
+    new_prec = []
+    for g, idx in zip(groups, member):
+        sl = slice(starts[g[0]], starts[g[-1] + 1])
+        touching = [b for b in g if any(np.any(J[i, starts[b]:starts[b + 1]] != 0.) for i in idx)]
+        if not idx:
+            new_prec += [blocks[b] for b in g]; continue
+        if len(touching) <= 1 and len(g) > 1:   # the update stays inside one block of the group: keep the block structure
+            for b in g:
+                P = blocks[b]
+                if b not in touching: new_prec.append(P); continue
+                Jb = J[idx][:, starts[b]:starts[b + 1]]
+                derivp = Jb * P if P.ndim == 1 else Jb.dot(P)
+                H = derivp.dot(Jb.T) + np.diag(prior_prec[idx])
+                new_prec.append((np.diag(P) if P.ndim == 1 else P) - derivp.T.dot(np.linalg.solve(H, derivp)))
+            continue
+        n = sl.stop - sl.start
+        P = np.zeros((n, n))
+        for b in g:
+            o = starts[b] - sl.start
+            P[o:o + bsizes[b], o:o + bsizes[b]] = np.diag(blocks[b]) if blocks[b].ndim == 1 else blocks[b]
+        Jb = J[idx][:, sl]
+        derivp = Jb.dot(P)
         H = derivp.dot(Jb.T) + np.diag(prior_prec[idx])
-        new_prec.append((np.diag(P) if P.ndim == 1 else P) - derivp.T.dot(np.linalg.solve(H, derivp)))
+        new_prec.append(P - derivp.T.dot(np.linalg.solve(H, derivp)))
     shift = J.T.dot(loc)
     out = dict(spec)
     out['solved'] = [dict(s) for s in solved if s.get('mode') != 'prec']
     out['precision'] = new_prec if isinstance(precision, (list, tuple)) else new_prec[0]
+    out.pop('prec_groups', None)
     values = {s['name']: float(s.get('value', 0.)) for s in prec}
     out['observables'], start = [], 0
     for obs in spec['observables']:

@@ -157,20 +157,39 @@ def marginalize_precision(spec):
     scale = np.array([float((s.get('prior') or {}).get('scale', np.inf)) if (s.get('prior') or {}).get('dist') == 'norm' else np.inf for s in prec])
     prior_prec = np.where(np.isinf(scale), 0., 1. / scale**2)
     blocks = _precision_blocks(spec)
+    # per LIKELIHOOD (reference :298-308): spec['prec_groups'] lists the precision blocks of each likelihood (default: one block each); the
+    # update uses the likelihood's full precision, and a '.prec' parameter shared between likelihoods is an error (:285-288)
+    groups = [list(g) for g in spec.get('prec_groups', [])] or [[b] for b in range(len(blocks))]
+    member = [[i for i in range(len(prec)) if any(np.any(J[i, blocks[b][0]] != 0.) for b in g)] for g in groups]
+    shared = [prec[i]['name'] for i in range(len(prec)) if sum(i in m for m in member) > 1]
+    if shared:
+        raise ValueError('cannot use .prec for parameters that are shared between likelihoods (we would need to create a joint covariance matrix!); common block is {}'.format(shared))
     new_prec, shift = [], J.T.dot(loc)
-    for sl, P in blocks:
-        Jb = J[:, sl]
-        idx = np.flatnonzero(np.any(Jb != 0., axis=1))
-        if idx.size == 0:
-            new_prec.append(P); continue
-        Jb = Jb[idx]
-        derivp = Jb * P if P.ndim == 1 else Jb.dot(P)
+    for g, idx in zip(groups, member):
+        if not idx:
+            new_prec += [blocks[b][1] for b in g]; continue
+        touching = [b for b in g if any(np.any(J[i, blocks[b][0]] != 0.) for i in idx)]
+        if len(g) == 1 or len(touching) <= 1:
+            for b in g:
+                sl, P = blocks[b]
+                if b not in touching: new_prec.append(P); continue
+                Jb = J[idx][:, sl]
+                derivp = Jb * P if P.ndim == 1 else Jb.dot(P)
+                H = derivp.dot(Jb.T) + np.diag(prior_prec[idx])
+                full = np.diag(P) if P.ndim == 1 else P
+                new_prec.append(full - derivp.T.dot(np.linalg.solve(H, derivp)))
+            continue
+        sl = slice(blocks[g[0]][0].start, blocks[g[-1]][0].stop)
+        import scipy.linalg
+        P = scipy.linalg.block_diag(*[np.diag(blocks[b][1]) if blocks[b][1].ndim == 1 else blocks[b][1] for b in g])
+        Jb = J[idx][:, sl]
+        derivp = Jb.dot(P)
         H = derivp.dot(Jb.T) + np.diag(prior_prec[idx])
-        full = np.diag(P) if P.ndim == 1 else P
-        new_prec.append(full - derivp.T.dot(np.linalg.solve(H, derivp)))
+        new_prec.append(P - derivp.T.dot(np.linalg.solve(H, derivp)))
     out = dict(spec)
     out['solved'] = [dict(s) for s in solved if s.get('mode') != 'prec']
     out['precision'] = new_prec if isinstance(spec['precision'], (list, tuple)) else new_prec[0]
+    out.pop('prec_groups', None)
     pnames = {s['name']: float(s.get('value', 0.)) for s in prec}
     observables, start = [], 0
     for obs in spec['observables']:

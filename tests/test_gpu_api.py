@@ -302,3 +302,33 @@ def test_derived_expression_parameter_reparametrisation(gpu_required):
     res1 = dl.vmap(like)({'b1': bs**2})
     assert np.allclose(res, res1, rtol=1e-12, atol=1e-9)
     assert np.isneginf(dl.vmap(like)({'b1': np.array([5.])}))[0]   # b1 prior limits [0, 4] are back
+
+
+def test_prec_premarginalisation_couples_observables_of_one_likelihood(gpu_required):
+    """'.prec' parameters entering TWO observables of one likelihood: the reference updates that likelihood's full precision (likelihoods/base.py:
+    298-308), which couples the observables (one dense block); the same parameters shared between two likelihoods are an error (:285-288)."""
+    base = configs.config_kaiser_window(eftlike=True, solved=True)
+    obs0 = base['observables'][0]
+    obs1 = dict(obs0, name='LRG2', data=obs0['data'] * 1.01)
+    spec = dict(base, observables=[obs0, obs1], precision=[base['precision'][0], 0.8 * base['precision'][0]], prec_groups=[[0, 1]],
+                solved=[dict(s, mode='prec') for s in base['solved']], fiducial={n: configs._FID[n] for n in base['params']})
+    X = configs.sample_points(spec, 40, seed=12)
+    ref = pipeline.evaluate(spec, X)
+    plan = dl.Plan(spec)
+    assert len(plan.spec['precision']) == 1 and plan.spec['precision'][0].shape == (2 * len(obs0['data']),) * 2   # one coupled block
+    got = plan.eval(X)
+    assert np.allclose(got['logposterior'], ref['logposterior'], rtol=1e-9, atol=1e-7)
+    plan.close()
+    # block-by-block treatment (the previous behaviour) gives a different answer: the coupling matters
+    wrong = pipeline.evaluate(dict(spec, prec_groups=[[0, 1]], precision=[spec['precision'][0], spec['precision'][1]]), X)['logposterior']
+    indep = [pipeline.marginalize_precision(dict(spec, observables=[o], precision=[p], prec_groups=[[0]])) for o, p in zip(spec['observables'], spec['precision'])]
+    assert not np.allclose(indep[0]['precision'][0], plan.spec['precision'][0][:len(obs0['data']), :len(obs0['data'])], rtol=1e-6)
+    assert np.allclose(wrong, ref['logposterior'])
+    for groups in ([[0], [1]], None):
+        bad = dict(spec)
+        if groups is None: bad.pop('prec_groups')
+        else: bad['prec_groups'] = groups
+        with pytest.raises(ValueError):
+            dl.Plan(bad)
+        with pytest.raises(ValueError):
+            pipeline.evaluate(bad, X)
