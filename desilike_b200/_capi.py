@@ -12,7 +12,7 @@ from .build import LIBPATH
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
 
-DLB_ABI_VERSION = 4
+DLB_ABI_VERSION = 5
 DLB_COEF_MAXF = 4
 GEN_TAYLOR, GEN_MLP, GEN_KAISER, GEN_BAO = 1, 2, 3, 4
 PT_NONFINITE, PT_OUT_OF_PRIOR, PT_NOT_SPD = 1, 2, 4
@@ -36,7 +36,8 @@ class BlockDesc(ctypes.Structure):
     _fields_ = [('ncols', ctypes.c_int32), ('nslots', ctypes.c_int32), ('nterms', ctypes.c_int32), ('terms', ctypes.POINTER(TermDesc)),
                 ('matrices_white', c_double_p), ('matrices_plain', c_double_p), ('r0_white', c_double_p), ('t0_plain', c_double_p),
                 ('slot_solved', c_int32_p), ('nconst', ctypes.c_int32), ('const_solved', c_int32_p), ('gconst_white', c_double_p),
-                ('transform_data', c_double_p), ('whitening_t', c_double_p), ('r0_data_white', c_double_p), ('ncols_white', ctypes.c_int32)]
+                ('transform_data', c_double_p), ('whitening_t', c_double_p), ('r0_data_white', c_double_p), ('ncols_white', ctypes.c_int32),
+                ('entry_kind', c_int32_p), ('entry_i', c_int32_p), ('entry_j', c_int32_p), ('skip_const_gram', ctypes.c_int32)]
 
 
 class PlanDesc(ctypes.Structure):
@@ -47,7 +48,8 @@ class PlanDesc(ctypes.Structure):
                 ('nblocks', ctypes.c_int32), ('blocks', ctypes.POINTER(BlockDesc)),
                 ('ns', ctypes.c_int32), ('nmarg', ctypes.c_int32), ('x0', c_double_p), ('xprior_kind', c_int32_p),
                 ('xprior_loc', c_double_p), ('xprior_scale', c_double_p), ('xprior_lo', c_double_p), ('xprior_hi', c_double_p),
-                ('nderived', ctypes.c_int32), ('derived_off', c_int32_p), ('derived_code', c_int32_p), ('derived_const', c_double_p)]
+                ('nderived', ctypes.c_int32), ('derived_off', c_int32_p), ('derived_code', c_int32_p), ('derived_const', c_double_p),
+                ('m0_extra', c_double_p)]
 
 
 # every symbol include/desilike_b200.h declares: (restype, argtypes)

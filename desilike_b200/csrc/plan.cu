@@ -339,8 +339,15 @@ static int build_block(dlb_plan* plan, const dlb_plan_desc* desc, const dlb_bloc
   const int nS = R * (R + 1) / 2;
   for (int i = 0; i < bd.nconst; ++i)
     for (int a = 0; a < R; ++a) map[nS + i * R + a] = a == 0 ? EntryMap{1, bd.const_solved[i], 0} : EntryMap{2, solved_of_slot(a), bd.const_solved[i]};
+  if (bd.entry_kind) {   // explicit meaning of every partial (split dense plans)
+    DLB_REQUIRE(bd.entry_i && bd.entry_j, "block: entry_kind needs entry_i / entry_j");
+    for (int e = 0; e < blk.npart; ++e) {
+      DLB_REQUIRE(bd.entry_kind[e] >= 0 && bd.entry_kind[e] <= 3, "block: entry kind must be 0 .. 3");
+      map[e] = EntryMap{bd.entry_kind[e], bd.entry_kind[e] == 0 || bd.entry_kind[e] == 3 ? 0 : bd.entry_i[e], bd.entry_kind[e] == 2 ? bd.entry_j[e] : 0};
+    }
+  }
   for (const EntryMap& m : map)
-    DLB_REQUIRE(m.kind == 0 || (m.i >= 0 && m.i < desc->ns && (m.kind == 1 || (m.j >= 0 && m.j < desc->ns))), "solved-parameter index out of range");
+    DLB_REQUIRE(m.kind == 0 || m.kind == 3 || (m.i >= 0 && m.i < desc->ns && (m.kind == 1 || (m.j >= 0 && m.j < desc->ns))), "solved-parameter index out of range");
   DLB_TRY(upload(plan, map.data(), map.size(), &blk.d_map));
   blk.h_map = map;
   return DLB_OK;
@@ -924,13 +931,15 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
     }
     for (int ib = 0; ib < desc->nblocks; ++ib) {
       const dlb_block_desc& bd = desc->blocks[ib];
-      for (int i = 0; i < bd.nconst; ++i)
+      for (int i = 0; i < bd.nconst && !bd.skip_const_gram; ++i)
         for (int j = 0; j < bd.nconst; ++j) {
           double s = 0.;
           for (int c = 0; c < bd.ncols; ++c) s += bd.gconst_white[(size_t)i * bd.ncols + c] * bd.gconst_white[(size_t)j * bd.ncols + c];
           M0[(size_t)bd.const_solved[i] * ns + bd.const_solved[j]] += s;
         }
     }
+    if (desc->m0_extra)
+      for (size_t i = 0; i < M0.size(); ++i) M0[i] += desc->m0_extra[i];
     DLB_TRY(upload(plan, M0.data(), M0.size(), &plan->d_M0));
     DLB_TRY(upload(plan, g0.data(), g0.size(), &plan->d_g0));
     DLB_TRY(upload(plan, desc->x0, (size_t)ns, &plan->d_x0));
@@ -948,9 +957,18 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
       const dlb_block_desc& bd = desc->blocks[ib];
       int first = -1;
       auto join = [&](int i) { if (first < 0) first = i; else parent[find(i)] = find(first); };
+      if (bd.entry_kind) {   // explicit maps: parameters coupled by a Hessian entry (or by the plan-constant extra Gram) share a group
+        for (int e = 0; e < plan->blocks[ib].npart; ++e)
+          if (bd.entry_kind[e] == 2) { join(bd.entry_i[e]); join(bd.entry_j[e]); first = -1; }
+        continue;
+      }
       for (int a = 0; a < bd.nslots - 1; ++a) join(bd.slot_solved[a]);
       for (int a = 0; a < bd.nconst; ++a) join(bd.const_solved[a]);
     }
+    if (desc->m0_extra)
+      for (int i = 0; i < ns; ++i)
+        for (int j = 0; j < i; ++j)
+          if (desc->m0_extra[(size_t)i * ns + j] != 0.) parent[find(i)] = find(j);
     std::vector<int> comp_off{0}, comp_idx, comp_nmarg;
     int maxsize = 0;
     for (int r = 0; r < ns; ++r) {
@@ -1002,6 +1020,7 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
             const EntryMap& m = blk.h_map[e];
             const long long prow = blk.poff + e;
             if (m.kind == 0) { chi_rows.push_back(prow); continue; }
+            if (m.kind == 3) continue;
             const int c = group_of[m.i];
             if (m.kind == 1) per[c].push_back(GroupEntry{prow, 1, local_of[m.i], 0});
             else {

@@ -110,7 +110,7 @@ __device__ __forceinline__ void finish_solve_body(const SolveParams& p, double* 
       const EntryMap m = blk.map[e];
       if (m.kind == 0) chi2 += v;
       else if (m.kind == 1) gL[m.i] -= v;
-      else { M[m.i * ld + m.j] += v; if (m.i != m.j) M[m.j * ld + m.i] += v; }
+      else if (m.kind == 2) { M[m.i * ld + m.j] += v; if (m.i != m.j) M[m.j * ld + m.i] += v; }
     }
     __syncwarp();
   }

@@ -217,6 +217,8 @@ class Lowered(object):
         else:
             groups = [(list(observables), np.asarray(prec, dtype=np.float64))]
         self.blocks = []
+        self.split_dense = False   # some dense precision block was split over several passes (theory vectors then come from a companion plan)
+        self.m0_extra = None
         self.two_stage = False   # any transformed observable: theory -> transform -> whitening as two contraction launches
         for group, P in groups:
             ncols = sum(len(o['data']) for o in group)
@@ -290,7 +292,12 @@ class Lowered(object):
             for si in const_rows:
                 if si in slot_of: raise LoweringError('solved parameter {} mixes constant and theta-dependent templates'.format(self.solved_names[si]))
             nslots = 1 + len(slot_of)
-            if nslots > 8: raise LoweringError('more than 7 theta-dependent solved templates per block are not supported')
+            if nslots > 8:
+                # dense joint precision coupling more theta-dependent solved templates than one pass holds (8 accumulator slots): split
+                if self.two_stage: raise LoweringError('observable transform together with a split dense precision is not supported')
+                self.blocks += self._lower_dense_split(group, P, terms, slot_of, const_rows, const_plain, data)
+                self.split_dense = True
+                continue
             blk = dict(ncols=ncols, nslots=nslots)
             keys = sorted(terms.keys())
             blk['terms'] = keys
@@ -321,9 +328,104 @@ class Lowered(object):
             blk['const_solved'] = i32(sorted(const_rows.keys()))
             blk['gconst_white'] = f64([L @ const_rows[si] for si in sorted(const_rows.keys())]).reshape(len(const_rows), ncols)
             self.blocks.append(blk)
-        self.ntheory = sum(b['ncols'] for b in self.blocks)
+        self.ntheory = sum(len(o['data']) for o in observables)
         self.with_plain = with_plain
         self._build_desc()
+
+    def _lower_dense_split(self, group, P, terms, slot_of, const_rows, const_plain, data):
+        """
+        Dense joint precision P over several observables whose theta-dependent solved templates (counter-term rows ~ pk11(theta)) number more than
+        the 7 one contraction pass can hold next to the residual (SURVEY.md section 8d, C4 'dense 2000 x 2000' stress variant: 5 tracers x 3 rows).
+
+        The Jacobian rows are observable-local BEFORE whitening, so instead of whitened rows J~ = L J the plan carries, per observable o,
+            S-slots   S_r = (t - d)[cols_o],  S_i = J_i[cols_o]  for the rows i of o            (un-whitened, local)
+            y-slots   y_j[cols_o] = (P S_j)[cols_o]  for j in {r} + all rows                     (precision-weighted, dense in j's observable)
+        and every quantity of the normal equations (reference likelihoods/base.py:165-187) is a sum over observables of S . y products:
+            chi2 = sum_o S_r . y_r,   gradient_i = -S_i . y_r (o = observable of i),   M_ij = S_i . y_j (once per unordered pair),
+        constant rows g_c (stochastic terms) enter through the auxiliary columns w_c = (P g_c)[cols_o] of the S-slots and a plan-constant Gram
+        g_c . P g_c' (dlb_plan_desc::m0_extra).  The y-slots are spread over passes of (8 - number of S-slots) each: one block per (observable, pass),
+        its Gram partials tagged explicitly (dlb_block_desc::entry_kind).
+        """
+        from collections import OrderedDict
+        sizes = [len(o['data']) for o in group]
+        starts = np.concatenate([[0], np.cumsum(sizes)]).astype(int)
+        ncols = int(starts[-1])
+        P = np.diag(P) if P.ndim == 1 else np.asarray(P, dtype=np.float64)
+        theta_slots = sorted(slot_of.items(), key=lambda kv: kv[1])        # [(solved index, slot)]
+        # observable of every theta-dependent row: its plain matrices must vanish outside one observable's columns
+        obs_of = {}
+        for key, mat in terms.items():
+            slot = key[0]
+            if slot == 0: continue
+            touched = [io for io in range(len(group)) if np.any(mat[:, starts[io]:starts[io + 1]] != 0.)]
+            if len(touched) > 1: raise LoweringError('split dense precision: a theta-dependent solved template spans several observables')
+            if touched:
+                if obs_of.setdefault(slot, touched[0]) != touched[0]: raise LoweringError('split dense precision: a solved template spans several observables')
+        slot_solved = {slot: si for si, slot in theta_slots}
+        yslots = [0] + [slot for _, slot in theta_slots]                    # global slot ids with a precision-weighted copy
+        const_list = sorted(const_rows.keys())
+        W = {si: P @ const_rows[si] for si in const_list}                   # w_c = P g_c
+        m0 = np.zeros((self.ns, self.ns))
+        for a in const_list:
+            for b in const_list: m0[a, b] += const_rows[a].dot(W[b])
+        self.m0_extra = m0 if self.m0_extra is None else self.m0_extra + m0
+        r0_full = data - const_plain
+        Pr0 = P @ r0_full
+        blocks = []
+        for io, obs in enumerate(group):
+            c0, c1 = int(starts[io]), int(starts[io + 1])
+            n_o = c1 - c0
+            local = [0] + [slot for slot in sorted(obs_of) if obs_of[slot] == io]      # S-slots of this observable (global slot ids)
+            if len(local) > 6: raise LoweringError('split dense precision: more than 5 theta-dependent solved templates in one observable')
+            per_pass = 8 - len(local)
+            npass = (len(yslots) + per_pass - 1) // per_pass
+            gen_o = None
+            for key in terms:
+                if np.any(terms[key][:, c0:c1] != 0.): gen_o = key[2]; break
+            cchunks = [const_list[q::npass] for q in range(npass)]              # constant rows spread over the passes (aux columns of the S-slots)
+            for q in range(npass):
+                ys = yslots[q * per_pass:(q + 1) * per_pass]
+                nsl = len(local) + len(ys)
+                bterms = OrderedDict()
+                for key, mat in terms.items():
+                    slot, coef, gi, foff, K = key
+                    if slot in local:
+                        sub = mat[:, c0:c1]
+                        if np.any(sub != 0.): bterms[(local.index(slot), coef, gi, foff, K)] = bterms.get((local.index(slot), coef, gi, foff, K), 0.) + sub
+                    if slot in ys:
+                        sub = mat @ P[:, c0:c1]
+                        k2 = (len(local) + ys.index(slot), coef, gi, foff, K)
+                        bterms[k2] = bterms.get(k2, 0.) + sub
+                if 0 in ys:   # y_r = P (t - d): the constant part -P (d - const) rides on the constant-one feature of the segment
+                    k2 = (len(local) + ys.index(0), -1, gen_o, 0, 1)
+                    bterms[k2] = bterms.get(k2, 0.) - Pr0[None, c0:c1]
+                keys = sorted(bterms.keys())
+                cs = cchunks[q]
+                npart = nsl * (nsl + 1) // 2 + nsl * len(cs)
+                kind, ei, ej = np.full(npart, 3, dtype=np.int32), np.zeros(npart, dtype=np.int32), np.zeros(npart, dtype=np.int32)
+
+                def pair(a, b): return a * nsl - (a * (a - 1)) // 2 + (b - a)
+                for ia, sa in enumerate(local):
+                    for jb, sb in enumerate(ys):
+                        e = pair(ia, len(local) + jb)
+                        if sa == 0 and sb == 0: kind[e] = 0
+                        elif sa != 0 and sb == 0: kind[e], ei[e] = 1, slot_solved[sa]            # gradient_i -= S_i . y_r
+                        elif sa != 0 and sb != 0:
+                            i, j = slot_solved[sa], slot_solved[sb]
+                            # every unordered pair once: take it where i's observable precedes j's (or i <= j inside one observable)
+                            if (obs_of[sa], i) <= (obs_of[sb], j): kind[e], ei[e], ej[e] = 2, i, j
+                nS = nsl * (nsl + 1) // 2
+                for ic, si in enumerate(cs):
+                    for ia, sa in enumerate(local):
+                        e = nS + ic * nsl + ia
+                        if sa == 0: kind[e], ei[e] = 1, si                                        # gradient_c -= r . P g_c
+                        else: kind[e], ei[e], ej[e] = 2, slot_solved[sa], si                      # M[i, c] += S_i . P g_c
+                blk = dict(ncols=n_o, nslots=nsl, terms=keys, plain=[np.zeros((k[4], n_o)) for k in keys], white=[np.ascontiguousarray(bterms[k]) for k in keys],
+                           r0_white=r0_full[c0:c1].copy(), ncols_white=n_o, t0_plain=np.zeros(n_o), transform_data=np.zeros(n_o),
+                           whitening_t=np.zeros((1, 1)), r0_data_white=np.zeros(n_o), slot_solved=i32(np.zeros(nsl - 1)), const_solved=i32(cs),
+                           gconst_white=f64([W[si][c0:c1] for si in cs]).reshape(len(cs), n_o), entry_kind=kind, entry_i=ei, entry_j=ej, skip_const_gram=1)
+                blocks.append(blk)
+        return blocks
 
     def _const_index(self, value):
         if value not in self.derived_consts: self.derived_consts.append(value)
@@ -364,7 +466,7 @@ class Lowered(object):
                 moff += mat.size
                 moff_plain += mat_plain.size
             white = f64(np.concatenate([m.ravel() for m in blk['white']]))
-            plain = f64(np.concatenate([m.ravel() for m in blk['plain']])) if (self.with_plain or self.two_stage) else None
+            plain = f64(np.concatenate([m.ravel() for m in blk['plain']])) if ((self.with_plain or self.two_stage) and not self.split_dense) else None
             r0, t0 = f64(blk['r0_white']), f64(blk['t0_plain'])
             ss, cs, gc = i32(blk['slot_solved']), i32(blk['const_solved']), f64(blk['gconst_white'])
             keep += [terms, white, plain, r0, t0, ss, cs, gc]
@@ -377,12 +479,21 @@ class Lowered(object):
             b.matrices_white, b.matrices_plain = as_ptr(white), as_ptr(plain)
             b.r0_white, b.t0_plain = as_ptr(r0), as_ptr(t0)
             b.slot_solved, b.nconst, b.const_solved, b.gconst_white = as_ptr(ss, ctypes.c_int32), len(cs), as_ptr(cs, ctypes.c_int32), as_ptr(gc)
+            if blk.get('entry_kind') is not None:
+                ek, ei, ej = i32(blk['entry_kind']), i32(blk['entry_i']), i32(blk['entry_j'])
+                keep += [ek, ei, ej]
+                b.entry_kind, b.entry_i, b.entry_j = as_ptr(ek, ctypes.c_int32), as_ptr(ei, ctypes.c_int32), as_ptr(ej, ctypes.c_int32)
+                b.skip_const_gram = int(blk.get('skip_const_gram', 0))
         desc.nblocks, desc.blocks = len(self.blocks), blocks
         skind, sloc, sscale, slo, shi = [np.ascontiguousarray(a) for a in self.xprior]
         keep += [gens, coefs, blocks, skind, sloc, sscale, slo, shi, self.x0]
         desc.ns, desc.nmarg = self.ns, self.nmarg
         desc.x0, desc.xprior_kind = as_ptr(self.x0), as_ptr(skind, ctypes.c_int32)
         desc.xprior_loc, desc.xprior_scale, desc.xprior_lo, desc.xprior_hi = as_ptr(sloc), as_ptr(sscale), as_ptr(slo), as_ptr(shi)
+        if self.m0_extra is not None:
+            m0 = f64(self.m0_extra)
+            keep.append(m0)
+            desc.m0_extra = as_ptr(m0)
         self.desc = desc
 
     def flops_per_point(self):

@@ -44,7 +44,19 @@ class Plan(object):
         self._unperm = np.argsort(self.lowered.solved_order) if self.ns else np.zeros(0, dtype=int)
         self._identity_perm = bool(np.array_equal(self._unperm, np.arange(self.ns)))   # all '.marg' (or all '.best'): plan order == spec order
 
+    def _theory_companion(self):
+        """Plans whose dense precision was split over several passes carry no un-whitened matrices: theory vectors do not depend on the precision,
+        so they come from a companion plan of the same spec with a unit diagonal precision per observable (built on first use)."""
+        if getattr(self, '_companion', None) is None:
+            spec = dict(self.spec, precision=[np.ones(len(o['data'])) for o in self.spec['observables']])
+            spec.pop('prec_groups', None)
+            self._companion = Plan(spec, with_theory=True)
+        return self._companion
+
     def close(self):
+        if getattr(self, '_companion', None) is not None:
+            self._companion.close()
+            self._companion = None
         if getattr(self, '_handle', None):
             self._lib.dlb_plan_destroy(self._handle)
             self._handle = None
@@ -132,6 +144,7 @@ class Plan(object):
 
     def theory(self, X):
         """Flat theory vectors [N, n] at the solved parameters' defaults (reference ``likelihood.flattheory``)."""
+        if self.lowered.split_dense: return self._theory_companion().theory(X)
         if _is_torch_cuda(X):
             import torch
             out = torch.empty((X.shape[0], self.ntheory), dtype=torch.float64, device=X.device)

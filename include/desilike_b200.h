@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DLB_ABI_VERSION 4
+#define DLB_ABI_VERSION 5
 
 typedef enum {
   DLB_OK = 0,
@@ -115,6 +115,13 @@ typedef struct {
    * |r|^2, and r = g . M - r0 lives in the row space of the stacked term matrices, so a QR factorisation at plan time replaces the n
    * data-space columns by sum_t K_t + 1 columns (desilike_b200/lowering.py); requires nslots == 1 and nconst == 0. */
   int32_t ncols_white;
+  /* Optional explicit meaning of the block's Gram partials (default NULL: slot 0 = residual, slots >= 1 / constant rows = Jacobian rows, every
+   * pair contributes).  Entry e of the nslots (nslots + 1) / 2 + nslots * nconst partials (pairs (a, b), a <= b, row-major; then, per constant row i,
+   * its dot product with every slot a) means: kind 0 chi2 += v; 1 gradient[i] -= v; 2 M[i][j] += v (and M[j][i] when i != j); 3 ignored.
+   * Used by plans that split a dense joint precision over several passes of <= 8 slots (desilike_b200/lowering.py: un-whitened slots S_i next to
+   * precision-weighted ones y_j = P S_j, chi2 / gradient / Hessian entries = S_i . y_j). */
+  const int32_t* entry_kind; const int32_t* entry_i; const int32_t* entry_j;
+  int32_t skip_const_gram;   /* != 0: the Gram of the constant rows of this block is NOT g_i . g_j (it is supplied through dlb_plan_desc::m0_extra) */
 } dlb_block_desc;
 
 typedef struct {
@@ -138,6 +145,7 @@ typedef struct {
    * pairs: 0 push column `argument` of the extended row (< d + i), 1 push derived_const[argument], 2 add, 3 sub, 4 mul, 5 div, 6 pow, 7 neg,
    * 8 exp, 9 log, 10 sqrt, 11 log10, 12 abs, 13 sin, 14 cos, 15 tanh (stack depth <= 16); evaluated by a small kernel in front of every pass. */
   int32_t nderived; const int32_t* derived_off; const int32_t* derived_code; const double* derived_const;
+  const double* m0_extra;   /* optional [ns, ns] (plan order) added to the constant part of the normal matrix (constant-row Gram of split dense plans) */
 } dlb_plan_desc;
 
 typedef struct dlb_plan dlb_plan;

@@ -248,15 +248,20 @@ def config_c5(seed=5, ntracers=5, order=4, nkin=350, nbins=134, coefficients='ra
         params += [q for q in p if q not in params]
     spec = dict(params=params, observables=observables, solved=solved_list)
     spec = _finish(spec, metas, rng, _FID)
-    if dense:
-        n = sum(len(o['data']) for o in observables)
-        import scipy.linalg
-        cov = scipy.linalg.block_diag(*[np.linalg.inv(p) for p in spec['precision']])
-        sig = np.sqrt(np.diag(cov))
-        A = rng.standard_normal((n, 8))
-        C = A.dot(A.T); C /= np.sqrt(np.outer(np.diag(C), np.diag(C)))
-        cov = cov + 0.02 * C * np.outer(sig, sig)
-        spec['precision'] = np.linalg.inv(cov)
+    if dense: _densify(spec, rng)
+    return spec
+
+
+def _densify(spec, rng):
+    """Joint covariance coupling the tracers (SURVEY.md section 8d C4 'dense 2000 x 2000' stress variant): block-diagonal + 2 % rank-8 coupling."""
+    n = sum(len(o['data']) for o in spec['observables'])
+    import scipy.linalg
+    cov = scipy.linalg.block_diag(*[np.linalg.inv(p) for p in spec['precision']])
+    sig = np.sqrt(np.diag(cov))
+    A = rng.standard_normal((n, 8))
+    C = A.dot(A.T); C /= np.sqrt(np.outer(np.diag(C), np.diag(C)))
+    cov = cov + 0.02 * C * np.outer(sig, sig)
+    spec['precision'] = np.linalg.inv(cov)
     return spec
 
 
@@ -270,7 +275,7 @@ def mlp_engine(rng, nin_tables, hidden=(64, 64, 64), ndim=4, activation='silu', 
     return dict(xlimits=xlimits, layers=layers, activation=activation, ylimits=ylimits, pca=None)
 
 
-def config_c4(seed=4, ntracers=5, hidden=(64, 64, 64), nkin=350, nbins=134, solved=True):
+def config_c4(seed=4, ntracers=5, hidden=(64, 64, 64), nkin=350, nbins=134, solved=True, dense=False):
     """C4: ``ntracers`` x [MLP pt-emulator -> EFT-like Kaiser combine -> window] -> joint chi2 with analytic marginalisation."""
     rng = np.random.default_rng(seed)
     ells = (0, 2, 4)
@@ -291,7 +296,9 @@ def config_c4(seed=4, ntracers=5, hidden=(64, 64, 64), nkin=350, nbins=134, solv
         observables.append(obs); metas.append(meta); solved_list += s
         params += [q for q in p if q not in params]
     spec = dict(params=params, observables=observables, solved=solved_list)
-    return _finish(spec, metas, rng, _FID)
+    spec = _finish(spec, metas, rng, _FID)
+    if dense: _densify(spec, rng)
+    return spec
 
 
 def config_c3(seed=3, ns_theory=33, broadband_solved=True):

@@ -62,6 +62,7 @@ def evaluate(low, X, feature_fn=None, white=True):
     skind, sloc, sscale, slo, shi = low.xprior
     xprec = np.where(skind == 2, 1. / sscale**2, 0.)
     M = np.zeros((N, ns, ns)) + np.diag(xprec)
+    if getattr(low, 'm0_extra', None) is not None: M = M + low.m0_extra
     gL = np.zeros((N, ns))
     chi2 = np.zeros(N)
     theory = []
@@ -86,6 +87,22 @@ def evaluate(low, X, feature_fn=None, white=True):
             r = t @ blk['whitening_t'] - blk['r0_data_white']
         else:
             r = slots[0] - blk['r0_white']
+        if blk.get('entry_kind') is not None:
+            # explicit meaning of the Gram partials (split dense plans, csrc/plan.cu: build_block): pairs (a <= b) then constant rows x slots
+            R, vals = blk['nslots'], []
+            sl = [r] + [slots[a] for a in range(1, R)]
+            for a in range(R):
+                for b in range(a, R): vals.append(np.sum(sl[a] * sl[b], axis=-1))
+            for i in range(len(blk['const_solved'])):
+                for a in range(R): vals.append(sl[a] @ blk['gconst_white'][i])
+            for e, v in enumerate(vals):
+                kind, i, j = int(blk['entry_kind'][e]), int(blk['entry_i'][e]), int(blk['entry_j'][e])
+                if kind == 0: chi2 += v
+                elif kind == 1: gL[:, i] -= v
+                elif kind == 2:
+                    M[:, i, j] += v
+                    if i != j: M[:, j, i] += v
+            continue
         chi2 += np.sum(r**2, axis=-1)
         rows = [(int(si), slots[1 + a]) for a, si in enumerate(blk['slot_solved'])]
         rows += [(int(si), np.broadcast_to(blk['gconst_white'][i], (N, blk['ncols']))) for i, si in enumerate(blk['const_solved'])]

@@ -298,3 +298,19 @@ def test_derived_expression_parameters_lowering():
     with pytest.raises(LoweringError):
         Lowered(dict(spec, derived=[dict(name='T0.b1', expr='__import__("os").getcwd()'), spec['derived'][1]]))
     assert expressions.depends('{a} + {b} * {a}') == ['a', 'b']
+
+
+@pytest.mark.parametrize('ntracers', [3, 5])
+def test_split_dense_precision_lowering(ntracers):
+    """Dense joint precision with more theta-dependent solved templates than one pass holds (SURVEY.md section 8d C4 'dense' stress variant:
+    5 tracers x 3 counter-term rows): the split plan (un-whitened S-slots x precision-weighted y-slots, explicit entry maps, constant-row Gram as
+    a plan constant) reproduces the oracle through the NumPy mirror of the kernels."""
+    from desilike_b200.lowering import Lowered
+    spec = configs.config_c5(ntracers=ntracers, nkin=20, nbins=6, order=2, solved=True, dense=True)
+    low = Lowered(spec)
+    assert low.split_dense and all(b['nslots'] <= 8 for b in low.blocks) and low.ntheory == ntracers * 18
+    X = configs.sample_points(spec, 6, seed=3)
+    ref = pipeline.evaluate(spec, X)
+    got = lowered_numpy.evaluate(low, X)
+    assert np.allclose(got['loglikelihood'], ref['loglikelihood'], rtol=1e-11, atol=1e-9)
+    assert np.allclose(got['x_solved'], ref['x_solved'], rtol=1e-8, atol=1e-8)

@@ -300,3 +300,19 @@ def test_per_point_failures_status_bits(gpu_required):
     got = plan.eval(X)
     assert np.all(got['status'] & _capi.PT_NOT_SPD) and np.all(np.isnan(got['logposterior'])) and np.all(np.isnan(got['x_solved']))
     plan.close()
+
+
+def test_dense_precision_many_solved_templates_split(gpu_required):
+    """SURVEY.md section 8d C4 / C5 'dense' stress variants: 5 tracers, joint dense precision, 15 theta-dependent + 20 constant marginalised
+    templates in ONE likelihood block (16 accumulator slots > the 8 of one pass): the split plan == the oracle, Taylor and MLP theories."""
+    check(configs.config_c5(ntracers=5, nkin=40, nbins=10, order=2, solved=True, dense=True), 150, seed=31, solved=True)
+    check(configs.config_c4(ntracers=5, nkin=40, nbins=10, hidden=(16, 16), dense=True), 130, seed=32, solved=True)
+    import desilike_b200
+    spec = configs.config_c5(ntracers=4, nkin=40, nbins=10, order=2, solved=True, dense=True)
+    for s in spec['solved'][::2]: s['marg'] = False     # mixed '.marg' / '.best'
+    plan = desilike_b200.Plan(spec)
+    X = configs.sample_points(spec, 64, seed=33)
+    got, ref = plan.eval(X, return_hessian=True), pipeline.evaluate(spec, X, return_hessian=True)
+    assert np.all(np.abs(got['logposterior'] - ref['logposterior']) <= 1e-8 * np.maximum(1., np.abs(ref['logposterior'])))
+    assert np.allclose(got['hessian'], ref['hessian'], rtol=1e-8, atol=1e-10 * np.max(np.abs(ref['hessian'])))
+    plan.close()
