@@ -97,27 +97,59 @@ class Emulator(object):
                                       'derivatives': deriv, 'powers': np.asarray(powers, dtype='i4')}
         return cls(state)
 
+    @staticmethod
+    def _theory_tables(theory, names):
+        """-> (evaluate(X) -> {table: [n, ny]}, {table: yshape}, fixed, calculator_class): the emulated tables of a direct theory, evaluated ON THE GPU
+        through its feature generator (``dlb_features_batch``).  Kaiser tracer theories: the perturbation-theory tables pk_dd / pk_dt / pk_tt
+        (what the reference emulates as ``theory.pt``); damped-BAO tracer theories: the multipoles without broadband, 'power' [nell, nk] or
+        'corr' [nell, ns] (the P -> xi FFTLog operator applied at plan time or by the FFTLog kernel)."""
+        from .plan import Plan
+        tspec = dict(theory.theory_spec(), params=list(names))
+        kind = tspec['kind']
+        if kind == 'kaiser':
+            tables, x, cls_ = ['pk_dd', 'pk_dt', 'pk_tt'], np.asarray(theory.k, dtype='f8'), ('desilike.theories.galaxy_clustering.full_shape', 'KaiserPowerSpectrumMultipoles')
+        elif kind == 'bao_pk':
+            tables, x, cls_ = ['power'], np.asarray(theory.k, dtype='f8'), ('desilike.theories.galaxy_clustering.bao', 'DampedBAOWigglesTracerPowerSpectrumMultipoles')
+        elif kind == 'bao_xi':
+            tables, x, cls_ = ['corr'], np.asarray(theory.s, dtype='f8'), ('desilike.theories.galaxy_clustering.bao', 'DampedBAOWigglesTracerCorrelationFunctionMultipoles')
+        else:
+            raise ValueError('emulator construction expects a direct Kaiser or damped-BAO tracer theory (got kind {!r})'.format(kind))
+        nin = len(x) * len(theory.ells)
+        obs = dict(name='fit', theory=tspec, terms=[dict(scale=1., factors=[], table=tables[0])], nin=nin, wmatrix=None, offset=None, data=np.zeros(nin))
+        plan = Plan(dict(params=list(names), priors={}, solved=[], observables=[obs], precision=[np.ones(nin)]), with_theory=False, merge_terms=False)
+        gen = plan.lowered.gens[0]
+
+        def evaluate(X):
+            feats = plan.features(0, np.ascontiguousarray(X, dtype='f8'))
+            out = {}
+            for name in tables:
+                foff, K, D = gen.tables[name]
+                out[name] = feats[:, foff:foff + K] if D is None else feats[:, foff:foff + K] @ D
+            return out
+
+        evaluate.close = plan.close
+        fixed = {('s' if kind == 'bao_xi' else 'k'): x, 'ells': tuple(theory.ells), 'z': getattr(theory.template, 'z', 1.)}
+        return evaluate, {name: (len(theory.ells), len(x)) for name in tables}, fixed, cls_
+
     @classmethod
     def fit_taylor(cls, theory, order=4, delta=None, params=None, nbatch=None):
         """
-        Build a Taylor emulator of the perturbation-theory tables of a direct tracer theory (e.g. ``KaiserTracerPowerSpectrumMultipoles``),
-        the ``.fit`` half of the reference's emulator API (``Emulator(calculator, engine=TaylorEmulatorEngine(order=4)).set_samples().fit()``,
-        reference emulators/__init__.py:438-507; docs/user/getting_started.rst:281-288).
+        Build a Taylor emulator of a direct tracer theory's tables -- Kaiser: the perturbation-theory tables (``KaiserTracerPowerSpectrumMultipoles``);
+        damped BAO: the P_ell(k) / xi_ell(s) multipoles without broadband -- the ``.fit`` half of the reference's emulator API
+        (``Emulator(calculator, engine=TaylorEmulatorEngine(order=4)).set_samples().fit()``, reference emulators/__init__.py:438-507;
+        docs/user/getting_started.rst:281-288).
 
         The reference differentiates the calculator with ``Differentiation`` (jax autodiff or finite differences, differentiation.py:469-551)
         and stores ``derivatives[t] = d^alpha y / alpha!`` for the term list ``powers`` (emulators/__init__.py:471-507).  Here the theory
-        tables are evaluated ON THE GPU (the Kaiser kernel, through ``dlb_features_batch``) on the tensor-product stencil of
+        tables are evaluated ON THE GPU (the theory kernels, through ``dlb_features_batch``) on the tensor-product stencil of
         ``order + 1`` (odd) nodes per parameter around the parameters' default values, and the Taylor coefficients follow from the
         exact polynomial interpolation of the stencil (central finite differences, exact for polynomials of degree <= order).
 
         ``delta``: stencil spacing per parameter (default: ``Parameter.delta`` or 0.02); ``params``: subset of the theory's varied
-        perturbation-theory parameters (default: all of them).
+        parameters entering the tables (default: all of them).
         """
         import itertools
-        from .plan import Plan
         tspec = theory.theory_spec()
-        if tspec['kind'] != 'kaiser':
-            raise ValueError('fit_taylor expects a direct Kaiser tracer theory (got kind {!r})'.format(tspec['kind']))
         names = list(params) if params is not None else [n for n in tspec['params'] if not theory.all_params[n].fixed]
         ndim = len(names)
         center = np.array([float(theory.all_params[n].value) for n in names])
@@ -135,25 +167,71 @@ class Emulator(object):
         nodes = np.arange(npts, dtype='f8') - npts // 2
         grids = np.meshgrid(*[nodes] * ndim, indexing='ij')
         X = np.stack([g.ravel() for g in grids], axis=-1) * delta + center
-        # a minimal plan around the theory generator: the tables ARE its features
-        tspec = dict(tspec, params=names)
-        nin = len(theory.k) * len(theory.ells)
-        obs = dict(name='fit', theory=tspec, terms=[dict(scale=1., factors=[], table='pk_dd')], nin=nin, wmatrix=None, offset=None, data=np.zeros(nin))
-        plan = Plan(dict(params=names, priors={}, solved=[], observables=[obs], precision=[np.ones(nin)]), with_theory=False, merge_terms=False)
-        feats = plan.features(0, X)
-        gen = plan.lowered.gens[0]
+        evaluate, yshapes, fixed, calculator_class = cls._theory_tables(theory, names)
+        values = evaluate(X)
+        evaluate.close()
         tables = {}
-        for name in ['pk_dd', 'pk_dt', 'pk_tt']:
-            foff, K, _ = gen.tables[name]
-            Y = feats[:, foff:foff + K].reshape((npts,) * ndim + (K,))
-            Vinv = np.linalg.inv(np.vander(nodes, npts, increasing=True))
+        Vinv = np.linalg.inv(np.vander(nodes, npts, increasing=True))
+        for name, yshape in yshapes.items():
+            Y = values[name].reshape((npts,) * ndim + (-1,))
             for ax in range(ndim):
                 Y = np.moveaxis(np.tensordot(Vinv, np.moveaxis(Y, ax, 0), axes=(1, 0)), 0, ax)
-            tables[name] = np.array([Y[tuple(p)] / np.prod(delta**p) for p in powers]).reshape(len(powers), len(theory.ells), len(theory.k))
-        plan.close()
-        fixed = dict(k=np.asarray(theory.k, dtype='f8'), ells=tuple(theory.ells), z=getattr(theory.template, 'z', 1.))
+            tables[name] = np.array([Y[tuple(p)] / np.prod(delta**p) for p in powers]).reshape((len(powers),) + tuple(yshape))
         all_params = [theory.all_params[n] for n in tspec['params'] if n in theory.all_params.names()] if hasattr(theory.all_params, 'names') else None
-        return cls.from_taylor(names, center, powers, tables, fixed, all_params=all_params)
+        return cls.from_taylor(names, center, powers, tables, fixed, all_params=all_params, calculator_class=calculator_class)
+
+    @staticmethod
+    def qmc_points(lower, upper, niterations, engine='rqrs', seed=0.5, offset=0):
+        """Quasi-Monte-Carlo design of the reference's ``QMCSampler`` (desilike/samplers/qmc.py:13-36, :122-126): the R additive recurrence
+        ('rqrs', the default: point n = (seed + n phi^-(1 + j)) mod 1 per dimension j, phi the root of phi^(d+1) = phi + 1) or one of SciPy's
+        engines ('sobol', 'halton', 'lhs'), scaled to [lower, upper]."""
+        lower, upper = np.asarray(lower, dtype='f8'), np.asarray(upper, dtype='f8')
+        d = lower.size
+        if engine == 'rqrs':
+            phi = 1.0
+            check = phi**(d + 1) - phi - 1
+            while abs(check) > 1e-12:
+                phi -= (phi**(d + 1) - phi - 1) / ((d + 1) * phi**d - 1)
+                check = phi**(d + 1) - phi - 1
+            inv_phi = np.array([phi**(-(1 + j)) for j in range(d)])
+            u = (float(seed) + np.arange(offset + 1, offset + niterations + 1)[:, None] * inv_phi) % 1.
+        else:
+            from scipy.stats import qmc
+            eng = {'sobol': qmc.Sobol, 'halton': qmc.Halton, 'lhs': qmc.LatinHypercube}[engine](d=d, seed=None if seed == 0.5 else int(seed))
+            if offset: eng.fast_forward(offset)
+            u = eng.random(n=niterations)
+        return lower + u * (upper - lower)
+
+    @classmethod
+    def qmc_samples(cls, theory, niterations=int(1e5), engine='rqrs', params=None, seed=0.5, offset=0, nbatch=1 << 18):
+        """
+        Training samples of an MLP emulator (reference ``MLPEmulatorEngine.get_default_samples``, emulators/__init__.py:510-533: ``QMCSampler``
+        with the 'rqrs' engine, 1e5 points in the box value +- proposal of every varied parameter, samplers/qmc.py:112-126), the theory tables
+        evaluated ON THE GPU in batches through the theory kernels.  -> dict(params=[names], X [n, d], Y={table: [n, *yshape]}, lower, upper).
+        The network training itself is not part of this module.
+        """
+        tspec = theory.theory_spec()
+        names = list(params) if params is not None else [n for n in tspec['params'] if not theory.all_params[n].fixed]
+        lower, upper = [], []
+        for n in names:
+            p = theory.all_params[n]
+            prop = getattr(p, 'proposal', None)
+            if prop is None:   # reference Parameter.proposal: scale of the ref (else prior) distribution
+                for dist in (p.ref, p.prior):
+                    if dist is None: continue
+                    if dist.get('dist', 'uniform') == 'uniform' and dist.get('limits') is not None and np.all(np.isfinite(dist['limits'])):
+                        prop = 0.5 * (dist['limits'][1] - dist['limits'][0]); break
+                    if 'scale' in dist: prop = float(dist['scale']); break
+            if prop is None: raise ValueError('Provide parameter limits or proposal for {}'.format(n))
+            lower.append(p.value - prop); upper.append(p.value + prop)
+        X = cls.qmc_points(lower, upper, niterations, engine=engine, seed=seed, offset=offset)
+        evaluate, yshapes, fixed, _ = cls._theory_tables(theory, names)
+        Y = {name: np.empty((niterations,) + tuple(shape)) for name, shape in yshapes.items()}
+        for start in range(0, niterations, nbatch):
+            vals = evaluate(X[start:start + nbatch])
+            for name in Y: Y[name][start:start + nbatch] = vals[name].reshape((-1,) + tuple(yshapes[name]))
+        evaluate.close()
+        return dict(params=names, X=X, Y=Y, lower=np.array(lower), upper=np.array(upper), fixed=fixed)
 
     @classmethod
     def from_mlp(cls, params, mlp, tables, yshapes, fixed, defaults=None, all_params=None,
@@ -249,7 +327,8 @@ class EmulatedCalculator(BaseCalculator):
         self.emulator = emulator
         state = emulator.state
         self.fixed = state['fixed']
-        self.k, self.ells = np.asarray(self.fixed['k'], dtype='f8'), tuple(self.fixed['ells'])
+        self.k, self.ells = np.asarray(self.fixed['k'] if 'k' in self.fixed else self.fixed['s'], dtype='f8'), tuple(self.fixed['ells'])
+        self.s = self.k if 's' in self.fixed else None
         self.varied_params_names = list(state.get('varied_params', []))
         params = []
         for ps in state.get('all_params', {}).get('data', []):
@@ -301,6 +380,27 @@ class EmulatedCalculator(BaseCalculator):
                 tables['pk11_l0'] = np.tile(base, nell)
             return dict(kind='mlp', params=params, mlp=mlp, tables=tables, defaults=defaults)
         raise ValueError('emulator engine {!r} is not on the CUDA path'.format(kind))
+
+    def scalar_expression(self, name):
+        """A scalar output of the emulated calculator (e.g. ``sigma8``, ``fsigma8`` of a perturbation-theory calculator) as a derived-parameter
+        EXPRESSION of the emulator's parameters (desilike_b200/expressions.py): a constant when the state holds it as a fixed entry, the Taylor
+        polynomial sum_t D_t prod_j ({p_j} - c_j)^pow_tj for a scalar Taylor engine (layout of reference emulators/__init__.py:471-507)."""
+        state = self.emulator.state
+        if name in state['engines']:
+            e = state['engines'][name]
+            if e['name'] != 'taylor' or int(np.prod(e['yshape'])) != 1:
+                raise ValueError('scalar {!r}: only scalar Taylor engines can feed derived parameters on the CUDA path (got {!r}, yshape {})'.format(name, e['name'], e['yshape']))
+            center, powers, deriv = np.asarray(e['center'], dtype='f8'), np.asarray(e['powers'], dtype='i4'), np.asarray(e['derivatives'], dtype='f8').ravel()
+            out = []
+            for t in range(len(powers)):
+                if deriv[t] == 0.: continue
+                fac = ['({!r})'.format(float(deriv[t]))]
+                for j, p in enumerate(e['params']):
+                    if powers[t, j]: fac.append('({{{}}} - ({!r}))**{:d}'.format(p, float(center[j]), int(powers[t, j])))
+                out.append(' * '.join(fac))
+            return ' + '.join(out) if out else '0.'
+        if name in state['fixed']: return repr(float(state['fixed'][name]))
+        raise ValueError('the emulator provides no {!r} (neither an engine nor a fixed entry)'.format(name))
 
     def table_spec(self, name):
         """Taylor engine ``name`` as (theory spec without tables, derivatives [T, *yshape]) -- for tracer theories that post-process the

@@ -244,29 +244,84 @@ class LPTVelocileptorsTracerPowerSpectrumMultipoles(TableBiasTracerPowerSpectrum
     _monomials = [(), ('b1',), ('b1', 'b1'), ('b2',), ('b1', 'b2'), ('b2', 'b2'), ('bs',), ('b1', 'bs'), ('b2', 'bs'), ('bs', 'bs'), ('b3',), ('b1', 'b3'),
                   ('alpha0',), ('alpha2',), ('alpha4',), ('alpha6',), ('sn0',), ('sn2',), ('sn4',)]
 
-    def __init__(self, pt, k=None, ells=(0, 2, 4), shotnoise=1e4, tracer=None, prior_basis='standard'):
-        if prior_basis not in (None, 'standard'):
-            raise ValueError("only the standard bias basis is on the CUDA path (prior_basis='physical' divides by the emulated sigma8, reference full_shape.py:1299-1306)")
+    # reference full_shape.py:1075-1090 (get_physical_stochastic_settings)
+    _physical_settings = {'BGS': dict(fsat=0.15, sigv=150 * 10**(1 / 3) * (1 + 0.2)**0.5 / 70.), 'LRG': dict(fsat=0.15, sigv=150 * 10**(1 / 3) * (1 + 0.8)**0.5 / 70.),
+                          'ELG': dict(fsat=0.10, sigv=150 * 2.1**0.5 / 70.), 'QSO': dict(fsat=0.03, sigv=150 * 10**(0.7 / 3) * 2.4**0.5 / 70.), None: dict(fsat=0.1, sigv=5.)}
+
+    def __init__(self, pt, k=None, ells=(0, 2, 4), shotnoise=1e4, tracer=None, prior_basis='standard', tracer_type=None, fsat=None, sigv=None):
+        """``prior_basis='physical'`` (the reference's default, full_shape.py:1275, :1299-1307): the sampled parameters are b1p .. sn4p and
+            b1 = b1p / sigma8 - 1,  b2 = b2p / sigma8^2,  bs = bsp / sigma8^2,  b3 = b3p / sigma8^3,     f = fsigma8 / sigma8,
+            alpha0 = (1 + b1)^2 alpha0p,  alpha2 = f (1 + b1) (alpha0p + alpha2p),  alpha4 = f (f alpha2p + (1 + b1) alpha4p),  alpha6 = f^2 alpha4p,
+            sn_i = sn_ip snd (fsat if i > 0) sigv^i
+        with sigma8 / fsigma8 taken from the emulator (scalar Taylor engines, or fixed entries).  On the CUDA path b1 .. b3, sigma8 and f become
+        derived-expression parameters (evaluated per point by the derived-parameter kernel) and the alpha / sn slices expand into monomial terms
+        in (b1, f) that stay linear in alpha*p / sn*p: these can still be tagged ``derived='.marg'``."""
+        if prior_basis not in (None, 'standard', 'physical'): raise ValueError("prior_basis must be 'standard' or 'physical'")
         BaseTracerPowerSpectrumMultipoles.__init__(self, template=None, pt=pt, k=k, ells=ells, shotnoise=shotnoise, tracer=tracer)
+        self.is_physical_prior = prior_basis == 'physical'
+        self.nd = 1e-4                      # reference full_shape.py:1154: the shot-noise terms are normalised by 1e-4 whatever `shotnoise`
+        self.fsat = self.snd = self.sigv = 1.
         norm = lambda scale: dict(dist='norm', loc=0., scale=scale)
         P = lambda name, **kw: Parameter(name, namespace=self.tracer, **kw)
-        # reference full_shape.yaml:476-578
+        if not self.is_physical_prior:
+            # reference full_shape.yaml:476-578
+            self.params = ParameterCollection([
+                P('b1', value=1., prior=dict(limits=[-1., 10.]), ref=dict(limits=[0.4, 0.6])), P('b2', value=0., prior=norm(10.), ref=norm(0.5)),
+                P('bs', value=0., prior=norm(5.), ref=norm(0.5)), P('b3', value=0., fixed=True, prior=norm(5.), ref=norm(0.5)),
+                P('alpha0', value=0., prior=norm(30.), ref=norm(1.)), P('alpha2', value=0., prior=norm(50.), ref=norm(1.)), P('alpha4', value=0., prior=norm(50.), ref=norm(1.)),
+                P('alpha6', value=0., fixed=True, prior=norm(50.), ref=norm(1.)),
+                P('sn0', value=0., prior=norm(4.), ref=norm(0.1)), P('sn2', value=0., prior=norm(100.), ref=norm(0.1)), P('sn4', value=0., prior=norm(500.), ref=norm(0.1))])
+            return
+        settings = dict(self._physical_settings[str(tracer_type).upper() if tracer_type is not None else None])
+        self.fsat = settings['fsat'] if fsat is None else float(fsat)
+        self.sigv = settings['sigv'] if sigv is None else float(sigv)
+        self.snd = float(shotnoise) * self.nd
+        ns = self._ns
+        s8 = '(' + pt.scalar_expression('sigma8') + ')'
+        fs8 = '(' + pt.scalar_expression('fsigma8') + ')'
+        ref1 = dict(dist='norm', loc=0., scale=1.)
+        # reference full_shape.py:1114-1131 (priors of the physical basis) + the derived standard-basis parameters
         self.params = ParameterCollection([
-            P('b1', value=1., prior=dict(limits=[-1., 10.]), ref=dict(limits=[0.4, 0.6])), P('b2', value=0., prior=norm(10.), ref=norm(0.5)),
-            P('bs', value=0., prior=norm(5.), ref=norm(0.5)), P('b3', value=0., fixed=True, prior=norm(5.), ref=norm(0.5)),
-            P('alpha0', value=0., prior=norm(30.), ref=norm(1.)), P('alpha2', value=0., prior=norm(50.), ref=norm(1.)), P('alpha4', value=0., prior=norm(50.), ref=norm(1.)),
-            P('alpha6', value=0., fixed=True, prior=norm(50.), ref=norm(1.)),
-            P('sn0', value=0., prior=norm(4.), ref=norm(0.1)), P('sn2', value=0., prior=norm(100.), ref=norm(0.1)), P('sn4', value=0., prior=norm(500.), ref=norm(0.1))])
+            P('b1p', value=1., prior=dict(dist='uniform', limits=[0., 3.]), ref=dict(dist='norm', loc=1., scale=0.1)),
+            P('b2p', value=0., prior=norm(5.), ref=ref1), P('bsp', value=0., prior=norm(5.), ref=ref1), P('b3p', value=0., fixed=True, prior=norm(5.), ref=ref1),
+            P('alpha0p', value=0., prior=norm(12.5), ref=ref1), P('alpha2p', value=0., prior=norm(12.5), ref=ref1), P('alpha4p', value=0., prior=norm(12.5), ref=ref1),
+            P('sn0p', value=0., prior=norm(2.), ref=ref1), P('sn2p', value=0., prior=norm(5.), ref=ref1), P('sn4p', value=0., prior=norm(5.), ref=ref1),
+            P('sigma8', derived=s8), P('f', derived=fs8 + ' / {' + ns('sigma8') + '}'),
+            P('b1', derived='{' + ns('b1p') + '} / {' + ns('sigma8') + '} - 1.'), P('b2', derived='{' + ns('b2p') + '} / {' + ns('sigma8') + '}**2'),
+            P('bs', derived='{' + ns('bsp') + '} / {' + ns('sigma8') + '}**2'), P('b3', derived='{' + ns('b3p') + '} / {' + ns('sigma8') + '}**3')])
 
     def _monomial(self, i):
         mono = self._monomials[i]
         return (1. / self.nd if mono and mono[0].startswith('sn') else 1.), mono
 
+    def terms(self):
+        if not self.is_physical_prior: return super().terms()
+        ns, tab = self._ns, lambda i: '{}_{:d}'.format(self.table_name, i)
+        terms = []
+        for i in range(12):   # deterministic bias monomials in the derived (b1, b2, bs, b3)
+            scale, names = self._monomial(i)
+            factors = {}
+            for name in names: factors[ns(name)] = factors.get(ns(name), 0) + 1
+            terms.append(dict(scale=scale, factors=list(factors.items()), table=tab(i)))
+        b1, f = ns('b1'), ns('f')
+        T = lambda i, scale, *factors: terms.append(dict(scale=scale, factors=[(n, p) for n, p in factors], table=tab(i)))
+        a0, a2, a4 = ns('alpha0p'), ns('alpha2p'), ns('alpha4p')
+        T(12, 1., (a0, 1)); T(12, 2., (b1, 1), (a0, 1)); T(12, 1., (b1, 2), (a0, 1))                       # alpha0 = (1 + b1)^2 alpha0p
+        for a in (a0, a2): T(13, 1., (f, 1), (a, 1)); T(13, 1., (f, 1), (b1, 1), (a, 1))                   # alpha2 = f (1 + b1) (alpha0p + alpha2p)
+        T(14, 1., (f, 2), (a2, 1)); T(14, 1., (f, 1), (a4, 1)); T(14, 1., (f, 1), (b1, 1), (a4, 1))      # alpha4 = f (f alpha2p + (1 + b1) alpha4p)
+        T(15, 1., (f, 2), (a4, 1))                                                                         # alpha6 = f^2 alpha4p
+        for j, i in enumerate([0, 2, 4]):                                                                  # sn_i / nd = sn_ip snd (fsat) sigv^i / nd
+            T(16 + j, self.snd * (self.fsat if i > 0 else 1.) * self.sigv**i / self.nd, (ns('sn{:d}p'.format(i)), 1))
+        return terms
+
 
 # ---------------------------------------------------------------------------------------------------------------------
 class _BaseBAOTracer(BaseCalculator):
 
-    def __init__(self, template, ells=(0, 2), mu=10, mode='', smoothing_radius=15., tracer=None):
+    def __init__(self, template=None, ells=(0, 2), mu=10, mode='', smoothing_radius=15., tracer=None, pt=None):
+        # pt: an ``EmulatedCalculator`` of this theory's multipoles without broadband ('power' / 'corr' engine, e.g. from ``Emulator.fit_taylor``)
+        self.pt = pt
+        if pt is None and template is None: raise ValueError('provide a template (direct theory) or pt (emulated multipoles)')
         self.template, self.ells, self.mu, self.mode, self.smoothing_radius, self.tracer = template, tuple(ells), int(mu), str(mode), float(smoothing_radius), tracer
         if self.mode not in ('', 'recsym', 'reciso'): raise ValueError('Reconstruction mode {} must be one of ["", "recsym", "reciso"]'.format(mode))
         self.params = ParameterCollection([
@@ -278,7 +333,17 @@ class _BaseBAOTracer(BaseCalculator):
 
     @property
     def all_params(self):
+        if self.pt is not None:   # the emulator carries the template / damping parameters; this class adds the broadband ones
+            own = ParameterCollection([p for p in self.params if p.basename.startswith('al')])
+            return self.pt.params + own
         return self.template.params + self.params
+
+    def _emulated_spec(self, table, x):
+        spec = self.pt.theory_spec()
+        if table not in spec['tables']: raise ValueError('the emulator has no {!r} engine (engines: {})'.format(table, sorted(spec['tables'])))
+        if len(self.pt.k) != len(x) or not np.allclose(self.pt.k, x) or tuple(self.pt.ells) != tuple(self.ells):
+            raise ValueError('the emulator was built on a different grid / multipoles than requested')
+        return spec
 
     def _theory_common(self):
         k_t = np.geomspace(1e-4, 1., 2000) if self.template.k is None else self.template.k   # reference bao.py:67,79
@@ -304,11 +369,12 @@ class DampedBAOWigglesTracerPowerSpectrumMultipoles(_BaseBAOTracer):
     al{ell}_{pow} (k / kp)^pow, pow in [-3, 1] (reference bao.py:467-476, :527-534)."""
     is_correlation = False
 
-    def __init__(self, template, k=None, kp=None, **kwargs):
+    def __init__(self, template=None, k=None, kp=None, **kwargs):
         super().__init__(template, **kwargs)
         self.k = np.linspace(0.01, 0.2, 101) if k is None else np.asarray(k, dtype='f8')
+        if self.pt is not None and k is None: self.k = np.asarray(self.pt.k, dtype='f8')
         if kp is None:
-            if template.rs_drag_fid is None: raise ValueError('provide kp or the template rs_drag (kp defaults to 2 pi / rs_drag, reference bao.py:493)')
+            if template is None or template.rs_drag_fid is None: raise ValueError('provide kp or the template rs_drag (kp defaults to 2 pi / rs_drag, reference bao.py:493)')
             kp = 2. * np.pi / template.rs_drag_fid
         self.kp = float(kp)
         for ell in self.ells:
@@ -323,6 +389,7 @@ class DampedBAOWigglesTracerPowerSpectrumMultipoles(_BaseBAOTracer):
         return len(self.ells) * len(self.k)
 
     def theory_spec(self):
+        if self.pt is not None: return self._emulated_spec('power', self.k)
         return dict(self._theory_common(), kind='bao_pk', k=self.k)
 
     def terms(self):
@@ -334,11 +401,12 @@ class DampedBAOWigglesTracerCorrelationFunctionMultipoles(_BaseBAOTracer):
     al{ell}_{pow} (s / sp)^pow, pow in [-2, 2], sp = 2 pi / 0.02 (reference bao.py:849-853, :867, :905)."""
     is_correlation = True
 
-    def __init__(self, template, s=None, sp=None, fftlog='fold', **kwargs):
+    def __init__(self, template=None, s=None, sp=None, fftlog='fold', **kwargs):
         super().__init__(template, **kwargs)
         # fftlog: 'fold' = the (linear) P_ell(kin) -> xi_ell(s) operator is folded into the plan's term matrices; 'kernel' = explicit FFTLog kernel
         self.fftlog = str(fftlog)
         self.s = np.linspace(20., 200., 101) if s is None else np.asarray(s, dtype='f8')
+        if self.pt is not None and s is None: self.s = np.asarray(self.pt.k, dtype='f8')
         self.sp = 2. * np.pi / 0.02 if sp is None else float(sp)
         for ell in self.ells:
             for power in range(-2, 3):
@@ -352,6 +420,7 @@ class DampedBAOWigglesTracerCorrelationFunctionMultipoles(_BaseBAOTracer):
         return len(self.ells) * len(self.s)
 
     def theory_spec(self):
+        if self.pt is not None: return self._emulated_spec('corr', self.s)
         return dict(self._theory_common(), kind='bao_xi', s=self.s, fftlog=self.fftlog)
 
     def terms(self):

@@ -312,6 +312,19 @@ def cubic_transform(flattheory, flatdata):
 LPT_BIAS_PARAMS = ['b1', 'b2', 'bs', 'b3', 'alpha0', 'alpha2', 'alpha4', 'alpha6', 'sn0', 'sn2', 'sn4']
 
 
+def lpt_physical_pars(p, sigma8, fsigma8, shotnoise=1e4, fsat=0.1, sigv=5., nd=1e-4):
+    """Physical prior basis of the velocileptors tracers, restated from reference full_shape.py:1299-1307 (+ :1154-1157: snd = shotnoise * nd with
+    nd = 1e-4): sampled (b1p, b2p, bsp, b3p, alpha0p, alpha2p, alpha4p, sn0p, sn2p, sn4p) -> the 11 standard-basis parameters fed to
+    ``combine_bias_terms_poles``."""
+    f = fsigma8 / sigma8
+    snd = shotnoise * nd
+    b1L, b2L, bsL, b3L = p['b1p'] / sigma8 - 1., p['b2p'] / sigma8**2, p['bsp'] / sigma8**2, p['b3p'] / sigma8**3
+    pars = [b1L, b2L, bsL, b3L]
+    pars += [(1 + b1L)**2 * p['alpha0p'], f * (1 + b1L) * (p['alpha0p'] + p['alpha2p']), f * (f * p['alpha2p'] + (1 + b1L) * p['alpha4p']), f**2 * p['alpha4p']]
+    pars += [p['sn{:d}p'.format(i)] * snd * (fsat if i > 0 else 1.) * sigv**i for i in [0, 2, 4]]
+    return pars
+
+
 def lpt_bias_monomials(pars, nd=1e-4):
     b1, b2, bs, b3, alpha0, alpha2, alpha4, alpha6, sn0, sn2, sn4 = pars
     return np.array([1, b1, b1**2, b2, b1 * b2, b2**2, bs, b1 * bs, b2 * bs, bs**2, b3, b1 * b3, alpha0, alpha2, alpha4, alpha6,

@@ -8,7 +8,7 @@ def taylor_powers(d, order):
     return np.array([p for total in range(order + 1) for p in itertools.product(range(order + 1), repeat=d) if sum(p) == total], dtype='i4')
 
 
-def make_lpt_likelihood(marg=True, seed=11, order=2, nk=24, tracer=None, engine='taylor'):
+def make_lpt_likelihood(marg=True, seed=11, order=2, nk=24, tracer=None, engine='taylor', physical=False):
     """-> (likelihood, emulator-state pieces) with a random Taylor emulator of pktable [3, nk_pt, 19] in (qpar, qper, dm, df)."""
     import desilike_b200 as dl
     from oracle import synthetic
@@ -37,12 +37,20 @@ def make_lpt_likelihood(marg=True, seed=11, order=2, nk=24, tracer=None, engine=
         emu = dl.Emulator.from_mlp(params, mlp, {'pktable': slice(0, ny)}, {'pktable': (len(ells), len(kpt), 19)}, fixed=dict(k=kpt, ells=ells, z=1.), all_params=all_params,
                                    defaults=dict(zip(params, center)), calculator_class=('desilike.theories.galaxy_clustering.full_shape', 'LPTVelocileptorsPowerSpectrumMultipoles'))
     else:
-        emu = dl.Emulator.from_taylor(params, center, powers, {'pktable': deriv}, fixed=dict(k=kpt, ells=ells, z=1.), all_params=all_params,
+        tables = {'pktable': deriv}
+        scalars = None
+        if physical:   # sigma8(theta), fsigma8(theta) as scalar Taylor engines of the same emulator (what the pt calculator exposes, reference full_shape.py:1300-1301)
+            s8 = rng.standard_normal(len(powers)) * 0.05 * 0.3**powers.sum(axis=-1); s8[0] = 0.8
+            fs8 = rng.standard_normal(len(powers)) * 0.03 * 0.3**powers.sum(axis=-1); fs8[0] = 0.45
+            tables.update(sigma8=s8, fsigma8=fs8)
+            scalars = dict(sigma8=s8, fsigma8=fs8)
+        emu = dl.Emulator.from_taylor(params, center, powers, tables, fixed=dict(k=kpt, ells=ells, z=1.), all_params=all_params,
                                       calculator_class=('desilike.theories.galaxy_clustering.full_shape', 'LPTVelocileptorsPowerSpectrumMultipoles'))
-    theory = dl.LPTVelocileptorsTracerPowerSpectrumMultipoles(pt=emu.to_calculator(), k=k, ells=ells, shotnoise=1e4, tracer=tracer)
+    theory = dl.LPTVelocileptorsTracerPowerSpectrumMultipoles(pt=emu.to_calculator(), k=k, ells=ells, shotnoise=0.8e4 if physical else 1e4, tracer=tracer,
+                                                              prior_basis='physical' if physical else 'standard', tracer_type='LRG' if physical else None)
     if marg:
         for name in ['alpha0', 'alpha2', 'alpha4', 'sn0', 'sn2', 'sn4']:
-            theory.params[theory._ns(name)].update(derived='.marg')
+            theory.params[theory._ns(name + ('p' if physical else ''))].update(derived='.marg')
     n = len(ells) * nk
     fid = dict(b1=1.8, b2=0.4, bs=-0.3)
     # data = the model at a fiducial point (linear parameters at 0) + noise
@@ -55,7 +63,9 @@ def make_lpt_likelihood(marg=True, seed=11, order=2, nk=24, tracer=None, engine=
     data = data + 0.3 * sig * rng.standard_normal(n)
     obs = dl.TracerPowerSpectrumMultipolesObservable(data=data.reshape(len(ells), nk), k=[k] * len(ells), ells=ells, theory=theory, name='lpt')
     like = dl.ObservablesGaussianLikelihood(observables=[obs], covariance=cov)
-    return like, dict(kpt=kpt, k=k, ells=ells, params=params, center=center, powers=powers, deriv=deriv, cov=cov, data=data, mlp=mlp)
+    info = dict(kpt=kpt, k=k, ells=ells, params=params, center=center, powers=powers, deriv=deriv, cov=cov, data=data, mlp=mlp)
+    if physical: info.update(scalars=scalars, physical=dict(shotnoise=0.8e4, fsat=theory.fsat, sigv=theory.sigv))
+    return like, info
 
 
 def direct_theory(info, X, names, nd=1e-4):
@@ -71,5 +81,9 @@ def direct_theory(info, X, names, nd=1e-4):
             mono = np.prod(diffs**info['powers'], axis=-1)
             pktable = np.tensordot(mono, info['deriv'], axes=(0, 0))
         pars = [v.get(n, 0.) for n in core.LPT_BIAS_PARAMS]
+        if info.get('physical') is not None:   # physical prior basis (reference full_shape.py:1299-1307): sigma8 / fsigma8 from their Taylor engines
+            sigma8, fsigma8 = mono.dot(info['scalars']['sigma8']), mono.dot(info['scalars']['fsigma8'])
+            p = {n: v.get(n, 0.) for n in ['b1p', 'b2p', 'bsp', 'b3p', 'alpha0p', 'alpha2p', 'alpha4p', 'sn0p', 'sn2p', 'sn4p']}
+            pars = core.lpt_physical_pars(p, sigma8, fsigma8, **info['physical'])
         out.append(core.lpt_tracer_power(pktable, info['kpt'], info['k'], pars, nd=nd).ravel())
     return np.array(out)

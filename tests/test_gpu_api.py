@@ -332,3 +332,60 @@ def test_prec_premarginalisation_couples_observables_of_one_likelihood(gpu_requi
             dl.Plan(bad)
         with pytest.raises(ValueError):
             pipeline.evaluate(bad, X)
+
+
+def test_fit_taylor_and_qmc_samples_for_bao_theory(gpu_required, tmp_path):
+    """Emulator construction beyond Kaiser: ``Emulator.fit_taylor`` of a damped-BAO P(k) tracer theory (theory
+    evaluated on the GPU on the finite-difference stencil) -> emulator file -> ``DampedBAOWigglesTracerPowerSpectrumMultipoles(pt=...)`` ->
+    the emulated likelihood reproduces the direct one around the expansion point; ``Emulator.qmc_samples``: the MLP training design
+    (reference emulators/__init__.py:528-533) with the tables evaluated on the GPU == the oracle tables at the same points."""
+    k = np.linspace(0.02, 0.3, 57)
+    template = dl.BAOPowerSpectrumTemplate(pk_dd_fid=synthetic.pk_fid, pknow_dd_fid=synthetic.pknow_fid, f_fid=synthetic.F_FID, rs_drag=synthetic.RS_DRAG)
+    theory = dl.DampedBAOWigglesTracerPowerSpectrumMultipoles(template=template, k=k, ells=(0, 2))
+    for p in theory.params.select(basename='al*'): p.update(fixed=True)
+    for name, value in [('b1', 2.), ('sigmas', 3.)]: theory.all_params[name].update(value=value)
+    emu = dl.Emulator.fit_taylor(theory, order=4, delta=[0.01, 0.01, 0.05, 0.02, 0.3])
+    fn = str(tmp_path / 'bao_emu.npy')
+    emu.save(fn)
+    pt = dl.EmulatedCalculator.load(fn)
+    assert pt.emulator.state['engines']['power']['yshape'] == (2, 57)
+    emulated = dl.DampedBAOWigglesTracerPowerSpectrumMultipoles(pt=pt, ells=(0, 2), kp=theory.kp)
+    for p in emulated.params.select(basename='al*'): p.update(fixed=True)
+    cov = np.diag(np.full(114, 4e4))
+    likes = []
+    for th in (theory, emulated):
+        obs = dl.TracerPowerSpectrumMultipolesObservable(data={'b1': 2., 'sigmas': 3.}, k=[k, k], ells=(0, 2), theory=th, covariance=cov)
+        likes.append(dl.ObservablesGaussianLikelihood([obs]))
+    assert likes[0].plan.params == likes[1].plan.params == ['qpar', 'qper', 'b1', 'dbeta', 'sigmas']
+    rng = np.random.default_rng(3)
+    params = {'qpar': rng.uniform(0.99, 1.01, 50), 'qper': rng.uniform(0.99, 1.01, 50), 'b1': rng.uniform(1.95, 2.05, 50),
+              'dbeta': rng.uniform(0.98, 1.02, 50), 'sigmas': rng.uniform(2.8, 3.2, 50)}
+    direct, emul = dl.vmap(likes[0])(params), dl.vmap(likes[1])(params)
+    assert np.max(np.abs(emul - direct)) < 2e-3 * max(1., np.max(np.abs(direct)))    # 5th-order Taylor remainder inside the stencil
+    # training design of an MLP emulator: QMC points, tables on the GPU
+    samples = dl.Emulator.qmc_samples(theory, niterations=300, params=['qpar', 'qper', 'b1'])
+    assert samples['X'].shape == (300, 3) and samples['Y']['power'].shape == (300, 2, 57)
+    assert np.all(samples['X'] >= samples['lower']) and np.all(samples['X'] <= samples['upper'])
+    tspec = dict(theory.theory_spec(), params=['qpar', 'qper', 'b1'])
+    ref = pipeline.theory_tables(tspec, samples['X'][:40], ['qpar', 'qper', 'b1'])['power']
+    got = samples['Y']['power'][:40].reshape(40, -1)
+    assert np.max(np.abs(got - ref) / np.max(np.abs(ref), axis=0)) < 1e-10
+
+
+@pytest.mark.parametrize('marg', [False, True])
+def test_lpt_physical_prior_basis(gpu_required, marg):
+    """Velocileptors ``prior_basis='physical'`` (reference full_shape.py:1299-1307) on the CUDA path: theory vectors vs the direct restatement,
+    log-posterior and the marginalised alpha*p / sn*p vs the oracle."""
+    import lpt_helpers
+    like, info = lpt_helpers.make_lpt_likelihood(marg=marg, physical=True)
+    spec = like.spec
+    rng = np.random.default_rng(6)
+    N = 200
+    X = np.column_stack([rng.uniform(0.97, 1.03, N) if n in ('qpar', 'qper', 'df') else rng.uniform(-0.03, 0.03, N) if n == 'dm' else
+                         rng.uniform(1.2, 1.8, N) if n == 'b1p' else rng.normal(0., 0.3, N) for n in spec['params']])
+    theory = like.plan.theory(X[:40])
+    direct = lpt_helpers.direct_theory(info, X[:40], spec['params'])
+    assert np.max(np.abs(theory - direct) / np.max(np.abs(direct), axis=0)) < 1e-10
+    got, ref = like.plan.eval(X), pipeline.evaluate(spec, X)
+    assert np.all(np.abs(got['logposterior'] - ref['logposterior']) <= 1e-8 * np.maximum(1., np.abs(ref['logposterior'])))
+    if marg: assert np.allclose(got['x_solved'], ref['x_solved'], rtol=1e-7, atol=1e-7)

@@ -404,3 +404,27 @@ def test_power_fiber_collision_kernels_match_reference_class():
                                                      fiber_collisions=dict(fs=0.5, Dfc=0.8))
     ospec = obs.observable_spec()
     assert np.allclose(ospec['wmatrix'] @ power.ravel() + ospec['offset'], W @ ref.ravel(), rtol=1e-11, atol=1e-8)
+
+
+def test_lpt_physical_prior_basis_lowering():
+    """Velocileptors ``prior_basis='physical'`` (the reference default, full_shape.py:1275, :1299-1307) on the lowered plan: sigma8 / fsigma8 from
+    scalar Taylor engines become derived-expression parameters, b1 .. b3 derived from them, the alpha / sn slices expanded in (b1, f); the NumPy
+    mirror of the kernels == the direct restatement (Taylor predict -> physical mapping -> bias combine -> interp1d), sampled and marginalised."""
+    import lowered_numpy
+    import lpt_helpers
+    from desilike_b200.lowering import Lowered
+    for marg in (False, True):
+        like, info = lpt_helpers.make_lpt_likelihood(marg=marg, physical=True)
+        spec = like._finalize_spec(like.build_spec())
+        assert [dp['name'] for dp in spec['derived']][:2] == ['sigma8', 'f'] and 'b1p' in spec['params'] and 'b1' not in spec['params']
+        low = Lowered(spec, with_plain=True)
+        rng = np.random.default_rng(5)
+        X = np.column_stack([rng.uniform(0.97, 1.03, 12) if n in ('qpar', 'qper', 'df') else rng.uniform(-0.03, 0.03, 12) if n == 'dm' else
+                             rng.uniform(1.2, 1.8, 12) if n == 'b1p' else rng.normal(0., 0.3, 12) for n in spec['params']])
+        theory = lowered_numpy.evaluate(low, X, white=False)
+        direct = lpt_helpers.direct_theory(info, X, spec['params'])
+        assert np.max(np.abs(theory - direct) / np.max(np.abs(direct), axis=0)) < 1e-11
+        got = lowered_numpy.evaluate(low, X)
+        ref = pipeline.evaluate(spec, X)
+        assert np.allclose(got['logposterior'], ref['logposterior'], rtol=1e-10, atol=1e-8)
+        if marg: assert np.allclose(got['x_solved'], ref['x_solved'], rtol=1e-8, atol=1e-8)

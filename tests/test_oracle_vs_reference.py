@@ -215,3 +215,21 @@ def test_reference_power_observable_with_fiber_collisions():
                                                         theory=dl.KaiserTracerPowerSpectrumMultipoles(template=template))
     assert np.allclose(mirror.matrix_full, np.asarray(obs.wmatrix.matrix_full), rtol=1e-12, atol=1e-14)
     assert np.allclose(mirror.offset, np.asarray(obs.wmatrix.offset), rtol=1e-10, atol=1e-9)
+
+
+def test_qmc_design_matches_reference_sequence():
+    """``Emulator.qmc_points`` (training design of MLP emulators) == the reference's in-tree ``RQuasiRandomSequence`` + ``qmc.scale``
+    (desilike/samplers/qmc.py:13-36, :122-126), including a resumed sequence (offset)."""
+    ref_harness.setup()
+    from scipy.stats import qmc
+    from desilike.samplers.qmc import RQuasiRandomSequence
+    import desilike_b200 as dl
+    lower, upper = np.array([0.9, 0.9, -0.1, 0.5]), np.array([1.1, 1.2, 0.1, 1.5])
+    eng = RQuasiRandomSequence(d=4, seed=0.5)
+    eng.reset()
+    ref = qmc.scale(eng.random(n=257), lower, upper)
+    got = dl.Emulator.qmc_points(lower, upper, 257, engine='rqrs', seed=0.5)
+    assert np.allclose(got, ref, rtol=0, atol=1e-15)
+    eng.reset(); eng.fast_forward(100)
+    ref = qmc.scale(eng.random(n=50), lower, upper)
+    assert np.allclose(dl.Emulator.qmc_points(lower, upper, 50, offset=100), ref, rtol=0, atol=1e-15)
