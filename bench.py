@@ -504,17 +504,22 @@ def run_workload(ctx, args, workload, N, steps, warmup, main, peaks):
         api = 'desilike_b200.Plan.eval(pinned host ndarray) -> dlb_eval_batch'
         h2d, d2h = N * d * 8, N * (3 * 8 + 4) + N * ns * 8
     elif gather is not None:
-        hgat = torch.empty(total * (1 + ns), dtype=torch.float64, pin_memory=True)
+        # what a host-side consumer of a sharded evaluation reads back (reference samplers/base.py:196-200: logposterior of ALL points on every
+        # rank; the derived values -- here the solved parameters -- of its own points): gathered logposterior + own x_solved slice + local outputs
+        hgat = torch.empty(total, dtype=torch.float64, pin_memory=True)
+        hxs = torch.empty(max(N * ns, 1), dtype=torch.float64, pin_memory=True)
         lhost = {k: hout[k] for k in ('loglikelihood', 'logprior', 'status')}
 
-        def e2e_step(i):   # host parameters in -> finish kernel stores into every rank's window -> the gathered results back to the host
+        def e2e_step(i):   # host parameters in -> finish kernel stores into every rank's window -> results back to the host
             b = i % nbuf
             plan.eval_gather(hosts[i % 4], gather, b, rank * N, total, with_solved=ns > 0, out=lhost)
             gather.wait(b)
-            hgat.copy_(gather.buffer(b, total * (1 + ns)), non_blocking=True)
+            window = gather.buffer(b, total * (1 + ns))
+            hgat.copy_(window[:total], non_blocking=True)
+            if ns: hxs.copy_(window[total + rank * N * ns:total + (rank + 1) * N * ns], non_blocking=True)
             torch.cuda.synchronize()
-        api = 'desilike_b200.Plan.eval_gather(pinned host ndarray) -> dlb_eval_batch_gather; PeerGather.wait; D2H of the gathered window'
-        h2d, d2h = N * d * 8, N * (2 * 8 + 4) + total * (1 + ns) * 8
+        api = 'desilike_b200.Plan.eval_gather(pinned host ndarray) -> dlb_eval_batch_gather; PeerGather.wait; D2H of the gathered logposterior + own x_solved'
+        h2d, d2h = N * d * 8, N * (2 * 8 + 4) + total * 8 + N * ns * 8
     else:
         def e2e_step(i):
             plan.eval(hosts[i % 4], out=hout)

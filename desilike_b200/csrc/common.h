@@ -89,6 +89,7 @@ struct BlockDev {     // one output block as seen by the contraction kernel (dev
                                        // rank-reduced, lower-triangular problem are neither loaded nor multiplied), or NULL
   const unsigned long long* tmask;     // [ncb][nchunks][2] per (column block, k-chunk, warp of the pair): up to 8 runs of k4 steps, 8 bits each (5 bits
                                        // length, 3 bits = number of leading n-tiles of that warp with non-zero 4 x 8 sub-tiles); ~0: everything is multiplied; or NULL
+  int oslot;                           // output mode of a transformed multi-slot block: column stride between the slots' outputs (0: slot 0 only)
   const double* tdata;                 // output mode: [ncols] data d of the 'cubic'-transformed columns (0: untransformed column), or NULL
 };
 

@@ -511,11 +511,26 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
                     if (p.act == 1) v = silu(v);                   // silu  (reference emulators/conversion.py:27)
                     else if (p.act == 2) v = fmax(v, 0.);          // relu  (:29)
                     else if (p.act == 3) v = tanh(v);              // tanh  (:31)
+                    double dscale = 1.;                            // u'(t) of the transformed columns
                     if (blk->tdata) {   // observable transform (reference observables/galaxy_clustering/power_spectrum.py:402-404)
                       const double dcol = __ldg(blk->tdata + col);
-                      if (dcol != 0.) v = (3. * cbrt(v / dcol) - 2.) * dcol;
+                      if (dcol != 0.) {
+                        const double c = cbrt(v / dcol);
+                        v = (3. * c - 2.) * dcol;
+                        dscale = 1. / (c * c);
+                      }
                     }
-                    p.out[row * p.ostride + blk->ocol0 + col] = v;
+                    double* o = p.out + row * p.ostride + blk->ocol0 + col;
+                    *o = v;
+                    if constexpr (R > 1) {
+                      // solved-parameter templates of a transformed block: Jacobian rows of u(t(x)) at the defaults, u'(t) dt/dx_a (the reference
+                      // differentiates flatdiff THROUGH the transform, likelihoods/base.py:152-158)
+                      if (blk->oslot > 0) {
+#pragma unroll
+                        for (int a = 1; a < R; ++a)
+                          if (a < Rb) o[a * blk->oslot] = acc[a][mt][nt][e] * dscale;
+                      }
+                    }
                   }
                 }
             }

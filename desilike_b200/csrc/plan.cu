@@ -378,6 +378,7 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
       bd.ncols = pass == 0 ? b->ncols_w : b->ncols;
       bd.ocol0 = b->coloff; bd.gen = b->gen; bd.fill = b->fill; bd.fbase = b->fbase; bd.acols = std::min((b->maxcol + 1) & ~1, L.ast);
       bd.tdata = pass == 1 ? b->d_tdata : nullptr;
+      bd.oslot = 0;
       bd.tmask = pass == 0 ? b->d_tmask_white : b->d_tmask_plain;
       if (bd.tmask) (pass == 0 ? L.masked_white : L.masked_plain) = true;
       bd.cb_first = pass == 0 ? b->d_cb_first : nullptr;
@@ -387,7 +388,10 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
     DLB_TRY(upload(plan, tab.data(), tab.size(), pass == 0 ? &L.d_white : &L.d_plain));
     if (pass == 1 && blocks[0]->d_tdata) {
       std::vector<BlockDev> tab_t(tab);
-      for (size_t ib = 0; ib < blocks.size(); ++ib) tab_t[ib].ocol0 = blocks[ib]->tcol;
+      for (size_t ib = 0; ib < blocks.size(); ++ib) {   // stage 1 of a two-stage plan: [u | u' S_1 | ...] of the block at column tcol of w_T
+        tab_t[ib].ocol0 = blocks[ib]->tcol;
+        tab_t[ib].oslot = blocks[ib]->nslots > 1 ? ((blocks[ib]->ncols + 3) & ~3) : 0;
+      }
       DLB_TRY(upload(plan, tab_t.data(), tab_t.size(), &L.d_plain_t));
     }
     // per-tile TMA schedule: for every block, column block: the k-chunk tiles in order, then the epilogue constants
@@ -865,15 +869,17 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
   plan->ntheory = coloff; plan->ptotal = poff;
   for (int ib = 0; ib < desc->nblocks; ++ib) plan->two_stage = plan->two_stage || desc->blocks[ib].transform_data != nullptr;
   if (plan->two_stage) {
-    DLB_REQUIRE(desc->ns == 0, "observable transform: solved parameters are not supported in a two-stage plan");
+    // Solved parameters in a two-stage plan: the reference linearises flatdiff = u(t(x)) - data at the defaults (FastFisher, likelihoods/base.py:
+    // 152-158: jacfwd through the transform), i.e. Jacobian rows u'(t) * dt/dx_i.  Stage 1 then carries EVERY solved template of the block as a slot
+    // (constant templates too: scaled by u'(t(theta)) they depend on theta) and writes [u | u' S_1 | u' S_2 ...] per block into w_T.
     int tcol = 0;
     for (int ib = 0; ib < desc->nblocks; ++ib) {
       const dlb_block_desc& bd = desc->blocks[ib];
-      DLB_REQUIRE(bd.transform_data && bd.whitening_t && bd.r0_data_white && bd.matrices_plain && bd.t0_plain && bd.nslots == 1 && bd.nconst == 0,
-                  "observable transform: every block needs transform_data, whitening_t, r0_data_white, matrices_plain, t0_plain");
+      DLB_REQUIRE(bd.transform_data && bd.whitening_t && bd.r0_data_white && bd.matrices_plain && bd.t0_plain && bd.nconst == 0,
+                  "observable transform: every block needs transform_data, whitening_t, r0_data_white, matrices_plain, t0_plain (and nconst == 0)");
       DLB_TRY(upload(plan, bd.transform_data, (size_t)bd.ncols, &plan->blocks[ib].d_tdata));
       plan->blocks[ib].tcol = tcol;
-      tcol += (bd.ncols + 3) & ~3;   // blocks start on 32-byte boundaries; k-chunks may read up to the padded length (zeros)
+      tcol += bd.nslots * ((bd.ncols + 3) & ~3);   // slots start on 32-byte boundaries; k-chunks may read up to the padded length (zeros)
     }
     plan->tstride = tcol;
   }
@@ -881,14 +887,16 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
   if (plan->two_stage) {
     int maxn = 0;
     for (int ib = 0; ib < desc->nblocks; ++ib) maxn = std::max(maxn, desc->blocks[ib].ncols);
-    const Variant wvar = pick_variant(plan, 1, false, 0, 0, 1, maxn);
+    const Variant wvar = pick_variant(plan, max_slots, false, 0, 0, npart_bound, maxn);
     plan->wblocks.resize(desc->nblocks);
     std::vector<Block*> wptr;
     for (int ib = 0; ib < desc->nblocks; ++ib) {
       const dlb_block_desc& bd = desc->blocks[ib];
       Block& wb = plan->wblocks[ib];
-      std::vector<TermSpec> terms{TermSpec{0, -1, plan->blocks[ib].tcol, plan->blocks[ib].tcol, bd.ncols, bd.whitening_t, nullptr}};
-      DLB_TRY(build_block_core(plan, wvar, false, bd.ncols, 1, terms, bd.r0_data_white, nullptr, 0, nullptr, wb));
+      const int cpad = (bd.ncols + 3) & ~3;
+      std::vector<TermSpec> terms;
+      for (int a = 0; a < bd.nslots; ++a) terms.push_back(TermSpec{a, -1, plan->blocks[ib].tcol + a * cpad, plan->blocks[ib].tcol + a * cpad, bd.ncols, bd.whitening_t, nullptr});
+      DLB_TRY(build_block_core(plan, wvar, false, bd.ncols, bd.nslots, terms, bd.r0_data_white, nullptr, 0, nullptr, wb));
       wb.poff = plan->blocks[ib].poff; wb.coloff = plan->blocks[ib].coloff; wb.gen = -1; wb.d_map = plan->blocks[ib].d_map;
       wptr.push_back(&wb);
     }

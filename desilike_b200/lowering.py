@@ -234,9 +234,6 @@ class Lowered(object):
                 n_o, nin = len(obs['data']), int(obs['nin'])
                 if obs.get('transform') is not None:
                     if obs['transform'] != 'cubic': raise LoweringError('unknown observable transform {!r}'.format(obs['transform']))
-                    if solved:
-                        raise LoweringError("observable transform 'cubic' is non-linear in the theory: analytically solved parameters are not "
-                                            "supported together with it on the CUDA path")
                     if np.any(f64(obs['data']) == 0.): raise LoweringError("transform 'cubic' divides by the data vector: zero entries found")
                     tdata[c0:c0 + n_o] = f64(obs['data'])
                     self.two_stage = True
@@ -291,6 +288,14 @@ class Lowered(object):
                 c0 += n_o
             for si in const_rows:
                 if si in slot_of: raise LoweringError('solved parameter {} mixes constant and theta-dependent templates'.format(self.solved_names[si]))
+            if np.any(tdata != 0.) and const_rows:
+                # transformed observable: the Jacobian rows are u'(t(theta)) dt/dx_i (the reference differentiates flatdiff through the transform,
+                # likelihoods/base.py:152-158), so constant templates become slots as well -- riding on the constant-one feature of the segment
+                gi0 = gen_of[id(group[0]['theory'])]
+                for si in sorted(const_rows):
+                    slot_of[si] = 1 + len(slot_of)
+                    terms[(slot_of[si], -1, gi0, 0, 1)] = const_rows[si][None, :].copy()
+                const_rows = {}
             nslots = 1 + len(slot_of)
             if nslots > 8:
                 # dense joint precision coupling more theta-dependent solved templates than one pass holds (8 accumulator slots): split

@@ -237,12 +237,16 @@ def evaluate(spec, X, return_theory=False, return_hessian=False):
     for obs in spec['observables']:
         tables = theory_tables(obs['theory'], X, names)
         flat = observable_flat(obs, X, names, x0, tables=tables)
+        dscale = 1.
         if obs.get('transform') == 'cubic':
+            # the reference obtains the Jacobian of flatdiff by jacfwd THROUGH the transform (likelihoods/base.py:152-158), at the solved
+            # parameters' defaults: rows u'(t) dt/dx with u'(t) = (t / d)^(-2/3) for u = (3 (t / d)^(1/3) - 2) d (power_spectrum.py:402-404)
+            dscale = np.cbrt(flat / obs['data'])**-2
             flat = core.cubic_transform(flat, obs['data'])
         flats.append(flat)
         if solved:
             snames = {t.get('solved') for t in obs['terms']}
-            jacs.append(np.stack([observable_flat(obs, X, names, x0, tables=tables, only_solved=s['name']) if s['name'] in snames
+            jacs.append(np.stack([dscale * observable_flat(obs, X, names, x0, tables=tables, only_solved=s['name']) if s['name'] in snames
                                   else np.zeros_like(flat) for s in solved], axis=1))  # [N, ns, nobs]
     flattheory = np.concatenate(flats, axis=-1)
     flatdata = np.concatenate([obs['data'] for obs in spec['observables']])

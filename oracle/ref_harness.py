@@ -108,11 +108,13 @@ def run_vmap(likelihood, spec, X, return_theory=True):
     return out
 
 
-def install_jacfwd_stub():
+def install_jacfwd_stub(step=1.):
     """The reference's FastFisher.__call__ (reference desilike/likelihoods/base.py:129-200) does ``import jax`` and calls
     ``jax.jacfwd(getter)(x)``; jax is absent.  The theory is exactly linear in the solved parameters, so a central
     difference with unit step IS the Jacobian (up to rounding).  Injecting this shim AFTER desilike was imported
-    (so desilike.jax keeps its NumPy fallback) lets the reference's own FastFisher/_solve code run unmodified."""
+    (so desilike.jax keeps its NumPy fallback) lets the reference's own FastFisher/_solve code run unmodified.
+    ``step`` < 1: for a flatdiff that is NOT linear in the solved parameters (observable transform='cubic') the shim returns the Richardson-
+    extrapolated central difference (4 D(step / 2) - D(step)) / 3, accurate to O(step^4) -- far below the fixture tolerances."""
     import types
 
     def jacfwd(fun, argnums=0, has_aux=False, holomorphic=False):
@@ -120,10 +122,15 @@ def install_jacfwd_stub():
             x = np.asarray(x, dtype='f8')
             cols = []
             for i in range(x.size):
-                e = np.zeros_like(x); e[i] = 1.
-                up = [np.array(a) for a in fun(x + e)]
-                dn = [np.array(a) for a in fun(x - e)]
-                cols.append([(u - d) / 2. for u, d in zip(up, dn)])
+                e = np.zeros_like(x); e[i] = step
+
+                def central(h):
+                    up = [np.array(a) for a in fun(x + h * e)]
+                    dn = [np.array(a) for a in fun(x - h * e)]
+                    return [(u - d) / (2. * h * step) for u, d in zip(up, dn)]
+
+                if step == 1.: cols.append(central(1.))
+                else: cols.append([(4. * a - b) / 3. for a, b in zip(central(0.5), central(1.))])
             return [np.stack([c[j] for c in cols], axis=-1) for j in range(len(cols[0]))]
         return jac
 

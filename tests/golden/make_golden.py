@@ -26,6 +26,9 @@ CASES = {
     'eftlike_prec': dict(config='config_kaiser_window', kwargs=dict(eftlike=True, solved=True), eftlike=True, mode='.prec', n=48, seed=109),
     'kaiser_window_syst': dict(config='config_kaiser_window', kwargs=dict(eftlike=False, solved=False, systematic=True), eftlike=False, mode='.marg', n=32, seed=111),
     'kaiser_window_cubic': dict(config='config_kaiser_window', kwargs=dict(eftlike=False, solved=False, transform='cubic'), eftlike=False, mode=None, n=32, seed=106),
+    # transform='cubic' together with analytically marginalised terms: flatdiff is not linear in them, the reference linearises at the defaults
+    # (jacfwd through the transform, likelihoods/base.py:152-158) -- the jacfwd shim then uses an extrapolated small-step difference
+    'eftlike_cubic_marg': dict(config='config_kaiser_window', kwargs=dict(eftlike=True, solved=True, transform='cubic'), eftlike=True, mode='.marg', n=32, seed=112, jac_step=3e-3),
 }
 
 
@@ -38,11 +41,12 @@ def build_spec(case):
     return spec
 
 
-def main():
+def main(only=None):
     for name, case in CASES.items():
+        if only and name not in only: continue
         spec = build_spec(case)
         like = ref_harness.reference_kaiser_likelihood(spec, eftlike=case['eftlike'], solved_mode=case['mode'])
-        if spec['solved']: ref_harness.install_jacfwd_stub()
+        if spec['solved']: ref_harness.install_jacfwd_stub(step=case.get('jac_step', 1.))
         X = configs.sample_points(spec, case['n'], seed=case['seed'])
         if not spec['solved']:
             X[1, 0] = 1.3   # out of prior -> -inf
@@ -201,6 +205,9 @@ def xi_window():
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 1:   # python tests/golden/make_golden.py <case> [<case> ...]: (re)generate only those likelihood fixtures
+        main(only=sys.argv[1:])
+        sys.exit(0)
     fiber_collisions()
     covariance_corrections()
     xi_window()

@@ -76,7 +76,7 @@ def evaluate(low, X, feature_fn=None, white=True):
             # two-stage plans (observable transform, csrc/plan.cu:run_two_stage): theory through the un-whitened matrices, transform in
             # the epilogue, then the whitening contraction
             t = slots[0] + blk['t0_plain'] if not white else sum((np.atleast_1d(C[:, key[1]])[:, None] if key[1] >= 0 else 1.) * (F[key[2]][:, key[3]:key[3] + key[4]] @ mp)
-                                                                 for key, mp in zip(blk['terms'], blk['plain'])) + blk['t0_plain']
+                                                                 for key, mp in zip(blk['terms'], blk['plain']) if key[0] == 0) + blk['t0_plain']
             if low.two_stage:
                 d = blk['transform_data']
                 with np.errstate(divide='ignore', invalid='ignore'):
@@ -85,6 +85,22 @@ def evaluate(low, X, feature_fn=None, white=True):
                 theory.append(t)
                 continue
             r = t @ blk['whitening_t'] - blk['r0_data_white']
+            if blk['nslots'] > 1:   # solved parameters of a transformed block: Jacobian rows u'(t) dt/dx_a (csrc/contract.cu output mode, oslot > 0)
+                t_plain = sum((np.atleast_1d(C[:, key[1]])[:, None] if key[1] >= 0 else 1.) * (F[key[2]][:, key[3]:key[3] + key[4]] @ mp)
+                              for key, mp in zip(blk['terms'], blk['plain']) if key[0] == 0) + blk['t0_plain']
+                d = blk['transform_data']
+                with np.errstate(divide='ignore', invalid='ignore'):
+                    up = np.where(d != 0., np.cbrt(t_plain / np.where(d != 0., d, 1.))**-2, 1.)
+                chi2 += np.sum(r**2, axis=-1)
+                rows = []
+                for a, si in enumerate(blk['slot_solved']):
+                    Sa = sum((np.atleast_1d(C[:, key[1]])[:, None] if key[1] >= 0 else 1.) * (F[key[2]][:, key[3]:key[3] + key[4]] @ mp)
+                             for key, mp in zip(blk['terms'], blk['plain']) if key[0] == 1 + a)
+                    rows.append((int(si), (Sa * up) @ blk['whitening_t']))
+                for si, Ji in rows:
+                    gL[:, si] -= np.sum(Ji * r, axis=-1)
+                    for sj, Jj in rows: M[:, si, sj] += np.sum(Ji * Jj, axis=-1)
+                continue
         else:
             r = slots[0] - blk['r0_white']
         if blk.get('entry_kind') is not None:

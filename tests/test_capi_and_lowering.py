@@ -102,10 +102,6 @@ def test_marg_parameters_are_ordered_first():
 
 def test_unsupported_features_fail_loudly():
     from desilike_b200.lowering import Lowered, LoweringError
-    spec = configs.config_kaiser_window(eftlike=True, solved=True, nkin=20, nbins=6)
-    spec['observables'][0]['transform'] = 'cubic'   # non-linear in the theory: no analytic solve
-    with pytest.raises(LoweringError):
-        Lowered(spec)
     spec = configs.config_kaiser_window(eftlike=False, solved=False, nkin=20, nbins=6)
     spec['observables'][0]['transform'] = 'quartic'
     with pytest.raises(LoweringError):
@@ -130,6 +126,7 @@ THEORY_CASES = {
     'c3_bao_fftlog': lambda: configs.config_c3(),                    # P -> xi operator folded into the term matrices (default)
     'c3_bao_fftlog_kernel': lambda: _c3_kernel(),                    # explicit FFTLog kernel payload
     'kaiser_window_cubic': lambda: configs.config_kaiser_window(eftlike=False, solved=False, transform='cubic'),   # two-stage plan
+    'kaiser_window_cubic_marg': lambda: configs.config_kaiser_window(eftlike=True, solved=True, transform='cubic'),   # + Jacobian rows u'(t) dt/dx
     'c4_mlp': lambda: configs.config_c4(ntracers=2, nkin=40, nbins=10, hidden=(16, 16)),
 }
 

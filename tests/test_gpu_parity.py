@@ -316,3 +316,15 @@ def test_dense_precision_many_solved_templates_split(gpu_required):
     assert np.all(np.abs(got['logposterior'] - ref['logposterior']) <= 1e-8 * np.maximum(1., np.abs(ref['logposterior'])))
     assert np.allclose(got['hessian'], ref['hessian'], rtol=1e-8, atol=1e-10 * np.max(np.abs(ref['hessian'])))
     plan.close()
+
+
+def test_cubic_transform_with_solved_parameters(gpu_required):
+    """transform='cubic' together with analytically marginalised terms: flatdiff = u(t(x)) - data is not linear in x, the reference linearises
+    at the defaults (jacfwd through the transform, likelihoods/base.py:152-158).  Stage 1 of the plan writes [u | u'(t) dt/dx_i] (constant templates
+    become slots too), stage 2 whitens all of them; direct Kaiser theory (7 templates) and Taylor-emulated tracers, '.marg' and '.best'."""
+    check(configs.config_kaiser_window(eftlike=True, solved=True, transform='cubic'), 300, seed=41, solved=True)
+    spec = configs.config_c5(ntracers=2, nkin=40, nbins=10, order=2, solved=True)
+    spec['observables'][1]['transform'] = 'cubic'
+    spec['observables'][0]['transform'] = 'cubic'
+    for s in spec['solved'][1::2]: s['marg'] = False
+    check(spec, 257, seed=42, solved=True)

