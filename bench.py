@@ -415,8 +415,7 @@ def run_workload(ctx, args, workload, N, steps, warmup, main, peaks):
         if world == 1:
             plan.eval(pool[i % npool], out=outs)
         elif gather is not None:
-            plan.eval_gather(pool[i % npool], gather, i % nbuf, rank * N, total, with_solved=ns > 0, out=louts)
-            if i > 0: gather.wait((i - 1) % nbuf)
+            plan.eval_gather(pool[i % npool], gather, i % nbuf, rank * N, total, with_solved=ns > 0, out=louts, wait=(i - 1) % nbuf if i > 0 else None)
         else:   # NCCL: in-place all-gather of logposterior (+ x_solved), double buffered so that it overlaps the next evaluation
             b = i % 2
             if works[b] is not None:

@@ -12,7 +12,7 @@ from .build import LIBPATH
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
 
-DLB_ABI_VERSION = 5
+DLB_ABI_VERSION = 6
 DLB_COEF_MAXF = 4
 GEN_TAYLOR, GEN_MLP, GEN_KAISER, GEN_BAO = 1, 2, 3, 4
 PT_NONFINITE, PT_OUT_OF_PRIOR, PT_NOT_SPD = 1, 2, 4
@@ -78,7 +78,7 @@ SYMBOLS = {
     'dlb_gather_connect': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'dlb_gather_buffer': (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int32]),
     'dlb_eval_batch_gather': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
-                                             ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+                                             ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
     'dlb_gather_publish': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
     'dlb_gather_wait': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
     'dlb_gather_status': (ctypes.c_int, [ctypes.c_void_p]),

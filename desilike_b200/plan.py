@@ -117,12 +117,13 @@ class Plan(object):
             out['x_solved'] = out['x_solved_plan_order'] if self._identity_perm else out['x_solved_plan_order'][:, torch.as_tensor(self._unperm, device=X.device)]
         return out
 
-    def eval_gather(self, X, gather, buf, slice_start, total, with_solved=False, out=None):
+    def eval_gather(self, X, gather, buf, slice_start, total, with_solved=False, out=None, wait=None):
         """Evaluate this rank's slice ``X[n, d]`` (rows ``slice_start : slice_start + n`` of a batch of ``total`` points) and let the finish
         kernel store logposterior (and x_solved, plan order) straight into buffer ``buf`` of EVERY rank's gather window
         (``distributed.PeerGather``; replaces reference base.py:335 / samplers/base.py:196-200).  ``X``: float64 CUDA tensor (enqueued on the
         current torch stream) or (pinned) host ndarray (staged by the library).  Optional local outputs in ``out``: ``loglikelihood``,
-        ``logprior`` (float64) and ``status`` (int32), CUDA tensors or host ndarrays of length n."""
+        ``logprior`` (float64) and ``status`` (int32), CUDA tensors or host ndarrays of length n.  ``wait``: buffer index whose acquire
+        (``PeerGather.wait``) is enqueued behind this evaluation in the same call (pipelined loops: one library call per step)."""
         import torch
         out = out or {}
         if _is_torch_cuda(X):
@@ -140,7 +141,8 @@ class Plan(object):
             if key not in out: return None
             return out[key].data_ptr() if _is_torch_cuda(out[key]) else out[key].ctypes.data
         _capi.check(self._lib.dlb_eval_batch_gather(self._handle, xptr, X.shape[0], gather._handle, int(buf), int(slice_start),
-                                                    int(total), int(bool(with_solved)), ptr('loglikelihood'), ptr('logprior'), ptr('status'), ctypes.c_void_p(stream)))
+                                                    int(total), int(bool(with_solved)), ptr('loglikelihood'), ptr('logprior'), ptr('status'),
+                                                    -1 if wait is None else int(wait), ctypes.c_void_p(stream)))
 
     def theory(self, X):
         """Flat theory vectors [N, n] at the solved parameters' defaults (reference ``likelihood.flattheory``)."""

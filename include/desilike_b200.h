@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DLB_ABI_VERSION 5
+#define DLB_ABI_VERSION 6
 
 typedef enum {
   DLB_OK = 0,
@@ -217,7 +217,9 @@ int dlb_gather_ipc_handle(const dlb_gather* gather, void* handle /* [DLB_IPC_HAN
 int dlb_gather_connect(dlb_gather* gather, const void* handles /* [world, DLB_IPC_HANDLE_BYTES], rank-major */);
 double* dlb_gather_buffer(dlb_gather* gather, int32_t buf);   /* this rank's copy of buffer `buf` (device pointer, [capacity]) */
 int dlb_eval_batch_gather(dlb_plan* plan, const double* params, int64_t N, dlb_gather* gather, int32_t buf, int64_t slice_start, int64_t total,
-                          int32_t with_solved, double* loglikelihood, double* logprior, int32_t* status, void* stream);
+                          int32_t with_solved, double* loglikelihood, double* logprior, int32_t* status, int32_t wait_buf, void* stream);
+/* wait_buf >= 0: additionally enqueue dlb_gather_wait(gather, wait_buf) behind the evaluation (one call per step of a pipelined loop: the acquire
+ * of the previous step's buffer overlaps this step's NVLink stores). */
 /* Generic form: store src[0 : count] (device) at [offset, offset + count) of buffer `buf` of every rank's window and publish. */
 int dlb_gather_publish(dlb_gather* gather, int32_t buf, const double* src, int64_t count, int64_t offset, void* stream);
 int dlb_gather_wait(dlb_gather* gather, int32_t buf, void* stream);
