@@ -73,6 +73,8 @@ SYMBOLS = {
     'dlb_last_kernel_ms': (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_double_p]),
     'dlb_set_timing': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     'dlb_last_fftlog_ms': (ctypes.c_int, [c_double_p]),
+    'dlb_ozaki_matmul': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                        ctypes.c_void_p]),
     'dlb_gather_create': (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
     'dlb_gather_ipc_handle': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'dlb_gather_connect': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, 'csrc')
 LIBDIR = os.path.join(ROOT, 'lib')
 LIBPATH = os.path.join(LIBDIR, 'libdesilike_b200.so')
-SOURCES = ['plan.cu', 'contract.cu', 'contract_masked.cu', 'features.cu', 'theory_kernels.cu', 'solve.cu', 'peaks.cu', 'sampler.cu', 'mlp.cu', 'gather.cu']
+SOURCES = ['plan.cu', 'contract.cu', 'contract_masked.cu', 'features.cu', 'theory_kernels.cu', 'solve.cu', 'peaks.cu', 'sampler.cu', 'mlp.cu', 'gather.cu', 'ozaki.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC', '-shared',
               '-cudart', 'static']
 

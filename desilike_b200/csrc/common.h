@@ -182,6 +182,15 @@ size_t mlp_fused_smem(const int* idata_host);
 int launch_mlp_fused(const DevGen* d_gens, const int* d_mlp_index, int nmlp, size_t smem, const double* params, int d, long long N, long long npad,
                      double* F, int fstride, int nsm, cudaStream_t stream);
 
+// FP64-grade GEMM on tcgen05 int8 tensor cores (csrc/ozaki.cu): wide MLP hidden layers, opt-in
+size_t ozaki_slice_bytes(long long rows_pad, int K, int ns);
+long long ozaki_rows_pad(long long rows);
+void ozaki_slice_weights(const double* W, int K, int N, int ns, std::vector<int8_t>& slices, std::vector<int>& exps);
+int launch_ozaki_layer(const double* X, long long rows, int K, long long ld, const int8_t* Bslices, const int* Eb, const double* bias, int ncols, int ns, int act,
+                       double* out, long long ldo, int8_t* work_slices, int* work_exps, int nsm, cudaStream_t stream);
+int launch_mlp_small_layer(const double* X, long long rows, int K, long long ld, const double* W, const double* bias, int ncols, int act, double* out, long long ldo,
+                           cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------------------------------------
 // prior + marginalisation solve (csrc/solve.cu)
 // ---------------------------------------------------------------------------------------------------------------------

@@ -1333,6 +1333,30 @@ int dlb_ensemble_step(dlb_plan* plan, double* walkers, double* logposterior, int
   return DLB_OK;
 }
 
+int dlb_ozaki_matmul(const double* X, int64_t rows, int32_t K, const double* W, const double* bias, int32_t N, int32_t slices, int32_t act, double* out) {
+  DLB_REQUIRE(X && W && out && rows > 0 && K > 0 && N > 0, "ozaki matmul: NULL buffer or empty problem");
+  int dev = 0, nsm = 0;
+  DLB_CUDA(cudaGetDevice(&dev));
+  DLB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  std::vector<int8_t> bsl; std::vector<int> beb;
+  ozaki_slice_weights(W, K, N, slices, bsl, beb);
+  const long long rows_pad = ozaki_rows_pad(rows);
+  double *dX = nullptr, *dO = nullptr, *dB = nullptr; int8_t *dBs = nullptr, *dAs = nullptr; int *dEb = nullptr, *dEa = nullptr;
+  struct Free { std::vector<void*> v; ~Free() { for (void* q : v) if (q) cudaFree(q); } } fr;
+  auto alloc = [&](void** ptr, size_t bytes) { cudaError_t e = cudaMalloc(ptr, std::max<size_t>(bytes, 16)); if (e == cudaSuccess) fr.v.push_back(*ptr); return e; };
+  DLB_CUDA(alloc((void**)&dX, (size_t)rows * K * 8)); DLB_CUDA(alloc((void**)&dO, (size_t)rows * N * 8)); DLB_CUDA(alloc((void**)&dB, (size_t)N * 8));
+  DLB_CUDA(alloc((void**)&dBs, bsl.size())); DLB_CUDA(alloc((void**)&dEb, beb.size() * 4));
+  DLB_CUDA(alloc((void**)&dAs, ozaki_slice_bytes(rows_pad, K, slices))); DLB_CUDA(alloc((void**)&dEa, (size_t)rows_pad * 4));
+  DLB_CUDA(cudaMemcpy(dX, X, (size_t)rows * K * 8, cudaMemcpyHostToDevice));
+  if (bias) DLB_CUDA(cudaMemcpy(dB, bias, (size_t)N * 8, cudaMemcpyHostToDevice));
+  DLB_CUDA(cudaMemcpy(dBs, bsl.data(), bsl.size(), cudaMemcpyHostToDevice));
+  DLB_CUDA(cudaMemcpy(dEb, beb.data(), beb.size() * 4, cudaMemcpyHostToDevice));
+  DLB_TRY(launch_ozaki_layer(dX, rows, K, K, dBs, dEb, bias ? dB : nullptr, N, slices, act, dO, N, dAs, dEa, nsm, nullptr));
+  DLB_CUDA(cudaDeviceSynchronize());
+  DLB_CUDA(cudaMemcpy(out, dO, (size_t)rows * N * 8, cudaMemcpyDeviceToHost));
+  return DLB_OK;
+}
+
 int dlb_last_fftlog_ms(double* ms) {
   DLB_REQUIRE(ms, "NULL output");
   return last_fftlog_ms(ms);

@@ -49,3 +49,39 @@ def lower_mlp(gen, theory, defaults):
         D = np.concatenate([c[sl][None, :], np.zeros((1, c[sl].size)), A[:, sl]], axis=0)
         if post is not None: D = D @ f64(post)
         gen.tables[name] = (0, H + 2, D)
+
+
+def ozaki_matmul(X, W, bias=None, slices=6, activation='identity'):
+    """``act(X @ W + bias)`` through the tcgen05 int8 tensor-core path (csrc/ozaki.cu: exact integer slicing, FP64 epilogue) -- the parity entry
+    of the kernels a plan uses for wide MLP hidden layers with ``Plan(..., mlp_slices=...)``.  Host arrays in, host array out."""
+    import ctypes
+    lib = _capi.load()
+    X, W = f64(X), f64(W)
+    out = np.empty((X.shape[0], W.shape[1]))
+    b = f64(bias) if bias is not None else None
+    _capi.check(lib.dlb_ozaki_matmul(X.ctypes.data, X.shape[0], X.shape[1], W.ctypes.data, b.ctypes.data if b is not None else None, W.shape[1], int(slices),
+                                     ACTIVATIONS[activation], out.ctypes.data))
+    return out
+
+
+def ozaki_matmul_reference(X, W, slices=6):
+    """NumPy statement of the same scheme (integer slice products are exact in float64 here): what the kernel must reproduce BIT FOR BIT."""
+    def slice_rows(A):
+        amax = np.max(np.abs(A), axis=1)
+        E = np.where(amax > 0, np.frexp(np.where(amax > 0, amax, 1.))[1] + 1, 0)
+        r = np.ldexp(A, -E[:, None])
+        q = []
+        for _ in range(slices):
+            r = r * 128.
+            qs = np.rint(r)
+            r = r - qs
+            q.append(qs)
+        return np.array(q), E
+    qa, Ea = slice_rows(np.asarray(X, dtype='f8'))
+    qb, Eb = slice_rows(np.ascontiguousarray(np.asarray(W, dtype='f8').T))
+    v = np.zeros((X.shape[0], W.shape[1]))
+    for t in range(slices - 1, -1, -1):
+        acc = np.zeros_like(v)
+        for i in range(t + 1): acc += qa[i] @ qb[t - i].T
+        v = v + acc * 2.**(-7 * (t + 2))
+    return np.ldexp(np.ldexp(v, Ea[:, None]), Eb[None, :])

@@ -227,6 +227,12 @@ int dlb_gather_status(const dlb_gather* gather);   /* 0, or 1 + the first rank a
 int dlb_gather_set_timeout(dlb_gather* gather, double seconds);
 void dlb_gather_destroy(dlb_gather* gather);
 
+/* FP64-grade GEMM on the tcgen05 int8 tensor cores (csrc/ozaki.cu; exact integer slicing, `slices` in [2, 8] signed 7-bit slices per operand):
+ * out [rows, N] = act(X [rows, K] . W [K, N] + bias [N]), act 0 none / 1 silu / 2 relu / 3 tanh; HOST buffers (staged by the call).  The parity /
+ * debug entry of the kernel pair the plan uses for wide MLP hidden layers when dlb_plan_desc::mlp_slices > 0 (reference emulators/conversion.py:
+ * 18-33: v <- act(v @ kernel + bias)). */
+int dlb_ozaki_matmul(const double* X, int64_t rows, int32_t K, const double* W, const double* bias, int32_t N, int32_t slices, int32_t act, double* out);
+
 /* Instrumentation ----------------------------------------------------------------------------------------------- */
 int64_t dlb_launch_count(void);                  /* kernels launched by this library since load (all plans) */
 /* Achieved FP64 rate (TFLOP/s) of a register-resident DMMA.8x8x4 loop (kind 0) or DFMA loop (kind 1) on the current
