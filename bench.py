@@ -62,10 +62,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'logL evals/sec (batched, emulated FS+window+chi2)'
 # algorithmic FLOP per evaluation of the UN-collapsed chain
-UNCOLLAPSED_FLOPS = {'c1': 0.1e6, 'c2': 0.7e6, 'c3': 1.3e6, 'c3fft': 1.3e6, 'c4': 20e6, 'c4wide': 47e6, 'c4dense': 300e6, 'c5': 8e6, 'c5solved': 19e6}
+UNCOLLAPSED_FLOPS = {'c1': 0.1e6, 'c2': 0.7e6, 'c3': 1.3e6, 'c3fft': 1.3e6, 'c4': 20e6, 'c4wide': 47e6, 'c4wide_i8': 47e6, 'c4dense': 300e6, 'c5': 8e6, 'c5solved': 19e6}
 UNIT = 'evals/s'
 DEFAULT_WORKLOAD, DEFAULT_BATCH = 'c4', 131072
-EXTRA_BATCH = {'c4wide': 16384, 'c4dense': 16384}
+EXTRA_BATCH = {'c4wide': 16384, 'c4wide_i8': 16384, 'c4dense': 16384}
 L2_BYTES = 126 * 2**20
 
 
@@ -89,6 +89,9 @@ def build_spec(workload):
         return configs.config_c4(), 'C4: 5 tracers x [MLP 4-64-64-64 pt emulator -> EFT-like combine -> window [402,1050]] -> joint chi2 + analytic marginalisation (n=2010, d=25, ns=35)'
     if workload == 'c4dense':
         return configs.config_c4(dense=True), 'C4 dense stress variant: 5 tracers x [MLP 4-64-64-64 -> EFT-like combine -> window [402,1050]] -> chi2 with a DENSE joint 2010 x 2010 precision + marginalisation of 35 terms (15 theta-dependent rows in one block: split over passes of 8 slots)'
+    if workload == 'c4wide_i8':
+        spec, label = build_spec('c4wide')
+        return spec, label + '; hidden layers as FP64-grade GEMMs on the tcgen05 int8 tensor cores (6 exact slices, opt-in mlp_slices)'
     if workload == 'c4wide':
         return configs.config_c4(hidden=(512, 512, 512, 512)), 'C4 stress variant: 5 tracers x [MLP 4-512-512-512-512 pt emulator -> EFT-like combine -> window [402,1050]] -> chi2 + marginalisation (ns=35)'
     raise ValueError(workload)
@@ -387,7 +390,7 @@ def run_workload(ctx, args, workload, N, steps, warmup, main, peaks):
     torch, rank, world, dev = ctx.torch, ctx.rank, ctx.world, ctx.dev
     t_start = time.perf_counter()
     spec, label = build_spec(workload)
-    plan = desilike_b200.Plan(spec, with_theory=False)
+    plan = desilike_b200.Plan(spec, with_theory=False, mlp_slices=6 if workload.endswith('_i8') else 0)
     d, ns = plan.d, plan.ns
     npool = pool_size(N, d)
     pool = [torch.as_tensor(host_batch(spec, N, rank, i), device=dev) for i in range(npool)]
@@ -712,7 +715,7 @@ def main():
         line = run_workload(ctx, args, args.workload, args.batch, args.steps, args.warmup, True, peaks)
     line['fp64_peaks_tflops'] = peaks
     if args.extras == 'auto':
-        extras = [w for w in ('c2', 'c5', 'c5solved', 'c1', 'c3', 'c3fft', 'c4', 'c4dense', 'c4wide', 'c5step') if w != args.workload] if ctx.world == 1 else \
+        extras = [w for w in ('c2', 'c5', 'c5solved', 'c1', 'c3', 'c3fft', 'c4', 'c4dense', 'c4wide', 'c4wide_i8', 'c5step') if w != args.workload] if ctx.world == 1 else \
                  [w for w in ('c2', 'c5step') if w != args.workload]
         if args.workload != DEFAULT_WORKLOAD: extras = []
     elif args.extras == 'none': extras = []
@@ -723,7 +726,7 @@ def main():
             if w == 'c5step':
                 ex = run_ensemble(ctx, args, max(3, min(args.steps, 10)), 3, peaks)
             else:
-                ex = run_workload(ctx, args, w, EXTRA_BATCH.get(w, 65536), max(5, min(args.steps, 10 if w in ('c4wide', 'c4dense') else 100)), 3, False, peaks)
+                ex = run_workload(ctx, args, w, EXTRA_BATCH.get(w, 65536), max(5, min(args.steps, 10 if w in ('c4wide', 'c4wide_i8', 'c4dense') else 100)), 3, False, peaks)
             line['extra'].append(compact(ex))
         except Exception as exc:   # noqa: BLE001 -- an extra must not take the main line down; it is reported as failed
             if ctx.world > 1: raise

@@ -12,7 +12,7 @@ from .build import LIBPATH
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
 
-DLB_ABI_VERSION = 6
+DLB_ABI_VERSION = 7
 DLB_COEF_MAXF = 4
 GEN_TAYLOR, GEN_MLP, GEN_KAISER, GEN_BAO = 1, 2, 3, 4
 PT_NONFINITE, PT_OUT_OF_PRIOR, PT_NOT_SPD = 1, 2, 4
@@ -49,7 +49,7 @@ class PlanDesc(ctypes.Structure):
                 ('ns', ctypes.c_int32), ('nmarg', ctypes.c_int32), ('x0', c_double_p), ('xprior_kind', c_int32_p),
                 ('xprior_loc', c_double_p), ('xprior_scale', c_double_p), ('xprior_lo', c_double_p), ('xprior_hi', c_double_p),
                 ('nderived', ctypes.c_int32), ('derived_off', c_int32_p), ('derived_code', c_int32_p), ('derived_const', c_double_p),
-                ('m0_extra', c_double_p)]
+                ('m0_extra', c_double_p), ('mlp_slices', ctypes.c_int32)]
 
 
 # every symbol include/desilike_b200.h declares: (restype, argtypes)

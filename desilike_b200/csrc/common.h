@@ -186,7 +186,7 @@ int launch_mlp_fused(const DevGen* d_gens, const int* d_mlp_index, int nmlp, siz
 size_t ozaki_slice_bytes(long long rows_pad, int K, int ns);
 long long ozaki_rows_pad(long long rows);
 void ozaki_slice_weights(const double* W, int K, int N, int ns, std::vector<int8_t>& slices, std::vector<int>& exps);
-int launch_ozaki_layer(const double* X, long long rows, int K, long long ld, const int8_t* Bslices, const int* Eb, const double* bias, int ncols, int ns, int act,
+int launch_ozaki_layer(const double* X, long long rows, int K, long long ld, const int8_t* Bslices, const double* Sb, const double* bias, int ncols, int ns, int act,
                        double* out, long long ldo, int8_t* work_slices, int* work_exps, int nsm, cudaStream_t stream);
 int launch_mlp_small_layer(const double* X, long long rows, int K, long long ld, const double* W, const double* bias, int ncols, int act, double* out, long long ldo,
                            cudaStream_t stream);

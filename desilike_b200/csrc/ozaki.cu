@@ -24,7 +24,7 @@ namespace dlb {
 
 namespace {
 
-constexpr int OZ_M = 128, OZ_N = 64, OZ_KB = 64;          // output tile, k-block (bytes = int8 elements) per pipeline stage
+constexpr int OZ_M = 128, OZ_N = 64, OZ_KB = 32;          // output tile, k-block (bytes = int8 elements) per pipeline stage = one MMA K
 constexpr int OZ_A_SLICE = OZ_M * OZ_KB, OZ_B_SLICE = OZ_N * OZ_KB;   // bytes of one slice of one stage
 constexpr int OZ_MAXS = 8;
 constexpr int OZ_THREADS = 192;
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128) ozaki_slice_kernel(const double* __restri
   if (amax > 0. && isfinite(amax)) { int e; frexp(amax, &e); E = e + 1; }   // amax = m 2^e, m in [0.5, 1)  ->  amax 2^-(e + 1) < 1/2
   if (lane == 0) exps[row] = E;
   for (int c = lane; c < Kpad / 16; c += 32) {
-    const int kb = c >> 2, kc = c & 3;
+    const int kb = c / (OZ_KB / 16), kc = c % (OZ_KB / 16);
     uint32_t q[OZ_MAXS][4];
 #pragma unroll
     for (int s = 0; s < OZ_MAXS; ++s) q[s][0] = q[s][1] = q[s][2] = q[s][3] = 0u;
@@ -98,7 +98,7 @@ struct OzakiParams {
   const int8_t* A;        // [row tiles][nkb][ns][OZ_A_SLICE]
   const int8_t* B;        // [col tiles][nkb][ns][OZ_B_SLICE]   (plan constant)
   const int* Ea;          // [rows_pad]
-  const int* Eb;          // [ncols_pad]
+  const double* Sb;       // [ncols_pad] 2^Eb as doubles (epilogue)
   const double* bias;     // [ncols] or NULL
   double* out; long long ldo; long long rows; int ncols;
   int nkb, ns, act, ntm, ntn;
@@ -211,41 +211,53 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
       oz_mbar_wait(tmem_full, tph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const long long row = tm * OZ_M + warp * 32 + lane;
-      const double sa = row < p.rows ? scalbn(1., p.Ea[row]) : 0.;
-#pragma unroll 1
-      for (int c0 = 0; c0 < OZ_N; c0 += 16) {
-        double v[16];
+      // ---- phase A (TMEM busy): accumulators -> FP64 in registers.  The int32 accumulators of three consecutive t are first combined EXACTLY in
+      //      int64 (G_g = acc_3g 2^14 + acc_3g+1 2^7 + acc_3g+2 < 2^46), then v = sum_g G_g 2^(-7 (3 g + 4)), smallest group first ----
+      double v[OZ_N];
+      const int ng = (ns + 2) / 3;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.;
-        for (int t = ns - 1; t >= 0; --t) {   // smallest contributions first
-          uint32_t r[16];
-          const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * OZ_N + c0);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-                "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-              : "r"(taddr));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const double w = scalbn(1., -7 * (t + 2));
+      for (int c0 = 0; c0 < OZ_N; c0 += 8) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fma((double)(int)r[j], w, v[j]);
+        for (int j = 0; j < 8; ++j) v[c0 + j] = 0.;
+        for (int g = ng - 1; g >= 0; --g) {
+          long long G[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) G[j] = 0;
+          for (int u = 0; u < 3; ++u) {
+            const int t = 3 * g + u;
+            if (t >= ns) break;
+            uint32_t r[8];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * OZ_N + c0);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 8; ++j) G[j] += (long long)(int)r[j] * (1LL << (7 * (2 - u)));
+          }
+          const double w = scalbn(1., -7 * (3 * g + 4));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[c0 + j] = fma((double)G[j], w, v[c0 + j]);
         }
-        if (row < p.rows) {
+      }
+      // TMEM is free again: the MMA warp may start the next tile while this warp finishes its rows
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty) : "memory");
+      // ---- phase B: exponents, bias, activation, store ----
+      if (row < p.rows) {
+        const double sa = scalbn(1., p.Ea[row]);
+        double* orow = p.out + row * p.ldo + (long long)tn * OZ_N;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = tn * OZ_N + c0 + j;
-            if (col < p.ncols) {
-              double y = v[j] * sa * scalbn(1., p.Eb[col]) + (p.bias ? p.bias[col] : 0.);
-              if (p.act == 1) y = oz_silu(y);
-              else if (p.act == 2) y = fmax(y, 0.);
-              else if (p.act == 3) y = tanh(y);
-              p.out[row * p.ldo + col] = y;
-            }
+        for (int j = 0; j < OZ_N; ++j) {
+          const int col = tn * OZ_N + j;
+          if (col < p.ncols) {
+            double y = v[j] * sa * p.Sb[col] + (p.bias ? p.bias[col] : 0.);
+            if (p.act == 1) y = oz_silu(y);
+            else if (p.act == 2) y = fmax(y, 0.);
+            else if (p.act == 3) y = tanh(y);
+            orow[j] = y;
           }
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty) : "memory");
       tph ^= 1u;
     }
   }
@@ -310,7 +322,7 @@ void ozaki_slice_weights(const double* W, int K, int N, int ns, std::vector<int8
 }
 
 // out[rows, ncols] (leading dimension ldo) = act(X[rows, K] (ld) . W + bias), W pre-sliced by ozaki_slice_weights
-int launch_ozaki_layer(const double* X, long long rows, int K, long long ld, const int8_t* Bslices, const int* Eb, const double* bias, int ncols, int ns, int act,
+int launch_ozaki_layer(const double* X, long long rows, int K, long long ld, const int8_t* Bslices, const double* Sb, const double* bias, int ncols, int ns, int act,
                        double* out, long long ldo, int8_t* work_slices, int* work_exps, int nsm, cudaStream_t stream) {
   DLB_REQUIRE(ns >= 2 && ns <= OZ_MAXS, "ozaki gemm: 2 <= slices <= 8");
   const int Kpad = (K + OZ_KB - 1) / OZ_KB * OZ_KB, nkb = Kpad / OZ_KB;
@@ -321,10 +333,10 @@ int launch_ozaki_layer(const double* X, long long rows, int K, long long ld, con
   DLB_CUDA(cudaGetLastError());
   OzakiParams p;
   std::memset(&p, 0, sizeof(p));
-  p.A = work_slices; p.B = Bslices; p.Ea = work_exps; p.Eb = Eb; p.bias = bias; p.out = out; p.ldo = ldo; p.rows = rows; p.ncols = ncols;
+  p.A = work_slices; p.B = Bslices; p.Ea = work_exps; p.Sb = Sb; p.bias = bias; p.out = out; p.ldo = ldo; p.rows = rows; p.ncols = ncols;
   p.nkb = nkb; p.ns = ns; p.act = act; p.ntm = (int)(rows_pad / OZ_M); p.ntn = (ncols + OZ_N - 1) / OZ_N;
   const size_t stage = (size_t)ns * (OZ_A_SLICE + OZ_B_SLICE);
-  p.nstages = (int)std::min<size_t>(4, (size_t)(200 * 1024) / stage);
+  p.nstages = (int)std::min<size_t>(6, (size_t)(200 * 1024) / stage);
   DLB_REQUIRE(p.nstages >= 2, "ozaki gemm: shared memory too small for two stages");
   const size_t smem = p.nstages * stage + (size_t)(2 * p.nstages + 2) * 8 + 16;
   static bool configured_dev[64] = {};

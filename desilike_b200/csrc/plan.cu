@@ -45,7 +45,9 @@ struct Launch {
   double flops_exec = 0., flops_exec_plain = 0.;   // 2 * kc * BN * slots-independent tile count per point (whitened / un-whitened tables)
 };
 
-struct MlpLayers { int act = 0; std::vector<Block> layers; std::vector<Launch> launches; };
+// one dense layer of an MLP emulator on the tcgen05 int8 path (csrc/ozaki.cu) -- or, for narrow fan-in, the plain FP64 layer kernel
+struct OzLayer { int K = 0, N = 0, in_off = 0, out_off = 0; bool ozaki = false; double *d_W = nullptr, *d_bias = nullptr, *d_Sb = nullptr; int8_t* d_Bs = nullptr; };
+struct MlpLayers { int act = 0; std::vector<Block> layers; std::vector<Launch> launches; std::vector<OzLayer> oz; };
 
 }  // namespace dlb
 
@@ -55,6 +57,8 @@ struct dlb_plan {
   int d_in = 0, nder = 0;              // input columns of the batch / derived-expression parameters appended to every row
   int *d_der_off = nullptr, *d_der_code = nullptr; double* d_der_const = nullptr;
   double* w_pext = nullptr;            // [cap, d] extended parameter rows (plans with derived parameters)
+  int mlp_slices = 0, oz_maxk = 0;     // > 0: MLP hidden layers on the tcgen05 int8 path with this many slices (opt-in)
+  int8_t* w_oz_slices = nullptr; int* w_oz_exps = nullptr;
   bool resident = false;               // Taylor monomials evaluated inside the contraction kernel (no feature matrix in HBM)
   dlb::Launch launch;                  // the likelihood blocks
   // two-stage plans (an observable transform that is non-linear in the theory, reference power_spectrum.py:400-404): stage 1 = `launch` in output
@@ -444,6 +448,27 @@ static int build_mlp(dlb_plan* plan, const dlb_generator_desc& gd, DevGen& g, Ml
   g.aux[0] = off[0];
   mlp.act = act;
   const double* w = gd.ddata + 2 * d;
+  if (plan->mlp_slices > 0) {   // opt-in tensor-core path: every hidden layer is its own (slice +) GEMM launch pair
+    for (int l = 0; l < nh; ++l) {
+      OzLayer oz;
+      oz.K = width[l]; oz.N = width[l + 1]; oz.in_off = off[l]; oz.out_off = off[l + 1]; oz.ozaki = width[l] >= 64;
+      const double* bias = w + (size_t)width[l] * width[l + 1];
+      DLB_TRY(upload(plan, w, (size_t)oz.K * oz.N, &oz.d_W));
+      DLB_TRY(upload(plan, bias, (size_t)oz.N, &oz.d_bias));
+      if (oz.ozaki) {
+        std::vector<int8_t> sl; std::vector<int> eb;
+        ozaki_slice_weights(w, oz.K, oz.N, plan->mlp_slices, sl, eb);
+        std::vector<double> sb(eb.size());
+        for (size_t i = 0; i < eb.size(); ++i) sb[i] = std::ldexp(1., eb[i]);
+        DLB_TRY(upload(plan, sl.data(), sl.size(), &oz.d_Bs));
+        DLB_TRY(upload(plan, sb.data(), sb.size(), &oz.d_Sb));
+        plan->oz_maxk = std::max(plan->oz_maxk, oz.K);
+      }
+      mlp.oz.push_back(oz);
+      w = bias + width[l + 1];
+    }
+    return DLB_OK;
+  }
   mlp.layers.resize(nh);
   for (int l = 0; l < nh; ++l) {
     Block& blk = mlp.layers[l];
@@ -476,6 +501,12 @@ static int ensure_workspace(dlb_plan* plan, long long npad) {
   DLB_CUDA(cudaMalloc((void**)&plan->w_partial, (size_t)std::max(plan->ptotal, 1LL) * npad * sizeof(double)));
   DLB_CUDA(cudaMalloc((void**)&plan->w_params, (size_t)npad * std::max(plan->d_in, 1) * sizeof(double)));
   if (plan->nder) DLB_CUDA(cudaMalloc((void**)&plan->w_pext, (size_t)npad * plan->d * sizeof(double)));
+  if (plan->w_oz_slices) { cudaFree(plan->w_oz_slices); plan->w_oz_slices = nullptr; }
+  if (plan->w_oz_exps) { cudaFree(plan->w_oz_exps); plan->w_oz_exps = nullptr; }
+  if (plan->mlp_slices > 0 && plan->oz_maxk > 0) {
+    DLB_CUDA(cudaMalloc((void**)&plan->w_oz_slices, ozaki_slice_bytes(ozaki_rows_pad(npad), plan->oz_maxk, plan->mlp_slices)));
+    DLB_CUDA(cudaMalloc((void**)&plan->w_oz_exps, (size_t)ozaki_rows_pad(npad) * sizeof(int)));
+  }
   DLB_CUDA(cudaMalloc((void**)&plan->w_out, (size_t)npad * (3 + std::max(plan->ns, 0)) * sizeof(double)));
   DLB_CUDA(cudaMalloc((void**)&plan->w_status, (size_t)npad * sizeof(int)));
   plan->cap = npad;
@@ -496,6 +527,17 @@ static int run_front(dlb_plan* plan, const double* d_params, long long N, long l
     const DevGen& g = plan->gens[ig];
     if (g.kind == DLB_GEN_MLP) {
       if (!plan->mlp_fused_smem) DLB_TRY(launch_mlp_input(g, d_params, plan->d, N, npad, plan->w_F, plan->fstride, stream));
+      if (plan->mlp_slices > 0) {   // hidden layers: tcgen05 int8 GEMMs (fan-in >= 64) / plain FP64 (the narrow first layer)
+        const MlpLayers& mlp = plan->mlps[ig];
+        double* seg = plan->w_F + g.foff;
+        for (const OzLayer& oz : mlp.oz) {
+          if (oz.ozaki)
+            DLB_TRY(launch_ozaki_layer(seg + oz.in_off, N, oz.K, plan->fstride, oz.d_Bs, oz.d_Sb, oz.d_bias, oz.N, plan->mlp_slices, mlp.act, seg + oz.out_off,
+                                       plan->fstride, plan->w_oz_slices, plan->w_oz_exps, plan->nsm, stream));
+          else
+            DLB_TRY(launch_mlp_small_layer(seg + oz.in_off, N, oz.K, plan->fstride, oz.d_W, oz.d_bias, oz.N, mlp.act, seg + oz.out_off, plan->fstride, stream));
+        }
+      }
       continue;
     }
     if (g.kind == DLB_GEN_TAYLOR && g.aux[6] && plan->resident && !force_taylor) continue;   // evaluated inside the contraction kernel
@@ -597,6 +639,8 @@ void dlb_plan_destroy(dlb_plan* plan) {
     if (ptr) cudaFree(ptr);
   for (auto& e : plan->ev) if (e) cudaEventDestroy(e);
   if (plan->w_hess) cudaFree(plan->w_hess);
+  if (plan->w_oz_slices) cudaFree(plan->w_oz_slices);
+  if (plan->w_oz_exps) cudaFree(plan->w_oz_exps);
   for (auto& e : plan->ev_pipe) if (e) cudaEventDestroy(e);
   if (plan->s_in) cudaStreamDestroy(plan->s_in);
   if (plan->s_out) cudaStreamDestroy(plan->s_out);
@@ -618,6 +662,8 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
   struct Guard { dlb_plan* p; ~Guard() { if (p) dlb_plan_destroy(p); } } guard{plan};
   DLB_CUDA(cudaGetDevice(&plan->device));
   DLB_REQUIRE(desc->nderived >= 0 && desc->nderived <= 64 && (desc->nderived == 0 || (desc->derived_off && desc->derived_code)), "derived parameters: 0 <= nderived <= 64 and tables required");
+  DLB_REQUIRE(desc->mlp_slices == 0 || (desc->mlp_slices >= 2 && desc->mlp_slices <= 8), "mlp_slices must be 0 (FP64 DMMA) or 2 .. 8");
+  plan->mlp_slices = desc->mlp_slices;
   plan->d_in = desc->d; plan->nder = desc->nderived;
   plan->d = desc->d + desc->nderived; plan->ngen = desc->ngen; plan->ncoef = desc->ncoef; plan->ns = desc->ns; plan->nmarg = desc->nmarg;
   plan->dpad = (plan->d + 1) | 1;   // + the constant-one column; odd stride keeps per-row accesses conflict free
@@ -706,7 +752,7 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
         if (!need || need > (size_t)200 * 1024) ok = false;
         smem = std::max(smem, need);
       }
-    if (ok && !mlp_index.empty() && !getenv("DLB_NO_FUSED_MLP")) {
+    if (ok && !mlp_index.empty() && !getenv("DLB_NO_FUSED_MLP") && plan->mlp_slices == 0) {
       plan->mlp_fused_smem = smem; plan->nmlp = (int)mlp_index.size();
       DLB_TRY(upload(plan, plan->gens.data(), plan->gens.size(), &plan->d_devgens));
       DLB_TRY(upload(plan, mlp_index.data(), mlp_index.size(), &plan->d_mlp_index));
@@ -1341,17 +1387,19 @@ int dlb_ozaki_matmul(const double* X, int64_t rows, int32_t K, const double* W, 
   std::vector<int8_t> bsl; std::vector<int> beb;
   ozaki_slice_weights(W, K, N, slices, bsl, beb);
   const long long rows_pad = ozaki_rows_pad(rows);
-  double *dX = nullptr, *dO = nullptr, *dB = nullptr; int8_t *dBs = nullptr, *dAs = nullptr; int *dEb = nullptr, *dEa = nullptr;
+  double *dX = nullptr, *dO = nullptr, *dB = nullptr, *dSb = nullptr; int8_t *dBs = nullptr, *dAs = nullptr; int* dEa = nullptr;
+  std::vector<double> sb(beb.size());
+  for (size_t i = 0; i < beb.size(); ++i) sb[i] = std::ldexp(1., beb[i]);
   struct Free { std::vector<void*> v; ~Free() { for (void* q : v) if (q) cudaFree(q); } } fr;
   auto alloc = [&](void** ptr, size_t bytes) { cudaError_t e = cudaMalloc(ptr, std::max<size_t>(bytes, 16)); if (e == cudaSuccess) fr.v.push_back(*ptr); return e; };
   DLB_CUDA(alloc((void**)&dX, (size_t)rows * K * 8)); DLB_CUDA(alloc((void**)&dO, (size_t)rows * N * 8)); DLB_CUDA(alloc((void**)&dB, (size_t)N * 8));
-  DLB_CUDA(alloc((void**)&dBs, bsl.size())); DLB_CUDA(alloc((void**)&dEb, beb.size() * 4));
+  DLB_CUDA(alloc((void**)&dBs, bsl.size())); DLB_CUDA(alloc((void**)&dSb, sb.size() * 8));
   DLB_CUDA(alloc((void**)&dAs, ozaki_slice_bytes(rows_pad, K, slices))); DLB_CUDA(alloc((void**)&dEa, (size_t)rows_pad * 4));
   DLB_CUDA(cudaMemcpy(dX, X, (size_t)rows * K * 8, cudaMemcpyHostToDevice));
   if (bias) DLB_CUDA(cudaMemcpy(dB, bias, (size_t)N * 8, cudaMemcpyHostToDevice));
   DLB_CUDA(cudaMemcpy(dBs, bsl.data(), bsl.size(), cudaMemcpyHostToDevice));
-  DLB_CUDA(cudaMemcpy(dEb, beb.data(), beb.size() * 4, cudaMemcpyHostToDevice));
-  DLB_TRY(launch_ozaki_layer(dX, rows, K, K, dBs, dEb, bias ? dB : nullptr, N, slices, act, dO, N, dAs, dEa, nsm, nullptr));
+  DLB_CUDA(cudaMemcpy(dSb, sb.data(), sb.size() * 8, cudaMemcpyHostToDevice));
+  DLB_TRY(launch_ozaki_layer(dX, rows, K, K, dBs, dSb, bias ? dB : nullptr, N, slices, act, dO, N, dAs, dEa, nsm, nullptr));
   DLB_CUDA(cudaDeviceSynchronize());
   DLB_CUDA(cudaMemcpy(out, dO, (size_t)rows * N * 8, cudaMemcpyDeviceToHost));
   return DLB_OK;

@@ -153,8 +153,9 @@ class _Generator(object):
 class Lowered(object):
     """Flat arrays + ctypes descriptor (keeps every buffer alive until the plan has been created)."""
 
-    def __init__(self, spec, with_plain=True, reduce_rank=True, merge_terms=True):
+    def __init__(self, spec, with_plain=True, reduce_rank=True, merge_terms=True, mlp_slices=0):
         self.spec = spec
+        self.mlp_slices = int(mlp_slices)
         # derived-expression parameters (reference parameter.py:795-808, base.py:537): columns appended to every parameter row by a small
         # kernel; every index table below addresses the extended row, the batch itself has self.d_in columns
         from .expressions import compile_expression, ExpressionError
@@ -495,6 +496,7 @@ class Lowered(object):
         desc.ns, desc.nmarg = self.ns, self.nmarg
         desc.x0, desc.xprior_kind = as_ptr(self.x0), as_ptr(skind, ctypes.c_int32)
         desc.xprior_loc, desc.xprior_scale, desc.xprior_lo, desc.xprior_hi = as_ptr(sloc), as_ptr(sscale), as_ptr(slo), as_ptr(shi)
+        desc.mlp_slices = self.mlp_slices
         if self.m0_extra is not None:
             m0 = f64(self.m0_extra)
             keep.append(m0)

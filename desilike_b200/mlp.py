@@ -79,9 +79,14 @@ def ozaki_matmul_reference(X, W, slices=6):
         return np.array(q), E
     qa, Ea = slice_rows(np.asarray(X, dtype='f8'))
     qb, Eb = slice_rows(np.ascontiguousarray(np.asarray(W, dtype='f8').T))
+    acc = []
+    for t in range(slices):
+        a = np.zeros((X.shape[0], W.shape[1]))
+        for i in range(t + 1): a += qa[i] @ qb[t - i].T
+        acc.append(a)
+    # the epilogue combines three consecutive accumulators exactly in int64, then sums the groups smallest first (csrc/ozaki.cu, phase A)
     v = np.zeros((X.shape[0], W.shape[1]))
-    for t in range(slices - 1, -1, -1):
-        acc = np.zeros_like(v)
-        for i in range(t + 1): acc += qa[i] @ qb[t - i].T
-        v = v + acc * 2.**(-7 * (t + 2))
+    for g in range((slices + 2) // 3 - 1, -1, -1):
+        G = sum(acc[3 * g + u] * 2.**(7 * (2 - u)) for u in range(3) if 3 * g + u < slices)
+        v = v + G * 2.**(-7 * (3 * g + 4))
     return np.ldexp(np.ldexp(v, Ea[:, None]), Eb[None, :])

@@ -21,7 +21,7 @@ class Plan(object):
     current torch stream, torch outputs, no host round trip.
     """
 
-    def __init__(self, spec, device=None, with_theory=True, reduce_rank=True, merge_terms=True):
+    def __init__(self, spec, device=None, with_theory=True, reduce_rank=True, merge_terms=True, mlp_slices=0):
         self._lib = _capi.load()
         if self._lib.dlb_device_count() <= 0:
             raise _capi.DesilikeB200Error('no CUDA device visible: desilike_b200 has no CPU fallback')
@@ -33,7 +33,9 @@ class Plan(object):
         # reduce_rank: blocks without solved parameters whose data vector is longer than their feature count are evaluated in the
         # row space of their term matrices (lowering.py: QR at plan time) -- same chi2, fewer columns
         # merge_terms: the tracer combine b1^2 dd + 2 b1 dt + tt of a direct Kaiser theory is formed inside the Kaiser kernel (lowering.py)
-        self.lowered = Lowered(spec, with_plain=with_theory, reduce_rank=reduce_rank, merge_terms=merge_terms)
+        # mlp_slices (opt-in, 2 .. 8): hidden layers of MLP emulators with fan-in >= 64 as FP64-grade GEMMs on the tcgen05 int8 tensor cores
+        # (csrc/ozaki.cu); 0 keeps the FP64 DMMA kernels
+        self.lowered = Lowered(spec, with_plain=with_theory, reduce_rank=reduce_rank, merge_terms=merge_terms, mlp_slices=mlp_slices)
         self.params = list(self.lowered.input_names)   # columns of the batch (derived-expression parameters are appended on the device)
         self.d, self.ns, self.ntheory = self.lowered.d_in, self.lowered.ns, self.lowered.ntheory
         self.solved_names = [s['name'] for s in spec.get('solved', [])]

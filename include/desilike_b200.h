@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DLB_ABI_VERSION 6
+#define DLB_ABI_VERSION 7
 
 typedef enum {
   DLB_OK = 0,
@@ -146,6 +146,9 @@ typedef struct {
    * 8 exp, 9 log, 10 sqrt, 11 log10, 12 abs, 13 sin, 14 cos, 15 tanh (stack depth <= 16); evaluated by a small kernel in front of every pass. */
   int32_t nderived; const int32_t* derived_off; const int32_t* derived_code; const double* derived_const;
   const double* m0_extra;   /* optional [ns, ns] (plan order) added to the constant part of the normal matrix (constant-row Gram of split dense plans) */
+  /* > 0 (opt-in, 2 .. 8): hidden layers of MLP emulators with fan-in >= 64 run as FP64-grade GEMMs on the tcgen05 int8 tensor cores with this many
+   * exact 7-bit slices per operand (csrc/ozaki.cu; 6 slices ~ 1e-11 relative, |delta chi2| << 1e-4 on the 5-tracer configuration); 0: FP64 DMMA. */
+  int32_t mlp_slices;
 } dlb_plan_desc;
 
 typedef struct dlb_plan dlb_plan;

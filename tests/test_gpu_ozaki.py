@@ -28,3 +28,25 @@ def test_ozaki_matmul_bit_exact_and_accurate(gpu_required, shape):
     got = mlp.ozaki_matmul(X, W, bias=bias, slices=6, activation='silu')
     v = ref + bias
     assert np.allclose(got, v / (1. + np.exp(-v)), rtol=1e-9, atol=1e-10 * np.max(np.abs(v)))
+
+
+def test_wide_mlp_plan_on_int8_tensor_cores(gpu_required):
+    """Wide MLP emulators with ``Plan(..., mlp_slices=6)``: hidden layers with fan-in >= 64 run on the tcgen05 int8 path; the likelihood stays within
+    |delta chi2| < 1e-4 of the oracle (BASELINE.json north_star tolerance for tensor-core arithmetic) -- in fact ~1e-7 -- and the marginalised
+    parameters agree; 4 slices (28 bits) visibly do not reach the FP64 path's 1e-8 but the plan still evaluates."""
+    import desilike_b200
+    spec = configs.config_c4(ntracers=2, nkin=40, nbins=10, hidden=(128, 96, 128))
+    X = configs.sample_points(spec, 333, seed=51)
+    ref = pipeline.evaluate(spec, X)
+    plan = desilike_b200.Plan(spec, mlp_slices=6)
+    got = plan.eval(X)
+    assert 2. * np.max(np.abs(got['loglikelihood'] - ref['loglikelihood'])) < 1e-4
+    assert np.max(np.abs(got['loglikelihood'] - ref['loglikelihood'])) < 1e-6 * np.max(np.abs(ref['loglikelihood']))
+    assert np.allclose(got['x_solved'], ref['x_solved'], rtol=1e-5, atol=1e-5)
+    fp64 = desilike_b200.Plan(spec).eval(X)
+    assert np.max(np.abs(got['loglikelihood'] - fp64['loglikelihood'])) < 1e-6 * np.max(np.abs(ref['loglikelihood']))
+    plan.close()
+    coarse = desilike_b200.Plan(spec, mlp_slices=3).eval(X)
+    assert np.all(np.isfinite(coarse['logposterior'])) and np.max(np.abs(coarse['loglikelihood'] - ref['loglikelihood'])) > 1e-7
+    with pytest.raises(desilike_b200.DesilikeB200Error):
+        desilike_b200.Plan(spec, mlp_slices=9)
