@@ -12,7 +12,7 @@ from .build import LIBPATH
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
 
-DLB_ABI_VERSION = 7
+DLB_ABI_VERSION = 8
 DLB_COEF_MAXF = 4
 GEN_TAYLOR, GEN_MLP, GEN_KAISER, GEN_BAO = 1, 2, 3, 4
 PT_NONFINITE, PT_OUT_OF_PRIOR, PT_NOT_SPD = 1, 2, 4
@@ -61,6 +61,7 @@ SYMBOLS = {
     'dlb_plan_destroy': (None, [ctypes.c_void_p]),
     'dlb_plan_ntheory': (ctypes.c_int, [ctypes.c_void_p]),
     'dlb_plan_nsolved': (ctypes.c_int, [ctypes.c_void_p]),
+    'dlb_plan_flags': (ctypes.c_int, [ctypes.c_void_p]),
     'dlb_plan_executed_flops': (ctypes.c_double, [ctypes.c_void_p]),
     'dlb_eval_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 5 + [ctypes.c_void_p]),
     'dlb_eval_batch_hessian': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 6 + [ctypes.c_void_p]),

@@ -188,6 +188,20 @@ long long ozaki_rows_pad(long long rows);
 void ozaki_slice_weights(const double* W, int K, int N, int ns, std::vector<int8_t>& slices, std::vector<int>& exps);
 int launch_ozaki_layer(const double* X, long long rows, int K, long long ld, const int8_t* Bslices, const double* Sb, const double* bias, int ncols, int ns, int act,
                        double* out, long long ldo, int8_t* work_slices, int* work_exps, int nsm, cudaStream_t stream);
+int launch_ozaki_slice(const double* X, long long rows, int K, long long ld, int ns, int8_t* work_slices, int* work_exps, cudaStream_t stream);
+int launch_ozaki_gemm(long long rows, int K, const int8_t* Aslices, const int* Ea, const int8_t* Bslices, const double* Sb, const double* bias, int ncols, int ns, int act,
+                      double* out, long long ldo, int nsm, cudaStream_t stream);
+constexpr int OZ_GRAM_MAXT = 16;
+struct OzakiGramParams {   // chi2 / normal-equation reduction of a GEMM output D[point, term * ncolx + col] (csrc/ozaki.cu: ozaki_gram_kernel)
+  const double* D; long long ldD; long long N, npad;
+  const double* params; int d;
+  const DevCoef* coefs;
+  int nterms, ncols, nconst, ncolx, R;
+  int tslot[OZ_GRAM_MAXT], tcoef[OZ_GRAM_MAXT];
+  const double* r0;        // [ncolx] whitened data over the data columns, r0 . g_i over the auxiliary columns
+  double* partial; long long poff;
+};
+int launch_ozaki_gram(const OzakiGramParams& p, cudaStream_t stream);
 int launch_mlp_small_layer(const double* X, long long rows, int K, long long ld, const double* W, const double* bias, int ncols, int act, double* out, long long ldo,
                            cudaStream_t stream);
 

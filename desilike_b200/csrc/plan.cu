@@ -15,8 +15,19 @@ static thread_local std::string g_error;
 std::atomic<long long> g_launches{0};
 void set_error(const std::string& msg) { g_error = msg; }
 
+// A likelihood block whose terms all read the SAME wide feature segment (the last hidden layer of a wide MLP emulator) evaluated on the tcgen05 int8
+// path (opt-in, dlb_plan_desc::mlp_slices): ONE FP64-grade GEMM D[point, term, column] = features . [M_1 | M_2 | ...] (csrc/ozaki.cu), then
+// ozaki_gram_kernel forms the slot values from the per-point bias coefficients and reduces them to the Gram partials of contract_kernel's layout.
+struct OzContract {
+  bool on = false;
+  int K = 0, fcol = 0, nterms = 0, ncols = 0, nconst = 0, ncolx = 0, ldD = 0, R = 1;
+  int tslot[OZ_GRAM_MAXT], tcoef[OZ_GRAM_MAXT];
+  int8_t* d_Bs = nullptr; double *d_Sb = nullptr, *d_r0 = nullptr;
+};
+
 struct Block {
   Variant var;
+  OzContract oz;
   int ncols = 0, nslots = 1, nconst = 0, ncb = 0, nchunks = 0, npart = 0, coloff = 0, gen = -1, maxcol = 0;
   std::vector<Chunk> h_chunks;
   int* d_cb_first = nullptr; std::vector<int> cb_first;   // whitened tiles: first non-zero k-chunk per column block
@@ -59,6 +70,7 @@ struct dlb_plan {
   double* w_pext = nullptr;            // [cap, d] extended parameter rows (plans with derived parameters)
   int mlp_slices = 0, oz_maxk = 0;     // > 0: MLP hidden layers on the tcgen05 int8 path with this many slices (opt-in)
   int8_t* w_oz_slices = nullptr; int* w_oz_exps = nullptr;
+  bool oz_contract = false; int oz_ldD = 0; double* w_oz_D = nullptr;   // every likelihood block runs as a tcgen05 GEMM + ozaki_gram_kernel
   bool resident = false;               // Taylor monomials evaluated inside the contraction kernel (no feature matrix in HBM)
   dlb::Launch launch;                  // the likelihood blocks
   // two-stage plans (an observable transform that is non-linear in the theory, reference power_spectrum.py:400-404): stage 1 = `launch` in output
@@ -328,6 +340,48 @@ static int build_block(dlb_plan* plan, const dlb_plan_desc* desc, const dlb_bloc
                              bd.matrices_plain ? bd.matrices_plain + td.moff_plain : nullptr});
   }
   DLB_TRY(build_block_core(plan, var, plan->resident, bd.ncols, bd.nslots, terms, bd.r0_white, bd.t0_plain, bd.nconst, bd.gconst_white, blk, bd.ncols_white));
+  // (features computed by their own kernels into F: everything except Taylor monomials evaluated inside the contraction kernel)
+  if (plan->mlp_slices > 0 && !(plan->resident && plan->gens[blk.gen].aux[6]) && !bd.transform_data && !getenv("DLB_NO_OZAKI_CONTRACT")) {
+    // eligible: every term contracts the same feature columns, long enough for the GEMM to beat the D round trip through HBM
+    bool same = bd.nterms <= OZ_GRAM_MAXT && terms[0].K >= 128 && bd.nconst <= 8;
+    for (const TermSpec& td : terms) same = same && td.fcol == terms[0].fcol && td.K == terms[0].K && td.white;
+    if (same) {
+      OzContract& oz = blk.oz;
+      oz.on = true; oz.K = terms[0].K; oz.fcol = terms[0].fcol; oz.nterms = bd.nterms; oz.ncols = blk.ncols_w; oz.nconst = bd.nconst;
+      oz.ncolx = (oz.ncols + oz.nconst + 1) & ~1; oz.R = bd.nslots;   // even: the Gram kernel reads column pairs
+      const int ncolsD = oz.nterms * oz.ncolx;
+      oz.ldD = (ncolsD + 63) / 64 * 64;
+      std::vector<double> B((size_t)oz.K * ncolsD, 0.);
+      for (int t = 0; t < oz.nterms; ++t) {
+        oz.tslot[t] = terms[t].slot; oz.tcoef[t] = terms[t].coef;
+        const double* mat = terms[t].white;
+        for (int k = 0; k < oz.K; ++k) {
+          double* dst = B.data() + (size_t)k * ncolsD + (size_t)t * oz.ncolx;
+          for (int c = 0; c < oz.ncols; ++c) dst[c] = mat[(size_t)k * oz.ncols + c];
+          for (int i = 0; i < oz.nconst; ++i) {   // auxiliary columns (M_t g_i), as in build_block_core
+            const double* g = bd.gconst_white + (size_t)i * oz.ncols;
+            double acc = 0.;
+            for (int c = 0; c < oz.ncols; ++c) acc += mat[(size_t)k * oz.ncols + c] * g[c];
+            dst[oz.ncols + i] = acc;
+          }
+        }
+      }
+      std::vector<int8_t> sl; std::vector<int> eb;
+      ozaki_slice_weights(B.data(), oz.K, ncolsD, plan->mlp_slices, sl, eb);
+      std::vector<double> sb(eb.size());
+      for (size_t i = 0; i < eb.size(); ++i) sb[i] = std::ldexp(1., eb[i]);
+      DLB_TRY(upload(plan, sl.data(), sl.size(), &oz.d_Bs));
+      DLB_TRY(upload(plan, sb.data(), sb.size(), &oz.d_Sb));
+      std::vector<double> r0x(oz.ncolx + 2, 0.);
+      for (int c = 0; c < oz.ncols; ++c) r0x[c] = bd.r0_white[c];
+      for (int i = 0; i < oz.nconst; ++i) {
+        double acc = 0.;
+        for (int c = 0; c < oz.ncols; ++c) acc += bd.r0_white[c] * bd.gconst_white[(size_t)i * oz.ncols + c];
+        r0x[oz.ncols + i] = acc;
+      }
+      DLB_TRY(upload(plan, r0x.data(), r0x.size(), &oz.d_r0));
+    }
+  }
   // entry map of the Gram partials (order fixed by contract_kernel's epilogue)
   std::vector<EntryMap> map(blk.npart);
   const int R = bd.nslots;
@@ -503,9 +557,11 @@ static int ensure_workspace(dlb_plan* plan, long long npad) {
   if (plan->nder) DLB_CUDA(cudaMalloc((void**)&plan->w_pext, (size_t)npad * plan->d * sizeof(double)));
   if (plan->w_oz_slices) { cudaFree(plan->w_oz_slices); plan->w_oz_slices = nullptr; }
   if (plan->w_oz_exps) { cudaFree(plan->w_oz_exps); plan->w_oz_exps = nullptr; }
+  if (plan->w_oz_D) { cudaFree(plan->w_oz_D); plan->w_oz_D = nullptr; }
   if (plan->mlp_slices > 0 && plan->oz_maxk > 0) {
     DLB_CUDA(cudaMalloc((void**)&plan->w_oz_slices, ozaki_slice_bytes(ozaki_rows_pad(npad), plan->oz_maxk, plan->mlp_slices)));
     DLB_CUDA(cudaMalloc((void**)&plan->w_oz_exps, (size_t)ozaki_rows_pad(npad) * sizeof(int)));
+    if (plan->oz_contract) DLB_CUDA(cudaMalloc((void**)&plan->w_oz_D, (size_t)ozaki_rows_pad(npad) * plan->oz_ldD * sizeof(double)));
   }
   DLB_CUDA(cudaMalloc((void**)&plan->w_out, (size_t)npad * (3 + std::max(plan->ns, 0)) * sizeof(double)));
   DLB_CUDA(cudaMalloc((void**)&plan->w_status, (size_t)npad * sizeof(int)));
@@ -581,6 +637,22 @@ static int run_two_stage(dlb_plan* plan, const double* d_params, long long N, lo
 
 static int run_contract(dlb_plan* plan, const double* d_params, long long N, long long npad, int mode, double* d_theory, cudaStream_t stream) {
   if (mode == 0 && plan->two_stage) return run_two_stage(plan, d_params, N, npad, stream);
+  if (mode == 0 && plan->oz_contract) {   // tcgen05 int8 path: per block one GEMM over all terms + the Gram reduction
+    for (const Block& b : plan->blocks) {
+      const OzContract& oz = b.oz;
+      DLB_TRY(launch_ozaki_slice(plan->w_F + oz.fcol, N, oz.K, plan->fstride, plan->mlp_slices, plan->w_oz_slices, plan->w_oz_exps, stream));
+      DLB_TRY(launch_ozaki_gemm(N, oz.K, plan->w_oz_slices, plan->w_oz_exps, oz.d_Bs, oz.d_Sb, nullptr, oz.ldD, plan->mlp_slices, 0, plan->w_oz_D, oz.ldD,
+                                plan->nsm, stream));
+      OzakiGramParams gp;
+      std::memset(&gp, 0, sizeof(gp));
+      gp.D = plan->w_oz_D; gp.ldD = oz.ldD; gp.N = N; gp.npad = npad; gp.params = d_params; gp.d = plan->d; gp.coefs = plan->d_coefs;
+      gp.nterms = oz.nterms; gp.ncols = oz.ncols; gp.nconst = oz.nconst; gp.ncolx = oz.ncolx; gp.R = oz.R;
+      for (int t = 0; t < oz.nterms; ++t) { gp.tslot[t] = oz.tslot[t]; gp.tcoef[t] = oz.tcoef[t]; }
+      gp.r0 = oz.d_r0; gp.partial = plan->w_partial; gp.poff = b.poff;
+      DLB_TRY(launch_ozaki_gram(gp, stream));
+    }
+    return DLB_OK;
+  }
   const Launch& L = plan->launch;
   ContractParams cp;
   fill_params(plan, L, cp, d_params, N, npad);
@@ -626,6 +698,12 @@ int dlb_device_count(void) {
 
 int dlb_plan_ntheory(const dlb_plan* plan) { return plan ? plan->ntheory : -1; }
 int dlb_plan_nsolved(const dlb_plan* plan) { return plan ? plan->ns : -1; }
+int dlb_plan_flags(const dlb_plan* plan) {
+  if (!plan) return -1;
+  bool ozl = false;
+  for (const MlpLayers& m : plan->mlps) for (const OzLayer& l : m.oz) ozl = ozl || l.ozaki;
+  return (plan->resident ? 1 : 0) | (plan->two_stage ? 2 : 0) | (plan->mlp_fused_smem ? 4 : 0) | (ozl ? 8 : 0) | (plan->oz_contract ? 16 : 0);
+}
 double dlb_plan_executed_flops(const dlb_plan* plan) {
   if (!plan) return -1.;
   return plan->two_stage ? plan->launch.flops_exec_plain + plan->wlaunch.flops_exec : plan->launch.flops_exec;
@@ -641,6 +719,7 @@ void dlb_plan_destroy(dlb_plan* plan) {
   if (plan->w_hess) cudaFree(plan->w_hess);
   if (plan->w_oz_slices) cudaFree(plan->w_oz_slices);
   if (plan->w_oz_exps) cudaFree(plan->w_oz_exps);
+  if (plan->w_oz_D) cudaFree(plan->w_oz_D);
   for (auto& e : plan->ev_pipe) if (e) cudaEventDestroy(e);
   if (plan->s_in) cudaStreamDestroy(plan->s_in);
   if (plan->s_out) cudaStreamDestroy(plan->s_out);
@@ -913,6 +992,13 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
     bptr.push_back(&blk);
   }
   plan->ntheory = coloff; plan->ptotal = poff;
+  {
+    bool all = plan->mlp_slices > 0;
+    for (const Block& b : plan->blocks) all = all && b.oz.on;
+    plan->oz_contract = all;
+    if (all)
+      for (const Block& b : plan->blocks) { plan->oz_ldD = std::max(plan->oz_ldD, b.oz.ldD); plan->oz_maxk = std::max(plan->oz_maxk, b.oz.K); }
+  }
   for (int ib = 0; ib < desc->nblocks; ++ib) plan->two_stage = plan->two_stage || desc->blocks[ib].transform_data != nullptr;
   if (plan->two_stage) {
     // Solved parameters in a two-stage plan: the reference linearises flatdiff = u(t(x)) - data at the defaults (FastFisher, likelihoods/base.py:
@@ -1105,7 +1191,8 @@ static const long long MAX_CHUNK = 1LL << 20;
 // Points per pass of the batched entry points: at most 2^20, fewer when the per-point workspace (feature rows of wide MLP emulators,
 // Gram partials, transformed theory vectors) would exceed ~16 GiB -- the workspace stays a small part of the 180 GB of HBM.
 static long long chunk_points(const dlb_plan* plan) {
-  const long long per_point = 8LL * ((long long)plan->fstride + std::max(plan->ptotal, 1LL) + plan->d + 4 + plan->ns + plan->tstride);
+  const long long per_point = 8LL * ((long long)plan->fstride + std::max(plan->ptotal, 1LL) + plan->d + 4 + plan->ns + plan->tstride + plan->oz_ldD) +
+                              (long long)plan->oz_maxk * plan->mlp_slices;
   long long n = (16LL << 30) / std::max(per_point, 1LL) / ROW_ALIGN * ROW_ALIGN;
   n = std::max<long long>(ROW_ALIGN * 32, std::min(MAX_CHUNK, n));
   // Feature matrices written by their own kernels (direct Kaiser / BAO theories) are consumed by the contraction right after: a pass whose

@@ -84,9 +84,11 @@ def ozaki_matmul_reference(X, W, slices=6):
         a = np.zeros((X.shape[0], W.shape[1]))
         for i in range(t + 1): a += qa[i] @ qb[t - i].T
         acc.append(a)
-    # the epilogue combines three consecutive accumulators exactly in int64, then sums the groups smallest first (csrc/ozaki.cu, phase A)
+    # the epilogue combines the accumulators in two groups of gs = ceil(slices / 2), each EXACTLY in int64 (G < 2^46 is also exact in float64
+    # here), then adds the two groups smallest first (csrc/ozaki.cu, phase A / B of the epilogue)
+    gs = (slices + 1) // 2
     v = np.zeros((X.shape[0], W.shape[1]))
-    for g in range((slices + 2) // 3 - 1, -1, -1):
-        G = sum(acc[3 * g + u] * 2.**(7 * (2 - u)) for u in range(3) if 3 * g + u < slices)
-        v = v + G * 2.**(-7 * (3 * g + 4))
+    for g in (1, 0):
+        G = sum(acc[gs * g + u] * 2.**(7 * (gs - 1 - u)) for u in range(gs) if gs * g + u < slices)
+        v = v + G * 2.**(-7 * (gs * g + gs + 1))
     return np.ldexp(np.ldexp(v, Ea[:, None]), Eb[None, :])

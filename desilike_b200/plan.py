@@ -42,6 +42,9 @@ class Plan(object):
         handle = ctypes.c_void_p()
         _capi.check(self._lib.dlb_plan_create(ctypes.byref(self.lowered.desc), ctypes.byref(handle)))
         self._handle = handle
+        flags = self._lib.dlb_plan_flags(handle)
+        # which kernels the plan runs (include/desilike_b200.h: dlb_plan_flags)
+        self.kernels = {name: bool(flags >> bit & 1) for bit, name in enumerate(['resident_taylor', 'two_stage', 'fused_mlp', 'int8_layers', 'int8_contraction'])}
         # plan order -> spec order of the solved parameters
         self._unperm = np.argsort(self.lowered.solved_order) if self.ns else np.zeros(0, dtype=int)
         self._identity_perm = bool(np.array_equal(self._unperm, np.arange(self.ns)))   # all '.marg' (or all '.best'): plan order == spec order

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DLB_ABI_VERSION 7
+#define DLB_ABI_VERSION 8
 
 typedef enum {
   DLB_OK = 0,
@@ -163,6 +163,9 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out);
 void dlb_plan_destroy(dlb_plan* plan);
 int dlb_plan_ntheory(const dlb_plan* plan);      /* total data-vector length n */
 int dlb_plan_nsolved(const dlb_plan* plan);
+/* which kernels the plan runs: bit 0 Taylor monomials inside the contraction kernel, 1 two-stage (observable transform), 2 fused MLP kernel,
+ * 3 MLP hidden layers on the tcgen05 int8 path, 4 likelihood blocks as tcgen05 int8 GEMMs + Gram reduction (both opt-in through mlp_slices) */
+int dlb_plan_flags(const dlb_plan* plan);
 /* FP64 tensor-pipe FLOPs per evaluation EXECUTED by the contraction launch(es) of dlb_eval_batch: 2 * k-chunk length * tile width over
  * the (column block, k-chunk) tiles actually multiplied (zero padding inside tiles included, skipped leading zero tiles excluded).
  * Diagnostic for bench.py: the gap to the algorithmic count is padding. */
