@@ -72,17 +72,32 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
   if (lane == 0) exps[row] = E;
   const double sc = scalbn(1., -E);
   const size_t sstride = (size_t)Kpad * 8;
-  for (int k = lane; k < Kpad; k += 32) {
-    double r = (row < rows && k < K) ? x[k] * sc : 0.;
-    if (!isfinite(r)) r = 0.;
+  // four consecutive k per lane: 32-byte loads (rows 32-byte aligned: `vec`), one 32-bit shared-memory store per slice
+  const bool vec = (ld & 3) == 0 && (reinterpret_cast<unsigned long long>(X) & 31ull) == 0ull;
+  for (int k = 4 * lane; k < Kpad; k += 128) {
+    double r[4];
+    if (row < rows && vec && k + 4 <= K) {
+      const double4 v = *reinterpret_cast<const double4*>(x + k);
+      r[0] = v.x * sc; r[1] = v.y * sc; r[2] = v.z * sc; r[3] = v.w * sc;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = (row < rows && k + j < K) ? x[k + j] * sc : 0.;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (!isfinite(r[j])) r[j] = 0.;
     unsigned char* dst = sl_smem + (size_t)(k >> 4) * 128 + warp * 16 + (k & 15);
 #pragma unroll
     for (int s = 0; s < OZ_MAXS; ++s)
       if (s < ns) {
-        r *= 128.;
-        const double qs = rint(r);
-        r -= qs;
-        dst[(size_t)s * sstride] = (unsigned char)(int)qs;
+        uint32_t w = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          r[j] *= 128.;
+          const double qs = rint(r[j]);
+          r[j] -= qs;
+          w |= ((uint32_t)(int)qs & 0xFFu) << (8 * j);
+        }
+        *reinterpret_cast<uint32_t*>(dst + (size_t)s * sstride) = w;
       }
   }
   __syncthreads();
@@ -340,17 +355,21 @@ __global__ void mlp_small_layer_kernel(const double* __restrict__ X, long long r
 // then the Gram partials in the order of contract_kernel's epilogue: S_a . S_b (a <= b) over the data columns, followed by S_a[ncols + i].
 // One warp per point (lanes stride over the columns: coalesced reads), OZ_GRAM_WARPS points per block; results staged in shared memory so
 // that the point-minor partial rows are written in contiguous runs.
-constexpr int OZ_GRAM_WARPS = 8;
+constexpr int OZ_GRAM_WARPS = 8, OZ_GRAM_RPW = 4, OZ_GRAM_ROWS = OZ_GRAM_WARPS * OZ_GRAM_RPW;   // rows per warp / per block
 
 template <int R>
-__global__ void __launch_bounds__(OZ_GRAM_WARPS * 32) ozaki_gram_kernel(const OzakiGramParams p) {
+__global__ void __launch_bounds__(OZ_GRAM_WARPS * 32, R <= 4 ? 4 : 2) ozaki_gram_kernel(const OzakiGramParams p) {
   constexpr int NP = R * (R + 1) / 2;
-  __shared__ double red[OZ_GRAM_WARPS][NP + R * 8 + 1];
+  __shared__ double red[OZ_GRAM_ROWS][NP + R * 8 + 1];
   __shared__ double cs[OZ_GRAM_WARPS][OZ_GRAM_MAXT];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row0 = (long long)blockIdx.x * OZ_GRAM_WARPS, row = row0 + warp;
+  const long long row0 = (long long)blockIdx.x * OZ_GRAM_ROWS;
   const int Rb = p.R, nS = Rb * (Rb + 1) / 2, npart = nS + Rb * p.nconst;
-  if (row < p.N) {
+  for (int rr = 0; rr < OZ_GRAM_RPW; ++rr) {
+    const int rl = rr * OZ_GRAM_WARPS + warp;
+    const long long row = row0 + rl;
+    if (row >= p.N) break;
+    __syncwarp();
     if (lane < p.nterms) {   // bias monomials of this point, one lane per term
       double v = 1.;
       if (p.tcoef[lane] >= 0) {
@@ -367,28 +386,25 @@ __global__ void __launch_bounds__(OZ_GRAM_WARPS * 32) ozaki_gram_kernel(const Oz
       cs[warp][lane] = v;
     }
     __syncwarp();
-    double c[OZ_GRAM_MAXT];
-#pragma unroll
-    for (int t = 0; t < OZ_GRAM_MAXT; ++t) c[t] = t < p.nterms ? cs[warp][t] : 0.;
     const double* Drow = p.D + row * p.ldD;
     double acc[NP];
 #pragma unroll
     for (int e = 0; e < NP; ++e) acc[e] = 0.;
     // two columns per lane and step (ncolx and ldD are even: 16-byte loads); column ncols (odd ncols) belongs to the auxiliary columns: masked
-#pragma unroll 2
     for (int col = 2 * lane; col < p.ncols; col += 64) {
       double S0[R], S1[R];
 #pragma unroll
       for (int a = 0; a < R; ++a) S0[a] = S1[a] = 0.;
-      const double2 rr = *reinterpret_cast<const double2*>(p.r0 + col);
-      S0[0] = -rr.x; S1[0] = -rr.y;
+      const double2 r0v = *reinterpret_cast<const double2*>(p.r0 + col);
+      S0[0] = -r0v.x; S1[0] = -r0v.y;
+#pragma unroll 6
+      for (int t = 0; t < p.nterms; ++t) {
+        const double2 v = __ldcs(reinterpret_cast<const double2*>(Drow + (size_t)t * p.ncolx + col));   // streamed once
+        const double c = cs[warp][t];
+        const int sl = p.tslot[t];
 #pragma unroll
-      for (int t = 0; t < OZ_GRAM_MAXT; ++t)
-        if (t < p.nterms) {
-          const double2 v = *reinterpret_cast<const double2*>(Drow + (size_t)t * p.ncolx + col);
-#pragma unroll
-          for (int a = 0; a < R; ++a) if (p.tslot[t] == a) { S0[a] = fma(c[t], v.x, S0[a]); S1[a] = fma(c[t], v.y, S1[a]); }
-        }
+        for (int a = 0; a < R; ++a) if (sl == a) { S0[a] = fma(c, v.x, S0[a]); S1[a] = fma(c, v.y, S1[a]); }
+      }
       if (col + 1 >= p.ncols) {
 #pragma unroll
         for (int a = 0; a < R; ++a) S1[a] = 0.;
@@ -412,7 +428,7 @@ __global__ void __launch_bounds__(OZ_GRAM_WARPS * 32) ozaki_gram_kernel(const Oz
       for (int a = 0; a < R; ++a)
 #pragma unroll
         for (int b = a; b < R; ++b)
-          if (b < Rb) red[warp][a * Rb - (a * (a - 1)) / 2 + (b - a)] = acc[a * R - (a * (a - 1)) / 2 + (b - a)];
+          if (b < Rb) red[rl][a * Rb - (a * (a - 1)) / 2 + (b - a)] = acc[a * R - (a * (a - 1)) / 2 + (b - a)];
     }
     // auxiliary columns: lane = (i, a)
     for (int e = lane; e < Rb * p.nconst; e += 32) {
@@ -420,12 +436,12 @@ __global__ void __launch_bounds__(OZ_GRAM_WARPS * 32) ozaki_gram_kernel(const Oz
       double v = a == 0 ? -p.r0[col] : 0.;
       for (int t = 0; t < p.nterms; ++t)
         if (p.tslot[t] == a) v += cs[warp][t] * Drow[(size_t)t * p.ncolx + col];
-      red[warp][nS + e] = v;
+      red[rl][nS + e] = v;
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < npart * OZ_GRAM_WARPS; i += OZ_GRAM_WARPS * 32) {
-    const int e = i / OZ_GRAM_WARPS, w = i - e * OZ_GRAM_WARPS;
+  for (int i = threadIdx.x; i < npart * OZ_GRAM_ROWS; i += OZ_GRAM_WARPS * 32) {
+    const int e = i / OZ_GRAM_ROWS, w = i - e * OZ_GRAM_ROWS;
     if (row0 + w < p.N) p.partial[(p.poff + e) * p.npad + row0 + w] = red[w][e];
   }
 }
@@ -540,7 +556,7 @@ int launch_ozaki_layer(const double* X, long long rows, int K, long long ld, con
 int launch_ozaki_gram(const OzakiGramParams& p, cudaStream_t stream) {
   DLB_REQUIRE(p.nterms >= 1 && p.nterms <= OZ_GRAM_MAXT && p.R >= 1 && p.R <= 8 && p.nconst >= 0 && p.nconst <= 8, "ozaki gram: 1 <= terms <= 16, 1 <= slots <= 8, nconst <= 8");
   DLB_REQUIRE((p.ncolx & 1) == 0 && (p.ldD & 1) == 0, "ozaki gram: even column counts required (16-byte loads)");
-  const unsigned grid = (unsigned)((p.N + OZ_GRAM_WARPS - 1) / OZ_GRAM_WARPS);
+  const unsigned grid = (unsigned)((p.N + OZ_GRAM_ROWS - 1) / OZ_GRAM_ROWS);
   if (p.R <= 1) ozaki_gram_kernel<1><<<grid, OZ_GRAM_WARPS * 32, 0, stream>>>(p);
   else if (p.R <= 2) ozaki_gram_kernel<2><<<grid, OZ_GRAM_WARPS * 32, 0, stream>>>(p);
   else if (p.R <= 4) ozaki_gram_kernel<4><<<grid, OZ_GRAM_WARPS * 32, 0, stream>>>(p);
