@@ -366,6 +366,8 @@ def roofline_for(workload, plan, phase, N, value_per_gpu, peaks):
     elif workload == 'c1':
         # dominant kernel: Kaiser + ShapeFit + AP.  SURVEY.md section 8d: Nkin * nmu * 60 + 500 * (exp, tanh) (special functions at ~30 FLOP each)
         kflops, kname, kms, peak = 36 * 8 * 60 + 500 * 2 * 30, 'dlb::kaiser_kernel (FP64 FMA pipe; ShapeFit + spline + Gauss-Legendre quadrature)', phase['features'], peaks['dfma']
+    elif workload.endswith('_i8') and plan.kernels.get('int8_contraction'):
+        return roofline_int8(workload, plan, phase, N, flops, traffic, peaks)
     else:
         kflops, kname, kms, peak = flops['contract'] + flops['gram'], 'dlb::contract_kernel (FP64 DMMA.8x8x4, persistent, one launch per likelihood)', phase['contract'], peaks['dmma']
     achieved = kflops * N / (kms * 1e-3) / 1e12
@@ -382,6 +384,46 @@ def roofline_for(workload, plan, phase, N, value_per_gpu, peaks):
         roofline['flops_per_eval_uncollapsed'] = uncollapsed
         roofline['algebraic_folding_factor'] = uncollapsed / max(flops['total'], 1)
     return roofline
+
+
+def roofline_int8(workload, plan, phase, N, flops, traffic, peaks):
+    """Wide-MLP plans on the tcgen05 int8 path (csrc/ozaki.cu): the dominant kernel is ozaki_gemm_kernel (hidden layers + one GEMM per likelihood block).
+    Algorithmic count = int8 multiply-adds the exact slicing scheme needs: ns (ns + 1) / 2 slice products of every [128 x 64 x 32] tile, i.e.
+    2 * ns (ns + 1) / 2 * sum over the GEMMs of Kpad * Ncols (padded to the 32-deep k blocks / 64-wide column tiles) per point.  Denominator: int8
+    dense = 2 x the bf16 dense throughput of MEASURED_PEAKS.json (the tensor pipe runs int8 at twice the bf16 rate; nominal 4500 TOP/s).  Time:
+    CUDA events around the features + contraction phases of the step, i.e. INCLUDING the slicing, first-layer and Gram-reduction kernels."""
+    ns = plan.lowered.mlp_slices
+    # GEMM shapes from the lowered generators (idata of an MLP generator = [nhidden, act, d, H_1 ..]) / blocks
+    gemm = []
+    for g in plan.lowered.gens:
+        if g.kind_name == 'mlp':
+            idata = [int(v) for v in g.idata]
+            widths = [idata[2]] + idata[3:3 + idata[0]]
+            for a, b in zip(widths[:-1], widths[1:]):
+                if a >= 64: gemm.append((a, b))
+    for b in plan.lowered.blocks:
+        K = b['terms'][0][4]
+        ncolx = (b['ncols_white'] or b['ncols']) + (0 if b['gconst_white'] is None else len(b['gconst_white']))
+        ncolx += ncolx & 1
+        gemm.append((K, len(b['terms']) * ncolx))
+    pad = lambda n, m: (n + m - 1) // m * m
+    macs = sum(pad(K, 32) * pad(Nc, 64) for K, Nc in gemm) * ns * (ns + 1) // 2
+    kms = phase['features'] + phase['contract']
+    achieved = 2. * macs * N / (kms * 1e-3) / 1e12
+    measured = None
+    try: measured = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))).get('bf16_tflops')
+    except Exception: measured = None
+    peak = 2. * measured if measured else 4500.
+    nlayers = len(gemm) - len(plan.lowered.blocks)
+    layer_flops = 2 * sum(a * b for a, b in gemm[:nlayers])   # FP64 multiply-adds of the hidden layers these GEMMs replace
+    fp64_equiv = (flops['contract'] + flops['gram'] + layer_flops) * N / (kms * 1e-3) / 1e12
+    return {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TOP/s (int8)', 'frac': achieved / peak, 'traffic': traffic,
+            'kernel': 'dlb::ozaki_gemm_kernel (tcgen05.mma kind::i8, TMEM accumulators; {:d} exact 7-bit slices per operand)'.format(ns),
+            'gemms_per_step': len(gemm), 'ms_per_step_in_kernel': kms, 'int8_macs_per_eval': macs, 'flops_per_eval_folded': flops,
+            'peak_source': ('2 x MEASURED_PEAKS.json bf16_tflops (burst)' if measured else 'nominal dense int8 (no MEASURED_PEAKS.json)'),
+            'fp64_equivalent_tflops': fp64_equiv, 'fp64_equivalent_vs_dmma_peak': fp64_equiv / peaks['dmma'],
+            'share_of_step': kms / (kms + phase['solve']) if kms else None, 'phase_ms': phase,
+            'note': 'time includes the slicing, first-layer and Gram-reduction kernels around the GEMMs'}
 
 
 def run_workload(ctx, args, workload, N, steps, warmup, main, peaks):

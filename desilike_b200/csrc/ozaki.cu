@@ -24,6 +24,7 @@
 #include "common.h"
 
 #include <cstring>
+#include <cstdio>
 
 namespace dlb {
 
@@ -33,7 +34,8 @@ constexpr int OZ_M = 128, OZ_N = 64, OZ_KB = 32;          // output tile, k-bloc
 constexpr int OZ_A_SLICE = OZ_M * OZ_KB, OZ_B_SLICE = OZ_N * OZ_KB;   // bytes of one slice of one stage
 constexpr int OZ_MAXS = 8;
 constexpr int OZ_EPI_WARPS = 8;
-constexpr int OZ_THREADS = (OZ_EPI_WARPS + 2) * 32;   // warps 0-7 epilogue, 8 TMA producer, 9 MMA issuer
+constexpr int OZ_MMA_WARPS = 2;
+constexpr int OZ_THREADS = (OZ_EPI_WARPS + 1 + OZ_MMA_WARPS + 1) * 32;   // warps 0-7 epilogue, 8 TMA producer, 9-10 MMA issuers, 11 idle (12 warps: 3 per scheduler)
 
 __device__ __forceinline__ uint32_t oz_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -120,6 +122,7 @@ struct OzakiParams {
   double* out; long long ldo; long long rows; int ncols;
   int nkb, ns, act, ntm, ntn;
   int nstages;
+  int C, ntg;             // thread-block cluster size along N (1, 2 or 4) and column-tile groups per row tile = ceil(ntn / C)
 };
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_NONE; LBO = byte distance between the two 16-byte k chunks of one
@@ -132,19 +135,25 @@ __device__ __forceinline__ double oz_silu(double v) { return v * fast_rcp(1. + f
 
 // All slice products of one k block: acc_t += A_i . B_j^T for i + j = t <= NS - 1.  The B slices of a stage lie side by side along N ([k chunk][slice]
 // [64 rows x 16 bytes]) and accumulator t sits at TMEM column 64 t, so ONE tcgen05.mma of N = 64 m multiplies A_i with the m consecutive slices
-// B_j .. B_j+m-1 into the accumulators i + j .. i + j + m - 1 (m <= 4: N <= 256): 8 instructions per k block instead of 21 for 6 slices.
+// B_j .. B_j+m-1 into the accumulators i + j .. i + j + m - 1 (m <= 4: N <= 256).
+// Issuing one tcgen05.mma costs a single warp ~100 cycles (ELECT -> R2UR x 4 -> UTCIMMA, a dependent chain) while a 128 x 64 x 32 product occupies the
+// tensor pipe for 32: TWO warps issue, each owning a disjoint set of accumulators (PART 0: t < T0, PART 1: t >= T0, T0 = (2 NS + 1) / 3 balances their
+// instruction counts) -- no two warps ever write the same TMEM columns, and every warp's own instructions stay in program order.
 // `accumulate` is false for the first k block of a tile, where the i = 0 products overwrite every accumulator.  Executed by the whole (converged)
-// MMA warp with warp-uniform operands; `elected` predicates the instruction itself.
-template <int NS>
+// warp with warp-uniform operands; `elected` predicates the instruction itself.
+template <int NS, int PART>
 __device__ __forceinline__ void oz_issue_kblock(uint32_t a0, uint32_t b0, uint32_t tmem, bool accumulate, uint32_t elected) {
+  constexpr int T0 = (2 * NS + 1) / 3;
   const uint64_t da0 = oz_desc(a0, OZ_M * 16, 128), db0 = oz_desc(b0, NS * (OZ_N * 16), 128);   // (the 14-bit address fields cannot carry: shared memory < 256 KB)
   const uint32_t acc0 = accumulate ? 1u : 0u;
 #pragma unroll
   for (int i = 0; i < NS; ++i) {
     const uint64_t da = da0 + (uint64_t)((i * OZ_A_SLICE) >> 4);
+    // B slices j with i + j in this warp's accumulator range
+    const int jlo = PART == 0 ? 0 : (T0 - i > 0 ? T0 - i : 0), jhi = PART == 0 ? (T0 - i < NS - i ? T0 - i : NS - i) : NS - i;   // [jlo, jhi)
 #pragma unroll
-    for (int j0 = 0; j0 < NS - i; j0 += 4) {
-      const int m = NS - i - j0 < 4 ? NS - i - j0 : 4;
+    for (int j0 = jlo; j0 < jhi; j0 += 4) {
+      const int m = jhi - j0 < 4 ? jhi - j0 : 4;
       // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed 8 bit, both K-major, N >> 3, M >> 4
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((OZ_N * m) >> 3) << 17) | ((uint32_t)(OZ_M >> 4) << 24);
       const uint64_t db = db0 + (uint64_t)((j0 * (OZ_N * 16)) >> 4);
@@ -156,6 +165,19 @@ __device__ __forceinline__ void oz_issue_kblock(uint32_t a0, uint32_t b0, uint32
           "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
           ::"r"(d), "l"(da), "l"(db), "r"(idesc), "r"(i == 0 ? acc0 : 1u), "r"(0u), "r"(elected) : "memory");
     }
+  }
+}
+
+template <int PART>
+__device__ __forceinline__ void oz_issue_kblock_ns(int ns, uint32_t a0, uint32_t b0, uint32_t tmem, bool accumulate, uint32_t elected) {
+  switch (ns) {   // fully unrolled per slice count
+    case 2: oz_issue_kblock<2, PART>(a0, b0, tmem, accumulate, elected); break;
+    case 3: oz_issue_kblock<3, PART>(a0, b0, tmem, accumulate, elected); break;
+    case 4: oz_issue_kblock<4, PART>(a0, b0, tmem, accumulate, elected); break;
+    case 5: oz_issue_kblock<5, PART>(a0, b0, tmem, accumulate, elected); break;
+    case 6: oz_issue_kblock<6, PART>(a0, b0, tmem, accumulate, elected); break;
+    case 7: oz_issue_kblock<7, PART>(a0, b0, tmem, accumulate, elected); break;
+    default: oz_issue_kblock<8, PART>(a0, b0, tmem, accumulate, elected); break;
   }
 }
 
@@ -183,10 +205,17 @@ __device__ __forceinline__ double oz_act(double y) {
 template <int ACT>
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_constant__ OzakiParams p) {
   extern __shared__ __align__(1024) unsigned char oz_smem[];
-  const int ns = p.ns, S = p.nstages;
+  const int ns = p.ns, S = p.nstages, C = p.C;
   const uint32_t stage_bytes = (uint32_t)ns * (OZ_A_SLICE + OZ_B_SLICE);
   unsigned char* stages = oz_smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(oz_smem + (size_t)S * stage_bytes);   // full[S], empty[S], tmem_full, tmem_empty
+  // Thread-block cluster of C CTAs along N: the C CTAs work on the column tiles tg C .. tg C + C - 1 of the SAME row tile in lock step and share
+  // its A slices -- CTA r fetches the r-th part of every A stage and multicasts it into the shared memory of all C CTAs (cp.async.bulk
+  // .multicast::cluster).  Opt-in (C = 1 by default, see launch_gemm_act for the measurements).  A stage is released to the producers when the MMAs of ALL C CTAs have read it: every MMA
+  // warp commits to the stage's `empty` barrier of every CTA (tcgen05.commit .multicast::cluster).
+  uint32_t crank = 0;
+  if (C > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const uint16_t cmask = (uint16_t)((1u << C) - 1u);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = oz_smem_u32(bars);
@@ -197,9 +226,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full(s)));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(empty(s)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty(s)), "r"(C * OZ_MMA_WARPS));   // every MMA warp of every CTA of the cluster reads (the multicast A chunks of) a stage
     }
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tmem_full));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tmem_full), "r"(OZ_MMA_WARPS));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tmem_empty), "r"(OZ_EPI_WARPS * 32));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -209,52 +238,63 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (C > 1) {   // no CTA may multicast into / arrive on a peer whose barriers are not initialised yet
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  const long long ntiles = (long long)p.ntm * p.ntn;
+  // work units: (row tile, group of C column tiles); cluster c takes units c, c + nclusters, ...; CTA r of the cluster the column tile tg C + r
+  // (beyond ntn: a dummy tile -- the CTA still takes part in the multicast loads and barriers, its results are not stored)
+  const long long nunits = (long long)p.ntm * p.ntg, unit0 = blockIdx.x / C, ustep = gridDim.x / C;
   if (warp == OZ_EPI_WARPS) {
     // ===== producer: one bulk copy of all A slices + one of all B slices per (tile, k block) =====
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long tm = tile / p.ntn; const int tn = (int)(tile - tm * p.ntn);
+      const uint32_t a_bytes = (uint32_t)ns * OZ_A_SLICE, a_part = a_bytes / (uint32_t)C;
+      for (long long unit = unit0; unit < nunits; unit += ustep) {
+        const long long tm = unit / p.ntg;
+        const int tn = min((int)(unit - tm * p.ntg) * C + (int)crank, p.ntn - 1);
         for (int kb = 0; kb < p.nkb; ++kb) {
           oz_mbar_wait(empty(s), ph ^ 1u);
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full(s)), "r"(stage_bytes) : "memory");
           const int8_t* srcA = p.A + ((size_t)(tm * p.nkb + kb) * ns) * OZ_A_SLICE;
           const int8_t* srcB = p.B + ((size_t)((long long)tn * p.nkb + kb) * ns) * OZ_B_SLICE;
           const uint32_t dst = oz_smem_u32(stages + (size_t)s * stage_bytes);
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(srcA),
-                       "r"((uint32_t)ns * OZ_A_SLICE), "r"(full(s)) : "memory");
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + (uint32_t)ns * OZ_A_SLICE), "l"(srcB),
+          if (C > 1)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                         ::"r"(dst + crank * a_part), "l"(srcA + (size_t)crank * a_part), "r"(a_part), "r"(full(s)), "h"(cmask) : "memory");
+          else
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(srcA), "r"(a_bytes), "r"(full(s))
+                         : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + a_bytes), "l"(srcB),
                        "r"((uint32_t)ns * OZ_B_SLICE), "r"(full(s)) : "memory");
           if (++s == S) { s = 0; ph ^= 1u; }
         }
       }
     }
-  } else if (warp == OZ_EPI_WARPS + 1) {
-    // ===== MMA issuer: the whole warp walks the pipeline (warp-uniform control flow and operands), lane 0 issues =====
+  } else if (warp > OZ_EPI_WARPS && warp <= OZ_EPI_WARPS + OZ_MMA_WARPS) {
+    // ===== MMA issuers (two warps, disjoint accumulators): the whole warp walks the pipeline (warp-uniform control flow and operands), lane 0 issues =====
+    const int part = warp - (OZ_EPI_WARPS + 1);
     const uint32_t elected = lane == 0 ? 1u : 0u;
     int s = 0; uint32_t ph = 0, tph = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (long long unit = unit0; unit < nunits; unit += ustep) {
       oz_mbar_wait(tmem_empty, tph ^ 1u);   // the epilogue has drained the accumulators of the previous tile
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int kb = 0; kb < p.nkb; ++kb) {
         oz_mbar_wait(full(s), ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a0 = oz_smem_u32(stages) + (uint32_t)s * stage_bytes, b0 = a0 + (uint32_t)ns * OZ_A_SLICE;
-        switch (ns) {   // fully unrolled per slice count
-          case 2: oz_issue_kblock<2>(a0, b0, tmem, kb > 0, elected); break;
-          case 3: oz_issue_kblock<3>(a0, b0, tmem, kb > 0, elected); break;
-          case 4: oz_issue_kblock<4>(a0, b0, tmem, kb > 0, elected); break;
-          case 5: oz_issue_kblock<5>(a0, b0, tmem, kb > 0, elected); break;
-          case 6: oz_issue_kblock<6>(a0, b0, tmem, kb > 0, elected); break;
-          case 7: oz_issue_kblock<7>(a0, b0, tmem, kb > 0, elected); break;
-          default: oz_issue_kblock<8>(a0, b0, tmem, kb > 0, elected); break;
-        }
+        if (part == 0) oz_issue_kblock_ns<0>(ns, a0, b0, tmem, kb > 0, elected);
+        else oz_issue_kblock_ns<1>(ns, a0, b0, tmem, kb > 0, elected);
         // the stage may be refilled once these MMAs have read it
-        if (elected) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty(s)) : "memory");
+        if (elected) {
+          if (C > 1)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(empty(s)), "h"(cmask) : "memory");
+          else
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty(s)) : "memory");
+        }
         __syncwarp();
         if (++s == S) { s = 0; ph ^= 1u; }
       }
@@ -262,14 +302,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
       __syncwarp();
       tph ^= 1u;
     }
-  } else {
+  } else if (warp < OZ_EPI_WARPS) {
     // ===== epilogue: warp w reads TMEM lanes 32 (w & 3) .. + 31 (= output rows of the tile), columns 32 (w >> 2) .. + 31 of every accumulator =====
     const int q = warp & 3, h = warp >> 2;
     const int gs = (ns + 1) >> 1;                     // accumulators per exact int64 group: (t + 1) K 64^2 2^(7 (gs - 1)) < 2^46 for gs <= 4
     const double w0 = scalbn(1., -7 * (gs + 1)), w1 = scalbn(1., -7 * (2 * gs + 1));
     uint32_t tph = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const long long tm = tile / p.ntn; const int tn = (int)(tile - tm * p.ntn);
+    for (long long unit = unit0; unit < nunits; unit += ustep) {
+      const long long tm = unit / p.ntg;
+      const int tn = (int)(unit - tm * p.ntg) * C + (int)crank;   // >= ntn: dummy tile
       oz_mbar_wait(tmem_full, tph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const long long row = tm * OZ_M + q * 32 + lane;
@@ -298,7 +339,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty) : "memory");
       // ---- phase B: exponents, bias, activation, store -- 8 outputs at a time: their column scales / biases come through the read-only path
       //      (no aliasing with the stores, so the loads are issued up front) and the 8 FP64 chains interleave ----
-      if (row < p.rows) {
+      if (row < p.rows && tn < p.ntn) {
         const double sa = scalbn(1., p.Ea[row]);
         const int col0 = tn * OZ_N + h * 32;
         double* orow = p.out + row * p.ldo + col0;
@@ -330,6 +371,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (C > 1) {   // peers may still multicast into this CTA's shared memory / arrive on its barriers until they are done, too
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
@@ -487,14 +532,39 @@ void ozaki_slice_weights(const double* W, int K, int N, int ns, std::vector<int8
 }
 
 template <int ACT>
-static int launch_gemm_act(const OzakiParams& p, unsigned grid, size_t smem, cudaStream_t stream) {
+static int launch_gemm_act(OzakiParams& p, int nsm, size_t smem, cudaStream_t stream) {
   static bool configured_dev[64] = {};
-  bool& configured = configured_dev[current_device_slot()];
-  if (!configured) {
+  static int max_clusters_dev[64][9] = {};
+  const int slot = current_device_slot();
+  if (!configured_dev[slot]) {
     DLB_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+    configured_dev[slot] = true;
   }
-  ozaki_gemm_kernel<ACT><<<grid, OZ_THREADS, smem, stream>>>(p);
+  // Cluster size.  Measured on B200 (c4wide, 16 384 points, 6 slices): 1 -> 2.86e6, 2 -> 2.83e6, 4 -> 2.64e6, 8 -> 2.46e6 evals/s (only 15 clusters of 8 =
+  // 120 SMs are co-schedulable): L2 already merges the concurrent reads of one A row tile by neighbouring CTAs, so the multicast saves no L2 -> SM
+  // bandwidth while the lock step of the cluster costs.  Default 1; DLB_OZAKI_CLUSTER = 2 | 4 | 8 keeps the multicast path testable.
+  int C = 1;
+  if (const char* e = getenv("DLB_OZAKI_CLUSTER")) { const int c = atoi(e); if ((c == 1 || c == 2 || c == 4 || c == 8) && p.ntn >= c) C = c; }
+  p.C = C; p.ntg = (p.ntn + C - 1) / C;
+  const long long nunits = (long long)p.ntm * p.ntg;
+  if (C > 1 && max_clusters_dev[slot][C] == 0) {   // cluster size forced through the environment: query its occupancy, too
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3((unsigned)(nsm / C * C)); q.blockDim = dim3(OZ_THREADS); q.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = (unsigned)C; at.val.clusterDim.y = at.val.clusterDim.z = 1;
+    q.attrs = &at; q.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, ozaki_gemm_kernel<ACT>, &q) != cudaSuccess) { cudaGetLastError(); n = -1; }
+    max_clusters_dev[slot][C] = n > 0 ? n : -1;
+    if (getenv("DLB_OZAKI_VERBOSE")) fprintf(stderr, "[ozaki] cluster size %d: %d active clusters\n", C, n);
+  }
+  int nclusters = C > 1 ? max_clusters_dev[slot][C] : nsm;
+  if (nclusters <= 0) nclusters = nsm / C;
+  const unsigned grid = (unsigned)(std::min<long long>(nclusters, nunits) * C);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(OZ_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = (unsigned)C; at.val.clusterDim.y = at.val.clusterDim.z = 1;
+  cfg.attrs = &at; cfg.numAttrs = 1;
+  DLB_CUDA(cudaLaunchKernelEx(&cfg, ozaki_gemm_kernel<ACT>, p));
   g_launches++;
   DLB_CUDA(cudaGetLastError());
   return DLB_OK;
@@ -534,13 +604,11 @@ int launch_ozaki_gemm(long long rows, int K, const int8_t* Aslices, const int* E
   p.nstages = (int)std::min<size_t>(8, (size_t)(200 * 1024) / stage);
   DLB_REQUIRE(p.nstages >= 2, "ozaki gemm: shared memory too small for two stages");
   const size_t smem = p.nstages * stage + (size_t)(2 * p.nstages + 2) * 8 + 16;
-  const long long ntiles = (long long)p.ntm * p.ntn;
-  const unsigned grid = (unsigned)std::min<long long>(nsm, ntiles);
   switch (act) {
-    case 0: return launch_gemm_act<0>(p, grid, smem, stream);
-    case 1: return launch_gemm_act<1>(p, grid, smem, stream);
-    case 2: return launch_gemm_act<2>(p, grid, smem, stream);
-    case 3: return launch_gemm_act<3>(p, grid, smem, stream);
+    case 0: return launch_gemm_act<0>(p, nsm, smem, stream);
+    case 1: return launch_gemm_act<1>(p, nsm, smem, stream);
+    case 2: return launch_gemm_act<2>(p, nsm, smem, stream);
+    case 3: return launch_gemm_act<3>(p, nsm, smem, stream);
   }
   set_error("ozaki gemm: unknown activation");
   return DLB_ERR_ARG;
