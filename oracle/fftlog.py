@@ -12,7 +12,7 @@ PARITY UNPINNED against the real cosmoprimo output (no golden vectors exist in t
 pinned *mathematically* against the defining integral restated at reference
 desilike/theories/galaxy_clustering/base.py:163-168:
     xi_ell(s) = (-1)^(ell/2) / (2 pi^2) * int k^2 dk P_ell(k) j_ell(k s)
-(see tests/test_oracle_fftlog.py: analytic Gaussian pair and brute-force quadrature).
+(see tests/test_oracle_math.py: analytic Gaussian pair and brute-force quadrature).
 """
 import numpy as np
 from scipy.special import loggamma
