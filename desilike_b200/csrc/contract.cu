@@ -121,20 +121,21 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[MT][NT][2], const double
   }
 }
 
-// A run of k4 steps restricted to the first NTC n-tiles of the warp
-template <int MT, int NT, int NTC, int KC>
+// A run of k4 steps restricted to the first NTC n-tiles of the warp.  FULLM: every m-tile of the warp is active (the usual case: only the last
+// row tile of a CTA's range is short) -- no per-DMMA predicates (predicated-off DMMAs are not free).
+template <int MT, int NT, int NTC, int KC, bool FULLM>
 __device__ __forceinline__ void mma_run(double (&acc)[MT][NT][2], const double* __restrict__ A, int astride, const double* __restrict__ B,
                                         const double (&beta)[MT], int k4a, int k4b, int mtc) {
 #pragma unroll 2
   for (int k4 = k4a; k4 < k4b; ++k4) {
     double a[MT], b[NTC];
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) a[mt] = mt < mtc ? A[mt * astride + k4 * 4] * beta[mt] : 0.;
+    for (int mt = 0; mt < MT; ++mt) a[mt] = (FULLM || mt < mtc) ? A[mt * astride + k4 * 4] * beta[mt] : 0.;
 #pragma unroll
     for (int nt = 0; nt < NTC; ++nt) b[nt] = B[nt * 16 * KC + k4 * 4];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
-      if (mt < mtc) {
+      if (FULLM || mt < mtc) {
 #pragma unroll
         for (int nt = 0; nt < NTC; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
       }
@@ -146,27 +147,34 @@ __device__ __forceinline__ void mma_run(double (&acc)[MT][NT][2], const double* 
 // csrc/plan.cu: build_block_core).  Zero sub-tiles of lower-triangular (rank-reduced) term matrices and of the padding of the last column
 // block are neither loaded nor multiplied.  (Measured and rejected: one code path with the loads / DMMAs predicated on nt < nact instead of
 // one instantiation per count -- C5 0.90 vs 0.75 ms: predicated-off DMMAs are not free.)
-template <int MT, int NT, int KC>
-__device__ __forceinline__ void mma_chunk_masked(double (&acc)[MT][NT][2], const double* A, int astride, const double* B, const double (&beta)[MT],
-                                                 int mtc, unsigned long long mask) {
+template <int MT, int NT, int KC, bool FULLM>
+__device__ __forceinline__ void mma_chunk_masked_m(double (&acc)[MT][NT][2], const double* A, int astride, const double* B, const double (&beta)[MT],
+                                                   int mtc, unsigned long long mask) {
   int k4 = 0;
   for (;;) {
     const int len = (int)(mask & 31ull);
     if (len == 0) break;
     const int nact = (int)((mask >> 5) & 7ull), k4e = k4 + len;
     mask >>= 8;
-    if (nact >= NT) mma_run<MT, NT, NT, KC>(acc, A, astride, B, beta, k4, k4e, mtc);
+    if (nact >= NT) mma_run<MT, NT, NT, KC, FULLM>(acc, A, astride, B, beta, k4, k4e, mtc);
     else switch (nact) {
       case 0: break;
-      case 1: mma_run<MT, NT, 1, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
-      case 2: if constexpr (NT > 2) mma_run<MT, NT, 2, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
-      case 3: if constexpr (NT > 3) mma_run<MT, NT, 3, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
-      case 4: if constexpr (NT > 4) mma_run<MT, NT, 4, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
-      case 5: if constexpr (NT > 5) mma_run<MT, NT, 5, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
-      default: if constexpr (NT > 6) mma_run<MT, NT, 6, KC>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+      case 1: mma_run<MT, NT, 1, KC, FULLM>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+      case 2: if constexpr (NT > 2) mma_run<MT, NT, 2, KC, FULLM>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+      case 3: if constexpr (NT > 3) mma_run<MT, NT, 3, KC, FULLM>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+      case 4: if constexpr (NT > 4) mma_run<MT, NT, 4, KC, FULLM>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+      case 5: if constexpr (NT > 5) mma_run<MT, NT, 5, KC, FULLM>(acc, A, astride, B, beta, k4, k4e, mtc); break;
+      default: if constexpr (NT > 6) mma_run<MT, NT, 6, KC, FULLM>(acc, A, astride, B, beta, k4, k4e, mtc); break;
     }
     k4 = k4e;
   }
+}
+
+template <int MT, int NT, int KC>
+__device__ __forceinline__ void mma_chunk_masked(double (&acc)[MT][NT][2], const double* A, int astride, const double* B, const double (&beta)[MT],
+                                                 int mtc, unsigned long long mask) {
+  if (mtc == MT) mma_chunk_masked_m<MT, NT, KC, true>(acc, A, astride, B, beta, mtc, mask);
+  else mma_chunk_masked_m<MT, NT, KC, false>(acc, A, astride, B, beta, mtc, mask);
 }
 
 template <int MT, int NT, int KC, bool MASKED>
