@@ -369,7 +369,8 @@ def roofline_for(workload, plan, phase, N, value_per_gpu, peaks):
     elif workload.endswith('_i8') and plan.kernels.get('int8_contraction'):
         return roofline_int8(workload, plan, phase, N, flops, traffic, peaks)
     else:
-        kflops, kname, kms, peak = flops['contract'] + flops['gram'], 'dlb::contract_kernel (FP64 DMMA.8x8x4, persistent, one launch per likelihood)', phase['contract'], peaks['dmma']
+        kflops, kname, kms, peak = flops['contract'] + flops['gram'], 'dlb::contract_kernel (FP64 DMMA.8x8x4, persistent, one launch per likelihood{})'.format(
+            '; quadratic-form plan: features x [K, T (T + 1) / 2 K + 8 T] instead of T matrices [K, n]' if plan.kernels.get('quadratic_form') else ''), phase['contract'], peaks['dmma']
     achieved = kflops * N / (kms * 1e-3) / 1e12
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic, 'kernel': kname,
                 'launches_per_step': 1, 'ms_per_step_in_kernel': kms, 'flops_per_eval_kernel': kflops, 'flops_per_eval_folded': flops,

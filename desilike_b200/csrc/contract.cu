@@ -219,7 +219,9 @@ __device__ __forceinline__ unsigned atom_add_acq_rel(unsigned* addr, unsigned v)
 
 // MASKED: the launch has sub-tile masks (BlockDev::tmask); plans without any use the instance that carries no masked code at all (the masked
 // path costs registers: C2 is 3 % slower with it compiled in, even when it never runs).
-template <int R, int MT, int NT, int WM, int CPS, int KC, bool RESIDENT, bool MASKED>
+// QF: quadratic-form blocks (single accumulator per column; the epilogue multiplies every column by its feature and scatters weighted group sums
+// into the Gram entries, see include/desilike_b200.h: dlb_block_desc::q_*).
+template <int R, int MT, int NT, int WM, int CPS, int KC, bool RESIDENT, bool MASKED, bool QF = false>
 __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_constant__ ContractParams p) {
   constexpr int NW = 2 * WM, NTH = NW * 32, UNIT = WM * 8, BM = UNIT * MT, BN = 16 * NT;
   constexpr int STAGE_DOUBLES = BN * KC + (RESIDENT ? 0 : BM * KC);
@@ -543,6 +545,56 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
                 }
             }
           }
+        } else if constexpr (QF) {
+          // ===== quadratic-form epilogue: this warp's n-tiles of 8 columns each belong to one group =====
+          const int* qt = blk->qtile + 3 * (cb * (BN / 8) + wn);   // n-tile 2 nt + wn of the column block
+          int cur = -1;
+          double sum[MT];
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) sum[mt] = 0.;
+          auto flush = [&](int gid) {   // quadratic group: quad reduction over the 8 columns of the lanes sharing a row, weighted scatter
+            const int4 grp = __ldg(blk->qgroup + gid);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              double sq = sum[mt];
+              sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+              sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+              if (lc == 0 && mt < mtc && grp.x == 0) {
+                const int row = mt * UNIT + wm * 8 + lr;
+                const double w = (grp.z >= 0 ? cs[grp.z * BM + row] : 1.) * (grp.w >= 0 ? cs[grp.w * BM + row] : 1.);
+                red[((size_t)wn * BM + row) * npm + grp.y] += sq * w;
+              }
+              sum[mt] = 0.;
+            }
+          };
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const int gid = __ldg(qt + 6 * nt), k0 = __ldg(qt + 6 * nt + 1), nv = __ldg(qt + 6 * nt + 2);
+            if (gid != cur) { if (cur >= 0) flush(cur); cur = gid; }
+            if (gid < 0) continue;
+            const int4 grp = __ldg(blk->qgroup + gid);
+            if (grp.x == 0) {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const double* f = A_s + (size_t)(mt * UNIT + wm * 8 + lr) * p.ast + k0 + 2 * lc;
+                const double f0 = 2 * lc < nv ? f[0] : 0., f1 = 2 * lc + 1 < nv ? f[1] : 0.;
+                sum[mt] = fma(acc[0][mt][nt][0], f0, fma(acc[0][mt][nt][1], f1, sum[mt]));
+              }
+            } else {   // direct group: every column is its own Gram entry
+              const int e0 = __ldg(blk->qdent + gid * 8 + 2 * lc), e1 = __ldg(blk->qdent + gid * 8 + 2 * lc + 1);
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                if (mt < mtc) {
+                  const int row = mt * UNIT + wm * 8 + lr;
+                  const double w = grp.z >= 0 ? cs[grp.z * BM + row] : 1.;
+                  double* redrow = red + ((size_t)wn * BM + row) * npm;
+                  if (e0 >= 0) redrow[e0] += acc[0][mt][nt][0] * w;
+                  if (e1 >= 0) redrow[e1] += acc[0][mt][nt][1] * w;
+                }
+              }
+            }
+          }
+          if (cur >= 0) flush(cur);
         } else {
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
@@ -609,7 +661,9 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
         for (int i = ptid; i < mtc * 8 * npart; i += 64) {
           const int e = i / (mtc * 8), rr = i - e * (mtc * 8);
           const int r = (rr >> 3) * UNIT + wm * 8 + (rr & 7);
-          out[(long long)e * p.npad + r] = red[(size_t)r * npm + e] + red[((size_t)BM + r) * npm + e];
+          double v = red[(size_t)r * npm + e] + red[((size_t)BM + r) * npm + e];
+          if constexpr (QF) v += __ldg(blk->qconst + e);
+          out[(long long)e * p.npad + r] = v;
         }
       }
       PROF(5)
@@ -661,11 +715,26 @@ int launch_contract_masked(const Variant& v, const ContractParams& p, int nsm, c
 int launch_contract_masked(const Variant& v, const ContractParams& p, int nsm, cudaStream_t stream) {
 #else
 int launch_contract(const Variant& v, const ContractParams& p, int nsm, cudaStream_t stream) {
-  if (p.masked) return launch_contract_masked(v, p, nsm, stream);
+  if (p.masked && !p.qform) return launch_contract_masked(v, p, nsm, stream);
 #endif
   const size_t smem = contract_smem_bytes(v, p.nstages, p.resident != 0, p.ast, p.dpad, p.ncoef, p.npart_max, p.ngen);
   if (smem > contract_smem_limit(v.CPS)) { set_error("contraction kernel: shared-memory budget exceeded"); return DLB_ERR_UNSUPPORTED; }
   const int grid = (int)std::min<long long>((long long)nsm * v.CPS, std::max<long long>(p.U, 1));
+#if !DLB_CONTRACT_MASKED
+  if (p.qform) {   // quadratic-form blocks: 16 warps, 64 x 112 tile, one accumulator per column, resident A
+    if (!(v.R == 1 && v.MT == 1 && v.NT == 7 && v.WM == 8 && v.CPS == 1 && v.KC == 36 && p.resident)) { set_error("quadratic-form plan: unexpected kernel variant"); return DLB_ERR_UNSUPPORTED; }
+    static bool configured_dev[64] = {};
+    bool& configured = configured_dev[current_device_slot()];
+    if (!configured) {
+      DLB_CUDA(cudaFuncSetAttribute(contract_kernel<1, 1, 7, 8, 1, 36, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)contract_smem_limit(1)));
+      configured = true;
+    }
+    contract_kernel<1, 1, 7, 8, 1, 36, true, false, true><<<grid, 8 * 64, smem, stream>>>(p);
+    g_launches++;
+    DLB_CUDA(cudaGetLastError());
+    return DLB_OK;
+  }
+#endif
   if (v.R == 1 && v.MT == 2 && v.NT == 7 && v.WM == 4 && v.CPS == 2 && v.KC == 28) return launch_mode<1, 2, 7, 4, 2, 28>(p, grid, smem, stream);
   if (v.R == 1 && v.MT == 2 && v.NT == 7 && v.WM == 4 && v.CPS == 2 && v.KC == 36) return launch_mode<1, 2, 7, 4, 2, 36>(p, grid, smem, stream);
   if (v.R == 1 && v.MT == 2 && v.NT == 5 && v.WM == 4 && v.CPS == 2 && v.KC == 28) return launch_mode<1, 2, 5, 4, 2, 28>(p, grid, smem, stream);

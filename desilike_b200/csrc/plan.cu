@@ -40,6 +40,7 @@ struct Block {
   double *d_tiles_white = nullptr, *d_tiles_plain = nullptr, *d_epi_white = nullptr, *d_epi_plain = nullptr;
   EntryMap* d_map = nullptr;
   std::vector<EntryMap> h_map;
+  int *d_qtile = nullptr, *d_qdent = nullptr; int4* d_qgroup = nullptr; double* d_qconst = nullptr;   // quadratic-form tables (dlb_block_desc::q_*)
   double* d_tdata = nullptr;   // 'cubic' observable transform: data of the transformed columns (two-stage plans)
   int tcol = 0;                // first column of the block in the transformed-theory buffer of a two-stage plan
 };
@@ -75,6 +76,11 @@ struct dlb_plan {
   dlb::Launch launch;                  // the likelihood blocks
   // two-stage plans (an observable transform that is non-linear in the theory, reference power_spectrum.py:400-404): stage 1 = `launch` in output
   // mode with the un-whitened matrices and the transform in its epilogue -> w_T [npad, tstride]; stage 2 = `wlaunch`: r = u . L^T - L data
+  // quadratic-form plans (dlb_block_desc::q_*): the likelihood evaluation runs `qlaunch` over `qblocks` (ONE term per block: features . q_matrix, single
+  // accumulator per column, Gram entries formed in the epilogue); `launch` / `blocks` keep serving the theory-vector entry
+  bool qform = false;
+  dlb::Launch qlaunch;
+  std::vector<dlb::Block> qblocks;
   bool two_stage = false;
   dlb::Launch wlaunch;
   std::vector<dlb::Block> wblocks;
@@ -440,6 +446,7 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
       bd.tmask = pass == 0 ? b->d_tmask_white : b->d_tmask_plain;
       if (bd.tmask) (pass == 0 ? L.masked_white : L.masked_plain) = true;
       bd.cb_first = pass == 0 ? b->d_cb_first : nullptr;
+      bd.qtile = b->d_qtile; bd.qgroup = b->d_qgroup; bd.qdent = b->d_qdent; bd.qconst = b->d_qconst;
       tab.push_back(bd);
     }
     if (!ok) continue;
@@ -653,9 +660,11 @@ static int run_contract(dlb_plan* plan, const double* d_params, long long N, lon
     }
     return DLB_OK;
   }
-  const Launch& L = plan->launch;
+  const bool qf = mode == 0 && plan->qform;
+  const Launch& L = qf ? plan->qlaunch : plan->launch;
   ContractParams cp;
   fill_params(plan, L, cp, d_params, N, npad);
+  cp.qform = qf ? 1 : 0;
   cp.blocks = mode == 0 ? L.d_white : L.d_plain;
   cp.sched = mode == 0 ? L.d_sched_white : L.d_sched_plain; cp.nsched = mode == 0 ? L.nsched : L.nsched_plain;
   cp.masked = mode == 0 ? L.masked_white : L.masked_plain;
@@ -702,10 +711,11 @@ int dlb_plan_flags(const dlb_plan* plan) {
   if (!plan) return -1;
   bool ozl = false;
   for (const MlpLayers& m : plan->mlps) for (const OzLayer& l : m.oz) ozl = ozl || l.ozaki;
-  return (plan->resident ? 1 : 0) | (plan->two_stage ? 2 : 0) | (plan->mlp_fused_smem ? 4 : 0) | (ozl ? 8 : 0) | (plan->oz_contract ? 16 : 0);
+  return (plan->resident ? 1 : 0) | (plan->two_stage ? 2 : 0) | (plan->mlp_fused_smem ? 4 : 0) | (ozl ? 8 : 0) | (plan->oz_contract ? 16 : 0) | (plan->qform ? 32 : 0);
 }
 double dlb_plan_executed_flops(const dlb_plan* plan) {
   if (!plan) return -1.;
+  if (plan->qform) return plan->qlaunch.flops_exec;
   return plan->two_stage ? plan->launch.flops_exec_plain + plan->wlaunch.flops_exec : plan->launch.flops_exec;
 }
 
@@ -1016,6 +1026,51 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
     plan->tstride = tcol;
   }
   DLB_TRY(build_launch(plan, bptr, resident, ast, desc->ncoef, plan->launch));
+  {   // quadratic-form evaluation (lowering.py: qform_tables): every block or none
+    bool allq = resident && !plan->two_stage && !getenv("DLB_NO_QFORM");
+    for (int ib = 0; ib < desc->nblocks; ++ib) {
+      const dlb_block_desc& bd = desc->blocks[ib];
+      allq = allq && bd.q_ncols > 0 && bd.q_matrix && bd.q_tiles && bd.q_groups && bd.q_dent && bd.q_const && bd.q_ngroups > 0 && (bd.q_ncols % 8) == 0;
+    }
+    const Variant qv{1, 1, 7, 8, 1, 36};
+    if (allq && contract_smem_bytes(qv, 2, true, ast, plan->dpad, desc->ncoef, npart_bound, desc->ngen) <= contract_smem_limit(1)) {
+      plan->qblocks.resize(desc->nblocks);
+      std::vector<Block*> qptr;
+      const int BN = variant_bn(qv);
+      for (int ib = 0; ib < desc->nblocks; ++ib) {
+        const dlb_block_desc& bd = desc->blocks[ib];
+        const dlb_term_desc& t0 = bd.terms[0];
+        Block& qb = plan->qblocks[ib];
+        const Block& ob = plan->blocks[ib];
+        std::vector<TermSpec> terms{TermSpec{0, -1, plan->gens[t0.gen].foff + t0.foff, t0.foff, t0.K, bd.q_matrix, nullptr}};
+        std::vector<double> zeros((size_t)bd.q_ncols, 0.);
+        DLB_TRY(build_block_core(plan, qv, true, bd.q_ncols, 1, terms, zeros.data(), nullptr, 0, nullptr, qb));
+        qb.npart = ob.npart; qb.poff = ob.poff; qb.coloff = ob.coloff; qb.gen = ob.gen; qb.fill = ob.fill; qb.fbase = ob.fbase; qb.d_map = ob.d_map;
+        DLB_REQUIRE(qb.maxcol <= ast, "internal: resident A tile narrower than the quadratic-form features");
+        const int ntile = qb.ncb * (BN / 8), nt_in = bd.q_ncols / 8;
+        std::vector<int> tiles((size_t)3 * ntile, 0);
+        for (int t = 0; t < ntile; ++t) tiles[3 * t] = -1;
+        for (int t = 0; t < nt_in; ++t) {
+          DLB_REQUIRE(bd.q_tiles[3 * t] >= -1 && bd.q_tiles[3 * t] < bd.q_ngroups && bd.q_tiles[3 * t + 1] >= 0 && bd.q_tiles[3 * t + 1] + 8 <= ast + 8 && bd.q_tiles[3 * t + 2] >= 0 &&
+                      bd.q_tiles[3 * t + 2] <= 8, "quadratic-form tables: tile entry out of range");
+          for (int j = 0; j < 3; ++j) tiles[3 * t + j] = bd.q_tiles[3 * t + j];
+        }
+        for (int g = 0; g < bd.q_ngroups; ++g) {
+          const int32_t* q = bd.q_groups + 4 * g;
+          DLB_REQUIRE((q[0] == 0 || q[0] == 1) && q[1] >= 0 && q[1] < ob.npart && q[2] >= -1 && q[2] < desc->ncoef && q[3] >= -1 && q[3] < desc->ncoef,
+                      "quadratic-form tables: group entry out of range");
+          for (int j = 0; j < 8; ++j) DLB_REQUIRE(bd.q_dent[8 * g + j] >= -1 && bd.q_dent[8 * g + j] < ob.npart, "quadratic-form tables: direct entry out of range");
+        }
+        DLB_TRY(upload(plan, tiles.data(), tiles.size(), &qb.d_qtile));
+        DLB_TRY(upload(plan, reinterpret_cast<const int4*>(bd.q_groups), (size_t)bd.q_ngroups, &qb.d_qgroup));
+        DLB_TRY(upload(plan, bd.q_dent, (size_t)8 * bd.q_ngroups, &qb.d_qdent));
+        DLB_TRY(upload(plan, bd.q_const, (size_t)ob.npart, &qb.d_qconst));
+        qptr.push_back(&qb);
+      }
+      DLB_TRY(build_launch(plan, qptr, true, ast, desc->ncoef, plan->qlaunch));
+      plan->qform = true;
+    }
+  }
   if (plan->two_stage) {
     int maxn = 0;
     for (int ib = 0; ib < desc->nblocks; ++ib) maxn = std::max(maxn, desc->blocks[ib].ncols);

@@ -150,12 +150,72 @@ class _Generator(object):
         return g
 
 
+def qform_tables(blk, force=False):
+    """
+    Quadratic-form evaluation of a likelihood block whose terms all contract the SAME K features f (one emulator per tracer: the usual case).
+
+    The normal equations only need dot products of the slot vectors S_a = sum_{x in a} c_x(theta) f . M_x (minus r0 for a = 0) over the n whitened
+    columns, and   (f . M_x) . (f . M_y) = f (M_x M_y^T) f^T   is a quadratic form in the K features.  With T terms the kernel then multiplies f by
+    T (T + 1) / 2 matrices of K x K (+ a few linear columns) instead of T matrices of K x n: fewer columns whenever (T + 1) K / 2 < n -- e.g. 5 tracers x
+    [66 features, 6 terms, n = 406]: 1560 columns instead of 2436 -- and every column is a single accumulator (no slots), so the faster single-slot
+    kernel variants apply.  Exact algebra, done once here in FP64 like the whitening and window folding.
+
+    Output columns, in n-tiles of 8 (one group per tile):
+      * quadratic group (x <= y): columns k' < K hold s_xy (M_x M_y^T)[:, k'], s_xy = 2 if x != y share a slot else 1; the epilogue multiplies column k' by
+        f[k'] and adds the sum, weighted by c_x c_y, to Gram entry pair(slot_x, slot_y);
+      * direct group of term x: column 0 = -(2 if slot_x == 0 else 1) M_x r0 -> entry pair(0, slot_x); column 1 + i = M_x g_i -> entry of (constant row i,
+        slot_x); each weighted by c_x.
+    ``const`` holds the theta-independent parts (|r0|^2, -r0 . g_i).  Returns None when not applicable (or not worthwhile, unless ``force``).
+    """
+    keys, white, R, n = blk['terms'], blk['white'], blk['nslots'], blk['ncols_white']
+    T = len(keys)
+    gi, foff, K = keys[0][2:5]
+    if any(tuple(k[2:5]) != (gi, foff, K) for k in keys) or blk.get('entry_kind') is not None: return None
+    g = np.asarray(blk['gconst_white'], dtype=np.float64).reshape(-1, n)
+    nconst = g.shape[0]
+    if nconst > 7 or T > 16: return None
+    Kp = (K + 7) // 8 * 8
+    ncolq = T * (T + 1) // 2 * Kp + T * 8
+    if not force and (R < 2 or K > 128 or ncolq >= 0.85 * T * (n + nconst)): return None
+    r0 = np.asarray(blk['r0_white'], dtype=np.float64)
+    nS = R * (R + 1) // 2
+
+    def pair(a, b):
+        a, b = min(a, b), max(a, b)
+        return a * R - (a * (a - 1)) // 2 + (b - a)
+
+    mat = np.zeros((K, ncolq))
+    tiles, groups, dent = [], [], []   # tiles: (group, first feature of the tile relative to the generator segment, valid columns)
+    col = 0
+    for x in range(T):
+        for y in range(x, T):
+            a, b = keys[x][0], keys[y][0]
+            mat[:, col:col + K] = (2. if (x != y and a == b) else 1.) * (white[x] @ white[y].T)   # column k' pairs with f[k']: sum_k f_k C[k, k'] f_k'
+            groups.append((0, pair(a, b), keys[x][1], keys[y][1])); dent.append([-1] * 8)
+            for j in range(Kp // 8): tiles.append((len(groups) - 1, foff + 8 * j, min(8, K - 8 * j)))
+            col += Kp
+    for x in range(T):
+        a = keys[x][0]
+        ent = [-1] * 8
+        mat[:, col] = -(2. if a == 0 else 1.) * (white[x] @ r0); ent[0] = pair(0, a)
+        for i in range(nconst):
+            mat[:, col + 1 + i] = white[x] @ g[i]; ent[1 + i] = nS + i * R + a
+        groups.append((1, 0, keys[x][1], -1)); dent.append(ent)
+        tiles.append((len(groups) - 1, foff, 8))
+        col += 8
+    const = np.zeros(nS + R * nconst)
+    const[pair(0, 0)] = r0.dot(r0)
+    for i in range(nconst): const[nS + i * R] = -r0.dot(g[i])
+    return dict(matrix=mat, ncolq=ncolq, gen=gi, foff=foff, K=K, tiles=i32(tiles), groups=i32(groups), dent=i32(dent), const=f64(const))
+
+
 class Lowered(object):
     """Flat arrays + ctypes descriptor (keeps every buffer alive until the plan has been created)."""
 
-    def __init__(self, spec, with_plain=True, reduce_rank=True, merge_terms=True, mlp_slices=0):
+    def __init__(self, spec, with_plain=True, reduce_rank=True, merge_terms=True, mlp_slices=0, qform='auto'):
         self.spec = spec
         self.mlp_slices = int(mlp_slices)
+        self.qform = qform   # quadratic-form evaluation of blocks with solved parameters: 'auto' (when it multiplies fewer columns), True, False
         # derived-expression parameters (reference parameter.py:795-808, base.py:537): columns appended to every parameter row by a small
         # kernel; every index table below addresses the extended row, the batch itself has self.d_in columns
         from .expressions import compile_expression, ExpressionError
@@ -333,7 +393,11 @@ class Lowered(object):
             blk['slot_solved'] = i32([si for si, _ in inv])
             blk['const_solved'] = i32(sorted(const_rows.keys()))
             blk['gconst_white'] = f64([L @ const_rows[si] for si in sorted(const_rows.keys())]).reshape(len(const_rows), ncols)
+            if self.qform is not False and not self.two_stage and blk['ncols_white'] == ncols:
+                blk['qform'] = qform_tables(blk, force=self.qform is True)
             self.blocks.append(blk)
+        if any(b.get('qform') is None for b in self.blocks):   # all blocks or none: one kernel variant per launch
+            for b in self.blocks: b['qform'] = None
         self.ntheory = sum(len(o['data']) for o in observables)
         self.with_plain = with_plain
         self._build_desc()
@@ -485,6 +549,12 @@ class Lowered(object):
             b.matrices_white, b.matrices_plain = as_ptr(white), as_ptr(plain)
             b.r0_white, b.t0_plain = as_ptr(r0), as_ptr(t0)
             b.slot_solved, b.nconst, b.const_solved, b.gconst_white = as_ptr(ss, ctypes.c_int32), len(cs), as_ptr(cs, ctypes.c_int32), as_ptr(gc)
+            if blk.get('qform') is not None:
+                q = blk['qform']
+                qm, qt, qg, qd, qc = f64(q['matrix']), i32(q['tiles']), i32(q['groups']), i32(q['dent']), f64(q['const'])
+                keep += [qm, qt, qg, qd, qc]
+                b.q_ncols, b.q_ngroups = int(q['ncolq']), len(qg)
+                b.q_matrix, b.q_tiles, b.q_groups, b.q_dent, b.q_const = as_ptr(qm), as_ptr(qt, ctypes.c_int32), as_ptr(qg, ctypes.c_int32), as_ptr(qd, ctypes.c_int32), as_ptr(qc)
             if blk.get('entry_kind') is not None:
                 ek, ei, ej = i32(blk['entry_kind']), i32(blk['entry_i']), i32(blk['entry_j'])
                 keep += [ek, ei, ej]
@@ -509,6 +579,10 @@ class Lowered(object):
         gram = 0
         for blk in self.blocks:
             R, nc = blk['nslots'], len(blk['const_solved'])
+            if blk.get('qform') is not None:   # quadratic-form evaluation: ONE matrix [K, ncolq]; the epilogue multiplies every column by its feature
+                contract += 2 * blk['qform']['K'] * blk['qform']['ncolq']
+                gram += 2 * blk['qform']['ncolq']
+                continue
             for (slot, coef, gen, foff, K), mat in zip(blk['terms'], blk['white']):
                 # + nc auxiliary columns per term: the dot products with the constant whitened Jacobian rows come out of the
                 # contraction itself (csrc/plan.cu: build_block_core).  Rank-reduced blocks are lower triangular: only the non-zero

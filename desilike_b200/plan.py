@@ -21,7 +21,7 @@ class Plan(object):
     current torch stream, torch outputs, no host round trip.
     """
 
-    def __init__(self, spec, device=None, with_theory=True, reduce_rank=True, merge_terms=True, mlp_slices=0):
+    def __init__(self, spec, device=None, with_theory=True, reduce_rank=True, merge_terms=True, mlp_slices=0, qform='auto'):
         self._lib = _capi.load()
         if self._lib.dlb_device_count() <= 0:
             raise _capi.DesilikeB200Error('no CUDA device visible: desilike_b200 has no CPU fallback')
@@ -35,7 +35,8 @@ class Plan(object):
         # merge_terms: the tracer combine b1^2 dd + 2 b1 dt + tt of a direct Kaiser theory is formed inside the Kaiser kernel (lowering.py)
         # mlp_slices (opt-in, 2 .. 8): hidden layers of MLP emulators with fan-in >= 64 as FP64-grade GEMMs on the tcgen05 int8 tensor cores
         # (csrc/ozaki.cu); 0 keeps the FP64 DMMA kernels
-        self.lowered = Lowered(spec, with_plain=with_theory, reduce_rank=reduce_rank, merge_terms=merge_terms, mlp_slices=mlp_slices)
+        # qform: blocks with solved parameters as quadratic forms of their features ('auto': when that multiplies fewer columns; True / False)
+        self.lowered = Lowered(spec, with_plain=with_theory, reduce_rank=reduce_rank, merge_terms=merge_terms, mlp_slices=mlp_slices, qform=qform)
         self.params = list(self.lowered.input_names)   # columns of the batch (derived-expression parameters are appended on the device)
         self.d, self.ns, self.ntheory = self.lowered.d_in, self.lowered.ns, self.lowered.ntheory
         self.solved_names = [s['name'] for s in spec.get('solved', [])]
@@ -44,7 +45,7 @@ class Plan(object):
         self._handle = handle
         flags = self._lib.dlb_plan_flags(handle)
         # which kernels the plan runs (include/desilike_b200.h: dlb_plan_flags)
-        self.kernels = {name: bool(flags >> bit & 1) for bit, name in enumerate(['resident_taylor', 'two_stage', 'fused_mlp', 'int8_layers', 'int8_contraction'])}
+        self.kernels = {name: bool(flags >> bit & 1) for bit, name in enumerate(['resident_taylor', 'two_stage', 'fused_mlp', 'int8_layers', 'int8_contraction', 'quadratic_form'])}
         # plan order -> spec order of the solved parameters
         self._unperm = np.argsort(self.lowered.solved_order) if self.ns else np.zeros(0, dtype=int)
         self._identity_perm = bool(np.array_equal(self._unperm, np.arange(self.ns)))   # all '.marg' (or all '.best'): plan order == spec order

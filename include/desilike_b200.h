@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DLB_ABI_VERSION 8
+#define DLB_ABI_VERSION 9
 
 typedef enum {
   DLB_OK = 0,
@@ -122,6 +122,13 @@ typedef struct {
    * precision-weighted ones y_j = P S_j, chi2 / gradient / Hessian entries = S_i . y_j). */
   const int32_t* entry_kind; const int32_t* entry_i; const int32_t* entry_j;
   int32_t skip_const_gram;   /* != 0: the Gram of the constant rows of this block is NOT g_i . g_j (it is supplied through dlb_plan_desc::m0_extra) */
+  /* Optional quadratic-form tables (q_ncols > 0; every block of the plan or none; desilike_b200/lowering.py: qform_tables).  All terms of the block
+   * contract the same K features f; instead of the nterms matrices [K, ncols] the kernel multiplies f by ONE matrix q_matrix [K, q_ncols] whose columns
+   * come in n-tiles of 8, one group per tile: q_tiles[3 t ..] = (group, first feature column of the tile relative to the generator segment, number of
+   * valid columns); q_groups[4 g ..] = (kind, Gram entry, coefficient a, coefficient b; -1 = 1).  kind 0 (quadratic): column k' is multiplied by
+   * feature k', the group's sum weighted by coef_a coef_b is added to its Gram entry.  kind 1 (direct): column j is added, weighted by coef_a, to
+   * Gram entry q_dent[8 g + j] (-1: unused).  q_const [npart] is added to the partials (theta-independent parts).  Same partials as the slot form. */
+  int32_t q_ncols; int32_t q_ngroups; const double* q_matrix; const int32_t* q_tiles; const int32_t* q_groups; const int32_t* q_dent; const double* q_const;
 } dlb_block_desc;
 
 typedef struct {
@@ -164,7 +171,8 @@ void dlb_plan_destroy(dlb_plan* plan);
 int dlb_plan_ntheory(const dlb_plan* plan);      /* total data-vector length n */
 int dlb_plan_nsolved(const dlb_plan* plan);
 /* which kernels the plan runs: bit 0 Taylor monomials inside the contraction kernel, 1 two-stage (observable transform), 2 fused MLP kernel,
- * 3 MLP hidden layers on the tcgen05 int8 path, 4 likelihood blocks as tcgen05 int8 GEMMs + Gram reduction (both opt-in through mlp_slices) */
+ * 3 MLP hidden layers on the tcgen05 int8 path, 4 likelihood blocks as tcgen05 int8 GEMMs + Gram reduction (both opt-in through mlp_slices),
+ * 5 likelihood blocks evaluated as quadratic forms of their features (dlb_block_desc::q_*) */
 int dlb_plan_flags(const dlb_plan* plan);
 /* FP64 tensor-pipe FLOPs per evaluation EXECUTED by the contraction launch(es) of dlb_eval_batch: 2 * k-chunk length * tile width over
  * the (column block, k-chunk) tiles actually multiplied (zero padding inside tiles included, skipped leading zero tiles excluded).

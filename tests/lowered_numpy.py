@@ -54,7 +54,7 @@ def expand(low, X):
     return np.column_stack(cols)
 
 
-def evaluate(low, X, feature_fn=None, white=True):
+def evaluate(low, X, feature_fn=None, white=True, use_qform=False):
     X = expand(low, X)
     N = X.shape[0]
     F, C = features(low, X, feature_fn), coefficients(low, X)
@@ -103,6 +103,38 @@ def evaluate(low, X, feature_fn=None, white=True):
                 continue
         else:
             r = slots[0] - blk['r0_white']
+        if use_qform and blk.get('qform') is not None:
+            # quadratic-form tables (lowering.qform_tables; csrc/contract.cu QF epilogue): the same Gram partials from f . q_matrix
+            q, R, nc = blk['qform'], blk['nslots'], len(blk['const_solved'])
+            f = F[q['gen']]
+            out = f[:, q['foff']:q['foff'] + q['K']] @ q['matrix']
+            nS = R * (R + 1) // 2
+            part = np.zeros((N, nS + R * nc)) + q['const']
+            for t8, (gid, k0, nv) in enumerate(q['tiles']):
+                kind, e, ca, cb = q['groups'][gid]
+                w = (C[:, ca] if ca >= 0 else 1.) * (C[:, cb] if cb >= 0 else 1.)
+                cols = out[:, 8 * t8:8 * t8 + 8]
+                if kind == 0: part[:, e] += w * np.sum(cols[:, :nv] * f[:, k0:k0 + nv], axis=-1)
+                else:
+                    for j in range(8):
+                        if q['dent'][gid][j] >= 0: part[:, q['dent'][gid][j]] += w * cols[:, j]
+            sidx = [None] + [int(si) for si in blk['slot_solved']]
+            for a in range(R):
+                for b in range(a, R):
+                    v = part[:, a * R - (a * (a - 1)) // 2 + (b - a)]
+                    if a == 0 and b == 0: chi2 += v
+                    elif a == 0: gL[:, sidx[b]] -= v
+                    else:
+                        M[:, sidx[a], sidx[b]] += v
+                        if a != b: M[:, sidx[b], sidx[a]] += v
+            for i, ci in enumerate(blk['const_solved']):
+                for a in range(R):
+                    v = part[:, nS + i * R + a]
+                    if a == 0: gL[:, int(ci)] -= v
+                    else:
+                        M[:, sidx[a], int(ci)] += v; M[:, int(ci), sidx[a]] += v
+                for j, cj in enumerate(blk['const_solved']): M[:, int(ci), int(cj)] += blk['gconst_white'][i].dot(blk['gconst_white'][j])
+            continue
         if blk.get('entry_kind') is not None:
             # explicit meaning of the Gram partials (split dense plans, csrc/plan.cu: build_block): pairs (a <= b) then constant rows x slots
             R, vals = blk['nslots'], []

@@ -311,3 +311,33 @@ def test_split_dense_precision_lowering(ntracers):
     got = lowered_numpy.evaluate(low, X)
     assert np.allclose(got['loglikelihood'], ref['loglikelihood'], rtol=1e-11, atol=1e-9)
     assert np.allclose(got['x_solved'], ref['x_solved'], rtol=1e-8, atol=1e-8)
+
+
+@pytest.mark.parametrize('name', ['c4_mlp', 'c5_taylor_solved', 'eft_marg_best'])
+def test_quadratic_form_tables_reproduce_the_slot_form(name):
+    """Blocks with solved parameters whose terms share one feature segment can be evaluated as quadratic forms f (M_x M_y^T) f^T of the features
+    (lowering.qform_tables): the NumPy mirror of that epilogue gives the same chi2 / normal equations as the slot form and the oracle; 'auto'
+    only switches when it multiplies fewer columns (the full-size 5-tracer configurations do, the small ones here are forced)."""
+    from desilike_b200.lowering import Lowered
+    spec = {'c4_mlp': lambda: configs.config_c4(ntracers=2, nkin=40, nbins=10, hidden=(16, 16)),
+            'c5_taylor_solved': lambda: configs.config_c5(ntracers=2, nkin=40, nbins=12, order=2, solved=True),
+            'eft_marg_best': lambda: configs.config_kaiser_window(eftlike=True, solved=True)}[name]()
+    X = configs.sample_points(spec, 7, seed=11)
+    ref = pipeline.evaluate(spec, X)
+    fn = _mlp_features if name == 'c4_mlp' else lowered_numpy.theory_features
+    low = Lowered(spec, qform=True)
+    if name == 'eft_marg_best':   # terms over different feature sub-segments (Kaiser tables): not applicable, the slot form stays
+        assert all(b.get('qform') is None for b in low.blocks)
+        return
+    assert all(b.get('qform') is not None for b in low.blocks)
+    slot = lowered_numpy.evaluate(low, X, feature_fn=fn)
+    quad = lowered_numpy.evaluate(low, X, feature_fn=fn, use_qform=True)
+    for key in ('logposterior', 'loglikelihood', 'x_solved'):
+        assert np.allclose(quad[key], slot[key], rtol=1e-10, atol=1e-8), key
+        assert np.allclose(quad[key], ref[key], rtol=1e-9, atol=1e-7), key
+    assert all(b.get('qform') is None for b in Lowered(spec, qform=False).blocks)
+    # full-size 5-tracer blocks: 6 terms x 66 features against 402 + 4 columns -> 'auto' picks the quadratic form (1560 instead of 2436 columns)
+    if name == 'c4_mlp':
+        big = Lowered(configs.config_c4(ntracers=1), with_plain=False)
+        q = big.blocks[0]['qform']
+        assert q is not None and q['ncolq'] == 21 * 72 + 6 * 8 and q['matrix'].shape == (66, 1560)

@@ -1,0 +1,35 @@
+"""Quadratic-form evaluation of blocks with solved parameters (lowering.qform_tables + the QF epilogue of csrc/contract.cu): same chi2, marginalised /
+profiled parameters and status as the slot form and as the oracle."""
+import numpy as np
+import pytest
+
+from oracle import configs, pipeline
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('name', ['c4_small_forced', 'c5solved_small_forced', 'c4_full_auto', 'c5solved_full_auto'])
+def test_quadratic_form_plan_matches_slot_form_and_oracle(gpu_required, name):
+    import desilike_b200
+    spec, force = {'c4_small_forced': (lambda: configs.config_c4(ntracers=2, nkin=40, nbins=10, hidden=(16, 16)), True),
+                   'c5solved_small_forced': (lambda: configs.config_c5(ntracers=2, nkin=40, nbins=12, order=2, solved=True), True),
+                   'c4_full_auto': (lambda: configs.config_c4(ntracers=2), 'auto'),
+                   'c5solved_full_auto': (lambda: configs.config_c5(ntracers=2, solved=True), 'auto')}[name]
+    spec = spec()
+    X = configs.sample_points(spec, 1000 if 'small' in name else 300, seed=13)
+    ref = pipeline.evaluate(spec, X)
+    quad = desilike_b200.Plan(spec, qform=force)
+    slot = desilike_b200.Plan(spec, qform=False)
+    assert quad.kernels['quadratic_form'] and not slot.kernels['quadratic_form']
+    got, base = quad.eval(X), slot.eval(X)
+    scale = np.max(np.abs(ref['loglikelihood']))
+    for other in (ref, base):
+        assert np.max(np.abs(got['loglikelihood'] - other['loglikelihood'])) < 1e-10 * scale
+        assert np.allclose(got['x_solved'], other['x_solved'], rtol=1e-7, atol=1e-8 * np.max(np.abs(ref['x_solved'])))
+        assert np.allclose(got['logposterior'], other['logposterior'], rtol=1e-9, atol=1e-7)
+    assert np.array_equal(got['status'], base['status'])
+    # theory vectors still come from the term matrices
+    assert np.array_equal(quad.theory(X[:50]), slot.theory(X[:50]))
+    # several passes / ragged tails
+    sub = quad.eval(X[:77])
+    assert np.array_equal(sub['logposterior'], got['logposterior'][:77])
