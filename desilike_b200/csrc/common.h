@@ -89,9 +89,9 @@ struct BlockDev {     // one output block as seen by the contraction kernel (dev
                                        // rank-reduced, lower-triangular problem are neither loaded nor multiplied), or NULL
   const unsigned long long* tmask;     // [ncb][nchunks][2] per (column block, k-chunk, warp of the pair): up to 8 runs of k4 steps, 8 bits each (5 bits
                                        // length, 3 bits = number of leading n-tiles of that warp with non-zero 4 x 8 sub-tiles); ~0: everything is multiplied; or NULL
-  // quadratic-form blocks (dlb_block_desc::q_*; contract.cu QF epilogue): per 8-column n-tile (group, first feature column, valid columns), padded to
-  // ncb * BN / 8 tiles with group -1; per group (kind, Gram entry, coefficient a, coefficient b); direct groups: Gram entry of each of their 8 columns
-  const int* qtile; const int4* qgroup; const int* qdent; const double* qconst;
+  // quadratic-form blocks (dlb_block_desc::q_*; contract.cu QF epilogue): per 8-column n-tile a 16-byte record (group, valid columns, kind, first feature
+  // column, Gram entry, coefficients), padded to ncb * BN / 8 tiles with group -1; direct groups: Gram entry of each of their 8 columns
+  const int* qtile; const int* qdent; const double* qconst;   // qtile: one int4 record per n-tile (contract.cu QF epilogue)
   int oslot;                           // output mode of a transformed multi-slot block: column stride between the slots' outputs (0: slot 0 only)
   const double* tdata;                 // output mode: [ncols] data d of the 'cubic'-transformed columns (0: untransformed column), or NULL
 };

@@ -104,14 +104,16 @@ __device__ __forceinline__ double ipow(double x, int n) {
 // One k-chunk of DMMAs for MTC active m-tiles: acc[mt][nt] += (beta[mt] * A[mt-rows, k]) . B[k, nt-cols].
 // The two warps of a pair interleave their n-tiles (warp wn owns the 8-column tiles 2 nt + wn of the column block), so that column
 // blocks whose right part is structurally zero (triangular rank-reduced problems, padding of the last block) stay balanced over the pair.
-template <int MT, int NT, int MTC, int KC>
+// BETA = false: the A fragment is used as is (quadratic-form blocks: no per-point coefficient on the terms -- and no scalar FP64 multiply queued behind
+// the DMMAs in the shared FP64 pipe).
+template <int MT, int NT, int MTC, int KC, bool BETA = true>
 __device__ __forceinline__ void mma_chunk(double (&acc)[MT][NT][2], const double* __restrict__ A, int astride, const double* __restrict__ B,
                                           const double (&beta)[MT], int nk4) {
 #pragma unroll 3
   for (int k4 = 0; k4 < nk4; ++k4) {
     double a[MTC], b[NT];
 #pragma unroll
-    for (int mt = 0; mt < MTC; ++mt) a[mt] = A[mt * astride + k4 * 4] * beta[mt];
+    for (int mt = 0; mt < MTC; ++mt) a[mt] = BETA ? A[mt * astride + k4 * 4] * beta[mt] : A[mt * astride + k4 * 4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) b[nt] = B[nt * 16 * KC + k4 * 4];
 #pragma unroll
@@ -177,16 +179,16 @@ __device__ __forceinline__ void mma_chunk_masked(double (&acc)[MT][NT][2], const
   else mma_chunk_masked_m<MT, NT, KC, false>(acc, A, astride, B, beta, mtc, mask);
 }
 
-template <int MT, int NT, int KC, bool MASKED>
+template <int MT, int NT, int KC, bool MASKED, bool BETA = true>
 __device__ __forceinline__ void mma_chunk_dispatch(double (&acc)[MT][NT][2], const double* A, int astride, const double* B, const double (&beta)[MT],
                                                    int nk4, int mtc, unsigned long long mask) {
   if constexpr (MASKED) {
     if (mask != ~0ull) { mma_chunk_masked<MT, NT, KC>(acc, A, astride, B, beta, mtc, mask); return; }
   }
-  if (mtc == MT) { mma_chunk<MT, NT, MT, KC>(acc, A, astride, B, beta, nk4); return; }
-  if constexpr (MT > 1) { if (mtc == 1) { mma_chunk<MT, NT, 1, KC>(acc, A, astride, B, beta, nk4); return; } }
-  if constexpr (MT > 2) { if (mtc == 2) { mma_chunk<MT, NT, 2, KC>(acc, A, astride, B, beta, nk4); return; } }
-  if constexpr (MT > 3) { if (mtc == 3) { mma_chunk<MT, NT, 3, KC>(acc, A, astride, B, beta, nk4); return; } }
+  if (mtc == MT) { mma_chunk<MT, NT, MT, KC, BETA>(acc, A, astride, B, beta, nk4); return; }
+  if constexpr (MT > 1) { if (mtc == 1) { mma_chunk<MT, NT, 1, KC, BETA>(acc, A, astride, B, beta, nk4); return; } }
+  if constexpr (MT > 2) { if (mtc == 2) { mma_chunk<MT, NT, 2, KC, BETA>(acc, A, astride, B, beta, nk4); return; } }
+  if constexpr (MT > 3) { if (mtc == 3) { mma_chunk<MT, NT, 3, KC, BETA>(acc, A, astride, B, beta, nk4); return; } }
 }
 
 // Position in the CTA's chunk sequence (tile, block, column block, chunk); chunk == nchunks is the epilogue-constants chunk.
@@ -257,6 +259,11 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
   }
   if constexpr (RESIDENT) {
     for (int i = tid; i < p.ngen * (int)(sizeof(GenDev) / 4); i += NTH) reinterpret_cast<int*>(gens_s)[i] = reinterpret_cast<const int*>(p.gens)[i];
+  }
+  if constexpr (QF) {   // the epilogue reads feature columns up to the 8-column padding of a group (x exact zeros): every A entry must be finite
+    for (int i = tid; i < BM * p.ast; i += NTH) A_s[i] = 0.;
+    for (int i = tid; i < 2 * BM * p.dpad; i += NTH) xs0[i] = 0.;
+    __syncthreads();
   }
   for (int i = tid; i < 2 * BM; i += NTH) xs0[(size_t)i * p.dpad + p.d] = 1.;   // constant-one column (absent monomial factors)
   // Parameter rows of this warp pair for a tile starting at unit u with mtc units -> buffer xb (cp.async; rows beyond N replicate
@@ -493,15 +500,16 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
           const int nk4 = ch.w >> 2;
 #pragma unroll
           for (int sl = 0; sl < R; ++sl)
-            if (ch.x == sl) mma_chunk_dispatch<MT, NT, KC, MASKED>(acc[sl], Ap, astride, Bp, beta, nk4, mtc, mask);
+            if (ch.x == sl) mma_chunk_dispatch<MT, NT, KC, MASKED, !QF>(acc[sl], Ap, astride, Bp, beta, nk4, mtc, mask);
           PROF(3)
           release(s);
           PROF(5)
           if (++s == S) { s = 0; ph ^= 1; }
         }
 
-        // ===== epilogue: r0 of this column block arrives as one more transaction of the ring =====
-        mbar_wait_u32(full_u32 + 8u * s, ph);
+        // ===== epilogue: r0 of this column block arrives as one more transaction of the ring (quadratic-form blocks have no such constants: their
+        //       schedule carries the k-chunks only, so the next column block's chunk is already in flight) =====
+        if constexpr (!QF) mbar_wait_u32(full_u32 + 8u * s, ph);
         PROF(0)
         const int colw = wn * 8 + 2 * lc;  // + nt * 16 + e   (interleaved n-tiles: warp wn owns the 8-column tiles 2 nt + wn)
         const double* epi = stage_base + (size_t)s * STAGE_DOUBLES;
@@ -546,47 +554,55 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
             }
           }
         } else if constexpr (QF) {
-          // ===== quadratic-form epilogue: this warp's n-tiles of 8 columns each belong to one group =====
-          const int* qt = blk->qtile + 3 * (cb * (BN / 8) + wn);   // n-tile 2 nt + wn of the column block
-          int cur = -1;
+          // ===== quadratic-form epilogue: this warp's n-tiles of 8 columns each belong to one group.  Per tile one 16-byte record
+          //       { group | valid columns << 16 | kind << 24, first feature column, Gram entry, (coef a + 1) | (coef b + 1) << 16 } =====
+          const int4* qt = reinterpret_cast<const int4*>(blk->qtile) + (cb * (BN / 8) + wn);   // n-tile 2 nt + wn of the column block
+          int4 meta[NT];
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) meta[nt] = __ldg(qt + 2 * nt);
+          int cur = -1, cur_e = 0, cur_c = 0;
           double sum[MT];
+          const double* frow[MT];
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) frow[mt] = A_s + (size_t)(mt * UNIT + wm * 8 + lr) * p.ast + 2 * lc;
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) sum[mt] = 0.;
-          auto flush = [&](int gid) {   // quadratic group: quad reduction over the 8 columns of the lanes sharing a row, weighted scatter
-            const int4 grp = __ldg(blk->qgroup + gid);
+          auto flush = [&]() {   // quadratic group: quad reduction over the 8 columns of the lanes sharing a row, weighted scatter
+            const int ca = (cur_c & 0xFFFF) - 1, cbq = (cur_c >> 16) - 1;
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
               double sq = sum[mt];
               sq += __shfl_xor_sync(0xffffffffu, sq, 1);
               sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-              if (lc == 0 && mt < mtc && grp.x == 0) {
+              if (lc == 0 && mt < mtc) {
                 const int row = mt * UNIT + wm * 8 + lr;
-                const double w = (grp.z >= 0 ? cs[grp.z * BM + row] : 1.) * (grp.w >= 0 ? cs[grp.w * BM + row] : 1.);
-                red[((size_t)wn * BM + row) * npm + grp.y] += sq * w;
+                const double w = (ca >= 0 ? cs[ca * BM + row] : 1.) * (cbq >= 0 ? cs[cbq * BM + row] : 1.);
+                red[((size_t)wn * BM + row) * npm + cur_e] += sq * w;
               }
               sum[mt] = 0.;
             }
           };
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
-            const int gid = __ldg(qt + 6 * nt), k0 = __ldg(qt + 6 * nt + 1), nv = __ldg(qt + 6 * nt + 2);
-            if (gid != cur) { if (cur >= 0) flush(cur); cur = gid; }
+            const int gid = (short)(meta[nt].x & 0xFFFF), kind = meta[nt].x >> 24, k0 = meta[nt].y;
+            if (gid != cur) { if (cur >= 0) flush(); cur = kind == 0 ? gid : -1; cur_e = meta[nt].z; cur_c = meta[nt].w; }
             if (gid < 0) continue;
-            const int4 grp = __ldg(blk->qgroup + gid);
-            if (grp.x == 0) {
+            if (kind == 0) {
+              // columns beyond the group's K features hold exact zeros in the accumulators (zero matrix columns) and finite values in A_s (zeroed
+              // at kernel start; a read past the row end lands in the next row / the parameter tile): no guard needed
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
-                const double* f = A_s + (size_t)(mt * UNIT + wm * 8 + lr) * p.ast + k0 + 2 * lc;
-                const double f0 = 2 * lc < nv ? f[0] : 0., f1 = 2 * lc + 1 < nv ? f[1] : 0.;
-                sum[mt] = fma(acc[0][mt][nt][0], f0, fma(acc[0][mt][nt][1], f1, sum[mt]));
+                const double2 f = *reinterpret_cast<const double2*>(frow[mt] + k0);
+                sum[mt] = fma(acc[0][mt][nt][0], f.x, fma(acc[0][mt][nt][1], f.y, sum[mt]));
               }
             } else {   // direct group: every column is its own Gram entry
               const int e0 = __ldg(blk->qdent + gid * 8 + 2 * lc), e1 = __ldg(blk->qdent + gid * 8 + 2 * lc + 1);
+              const int ca = (meta[nt].w & 0xFFFF) - 1;
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
                 if (mt < mtc) {
                   const int row = mt * UNIT + wm * 8 + lr;
-                  const double w = grp.z >= 0 ? cs[grp.z * BM + row] : 1.;
+                  const double w = ca >= 0 ? cs[ca * BM + row] : 1.;
                   double* redrow = red + ((size_t)wn * BM + row) * npm;
                   if (e0 >= 0) redrow[e0] += acc[0][mt][nt][0] * w;
                   if (e1 >= 0) redrow[e1] += acc[0][mt][nt][1] * w;
@@ -594,7 +610,7 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
               }
             }
           }
-          if (cur >= 0) flush(cur);
+          if (cur >= 0) flush();
         } else {
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
@@ -649,9 +665,11 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
           }
         }
         PROF(6)
-        release(s);
-        PROF(5)
-        if (++s == S) { s = 0; ph ^= 1; }
+        if constexpr (!QF) {
+          release(s);
+          PROF(5)
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
       }  // cb
 
       if (p.mode == 0) {
@@ -687,6 +705,22 @@ int launch_variant(const ContractParams& p, int grid, size_t smem, cudaStream_t 
   return DLB_OK;
 }
 
+#if !DLB_CONTRACT_MASKED
+template <int NT, int KC>
+int launch_qf(const ContractParams& p, int grid, size_t smem, cudaStream_t stream) {
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[current_device_slot()];
+  if (!configured) {
+    DLB_CUDA(cudaFuncSetAttribute(contract_kernel<1, 1, NT, 8, 1, KC, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)contract_smem_limit(1)));
+    configured = true;
+  }
+  contract_kernel<1, 1, NT, 8, 1, KC, true, false, true><<<grid, 8 * 64, smem, stream>>>(p);
+  g_launches++;
+  DLB_CUDA(cudaGetLastError());
+  return DLB_OK;
+}
+#endif
+
 template <int R, int MT, int NT, int WM, int CPS, int KC>
 int launch_mode(const ContractParams& p, int grid, size_t smem, cudaStream_t stream) {
   return p.resident ? launch_variant<R, MT, NT, WM, CPS, KC, true>(p, grid, smem, stream) : launch_variant<R, MT, NT, WM, CPS, KC, false>(p, grid, smem, stream);
@@ -721,18 +755,13 @@ int launch_contract(const Variant& v, const ContractParams& p, int nsm, cudaStre
   if (smem > contract_smem_limit(v.CPS)) { set_error("contraction kernel: shared-memory budget exceeded"); return DLB_ERR_UNSUPPORTED; }
   const int grid = (int)std::min<long long>((long long)nsm * v.CPS, std::max<long long>(p.U, 1));
 #if !DLB_CONTRACT_MASKED
-  if (p.qform) {   // quadratic-form blocks: 16 warps, 64 x 112 tile, one accumulator per column, resident A
-    if (!(v.R == 1 && v.MT == 1 && v.NT == 7 && v.WM == 8 && v.CPS == 1 && v.KC == 36 && p.resident)) { set_error("quadratic-form plan: unexpected kernel variant"); return DLB_ERR_UNSUPPORTED; }
-    static bool configured_dev[64] = {};
-    bool& configured = configured_dev[current_device_slot()];
-    if (!configured) {
-      DLB_CUDA(cudaFuncSetAttribute(contract_kernel<1, 1, 7, 8, 1, 36, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)contract_smem_limit(1)));
-      configured = true;
-    }
-    contract_kernel<1, 1, 7, 8, 1, 36, true, false, true><<<grid, 8 * 64, smem, stream>>>(p);
-    g_launches++;
-    DLB_CUDA(cudaGetLastError());
-    return DLB_OK;
+  if (p.qform) {   // quadratic-form blocks: 16 warps, 64-row tiles, one accumulator per column, resident A
+    if (!(v.R == 1 && v.MT == 1 && v.WM == 8 && v.CPS == 1 && p.resident)) { set_error("quadratic-form plan: unexpected kernel variant"); return DLB_ERR_UNSUPPORTED; }
+    if (v.NT == 7 && v.KC == 36) return launch_qf<7, 36>(p, grid, smem, stream);
+    if (v.NT == 6 && v.KC == 76) return launch_qf<6, 76>(p, grid, smem, stream);
+    if (v.NT == 7 && v.KC == 68) return launch_qf<7, 68>(p, grid, smem, stream);
+    set_error("quadratic-form plan: unexpected kernel variant");
+    return DLB_ERR_UNSUPPORTED;
   }
 #endif
   if (v.R == 1 && v.MT == 2 && v.NT == 7 && v.WM == 4 && v.CPS == 2 && v.KC == 28) return launch_mode<1, 2, 7, 4, 2, 28>(p, grid, smem, stream);

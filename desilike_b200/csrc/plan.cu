@@ -40,7 +40,7 @@ struct Block {
   double *d_tiles_white = nullptr, *d_tiles_plain = nullptr, *d_epi_white = nullptr, *d_epi_plain = nullptr;
   EntryMap* d_map = nullptr;
   std::vector<EntryMap> h_map;
-  int *d_qtile = nullptr, *d_qdent = nullptr; int4* d_qgroup = nullptr; double* d_qconst = nullptr;   // quadratic-form tables (dlb_block_desc::q_*)
+  int *d_qtile = nullptr, *d_qdent = nullptr; double* d_qconst = nullptr;   // quadratic-form tables (dlb_block_desc::q_*), tiles as packed 16-byte records
   double* d_tdata = nullptr;   // 'cubic' observable transform: data of the transformed columns (two-stage plans)
   int tcol = 0;                // first column of the block in the transformed-theory buffer of a two-stage plan
 };
@@ -446,7 +446,7 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
       bd.tmask = pass == 0 ? b->d_tmask_white : b->d_tmask_plain;
       if (bd.tmask) (pass == 0 ? L.masked_white : L.masked_plain) = true;
       bd.cb_first = pass == 0 ? b->d_cb_first : nullptr;
-      bd.qtile = b->d_qtile; bd.qgroup = b->d_qgroup; bd.qdent = b->d_qdent; bd.qconst = b->d_qconst;
+      bd.qtile = b->d_qtile; bd.qdent = b->d_qdent; bd.qconst = b->d_qconst;
       tab.push_back(bd);
     }
     if (!ok) continue;
@@ -471,7 +471,7 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
           (pass == 0 ? L.flops_exec : L.flops_exec_plain) += 2. * (ex.empty() ? (double)b->h_chunks[c].kc * BN : ex[(size_t)cb * b->nchunks + c]);
           sched.push_back(SchedEntry{tab[ib].tiles + ((size_t)cb * b->nchunks + c) * ((size_t)BN * KC), (unsigned)(BN * KC * 8), (int)((ib << 16) | (unsigned)c)});
         }
-        sched.push_back(SchedEntry{tab[ib].epi + (size_t)cb * BN, (unsigned)(BN * 8), -1});
+        if (!b->d_qtile) sched.push_back(SchedEntry{tab[ib].epi + (size_t)cb * BN, (unsigned)(BN * 8), -1});   // (quadratic-form blocks have no epilogue constants)
       }
     }
     (pass == 0 ? L.nsched : L.nsched_plain) = (int)sched.size();
@@ -1032,8 +1032,22 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
       const dlb_block_desc& bd = desc->blocks[ib];
       allq = allq && bd.q_ncols > 0 && bd.q_matrix && bd.q_tiles && bd.q_groups && bd.q_dent && bd.q_const && bd.q_ngroups > 0 && (bd.q_ncols % 8) == 0;
     }
-    const Variant qv{1, 1, 7, 8, 1, 36};
-    if (allq && contract_smem_bytes(qv, 2, true, ast, plan->dpad, desc->ncoef, npart_bound, desc->ngen) <= contract_smem_limit(1)) {
+    // 16 warps, 64-row tiles.  Preference: one k-chunk per column block (the per-chunk cost -- stage release, barrier wait -- is the largest loss of short
+    // contractions): KC = 68 with 112-column blocks when the features fit, else KC = 76 with 96-column blocks, else two chunks of 36
+    int qK = 0;
+    for (int ib = 0; ib < desc->nblocks && allq; ++ib) qK = std::max(qK, desc->blocks[ib].terms[0].K);
+    std::vector<Variant> qcand;
+    if (const char* e = getenv("DLB_QF_VARIANT")) { const int i = atoi(e); qcand.push_back(i == 0 ? Variant{1, 1, 7, 8, 1, 68} : (i == 1 ? Variant{1, 1, 6, 8, 1, 76} : Variant{1, 1, 7, 8, 1, 36})); }
+    else {
+      if (chunk_extent(qK) <= 68) qcand.push_back(Variant{1, 1, 7, 8, 1, 68});
+      if (chunk_extent(qK) <= 76) qcand.push_back(Variant{1, 1, 6, 8, 1, 76});
+      qcand.push_back(Variant{1, 1, 7, 8, 1, 36});
+    }
+    Variant qv = qcand.back();
+    bool qfits = false;
+    for (const Variant& c : qcand)
+      if (contract_smem_bytes(c, 2, true, ast, plan->dpad, desc->ncoef, npart_bound, desc->ngen) <= contract_smem_limit(1)) { qv = c; qfits = true; break; }
+    if (allq && qfits) {
       plan->qblocks.resize(desc->nblocks);
       std::vector<Block*> qptr;
       const int BN = variant_bn(qv);
@@ -1048,21 +1062,26 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
         qb.npart = ob.npart; qb.poff = ob.poff; qb.coloff = ob.coloff; qb.gen = ob.gen; qb.fill = ob.fill; qb.fbase = ob.fbase; qb.d_map = ob.d_map;
         DLB_REQUIRE(qb.maxcol <= ast, "internal: resident A tile narrower than the quadratic-form features");
         const int ntile = qb.ncb * (BN / 8), nt_in = bd.q_ncols / 8;
-        std::vector<int> tiles((size_t)3 * ntile, 0);
-        for (int t = 0; t < ntile; ++t) tiles[3 * t] = -1;
-        for (int t = 0; t < nt_in; ++t) {
-          DLB_REQUIRE(bd.q_tiles[3 * t] >= -1 && bd.q_tiles[3 * t] < bd.q_ngroups && bd.q_tiles[3 * t + 1] >= 0 && bd.q_tiles[3 * t + 1] + 8 <= ast + 8 && bd.q_tiles[3 * t + 2] >= 0 &&
-                      bd.q_tiles[3 * t + 2] <= 8, "quadratic-form tables: tile entry out of range");
-          for (int j = 0; j < 3; ++j) tiles[3 * t + j] = bd.q_tiles[3 * t + j];
-        }
         for (int g = 0; g < bd.q_ngroups; ++g) {
           const int32_t* q = bd.q_groups + 4 * g;
           DLB_REQUIRE((q[0] == 0 || q[0] == 1) && q[1] >= 0 && q[1] < ob.npart && q[2] >= -1 && q[2] < desc->ncoef && q[3] >= -1 && q[3] < desc->ncoef,
                       "quadratic-form tables: group entry out of range");
           for (int j = 0; j < 8; ++j) DLB_REQUIRE(bd.q_dent[8 * g + j] >= -1 && bd.q_dent[8 * g + j] < ob.npart, "quadratic-form tables: direct entry out of range");
         }
+        DLB_REQUIRE(bd.q_ngroups < 32768 && desc->ncoef < 65535, "quadratic-form tables: too many groups / coefficients");
+        // one 16-byte record per n-tile: { group | valid columns << 16 | kind << 24, first feature column, Gram entry, (coef a + 1) | (coef b + 1) << 16 }
+        std::vector<int> tiles((size_t)4 * ntile, 0);
+        for (int t = 0; t < ntile; ++t) tiles[4 * t] = 0xFFFF;   // group -1
+        for (int t = 0; t < nt_in; ++t) {
+          const int gid = bd.q_tiles[3 * t], k0 = bd.q_tiles[3 * t + 1], nv = bd.q_tiles[3 * t + 2];
+          DLB_REQUIRE(gid >= -1 && gid < bd.q_ngroups && k0 >= 0 && k0 <= ast && nv >= 0 && nv <= 8, "quadratic-form tables: tile entry out of range");
+          if (gid < 0) continue;
+          const int32_t* q = bd.q_groups + 4 * gid;
+          tiles[4 * t] = gid | (nv << 16) | (q[0] << 24);
+          tiles[4 * t + 1] = k0; tiles[4 * t + 2] = q[1];
+          tiles[4 * t + 3] = (q[2] + 1) | ((q[3] + 1) << 16);
+        }
         DLB_TRY(upload(plan, tiles.data(), tiles.size(), &qb.d_qtile));
-        DLB_TRY(upload(plan, reinterpret_cast<const int4*>(bd.q_groups), (size_t)bd.q_ngroups, &qb.d_qgroup));
         DLB_TRY(upload(plan, bd.q_dent, (size_t)8 * bd.q_ngroups, &qb.d_qdent));
         DLB_TRY(upload(plan, bd.q_const, (size_t)ob.npart, &qb.d_qconst));
         qptr.push_back(&qb);
