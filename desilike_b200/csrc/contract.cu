@@ -555,49 +555,44 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
           }
         } else if constexpr (QF) {
           // ===== quadratic-form epilogue: this warp's n-tiles of 8 columns each belong to one group.  Per tile one 16-byte record
-          //       { group | valid columns << 16 | kind << 24, first feature column, Gram entry, (coef a + 1) | (coef b + 1) << 16 } =====
+          //       { group | valid columns << 16 | kind << 24, first feature column, Gram entry, (coef a + 1) | (coef b + 1) << 16 }.
+          //       Every quadratic tile is reduced and scattered on its own -- short straight-line code (the version that merged the tiles of a
+          //       group before reducing was if-converted into ~700 instructions per column block) =====
           const int4* qt = reinterpret_cast<const int4*>(blk->qtile) + (cb * (BN / 8) + wn);   // n-tile 2 nt + wn of the column block
           int4 meta[NT];
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) meta[nt] = __ldg(qt + 2 * nt);
-          int cur = -1, cur_e = 0, cur_c = 0;
-          double sum[MT];
           const double* frow[MT];
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) frow[mt] = A_s + (size_t)(mt * UNIT + wm * 8 + lr) * p.ast + 2 * lc;
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) sum[mt] = 0.;
-          auto flush = [&]() {   // quadratic group: quad reduction over the 8 columns of the lanes sharing a row, weighted scatter
-            const int ca = (cur_c & 0xFFFF) - 1, cbq = (cur_c >> 16) - 1;
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              double sq = sum[mt];
-              sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-              sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-              if (lc == 0 && mt < mtc) {
-                const int row = mt * UNIT + wm * 8 + lr;
-                const double w = (ca >= 0 ? cs[ca * BM + row] : 1.) * (cbq >= 0 ? cs[cbq * BM + row] : 1.);
-                red[((size_t)wn * BM + row) * npm + cur_e] += sq * w;
-              }
-              sum[mt] = 0.;
-            }
-          };
+          int any_direct = 0;
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
-            const int gid = (short)(meta[nt].x & 0xFFFF), kind = meta[nt].x >> 24, k0 = meta[nt].y;
-            if (gid != cur) { if (cur >= 0) flush(); cur = kind == 0 ? gid : -1; cur_e = meta[nt].z; cur_c = meta[nt].w; }
-            if (gid < 0) continue;
-            if (kind == 0) {
-              // columns beyond the group's K features hold exact zeros in the accumulators (zero matrix columns) and finite values in A_s (zeroed
-              // at kernel start; a read past the row end lands in the next row / the parameter tile): no guard needed
+            // columns beyond the group's K features hold exact zeros in the accumulators (zero matrix columns) and finite values in A_s (zeroed at
+            // kernel start; a read past the row end lands in the next row / the parameter tile): no guard needed.  Padding tiles (group -1) and
+            // direct tiles carry weight 0 here.
+            const int kind = meta[nt].x >> 24, ca = (meta[nt].w & 0xFFFF) - 1, cbq = (meta[nt].w >> 16) - 1;
+            const bool quad = kind == 0 && (meta[nt].x & 0xFFFF) != 0xFFFF;
+            any_direct |= kind;
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                const double2 f = *reinterpret_cast<const double2*>(frow[mt] + k0);
-                sum[mt] = fma(acc[0][mt][nt][0], f.x, fma(acc[0][mt][nt][1], f.y, sum[mt]));
+            for (int mt = 0; mt < MT; ++mt) {
+              const double2 f = *reinterpret_cast<const double2*>(frow[mt] + meta[nt].y);
+              double sq = fma(acc[0][mt][nt][0], f.x, acc[0][mt][nt][1] * f.y);
+              sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+              sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+              if (lc == 0 && mt < mtc && quad) {
+                const int row = mt * UNIT + wm * 8 + lr;
+                const double w = (ca >= 0 ? cs[ca * BM + row] : 1.) * (cbq >= 0 ? cs[cbq * BM + row] : 1.);
+                red[((size_t)wn * BM + row) * npm + meta[nt].z] += sq * w;
               }
-            } else {   // direct group: every column is its own Gram entry
+            }
+          }
+          if (any_direct) {   // (warp-uniform; one column block in ~14 holds the direct groups) every column is its own Gram entry
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+              if ((meta[nt].x >> 24) == 0) continue;
+              const int gid = meta[nt].x & 0xFFFF, ca = (meta[nt].w & 0xFFFF) - 1;
               const int e0 = __ldg(blk->qdent + gid * 8 + 2 * lc), e1 = __ldg(blk->qdent + gid * 8 + 2 * lc + 1);
-              const int ca = (meta[nt].w & 0xFFFF) - 1;
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
                 if (mt < mtc) {
@@ -610,7 +605,6 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
               }
             }
           }
-          if (cur >= 0) flush();
         } else {
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
