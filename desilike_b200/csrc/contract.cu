@@ -260,6 +260,9 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
   if constexpr (RESIDENT) {
     for (int i = tid; i < p.ngen * (int)(sizeof(GenDev) / 4); i += NTH) reinterpret_cast<int*>(gens_s)[i] = reinterpret_cast<const int*>(p.gens)[i];
   }
+  if constexpr (QF && CPS == 2) {   // two CTAs per SM: start the second-resident one half a column block late, so that one's epilogue overlaps the other's DMMAs
+    if (blockIdx.x >= (gridDim.x + 1) / 2) __nanosleep(3000);
+  }
   if constexpr (QF) {   // the epilogue reads feature columns up to the 8-column padding of a group (x exact zeros): every A entry must be finite
     for (int i = tid; i < BM * p.ast; i += NTH) A_s[i] = 0.;
     for (int i = tid; i < 2 * BM * p.dpad; i += NTH) xs0[i] = 0.;
@@ -700,15 +703,15 @@ int launch_variant(const ContractParams& p, int grid, size_t smem, cudaStream_t 
 }
 
 #if !DLB_CONTRACT_MASKED
-template <int NT, int KC>
+template <int NT, int WM, int CPS, int KC>
 int launch_qf(const ContractParams& p, int grid, size_t smem, cudaStream_t stream) {
   static bool configured_dev[64] = {};
   bool& configured = configured_dev[current_device_slot()];
   if (!configured) {
-    DLB_CUDA(cudaFuncSetAttribute(contract_kernel<1, 1, NT, 8, 1, KC, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)contract_smem_limit(1)));
+    DLB_CUDA(cudaFuncSetAttribute(contract_kernel<1, 1, NT, WM, CPS, KC, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)contract_smem_limit(CPS)));
     configured = true;
   }
-  contract_kernel<1, 1, NT, 8, 1, KC, true, false, true><<<grid, 8 * 64, smem, stream>>>(p);
+  contract_kernel<1, 1, NT, WM, CPS, KC, true, false, true><<<grid, WM * 64, smem, stream>>>(p);
   g_launches++;
   DLB_CUDA(cudaGetLastError());
   return DLB_OK;
@@ -749,11 +752,12 @@ int launch_contract(const Variant& v, const ContractParams& p, int nsm, cudaStre
   if (smem > contract_smem_limit(v.CPS)) { set_error("contraction kernel: shared-memory budget exceeded"); return DLB_ERR_UNSUPPORTED; }
   const int grid = (int)std::min<long long>((long long)nsm * v.CPS, std::max<long long>(p.U, 1));
 #if !DLB_CONTRACT_MASKED
-  if (p.qform) {   // quadratic-form blocks: 16 warps, 64-row tiles, one accumulator per column, resident A
-    if (!(v.R == 1 && v.MT == 1 && v.WM == 8 && v.CPS == 1 && p.resident)) { set_error("quadratic-form plan: unexpected kernel variant"); return DLB_ERR_UNSUPPORTED; }
-    if (v.NT == 7 && v.KC == 36) return launch_qf<7, 36>(p, grid, smem, stream);
-    if (v.NT == 6 && v.KC == 76) return launch_qf<6, 76>(p, grid, smem, stream);
-    if (v.NT == 7 && v.KC == 68) return launch_qf<7, 68>(p, grid, smem, stream);
+  if (p.qform) {   // quadratic-form blocks: one accumulator per column, resident A; 16 warps x 64-row tiles, or 2 CTAs / SM x 8 warps x 32-row tiles
+    if (!(v.R == 1 && v.MT == 1 && p.resident)) { set_error("quadratic-form plan: unexpected kernel variant"); return DLB_ERR_UNSUPPORTED; }
+    if (v.WM == 8 && v.CPS == 1 && v.NT == 7 && v.KC == 36) return launch_qf<7, 8, 1, 36>(p, grid, smem, stream);
+    if (v.WM == 8 && v.CPS == 1 && v.NT == 6 && v.KC == 76) return launch_qf<6, 8, 1, 76>(p, grid, smem, stream);
+    if (v.WM == 8 && v.CPS == 1 && v.NT == 7 && v.KC == 68) return launch_qf<7, 8, 1, 68>(p, grid, smem, stream);
+    if (v.WM == 4 && v.CPS == 2 && v.NT == 7 && v.KC == 36) return launch_qf<7, 4, 2, 36>(p, grid, smem, stream);
     set_error("quadratic-form plan: unexpected kernel variant");
     return DLB_ERR_UNSUPPORTED;
   }

@@ -1032,13 +1032,14 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
       const dlb_block_desc& bd = desc->blocks[ib];
       allq = allq && bd.q_ncols > 0 && bd.q_matrix && bd.q_tiles && bd.q_groups && bd.q_dent && bd.q_const && bd.q_ngroups > 0 && (bd.q_ncols % 8) == 0;
     }
-    // 16 warps, 64-row tiles.  Preference: one k-chunk per column block (the per-chunk cost -- stage release, barrier wait -- is the largest loss of short
-    // contractions): KC = 68 with 112-column blocks when the features fit, else KC = 76 with 96-column blocks, else two chunks of 36
+    // Candidates (measured within 3 % of each other on C4 / C5 + marginalisation): 2 CTAs / SM x 8 warps with 32-row tiles and two k-chunks of 36, then
+    // the 16-warp, 64-row forms: KC = 68 with 112-column blocks (one k-chunk per column block) when the features fit, KC = 76 with 96-column blocks, KC = 36
     int qK = 0;
     for (int ib = 0; ib < desc->nblocks && allq; ++ib) qK = std::max(qK, desc->blocks[ib].terms[0].K);
     std::vector<Variant> qcand;
-    if (const char* e = getenv("DLB_QF_VARIANT")) { const int i = atoi(e); qcand.push_back(i == 0 ? Variant{1, 1, 7, 8, 1, 68} : (i == 1 ? Variant{1, 1, 6, 8, 1, 76} : Variant{1, 1, 7, 8, 1, 36})); }
+    if (const char* e = getenv("DLB_QF_VARIANT")) { const int i = atoi(e); qcand.push_back(i == 0 ? Variant{1, 1, 7, 8, 1, 68} : (i == 1 ? Variant{1, 1, 6, 8, 1, 76} : (i == 3 ? Variant{1, 1, 7, 4, 2, 36} : Variant{1, 1, 7, 8, 1, 36}))); }
     else {
+      qcand.push_back(Variant{1, 1, 7, 4, 2, 36});   // 2 CTAs / SM x 8 warps, 32-row tiles: one CTA's epilogue overlaps the other's DMMAs (C4 +2 %, C5 + marg. +3 % over the 16-warp forms)
       if (chunk_extent(qK) <= 68) qcand.push_back(Variant{1, 1, 7, 8, 1, 68});
       if (chunk_extent(qK) <= 76) qcand.push_back(Variant{1, 1, 6, 8, 1, 76});
       qcand.push_back(Variant{1, 1, 7, 8, 1, 36});
@@ -1046,7 +1047,7 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
     Variant qv = qcand.back();
     bool qfits = false;
     for (const Variant& c : qcand)
-      if (contract_smem_bytes(c, 2, true, ast, plan->dpad, desc->ncoef, npart_bound, desc->ngen) <= contract_smem_limit(1)) { qv = c; qfits = true; break; }
+      if (contract_smem_bytes(c, 2, true, ast, plan->dpad, desc->ncoef, npart_bound, desc->ngen) <= contract_smem_limit(c.CPS)) { qv = c; qfits = true; break; }
     if (allq && qfits) {
       plan->qblocks.resize(desc->nblocks);
       std::vector<Block*> qptr;
