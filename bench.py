@@ -552,8 +552,7 @@ def run_workload(ctx, args, workload, N, steps, warmup, main, peaks):
         # what a host-side consumer of a sharded evaluation reads back (reference samplers/base.py:196-200: logposterior of ALL points on every
         # rank; the derived values -- here the solved parameters -- of its own points): gathered logposterior + own x_solved slice + local outputs
         hgat = torch.empty(total, dtype=torch.float64, pin_memory=True)
-        hxs = torch.empty(max(N * ns, 1), dtype=torch.float64, pin_memory=True)
-        lhost = {k: hout[k] for k in ('loglikelihood', 'logprior', 'status')}
+        lhost = {k: hout[k] for k in ('loglikelihood', 'logprior', 'status') + (('x_solved_plan_order',) if ns else ())}   # own points: pipelined copy-out
 
         def e2e_step(i):   # host parameters in -> finish kernel stores into every rank's window -> results back to the host
             b = i % nbuf
@@ -561,9 +560,8 @@ def run_workload(ctx, args, workload, N, steps, warmup, main, peaks):
             gather.wait(b)
             window = gather.buffer(b, total * (1 + ns))
             hgat.copy_(window[:total], non_blocking=True)
-            if ns: hxs.copy_(window[total + rank * N * ns:total + (rank + 1) * N * ns], non_blocking=True)
             torch.cuda.synchronize()
-        api = 'desilike_b200.Plan.eval_gather(pinned host ndarray) -> dlb_eval_batch_gather; PeerGather.wait; D2H of the gathered logposterior + own x_solved'
+        api = 'desilike_b200.Plan.eval_gather(pinned host ndarray, own loglikelihood / logprior / status / x_solved copied out per sub-batch) -> dlb_eval_batch_gather; PeerGather.wait; D2H of the gathered logposterior'
         h2d, d2h = N * d * 8, N * (2 * 8 + 4) + total * 8 + N * ns * 8
     else:
         def e2e_step(i):

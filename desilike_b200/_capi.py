@@ -83,7 +83,7 @@ SYMBOLS = {
     'dlb_gather_connect': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'dlb_gather_buffer': (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int32]),
     'dlb_eval_batch_gather': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
-                                             ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
+                                             ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
     'dlb_gather_publish': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
     'dlb_gather_wait': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
     'dlb_gather_status': (ctypes.c_int, [ctypes.c_void_p]),

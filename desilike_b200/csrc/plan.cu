@@ -1296,9 +1296,9 @@ int dlb_eval_batch_hessian(dlb_plan* plan, const double* params, int64_t N, doub
 }
 
 int dlb_eval_batch_gather(dlb_plan* plan, const double* params, int64_t N, dlb_gather* gather, int32_t buf, int64_t slice_start, int64_t total,
-                          int32_t with_solved, double* loglikelihood, double* logprior, int32_t* status, int32_t wait_buf, void* stream_) {
+                          int32_t with_solved, double* loglikelihood, double* logprior, double* x_solved, int32_t* status, int32_t wait_buf, void* stream_) {
   DLB_REQUIRE(gather, "NULL gather");
-  DLB_TRY(eval_impl(plan, params, N, nullptr, loglikelihood, logprior, nullptr, nullptr, status, stream_, gather, buf, slice_start, total, with_solved != 0));
+  DLB_TRY(eval_impl(plan, params, N, nullptr, loglikelihood, logprior, x_solved, nullptr, status, stream_, gather, buf, slice_start, total, with_solved != 0));
   if (wait_buf >= 0) return dlb_gather_wait(gather, wait_buf, stream_);
   return DLB_OK;
 }

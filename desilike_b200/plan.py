@@ -128,7 +128,8 @@ class Plan(object):
         kernel store logposterior (and x_solved, plan order) straight into buffer ``buf`` of EVERY rank's gather window
         (``distributed.PeerGather``; replaces reference base.py:335 / samplers/base.py:196-200).  ``X``: float64 CUDA tensor (enqueued on the
         current torch stream) or (pinned) host ndarray (staged by the library).  Optional local outputs in ``out``: ``loglikelihood``,
-        ``logprior`` (float64) and ``status`` (int32), CUDA tensors or host ndarrays of length n.  ``wait``: buffer index whose acquire
+        ``logprior`` (float64), ``status`` (int32) of length n and ``x_solved_plan_order`` [n, ns] (this rank's own solved values), CUDA tensors or host
+        ndarrays (host buffers are filled by the pipelined copy-out of the sub-batches).  ``wait``: buffer index whose acquire
         (``PeerGather.wait``) is enqueued behind this evaluation in the same call (pipelined loops: one library call per step)."""
         import torch
         out = out or {}
@@ -147,7 +148,8 @@ class Plan(object):
             if key not in out: return None
             return out[key].data_ptr() if _is_torch_cuda(out[key]) else out[key].ctypes.data
         _capi.check(self._lib.dlb_eval_batch_gather(self._handle, xptr, X.shape[0], gather._handle, int(buf), int(slice_start),
-                                                    int(total), int(bool(with_solved)), ptr('loglikelihood'), ptr('logprior'), ptr('status'),
+                                                    int(total), int(bool(with_solved)), ptr('loglikelihood'), ptr('logprior'),
+                                                    ptr('x_solved_plan_order') if self.ns else None, ptr('status'),
                                                     -1 if wait is None else int(wait), ctypes.c_void_p(stream)))
 
     def theory(self, X):

@@ -231,7 +231,9 @@ int dlb_gather_ipc_handle(const dlb_gather* gather, void* handle /* [DLB_IPC_HAN
 int dlb_gather_connect(dlb_gather* gather, const void* handles /* [world, DLB_IPC_HANDLE_BYTES], rank-major */);
 double* dlb_gather_buffer(dlb_gather* gather, int32_t buf);   /* this rank's copy of buffer `buf` (device pointer, [capacity]) */
 int dlb_eval_batch_gather(dlb_plan* plan, const double* params, int64_t N, dlb_gather* gather, int32_t buf, int64_t slice_start, int64_t total,
-                          int32_t with_solved, double* loglikelihood, double* logprior, int32_t* status, int32_t wait_buf, void* stream);
+                          int32_t with_solved, double* loglikelihood, double* logprior, double* x_solved, int32_t* status, int32_t wait_buf, void* stream);
+/* loglikelihood / logprior / x_solved [N, ns] / status: optional LOCAL outputs of this rank's own points (device or host; host buffers are filled by
+ * the pipelined copy-out of the sub-batches, overlapping the evaluation). */
 /* wait_buf >= 0: additionally enqueue dlb_gather_wait(gather, wait_buf) behind the evaluation (one call per step of a pipelined loop: the acquire
  * of the previous step's buffer overlaps this step's NVLink stores). */
 /* Generic form: store src[0 : count] (device) at [offset, offset + count) of buffer `buf` of every rank's window and publish. */

@@ -28,7 +28,8 @@ def test_gather_window_world1(gpu_required):
     for buf in (0, 1, 0):
         g.buffer(buf).zero_()
         ll = torch.empty(N, dtype=torch.float64, device='cuda')
-        plan.eval_gather(Xd, g, buf, 0, N, with_solved=True, out=dict(loglikelihood=ll))
+        xs_local = torch.empty((N, plan.ns), dtype=torch.float64, device='cuda')
+        plan.eval_gather(Xd, g, buf, 0, N, with_solved=True, out=dict(loglikelihood=ll, x_solved_plan_order=xs_local))
         g.wait(buf)
         torch.cuda.synchronize()
         g.check()
@@ -36,6 +37,7 @@ def test_gather_window_world1(gpu_required):
         assert np.array_equal(w[:N], ref['logposterior'])
         assert np.array_equal(w[N:N + N * plan.ns].reshape(N, plan.ns)[:, plan._unperm], ref['x_solved'])
         assert np.array_equal(ll.cpu().numpy(), ref['loglikelihood'])
+        assert np.array_equal(xs_local.cpu().numpy()[:, plan._unperm], ref['x_solved'])   # the rank's own solved values as a local output, too
     # a slice in the middle of a larger batch, no solved values
     g.buffer(0).zero_()
     plan.eval_gather(Xd[:100], g, 0, 300, 1000)
