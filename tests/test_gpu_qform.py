@@ -33,3 +33,18 @@ def test_quadratic_form_plan_matches_slot_form_and_oracle(gpu_required, name):
     # several passes / ragged tails
     sub = quad.eval(X[:77])
     assert np.array_equal(sub['logposterior'], got['logposterior'][:77])
+
+
+def test_quadratic_form_plan_hessian_and_multipass(gpu_required, monkeypatch):
+    """The Hessian entry and the several-passes path (DLB_MAX_CHUNK) run the same quadratic-form launch."""
+    import desilike_b200
+    spec = configs.config_c5(ntracers=2, nkin=40, nbins=12, order=2, solved=True)
+    X = configs.sample_points(spec, 2000, seed=17)
+    quad, slot = desilike_b200.Plan(spec, qform=True), desilike_b200.Plan(spec, qform=False)
+    a, b = quad.eval(X, return_hessian=True), slot.eval(X, return_hessian=True)
+    assert np.allclose(a['hessian'], b['hessian'], rtol=1e-9, atol=1e-9 * np.max(np.abs(b['hessian'])))
+    assert np.allclose(a['logposterior'], b['logposterior'], rtol=1e-10, atol=1e-8)
+    one = quad.eval(X)   # (same finish kernel as the multi-pass run below; the Hessian entry uses the warp-per-point one)
+    monkeypatch.setenv('DLB_MAX_CHUNK', '768')
+    c = quad.eval(X)
+    assert np.array_equal(c['logposterior'], one['logposterior']) and np.array_equal(c['x_solved'], one['x_solved'])
