@@ -207,18 +207,30 @@ constexpr int SPLINE_DOUBLES(int nt) { return 5 * nt + 4; }
 // (4) the lanes form the mu sums of every (segment, ell, k) output of the block and store them coalesced.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int KAISER_WARPS = 4;
-constexpr int KAISER_KB = 32;
+constexpr int KAISER_KB = 24;   // (32 -> 24 and the exact padding bound below: 8 instead of 6 co-resident blocks per SM)
 constexpr int MAX_ELL = 3;
 constexpr int KAISER_MAXSEG = 8;
 
+// largest padded index pidx(j, lgL) = j + (j >> lgL) + 1 over windows of m <= nw unknowns, lgL = smallest with (32 << lgL) >= m (>= 1)
+__host__ __device__ inline int kaiser_padded_len(int nw) {
+  int best = 0;
+  for (int lgL = 1; lgL < 16; ++lgL) {
+    const int mmax = nw < (32 << lgL) ? nw : (32 << lgL);   // windows using this lgL have m <= 32 << lgL
+    const int len = mmax + (mmax >> lgL) + 2;
+    best = len > best ? len : best;
+    if ((32 << lgL) >= nw) break;
+  }
+  return best;
+}
+
 __host__ __device__ inline int kaiser_warp_doubles(int nw, int nmu, int nell, int nseg, int interp) {
   // y | M (padded) | node values | segment weights | per-mu AP quantities | segment coefficients
-  return (nw + 4) + (interp == 0 ? nw + nw / 2 + 8 : 0) + KAISER_KB * (nmu | 1) + nseg * nell * nmu + 3 * nmu + 3 * nseg + 2;
+  return (nw + 4) + (interp == 0 ? kaiser_padded_len(nw) + 6 : 0) + KAISER_KB * (nmu | 1) + nseg * nell * nmu + 3 * nmu + 3 * nseg + 2;
 }
 
 // NMU: number of mu nodes when known at compile time (8: the reference default, full_shape.py:484), 0: generic.  INTERP: 0 not-a-knot, 1 local cubic.
 template <int NMU, int INTERP>
-__global__ void __launch_bounds__(KAISER_WARPS * 32, 6) kaiser_kernel(const DevGen g, const double* __restrict__ params, int d, long long N,
+__global__ void __launch_bounds__(KAISER_WARPS * 32, 8) kaiser_kernel(const DevGen g, const double* __restrict__ params, int d, long long N,
                                                                    long long npad, double* __restrict__ F, int fstride, int warp_doubles) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -238,7 +250,7 @@ __global__ void __launch_bounds__(KAISER_WARPS * 32, 6) kaiser_kernel(const DevG
   const int pst = nmu | 1;
   double* y = sm + (size_t)warp * warp_doubles;
   double* M = y + nw_max + 4;
-  double* P = M + (INTERP == 0 ? nw_max + nw_max / 2 + 8 : 0);
+  double* P = M + (INTERP == 0 ? kaiser_padded_len(nw_max) + 6 : 0);
   double* wseg = P + KAISER_KB * pst;
   double* smu = wseg + nseg * nell * nmu;      // [nmu][3]: log10(F / qper), mu_ap^2, damping coefficient
   double* coef = smu + 3 * nmu;                // [nseg][3]
