@@ -23,9 +23,11 @@ EFT-like combine -> window] -> joint chi2 with analytic marginalisation of 35 co
              same plan-time-folded algebra the GPU executes, in vectorised NumPy (so that the GPU/CPU ratio is not read as pure hardware).
   extra      compact lines (value, e2e, roofline, cpu_baseline) of the other SURVEY.md section 8d workloads, measured in the same run.
 
-Synthetic inputs: the workload definitions (spec constants, fiducial data vector, covariance) of SURVEY.md section 8d live in
-oracle/configs.py, shared with the tests; bench.py imports them to BUILD its inputs before any timing.  Every timed region of the default
-arm executes desilike_b200 (the C-ABI library) only; oracle/pipeline.py runs in the cpu_baseline leg and in ``--impl reference``.
+Synthetic inputs: the workload definitions (spec constants, fiducial data vector, covariance) of SURVEY.md section 8d live product-side in
+desilike_b200/workloads.py (the tests reach the same generators through oracle/configs.py).  The default arm builds them without importing
+oracle/ (the synthetic data vector = theory at a fiducial point comes from the package's own CUDA path); every timed region of the default
+arm executes desilike_b200 (the C-ABI library) only; oracle/pipeline.py runs in the cpu_baseline leg and in ``--impl reference`` (whose
+workloads are built through oracle/configs.py: no GPU needed).
 
 ``--impl reference``: the reference is pure Python and /root/reference does not travel to the GPU box, so the reference
 arm times the oracle port (oracle/pipeline.py -- the one other place bench.py may execute oracle/) with all host threads.
@@ -69,8 +71,22 @@ EXTRA_BATCH = {'c4wide': 16384, 'c4wide_i8': 16384, 'c4dense': 16384}
 L2_BYTES = 126 * 2**20
 
 
+_IMPL = 'ours'
+
+
+def workload_module():
+    """Synthetic-workload generators.  Default arm: the product-side module (desilike_b200/workloads.py; the synthetic data vectors -- theory at a
+    fiducial point -- come from the package's own CUDA path).  Reference arm: the same generators through oracle/configs.py, which installs the oracle
+    for that step (no GPU needed)."""
+    if _IMPL == 'reference':
+        from oracle import configs
+        return configs
+    from desilike_b200 import workloads
+    return workloads
+
+
 def build_spec(workload):
-    from oracle import configs
+    configs = workload_module()
     if workload == 'c1':
         return configs.config_c1(), 'C1: KaiserTracerPowerSpectrumMultipoles (ShapeFit template, ell=0,2,4, k=0.02-0.2, 36 bins/ell) -> chi2 (n=108, d=6), direct theory (no emulator)'
     if workload == 'c3':
@@ -111,7 +127,7 @@ def config_dict(label, N, world, d):
 
 def host_batch(spec, N, rank, idx):
     """Batch ``idx`` of rank ``rank``'s input pool (deterministic: any rank can rebuild any other rank's inputs for the gather check)."""
-    from oracle import configs
+    configs = workload_module()
     X = configs.sample_points(spec, N, seed=1000 + 97 * rank + idx % 8)
     if idx >= 8: X = X * (1. + 1e-6 * idx)   # cheap distinct batches: a jitter within the prior box keeps the workload identical
     return X
@@ -627,7 +643,7 @@ def run_ensemble(ctx, args, steps, warmup, peaks):
     every rank (peer stores over NVLink, or an NCCL all-gather).  Walkers, proposals and log-posteriors are device resident
     (dlb_ensemble_step); `value` = log-posterior evaluations / s."""
     import desilike_b200
-    from oracle import configs
+    configs = workload_module()
     torch, rank, world, dev = ctx.torch, ctx.rank, ctx.world, ctx.dev
     spec = configs.config_c5(coefficients='random')
     plan = desilike_b200.Plan(spec, with_theory=False)
@@ -742,7 +758,9 @@ def main():
     if args.batch is None:
         args.batch = DEFAULT_BATCH if args.workload == DEFAULT_WORKLOAD else EXTRA_BATCH.get(args.workload, 65536)
 
-    from oracle import configs
+    global _IMPL
+    _IMPL = args.impl
+    configs = workload_module()
     if args.impl == 'reference':
         spec, label = build_spec('c5' if args.workload == 'c5step' else args.workload)
         X = configs.sample_points(spec, min(args.batch, 32768), seed=100)

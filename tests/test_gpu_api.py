@@ -8,6 +8,8 @@ import numpy as np
 import pytest
 
 import desilike_b200 as dl
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 from oracle import configs, pipeline, synthetic
 from test_host_api import make_kaiser_likelihood
 
@@ -389,3 +391,24 @@ def test_lpt_physical_prior_basis(gpu_required, marg):
     got, ref = like.plan.eval(X), pipeline.evaluate(spec, X)
     assert np.all(np.abs(got['logposterior'] - ref['logposterior']) <= 1e-8 * np.maximum(1., np.abs(ref['logposterior'])))
     if marg: assert np.allclose(got['x_solved'], ref['x_solved'], rtol=1e-7, atol=1e-7)
+
+
+def test_workload_generators_product_side(gpu_required):
+    """bench.py builds its workloads from desilike_b200/workloads.py without the checker package: the synthetic data vector (theory at the fiducial point)
+    then comes from the CUDA path itself and equals the oracle-built one to rounding; a subprocess confirms that no oracle module gets imported."""
+    import subprocess, sys
+    from desilike_b200 import workloads
+    from oracle import configs, pipeline
+    kw = dict(ntracers=2, nkin=40, nbins=10, hidden=(16, 16))
+    ref = configs.config_c4(**kw)                      # oracle hooks (installed by oracle/configs.py)
+    workloads.set_hooks(None, None)
+    try: own = workloads.config_c4(**kw)               # default hooks: Plan.theory
+    finally: workloads.set_hooks(theory_flat=pipeline.observable_flat, theory_tables=pipeline.theory_tables)
+    for a, b in zip(own['observables'], ref['observables']):
+        assert np.allclose(a['data'], b['data'], rtol=1e-11, atol=1e-11 * np.max(np.abs(b['data'])))
+        assert np.array_equal(a['wmatrix'], b['wmatrix'])
+    for pa, pb in zip(own['precision'], ref['precision']): assert np.allclose(pa, pb, rtol=1e-8)
+    code = ("import sys, bench; spec, label = bench.build_spec('c5solved'); "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), [m for m in sys.modules if m.startswith('oracle')]; print(len(spec['params']))")
+    res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
