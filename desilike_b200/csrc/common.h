@@ -182,8 +182,8 @@ int launch_derived(const double* params, int d_in, int nder, const int* off, con
                    cudaStream_t stream);   // csrc/features.cu: extended parameter rows
 int launch_mlp_input(const DevGen& g, const double* params, int d, long long N, long long npad, double* F, int fstride, cudaStream_t stream);
 // fused MLP forward (csrc/mlp.cu)
-size_t mlp_fused_smem(const int* idata_host);
-int launch_mlp_fused(const DevGen* d_gens, const int* d_mlp_index, int nmlp, size_t smem, const double* params, int d, long long N, long long npad,
+size_t mlp_fused_smem(const int* idata_host, int groups);
+int launch_mlp_fused(const DevGen* d_gens, const int* d_mlp_index, int nmlp, size_t smem, int groups, const double* params, int d, long long N, long long npad,
                      double* F, int fstride, int nsm, cudaStream_t stream);
 
 // FP64-grade GEMM on tcgen05 int8 tensor cores (csrc/ozaki.cu): wide MLP hidden layers, opt-in

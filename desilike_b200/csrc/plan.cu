@@ -94,6 +94,7 @@ struct dlb_plan {
   std::vector<dlb::Block> blocks;
   std::vector<dlb::MlpLayers> mlps;   // one per generator (empty unless kind == MLP)
   size_t mlp_fused_smem = 0;           // > 0: every MLP emulator runs in the fused kernel (csrc/mlp.cu)
+  int mlp_groups = 1;                  // warp groups per CTA of the fused kernel
   dlb::DevGen* d_devgens = nullptr; int* d_mlp_index = nullptr; int nmlp = 0;
   std::vector<std::pair<dlb::Launch, int>> mlp_launches;   // hidden layers of ALL MLP generators, one launch per (depth, activation, A mode)
   dlb::DevCoef* d_coefs = nullptr;
@@ -607,7 +608,7 @@ static int run_front(dlb_plan* plan, const double* d_params, long long N, long l
     DLB_TRY(launch_features(g, d_params, plan->d, N, npad, plan->w_F, plan->fstride, stream));
   }
   if (plan->mlp_fused_smem)
-    return launch_mlp_fused(plan->d_devgens, plan->d_mlp_index, plan->nmlp, plan->mlp_fused_smem, d_params, plan->d, N, npad, plan->w_F, plan->fstride,
+    return launch_mlp_fused(plan->d_devgens, plan->d_mlp_index, plan->nmlp, plan->mlp_fused_smem, plan->mlp_groups, d_params, plan->d, N, npad, plan->w_F, plan->fstride,
                             plan->nsm, stream);
   for (const auto& la : plan->mlp_launches) {   // hidden layers, depth by depth, all MLP emulators of the likelihood in one launch
     const Launch& L = la.first;
@@ -834,13 +835,20 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
     std::vector<int> mlp_index;
     size_t smem = 0;
     bool ok = true;
-    for (int ig = 0; ig < desc->ngen; ++ig)
-      if (desc->gens[ig].kind == DLB_GEN_MLP) {
-        mlp_index.push_back(ig);
-        const size_t need = mlp_fused_smem(desc->gens[ig].idata);
-        if (!need || need > (size_t)200 * 1024) ok = false;
-        smem = std::max(smem, need);
-      }
+    int groups = getenv("DLB_MLP_ONE_GROUP") ? 1 : 2;   // two out-of-phase warp groups per CTA when their activation buffers fit next to the weights
+    for (;;) {
+      mlp_index.clear(); smem = 0; ok = true;
+      for (int ig = 0; ig < desc->ngen; ++ig)
+        if (desc->gens[ig].kind == DLB_GEN_MLP) {
+          mlp_index.push_back(ig);
+          const size_t need = mlp_fused_smem(desc->gens[ig].idata, groups);
+          if (!need || need > (size_t)224 * 1024) ok = false;
+          smem = std::max(smem, need);
+        }
+      if (ok || groups == 1) break;
+      groups = 1;
+    }
+    plan->mlp_groups = groups;
     if (ok && !mlp_index.empty() && !getenv("DLB_NO_FUSED_MLP") && plan->mlp_slices == 0) {
       plan->mlp_fused_smem = smem; plan->nmlp = (int)mlp_index.size();
       DLB_TRY(upload(plan, plan->gens.data(), plan->gens.size(), &plan->d_devgens));
