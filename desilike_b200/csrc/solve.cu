@@ -332,6 +332,17 @@ __device__ __forceinline__ void finish_solve_thread_body(const SolveParams& p, d
     }
     const int t1 = p.gent_off[c + 1];
     int t = p.gent_off[c];
+    for (; t + 8 <= t1; t += 8) {   // eight independent loads in flight (two warps per scheduler: memory-level parallelism has to come from the thread)
+      GroupEntry e[8];
+      double v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { e[q] = p.gent[t + q]; v[q] = p.partial[e[q].prow * p.npad + pt]; }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (e[q].kind == 1) gl[e[q].li * ST_THREADS] -= v[q];
+        else M[(e[q].li * SOLVE_NREG + e[q].lj) * ST_THREADS] += v[q];
+      }
+    }
     for (; t + 4 <= t1; t += 4) {   // four independent loads in flight
       GroupEntry e[4];
       double v[4];
@@ -360,31 +371,36 @@ __device__ __forceinline__ void finish_solve_thread_body(const SolveParams& p, d
 #pragma unroll
       for (int j = 0; j <= i; ++j) a[i][j] = (i < n) ? M[(i * SOLVE_NREG + j) * ST_THREADS] : (i == j ? 1. : 0.);
     }
+    // LDL^T instead of Cholesky: per pivot ONE reciprocal (no sqrt, no further divisions in the substitutions) and log det from the product of the
+    // pivots (two partial products of <= 4 factors each: no overflow for pivots up to 1e+-75) -- the dependent sqrt / div / log chain of the
+    // Cholesky form was most of this kernel's time (one thread per point, two warps per scheduler: nothing hides the latency)
     bool ok = true;
+    double inv[SOLVE_NREG], det0 = 1., det1 = 1.;
 #pragma unroll
     for (int j = 0; j < SOLVE_NREG; ++j) {
       const double djj = a[j][j];
       if (j < n && (!(djj > 0.) || !isfinite(djj))) ok = false;
-      const double l = sqrt(djj), inv = 1. / l;
-      if (j < nm) logdet += 2. * log(l);
-      a[j][j] = l;
+      inv[j] = 1. / djj;
+      if (j < nm) { if (j < SOLVE_NREG / 2) det0 *= djj; else det1 *= djj; }
+      double col[SOLVE_NREG];
 #pragma unroll
-      for (int i = j + 1; i < SOLVE_NREG; ++i) a[i][j] *= inv;
+      for (int i = j + 1; i < SOLVE_NREG; ++i) { col[i] = a[i][j]; a[i][j] = col[i] * inv[j]; }   // a[i][j] <- l_ij
 #pragma unroll
       for (int i = j + 1; i < SOLVE_NREG; ++i)
 #pragma unroll
-        for (int k = j + 1; k <= i; ++k) a[i][k] -= a[i][j] * a[k][j];
+        for (int k = j + 1; k <= i; ++k) a[i][k] -= col[i] * a[k][j];                              // -= l_ij d_j l_kj
     }
     if (!ok) { spd = false; continue; }
+    logdet += log(det0) + log(det1);
 #pragma unroll
-    for (int j = 0; j < SOLVE_NREG; ++j) {   // forward L y = g
-      yy[j] /= a[j][j];
+    for (int j = 0; j < SOLVE_NREG; ++j) {   // forward L z = g (unit lower triangular)
 #pragma unroll
       for (int i = j + 1; i < SOLVE_NREG; ++i) yy[i] -= a[i][j] * yy[j];
     }
 #pragma unroll
-    for (int j = SOLVE_NREG - 1; j >= 0; --j) {   // backward L^T dx = y
-      yy[j] /= a[j][j];
+    for (int j = 0; j < SOLVE_NREG; ++j) yy[j] *= inv[j];   // D w = z
+#pragma unroll
+    for (int j = SOLVE_NREG - 1; j >= 0; --j) {   // backward L^T dx = w
 #pragma unroll
       for (int i = 0; i < j; ++i) yy[i] -= a[j][i] * yy[j];
     }
