@@ -594,16 +594,25 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
               if ((meta[nt].x >> 24) == 0) continue;
-              const int gid = meta[nt].x & 0xFFFF, ca = (meta[nt].w & 0xFFFF) - 1;
-              const int e0 = __ldg(blk->qdent + gid * 8 + 2 * lc), e1 = __ldg(blk->qdent + gid * 8 + 2 * lc + 1);
+              const int gid = meta[nt].x & 0xFFFF;
+              const int* de = blk->qdent + gid * 24 + 6 * lc;   // per column (Gram entry, coefficient a, coefficient b)
+              int ent[2][3];
+#pragma unroll
+              for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) ent[e][q] = __ldg(de + 3 * e + q);
+              // (the columns of a direct tile feed DISTINCT Gram entries -- lowering.qform_tables packs them that way: no conflicts between the lanes)
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
                 if (mt < mtc) {
                   const int row = mt * UNIT + wm * 8 + lr;
-                  const double w = ca >= 0 ? cs[ca * BM + row] : 1.;
                   double* redrow = red + ((size_t)wn * BM + row) * npm;
-                  if (e0 >= 0) redrow[e0] += acc[0][mt][nt][0] * w;
-                  if (e1 >= 0) redrow[e1] += acc[0][mt][nt][1] * w;
+#pragma unroll
+                  for (int e = 0; e < 2; ++e)
+                    if (ent[e][0] >= 0) {
+                      const double w = (ent[e][1] >= 0 ? cs[ent[e][1] * BM + row] : 1.) * (ent[e][2] >= 0 ? cs[ent[e][2] * BM + row] : 1.);
+                      redrow[ent[e][0]] += acc[0][mt][nt][e] * w;
+                    }
                 }
               }
             }

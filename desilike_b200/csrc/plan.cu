@@ -1075,7 +1075,12 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
           const int32_t* q = bd.q_groups + 4 * g;
           DLB_REQUIRE((q[0] == 0 || q[0] == 1) && q[1] >= 0 && q[1] < ob.npart && q[2] >= -1 && q[2] < desc->ncoef && q[3] >= -1 && q[3] < desc->ncoef,
                       "quadratic-form tables: group entry out of range");
-          for (int j = 0; j < 8; ++j) DLB_REQUIRE(bd.q_dent[8 * g + j] >= -1 && bd.q_dent[8 * g + j] < ob.npart, "quadratic-form tables: direct entry out of range");
+          for (int j = 0; j < 8; ++j)
+            DLB_REQUIRE(bd.q_dent[24 * g + 3 * j] >= -1 && bd.q_dent[24 * g + 3 * j] < ob.npart && bd.q_dent[24 * g + 3 * j + 1] >= -1 && bd.q_dent[24 * g + 3 * j + 1] < desc->ncoef &&
+                        bd.q_dent[24 * g + 3 * j + 2] >= -1 && bd.q_dent[24 * g + 3 * j + 2] < desc->ncoef, "quadratic-form tables: direct entry out of range");
+          for (int j = 0; j < 8; ++j)
+            for (int i = 0; i < j; ++i)
+              DLB_REQUIRE(bd.q_dent[24 * g + 3 * j] < 0 || bd.q_dent[24 * g + 3 * j] != bd.q_dent[24 * g + 3 * i], "quadratic-form tables: the columns of a direct tile must feed distinct Gram entries");
         }
         DLB_REQUIRE(bd.q_ngroups < 32768 && desc->ncoef < 65535, "quadratic-form tables: too many groups / coefficients");
         // one 16-byte record per n-tile: { group | valid columns << 16 | kind << 24, first feature column, Gram entry, (coef a + 1) | (coef b + 1) << 16 }
@@ -1091,7 +1096,7 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
           tiles[4 * t + 3] = (q[2] + 1) | ((q[3] + 1) << 16);
         }
         DLB_TRY(upload(plan, tiles.data(), tiles.size(), &qb.d_qtile));
-        DLB_TRY(upload(plan, bd.q_dent, (size_t)8 * bd.q_ngroups, &qb.d_qdent));
+        DLB_TRY(upload(plan, bd.q_dent, (size_t)24 * bd.q_ngroups, &qb.d_qdent));
         DLB_TRY(upload(plan, bd.q_const, (size_t)ob.npart, &qb.d_qconst));
         qptr.push_back(&qb);
       }

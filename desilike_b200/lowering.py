@@ -150,21 +150,24 @@ class _Generator(object):
         return g
 
 
-def qform_tables(blk, force=False):
+def qform_tables(blk, force=False, coef_keys=None, const_features=None):
     """
     Quadratic-form evaluation of a likelihood block whose terms all contract the SAME K features f (one emulator per tracer: the usual case).
 
     The normal equations only need dot products of the slot vectors S_a = sum_{x in a} c_x(theta) f . M_x (minus r0 for a = 0) over the n whitened
     columns, and   (f . M_x) . (f . M_y) = f (M_x M_y^T) f^T   is a quadratic form in the K features.  With T terms the kernel then multiplies f by
     T (T + 1) / 2 matrices of K x K (+ a few linear columns) instead of T matrices of K x n: fewer columns whenever (T + 1) K / 2 < n -- e.g. 5 tracers x
-    [66 features, 6 terms, n = 406]: 1560 columns instead of 2436 -- and every column is a single accumulator (no slots), so the faster single-slot
+    [66 features, 6 terms, n = 406]: 1336 columns instead of 2436 -- and every column is a single accumulator (no slots), so the faster single-slot
     kernel variants apply.  Exact algebra, done once here in FP64 like the whitening and window folding.
 
     Output columns, in n-tiles of 8 (one group per tile):
-      * quadratic group (x <= y): columns k' < K hold s_xy (M_x M_y^T)[:, k'], s_xy = 2 if x != y share a slot else 1; the epilogue multiplies column k' by
-        f[k'] and adds the sum, weighted by c_x c_y, to Gram entry pair(slot_x, slot_y);
-      * direct group of term x: column 0 = -(2 if slot_x == 0 else 1) M_x r0 -> entry pair(0, slot_x); column 1 + i = M_x g_i -> entry of (constant row i,
-        slot_x); each weighted by c_x.
+      * quadratic group of a (Gram entry, weight monomial c_x c_y): column k' holds sum over its term pairs of s_xy (M_x M_y^T)[:, k'], s_xy = 2 if x != y share
+        a slot else 1; the epilogue multiplies column k' by f[k'] and adds the sum, weighted by c_x c_y, to the Gram entry pair(slot_x, slot_y).  Term pairs
+        with the same entry and weight monomial (e.g. (1, b1^2) and (b1, b1)) share a group.  Features that are CONSTANT (``const_features``: the
+        (1, 0) head of an MLP segment) get no quadratic column: a zero feature drops out, a constant one becomes a direct column -- for 64 hidden units
+        the quadratic columns then fill exactly 8 tiles;
+      * direct tiles: every column is added, with its own weight c_a c_b, to its own Gram entry: the constant-feature columns above, per term x
+        -(2 if slot_x == 0 else 1) M_x r0 -> entry pair(0, slot_x) and M_x g_i -> entry of (constant row i, slot_x), weighted by c_x.
     ``const`` holds the theta-independent parts (|r0|^2, -r0 . g_i).  Returns None when not applicable (or not worthwhile, unless ``force``).
     """
     keys, white, R, n = blk['terms'], blk['white'], blk['nslots'], blk['ncols_white']
@@ -173,10 +176,13 @@ def qform_tables(blk, force=False):
     if any(tuple(k[2:5]) != (gi, foff, K) for k in keys) or blk.get('entry_kind') is not None: return None
     g = np.asarray(blk['gconst_white'], dtype=np.float64).reshape(-1, n)
     nconst = g.shape[0]
-    if nconst > 7 or T > 16: return None
-    Kp = (K + 7) // 8 * 8
-    ncolq = T * (T + 1) // 2 * Kp + T * 8
-    if not force and (R < 2 or K > 128 or ncolq >= 0.85 * T * (n + nconst)): return None
+    if T > 16: return None
+    # quadratic columns: the non-constant features when they form one run starting at an even feature index (16-byte feature loads in the epilogue)
+    consts = {k - foff: float(v) for k, v in (const_features or {}).items() if foff <= k < foff + K}
+    kq = [k for k in range(K) if k not in consts]
+    if not consts or not kq or kq != list(range(kq[0], kq[-1] + 1)) or (foff + kq[0]) % 2: consts, kq = {}, list(range(K))
+    Kp = (len(kq) + 7) // 8 * 8
+    if not force and (R < 2 or K > 128 or (T * (T + 1) // 2 * Kp + T * 8) >= 0.85 * T * (n + nconst)): return None
     r0 = np.asarray(blk['r0_white'], dtype=np.float64)
     nS = R * (R + 1) // 2
 
@@ -184,23 +190,67 @@ def qform_tables(blk, force=False):
         a, b = min(a, b), max(a, b)
         return a * R - (a * (a - 1)) // 2 + (b - a)
 
-    mat = np.zeros((K, ncolq))
-    tiles, groups, dent = [], [], []   # tiles: (group, first feature of the tile relative to the generator segment, valid columns)
-    col = 0
+    # term pairs whose Gram entry AND weight monomial c_x c_y coincide (e.g. (1, b1^2) and (b1, b1) in slot 0) share one group: their matrices add up
+    inv_keys = {j: key for key, j in (coef_keys or {}).items()}
+
+    def monomial(cx, cy):
+        if coef_keys is None: return ('pair', cx, cy)   # no algebra available: never merge
+        powers = {}
+        for c in (cx, cy):
+            for idx, pw in (inv_keys[c] if c >= 0 else ()): powers[idx] = powers.get(idx, 0) + pw
+        return tuple(sorted((i, pw) for i, pw in powers.items() if pw != 0))
+
+    merged = {}   # (entry, weight monomial) -> [matrix, coef x, coef y]
     for x in range(T):
         for y in range(x, T):
             a, b = keys[x][0], keys[y][0]
-            mat[:, col:col + K] = (2. if (x != y and a == b) else 1.) * (white[x] @ white[y].T)   # column k' pairs with f[k']: sum_k f_k C[k, k'] f_k'
-            groups.append((0, pair(a, b), keys[x][1], keys[y][1])); dent.append([-1] * 8)
-            for j in range(Kp // 8): tiles.append((len(groups) - 1, foff + 8 * j, min(8, K - 8 * j)))
-            col += Kp
+            C = (2. if (x != y and a == b) else 1.) * (white[x] @ white[y].T)   # column k' pairs with f[k']: sum_k f_k C[k, k'] f_k'
+            C = 0.5 * (C + C.T) if x == y else C
+            key = (pair(a, b), monomial(keys[x][1], keys[y][1]))
+            if key in merged: merged[key][0] = merged[key][0] + C
+            else: merged[key] = [C, keys[x][1], keys[y][1]]
+    direct = []   # (matrix column [K], Gram entry, coef a, coef b)
+    for (entry, _), (C, cx, cy) in merged.items():
+        # f C f^T with constant features c: the (non-constant, constant) cross terms and the (constant, constant) part are linear / constant in f --
+        # both are the dot product of f with a fixed column: sum_k f_k (sum_{k' const} (C[k, k'] + C[k', k] [k non-constant]) c_k')
+        col = np.zeros(K)
+        for kc, v in consts.items():
+            if v == 0.: continue
+            col += v * C[:, kc]
+            col[kq] += v * C[kc, kq]
+        if consts and np.any(col != 0.): direct.append((col, entry, cx, cy))
     for x in range(T):
         a = keys[x][0]
-        ent = [-1] * 8
-        mat[:, col] = -(2. if a == 0 else 1.) * (white[x] @ r0); ent[0] = pair(0, a)
-        for i in range(nconst):
-            mat[:, col + 1 + i] = white[x] @ g[i]; ent[1 + i] = nS + i * R + a
-        groups.append((1, 0, keys[x][1], -1)); dent.append(ent)
+        direct.append((-(2. if a == 0 else 1.) * (white[x] @ r0), pair(0, a), keys[x][1], -1))
+        for i in range(nconst): direct.append((white[x] @ g[i], nS + i * R + a, keys[x][1], -1))
+    # direct columns with the same Gram entry and weight monomial add up (e.g. -2 M_x r0 joins the constant-feature column of the pair (x, '1' term));
+    # then tiles of 8 columns with DISTINCT Gram entries each (the lanes of a tile update their entries concurrently in the kernel)
+    dmerged = {}
+    for vec, entry, ca, cb in direct:
+        key = (entry, monomial(ca, cb))
+        if key in dmerged: dmerged[key][0] = dmerged[key][0] + vec
+        else: dmerged[key] = [vec, entry, ca, cb]
+    dtiles = []
+    for vec, entry, ca, cb in dmerged.values():
+        for tile in dtiles:
+            if len(tile) < 8 and all(e != entry for _, e, _, _ in tile): tile.append((vec, entry, ca, cb)); break
+        else: dtiles.append([(vec, entry, ca, cb)])
+    ndt = len(dtiles)
+    ncolq = len(merged) * Kp + ndt * 8
+    mat = np.zeros((K, ncolq))
+    tiles, groups, dent = [], [], []   # tiles: (group, first feature of the tile relative to the generator segment, valid columns)
+    col = 0
+    for (entry, _), (C, cx, cy) in merged.items():
+        mat[:, col:col + len(kq)] = C[:, kq]
+        if consts: mat[[k for k in consts], col:col + len(kq)] = 0.   # rows of constant features: their contribution sits in the direct columns
+        groups.append((0, entry, cx, cy)); dent.append([[-1, -1, -1]] * 8)
+        for j in range(Kp // 8): tiles.append((len(groups) - 1, foff + kq[0] + 8 * j, min(8, len(kq) - 8 * j)))
+        col += Kp
+    for t in range(ndt):
+        ent = [[-1, -1, -1] for _ in range(8)]
+        for j, (vec, entry, ca, cb) in enumerate(dtiles[t]):
+            mat[:, col + j] = vec; ent[j] = [entry, ca, cb]
+        groups.append((1, 0, -1, -1)); dent.append(ent)
         tiles.append((len(groups) - 1, foff, 8))
         col += 8
     const = np.zeros(nS + R * nconst)
@@ -394,7 +444,8 @@ class Lowered(object):
             blk['const_solved'] = i32(sorted(const_rows.keys()))
             blk['gconst_white'] = f64([L @ const_rows[si] for si in sorted(const_rows.keys())]).reshape(len(const_rows), ncols)
             if self.qform is not False and not self.two_stage and blk['ncols_white'] == ncols:
-                blk['qform'] = qform_tables(blk, force=self.qform is True)
+                blk['qform'] = qform_tables(blk, force=self.qform is True, coef_keys=self.coef_keys,
+                                            const_features=getattr(self.gens[keys[0][2]], 'const_features', None))
             self.blocks.append(blk)
         if any(b.get('qform') is None for b in self.blocks):   # all blocks or none: one kernel variant per launch
             for b in self.blocks: b['qform'] = None

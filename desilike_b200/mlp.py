@@ -34,6 +34,7 @@ def lower_mlp(gen, theory, defaults):
     gen.ddata = np.concatenate([a, b] + [np.concatenate([k.ravel(), bb]) for k, bb in hidden]) if True else None
     H = widths[-1] if widths else d
     gen.nfeat = 2 + H
+    gen.const_features = {0: 1., 1: 0.}   # the (1, 0) head of the feature segment (lowering.qform_tables: no quadratic columns for constant features)
     # fold last layer + inverse y-operations:  y = h . A + c
     A, c = W_out, b_out
     if mlp.get('pca') is not None:

@@ -126,8 +126,8 @@ typedef struct {
    * contract the same K features f; instead of the nterms matrices [K, ncols] the kernel multiplies f by ONE matrix q_matrix [K, q_ncols] whose columns
    * come in n-tiles of 8, one group per tile: q_tiles[3 t ..] = (group, first feature column of the tile relative to the generator segment, number of
    * valid columns); q_groups[4 g ..] = (kind, Gram entry, coefficient a, coefficient b; -1 = 1).  kind 0 (quadratic): column k' is multiplied by
-   * feature k', the group's sum weighted by coef_a coef_b is added to its Gram entry.  kind 1 (direct): column j is added, weighted by coef_a, to
-   * Gram entry q_dent[8 g + j] (-1: unused).  q_const [npart] is added to the partials (theta-independent parts).  Same partials as the slot form. */
+   * feature k', the group's sum weighted by coef_a coef_b is added to its Gram entry.  kind 1 (direct): column j is added to Gram entry q_dent[24 g + 3 j] (-1: unused), weighted by the
+   * coefficients q_dent[24 g + 3 j + 1] and [.. + 2] (-1 = 1).  q_const [npart] is added to the partials (theta-independent parts).  Same partials as the slot form. */
   int32_t q_ncols; int32_t q_ngroups; const double* q_matrix; const int32_t* q_tiles; const int32_t* q_groups; const int32_t* q_dent; const double* q_const;
 } dlb_block_desc;
 

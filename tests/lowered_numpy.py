@@ -112,12 +112,14 @@ def evaluate(low, X, feature_fn=None, white=True, use_qform=False):
             part = np.zeros((N, nS + R * nc)) + q['const']
             for t8, (gid, k0, nv) in enumerate(q['tiles']):
                 kind, e, ca, cb = q['groups'][gid]
-                w = (C[:, ca] if ca >= 0 else 1.) * (C[:, cb] if cb >= 0 else 1.)
                 cols = out[:, 8 * t8:8 * t8 + 8]
-                if kind == 0: part[:, e] += w * np.sum(cols[:, :nv] * f[:, k0:k0 + nv], axis=-1)
+                if kind == 0:
+                    w = (C[:, ca] if ca >= 0 else 1.) * (C[:, cb] if cb >= 0 else 1.)
+                    part[:, e] += w * np.sum(cols[:, :nv] * f[:, k0:k0 + nv], axis=-1)
                 else:
                     for j in range(8):
-                        if q['dent'][gid][j] >= 0: part[:, q['dent'][gid][j]] += w * cols[:, j]
+                        ej, caj, cbj = q['dent'][gid][j]
+                        if ej >= 0: part[:, ej] += (C[:, caj] if caj >= 0 else 1.) * (C[:, cbj] if cbj >= 0 else 1.) * cols[:, j]
             sidx = [None] + [int(si) for si in blk['slot_solved']]
             for a in range(R):
                 for b in range(a, R):
