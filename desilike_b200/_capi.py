@@ -12,7 +12,7 @@ from .build import LIBPATH
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
 
-DLB_ABI_VERSION = 9
+DLB_ABI_VERSION = 10
 DLB_COEF_MAXF = 4
 GEN_TAYLOR, GEN_MLP, GEN_KAISER, GEN_BAO = 1, 2, 3, 4
 PT_NONFINITE, PT_OUT_OF_PRIOR, PT_NOT_SPD = 1, 2, 4
@@ -39,7 +39,8 @@ class BlockDesc(ctypes.Structure):
                 ('transform_data', c_double_p), ('whitening_t', c_double_p), ('r0_data_white', c_double_p), ('ncols_white', ctypes.c_int32),
                 ('entry_kind', c_int32_p), ('entry_i', c_int32_p), ('entry_j', c_int32_p), ('skip_const_gram', ctypes.c_int32),
                 ('q_ncols', ctypes.c_int32), ('q_ngroups', ctypes.c_int32), ('q_matrix', c_double_p), ('q_tiles', c_int32_p), ('q_groups', c_int32_p),
-                ('q_dent', c_int32_p), ('q_const', c_double_p)]
+                ('q_dent', c_int32_p), ('q_const', c_double_p), ('q_foff', ctypes.c_int32), ('q_K', ctypes.c_int32), ('q_nw', ctypes.c_int32),
+                ('q_wconst_val', c_double_p), ('q_wconst_idx', c_int32_p)]
 
 
 class PlanDesc(ctypes.Structure):

@@ -92,6 +92,7 @@ struct BlockDev {     // one output block as seen by the contraction kernel (dev
   // quadratic-form blocks (dlb_block_desc::q_*; contract.cu QF epilogue): per 8-column n-tile a 16-byte record (group, valid columns, kind, first feature
   // column, Gram entry, coefficients), padded to ncb * BN / 8 tiles with group -1; direct groups: Gram entry of each of their 8 columns
   const int* qtile; const int* qdent; const double* qconst;   // qtile: one int4 record per n-tile (contract.cu QF epilogue)
+  const int* qw_off; const int* qw_coef; const double* qw_val;  // weighted constants of Gram entry e: items qw_off[e] .. qw_off[e + 1] - 1, value x coef[2 t] x coef[2 t + 1]
   int oslot;                           // output mode of a transformed multi-slot block: column stride between the slots' outputs (0: slot 0 only)
   const double* tdata;                 // output mode: [ncols] data d of the 'cubic'-transformed columns (0: untransformed column), or NULL
 };

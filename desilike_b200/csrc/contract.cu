@@ -686,7 +686,13 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
           const int e = i / (mtc * 8), rr = i - e * (mtc * 8);
           const int r = (rr >> 3) * UNIT + wm * 8 + (rr & 7);
           double v = red[(size_t)r * npm + e] + red[((size_t)BM + r) * npm + e];
-          if constexpr (QF) v += __ldg(blk->qconst + e);
+          if constexpr (QF) {
+            v += __ldg(blk->qconst + e);
+            for (int t = __ldg(blk->qw_off + e); t < __ldg(blk->qw_off + e + 1); ++t) {   // constant-feature parts: theta-dependent through their weight only
+              const int ca = __ldg(blk->qw_coef + 2 * t), cbq = __ldg(blk->qw_coef + 2 * t + 1);
+              v += __ldg(blk->qw_val + t) * (ca >= 0 ? cs[ca * BM + r] : 1.) * (cbq >= 0 ? cs[cbq * BM + r] : 1.);
+            }
+          }
           out[(long long)e * p.npad + r] = v;
         }
       }

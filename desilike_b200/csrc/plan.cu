@@ -41,6 +41,7 @@ struct Block {
   EntryMap* d_map = nullptr;
   std::vector<EntryMap> h_map;
   int *d_qtile = nullptr, *d_qdent = nullptr; double* d_qconst = nullptr;   // quadratic-form tables (dlb_block_desc::q_*), tiles as packed 16-byte records
+  int *d_qw_off = nullptr, *d_qw_coef = nullptr; double* d_qw_val = nullptr;
   double* d_tdata = nullptr;   // 'cubic' observable transform: data of the transformed columns (two-stage plans)
   int tcol = 0;                // first column of the block in the transformed-theory buffer of a two-stage plan
 };
@@ -447,7 +448,7 @@ static int build_launch(dlb_plan* plan, const std::vector<Block*>& blocks, bool 
       bd.tmask = pass == 0 ? b->d_tmask_white : b->d_tmask_plain;
       if (bd.tmask) (pass == 0 ? L.masked_white : L.masked_plain) = true;
       bd.cb_first = pass == 0 ? b->d_cb_first : nullptr;
-      bd.qtile = b->d_qtile; bd.qdent = b->d_qdent; bd.qconst = b->d_qconst;
+      bd.qtile = b->d_qtile; bd.qdent = b->d_qdent; bd.qconst = b->d_qconst; bd.qw_off = b->d_qw_off; bd.qw_coef = b->d_qw_coef; bd.qw_val = b->d_qw_val;
       tab.push_back(bd);
     }
     if (!ok) continue;
@@ -1043,7 +1044,7 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
     // Candidates (measured within 3 % of each other on C4 / C5 + marginalisation): 2 CTAs / SM x 8 warps with 32-row tiles and two k-chunks of 36, then
     // the 16-warp, 64-row forms: KC = 68 with 112-column blocks (one k-chunk per column block) when the features fit, KC = 76 with 96-column blocks, KC = 36
     int qK = 0;
-    for (int ib = 0; ib < desc->nblocks && allq; ++ib) qK = std::max(qK, desc->blocks[ib].terms[0].K);
+    for (int ib = 0; ib < desc->nblocks && allq; ++ib) qK = std::max(qK, desc->blocks[ib].q_K);
     std::vector<Variant> qcand;
     if (const char* e = getenv("DLB_QF_VARIANT")) { const int i = atoi(e); qcand.push_back(i == 0 ? Variant{1, 1, 7, 8, 1, 68} : (i == 1 ? Variant{1, 1, 6, 8, 1, 76} : (i == 3 ? Variant{1, 1, 7, 4, 2, 36} : Variant{1, 1, 7, 8, 1, 36}))); }
     else {
@@ -1065,7 +1066,9 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
         const dlb_term_desc& t0 = bd.terms[0];
         Block& qb = plan->qblocks[ib];
         const Block& ob = plan->blocks[ib];
-        std::vector<TermSpec> terms{TermSpec{0, -1, plan->gens[t0.gen].foff + t0.foff, t0.foff, t0.K, bd.q_matrix, nullptr}};
+        DLB_REQUIRE(bd.q_K > 0 && bd.q_foff >= t0.foff && (bd.q_foff % 2) == 0 && bd.q_foff + bd.q_K <= t0.foff + t0.K && bd.q_nw >= 0 && (bd.q_nw == 0 || (bd.q_wconst_val && bd.q_wconst_idx)),
+                    "quadratic-form tables: feature range / weighted constants invalid");
+        std::vector<TermSpec> terms{TermSpec{0, -1, plan->gens[t0.gen].foff + bd.q_foff, bd.q_foff, bd.q_K, bd.q_matrix, nullptr}};
         std::vector<double> zeros((size_t)bd.q_ncols, 0.);
         DLB_TRY(build_block_core(plan, qv, true, bd.q_ncols, 1, terms, zeros.data(), nullptr, 0, nullptr, qb));
         qb.npart = ob.npart; qb.poff = ob.poff; qb.coloff = ob.coloff; qb.gen = ob.gen; qb.fill = ob.fill; qb.fbase = ob.fbase; qb.d_map = ob.d_map;
@@ -1098,6 +1101,21 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
         DLB_TRY(upload(plan, tiles.data(), tiles.size(), &qb.d_qtile));
         DLB_TRY(upload(plan, bd.q_dent, (size_t)24 * bd.q_ngroups, &qb.d_qdent));
         DLB_TRY(upload(plan, bd.q_const, (size_t)ob.npart, &qb.d_qconst));
+        {   // weighted constants, grouped by Gram entry
+          std::vector<int> woff((size_t)ob.npart + 1, 0), wcoef((size_t)2 * std::max(bd.q_nw, 1), -1);
+          std::vector<double> wval((size_t)std::max(bd.q_nw, 1), 0.);
+          int prev = 0;
+          for (int w = 0; w < bd.q_nw; ++w) {
+            const int e = bd.q_wconst_idx[3 * w], ca = bd.q_wconst_idx[3 * w + 1], cbq = bd.q_wconst_idx[3 * w + 2];
+            DLB_REQUIRE(e >= prev && e < ob.npart && ca >= -1 && ca < desc->ncoef && cbq >= -1 && cbq < desc->ncoef, "quadratic-form tables: weighted constants must be sorted by entry, indices in range");
+            prev = e;
+            woff[e + 1] += 1; wcoef[2 * w] = ca; wcoef[2 * w + 1] = cbq; wval[w] = bd.q_wconst_val[w];
+          }
+          for (int e = 0; e < ob.npart; ++e) woff[e + 1] += woff[e];
+          DLB_TRY(upload(plan, woff.data(), woff.size(), &qb.d_qw_off));
+          DLB_TRY(upload(plan, wcoef.data(), wcoef.size(), &qb.d_qw_coef));
+          DLB_TRY(upload(plan, wval.data(), wval.size(), &qb.d_qw_val));
+        }
         qptr.push_back(&qb);
       }
       DLB_TRY(build_launch(plan, qptr, true, ast, desc->ncoef, plan->qlaunch));

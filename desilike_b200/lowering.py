@@ -205,31 +205,42 @@ def qform_tables(blk, force=False, coef_keys=None, const_features=None):
         for y in range(x, T):
             a, b = keys[x][0], keys[y][0]
             C = (2. if (x != y and a == b) else 1.) * (white[x] @ white[y].T)   # column k' pairs with f[k']: sum_k f_k C[k, k'] f_k'
-            C = 0.5 * (C + C.T) if x == y else C
             key = (pair(a, b), monomial(keys[x][1], keys[y][1]))
             if key in merged: merged[key][0] = merged[key][0] + C
             else: merged[key] = [C, keys[x][1], keys[y][1]]
-    direct = []   # (matrix column [K], Gram entry, coef a, coef b)
+    # With constant features c (values v) the contraction only runs over the non-constant ones N (rows kq): for a matrix C
+    #     f C f^T = f_N C_NN f_N^T + f_N . (C_Nc + C_cN^T) v + v^T C_cc v,
+    # i.e. quadratic columns, one direct (linear) column and a constant; a linear form f . h = f_N . h_N + v . h_c likewise.  The constants are
+    # theta-dependent only through their weight c_a c_b: ``wconst`` = (Gram entry, coef a, coef b, value), added once per point by the kernel.
+    kc_idx, kc_val = list(consts), np.array([consts[k] for k in consts])
+    direct, wconst = [], []   # direct: (matrix column over the rows kq, Gram entry, coef a, coef b)
+
+    def linear(h, entry, ca, cb):   # f . h for a vector over ALL K features
+        direct.append((h[kq], entry, ca, cb))
+        if kc_idx and np.any(h[kc_idx] != 0.): wconst.append((float(kc_val.dot(h[kc_idx])), entry, ca, cb))
+
     for (entry, _), (C, cx, cy) in merged.items():
-        # f C f^T with constant features c: the (non-constant, constant) cross terms and the (constant, constant) part are linear / constant in f --
-        # both are the dot product of f with a fixed column: sum_k f_k (sum_{k' const} (C[k, k'] + C[k', k] [k non-constant]) c_k')
-        col = np.zeros(K)
-        for kc, v in consts.items():
-            if v == 0.: continue
-            col += v * C[:, kc]
-            col[kq] += v * C[kc, kq]
-        if consts and np.any(col != 0.): direct.append((col, entry, cx, cy))
+        if not kc_idx: continue
+        lin = np.zeros(K)
+        lin[kq] = (C[np.ix_(kq, kc_idx)] + C[np.ix_(kc_idx, kq)].T) @ kc_val
+        if np.any(lin != 0.): direct.append((lin[kq], entry, cx, cy))
+        cc = float(kc_val @ C[np.ix_(kc_idx, kc_idx)] @ kc_val)
+        if cc != 0.: wconst.append((cc, entry, cx, cy))
     for x in range(T):
         a = keys[x][0]
-        direct.append((-(2. if a == 0 else 1.) * (white[x] @ r0), pair(0, a), keys[x][1], -1))
-        for i in range(nconst): direct.append((white[x] @ g[i], nS + i * R + a, keys[x][1], -1))
-    # direct columns with the same Gram entry and weight monomial add up (e.g. -2 M_x r0 joins the constant-feature column of the pair (x, '1' term));
-    # then tiles of 8 columns with DISTINCT Gram entries each (the lanes of a tile update their entries concurrently in the kernel)
-    dmerged = {}
+        linear(-(2. if a == 0 else 1.) * (white[x] @ r0), pair(0, a), keys[x][1], -1)
+        for i in range(nconst): linear(white[x] @ g[i], nS + i * R + a, keys[x][1], -1)
+    # direct columns / weighted constants with the same Gram entry and weight monomial add up (e.g. -2 M_x r0 joins the constant-feature column of
+    # the pair (x, '1' term)); then tiles of 8 columns with DISTINCT Gram entries each (the lanes of a tile update their entries concurrently)
+    dmerged, wmerged = {}, {}
     for vec, entry, ca, cb in direct:
         key = (entry, monomial(ca, cb))
         if key in dmerged: dmerged[key][0] = dmerged[key][0] + vec
         else: dmerged[key] = [vec, entry, ca, cb]
+    for val, entry, ca, cb in wconst:
+        key = (entry, monomial(ca, cb))
+        if key in wmerged: wmerged[key][0] += val
+        else: wmerged[key] = [val, entry, ca, cb]
     dtiles = []
     for vec, entry, ca, cb in dmerged.values():
         for tile in dtiles:
@@ -237,12 +248,11 @@ def qform_tables(blk, force=False, coef_keys=None, const_features=None):
         else: dtiles.append([(vec, entry, ca, cb)])
     ndt = len(dtiles)
     ncolq = len(merged) * Kp + ndt * 8
-    mat = np.zeros((K, ncolq))
+    mat = np.zeros((len(kq), ncolq))
     tiles, groups, dent = [], [], []   # tiles: (group, first feature of the tile relative to the generator segment, valid columns)
     col = 0
     for (entry, _), (C, cx, cy) in merged.items():
-        mat[:, col:col + len(kq)] = C[:, kq]
-        if consts: mat[[k for k in consts], col:col + len(kq)] = 0.   # rows of constant features: their contribution sits in the direct columns
+        mat[:, col:col + len(kq)] = C[np.ix_(kq, kq)]
         groups.append((0, entry, cx, cy)); dent.append([[-1, -1, -1]] * 8)
         for j in range(Kp // 8): tiles.append((len(groups) - 1, foff + kq[0] + 8 * j, min(8, len(kq) - 8 * j)))
         col += Kp
@@ -251,12 +261,14 @@ def qform_tables(blk, force=False, coef_keys=None, const_features=None):
         for j, (vec, entry, ca, cb) in enumerate(dtiles[t]):
             mat[:, col + j] = vec; ent[j] = [entry, ca, cb]
         groups.append((1, 0, -1, -1)); dent.append(ent)
-        tiles.append((len(groups) - 1, foff, 8))
+        tiles.append((len(groups) - 1, foff + kq[0], 8))
         col += 8
     const = np.zeros(nS + R * nconst)
     const[pair(0, 0)] = r0.dot(r0)
     for i in range(nconst): const[nS + i * R] = -r0.dot(g[i])
-    return dict(matrix=mat, ncolq=ncolq, gen=gi, foff=foff, K=K, tiles=i32(tiles), groups=i32(groups), dent=i32(dent), const=f64(const))
+    wlist = sorted(wmerged.values(), key=lambda w: w[1])   # by Gram entry
+    return dict(matrix=mat, ncolq=ncolq, gen=gi, foff=foff + kq[0], K=len(kq), tiles=i32(tiles), groups=i32(groups), dent=i32(dent), const=f64(const),
+                wconst_val=f64([w[0] for w in wlist]), wconst_idx=i32([[w[1], w[2], w[3]] for w in wlist]).reshape(-1, 3))
 
 
 class Lowered(object):
@@ -603,8 +615,11 @@ class Lowered(object):
             if blk.get('qform') is not None:
                 q = blk['qform']
                 qm, qt, qg, qd, qc = f64(q['matrix']), i32(q['tiles']), i32(q['groups']), i32(q['dent']), f64(q['const'])
-                keep += [qm, qt, qg, qd, qc]
+                qwv, qwi = f64(q['wconst_val']), i32(q['wconst_idx'])
+                keep += [qm, qt, qg, qd, qc, qwv, qwi]
                 b.q_ncols, b.q_ngroups = int(q['ncolq']), len(qg)
+                b.q_foff, b.q_K, b.q_nw = int(q['foff']), int(q['K']), len(qwv)
+                if len(qwv): b.q_wconst_val, b.q_wconst_idx = as_ptr(qwv), as_ptr(qwi, ctypes.c_int32)
                 b.q_matrix, b.q_tiles, b.q_groups, b.q_dent, b.q_const = as_ptr(qm), as_ptr(qt, ctypes.c_int32), as_ptr(qg, ctypes.c_int32), as_ptr(qd, ctypes.c_int32), as_ptr(qc)
             if blk.get('entry_kind') is not None:
                 ek, ei, ej = i32(blk['entry_kind']), i32(blk['entry_i']), i32(blk['entry_j'])

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DLB_ABI_VERSION 9
+#define DLB_ABI_VERSION 10
 
 typedef enum {
   DLB_OK = 0,
@@ -129,6 +129,10 @@ typedef struct {
    * feature k', the group's sum weighted by coef_a coef_b is added to its Gram entry.  kind 1 (direct): column j is added to Gram entry q_dent[24 g + 3 j] (-1: unused), weighted by the
    * coefficients q_dent[24 g + 3 j + 1] and [.. + 2] (-1 = 1).  q_const [npart] is added to the partials (theta-independent parts).  Same partials as the slot form. */
   int32_t q_ncols; int32_t q_ngroups; const double* q_matrix; const int32_t* q_tiles; const int32_t* q_groups; const int32_t* q_dent; const double* q_const;
+  /* q_matrix is [q_K, q_ncols] over the feature columns q_foff .. q_foff + q_K - 1 of the generator segment (the NON-constant features: constant ones --
+   * the (1, 0) head of an MLP segment -- are folded into direct columns and into the q_nw weighted constants: entry q_wconst_idx[3 w] += q_wconst_val[w] x
+   * coefficient q_wconst_idx[3 w + 1] x coefficient q_wconst_idx[3 w + 2] (-1 = 1), sorted by entry, added once per point). */
+  int32_t q_foff; int32_t q_K; int32_t q_nw; const double* q_wconst_val; const int32_t* q_wconst_idx;
 } dlb_block_desc;
 
 typedef struct {

@@ -110,6 +110,8 @@ def evaluate(low, X, feature_fn=None, white=True, use_qform=False):
             out = f[:, q['foff']:q['foff'] + q['K']] @ q['matrix']
             nS = R * (R + 1) // 2
             part = np.zeros((N, nS + R * nc)) + q['const']
+            for val, (ew, caw, cbw) in zip(q['wconst_val'], q['wconst_idx']):   # weighted constants (constant features)
+                part[:, ew] += val * (C[:, caw] if caw >= 0 else 1.) * (C[:, cbw] if cbw >= 0 else 1.)
             for t8, (gid, k0, nv) in enumerate(q['tiles']):
                 kind, e, ca, cb = q['groups'][gid]
                 cols = out[:, 8 * t8:8 * t8 + 8]

@@ -343,7 +343,7 @@ def test_quadratic_form_tables_reproduce_the_slot_form(name):
         # 21 term pairs, of which (1, b1^2) and (b1, b1) of slot 0 carry the same weight b1^2 into the same Gram entry: 20 groups of 64 quadratic columns
         # (the hidden units; the constant (1, 0) head of the segment goes to direct columns: 20, the 6 r0 columns merge into them, + 6 x 4 constant rows
         # = 44 -> 6 tiles of distinct Gram entries)
-        assert q is not None and q['ncolq'] == 20 * 64 + 6 * 8 and q['matrix'].shape == (66, 1328)
+        assert q is not None and q['ncolq'] == 20 * 64 + 6 * 8 and q['matrix'].shape == (64, 1328) and (q['foff'], q['K']) == (2, 64)
         for gid, (kind, _, _, _) in enumerate(q['groups']):
             if kind == 1:
                 ents = [e for e, _, _ in q['dent'][gid] if e >= 0]
