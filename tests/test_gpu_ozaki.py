@@ -72,3 +72,18 @@ def test_wide_mlp_contraction_at_the_stress_variant_shapes(gpu_required):
         assert 2. * np.max(np.abs(got['loglikelihood'] - other['loglikelihood'])) < 1e-4
         assert np.allclose(got['x_solved'], other['x_solved'], rtol=1e-5, atol=1e-5)
     assert np.array_equal(got['status'], fp64['status'])
+
+
+@pytest.mark.parametrize('cluster', [2, 4])
+def test_ozaki_matmul_cluster_multicast_path(gpu_required, monkeypatch, cluster):
+    """Opt-in thread-block clusters with TMA multicast of the A operand (DLB_OZAKI_CLUSTER): same bits as the default launch and as the NumPy statement,
+    including column-tile counts that are not a multiple of the cluster size (dummy tiles)."""
+    from desilike_b200 import mlp
+    rng = np.random.default_rng(cluster)
+    for rows, K, N in [(500, 512, 512), (333, 200, 6 * 64 + 10), (130, 96, 5 * 64)]:
+        X, W = rng.standard_normal((rows, K)), rng.standard_normal((K, N))
+        base = mlp.ozaki_matmul(X, W, slices=6)
+        monkeypatch.setenv('DLB_OZAKI_CLUSTER', str(cluster))
+        got = mlp.ozaki_matmul(X, W, slices=6)
+        monkeypatch.delenv('DLB_OZAKI_CLUSTER')
+        assert np.array_equal(got, base) and np.array_equal(got, mlp.ozaki_matmul_reference(X, W, slices=6))
