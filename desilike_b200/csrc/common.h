@@ -119,6 +119,7 @@ struct ContractParams {
   int nstages, resident, ast, dpad, npart_max;
   int masked;                            // some block of the launch has sub-tile masks (BlockDev::tmask): use the kernel instances with the masked path
   int qform;                             // quadratic-form blocks (BlockDev::qtile): the QF kernel instance
+  int qf_offset_ns;                      // 2 CTAs / SM: start delay of the second-resident CTA (phase offset between the two)
   long long U;                           // number of row units (variant_unit rows each) to process
   long long* prof;                       // DLB_PROFILE builds: 8 cycle counters (summed over warps)
 };

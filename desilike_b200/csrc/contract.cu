@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
     for (int i = tid; i < p.ngen * (int)(sizeof(GenDev) / 4); i += NTH) reinterpret_cast<int*>(gens_s)[i] = reinterpret_cast<const int*>(p.gens)[i];
   }
   if constexpr (QF && CPS == 2) {   // two CTAs per SM: start the second-resident one half a column block late, so that one's epilogue overlaps the other's DMMAs
-    if (blockIdx.x >= (gridDim.x + 1) / 2) __nanosleep(3000);
+    if (blockIdx.x >= (gridDim.x + 1) / 2) __nanosleep((unsigned)p.qf_offset_ns);
   }
   if constexpr (QF) {   // the epilogue reads feature columns up to the 8-column padding of a group (x exact zeros): every A entry must be finite
     for (int i = tid; i < BM * p.ast; i += NTH) A_s[i] = 0.;

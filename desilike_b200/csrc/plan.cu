@@ -667,6 +667,8 @@ static int run_contract(dlb_plan* plan, const double* d_params, long long N, lon
   ContractParams cp;
   fill_params(plan, L, cp, d_params, N, npad);
   cp.qform = qf ? 1 : 0;
+  static const int qf_offset = getenv("DLB_QF_OFFSET_NS") ? atoi(getenv("DLB_QF_OFFSET_NS")) : 3000;
+  cp.qf_offset_ns = qf_offset;
   cp.blocks = mode == 0 ? L.d_white : L.d_plain;
   cp.sched = mode == 0 ? L.d_sched_white : L.d_sched_plain; cp.nsched = mode == 0 ? L.nsched : L.nsched_plain;
   cp.masked = mode == 0 ? L.masked_white : L.masked_plain;
