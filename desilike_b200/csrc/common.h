@@ -226,6 +226,7 @@ struct GatherDev {
   int world;                               // 0: no gather
   int signal;                              // publish the sequence number at the end of this launch (last launch of an evaluation)
   int with_solved;
+  int xs_only;                             // >= 0: x_solved is stored into this rank's window only (the peers get it by DMA afterwards, gather_push_xs); -1: every rank
   double* lp[DLB_MAX_RANKS];               // every rank's window, at this launch's first point: logposterior [n]
   double* xs[DLB_MAX_RANKS];               // ... x_solved [n, ns] (plan order), or NULL
   unsigned long long* flag[DLB_MAX_RANKS]; // this rank's flag word in every rank's window
@@ -257,6 +258,14 @@ int launch_solve(const SolveParams& p, cudaStream_t stream);
 int gather_fill(dlb_gather* g, int buf, long long start, long long n, long long total, int ns, bool with_solved, bool signal, GatherDev* out);
 void gather_next_sequence(dlb_gather* g, int buf);
 int gather_publish_empty(dlb_gather* g, int buf, long long total, cudaStream_t stream);
+// DMA form of the x_solved exchange (large payloads): the finish kernel stores x_solved into the OWN window only and does not publish; after the
+// evaluation gather_push_xs copies the rank's slice to every peer's window with the copy engines on a side stream (no SM, no NVLink stores stalling the
+// next evaluation's kernels) and publishes the sequence number behind the copies.  gather_before_write makes `stream` wait for the previous push out of
+// the same buffer.
+bool gather_use_dma(const dlb_gather* g, long long n, int ns, bool with_solved);
+int gather_rank(const dlb_gather* g);
+int gather_before_write(dlb_gather* g, int buf, cudaStream_t stream);
+int gather_push_xs(dlb_gather* g, int buf, long long start, long long n, long long total, int ns, cudaStream_t stream);
 
 int measure_fp64_peak(int kind, double* tflops);
 

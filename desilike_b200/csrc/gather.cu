@@ -24,6 +24,9 @@ struct dlb_gather {
   int* h_err = nullptr; int* d_err = nullptr;   // mapped pinned: first rank that timed out in a wait (1-based), 0 = none
   unsigned long long seq[8] = {};         // evaluations published into each buffer so far
   double timeout_s = 20.;
+  cudaStream_t s_push = nullptr;          // side stream of the DMA pushes
+  cudaEvent_t ev_done = nullptr, ev_push[8] = {};
+  bool pushed[8] = {};
 };
 
 namespace dlb {
@@ -45,7 +48,7 @@ int gather_fill(dlb_gather* g, int buf, long long start, long long n, long long 
   DLB_REQUIRE(buf >= 0 && buf < g->nbuf, "gather: buffer index out of range");
   const long long need = total * (with_solved ? 1 + ns : 1);
   DLB_REQUIRE(start >= 0 && n >= 0 && start + n <= total && need <= g->capacity, "gather: slice outside the batch or batch larger than the window capacity");
-  out->world = g->world; out->signal = signal ? 1 : 0; out->with_solved = (with_solved && ns > 0) ? 1 : 0;
+  out->world = g->world; out->signal = signal ? 1 : 0; out->with_solved = (with_solved && ns > 0) ? 1 : 0; out->xs_only = -1;
   for (int r = 0; r < g->world; ++r) {
     double* base = gather_peer_buffer(g, r, buf);
     out->lp[r] = base + start;
@@ -58,6 +61,23 @@ int gather_fill(dlb_gather* g, int buf, long long start, long long n, long long 
 }
 
 void gather_next_sequence(dlb_gather* g, int buf) { g->seq[buf] += 1; }
+
+int gather_rank(const dlb_gather* g) { return g->rank; }
+
+// DMA pushes pay ~2 (world - 1) copy launches per evaluation: worthwhile for large x_solved payloads only (default threshold 8 MB; DLB_GATHER_DMA=0
+// disables, =1 forces)
+bool gather_use_dma(const dlb_gather* g, long long n, int ns, bool with_solved) {
+  if (!g || g->world <= 1 || !with_solved || ns <= 0 || n <= 0) return false;
+  static const int mode = getenv("DLB_GATHER_DMA") ? atoi(getenv("DLB_GATHER_DMA")) : -1;
+  if (mode == 0) return false;
+  if (mode == 1) return true;
+  return (size_t)n * ns * sizeof(double) >= ((size_t)8 << 20);
+}
+
+int gather_before_write(dlb_gather* g, int buf, cudaStream_t stream) {
+  if (g->pushed[buf]) DLB_CUDA(cudaStreamWaitEvent(stream, g->ev_push[buf], 0));   // the previous push out of this buffer has read the own slice
+  return DLB_OK;
+}
 
 namespace {
 
@@ -76,6 +96,15 @@ __global__ void gather_publish_kernel(const double* __restrict__ src, long long 
       __threadfence_system();
       for (int r = 0; r < gd.world; ++r) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(gd.flag[r]), "l"(gd.seq) : "memory");
     }
+  }
+}
+
+// sequence number to every rank's flag word (behind DMA copies on the same stream; its own kernel: the block counter of gather_publish_kernel / the
+// finish kernels belongs to the launches of the main stream, which may run concurrently)
+__global__ void gather_flag_kernel(GatherDev gd) {
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    for (int r = 0; r < gd.world; ++r) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(gd.flag[r]), "l"(gd.seq) : "memory");
   }
 }
 
@@ -101,6 +130,28 @@ int gather_publish_empty(dlb_gather* g, int buf, long long total, cudaStream_t s
   gather_publish_kernel<<<1, 32, 0, stream>>>(nullptr, 0, gd);
   g_launches++;
   DLB_CUDA(cudaGetLastError());
+  return DLB_OK;
+}
+
+int gather_push_xs(dlb_gather* g, int buf, long long start, long long n, long long total, int ns, cudaStream_t stream) {
+  if (!g->s_push) {
+    DLB_CUDA(cudaStreamCreateWithFlags(&g->s_push, cudaStreamNonBlocking));
+    DLB_CUDA(cudaEventCreateWithFlags(&g->ev_done, cudaEventDisableTiming));
+    for (int b = 0; b < g->nbuf; ++b) DLB_CUDA(cudaEventCreateWithFlags(&g->ev_push[b], cudaEventDisableTiming));
+  }
+  DLB_CUDA(cudaEventRecord(g->ev_done, stream));            // the finish kernels of this evaluation have filled the own window
+  DLB_CUDA(cudaStreamWaitEvent(g->s_push, g->ev_done, 0));
+  const size_t off = (size_t)total + (size_t)start * ns, bytes = (size_t)n * ns * sizeof(double);
+  const double* src = gather_peer_buffer(g, g->rank, buf) + off;
+  for (int r = 0; r < g->world; ++r)
+    if (r != g->rank) DLB_CUDA(cudaMemcpyAsync(gather_peer_buffer(g, r, buf) + off, src, bytes, cudaMemcpyDeviceToDevice, g->s_push));
+  GatherDev gd;
+  DLB_TRY(gather_fill(g, buf, 0, 0, total, 0, false, true, &gd));
+  gather_flag_kernel<<<1, 32, 0, g->s_push>>>(gd);   // behind the copies: sequence number to every rank's flag word
+  g_launches++;
+  DLB_CUDA(cudaGetLastError());
+  DLB_CUDA(cudaEventRecord(g->ev_push[buf], g->s_push));
+  g->pushed[buf] = true;
   return DLB_OK;
 }
 
@@ -169,6 +220,9 @@ int dlb_gather_publish(dlb_gather* g, int32_t buf, const double* src, int64_t co
   DLB_REQUIRE(g && (src || count == 0) && count >= 0 && offset >= 0, "gather publish: NULL gather / src or negative count / offset");
   DLB_REQUIRE(buf >= 0 && buf < g->nbuf && offset + count <= g->capacity, "gather publish: buffer index / range outside the window");
   DLB_CUDA(cudaSetDevice(g->device));
+  // a DMA push of an evaluation into this buffer publishes its (older) sequence number from the side stream: this publish must come after it, so that
+  // the flags stay monotonic and a wait for the newer number also covers the pushed data
+  DLB_TRY(gather_before_write(g, buf, (cudaStream_t)stream_));
   g->seq[buf] += 1;
   GatherDev gd;
   DLB_TRY(gather_fill(g, buf, offset, count, offset + count, 0, false, true, &gd));
@@ -211,6 +265,9 @@ void dlb_gather_destroy(dlb_gather* g) {
   if (g->window) cudaFree(g->window);
   if (g->counter) cudaFree(g->counter);
   if (g->h_err) cudaFreeHost(g->h_err);
+  if (g->s_push) cudaStreamDestroy(g->s_push);
+  if (g->ev_done) cudaEventDestroy(g->ev_done);
+  for (auto& e : g->ev_push) if (e) cudaEventDestroy(e);
   delete g;
 }
 

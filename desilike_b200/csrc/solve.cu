@@ -30,7 +30,8 @@ __device__ __forceinline__ void store_logpost(const SolveParams& p, long long pt
 __device__ __forceinline__ void store_xsolved(const SolveParams& p, long long pt, int i, double v) {
   if (p.xsolved) p.xsolved[pt * p.ns + i] = v;
   if (p.gather.with_solved)
-    for (int r = 0; r < p.gather.world; ++r) p.gather.xs[r][pt * p.ns + i] = v;
+    for (int r = 0; r < p.gather.world; ++r)
+      if (p.gather.xs_only < 0 || r == p.gather.xs_only) p.gather.xs[r][pt * p.ns + i] = v;
 }
 __device__ __forceinline__ bool wants_xsolved(const SolveParams& p) { return p.xsolved != nullptr || p.gather.with_solved; }
 
@@ -440,7 +441,8 @@ __global__ void __launch_bounds__(ST_THREADS) finish_solve_thread_kernel(const _
       const double v = xstage[e];
       if (p.xsolved) p.xsolved[e0 + e] = v;
       if (p.gather.with_solved)
-        for (int r = 0; r < p.gather.world; ++r) p.gather.xs[r][e0 + e] = v;
+        for (int r = 0; r < p.gather.world; ++r)
+          if (p.gather.xs_only < 0 || r == p.gather.xs_only) p.gather.xs[r][e0 + e] = v;
     }
   }
   gather_tail(p);
