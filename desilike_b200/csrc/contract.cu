@@ -109,7 +109,7 @@ __device__ __forceinline__ double ipow(double x, int n) {
 template <int MT, int NT, int MTC, int KC, bool BETA = true>
 __device__ __forceinline__ void mma_chunk(double (&acc)[MT][NT][2], const double* __restrict__ A, int astride, const double* __restrict__ B,
                                           const double (&beta)[MT], int nk4) {
-#pragma unroll 3
+#pragma unroll(BETA ? 3 : 8)   // (quadratic-form chunks are 8 k4 steps for 64 features: no remainder loop)
   for (int k4 = 0; k4 < nk4; ++k4) {
     double a[MTC], b[NT];
 #pragma unroll
