@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const MlpFuse
           for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.;
         const double* A = Hin + (wm * 16 + lr) * MLP_AS + lc;
         const double* B = wl + (wn * 32 + lr) * ks + lc;
+#pragma unroll 4
         for (int k4 = 0; k4 < kpad / 4; ++k4) {
           double a[2], b[4];
 #pragma unroll
