@@ -572,8 +572,8 @@ __global__ void __launch_bounds__(WM * 64, CPS) contract_kernel(const __grid_con
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
             // columns beyond the group's K features hold exact zeros in the accumulators (zero matrix columns) and finite values in A_s (zeroed at
-            // kernel start; a read past the row end lands in the next row / the parameter tile): no guard needed.  Padding tiles (group -1) and
-            // direct tiles carry weight 0 here.
+            // kernel start; the plan sizes the row stride so that whole 8-column tiles stay inside the row): no guard needed.  Padding tiles (group -1)
+            // and direct tiles carry weight 0 here.
             const int kind = meta[nt].x >> 24, ca = (meta[nt].w & 0xFFFF) - 1, cbq = (meta[nt].w >> 16) - 1;
             const bool quad = kind == 0 && (meta[nt].x & 0xFFFF) != 0xFFFF;
             any_direct |= kind;

@@ -897,6 +897,9 @@ int dlb_plan_create(const dlb_plan_desc* desc, dlb_plan** out) {
       ast = std::max(ast, td.foff + chunk_extent(td.K));
       maxK = std::max(maxK, td.K);
     }
+    // quadratic-form tables: the epilogue reads whole 8-column feature tiles -- keep them inside the row of the resident A tile (its padding is zero), so
+    // that a non-finite feature of one point can never reach a neighbouring point through a read past the row end
+    if (bd.q_ncols > 0 && bd.q_K > 0) ast = std::max(ast, bd.q_foff + ((bd.q_K + 7) & ~7));
   }
   ast = round_ast(ast);
   int npart_bound = 1;

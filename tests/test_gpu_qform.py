@@ -48,3 +48,28 @@ def test_quadratic_form_plan_hessian_and_multipass(gpu_required, monkeypatch):
     monkeypatch.setenv('DLB_MAX_CHUNK', '768')
     c = quad.eval(X)
     assert np.array_equal(c['logposterior'], one['logposterior']) and np.array_equal(c['x_solved'], one['x_solved'])
+
+
+@pytest.mark.parametrize('name', ['mlp', 'taylor'])
+def test_quadratic_form_non_finite_point_stays_isolated(gpu_required, name):
+    """A NaN / overflowing parameter point poisons its own result only: the feature tiles the epilogue reads never cross into a neighbouring
+    point's row of the resident A tile (points at the edges of the 64 / 128-point tiles included)."""
+    import desilike_b200
+    from desilike_b200 import _capi
+    spec = (configs.config_c4(ntracers=2, nkin=40, nbins=10, hidden=(20, 20)) if name == 'mlp'
+            else configs.config_c5(ntracers=2, nkin=40, nbins=12, order=2, solved=True))
+    for key in spec['priors']: spec['priors'][key] = None
+    plan = desilike_b200.Plan(spec, qform=True)
+    assert plan.kernels['quadratic_form']
+    X = configs.sample_points(spec, 700, seed=23)
+    clean = plan.eval(X)
+    bad = [0, 63, 64, 127, 128, 255, 699]
+    Y = X.copy()
+    Y[bad[::2], 0] = np.nan
+    Y[bad[1::2], :] = 1e200
+    got = plan.eval(Y)
+    ok = np.ones(len(X), dtype=bool); ok[bad] = False
+    assert not np.any(np.isfinite(got['logposterior'][bad[::2]])) and np.all(got['status'][bad[::2]] & (_capi.PT_NONFINITE | _capi.PT_NOT_SPD))
+    for key in ['logposterior', 'loglikelihood', 'x_solved', 'status']:
+        assert np.array_equal(got[key][ok], clean[key][ok]), key
+    plan.close()
