@@ -64,6 +64,8 @@ struct MlpLayers { int act = 0; std::vector<Block> layers; std::vector<Launch> l
 
 }  // namespace dlb
 
+constexpr int MAX_SUB = 8;   // sub-batches of the pipelined host-buffer path
+
 struct dlb_plan {
   int device = 0;
   int d = 0, ngen = 0, ncoef = 0, fstride = 4, ns = 0, nmarg = 0, ntheory = 0, nsm = 1, dpad = 1;   // d: columns of the EXTENDED parameter row (inputs + derived)
@@ -110,7 +112,7 @@ struct dlb_plan {
   dlb::GroupEntry* d_gent = nullptr; int *d_gent_off = nullptr, *d_m0_off = nullptr; long long* d_chi_rows = nullptr; int nchi = 0, comp_max = 0;
   double* w_hess = nullptr; long long hess_cap = 0;
   cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host-buffer path
-  cudaEvent_t ev_pipe[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_pipe[2 * MAX_SUB + 2] = {};      // [c] sub-batch c copied in, [MAX_SUB + c] its kernels done, then pipeline start / end
   dlb::SolveBlock* d_solve_blocks = nullptr;
   long long ptotal = 0;  // partial rows (in units of npad doubles)
   std::vector<void*> owned;
@@ -1322,6 +1324,63 @@ int dlb_eval_batch(dlb_plan* plan, const double* params, int64_t N, double* logp
   return dlb_eval_batch_hessian(plan, params, N, logposterior, loglikelihood, logprior, x_solved, nullptr, status, stream_);
 }
 
+// Sub-batches of the pipelined host-buffer path  H2D (copy-in stream) | kernels (caller's stream) | D2H (copy-out stream).
+// The persistent contraction kernel takes as long as its busiest CTA, so lengths are whole multiples of the WAVE QUANTUM (grid x tile rows) of the
+// likelihood contraction (the last sub-batch takes the rest): a split then adds no tile pass.  Candidates: equal pass counts, and a short first / last
+// sub-batch (1-2 passes: little H2D before the first kernel, little D2H after the last) around equal middle ones; the three-stage timeline of every
+// candidate is simulated with the plan's executed FLOP per point at ~ 55 % of the FP64 tensor peak and 50 GB/s per PCIe direction, and the shortest wins.
+// Every launch after the first is charged a fraction of a tile pass for ramp-up / tail imbalance (measured on B200, 131 072 points: C4 0.12 ms of a
+// 0.36 ms pass; variants whose second-resident CTA starts with a half tile stream the matrices once more per launch -- C5 0.2 ms) plus a fixed cost
+// for the launches, cross-stream events and small copies.  DLB_NSUB forces the count.
+static int choose_sub_batches(const dlb_plan* plan, long long n, double bytes_in, double bytes_out, long long* lens) {
+  const int forced = getenv("DLB_NSUB") ? atoi(getenv("DLB_NSUB")) : 0;   // (read per call: tests switch it)
+  static const double T_SUB = getenv("DLB_SUB_COST_US") ? atof(getenv("DLB_SUB_COST_US")) * 1e-6 : 40e-6;
+  const Launch& L = plan->two_stage ? plan->wlaunch : (plan->qform ? plan->qlaunch : plan->launch);
+  const long long Q = (std::max<long long>(64, (long long)plan->nsm * L.var.CPS * variant_bm(L.var)) + 63) / 64 * 64;
+  const double t_pt = std::max(dlb_plan_executed_flops(plan), 0.) / 20e12, BW = 50e9;
+  const double t_launch = T_SUB + ((L.var.CPS == 2 && L.var.MT > 1) ? 0.8 : 0.3) * (double)Q * t_pt;
+  const long long P = (n + Q - 1) / Q;   // tile passes of the whole batch
+  auto simulate = [&](const long long* len, int c) {
+    double tin = 0., kend = 0., tout = 0.;
+    for (int i = 0; i < c; ++i) {
+      tin += (double)len[i] * bytes_in / BW;
+      kend = std::max(tin, kend) + (double)len[i] * t_pt + (i ? t_launch : 0.);
+      tout = std::max(kend, tout) + (double)len[i] * bytes_out / BW;
+    }
+    return tout;
+  };
+  lens[0] = n;
+  int best = 1;
+  double best_t = simulate(lens, 1);
+  bool have_forced = forced == 1;
+  long long cand[MAX_SUB];
+  auto consider = [&](const long long* passes, int c) {
+    long long used = 0;
+    for (int i = 0; i + 1 < c; ++i) { cand[i] = passes[i] * Q; used += cand[i]; }
+    if (used >= n) return;
+    cand[c - 1] = n - used;
+    const double t = simulate(cand, c);
+    if (forced ? (c == forced && (!have_forced || t < best_t)) : t < best_t) {
+      best = c; best_t = t; have_forced = have_forced || forced == c;
+      for (int i = 0; i < c; ++i) lens[i] = cand[i];
+    }
+  };
+  long long passes[MAX_SUB];
+  for (int c = 2; c <= MAX_SUB && c <= P; ++c) {
+    for (int i = 0; i < c; ++i) passes[i] = P / c + (i < P % c ? 1 : 0);       // equal pass counts
+    consider(passes, c);
+    for (int f = 1; f <= 2; ++f)
+      for (int l = 1; l <= 2; ++l) {                                             // short first / last sub-batch
+        const long long mid = P - f - l;
+        if (c < 3 || mid < c - 2) continue;
+        passes[0] = f; passes[c - 1] = l;
+        for (int i = 0; i < c - 2; ++i) passes[1 + i] = mid / (c - 2) + (i < mid % (c - 2) ? 1 : 0);
+        consider(passes, c);
+      }
+  }
+  return best;
+}
+
 static int eval_impl(dlb_plan* plan, const double* params, int64_t N, double* logposterior, double* loglikelihood, double* logprior,
                      double* x_solved, double* hessian, int32_t* status, void* stream_, dlb_gather* gather, int gbuf, long long gstart, long long gtotal,
                      bool gsolved);
@@ -1376,11 +1435,15 @@ static int eval_impl(dlb_plan* plan, const double* params, int64_t N, double* lo
       DLB_CUDA(cudaMalloc((void**)&plan->w_hess, (size_t)n * nhess * sizeof(double)));
       plan->hess_cap = n;
     }
-    // Host buffers: split the chunk into sub-chunks and pipeline  H2D (copy-in stream) | kernels (caller's stream) | D2H (copy-out
-    // stream)  so that the PCIe transfers of one sub-chunk overlap the kernels of its neighbours.  Device buffers: one pass.
-    static const long long SUB_MIN = getenv("DLB_SUB_MIN") ? atoll(getenv("DLB_SUB_MIN")) : 65536;   // smaller sub-chunks cost more in kernel efficiency than the overlap gains (measured at 16384: C5 e2e -19 %)
+    // Host buffers: split the chunk into sub-batches and pipeline  H2D (copy-in stream) | kernels (caller's stream) | D2H (copy-out
+    // stream)  so that the PCIe transfers of one sub-batch overlap the kernels of its neighbours.  Device buffers: one pass.
+    long long sublens[MAX_SUB] = {n};
     int nsub = 1;
-    if (any_host && !plan->timing && n >= 2 * SUB_MIN) nsub = (int)std::min<long long>(4, n / SUB_MIN);
+    if (any_host && !plan->timing) {
+      const double bytes_out = ((logposterior && !lp_dev) ? 8 : 0) + ((loglikelihood && !ll_dev) ? 8 : 0) + ((logprior && !pr_dev) ? 8 : 0) +
+                               ((x_solved && ns && !xs_dev) ? 8 * ns : 0) + ((status && !st_dev) ? 4 : 0) + ((hessian && !hs_dev) ? 8 * nhess : 0);
+      nsub = choose_sub_batches(plan, n, in_dev ? 0. : plan->d_in * 8., bytes_out, sublens);
+    }
     cudaStream_t s_in = stream, s_out = stream;
     if (nsub > 1) {
       if (!plan->s_in) {
@@ -1389,15 +1452,14 @@ static int eval_impl(dlb_plan* plan, const double* params, int64_t N, double* lo
         for (auto& e : plan->ev_pipe) DLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       }
       s_in = plan->s_in; s_out = plan->s_out;
-      DLB_CUDA(cudaEventRecord(plan->ev_pipe[8], stream));          // staging buffers may still be in use by earlier work on `stream`
-      DLB_CUDA(cudaStreamWaitEvent(s_in, plan->ev_pipe[8], 0));
-      DLB_CUDA(cudaStreamWaitEvent(s_out, plan->ev_pipe[8], 0));
+      DLB_CUDA(cudaEventRecord(plan->ev_pipe[2 * MAX_SUB], stream));          // staging buffers may still be in use by earlier work on `stream`
+      DLB_CUDA(cudaStreamWaitEvent(s_in, plan->ev_pipe[2 * MAX_SUB], 0));
+      DLB_CUDA(cudaStreamWaitEvent(s_out, plan->ev_pipe[2 * MAX_SUB], 0));
     }
-    const long long sublen = ((n + nsub - 1) / nsub + 63) / 64 * 64;
     double* w = plan->w_out;
-    for (int c = 0; c < nsub; ++c) {
-      const long long off = (long long)c * sublen, len = std::min(sublen, n - off);
-      if (len <= 0) break;
+    long long off = 0;
+    for (int c = 0; c < nsub; off += sublens[c], ++c) {
+      const long long len = sublens[c];
       const long long npad_s = (len + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
       const double* d_params = params + (start + off) * plan->d_in;
       if (!in_dev) {
@@ -1435,14 +1497,14 @@ static int eval_impl(dlb_plan* plan, const double* params, int64_t N, double* lo
       sp.nhess = nhess; sp.hess_ij = plan->d_hess_ij; sp.comp_of = plan->d_comp_of;
       sp.gent = plan->d_gent; sp.gent_off = plan->d_gent_off; sp.chi_rows = plan->d_chi_rows; sp.nchi = plan->nchi; sp.m0_off = plan->d_m0_off; sp.comp_max = plan->comp_max;
       if (gather) {   // the finish kernel stores this sub-batch's results into every rank's window; the last launch publishes the sequence number
-        const bool last = start + CHUNK >= N && off + sublen >= n;
+        const bool last = start + CHUNK >= N && c == nsub - 1;
         DLB_TRY(gather_fill(gather, gbuf, gstart + g0, len, gtotal, ns, gsolved, last && !gdma, &sp.gather));
         if (gdma) sp.gather.xs_only = gather_rank(gather);
       }
       rc = launch_solve(sp, stream);
       if (rc) return rc;
       if (plan->timing) DLB_CUDA(cudaEventRecord(plan->ev[3], stream));
-      if (nsub > 1) { DLB_CUDA(cudaEventRecord(plan->ev_pipe[4 + c], stream)); DLB_CUDA(cudaStreamWaitEvent(s_out, plan->ev_pipe[4 + c], 0)); }
+      if (nsub > 1) { DLB_CUDA(cudaEventRecord(plan->ev_pipe[MAX_SUB + c], stream)); DLB_CUDA(cudaStreamWaitEvent(s_out, plan->ev_pipe[MAX_SUB + c], 0)); }
       if (logposterior && !lp_dev) DLB_CUDA(cudaMemcpyAsync(logposterior + g0, sp.logpost, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost, s_out));
       if (loglikelihood && !ll_dev) DLB_CUDA(cudaMemcpyAsync(loglikelihood + g0, sp.loglike, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost, s_out));
       if (logprior && !pr_dev) DLB_CUDA(cudaMemcpyAsync(logprior + g0, sp.logprior, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost, s_out));
@@ -1451,8 +1513,8 @@ static int eval_impl(dlb_plan* plan, const double* params, int64_t N, double* lo
       if (hessian && !hs_dev) DLB_CUDA(cudaMemcpyAsync(hessian + g0 * nhess, sp.hess, (size_t)len * nhess * sizeof(double), cudaMemcpyDeviceToHost, s_out));
     }
     if (nsub > 1) {   // the caller's stream (and the host) see the call complete only when the last copy-out has landed
-      DLB_CUDA(cudaEventRecord(plan->ev_pipe[9], s_out));
-      DLB_CUDA(cudaStreamWaitEvent(stream, plan->ev_pipe[9], 0));
+      DLB_CUDA(cudaEventRecord(plan->ev_pipe[2 * MAX_SUB + 1], s_out));
+      DLB_CUDA(cudaStreamWaitEvent(stream, plan->ev_pipe[2 * MAX_SUB + 1], 0));
     }
     if (any_host || plan->timing || start + CHUNK < N) DLB_CUDA(cudaStreamSynchronize(stream));
     if (plan->timing) {

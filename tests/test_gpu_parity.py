@@ -175,20 +175,24 @@ def test_posterior_hessian_and_sample_solved(gpu_required):
     assert np.max(np.abs(np.cov(draws.T) - cov) / np.sqrt(np.outer(np.diag(cov), np.diag(cov)))) < 0.1
 
 
-def test_pipelined_host_path_large_batch(gpu_required):
-    """Host buffers with N >= 131072 go through the sub-chunk pipeline (H2D | kernels | D2H on three streams): same results as the
-    one-pass device path, including a ragged last sub-chunk."""
+def test_pipelined_host_path_large_batch(gpu_required, monkeypatch):
+    """Large host buffers go through the sub-batch pipeline (H2D | kernels | D2H on three streams; sub-batch lengths rounded to the wave quantum of
+    the contraction, count from the cost model of plan.cu choose_sub_batches or forced by DLB_NSUB): same results as the one-pass device path,
+    including a ragged last sub-batch."""
     import torch
     import desilike_b200
     spec = configs.config_c5(ntracers=1, nkin=40, nbins=10, order=2, solved=True)
     plan = desilike_b200.Plan(spec)
     N = 3 * 65536 + 1234
     X = configs.sample_points(spec, N, seed=77)
-    host = plan.eval(X)
     dev = plan.eval(torch.as_tensor(X, device='cuda'))
     torch.cuda.synchronize()
-    for key in ['logposterior', 'loglikelihood', 'logprior', 'x_solved', 'status']:
-        assert np.array_equal(host[key], dev[key].cpu().numpy()), key
+    for forced in [None, '1', '2', '5', '8']:
+        if forced is None: monkeypatch.delenv('DLB_NSUB', raising=False)
+        else: monkeypatch.setenv('DLB_NSUB', forced)
+        host = plan.eval(X)
+        for key in ['logposterior', 'loglikelihood', 'logprior', 'x_solved', 'status']:
+            assert np.array_equal(host[key], dev[key].cpu().numpy()), (forced, key)
     plan.close()
 
 
