@@ -17,10 +17,11 @@ tests/test_oracle_vs_reference.py (build container; the reference does not trave
 import numpy as np
 
 from .likelihoods import resolve_terms
-from .theories import KaiserTracerPowerSpectrumMultipoles, EFTLikeKaiserTracerPowerSpectrumMultipoles
+from .theories import KaiserTracerPowerSpectrumMultipoles, EFTLikeKaiserTracerPowerSpectrumMultipoles, KaiserTracerCorrelationFunctionMultipoles
 
 _THEORIES = {'KaiserTracerPowerSpectrumMultipoles': KaiserTracerPowerSpectrumMultipoles,
-             'EFTLikeKaiserTracerPowerSpectrumMultipoles': EFTLikeKaiserTracerPowerSpectrumMultipoles}
+             'EFTLikeKaiserTracerPowerSpectrumMultipoles': EFTLikeKaiserTracerPowerSpectrumMultipoles,
+             'KaiserTracerCorrelationFunctionMultipoles': KaiserTracerCorrelationFunctionMultipoles}
 
 
 def _prior(prior):
@@ -80,20 +81,24 @@ def spec_from_likelihood(likelihood, solved_default='.marg', all_params=None):
 
         def own_varied(slots):
             return [n for n in varied if n in own and n.split('.')[-1] in slots]
-        if tname in _THEORIES and not is_xi:
+        if tname in _THEORIES and is_xi == tname.endswith('CorrelationFunctionMultipoles'):
             pt, tpl = th.pt, th.pt.template
             if type(tpl).__name__ != 'ShapeFitPowerSpectrumTemplate':
                 raise NotImplementedError('template {} is not on the CUDA path through this adapter'.format(type(tpl).__name__))
             b1 = [p for p in th.all_params if p.basename == 'b1'][0]
             # bias-combine terms from the mirror class (full_shape.py:545-550, :628-634); only k, ells, nd and the parameter names are needed
-            mirror = _THEORIES[tname](template=None, k=xin, ells=ellsin, shotnoise=1. / float(th.nd), tracer=b1.namespace or None)
+            if is_xi:   # Hankel transforms of the Kaiser tracer P_ell on kin (full_shape.py:336-365, :553-574)
+                mirror = _THEORIES[tname](template=None, s=xin, ells=ellsin, interp_order=int(th.interp_order), tracer=b1.namespace or None)
+            else:
+                mirror = _THEORIES[tname](template=None, k=xin, ells=ellsin, shotnoise=1. / float(th.nd), tracer=b1.namespace or None)
             if hasattr(th, 'kp'): mirror.kp = float(th.kp)
             terms = list(mirror.terms())
-            theory = dict(kind='kaiser', k=xin, ells=ellsin, nmu=len(pt.mu),
+            theory = dict(kind='kaiser', k=np.array(th.kin, dtype='f8') if is_xi else xin, ells=ellsin, nmu=len(pt.mu),
                           template=dict(kind='shapefit', k=np.array(tpl.k, dtype='f8'), pk_dd_fid=np.array(tpl.pk_dd_fid, dtype='f8'),
                                         pknow_dd_fid=np.array(tpl.pknow_dd_fid, dtype='f8'), f_fid=float(tpl.f_fid), a=float(tpl.a), kp=float(tpl.kp),
                                         apmode=str(tpl.apeffect.mode), eta=float(getattr(tpl, 'eta', 1. / 3.)), only_now=bool(getattr(tpl, 'only_now', False))),
                           params=own_varied(('qpar', 'qper', 'qiso', 'qap', 'dm', 'dn', 'df', 'sigmapar', 'sigmaper')), defaults=basenames)
+            if is_xi: theory.update(s=xin, kin=np.array(th.kin, dtype='f8'), interp_order=int(th.interp_order))
         elif tname in ('DampedBAOWigglesTracerPowerSpectrumMultipoles', 'DampedBAOWigglesTracerCorrelationFunctionMultipoles') and is_xi == tname.endswith('CorrelationFunctionMultipoles'):
             # damped BAO (bao.py:117-151) + power-law broadband in x / pivot (bao.py:467-476, :527-534; :849-853, :905)
             pt, tpl = th.pt, th.pt.template
@@ -109,7 +114,7 @@ def spec_from_likelihood(likelihood, solved_default='.marg', all_params=None):
                           template=dict(kind='bao', k=np.array(tpl.k, dtype='f8'), pk_dd_fid=np.array(tpl.pk_dd_fid, dtype='f8'), pknow_dd_fid=np.array(tpl.pknow_dd_fid, dtype='f8'),
                                         f_fid=float(tpl.f_fid), apmode=str(tpl.apeffect.mode), eta=float(getattr(tpl, 'eta', 1. / 3.))),
                           params=own_varied(('qpar', 'qper', 'qiso', 'qap', 'df', 'b1', 'dbeta', 'sigmas', 'sigmapar', 'sigmaper')), defaults=basenames)
-            if is_xi: theory.update(s=xin, kin=np.array(th.kin, dtype='f8') if hasattr(th, 'kin') else None)
+            if is_xi: theory.update(s=xin, kin=np.array(th.kin, dtype='f8') if hasattr(th, 'kin') else None, interp_order=int(getattr(th, 'interp_order', 1)))
             else: theory.update(k=xin)
         else:
             raise NotImplementedError('theory {} is not on the CUDA path through this adapter'.format(tname))

@@ -68,19 +68,31 @@ def fftlog_constants(kin, ells, s_out, ng=2048, kmin=1e-4, kmax=1e3, q=0., minfo
                 j0=j0, c0=c0, c1=c1, u=[uu[..., 0] + 1j * uu[..., 1] for uu in u], post=post, outj=outj, outw=outw)
 
 
-def fftlog_operator(kin, ells, s_out, **kwargs):
+def fftlog_operator(kin, ells, s_out, interp_order=1, **kwargs):
     """The whole P_ell(kin) -> xi_ell(s_out) chain of ``get_corr`` (reference desilike/theories/galaxy_clustering/base.py:127-136:
     log-k resampling + damped high-k extrapolation, FFTLog, linear interpolation onto ``s_out``) is LINEAR in P_ell(kin): returns
     the operators ``T`` [nell, nkin, ns] with ``xi_ell(s_out) = P_ell(kin) @ T[ell]``, obtained at plan time by pushing the unit
     vectors through the transform (NumPy real FFTs of 4096 points, once).  The lowering folds ``T`` into the term matrices together
     with the window and the whitening, so the per-point path is the damped-BAO kernel followed by the contraction; the explicit
-    FFTLog kernel (csrc/theory_kernels.cu:fftlog_kernel) remains available with ``theory['fftlog'] = 'kernel'``."""
+    FFTLog kernel (csrc/theory_kernels.cu:fftlog_kernel) remains available with ``theory['fftlog'] = 'kernel'``.
+
+    ``interp_order=3`` (reference base.py:53, :131): the resampling below ``kin[-1]`` is the reference's NumPy-branch ``interp1d(..., method=3)``
+    (desilike/jax.py:263-265: SciPy's not-a-knot cubic spline in log10 k with extrapolation) -- still linear in the ordinates, so only the
+    resampling rows of the operator change; the high-k extrapolation stays the 2-point rule."""
+    if interp_order not in (1, 3): raise ValueError('interp_order must be one of [1, 3]')
     fc = fftlog_constants(kin, ells, s_out, **kwargs)
     nkin, ng, npad_size = np.size(kin), fc['ng'], fc['npad_size']
     X = np.zeros((nkin, npad_size))
     idx = np.arange(ng)
     np.add.at(X, (fc['j0'], fc['pad_in_left'] + idx), fc['c0'])
     np.add.at(X, (fc['j0'] + 1, fc['pad_in_left'] + idx), fc['c1'])
+    if interp_order == 3:
+        from scipy import interpolate
+        kin = np.asarray(kin, dtype=np.float64)
+        mid = fc['k'] <= kin[-1]
+        R = interpolate.interp1d(np.log10(kin), np.eye(nkin), kind='cubic', fill_value='extrapolate', axis=0)(np.log10(fc['k'][mid]))   # [nmid, nkin]
+        pre = fc['k']**(3. - (1.5 + kwargs.get('q', 0.))) / (2. * np.pi)**1.5
+        X[:, fc['pad_in_left'] + idx[mid]] = (R * pre[mid, None]).T
     spec = np.fft.rfft(X, axis=-1)
     T = []
     for ill in range(len(ells)):

@@ -145,6 +145,36 @@ class KaiserTracerPowerSpectrumMultipoles(BaseTracerPowerSpectrumMultipoles):
                 dict(scale=1., factors=[], table='pk_tt'), dict(scale=1. / self.nd, factors=[(sn0, 1)], table=None, colvec=e0)]
 
 
+class KaiserTracerCorrelationFunctionMultipoles(KaiserTracerPowerSpectrumMultipoles):
+    """xi_ell(s) = Hankel transforms of the Kaiser tracer P_ell(k) = b1^2 pk_dd + 2 b1 pk_dt + pk_tt evaluated on ``kin`` (reference
+    full_shape.py:336-365, :553-574; get_corr base.py:46-136: resampling onto the FFTLog grid -- ``interp_order`` 1 linear / 3 cubic in log10 k --,
+    damped high-k extrapolation, FFTLog, interpolation onto s).  No stochastic parameter (reference :573)."""
+    is_correlation = True
+
+    def __init__(self, template=None, pt=None, s=None, ells=(0, 2, 4), mu=8, interp_order=1, tracer=None):
+        if pt is not None: raise NotImplementedError('emulated pt for the Kaiser correlation function is not on the CUDA path')
+        self.interp_order = {'linear': 1, 'cubic': 3}.get(interp_order, interp_order)
+        if self.interp_order not in [1, 3]: raise ValueError('interp_order must be one of {}'.format([1, 3]))
+        self.kin = np.geomspace(1e-4, 0.6, int(300. / self.interp_order + 0.5))   # reference base.py:61-67
+        super().__init__(template=template, pt=None, k=self.kin, ells=ells, mu=mu, tracer=tracer)
+        self.s = np.linspace(20., 200, 101) if s is None else np.asarray(s, dtype='f8')
+        self.params = ParameterCollection([Parameter('b1', prior=dict(limits=[0., 4.]), ref=dict(limits=[1., 2.]), namespace=self.tracer)])
+
+    def set_k(self, s, ells):
+        self.s, self.ells = np.asarray(s, dtype='f8'), tuple(ells)
+
+    @property
+    def nin(self):
+        return len(self.ells) * len(self.s)
+
+    def theory_spec(self):
+        return dict(super().theory_spec(), s=self.s, kin=self.kin, interp_order=self.interp_order)
+
+    def terms(self):
+        b1 = self._ns('b1')
+        return [dict(scale=1., factors=[(b1, 2)], table='pk_dd'), dict(scale=2., factors=[(b1, 1)], table='pk_dt'), dict(scale=1., factors=[], table='pk_tt')]
+
+
 class EFTLikeKaiserTracerPowerSpectrumMultipoles(KaiserTracerPowerSpectrumMultipoles):
     """Kaiser + EFT-like counter terms ct{ell}_{pow} * (k / kp)^pow * pk11_{ell=0} and stochastic terms sn{ell}_{pow} * (k / kp)^pow / nd
     (reference full_shape.py:577-640), exactly marginalisable (set ``derived='.marg'``)."""

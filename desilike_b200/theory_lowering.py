@@ -60,7 +60,7 @@ def kaiser_set_segments(gen, segments):
     gen.idata = np.array(header + recs, dtype=np.int32)
     gen.ddata = np.concatenate([base, derived, ratios])
     gen.nfeat = total
-    gen.tables = {seg['name']: (2 + i * ntab, nin, None) for i, seg in enumerate(segments)}
+    gen.tables = {seg['name']: (2 + i * ntab, nin, kz.get('fold')) for i, seg in enumerate(segments)}   # fold: P_ell(kin) -> xi_ell(s) operator or None
     gen.segments = list(segments)
 
 
@@ -124,7 +124,21 @@ def lower_theory(gen, theory, defaults, names=None, priors=None):
     names = gen._names
     if kind == 'kaiser':
         gen.kind = _capi.GEN_KAISER
-        k = f64(theory['k'])
+        fold = None
+        if theory.get('s') is not None:
+            # correlation function multipoles (reference full_shape.py:336-365, :553-574 through get_corr, base.py:46-136): the Kaiser tables are
+            # evaluated on kin and the (linear) resampling + FFTLog + interpolation onto s is folded into the term matrices at plan time
+            from .fftlog import fftlog_operator
+            if theory.get('fftlog', 'fold') != 'fold': raise ValueError("Kaiser correlation function multipoles: only theory['fftlog'] = 'fold'")
+            interp_order = {'linear': 1, 'cubic': 3}.get(theory.get('interp_order', 1), theory.get('interp_order', 1))   # reference base.py:53-57
+            if interp_order not in (1, 3): raise ValueError('interp_order must be one of [1, 3]')
+            k = np.geomspace(1e-4, 0.6, int(300. / interp_order + 0.5)) if theory.get('kin') is None else f64(theory['kin'])  # reference base.py:61-67
+            s_out = f64(theory['s'])
+            T = fftlog_operator(k, ells, s_out, interp_order=interp_order)
+            fold = np.zeros((len(ells) * k.size, len(ells) * s_out.size))
+            for ill in range(len(ells)): fold[ill * k.size:(ill + 1) * k.size, ill * s_out.size:(ill + 1) * s_out.size] = T[ill]
+        else:
+            k = f64(theory['k'])
         nmu = int(theory.get('nmu', 8))
         mu, wmu = legendre_weights(ells, nmu)
         k_t = f64(tpl['k'])
@@ -158,7 +172,7 @@ def lower_theory(gen, theory, defaults, names=None, priors=None):
                            base=np.concatenate([[float(tpl.get('eta', 1. / 3.)), a, float(tpl['f_fid']), 0.], k, mu, wmu.ravel(), pk, Tt, Lt,
                                                 spline_constants(np.log10(k_t)), [np.log10(k).min(), np.log10(k).max()]]),
                            derived=np.concatenate([np.log10(k), np.append(np.diff(np.log10(k_t)), 0.), _converged_pivots(spline_constants(np.log10(k_t)), nt, uniform)]),
-                           ntab=ntab, nin=nin)
+                           ntab=ntab, nin=nin, fold=fold)
         # default output segments = the four plain tables; Lowered may replace them by merged combinations (kaiser_set_segments)
         kaiser_set_segments(gen, [dict(name='pk_dd', flag=0, combs=[(0, 1., ())]), dict(name='pk_dt', flag=0, combs=[(1, 1., ())]),
                                   dict(name='pk_tt', flag=0, combs=[(2, 1., ())]), dict(name='pk11_l0', flag=1, combs=[(0, 1., ())])])
@@ -174,9 +188,10 @@ def lower_theory(gen, theory, defaults, names=None, priors=None):
         nell, nt = len(ells), k_t.size
         if xi:
             s_out = f64(theory['s'])
-            interp_order = int(theory.get('interp_order', 1))
-            if interp_order != 1:
-                raise ValueError('interp_order=3 of the P -> xi resampling is not on the CUDA path (reference default is 1)')
+            interp_order = {'linear': 1, 'cubic': 3}.get(theory.get('interp_order', 1), theory.get('interp_order', 1))   # reference base.py:53-56
+            if interp_order not in (1, 3): raise ValueError('interp_order must be one of [1, 3]')
+            if interp_order == 3 and theory.get('fftlog', 'fold') != 'fold':
+                raise ValueError("interp_order=3 of the P -> xi resampling needs theory['fftlog'] = 'fold' (the explicit FFTLog kernel resamples linearly)")
             k = np.geomspace(1e-4, 0.6, int(300. / interp_order + 0.5)) if theory.get('kin') is None else f64(theory['kin'])  # reference base.py:67
         else:
             k = f64(theory['k'])
@@ -207,7 +222,7 @@ def lower_theory(gen, theory, defaults, names=None, priors=None):
             # P_ell(kin) -> xi_ell(s) (resampling, FFTLog, interpolation onto s) is linear: fold it at plan time like the window matrix;
             # the generator is the damped-BAO kernel in P(k) mode on kin, the table 'corr' a linear map of its P_ell(kin) features
             from .fftlog import fftlog_operator
-            T = fftlog_operator(k, ells, s_out)
+            T = fftlog_operator(k, ells, s_out, interp_order=interp_order)
             ns = s_out.size
             D = np.zeros((nin, nell * ns))
             for ill in range(nell): D[ill * nk:(ill + 1) * nk, ill * ns:(ill + 1) * ns] = T[ill]

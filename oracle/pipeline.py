@@ -41,8 +41,11 @@ def theory_tables(theory, X, names):
     if kind == 'kaiser':
         tpl = theory['template']
         mu, wmu = core.legendre_weights(theory['ells'], theory['nmu'])
-        k = np.asarray(theory['k'], dtype='f8')
-        out = {name: np.empty((X.shape[0], len(theory['ells']) * k.size)) for name in ['pk_dd', 'pk_dt', 'pk_tt', 'pk11_l0']}
+        # correlation function (reference full_shape.py:336-365, :553-574): the Kaiser tables on kin, each pushed through get_corr (base.py:127-136)
+        p2c = core.PowerToCorr(theory['s'], theory['ells'], kin=theory.get('kin'), interp_order=int(theory.get('interp_order', 1))) if theory.get('s') is not None else None
+        k = np.asarray(theory['k'], dtype='f8') if p2c is None else p2c.kin
+        nx = k.size if p2c is None else len(theory['s'])
+        out = {name: np.empty((X.shape[0], len(theory['ells']) * nx)) for name in ['pk_dd', 'pk_dt', 'pk_tt', 'pk11_l0']}
         for ip in range(X.shape[0]):
             p = dict(zip(theory['params'], Xe[ip]))
             p = {**theory.get('defaults', {}), **p}
@@ -51,13 +54,14 @@ def theory_tables(theory, X, names):
             f = tpl['f_fid'] * p.get('df', 1.)
             tabs = core.kaiser_tables(k, mu, wmu, tpl['k'], pk_t, f, qpar, qper, p.get('sigmapar', 0.), p.get('sigmaper', 0.), interp=theory.get('interp', tpl.get('interp', 'scipy')))
             for name in ['pk_dd', 'pk_dt', 'pk_tt']:
-                out[name][ip] = tabs[name].ravel()
-            out['pk11_l0'][ip] = np.tile(tabs['pk_dd'][list(theory['ells']).index(0)], len(theory['ells'])) if 0 in theory['ells'] else 0.
+                out[name][ip] = (tabs[name] if p2c is None else p2c(tabs[name])).ravel()
+            if p2c is not None: out['pk11_l0'][ip] = 0.   # (not a correlation-function table)
+            else: out['pk11_l0'][ip] = np.tile(tabs['pk_dd'][list(theory['ells']).index(0)], len(theory['ells'])) if 0 in theory['ells'] else 0.
         return out
     if kind == 'bao_xi':
         tpl = theory['template']
         mu, wmu = core.legendre_weights(theory['ells'], theory['nmu'])
-        p2c = core.PowerToCorr(theory['s'], theory['ells'], interp_order=1)
+        p2c = core.PowerToCorr(theory['s'], theory['ells'], kin=theory.get('kin'), interp_order=int(theory.get('interp_order', 1)))
         out = {'corr': np.empty((X.shape[0], len(theory['ells']) * len(theory['s'])))}
         for ip in range(X.shape[0]):
             p = dict(zip(theory['params'], Xe[ip]))

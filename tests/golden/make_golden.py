@@ -107,6 +107,27 @@ def lpt_combine():
     print('lpt_combine', table.shape, power.shape)
 
 
+def kaiser_corr():
+    """Theory-level fixture: the reference's KaiserTracerCorrelationFunctionMultipoles (full_shape.py:336-365, :553-574: Hankel transforms of the Kaiser
+    tracer P_ell on kin through get_corr, base.py:46-136; FFTLog routed to oracle/fftlog.py by the cosmoprimo stub) with the linear and the cubic
+    (interp_order=3) resampling onto the FFTLog grid, on seeded points."""
+    ref_harness.setup()
+    from desilike.theories.galaxy_clustering import ShapeFitPowerSpectrumTemplate, KaiserTracerCorrelationFunctionMultipoles
+    s, ells = np.arange(20., 152., 4.), (0, 2)
+    names = ['qpar', 'qper', 'dm', 'df', 'b1']
+    rng = np.random.default_rng(117)
+    X = np.stack([rng.uniform(0.9, 1.1, 10), rng.uniform(0.9, 1.1, 10), rng.uniform(-0.1, 0.1, 10), rng.uniform(0.8, 1.2, 10), rng.uniform(1., 3., 10)], axis=-1)
+    out = {}
+    for order in (1, 3):
+        xi = KaiserTracerCorrelationFunctionMultipoles(template=ShapeFitPowerSpectrumTemplate(z=1.), s=s, ells=ells, interp_order=order)
+        out['corr{:d}'.format(order)] = np.array([xi(**dict(zip(names, x))) for x in X])
+        out['kin{:d}'.format(order)] = np.array(xi.kin)
+        out['k_template'] = np.array(xi.template.k)
+        out['a'], out['kp'] = float(xi.template.a), float(xi.template.kp)
+    np.savez_compressed(os.path.join(HERE, 'kaiser_corr.npz'), case=json.dumps(dict(kind='kaiser_corr', names=names)), X=X, s=s, **out)
+    print('kaiser_corr', out['corr1'].shape, float(np.max(np.abs(out['corr3'] - out['corr1'])) / np.max(np.abs(out['corr1']))))
+
+
 def fiber_collisions():
     """Class-level fixture: kernels of the reference's TopHatFiberCollisionsCorrelationFunctionMultipoles (window.py:1192-1249), instantiated
     with a stub theory that only carries (s, ells)."""
@@ -213,4 +234,5 @@ if __name__ == '__main__':
     xi_window()
     lpt_combine()
     bao_theory()
+    kaiser_corr()
     main()

@@ -11,7 +11,7 @@ from oracle import configs, pipeline
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURES = sorted(f for f in glob.glob(os.path.join(HERE, 'golden', '*.npz')) if 'bao_theory' not in f and 'bao_broadband' not in f and 'lpt_combine' not in f and 'xi_window' not in f and 'covariance_corrections' not in f and 'fiber_collisions' not in f and 'taylor_state' not in f)
+FIXTURES = sorted(f for f in glob.glob(os.path.join(HERE, 'golden', '*.npz')) if 'bao_theory' not in f and 'bao_broadband' not in f and 'lpt_combine' not in f and 'xi_window' not in f and 'covariance_corrections' not in f and 'fiber_collisions' not in f and 'taylor_state' not in f and 'kaiser_corr' not in f)
 
 
 def test_kaiser_tables_match_oracle(gpu_required):
@@ -336,4 +336,27 @@ def test_kaiser_window_of_knots_edge_cases(gpu_required):
     plan = desilike_b200.Plan(spec)
     theory = plan.theory(X)
     assert np.max(np.abs(theory - ref['flattheory']) / np.max(np.abs(ref['flattheory']), axis=0)) < 1e-10
+    plan.close()
+
+
+@pytest.mark.parametrize('interp_order', [1, 3])
+def test_kaiser_correlation_function_matches_reference_class(gpu_required, interp_order):
+    """KaiserTracerCorrelationFunctionMultipoles on the CUDA path (kaiser_kernel on kin + the P -> xi operator folded into the term matrices; linear
+    and cubic resampling, reference base.py:127-136): theory vectors against the reference class's own outputs (tests/golden/kaiser_corr.npz) and
+    the likelihood against the oracle on a larger seeded batch."""
+    import os
+    import desilike_b200
+    from test_host_api import make_kaiser_corr_likelihood
+    data = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'kaiser_corr.npz'))
+    like, names = make_kaiser_corr_likelihood(interp_order, data)
+    spec = like._finalize_spec(like.build_spec())
+    plan = desilike_b200.Plan(spec)
+    golden = data['corr{:d}'.format(interp_order)].reshape(len(data['X']), -1)
+    got = plan.theory(data['X'])
+    assert np.max(np.abs(got - golden)) < 1e-10 * np.max(np.abs(golden))     # relative to the largest entry of the vectors
+    rng = np.random.default_rng(31)
+    X = np.column_stack([rng.uniform(0.9, 1.1, 300), rng.uniform(0.9, 1.1, 300), rng.uniform(-0.1, 0.1, 300), rng.uniform(0.8, 1.2, 300), rng.uniform(1., 3., 300)])
+    ref, res = pipeline.evaluate(spec, X), plan.eval(X)
+    assert np.all(res['status'] == 0)
+    assert np.allclose(res['loglikelihood'], ref['loglikelihood'], rtol=1e-9, atol=1e-7)
     plan.close()

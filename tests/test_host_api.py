@@ -428,3 +428,40 @@ def test_lpt_physical_prior_basis_lowering():
         ref = pipeline.evaluate(spec, X)
         assert np.allclose(got['logposterior'], ref['logposterior'], rtol=1e-10, atol=1e-8)
         if marg: assert np.allclose(got['x_solved'], ref['x_solved'], rtol=1e-8, atol=1e-8)
+
+
+def make_kaiser_corr_likelihood(interp_order, data):
+    """Mirror-class likelihood of the tests/golden/kaiser_corr.npz case (reference KaiserTracerCorrelationFunctionMultipoles + ShapeFit template)."""
+    s, names = data['s'], json.loads(str(data['case']))['names']
+    template = dl.ShapeFitPowerSpectrumTemplate(pk_dd_fid=synthetic.pk_fid, pknow_dd_fid=synthetic.pknow_fid, f_fid=synthetic.F_FID, a=float(data['a']), kp=float(data['kp']))
+    theory = dl.KaiserTracerCorrelationFunctionMultipoles(template=template, ells=(0, 2), interp_order=interp_order)
+    obs = dl.TracerCorrelationFunctionMultipolesObservable(data=np.zeros(2 * s.size), s=[s, s], ells=(0, 2), theory=theory)
+    like = dl.ObservablesGaussianLikelihood(observables=[obs], precision=np.eye(2 * s.size) * 1e4)
+    for param in like.all_params:
+        if param.name in names: param.update(fixed=False, prior=None)
+        else: param.update(fixed=True)
+    return like, names
+
+
+@pytest.mark.parametrize('interp_order', [1, 3])
+def test_kaiser_correlation_function_fold(interp_order):
+    """KaiserTracerCorrelationFunctionMultipoles (reference full_shape.py:336-365, :553-574): Kaiser tables on kin, the P -> xi operator (linear or
+    cubic resampling, base.py:127-136) folded into the term matrices.  Lowered plan (NumPy mirror of the kernels) == oracle == the reference
+    class's own outputs (tests/golden/kaiser_corr.npz, generated by tests/golden/make_golden.py:kaiser_corr)."""
+    import lowered_numpy
+    from desilike_b200.lowering import Lowered
+    data = np.load(os.path.join(HERE, 'golden', 'kaiser_corr.npz'))
+    like, names = make_kaiser_corr_likelihood(interp_order, data)
+    spec = like._finalize_spec(like.build_spec())
+    assert spec['params'] == names
+    th = spec['observables'][0]['theory']
+    assert np.allclose(th['kin'], data['kin{:d}'.format(interp_order)], rtol=1e-14) and np.allclose(th['template']['k'], data['k_template'], rtol=1e-14)
+    X, golden = data['X'], data['corr{:d}'.format(interp_order)].reshape(len(data['X']), -1)
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    scale = np.max(np.abs(golden))
+    assert np.max(np.abs(ref['flattheory'] - golden)) < 1e-13 * scale
+    low = Lowered(spec, with_plain=True)
+    got = lowered_numpy.evaluate(low, X, feature_fn=lowered_numpy.theory_features)
+    assert np.allclose(got['loglikelihood'], ref['loglikelihood'], rtol=1e-9, atol=1e-7)
+    with pytest.raises(ValueError):
+        dl.KaiserTracerCorrelationFunctionMultipoles(template=None, interp_order=2)

@@ -9,7 +9,7 @@ import pytest
 from oracle import configs, pipeline
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURES = sorted(f for f in glob.glob(os.path.join(HERE, 'golden', '*.npz')) if 'bao_theory' not in f and 'bao_broadband' not in f and 'lpt_combine' not in f and 'xi_window' not in f and 'covariance_corrections' not in f and 'fiber_collisions' not in f and 'taylor_state' not in f)
+FIXTURES = sorted(f for f in glob.glob(os.path.join(HERE, 'golden', '*.npz')) if 'bao_theory' not in f and 'bao_broadband' not in f and 'lpt_combine' not in f and 'xi_window' not in f and 'covariance_corrections' not in f and 'fiber_collisions' not in f and 'taylor_state' not in f and 'kaiser_corr' not in f)
 
 
 def load_case(fn):
@@ -62,6 +62,25 @@ def test_bao_theory_fixture():
             else:
                 got = p2c(core.bao_damped_power(p2c.kin, mu, wmu, kt, pk_t, pknow_t, synthetic.F_FID, x[0], x[1], **kw))
             assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref)), which
+
+
+def test_kaiser_correlation_fixture():
+    """Oracle Kaiser tables on kin -> get_corr (linear and cubic resampling) against the reference's KaiserTracerCorrelationFunctionMultipoles
+    outputs (tests/golden/make_golden.py:kaiser_corr; reference full_shape.py:336-365, :553-574, base.py:127-136)."""
+    import json
+    from oracle import pipeline, synthetic
+    data = np.load(os.path.join(HERE, 'golden', 'kaiser_corr.npz'))
+    names, X, kt = json.loads(str(data['case']))['names'], data['X'], data['k_template']
+    for order in (1, 3):
+        theory = dict(kind='kaiser', s=data['s'], ells=(0, 2), nmu=8, interp_order=order, params=names[:4], defaults={},
+                      template=dict(kind='shapefit', k=kt, pk_dd_fid=synthetic.pk_fid(kt), pknow_dd_fid=synthetic.pknow_fid(kt), f_fid=synthetic.F_FID,
+                                    a=float(data['a']), kp=float(data['kp']), apmode='qparqper'))
+        tabs = pipeline.theory_tables(theory, X, names)
+        b1 = X[:, 4:5]
+        got = b1**2 * tabs['pk_dd'] + 2. * b1 * tabs['pk_dt'] + tabs['pk_tt']
+        ref = data['corr{:d}'.format(order)].reshape(len(X), -1)
+        assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref)), order
+    assert np.max(np.abs(data['corr3'] - data['corr1'])) > 1e-5 * np.max(np.abs(data['corr1']))   # the two resamplings are distinguishable
 
 
 def test_lpt_combine_fixture():

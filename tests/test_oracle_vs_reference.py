@@ -98,6 +98,33 @@ def test_spec_from_reference_bao_likelihood(which):
     Lowered(spec)
 
 
+@pytest.mark.parametrize('interp_order', [1, 3])
+def test_spec_from_reference_kaiser_correlation_likelihood(interp_order):
+    """spec_from_likelihood on the reference's KaiserTracerCorrelationFunctionMultipoles likelihood (full_shape.py:336-365, :553-574), linear and cubic
+    (interp_order=3) resampling onto the FFTLog grid: the extracted spec evaluated by the oracle == the reference's own calls, and it lowers."""
+    import desilike_b200 as dl
+    ref_harness.setup()
+    from desilike.theories.galaxy_clustering import ShapeFitPowerSpectrumTemplate, KaiserTracerCorrelationFunctionMultipoles
+    from desilike.observables.galaxy_clustering import TracerCorrelationFunctionMultipolesObservable
+    from desilike.likelihoods import ObservablesGaussianLikelihood
+    rng = np.random.default_rng(19)
+    x = np.arange(20., 152., 4.)
+    theory = KaiserTracerCorrelationFunctionMultipoles(template=ShapeFitPowerSpectrumTemplate(z=1.), ells=(0, 2), interp_order=interp_order)
+    obs = TracerCorrelationFunctionMultipolesObservable(data={'b1': 2.}, s=[x, x], ells=(0, 2), theory=theory)
+    like = ObservablesGaussianLikelihood(observables=[obs], covariance=np.diag(np.full(2 * x.size, 1e-8)))
+    names = ['qpar', 'qper', 'dm', 'df', 'b1']
+    X = np.column_stack([rng.uniform(0.97, 1.03, 6), rng.uniform(0.97, 1.03, 6), rng.uniform(-0.05, 0.05, 6), rng.uniform(0.9, 1.1, 6), rng.uniform(1.8, 2.2, 6)])
+    ref = np.array([like(dict(zip(names, xx))) for xx in X])
+    spec = dl.spec_from_likelihood(like)
+    assert spec['params'] == names and not spec['solved']
+    th = spec['observables'][0]['theory']
+    assert th['interp_order'] == interp_order and len(th['kin']) == (300 if interp_order == 1 else 100)
+    got = pipeline.evaluate(spec, X)
+    assert np.allclose(got['logposterior'], ref, rtol=1e-9, atol=1e-7), np.max(np.abs(got['logposterior'] - ref))
+    from desilike_b200.lowering import Lowered
+    Lowered(spec)
+
+
 def test_vmap_accepts_reference_likelihood_objects():
     """desilike_b200.vmap(reference_likelihood): the adapter extracts the spec and maps parameter dicts to plan columns (no GPU here: the plan
     itself is not built; the point matrix and the spec are checked)."""
