@@ -8,7 +8,7 @@ from .plan import Plan, launch_count, measure_fp64_peak, pinned_empty, sample_so
 from .lowering import Lowered, LoweringError
 
 from .parameter import Parameter, ParameterCollection, Samples
-from .theories import (ShapeFitPowerSpectrumTemplate, BAOPowerSpectrumTemplate, KaiserTracerPowerSpectrumMultipoles, KaiserTracerCorrelationFunctionMultipoles,
+from .theories import (ShapeFitPowerSpectrumTemplate, BAOPowerSpectrumTemplate, KaiserTracerPowerSpectrumMultipoles, KaiserTracerCorrelationFunctionMultipoles, EFTLikeKaiserTracerCorrelationFunctionMultipoles,
                        EFTLikeKaiserTracerPowerSpectrumMultipoles, LPTVelocileptorsTracerPowerSpectrumMultipoles, TableBiasTracerPowerSpectrumMultipoles, DampedBAOWigglesTracerPowerSpectrumMultipoles,
                        DampedBAOWigglesTracerCorrelationFunctionMultipoles)
 from .emulators import Emulator, EmulatedCalculator
@@ -19,7 +19,7 @@ from .samplers import EnsembleSampler
 from .adapters import spec_from_likelihood
 
 __all__ = ['Parameter', 'ParameterCollection', 'Samples', 'ShapeFitPowerSpectrumTemplate', 'BAOPowerSpectrumTemplate',
-           'KaiserTracerPowerSpectrumMultipoles', 'KaiserTracerCorrelationFunctionMultipoles', 'EFTLikeKaiserTracerPowerSpectrumMultipoles', 'LPTVelocileptorsTracerPowerSpectrumMultipoles', 'TableBiasTracerPowerSpectrumMultipoles', 'DampedBAOWigglesTracerPowerSpectrumMultipoles',
+           'KaiserTracerPowerSpectrumMultipoles', 'KaiserTracerCorrelationFunctionMultipoles', 'EFTLikeKaiserTracerCorrelationFunctionMultipoles', 'EFTLikeKaiserTracerPowerSpectrumMultipoles', 'LPTVelocileptorsTracerPowerSpectrumMultipoles', 'TableBiasTracerPowerSpectrumMultipoles', 'DampedBAOWigglesTracerPowerSpectrumMultipoles',
            'DampedBAOWigglesTracerCorrelationFunctionMultipoles', 'Emulator', 'EmulatedCalculator', 'TracerPowerSpectrumMultipolesObservable',
            'TracerCorrelationFunctionMultipolesObservable', 'ObservablesGaussianLikelihood', 'SumLikelihood', 'PipelineError', 'vmap', 'status_to_errors', 'EnsembleSampler', 'spec_from_likelihood',
            'Plan', 'sample_solved', 'Lowered', 'LoweringError', 'DesilikeB200Error', 'load_library', 'launch_count', 'measure_fp64_peak', 'pinned_empty']

@@ -17,11 +17,13 @@ tests/test_oracle_vs_reference.py (build container; the reference does not trave
 import numpy as np
 
 from .likelihoods import resolve_terms
-from .theories import KaiserTracerPowerSpectrumMultipoles, EFTLikeKaiserTracerPowerSpectrumMultipoles, KaiserTracerCorrelationFunctionMultipoles
+from .theories import (KaiserTracerPowerSpectrumMultipoles, EFTLikeKaiserTracerPowerSpectrumMultipoles, KaiserTracerCorrelationFunctionMultipoles,
+                       EFTLikeKaiserTracerCorrelationFunctionMultipoles)
 
 _THEORIES = {'KaiserTracerPowerSpectrumMultipoles': KaiserTracerPowerSpectrumMultipoles,
              'EFTLikeKaiserTracerPowerSpectrumMultipoles': EFTLikeKaiserTracerPowerSpectrumMultipoles,
-             'KaiserTracerCorrelationFunctionMultipoles': KaiserTracerCorrelationFunctionMultipoles}
+             'KaiserTracerCorrelationFunctionMultipoles': KaiserTracerCorrelationFunctionMultipoles,
+             'EFTLikeKaiserTracerCorrelationFunctionMultipoles': EFTLikeKaiserTracerCorrelationFunctionMultipoles}
 
 
 def _prior(prior):
@@ -92,6 +94,7 @@ def spec_from_likelihood(likelihood, solved_default='.marg', all_params=None):
             else:
                 mirror = _THEORIES[tname](template=None, k=xin, ells=ellsin, shotnoise=1. / float(th.nd), tracer=b1.namespace or None)
             if hasattr(th, 'kp'): mirror.kp = float(th.kp)
+            elif hasattr(getattr(th, 'power', None), 'kp'): mirror.kp = float(th.power.kp)   # correlation function: the EFT-like pivot lives on its power spectrum
             terms = list(mirror.terms())
             theory = dict(kind='kaiser', k=np.array(th.kin, dtype='f8') if is_xi else xin, ells=ellsin, nmu=len(pt.mu),
                           template=dict(kind='shapefit', k=np.array(tpl.k, dtype='f8'), pk_dd_fid=np.array(tpl.pk_dd_fid, dtype='f8'),

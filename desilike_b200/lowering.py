@@ -92,7 +92,7 @@ def _merge_kaiser_terms(observables, names):
             segs.append(seg)
             return len(segs) - 1
 
-        merge = [t for t in obs['terms'] if t.get('table') in plain and t.get('solved') is None and t.get('colvec') is None and t.get('outvec') is None]
+        merge = [t for t in obs['terms'] if t.get('table') in plain and t.get('solved') is None and t.get('colvec') is None and t.get('featvec') is None and t.get('outvec') is None]
         terms = []
         if len(merge) >= 2:
             combs = tuple(sorted((KAISER_TABLE_ID[t['table']], float(t.get('scale', 1.)), tuple(sorted((names.index(n), int(p)) for n, p in t.get('factors', []))))
@@ -375,14 +375,20 @@ class Lowered(object):
                     scale = float(term.get('scale', 1.))
                     factors = list(term.get('factors', []))
                     colvec = f64(term['colvec']) if term.get('colvec') is not None else None
+                    # featvec: weights in the FEATURE space of the table, applied before its fold matrix (counter terms (k / kp)^pow pk11 of a
+                    # correlation-function theory: the weight acts on P(kin), the P -> xi operator comes after); colvec acts on the theory vector
+                    featvec = f64(term['featvec']) if term.get('featvec') is not None else None
                     sname = term.get('solved')
                     if term.get('table') is not None:
                         foff, K, D = gen.tables[term['table']]
+                        if featvec is not None and featvec.shape != (K,): raise LoweringError('featvec must have the length of its table ({:d})'.format(K))
                         if D is None:   # identity features: the table itself is the feature sub-segment
                             cv = np.ones(nin) if colvec is None else colvec
+                            if featvec is not None: cv = cv * featvec
                             mat = scale * (cv[:, None] * (W.T if W is not None else np.eye(nin)))
                         else:
-                            Dc = D if colvec is None else D * colvec
+                            Dc = D if featvec is None else featvec[:, None] * D
+                            if colvec is not None: Dc = Dc * colvec
                             mat = scale * (Dc @ W.T if W is not None else Dc)
                         theta_dep = True
                     else:

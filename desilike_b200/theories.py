@@ -210,6 +210,31 @@ class EFTLikeKaiserTracerPowerSpectrumMultipoles(KaiserTracerPowerSpectrumMultip
         return terms
 
 
+class EFTLikeKaiserTracerCorrelationFunctionMultipoles(KaiserTracerCorrelationFunctionMultipoles):
+    """Hankel transforms of the EFT-like Kaiser tracer P_ell(k): Kaiser + counter terms ct{ell}_{pow} (k / kp)^pow pk11_{ell=0} on ``kin`` (reference
+    full_shape.py:577-634, :664-684; no stochastic parameters, :683).  The counter terms stay linear after the P -> xi operator, so they can be
+    analytically marginalised (``derived='.marg'``): their templates are feature-space weights applied before the folded operator (``featvec``)."""
+    kp = 1.
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        for ell in (0, 2, 4):
+            self.params.set(Parameter('ct{:d}_2'.format(ell), value=0., prior=dict(dist='norm', loc=0., scale=100.), namespace=self.tracer))
+
+    def terms(self):
+        terms = super().terms()
+        nk = len(self.kin)
+        for p in self.params:
+            match = re.match(r'ct(\d+)_(-?\d+)$', p.basename)
+            if not match: continue
+            ell, power = int(match.group(1)), int(match.group(2))
+            if ell not in self.ells: continue
+            featvec = np.zeros((len(self.ells), nk))
+            featvec[self.ells.index(ell)] = (self.kin / self.kp)**power
+            terms.append(dict(scale=1., factors=[(p.name, 1)], table='pk11_l0', featvec=featvec.ravel()))
+        return terms
+
+
 class TableBiasTracerPowerSpectrumMultipoles(BaseTracerPowerSpectrumMultipoles):
     """Generic table model ``P_ell(k) = interp1d(k, pt.k, sum_i table[ell, :, i] * m_i(bias))`` behind a Taylor emulator of ``table`` [nell, nk_pt, nm]:
     the structure shared by the reference's perturbation-theory tracers (``combine_bias_terms_poles``, reference full_shape.py:1168, :1214, :1479,

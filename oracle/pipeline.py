@@ -53,10 +53,12 @@ def theory_tables(theory, X, names):
             pk_t = tpl['pk_dd_fid'] * core.shapefit_factor(tpl['k'], p.get('dm', 0.), p.get('dn', 0.), tpl['a'], tpl['kp'])
             f = tpl['f_fid'] * p.get('df', 1.)
             tabs = core.kaiser_tables(k, mu, wmu, tpl['k'], pk_t, f, qpar, qper, p.get('sigmapar', 0.), p.get('sigmaper', 0.), interp=theory.get('interp', tpl.get('interp', 'scipy')))
-            for name in ['pk_dd', 'pk_dt', 'pk_tt']:
-                out[name][ip] = (tabs[name] if p2c is None else p2c(tabs[name])).ravel()
-            if p2c is not None: out['pk11_l0'][ip] = 0.   # (not a correlation-function table)
-            else: out['pk11_l0'][ip] = np.tile(tabs['pk_dd'][list(theory['ells']).index(0)], len(theory['ells'])) if 0 in theory['ells'] else 0.
+            pk11 = np.tile(tabs['pk_dd'][list(theory['ells']).index(0)], (len(theory['ells']), 1)) if 0 in theory['ells'] else 0. * tabs['pk_dd']
+            for name, tab in [('pk_dd', tabs['pk_dd']), ('pk_dt', tabs['pk_dt']), ('pk_tt', tabs['pk_tt']), ('pk11_l0', pk11)]:
+                out[name][ip] = (tab if p2c is None else p2c(tab)).ravel()
+                if p2c is not None:   # the P(kin)-space tables too: terms with feature-space weights ('featvec') transform weight x table
+                    out.setdefault(name + '@kin', np.empty((X.shape[0], tab.size)))[ip] = tab.ravel()
+        if p2c is not None: out['@p2c'] = p2c
         return out
     if kind == 'bao_xi':
         tpl = theory['template']
@@ -106,6 +108,9 @@ def observable_flat(obs, X, names, xvalues, tables=None, only_solved=None):
             out = out + c[:, None] * np.asarray(term['outvec'], dtype='f8')
             continue
         vec = tables[term['table']] if term.get('table') is not None else 1.
+        if term.get('featvec') is not None:   # weights on P_ell(kin) BEFORE get_corr (EFT-like counter terms of a correlation-function theory)
+            p2c, raw = tables['@p2c'], tables[term['table'] + '@kin'] * np.asarray(term['featvec'], dtype='f8')
+            vec = np.array([p2c(r.reshape(len(p2c.ells), -1)).ravel() for r in raw])
         if term.get('colvec') is not None:
             vec = vec * term['colvec']
         P = P + c[:, None] * vec

@@ -124,6 +124,13 @@ def kaiser_corr():
         out['kin{:d}'.format(order)] = np.array(xi.kin)
         out['k_template'] = np.array(xi.template.k)
         out['a'], out['kp'] = float(xi.template.a), float(xi.template.kp)
+    # EFT-like class (full_shape.py:577-634, :664-684): counter terms ct{ell}_2 (k / kp)^2 pk11_{ell=0} on kin, transformed with the rest
+    from desilike.theories.galaxy_clustering import EFTLikeKaiserTracerCorrelationFunctionMultipoles
+    ct = rng.uniform(-20., 20., (X.shape[0], 2))
+    for order in (1, 3):
+        xi = EFTLikeKaiserTracerCorrelationFunctionMultipoles(template=ShapeFitPowerSpectrumTemplate(z=1.), s=s, ells=ells, interp_order=order)
+        out['corr_eft{:d}'.format(order)] = np.array([xi(**dict(zip(names + ['ct0_2', 'ct2_2'], np.append(x, c)))) for x, c in zip(X, ct)])
+    out['ct'] = ct
     np.savez_compressed(os.path.join(HERE, 'kaiser_corr.npz'), case=json.dumps(dict(kind='kaiser_corr', names=names)), X=X, s=s, **out)
     print('kaiser_corr', out['corr1'].shape, float(np.max(np.abs(out['corr3'] - out['corr1'])) / np.max(np.abs(out['corr1']))))
 

@@ -430,15 +430,20 @@ def test_lpt_physical_prior_basis_lowering():
         if marg: assert np.allclose(got['x_solved'], ref['x_solved'], rtol=1e-8, atol=1e-8)
 
 
-def make_kaiser_corr_likelihood(interp_order, data):
-    """Mirror-class likelihood of the tests/golden/kaiser_corr.npz case (reference KaiserTracerCorrelationFunctionMultipoles + ShapeFit template)."""
+def make_kaiser_corr_likelihood(interp_order, data, eftlike=None):
+    """Mirror-class likelihood of the tests/golden/kaiser_corr.npz case (reference KaiserTracerCorrelationFunctionMultipoles + ShapeFit template).
+    ``eftlike``: 'sampled' / 'marg' -> EFTLikeKaiserTracerCorrelationFunctionMultipoles with ct0_2, ct2_2 sampled / analytically marginalised."""
     s, names = data['s'], json.loads(str(data['case']))['names']
     template = dl.ShapeFitPowerSpectrumTemplate(pk_dd_fid=synthetic.pk_fid, pknow_dd_fid=synthetic.pknow_fid, f_fid=synthetic.F_FID, a=float(data['a']), kp=float(data['kp']))
-    theory = dl.KaiserTracerCorrelationFunctionMultipoles(template=template, ells=(0, 2), interp_order=interp_order)
-    obs = dl.TracerCorrelationFunctionMultipolesObservable(data=np.zeros(2 * s.size), s=[s, s], ells=(0, 2), theory=theory)
+    cls = dl.EFTLikeKaiserTracerCorrelationFunctionMultipoles if eftlike else dl.KaiserTracerCorrelationFunctionMultipoles
+    theory = cls(template=template, ells=(0, 2), interp_order=interp_order)
+    rng = np.random.default_rng(5)
+    obs = dl.TracerCorrelationFunctionMultipolesObservable(data=rng.normal(0., 0.05, 2 * s.size) if eftlike == 'marg' else np.zeros(2 * s.size), s=[s, s], ells=(0, 2), theory=theory)
     like = dl.ObservablesGaussianLikelihood(observables=[obs], precision=np.eye(2 * s.size) * 1e4)
+    if eftlike == 'sampled': names = names + ['ct0_2', 'ct2_2']
     for param in like.all_params:
         if param.name in names: param.update(fixed=False, prior=None)
+        elif eftlike == 'marg' and param.name in ('ct0_2', 'ct2_2'): param.update(fixed=False, derived='.marg', prior=dict(dist='norm', loc=0., scale=50.))
         else: param.update(fixed=True)
     return like, names
 
@@ -465,3 +470,28 @@ def test_kaiser_correlation_function_fold(interp_order):
     assert np.allclose(got['loglikelihood'], ref['loglikelihood'], rtol=1e-9, atol=1e-7)
     with pytest.raises(ValueError):
         dl.KaiserTracerCorrelationFunctionMultipoles(template=None, interp_order=2)
+
+
+@pytest.mark.parametrize('interp_order', [1, 3])
+def test_eftlike_kaiser_correlation_function_fold(interp_order):
+    """EFTLikeKaiserTracerCorrelationFunctionMultipoles (reference full_shape.py:577-634, :664-684): the counter terms ct{ell}_2 (k / kp)^2 pk11_{ell=0}
+    weight P(kin) BEFORE the folded P -> xi operator (term key ``featvec``).  Sampled: lowered plan == oracle == the reference class's outputs
+    (tests/golden/kaiser_corr.npz: corr_eft*); analytically marginalised: lowered plan == oracle (x_solved too)."""
+    import lowered_numpy
+    from desilike_b200.lowering import Lowered
+    data = np.load(os.path.join(HERE, 'golden', 'kaiser_corr.npz'))
+    like, names = make_kaiser_corr_likelihood(interp_order, data, eftlike='sampled')
+    spec = like._finalize_spec(like.build_spec())
+    assert spec['params'] == names and names[-2:] == ['ct0_2', 'ct2_2']
+    X, golden = np.column_stack([data['X'], data['ct']]), data['corr_eft{:d}'.format(interp_order)].reshape(len(data['X']), -1)
+    ref = pipeline.evaluate(spec, X, return_theory=True)
+    assert np.max(np.abs(ref['flattheory'] - golden)) < 1e-13 * np.max(np.abs(golden))
+    got = lowered_numpy.evaluate(Lowered(spec, with_plain=True), X, feature_fn=lowered_numpy.theory_features)
+    assert np.allclose(got['loglikelihood'], ref['loglikelihood'], rtol=1e-9, atol=1e-7)
+    like, names = make_kaiser_corr_likelihood(interp_order, data, eftlike='marg')
+    spec = like._finalize_spec(like.build_spec())
+    assert [s_['name'] for s_ in spec['solved']] == ['ct0_2', 'ct2_2']
+    ref = pipeline.evaluate(spec, data['X'])
+    got = lowered_numpy.evaluate(Lowered(spec), data['X'], feature_fn=lowered_numpy.theory_features)
+    assert np.allclose(got['logposterior'], ref['logposterior'], rtol=1e-9, atol=1e-7)
+    assert np.allclose(got['x_solved'], ref['x_solved'], rtol=1e-7, atol=1e-9)

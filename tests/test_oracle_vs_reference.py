@@ -125,6 +125,34 @@ def test_spec_from_reference_kaiser_correlation_likelihood(interp_order):
     Lowered(spec)
 
 
+@pytest.mark.parametrize('interp_order', [1, 3])
+def test_spec_from_reference_eftlike_kaiser_correlation_likelihood(interp_order):
+    """spec_from_likelihood on the reference's EFTLikeKaiserTracerCorrelationFunctionMultipoles likelihood (full_shape.py:577-634, :664-684) with the
+    counter terms analytically marginalised: oracle on the extracted spec == the reference's own calls."""
+    import desilike_b200 as dl
+    ref_harness.setup()
+    from desilike.theories.galaxy_clustering import ShapeFitPowerSpectrumTemplate, EFTLikeKaiserTracerCorrelationFunctionMultipoles
+    from desilike.observables.galaxy_clustering import TracerCorrelationFunctionMultipolesObservable
+    from desilike.likelihoods import ObservablesGaussianLikelihood
+    rng = np.random.default_rng(23)
+    x = np.arange(20., 152., 4.)
+    theory = EFTLikeKaiserTracerCorrelationFunctionMultipoles(template=ShapeFitPowerSpectrumTemplate(z=1.), ells=(0, 2), interp_order=interp_order)
+    obs = TracerCorrelationFunctionMultipolesObservable(data={'b1': 2., 'ct0_2': 3., 'ct2_2': -2.}, s=[x, x], ells=(0, 2), theory=theory)
+    like = ObservablesGaussianLikelihood(observables=[obs], covariance=np.diag(np.full(2 * x.size, 1e-8)))
+    for p in like.all_params:
+        if p.basename.startswith('ct'): p.update(fixed=False, derived='.marg', prior=dict(dist='norm', loc=0., scale=50.))
+    ref_harness.install_jacfwd_stub()
+    names = ['qpar', 'qper', 'dm', 'df', 'b1']
+    X = np.column_stack([rng.uniform(0.97, 1.03, 5), rng.uniform(0.97, 1.03, 5), rng.uniform(-0.05, 0.05, 5), rng.uniform(0.9, 1.1, 5), rng.uniform(1.8, 2.2, 5)])
+    ref = np.array([like(dict(zip(names, xx))) for xx in X])
+    spec = dl.spec_from_likelihood(like)
+    assert spec['params'] == names and [s_['name'] for s_ in spec['solved']] == ['ct0_2', 'ct2_2']
+    got = pipeline.evaluate(spec, X)
+    assert np.allclose(got['logposterior'], ref, rtol=1e-9, atol=1e-6), np.max(np.abs(got['logposterior'] - ref))
+    from desilike_b200.lowering import Lowered
+    Lowered(spec)
+
+
 def test_vmap_accepts_reference_likelihood_objects():
     """desilike_b200.vmap(reference_likelihood): the adapter extracts the spec and maps parameter dicts to plan columns (no GPU here: the plan
     itself is not built; the point matrix and the spec are checked)."""
