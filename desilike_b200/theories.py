@@ -152,13 +152,27 @@ class KaiserTracerCorrelationFunctionMultipoles(KaiserTracerPowerSpectrumMultipo
     is_correlation = True
 
     def __init__(self, template=None, pt=None, s=None, ells=(0, 2, 4), mu=8, interp_order=1, tracer=None):
-        if pt is not None: raise NotImplementedError('emulated pt for the Kaiser correlation function is not on the CUDA path')
         self.interp_order = {'linear': 1, 'cubic': 3}.get(interp_order, interp_order)
         if self.interp_order not in [1, 3]: raise ValueError('interp_order must be one of {}'.format([1, 3]))
         self.kin = np.geomspace(1e-4, 0.6, int(300. / self.interp_order + 0.5))   # reference base.py:61-67
-        super().__init__(template=template, pt=None, k=self.kin, ells=ells, mu=mu, tracer=tracer)
+        # pt: an EmulatedCalculator of the Kaiser perturbation-theory tables ON kin (what the reference emulates as ``theory.pt``, e.g.
+        # ``Emulator.fit_taylor(KaiserTracerPowerSpectrumMultipoles(template, k=xi.kin, ells=ells))``)
+        super().__init__(template=template, pt=pt, k=self.kin, ells=ells, mu=mu, tracer=tracer)
         self.s = np.linspace(20., 200, 101) if s is None else np.asarray(s, dtype='f8')
         self.params = ParameterCollection([Parameter('b1', prior=dict(limits=[0., 4.]), ref=dict(limits=[1., 2.]), namespace=self.tracer)])
+
+    def _fold(self):
+        """[nell * nkin, nell * ns]: the linear P_ell(kin) -> xi_ell(s) operator of get_corr (reference base.py:127-136), block diagonal in ell."""
+        from .fftlog import fftlog_operator
+        T = fftlog_operator(self.kin, self.ells, self.s, interp_order=self.interp_order)
+        nk, ns = self.kin.size, self.s.size
+        fold = np.zeros((len(self.ells) * nk, len(self.ells) * ns))
+        for ill in range(len(self.ells)): fold[ill * nk:(ill + 1) * nk, ill * ns:(ill + 1) * ns] = T[ill]
+        return fold
+
+    def _weighted_tables(self):
+        """Tables entering with weights on P(kin): {new table name: (source table, weights [nell * nkin])} (counter terms of the EFT-like class)."""
+        return {}
 
     def set_k(self, s, ells):
         self.s, self.ells = np.asarray(s, dtype='f8'), tuple(ells)
@@ -168,7 +182,24 @@ class KaiserTracerCorrelationFunctionMultipoles(KaiserTracerPowerSpectrumMultipo
         return len(self.ells) * len(self.s)
 
     def theory_spec(self):
-        return dict(super().theory_spec(), s=self.s, kin=self.kin, interp_order=self.interp_order)
+        if self.pt is None:
+            return dict(super().theory_spec(), s=self.s, kin=self.kin, interp_order=self.interp_order)
+        # emulated tables on (kin, ells): fold the P -> xi operator into the emulator's output maps (Taylor: coefficient matrices; MLP: linear post-map)
+        spec = self.pt.theory_spec(self)
+        fold, tables = self._fold(), {}
+        weighted = self._weighted_tables()
+        if spec['kind'] == 'taylor':
+            for name, deriv in spec['tables'].items(): tables[name] = np.asarray(deriv, dtype='f8') @ fold
+            for name, (src, w) in weighted.items(): tables[name] = (np.asarray(spec['tables'][src], dtype='f8') * w) @ fold
+        else:
+            def post(sl, w=None):   # MLP tables: output indices, optionally with a linear post-map [len(indices), nell * nkin]
+                sl, m = sl if isinstance(sl, tuple) else (sl, None)
+                if m is None: return (sl, fold if w is None else w[:, None] * fold)
+                m = np.asarray(m, dtype='f8')
+                return (sl, (m if w is None else m * w) @ fold)
+            for name, sl in spec['tables'].items(): tables[name] = post(sl)
+            for name, (src, w) in weighted.items(): tables[name] = post(spec['tables'][src], w)
+        return dict(spec, tables=tables)
 
     def terms(self):
         b1 = self._ns('b1')
@@ -221,9 +252,9 @@ class EFTLikeKaiserTracerCorrelationFunctionMultipoles(KaiserTracerCorrelationFu
         for ell in (0, 2, 4):
             self.params.set(Parameter('ct{:d}_2'.format(ell), value=0., prior=dict(dist='norm', loc=0., scale=100.), namespace=self.tracer))
 
-    def terms(self):
-        terms = super().terms()
-        nk = len(self.kin)
+    def _counter_terms(self):
+        """[(parameter name, weights on pk11_{ell=0}(kin) [nell * nkin])] (reference full_shape.py:588-618: (k / kp)^pow on the ell block)."""
+        out, nk = [], len(self.kin)
         for p in self.params:
             match = re.match(r'ct(\d+)_(-?\d+)$', p.basename)
             if not match: continue
@@ -231,7 +262,17 @@ class EFTLikeKaiserTracerCorrelationFunctionMultipoles(KaiserTracerCorrelationFu
             if ell not in self.ells: continue
             featvec = np.zeros((len(self.ells), nk))
             featvec[self.ells.index(ell)] = (self.kin / self.kp)**power
-            terms.append(dict(scale=1., factors=[(p.name, 1)], table='pk11_l0', featvec=featvec.ravel()))
+            out.append((p.name, featvec.ravel()))
+        return out
+
+    def _weighted_tables(self):
+        return {'pk11_l0@' + name: ('pk11_l0', w) for name, w in self._counter_terms()}
+
+    def terms(self):
+        terms = super().terms()
+        for name, w in self._counter_terms():
+            if self.pt is None: terms.append(dict(scale=1., factors=[(name, 1)], table='pk11_l0', featvec=w))
+            else: terms.append(dict(scale=1., factors=[(name, 1)], table='pk11_l0@' + name))   # weights folded into the emulator's output map
         return terms
 
 

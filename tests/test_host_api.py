@@ -495,3 +495,48 @@ def test_eftlike_kaiser_correlation_function_fold(interp_order):
     got = lowered_numpy.evaluate(Lowered(spec), data['X'], feature_fn=lowered_numpy.theory_features)
     assert np.allclose(got['logposterior'], ref['logposterior'], rtol=1e-9, atol=1e-7)
     assert np.allclose(got['x_solved'], ref['x_solved'], rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize('eftlike', [False, True])
+def test_kaiser_correlation_function_with_emulated_pt(eftlike):
+    """``KaiserTracerCorrelationFunctionMultipoles(pt=EmulatedCalculator)`` (and the EFT-like class): the reference emulates ``theory.pt`` = the Kaiser
+    tables on kin (full_shape.py:341-346); here the P -> xi operator (and the counter-term weights on P(kin)) are folded into the Taylor coefficient
+    matrices.  A Taylor emulator of the ORACLE's Kaiser tables on kin: at the expansion point the emulated xi equals the oracle's direct xi (tables
+    through oracle get_corr -- independent of the product's operator) to round-off, nearby to the truncation error; the lowered plan (NumPy mirror)
+    equals the oracle on the emulated spec."""
+    import lowered_numpy
+    from oracle import core
+    from desilike_b200.lowering import Lowered
+    data = np.load(os.path.join(HERE, 'golden', 'kaiser_corr.npz'))
+    like, names = make_kaiser_corr_likelihood(1, data, eftlike='sampled' if eftlike else None)
+    direct = like._finalize_spec(like.build_spec())
+    th = direct['observables'][0]['theory']
+    pnames = ['qpar', 'qper', 'dm', 'df']
+    center, delta = np.array([1., 1., 0., 1.]), np.array([0.01, 0.01, 0.01, 0.02])
+    ptheory = {k: v for k, v in th.items() if k not in ('s', 'kin', 'interp_order')}   # the P(k) theory on kin
+    ptheory['params'] = pnames
+
+    def func(P):
+        tabs = pipeline.theory_tables(ptheory, P, pnames)
+        return np.concatenate([tabs[n] for n in ('pk_dd', 'pk_dt', 'pk_tt')], axis=-1)
+    powers, derivs = core.taylor_fit_polynomial(func, center, 4, 2, delta)
+    nin = 2 * th['kin'].size
+    tables = {n: derivs[:, i * nin:(i + 1) * nin].reshape(-1, 2, th['kin'].size) for i, n in enumerate(('pk_dd', 'pk_dt', 'pk_tt'))}
+    pt = dl.Emulator.from_taylor(pnames, center, powers, tables, fixed=dict(k=th['kin'], ells=(0, 2), z=1.)).to_calculator()
+    cls = dl.EFTLikeKaiserTracerCorrelationFunctionMultipoles if eftlike else dl.KaiserTracerCorrelationFunctionMultipoles
+    obs = dl.TracerCorrelationFunctionMultipolesObservable(data=np.zeros(2 * data['s'].size), s=[data['s']] * 2, ells=(0, 2), theory=cls(pt=pt, ells=(0, 2)))
+    elike = dl.ObservablesGaussianLikelihood(observables=[obs], precision=np.eye(2 * data['s'].size) * 1e4)
+    for param in elike.all_params:
+        param.update(fixed=param.name not in names, **({} if param.name not in names else dict(prior=None)))
+    spec = elike._finalize_spec(elike.build_spec())
+    assert spec['params'] == names and spec['observables'][0]['theory']['kind'] == 'taylor'
+    extra = [5., -3.] if eftlike else []
+    X0 = np.array([list(center) + [1.8] + extra])
+    a, b = pipeline.evaluate(spec, X0, return_theory=True)['flattheory'], pipeline.evaluate(direct, X0, return_theory=True)['flattheory']
+    assert np.max(np.abs(a - b)) < 1e-11 * np.max(np.abs(b))
+    rng = np.random.default_rng(3)
+    X = X0 + rng.uniform(-1., 1., (6, X0.shape[1])) * np.array(list(0.3 * delta) + [0.5] + [3.] * len(extra))
+    a, b = pipeline.evaluate(spec, X, return_theory=True), pipeline.evaluate(direct, X, return_theory=True)
+    assert np.max(np.abs(a['flattheory'] - b['flattheory'])) < 1e-4 * np.max(np.abs(b['flattheory']))   # truncation error of the order-2 expansion
+    got = lowered_numpy.evaluate(Lowered(spec), X)
+    assert np.allclose(got['loglikelihood'], a['loglikelihood'], rtol=1e-9, atol=1e-7)
