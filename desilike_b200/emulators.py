@@ -106,6 +106,10 @@ class Emulator(object):
         from .plan import Plan
         tspec = dict(theory.theory_spec(), params=list(names))
         kind = tspec['kind']
+        if kind == 'kaiser' and tspec.get('s') is not None:
+            # correlation-function Kaiser theories: what is emulated is ``theory.pt`` = the P(k) tables on kin (reference full_shape.py:341-346); the
+            # P -> xi operator is folded into the emulator's output maps by the tracer class (theories.KaiserTracerCorrelationFunctionMultipoles)
+            tspec = {key: value for key, value in tspec.items() if key not in ('s', 'kin', 'interp_order')}
         if kind == 'kaiser':
             tables, x, cls_ = ['pk_dd', 'pk_dt', 'pk_tt'], np.asarray(theory.k, dtype='f8'), ('desilike.theories.galaxy_clustering.full_shape', 'KaiserPowerSpectrumMultipoles')
         elif kind == 'bao_pk':

@@ -412,3 +412,27 @@ def test_workload_generators_product_side(gpu_required):
             "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), [m for m in sys.modules if m.startswith('oracle')]; print(len(spec['params']))")
     res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd=ROOT, timeout=300)
     assert res.returncode == 0, res.stderr[-2000:]
+
+
+def test_fit_taylor_kaiser_correlation_function(gpu_required):
+    """``Emulator.fit_taylor`` of a Kaiser CORRELATION-FUNCTION theory emulates its ``pt`` = the P(k) tables on kin (reference full_shape.py:341-346);
+    ``KaiserTracerCorrelationFunctionMultipoles(pt=...)`` folds the P -> xi operator into the Taylor coefficient matrices: the emulated likelihood
+    reproduces the direct one at the expansion centre and within the truncation error around it."""
+    template = dl.ShapeFitPowerSpectrumTemplate(pk_dd_fid=synthetic.pk_fid, pknow_dd_fid=synthetic.pknow_fid, f_fid=synthetic.F_FID)
+    s, ells = np.arange(20., 152., 4.), (0, 2)
+    direct = dl.KaiserTracerCorrelationFunctionMultipoles(template=template, s=s, ells=ells)
+    emu = dl.Emulator.fit_taylor(direct, order=2, delta=[0.01, 0.01, 0.01, 0.02])
+    assert emu.state['engines']['pk_dd']['yshape'] == (2, 300) and np.allclose(emu.state['fixed']['k'], direct.kin)
+    emulated = dl.KaiserTracerCorrelationFunctionMultipoles(pt=emu.to_calculator(), s=s, ells=ells)
+
+    def likelihood(theory):
+        observable = dl.TracerCorrelationFunctionMultipolesObservable(data={'b1': 2.}, s=[s] * 2, ells=ells, theory=theory, covariance=np.eye(2 * s.size) * 1e-6)
+        return dl.ObservablesGaussianLikelihood([observable])
+
+    like_d, like_e = likelihood(direct), likelihood(emulated)
+    like_d(b1=2.); like_e(b1=2.)
+    scale = np.max(np.abs(like_d.flattheory))
+    assert np.max(np.abs(like_e.flattheory - like_d.flattheory)) < 1e-9 * scale          # at the centre
+    like_d(b1=1.7, qpar=1.004, dm=-0.003); like_e(b1=1.7, qpar=1.004, dm=-0.003)
+    diff = np.max(np.abs(like_e.flattheory - like_d.flattheory))
+    assert 0. < diff < 1e-4 * scale                                                        # truncation error of the order-2 expansion
