@@ -8,8 +8,8 @@ lowers (lowering.py).  Nothing of the reference is imported here: the objects ar
 module works on whatever desilike installation the caller has.
 
 Supported (everything else fails loudly): ``ObservablesGaussianLikelihood`` over ``TracerPowerSpectrumMultipolesObservable``s whose theory is
-``KaiserTracerPowerSpectrumMultipoles`` / ``EFTLikeKaiserTracerPowerSpectrumMultipoles`` with a ``ShapeFitPowerSpectrumTemplate`` (direct
-theory), and over power-spectrum / correlation-function observables of the damped-BAO tracers (``DampedBAOWigglesTracer*Multipoles``, power-law
+``KaiserTracerPowerSpectrumMultipoles`` / ``EFTLikeKaiserTracerPowerSpectrumMultipoles`` (and their ``...CorrelationFunctionMultipoles`` forms) with a
+``ShapeFitPowerSpectrumTemplate`` (direct theory) or with an EMULATED ``pt`` (the reference's ``EmulatedCalculator``: Taylor / MLP engines), and over power-spectrum / correlation-function observables of the damped-BAO tracers (``DampedBAOWigglesTracer*Multipoles``, power-law
 broadband), including systematic templates, the 'cubic' transform and '.marg' / '.best' solved parameters ('.prec' parameters are folded into
 the reference object's precision when it initialises, so a likelihood carrying them is rejected).  Tested against live reference objects in
 tests/test_oracle_vs_reference.py (build container; the reference does not travel to the GPU box).
@@ -24,6 +24,32 @@ _THEORIES = {'KaiserTracerPowerSpectrumMultipoles': KaiserTracerPowerSpectrumMul
              'EFTLikeKaiserTracerPowerSpectrumMultipoles': EFTLikeKaiserTracerPowerSpectrumMultipoles,
              'KaiserTracerCorrelationFunctionMultipoles': KaiserTracerCorrelationFunctionMultipoles,
              'EFTLikeKaiserTracerCorrelationFunctionMultipoles': EFTLikeKaiserTracerCorrelationFunctionMultipoles}
+
+
+def _own_params(calculator):
+    """Parameters of a reference calculator and of everything it requires, under their pipeline names (namespaces applied).
+
+    NOT ``calculator.all_params``: on a sub-calculator of a likelihood that property builds a NEW pipeline for the sub-calculator (reference
+    base.py:949-960, :1302-1305), which re-initialises the calculators it shares with the likelihood; the likelihood then rebuilds its own pipeline
+    and every parameter update made on ``likelihood.all_params`` (``derived='.marg'``, priors, fixed flags) is lost -- extracting a plan must not
+    change the object it reads.  Each calculator's ``runtime_info.params`` (base.py:915-921) and ``runtime_info._requires`` (:962-972) are plain
+    reads once the pipeline is initialised.  Objects without ``runtime_info`` (mirror classes, test doubles) list their own ``all_params``."""
+    seen, out, stack = set(), [], [calculator]
+    while stack:
+        calc = stack.pop()
+        if id(calc) in seen: continue
+        seen.add(id(calc))
+        info = getattr(calc, 'runtime_info', None)
+        if info is None or not hasattr(info, 'params'):
+            out += list(calc.all_params)
+            continue
+        out += list(info.params)
+        requires = getattr(info, '_requires', None)
+        stack += list(requires if requires is not None else info.requires)
+    names, unique = set(), []
+    for p in out:
+        if p.name not in names: names.add(p.name); unique.append(p)
+    return unique
 
 
 def _prior(prior):
@@ -72,7 +98,8 @@ def spec_from_likelihood(likelihood, solved_default='.marg', all_params=None):
         nin = len(ellsin) * xin.size
         # the kernel slots of a theory are resolved by BASENAME: restrict names and defaults to the theory's OWN parameters (a SumLikelihood with
         # namespaced per-tracer parameters LRG.b1 / ELG.b1 must not drive one tracer's kernel with another tracer's values)
-        own = [p.name for p in th.all_params]
+        own_params = _own_params(th)
+        own = [p.name for p in own_params]
         basenames = {}
         for n in own:
             if n not in defaults: continue
@@ -83,11 +110,29 @@ def spec_from_likelihood(likelihood, solved_default='.marg', all_params=None):
 
         def own_varied(slots):
             return [n for n in varied if n in own and n.split('.')[-1] in slots]
-        if tname in _THEORIES and is_xi == tname.endswith('CorrelationFunctionMultipoles'):
+        if tname in _THEORIES and is_xi == tname.endswith('CorrelationFunctionMultipoles') and getattr(th.pt, 'emulator', None) is not None:
+            # EMULATED perturbation theory: ``theory.pt`` is the reference's EmulatedCalculator (emulators/__init__.py:394-417); its emulator's state
+            # (``Emulator.__getstate__``, :210-216 -- the dict the emulator files hold: engines{center, powers, derivatives | model_operations},
+            # fixed{k, ells}, defaults) is read into the mirror emulator, and the mirror tracer class supplies the theory spec and the bias-combine terms
+            from .emulators import Emulator, EmulatedCalculator
+            emu = th.pt.emulator
+            mirror_pt = EmulatedCalculator(Emulator(dict(emu.__getstate__())))
+            b1 = [p for p in own_params if p.basename == 'b1'][0]
+            if is_xi:
+                mirror = _THEORIES[tname](pt=mirror_pt, s=xin, ells=ellsin, interp_order=int(th.interp_order), tracer=b1.namespace or None)
+            else:
+                mirror = _THEORIES[tname](pt=mirror_pt, k=xin, ells=ellsin, shotnoise=1. / float(th.nd), tracer=b1.namespace or None)
+            if hasattr(th, 'kp'): mirror.kp = float(th.kp)
+            elif hasattr(getattr(th, 'power', None), 'kp'): mirror.kp = float(th.power.kp)
+            terms = list(mirror.terms())
+            theory = dict(mirror.theory_spec())
+            # emulator inputs that the likelihood does not vary sit at the likelihood's CURRENT values, not at the emulator's stored defaults
+            theory['defaults'] = {**dict(theory.get('defaults', {})), **{p_: basenames[p_.split('.')[-1]] for p_ in theory['params'] if p_.split('.')[-1] in basenames}}
+        elif tname in _THEORIES and is_xi == tname.endswith('CorrelationFunctionMultipoles'):
             pt, tpl = th.pt, th.pt.template
             if type(tpl).__name__ != 'ShapeFitPowerSpectrumTemplate':
                 raise NotImplementedError('template {} is not on the CUDA path through this adapter'.format(type(tpl).__name__))
-            b1 = [p for p in th.all_params if p.basename == 'b1'][0]
+            b1 = [p for p in own_params if p.basename == 'b1'][0]
             # bias-combine terms from the mirror class (full_shape.py:545-550, :628-634); only k, ells, nd and the parameter names are needed
             if is_xi:   # Hankel transforms of the Kaiser tracer P_ell on kin (full_shape.py:336-365, :553-574)
                 mirror = _THEORIES[tname](template=None, s=xin, ells=ellsin, interp_order=int(th.interp_order), tracer=b1.namespace or None)
@@ -107,7 +152,7 @@ def spec_from_likelihood(likelihood, solved_default='.marg', all_params=None):
             pt, tpl = th.pt, th.pt.template
             if str(getattr(th, 'broadband', 'power')) != 'power': raise NotImplementedError('only the power-law broadband is on the CUDA path')
             pivot = float(th.sp if is_xi else th.kp)
-            names = {p.basename: p.name for p in th.all_params}
+            names = {p.basename: p.name for p in own_params}
             terms = [dict(scale=1., factors=[], table='corr' if is_xi else 'power')]
             for ill, ell in enumerate(ellsin):
                 for name, power in th.broadband_orders.get(ell, {}).items():
@@ -123,7 +168,7 @@ def spec_from_likelihood(likelihood, solved_default='.marg', all_params=None):
             raise NotImplementedError('theory {} is not on the CUDA path through this adapter'.format(tname))
         st = getattr(w, 'systematic_templates', None)
         if st is not None:   # window.py:470-473 / :732-733: flat += sum_i syst_i template_i
-            names = {p.basename: p.name for p in st.all_params}
+            names = {p.basename: p.name for p in _own_params(st)}
             for name, template in st.templates.items():
                 terms.append(dict(scale=1., factors=[(names.get(name, name), 1)], table=None, outvec=np.array(template, dtype='f8')))
         # window constants -> one matrix + offset

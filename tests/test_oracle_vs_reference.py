@@ -153,6 +153,82 @@ def test_spec_from_reference_eftlike_kaiser_correlation_likelihood(interp_order)
     Lowered(spec)
 
 
+def test_spec_extraction_leaves_the_reference_likelihood_untouched():
+    """Extracting a plan must not change the object it reads: ``sub_calculator.all_params`` would build a new pipeline for the sub-calculator
+    (reference base.py:949-960) and the likelihood would lose every update made on ``likelihood.all_params`` ('.marg' tags, priors).  The adapter
+    reads ``runtime_info.params`` instead: same '.marg' parameters before and after, a second extraction gives the same spec, and the reference
+    likelihood still evaluates to the same value."""
+    import desilike_b200 as dl
+    spec0 = configs.config_kaiser_window(seed=13, eftlike=True, solved=True)
+    like = ref_harness.reference_kaiser_likelihood(spec0, eftlike=True, solved_mode='.marg')
+    ref_harness.install_jacfwd_stub()
+    before = like(b1=1.7)
+    tags = {p.name: p.derived for p in like.all_params}
+    assert sum(tag == '.marg' for tag in tags.values()) == 7
+    first = dl.spec_from_likelihood(like)
+    assert {p.name: p.derived for p in like.all_params} == tags
+    second = dl.spec_from_likelihood(like)
+    assert first['params'] == second['params'] and [s_['name'] for s_ in first['solved']] == [s_['name'] for s_ in second['solved']] and len(first['solved']) == 7
+    assert like(b1=1.7) == before
+
+
+def test_spec_from_reference_likelihood_with_emulated_pt():
+    """spec_from_likelihood on a reference likelihood whose ``theory.pt`` is an EmulatedCalculator (reference emulators/__init__.py:394-417): the
+    adapter reads ``pt.emulator.__getstate__()`` (the emulator-file dict) into the mirror emulator.  cosmoprimo's emulator classes are absent here,
+    so the live reference likelihood (window, data, precision, EFT-like terms with '.marg' parameters: all real reference objects) gets a
+    duck-typed ``pt`` carrying the state of a Taylor emulator of the oracle's Kaiser tables.  The extracted spec is a Taylor spec with the
+    reference's parameters / solved terms / window; at the expansion point it evaluates to the direct extraction's values, nearby within the
+    truncation error, and it lowers (NumPy mirror of the kernels == oracle)."""
+    import lowered_numpy
+    import desilike_b200 as dl
+    from oracle import core
+    from desilike_b200.lowering import Lowered
+    spec0 = configs.config_kaiser_window(seed=13, eftlike=True, solved=True)
+    like = ref_harness.reference_kaiser_likelihood(spec0, eftlike=True, solved_mode='.marg')
+    ref_harness.install_jacfwd_stub()
+    like(b1=1.7)
+    direct = dl.spec_from_likelihood(like)
+    th = direct['observables'][0]['theory']
+    pnames, center, delta = ['qpar', 'qper', 'dm', 'df'], np.array([1., 1., 0., 1.]), np.array([0.01, 0.01, 0.01, 0.02])
+    ptheory = dict(th, params=pnames)
+
+    def func(P):
+        tabs = pipeline.theory_tables(ptheory, P, pnames)
+        return np.concatenate([tabs[n] for n in ('pk_dd', 'pk_dt', 'pk_tt')], axis=-1)
+    powers, derivs = core.taylor_fit_polynomial(func, center, 4, 2, delta)
+    nell, nk = len(th['ells']), len(th['k'])
+    tables = {n: derivs[:, i * nell * nk:(i + 1) * nell * nk].reshape(-1, nell, nk) for i, n in enumerate(('pk_dd', 'pk_dt', 'pk_tt'))}
+    state = dl.Emulator.from_taylor(pnames, center, powers, tables, fixed=dict(k=th['k'], ells=tuple(th['ells']), z=1.)).state
+
+    class FakeEmulator(object):
+        def __getstate__(self): return state
+
+    class FakePT(object):
+        emulator = FakeEmulator()
+
+    def proxy(obj, **override):   # (assigning to a reference calculator re-initialises its pipeline: read-only proxies instead)
+        p_ = type(type(obj).__name__, (object,), {'__getattr__': lambda self, name: getattr(obj, name)})()
+        p_.__dict__.update(override)
+        return p_
+
+    obs = like.observables[0]
+    spec = dl.spec_from_likelihood(proxy(like, observables=[proxy(obs, wmatrix=proxy(obs.wmatrix, theory=proxy(obs.wmatrix.theory, pt=FakePT())))]))
+    assert spec['observables'][0]['theory']['kind'] == 'taylor'
+    assert spec['params'] == direct['params'] and [s_['name'] for s_ in spec['solved']] == [s_['name'] for s_ in direct['solved']]
+    names = spec['params']
+    x0 = np.array([dict(zip(pnames, center)).get(n, 1.7 if n == 'b1' else 0.) for n in names])[None, :]
+    a, b = pipeline.evaluate(spec, x0), pipeline.evaluate(direct, x0)
+    assert np.allclose(a['logposterior'], b['logposterior'], rtol=1e-9, atol=1e-7) and np.allclose(a['x_solved'], b['x_solved'], rtol=1e-7, atol=1e-7)
+    rng = np.random.default_rng(2)
+    scale = np.array([0.3 * dict(zip(pnames, delta)).get(n, 0.3) for n in names])
+    X = x0 + rng.uniform(-1., 1., (6, len(names))) * scale
+    a, b = pipeline.evaluate(spec, X, return_theory=True), pipeline.evaluate(direct, X, return_theory=True)
+    assert np.max(np.abs(a['flattheory'] - b['flattheory'])) < 1e-4 * np.max(np.abs(b['flattheory']))
+    got = lowered_numpy.evaluate(Lowered(spec), X)
+    assert np.allclose(got['logposterior'], a['logposterior'], rtol=1e-9, atol=1e-7)
+    assert np.allclose(got['x_solved'], a['x_solved'], rtol=1e-7, atol=1e-8 * np.max(np.abs(a['x_solved'])))
+
+
 def test_vmap_accepts_reference_likelihood_objects():
     """desilike_b200.vmap(reference_likelihood): the adapter extracts the spec and maps parameter dicts to plan columns (no GPU here: the plan
     itself is not built; the point matrix and the spec are checked)."""
