@@ -151,8 +151,6 @@ def spec_from_likelihood(likelihood, solved_default='.marg', all_params=None):
             # damped BAO (bao.py:117-151) + power-law broadband in x / pivot (bao.py:467-476, :527-534; :849-853, :905)
             pt = th.pt
             emulated = getattr(pt, 'emulator', None) is not None
-            if emulated and is_xi:
-                raise NotImplementedError('emulated pt of the damped-BAO correlation function (the P(kin) engine behind get_corr) is not on the CUDA path through this adapter')
             tpl = None if emulated else pt.template
             if str(getattr(th, 'broadband', 'power')) != 'power': raise NotImplementedError('only the power-law broadband is on the CUDA path')
             pivot = float(th.sp if is_xi else th.kp)
@@ -162,21 +160,26 @@ def spec_from_likelihood(likelihood, solved_default='.marg', all_params=None):
                 for name, power in th.broadband_orders.get(ell, {}).items():
                     colvec = np.zeros((len(ellsin), xin.size)); colvec[ill] = (xin / pivot)**power
                     terms.append(dict(scale=1., factors=[(names.get(name, name), 1)], table=None, colvec=colvec.ravel()))
-            if emulated:   # theory.pt = the reference's EmulatedCalculator of the damped-BAO P_ell(k) ('power' engine): state -> mirror emulator
+            if emulated:   # theory.pt = the reference's EmulatedCalculator of the damped-BAO P_ell ('power' engine on k, or on kin behind get_corr): state -> mirror emulator
                 from .emulators import Emulator, EmulatedCalculator
                 mirror_pt = EmulatedCalculator(Emulator(dict(pt.emulator.__getstate__())))
-                if len(mirror_pt.k) != xin.size or not np.allclose(mirror_pt.k, xin) or tuple(mirror_pt.ells) != ellsin:
-                    raise ValueError('the emulator was built on a different (k, ells) grid than the one requested by the window / observable')
-                theory = dict(mirror_pt.theory_spec())
-                if 'power' not in theory['tables']: raise ValueError("the emulator has no 'power' engine (engines: {})".format(sorted(theory['tables'])))
+                if is_xi:   # the 'power' engine lives on kin (reference bao.py:820-833): the mirror class folds the P -> xi operator into its output map
+                    from .theories import DampedBAOWigglesTracerCorrelationFunctionMultipoles
+                    theory = dict(DampedBAOWigglesTracerCorrelationFunctionMultipoles(pt=mirror_pt, s=xin, ells=ellsin).theory_spec())
+                else:
+                    if len(mirror_pt.k) != xin.size or not np.allclose(mirror_pt.k, xin) or tuple(mirror_pt.ells) != ellsin:
+                        raise ValueError('the emulator was built on a different (k, ells) grid than the one requested by the window / observable')
+                    theory = dict(mirror_pt.theory_spec())
+                    if 'power' not in theory['tables']: raise ValueError("the emulator has no 'power' engine (engines: {})".format(sorted(theory['tables'])))
                 theory['defaults'] = {**dict(theory.get('defaults', {})), **{p_: basenames[p_.split('.')[-1]] for p_ in theory['params'] if p_.split('.')[-1] in basenames}}
             else:
                 theory = dict(kind='bao_xi' if is_xi else 'bao_pk', ells=ellsin, nmu=len(pt.mu), mode=str(pt.mode), smoothing_radius=float(pt.smoothing_radius),
                           template=dict(kind='bao', k=np.array(tpl.k, dtype='f8'), pk_dd_fid=np.array(tpl.pk_dd_fid, dtype='f8'), pknow_dd_fid=np.array(tpl.pknow_dd_fid, dtype='f8'),
                                         f_fid=float(tpl.f_fid), apmode=str(tpl.apeffect.mode), eta=float(getattr(tpl, 'eta', 1. / 3.))),
                           params=own_varied(('qpar', 'qper', 'qiso', 'qap', 'df', 'b1', 'dbeta', 'sigmas', 'sigmapar', 'sigmaper')), defaults=basenames)
-            if is_xi: theory.update(s=xin, kin=np.array(th.kin, dtype='f8') if hasattr(th, 'kin') else None, interp_order=int(getattr(th, 'interp_order', 1)))
-            elif not emulated: theory.update(k=xin)
+            if emulated: pass
+            elif is_xi: theory.update(s=xin, kin=np.array(th.kin, dtype='f8') if hasattr(th, 'kin') else None, interp_order=int(getattr(th, 'interp_order', 1)))
+            else: theory.update(k=xin)
         else:
             raise NotImplementedError('theory {} is not on the CUDA path through this adapter'.format(tname))
         st = getattr(w, 'systematic_templates', None)

@@ -145,6 +145,35 @@ class KaiserTracerPowerSpectrumMultipoles(BaseTracerPowerSpectrumMultipoles):
                 dict(scale=1., factors=[], table='pk_tt'), dict(scale=1. / self.nd, factors=[(sn0, 1)], table=None, colvec=e0)]
 
 
+def _xi_fold(kin, ells, s, interp_order=1):
+    """[nell * nkin, nell * ns]: the linear P_ell(kin) -> xi_ell(s) operator of get_corr (reference base.py:127-136), block diagonal in ell."""
+    from .fftlog import fftlog_operator
+    kin, s = np.asarray(kin, dtype='f8'), np.asarray(s, dtype='f8')
+    T = fftlog_operator(kin, ells, s, interp_order=interp_order)
+    fold = np.zeros((len(ells) * kin.size, len(ells) * s.size))
+    for ill in range(len(ells)): fold[ill * kin.size:(ill + 1) * kin.size, ill * s.size:(ill + 1) * s.size] = T[ill]
+    return fold
+
+
+def _fold_emulated_tables(spec, fold, weighted=None, keep=None):
+    """Emulated tables on (kin, ells) -> the same tables behind the P -> xi operator ``fold``, folded into the emulator's output maps (Taylor: coefficient
+    matrices; MLP: linear post-map).  ``weighted``: {new name: (source table, weights on P(kin))}; ``keep``: {new name: source table} (default: all)."""
+    tables, weighted = {}, weighted or {}
+    keep = {name: name for name in spec['tables']} if keep is None else keep
+    if spec['kind'] == 'taylor':
+        for name, src in keep.items(): tables[name] = np.asarray(spec['tables'][src], dtype='f8') @ fold
+        for name, (src, w) in weighted.items(): tables[name] = (np.asarray(spec['tables'][src], dtype='f8') * w) @ fold
+    else:
+        def post(sl, w=None):   # MLP tables: output indices, optionally with a linear post-map [len(indices), nell * nkin]
+            sl, m = sl if isinstance(sl, tuple) else (sl, None)
+            if m is None: return (sl, fold if w is None else w[:, None] * fold)
+            m = np.asarray(m, dtype='f8')
+            return (sl, (m if w is None else m * w) @ fold)
+        for name, src in keep.items(): tables[name] = post(spec['tables'][src])
+        for name, (src, w) in weighted.items(): tables[name] = post(spec['tables'][src], w)
+    return dict(spec, tables=tables)
+
+
 class KaiserTracerCorrelationFunctionMultipoles(KaiserTracerPowerSpectrumMultipoles):
     """xi_ell(s) = Hankel transforms of the Kaiser tracer P_ell(k) = b1^2 pk_dd + 2 b1 pk_dt + pk_tt evaluated on ``kin`` (reference
     full_shape.py:336-365, :553-574; get_corr base.py:46-136: resampling onto the FFTLog grid -- ``interp_order`` 1 linear / 3 cubic in log10 k --,
@@ -161,15 +190,6 @@ class KaiserTracerCorrelationFunctionMultipoles(KaiserTracerPowerSpectrumMultipo
         self.s = np.linspace(20., 200, 101) if s is None else np.asarray(s, dtype='f8')
         self.params = ParameterCollection([Parameter('b1', prior=dict(limits=[0., 4.]), ref=dict(limits=[1., 2.]), namespace=self.tracer)])
 
-    def _fold(self):
-        """[nell * nkin, nell * ns]: the linear P_ell(kin) -> xi_ell(s) operator of get_corr (reference base.py:127-136), block diagonal in ell."""
-        from .fftlog import fftlog_operator
-        T = fftlog_operator(self.kin, self.ells, self.s, interp_order=self.interp_order)
-        nk, ns = self.kin.size, self.s.size
-        fold = np.zeros((len(self.ells) * nk, len(self.ells) * ns))
-        for ill in range(len(self.ells)): fold[ill * nk:(ill + 1) * nk, ill * ns:(ill + 1) * ns] = T[ill]
-        return fold
-
     def _weighted_tables(self):
         """Tables entering with weights on P(kin): {new table name: (source table, weights [nell * nkin])} (counter terms of the EFT-like class)."""
         return {}
@@ -184,22 +204,8 @@ class KaiserTracerCorrelationFunctionMultipoles(KaiserTracerPowerSpectrumMultipo
     def theory_spec(self):
         if self.pt is None:
             return dict(super().theory_spec(), s=self.s, kin=self.kin, interp_order=self.interp_order)
-        # emulated tables on (kin, ells): fold the P -> xi operator into the emulator's output maps (Taylor: coefficient matrices; MLP: linear post-map)
-        spec = self.pt.theory_spec(self)
-        fold, tables = self._fold(), {}
-        weighted = self._weighted_tables()
-        if spec['kind'] == 'taylor':
-            for name, deriv in spec['tables'].items(): tables[name] = np.asarray(deriv, dtype='f8') @ fold
-            for name, (src, w) in weighted.items(): tables[name] = (np.asarray(spec['tables'][src], dtype='f8') * w) @ fold
-        else:
-            def post(sl, w=None):   # MLP tables: output indices, optionally with a linear post-map [len(indices), nell * nkin]
-                sl, m = sl if isinstance(sl, tuple) else (sl, None)
-                if m is None: return (sl, fold if w is None else w[:, None] * fold)
-                m = np.asarray(m, dtype='f8')
-                return (sl, (m if w is None else m * w) @ fold)
-            for name, sl in spec['tables'].items(): tables[name] = post(sl)
-            for name, (src, w) in weighted.items(): tables[name] = post(spec['tables'][src], w)
-        return dict(spec, tables=tables)
+        # emulated tables on (kin, ells): fold the P -> xi operator (and the weights of weighted tables) into the emulator's output maps
+        return _fold_emulated_tables(self.pt.theory_spec(self), _xi_fold(self.kin, self.ells, self.s, self.interp_order), weighted=self._weighted_tables())
 
     def terms(self):
         b1 = self._ns('b1')
@@ -502,7 +508,7 @@ class DampedBAOWigglesTracerCorrelationFunctionMultipoles(_BaseBAOTracer):
         # fftlog: 'fold' = the (linear) P_ell(kin) -> xi_ell(s) operator is folded into the plan's term matrices; 'kernel' = explicit FFTLog kernel
         self.fftlog = str(fftlog)
         self.s = np.linspace(20., 200., 101) if s is None else np.asarray(s, dtype='f8')
-        if self.pt is not None and s is None: self.s = np.asarray(self.pt.k, dtype='f8')
+        if self.pt is not None and s is None and self.pt.s is not None: self.s = np.asarray(self.pt.s, dtype='f8')   # ('corr' engine: emulated on s)
         self.sp = 2. * np.pi / 0.02 if sp is None else float(sp)
         for ell in self.ells:
             for power in range(-2, 3):
@@ -516,7 +522,13 @@ class DampedBAOWigglesTracerCorrelationFunctionMultipoles(_BaseBAOTracer):
         return len(self.ells) * len(self.s)
 
     def theory_spec(self):
-        if self.pt is not None: return self._emulated_spec('corr', self.s)
+        if self.pt is not None:
+            spec = self.pt.theory_spec()
+            if 'corr' not in spec['tables'] and 'power' in spec['tables']:
+                # the reference's structure: the emulated pt is the P_ell(kin) calculator behind get_corr (bao.py:820-833, base.py:61-67, :127-136)
+                if tuple(self.pt.ells) != tuple(self.ells): raise ValueError('the emulator was built on different multipoles than requested')
+                return _fold_emulated_tables(spec, _xi_fold(self.pt.k, self.ells, self.s), keep={'corr': 'power'})
+            return self._emulated_spec('corr', self.s)
         return dict(self._theory_common(), kind='bao_xi', s=self.s, fftlog=self.fftlog)
 
     def terms(self):

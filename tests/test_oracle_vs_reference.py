@@ -229,33 +229,45 @@ def test_spec_from_reference_likelihood_with_emulated_pt():
     assert np.allclose(got['x_solved'], a['x_solved'], rtol=1e-7, atol=1e-8 * np.max(np.abs(a['x_solved'])))
 
 
-def test_spec_from_reference_bao_likelihood_with_emulated_pt():
-    """Same for the damped-BAO P_ell(k) likelihood: ``theory.pt`` = an EmulatedCalculator with a 'power' engine (duck-typed, carrying the state of a
-    Taylor emulator of the oracle's damped-BAO multipoles); real reference window / data / precision / marginalised broadband terms."""
+@pytest.mark.parametrize('which', ['power', 'corr'])
+def test_spec_from_reference_bao_likelihood_with_emulated_pt(which):
+    """Same for the damped-BAO likelihoods: ``theory.pt`` = an EmulatedCalculator with a 'power' engine -- on the observable's k for P_ell(k), on kin
+    behind get_corr for xi_ell(s) (reference bao.py:820-833) -- duck-typed, carrying the state of a Taylor emulator of the oracle's damped-BAO
+    multipoles; real reference window / data / precision / marginalised broadband terms."""
     import lowered_numpy
     import desilike_b200 as dl
     from oracle import core
     from desilike_b200.lowering import Lowered
     ref_harness.setup()
-    from desilike.theories.galaxy_clustering import BAOPowerSpectrumTemplate, DampedBAOWigglesTracerPowerSpectrumMultipoles
-    from desilike.observables.galaxy_clustering import TracerPowerSpectrumMultipolesObservable
+    from desilike.theories.galaxy_clustering import (BAOPowerSpectrumTemplate, DampedBAOWigglesTracerPowerSpectrumMultipoles,
+                                                     DampedBAOWigglesTracerCorrelationFunctionMultipoles)
+    from desilike.observables.galaxy_clustering import TracerPowerSpectrumMultipolesObservable, TracerCorrelationFunctionMultipolesObservable
     from desilike.likelihoods import ObservablesGaussianLikelihood
-    x = np.arange(0.02, 0.3, 0.005)
-    theory = DampedBAOWigglesTracerPowerSpectrumMultipoles(template=BAOPowerSpectrumTemplate(z=1.), ells=(0, 2))
-    obs = TracerPowerSpectrumMultipolesObservable(data={'b1': 2., 'sigmas': 3.}, k=[x, x], ells=(0, 2), theory=theory)
-    like = ObservablesGaussianLikelihood(observables=[obs], covariance=np.diag(np.full(2 * x.size, 1e4)))
+    if which == 'power':
+        x = np.arange(0.02, 0.3, 0.005)
+        theory = DampedBAOWigglesTracerPowerSpectrumMultipoles(template=BAOPowerSpectrumTemplate(z=1.), ells=(0, 2))
+        obs = TracerPowerSpectrumMultipolesObservable(data={'b1': 2., 'sigmas': 3.}, k=[x, x], ells=(0, 2), theory=theory)
+        cov, keep = np.diag(np.full(2 * x.size, 1e4)), ('_-1', '_0', '_1')
+    else:
+        x = np.arange(20., 152., 4.)
+        theory = DampedBAOWigglesTracerCorrelationFunctionMultipoles(template=BAOPowerSpectrumTemplate(z=1.), ells=(0, 2))
+        obs = TracerCorrelationFunctionMultipolesObservable(data={'b1': 2., 'sigmas': 3.}, s=[x, x], ells=(0, 2), theory=theory)
+        cov, keep = np.diag(np.full(2 * x.size, 1e-8)), ('_0', '_2')
+    like = ObservablesGaussianLikelihood(observables=[obs], covariance=cov)
     for p in like.all_params:
         if p.basename.startswith('al'):
-            if p.basename.endswith(('_-1', '_0', '_1')): p.update(fixed=False, derived='.marg', prior=dict(dist='norm', loc=0., scale=1e4))
+            if p.basename.endswith(keep): p.update(fixed=False, derived='.marg', prior=dict(dist='norm', loc=0., scale=1e4))
             else: p.update(fixed=True)
     ref_harness.install_jacfwd_stub()
     like(b1=2.)
     direct = dl.spec_from_likelihood(like)
     th = direct['observables'][0]['theory']
     pnames, center, delta = ['qpar', 'qper', 'b1', 'dbeta', 'sigmas'], np.array([1., 1., 2., 1., 3.]), np.array([0.01, 0.01, 0.05, 0.02, 0.2])
-    ptheory = dict(th, params=pnames)
+    # the emulated calculator: P_ell on the observable's k, or on kin (the P(k) theory behind get_corr)
+    kem = x if which == 'power' else np.asarray(th['kin'], dtype='f8')
+    ptheory = dict({key: value for key, value in th.items() if key not in ('s', 'kin', 'interp_order', 'fftlog')}, kind='bao_pk', k=kem, params=pnames)
     powers, derivs = core.taylor_fit_polynomial(lambda P: pipeline.theory_tables(ptheory, P, pnames)['power'], center, 5, 2, delta)
-    state = dl.Emulator.from_taylor(pnames, center, powers, {'power': derivs.reshape(-1, 2, x.size)}, fixed=dict(k=x, ells=(0, 2), z=1.),
+    state = dl.Emulator.from_taylor(pnames, center, powers, {'power': derivs.reshape(-1, 2, kem.size)}, fixed=dict(k=kem, ells=(0, 2), z=1.),
                                     calculator_class=('desilike.theories.galaxy_clustering.bao', 'DampedBAOWigglesPowerSpectrumMultipoles')).state
 
     class FakeEmulator(object):
@@ -272,7 +284,7 @@ def test_spec_from_reference_bao_likelihood_with_emulated_pt():
     o = like.observables[0]
     spec = dl.spec_from_likelihood(proxy(like, observables=[proxy(o, wmatrix=proxy(o.wmatrix, theory=proxy(o.wmatrix.theory, pt=FakePT())))]))
     assert spec['observables'][0]['theory']['kind'] == 'taylor' and spec['params'] == direct['params'] == pnames
-    assert [s_['name'] for s_ in spec['solved']] == [s_['name'] for s_ in direct['solved']] and len(spec['solved']) == 6
+    assert [s_['name'] for s_ in spec['solved']] == [s_['name'] for s_ in direct['solved']] and len(spec['solved']) == 2 * len(keep)
     a, b = pipeline.evaluate(spec, center[None, :]), pipeline.evaluate(direct, center[None, :])
     assert np.allclose(a['logposterior'], b['logposterior'], rtol=1e-9, atol=1e-7)
     rng = np.random.default_rng(4)
