@@ -1335,6 +1335,15 @@ int dlb_eval_batch(dlb_plan* plan, const double* params, int64_t N, double* logp
 static int choose_sub_batches(const dlb_plan* plan, long long n, double bytes_in, double bytes_out, long long* lens) {
   const int forced = getenv("DLB_NSUB") ? atoi(getenv("DLB_NSUB")) : 0;   // (read per call: tests switch it)
   static const double T_SUB = getenv("DLB_SUB_COST_US") ? atof(getenv("DLB_SUB_COST_US")) * 1e-6 : 40e-6;
+  // The timeline model rests on the persistent contraction being the step: validated on the plans with a shared-memory-resident A tile (C2, C4, C5,
+  // C5 + marginalisation).  Plans led by other kernels (direct-theory generators, per-layer MLP launches, the int8 path, two-stage plans) keep the
+  // earlier rule: from 131 072 points up, up to 4 equal sub-batches of >= 65 536 points.
+  if (!forced && !(plan->mlp_slices == 0 && !plan->two_stage && plan->mlp_launches.empty() && (plan->qform || plan->resident))) {
+    const int c = n >= 131072 ? (int)std::min<long long>(4, n / 65536) : 1;
+    const long long len = ((n + c - 1) / c + 63) / 64 * 64;
+    for (int i = 0; i < c; ++i) lens[i] = i + 1 < c ? len : n - len * (c - 1);
+    return c;
+  }
   const Launch& L = plan->two_stage ? plan->wlaunch : (plan->qform ? plan->qlaunch : plan->launch);
   const long long Q = (std::max<long long>(64, (long long)plan->nsm * L.var.CPS * variant_bm(L.var)) + 63) / 64 * 64;
   const double t_pt = std::max(dlb_plan_executed_flops(plan), 0.) / 20e12, BW = 50e9;
