@@ -196,6 +196,23 @@ def test_pipelined_host_path_large_batch(gpu_required, monkeypatch):
     plan.close()
 
 
+def test_pipelined_host_path_non_resident_plan(gpu_required):
+    """Plans led by a direct-theory generator (no resident A tile) keep the equal-split pipeline (from 131 072 points up, <= 4 sub-batches,
+    plan.cu choose_sub_batches): host buffers == device buffers, ragged last sub-batch."""
+    import torch
+    import desilike_b200
+    spec = configs.config_kaiser_window(nkin=40, nbins=8, eftlike=True, solved=True)
+    plan = desilike_b200.Plan(spec)
+    assert not plan.kernels['resident_taylor'] and plan.ns == 7
+    X = configs.sample_points(spec, 2 * 65536 + 1234, seed=3)
+    dev = plan.eval(torch.as_tensor(X, device='cuda'))
+    torch.cuda.synchronize()
+    host = plan.eval(X)
+    for key in ['logposterior', 'loglikelihood', 'logprior', 'x_solved', 'status']:
+        assert np.array_equal(host[key], dev[key].cpu().numpy()), key
+    plan.close()
+
+
 def test_cubic_observable_transform_two_stage(gpu_required):
     """Observable transform 'cubic' (reference observables/galaxy_clustering/power_spectrum.py:400-404) on Taylor-emulated tracers: the plan runs
     theory -> transform -> whitening as two contraction launches; one tracer transformed, one not, block-diagonal and joint dense precision."""
