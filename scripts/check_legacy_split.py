@@ -4,9 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import desilike_b200
 from desilike_b200 import workloads as configs
-spec = configs.config_kaiser_window(nkin=40, nbins=8, eftlike=True, solved=True)
+spec = configs.config_kaiser_window(nkin=200, nbins=8, eftlike=True, solved=True)   # 1202 feature columns: too wide for a resident A tile
 plan = desilike_b200.Plan(spec)
-assert not plan.kernels['resident_taylor']
 X = configs.sample_points(spec, 2 * 65536 + 1234, seed=3)
 dev = plan.eval(torch.as_tensor(X, device='cuda')); torch.cuda.synchronize()
 host = plan.eval(X)
